@@ -1,0 +1,110 @@
+/* msgpu.h - C-ABI of the B200 batch decompressor for the three CAB-folder codecs
+ * (MSZIP / Quantum / LZX).
+ *
+ * This is the ONE interface the project adds on top of the reference's own entry
+ * points ("New batch surface").  The reference library decodes one
+ * stream at a time through
+ *     mszipd_init / mszipd_decompress / mszipd_free   (libmspack/mspack/mszip.h:85-120)
+ *     qtmd_init   / qtmd_decompress   / qtmd_free     (libmspack/mspack/qtm.h:92-122)
+ *     lzxd_init   / lzxd_decompress   / lzxd_free     (libmspack/mspack/lzx.h:146-214)
+ * A GPU needs thousands of independent streams ("units") in flight, so the batch
+ * call below takes an array of unit descriptors.  One unit == one fresh codec state:
+ * a CAB folder (cabd.c:1142-1177 creates a fresh decoder per folder) or a CHM LZX
+ * reset interval (chmd.c:1146-1186 starts a fresh lzxd_stream at an interval).
+ * The ABI-compatible streaming entry points in mspack_dropin.h are implemented on top of
+ * this call with n == 1.
+ *
+ * Plain C, plain pointers and sizes: no torch / C++ types cross this boundary.
+ */
+#ifndef MSGPU_H
+#define MSGPU_H 1
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* codec ids == the CAB folder compression-type ids (cab.h:50-52 cffoldCOMPTYPE_*) */
+#define MSGPU_CODEC_MSZIP   1
+#define MSGPU_CODEC_QUANTUM 2
+#define MSGPU_CODEC_LZX     3
+
+/* per-unit status == the reference's error codes (mspack.h:485-507) */
+#define MSGPU_ERR_OK         0
+#define MSGPU_ERR_ARGS       1
+#define MSGPU_ERR_READ       3   /* ran past the end of the unit's input (readbits.h:196-208) */
+#define MSGPU_ERR_WRITE      4
+#define MSGPU_ERR_NOMEMORY   6
+#define MSGPU_ERR_DATAFORMAT 8
+#define MSGPU_ERR_DECRUNCH   11
+
+/* unit flags */
+#define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:422-433 */
+
+/* One independent compressed unit.  32 bytes, no padding. */
+typedef struct msgpu_unit {
+    uint8_t  codec;           /* MSGPU_CODEC_*                                        */
+    uint8_t  window_bits;     /* LZX 15..21 (lzxd.c:294), Quantum 10..21 (qtmd.c:199) */
+    uint16_t reset_interval;  /* LZX: frames between resets, 0 = never (lzxd.c:423)   */
+    uint32_t flags;           /* MSGPU_FLAG_*                                         */
+    uint64_t in_off;          /* byte offset of the unit's compressed bytes           */
+    uint32_t in_len;          /* compressed byte count                                */
+    uint32_t out_len;         /* bytes to produce == X_decompress(state, out_len)     */
+    uint64_t out_off;         /* byte offset of the unit's output; multiple of 16     */
+} msgpu_unit;
+
+typedef struct msgpu_ctx msgpu_ctx;
+
+/* Create / destroy a decoder context on CUDA device `device` (scratch pools, streams).
+ * Returns NULL on failure (no CUDA device, out of memory): there is no CPU fallback. */
+msgpu_ctx *msgpu_create(int device);
+void       msgpu_destroy(msgpu_ctx *ctx);
+
+/* Human-readable text for the last failure on this context ("" if none). */
+const char *msgpu_last_error(const msgpu_ctx *ctx);
+
+/* Decode n units whose compressed bytes are ALREADY RESIDENT in device memory.
+ *   units     host array of n descriptors (copied to the device by the call)
+ *   d_in      device pointer, base for units[i].in_off
+ *   d_out     device pointer, base for units[i].out_off (16-byte aligned)
+ *   d_status  device pointer to n int32 (MSGPU_ERR_* per unit), may be NULL
+ *   stream    a cudaStream_t passed as void* (NULL = the context's own stream)
+ * Asynchronous with respect to the host when `stream` is given; returns 0 when the
+ * work was enqueued, nonzero MSGPU_ERR_* on argument / launch failure. */
+int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
+                              const void *d_in, size_t in_bytes,
+                              void *d_out, size_t out_bytes,
+                              int32_t *d_status, void *stream);
+
+/* Same, but with the unit table already in device memory (no host copy at all). */
+int msgpu_decode_batch_device_units(msgpu_ctx *ctx, const msgpu_unit *d_units, size_t n,
+                                    const void *d_in, size_t in_bytes,
+                                    void *d_out, size_t out_bytes,
+                                    int32_t *d_status, void *stream);
+
+/* End-to-end call with HOST buffers: copies units + input to the device, decodes,
+ * copies output and status back, synchronises.  `status` may be NULL.
+ * Returns 0 if the batch ran (per-unit results are in status[]), nonzero on failure. */
+int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
+                            const void *h_in, size_t in_bytes,
+                            void *h_out, size_t out_bytes, int32_t *status);
+
+/* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
+uint64_t msgpu_launch_count(const msgpu_ctx *ctx);
+
+/* Bytes of device scratch the context currently holds. */
+size_t msgpu_scratch_bytes(const msgpu_ctx *ctx);
+
+/* Milliseconds spent in the decode kernels of the most recent batch, measured with CUDA
+ * events on the launching stream (valid after the stream is synchronised; < 0 if none). */
+float msgpu_last_kernel_ms(msgpu_ctx *ctx);
+
+/* Library version string. */
+const char *msgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGPU_H */

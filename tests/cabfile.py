@@ -1,0 +1,63 @@
+"""Minimal single-cabinet .cab reader used by the tests to cut codec units out of the
+reference's fixture cabinets.
+
+Layout facts follow libmspack/mspack/cab.h:16-45 (CFHEADER 0x24 bytes, CFFOLDER 8 bytes,
+CFDATA 8 bytes, optional reserved areas) and the framing cabd.c applies before the codec sees
+the bytes: payloads are concatenated per folder (cabd.c:1294-1344) and Quantum gets a 0xFF
+trailer after every block (cabd.c:1330-1332).  Multi-cabinet folders are not handled here.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import List
+
+
+@dataclass
+class CabFolder:
+    comp_type: int            # raw typeCompress (method | level << 8)
+    method: int               # 0 none, 1 MSZIP, 2 Quantum, 3 LZX
+    window_bits: int          # (typeCompress >> 8) & 0x1f for Quantum / LZX
+    blocks: List[bytes] = field(default_factory=list)      # CFDATA payloads
+    usizes: List[int] = field(default_factory=list)        # uncompressed size per block
+
+    @property
+    def out_len(self) -> int:
+        return sum(self.usizes)
+
+    def unit_bytes(self) -> bytes:
+        """Bytes the codec's `read` callback delivers for this folder."""
+        if self.method == 2:
+            return b"".join(b + b"\xff" for b in self.blocks)
+        return b"".join(self.blocks)
+
+
+def parse_cab(data: bytes) -> List[CabFolder]:
+    if data[:4] != b"MSCF":
+        raise ValueError("not a cabinet")
+    (_, _, _, _, files_off, _, _, _, nfolders, nfiles, flags, _, _) = struct.unpack_from("<4sIIIIIBBHHHHH", data, 0)
+    pos = 0x24
+    hdr_res = fol_res = dat_res = 0
+    if flags & 4:
+        hdr_res, fol_res, dat_res = struct.unpack_from("<HBB", data, pos)
+        pos += 4 + hdr_res
+    for bit in (1, 2):                       # prev / next cabinet name + disk label
+        if flags & bit:
+            for _ in range(2):
+                pos = data.index(b"\0", pos) + 1
+    folders = []
+    for _ in range(nfolders):
+        off, nblocks, ctype = struct.unpack_from("<IHH", data, pos)
+        pos += 8 + fol_res
+        f = CabFolder(ctype, ctype & 0x0F, (ctype >> 8) & 0x1F)
+        p = off
+        for _b in range(nblocks):
+            if p + 8 > len(data):
+                break
+            _csum, csize, usize = struct.unpack_from("<IHH", data, p)
+            p += 8 + dat_res
+            f.blocks.append(data[p:p + csize])
+            f.usizes.append(usize)
+            p += csize
+        folders.append(f)
+    return folders
