@@ -1,0 +1,19 @@
+"""Unit descriptor shared by the host API and the generators.
+
+Mirrors `msgpu_unit` in include/msgpu.h (32 bytes, little-endian, no padding).  Codec ids are the
+CAB folder compression types (libmspack/mspack/cab.h:50-52).
+"""
+import numpy as np
+
+UNIT_DTYPE = np.dtype([
+    ("codec", "u1"), ("window_bits", "u1"), ("reset_interval", "<u2"), ("flags", "<u4"),
+    ("in_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4"), ("out_off", "<u8"),
+])
+assert UNIT_DTYPE.itemsize == 32
+
+CODEC_MSZIP, CODEC_QUANTUM, CODEC_LZX = 1, 2, 3
+FLAG_MSZIP_REPAIR = 0x1
+
+# MSPACK_ERR_* (libmspack/mspack/mspack.h:485-507)
+ERR_OK, ERR_ARGS, ERR_OPEN, ERR_READ, ERR_WRITE, ERR_SEEK, ERR_NOMEMORY = 0, 1, 2, 3, 4, 5, 6
+ERR_SIGNATURE, ERR_DATAFORMAT, ERR_CHECKSUM, ERR_CRUNCH, ERR_DECRUNCH = 7, 8, 9, 10, 11

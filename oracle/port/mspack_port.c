@@ -45,14 +45,16 @@ typedef struct {
     uint32_t in_len;
     uint64_t p;         /* bits consumed */
     uint64_t loaded;    /* Quantum only: bits fetched by the reference's 2-byte refills */
+    uint32_t base;      /* LZX only: byte offset p is measured from (0 or 1, see lzx_enter_bits) */
+    int bytemode;       /* LZX only: the reference's bit buffer is empty and it is reading raw bytes */
     int err;
 } bitin;
 
-static inline uint32_t in_byte(const bitin *b, uint64_t i) { return i < b->in_len ? b->in[i] : 0u; }
+static inline uint32_t in_byte(const bitin *b, uint64_t i) { i += b->base; return i < b->in_len ? b->in[i] : 0u; }
 
 /* the reference would have to fetch input bytes [0, need_bytes) : legal up to in_len + 2 */
 static inline int fetch_ok(bitin *b, uint64_t need_bytes) {
-    if (need_bytes > (uint64_t) b->in_len + 2u) { b->err = ERR_READ; return 0; }
+    if (need_bytes + b->base > (uint64_t) b->in_len + 2u) { b->err = ERR_READ; return 0; }
     return 1;
 }
 
@@ -82,6 +84,14 @@ static inline uint32_t lzx_read(bitin *b, unsigned n) {                /* READ_B
     uint32_t v;
     if (!lzx_ensure(b, n)) return 0;
     v = lzx_peek(b, n); b->p += n; return v;
+}
+
+/* The reference refills 16-bit words from its BYTE pointer.  After the raw bytes of an uncompressed
+ * block that pointer can be odd (an odd-sized block whose pad byte was not skipped because a reset
+ * cleared block_type first, lzxd.c:257-270 vs :469-474); words are then fetched from odd offsets.
+ * p stays "bits since base", with base moved by one byte so that p is 16-bit aligned again. */
+static inline void lzx_enter_bits(bitin *b) {
+    if (b->bytemode) { if ((b->p >> 3) & 1) { b->base++; b->p -= 8; } b->bytemode = 0; }
 }
 
 /* ---- MSB-first over 16-bit big-endian words == a plain big-endian bit stream (Quantum;
@@ -474,6 +484,7 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
         if (u->reset_interval && (frame % u->reset_interval) == 0) lzx_reset_state(s);   /* :423-438 */
         if (!s->header_read) {                                                          /* :447-453 */
             uint32_t i = 0, j = 0;
+            lzx_enter_bits(&s->b);
             if (lzx_read(&s->b, 1)) { i = lzx_read(&s->b, 16); j = lzx_read(&s->b, 16); }
             if (s->b.err) { ret = ERR_READ; goto out; }
             s->intel_filesize = (int32_t) ((i << 16) | j); s->header_read = 1;
@@ -488,6 +499,7 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
                     if (!fetch_ok(&s->b, (s->b.p >> 3) + 1)) { ret = ERR_READ; goto out; }
                     s->b.p += 8;
                 }
+                lzx_enter_bits(&s->b);
                 s->block_type = lzx_read(&s->b, 3); i = lzx_read(&s->b, 16); j = lzx_read(&s->b, 8);   /* :477-479 */
                 if (s->b.err) { ret = ERR_READ; goto out; }
                 s->block_remaining = s->block_length = (i << 8) | j;
@@ -515,6 +527,7 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
                     /* :505-507 read 1-16 bits to align to the next 16-bit word */
                     if ((s->b.p & 15) == 0) { if (!lzx_ensure(&s->b, 16)) { ret = ERR_READ; goto out; } s->b.p += 16; }
                     else s->b.p = (s->b.p + 15) & ~(uint64_t) 15;
+                    s->b.bytemode = 1;
                     for (i = 0; i < 12; i++) {
                         if (!fetch_ok(&s->b, (s->b.p >> 3) + 1)) { ret = ERR_READ; goto out; }
                         buf[i] = (uint8_t) in_byte(&s->b, s->b.p >> 3); s->b.p += 8;
@@ -592,16 +605,32 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
         }
         if (G - frame_start != frame_size) { ret = ERR_DECRUNCH; goto out; }            /* :689-693 */
         /* :696-697 re-align to the next 16-bit word (bits_left > 0 => the reference tops up first) */
-        if (s->b.p & 15) { if (!lzx_ensure(&s->b, 16)) { ret = ERR_READ; goto out; } s->b.p = (s->b.p + 15) & ~(uint64_t) 15; }
+        /* after raw bytes of an uncompressed block the reference's bit buffer is empty (bits_left == 0) and
+         * the realign is a no-op even if the byte pointer is odd; the pad byte goes with the next header */
+        if (!s->b.bytemode && (s->b.p & 15)) { if (!lzx_ensure(&s->b, 16)) { ret = ERR_READ; goto out; } s->b.p = (s->b.p + 15) & ~(uint64_t) 15; }
         frames[nframes].start = frame_start; frames[nframes].size = frame_size;
         frames[nframes].filesize = s->intel_filesize;
         frames[nframes].active = (s->intel_started && s->intel_filesize && frame < 32768 && frame_size > 10);
         nframes++; frame++;
     }
+    /* lzxd.c:419: end_frame = (offset + out_bytes) / 32768 + 1, so a request that ends exactly on a frame
+     * boundary runs one more, zero-sized, frame pass.  It decodes nothing, but when that frame index is a
+     * reset point it re-reads the intel header (1 or 33 bits, :447-453) and then tops the bit buffer up to
+     * re-align (:696-697) - two places where a unit cut exactly at its last byte reports MSPACK_ERR_READ
+     * although every output byte has been produced. */
+    if ((u->out_len % FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
+        uint64_t bp;
+        lzx_enter_bits(&s->b);
+        bp = s->b.p >> 3;                                /* p is 16-bit aligned here */
+        if (!fetch_ok(&s->b, bp + 2)) { ret = ERR_READ; goto e8; }
+        if (in_byte(&s->b, bp + 1) & 0x80) { if (!fetch_ok(&s->b, bp + 8)) { ret = ERR_READ; goto e8; } }
+        else if (!fetch_ok(&s->b, bp + 4)) { ret = ERR_READ; goto e8; }
+    }
+e8:
     for (f = 0; f < nframes; f++)
         if (frames[f].active) lzx_e8_frame(out + frames[f].start, frames[f].size, (int32_t) frames[f].start, frames[f].filesize);
 out:
-    if (produced) *produced = (ret == ERR_OK) ? u->out_len : 0;
+    if (produced) *produced = (ret == ERR_OK || G == u->out_len) ? u->out_len : 0;
     free(frames); free(s);
     return ret;
 }
