@@ -1,0 +1,124 @@
+"""Host-side Python binding of the C-ABI (include/msgpu.h) - plumbing for tests and bench.
+
+PyTorch is used only for device memory and streams; every decode call goes through
+libmsgpu.so.  There is no CPU fallback: if the CUDA library is missing or no GPU is present,
+constructing a BatchDecoder raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .units import UNIT_DTYPE
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmsgpu.so")
+
+# every symbol include/msgpu.h declares
+ABI_SYMBOLS = [
+    "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
+    "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
+    "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_version",
+]
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libmsgpu.so (built in-tree by libmspack_b200/build.py) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m libmspack_b200.build` "
+                           "(the CUDA extension is required, there is no CPU path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p
+    lib.msgpu_create.restype = vp
+    lib.msgpu_create.argtypes = [ctypes.c_int]
+    lib.msgpu_destroy.restype = None
+    lib.msgpu_destroy.argtypes = [vp]
+    lib.msgpu_last_error.restype = ctypes.c_char_p
+    lib.msgpu_last_error.argtypes = [vp]
+    lib.msgpu_decode_batch_device.restype = ctypes.c_int
+    lib.msgpu_decode_batch_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p, vp]
+    lib.msgpu_decode_batch_device_units.restype = ctypes.c_int
+    lib.msgpu_decode_batch_device_units.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p, vp]
+    lib.msgpu_decode_batch_host.restype = ctypes.c_int
+    lib.msgpu_decode_batch_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p]
+    lib.msgpu_launch_count.restype = ctypes.c_uint64
+    lib.msgpu_launch_count.argtypes = [vp]
+    lib.msgpu_scratch_bytes.restype = ctypes.c_size_t
+    lib.msgpu_scratch_bytes.argtypes = [vp]
+    lib.msgpu_last_kernel_ms.restype = ctypes.c_float
+    lib.msgpu_last_kernel_ms.argtypes = [vp]
+    lib.msgpu_version.restype = ctypes.c_char_p
+    lib.msgpu_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+class BatchDecoder:
+    """One msgpu context on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.device = int(device)
+        self.ctx = self.lib.msgpu_create(self.device)
+        if not self.ctx:
+            raise RuntimeError("msgpu_create failed: no usable CUDA device (libmspack_b200 has no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.msgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"msgpu error {rc}: {self.lib.msgpu_last_error(self.ctx).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.msgpu_launch_count(self.ctx))
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(self.lib.msgpu_scratch_bytes(self.ctx))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.msgpu_last_kernel_ms(self.ctx))
+
+    def decode_device(self, units: np.ndarray, d_in, d_out, d_status=None, stream=None) -> None:
+        """Inputs already resident: d_in / d_out / d_status are torch CUDA tensors (uint8 / uint8 / int32)."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        rc = self.lib.msgpu_decode_batch_device(
+            self.ctx, units.ctypes.data, len(units), ctypes.c_void_p(d_in.data_ptr()), d_in.numel(),
+            ctypes.c_void_p(d_out.data_ptr()), d_out.numel(),
+            ctypes.c_void_p(d_status.data_ptr()) if d_status is not None else None, sp)
+        self._check(rc)
+
+    def decode_host(self, units: np.ndarray, comp: np.ndarray, out_bytes: int):
+        """Host buffers in, host buffers out (H2D + decode + D2H inside the call)."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        out = np.empty(max(out_bytes, 1), dtype=np.uint8)
+        status = np.full(len(units), -1, dtype=np.int32)
+        rc = self.lib.msgpu_decode_batch_host(self.ctx, units.ctypes.data, len(units), comp.ctypes.data, comp.size,
+                                              out.ctypes.data, out_bytes, status.ctypes.data)
+        self._check(rc)
+        return out[:out_bytes], status
+
+    def decode_host_into(self, units: np.ndarray, comp_ptr: int, comp_bytes: int, out_ptr: int, out_bytes: int, status: np.ndarray):
+        """Same, with caller-owned (e.g. pinned) host buffers given as raw addresses."""
+        rc = self.lib.msgpu_decode_batch_host(self.ctx, units.ctypes.data, len(units), ctypes.c_void_p(comp_ptr), comp_bytes,
+                                              ctypes.c_void_p(out_ptr), out_bytes, status.ctypes.data)
+        self._check(rc)

@@ -1,0 +1,372 @@
+/* msgpu.cu - CUDA kernels (sm_100a) and the C-ABI of include/msgpu.h.
+ *
+ * Launch structure for one wave of units:
+ *     repeat until every unit of the wave is done:
+ *         k_p1_<codec>   one thread per unit : bitstream -> literals + match records, F frames per launch
+ *         k_p2_resolve   one warp per unit   : records -> output bytes (16-byte stores)
+ *     k_e8               one warp per LZX unit : E8 call translation of finished frames
+ *     k_status           per-unit MSPACK_ERR_* out
+ * There is no CPU path: without a CUDA device msgpu_create() fails.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "msgpu_core.cuh"
+#include "msgpu_p1_mszip.cuh"
+#include "msgpu_p1_lzx.cuh"
+#include "msgpu_p1_qtm.cuh"
+#include "msgpu_p2.cuh"
+
+/* ------------------------------------------------------------------------------------------ kernels */
+struct WaveArgs {
+    const msgpu_unit *units;     /* the wave's units (slot i == units[i]) */
+    const uint8_t *in_base;
+    uint8_t *out_base;
+    MsUnitState *ustate;         /* [slots] */
+    MsRec *recs;                 /* [slots][F][MS_MAXREC] */
+    uint8_t *lits;               /* [slots][F][MS_LITCAP] */
+    MsFrameInfo *finfo;          /* [slots][F] */
+    uint32_t *not_done;
+    int F;
+};
+
+template <int NT, int LROOT, int DROOT>
+__global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *aux)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    if (ti >= count) return;
+    uint32_t slot = order[ti];
+    ZipThread<NT, LROOT, DROOT> t;
+    t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
+    MsUnitState st = a.ustate[slot];
+    bool was_done = st.started && st.done;
+    p1_mszip_unit<NT, LROOT, DROOT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
+                                    a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, a.F);
+    if (!was_done) a.ustate[slot] = st;
+    if (!st.done) atomicAdd(a.not_done, 1u);
+}
+
+template <int NT, int MROOT, int LROOT>
+__global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *aux,
+                                               int32_t *e8info, const uint32_t *e8base)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    if (ti >= count) return;
+    uint32_t slot = order[ti];
+    LzxThread<NT, MROOT, LROOT> t;
+    t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
+    MsUnitState st = a.ustate[slot];
+    bool was_done = st.started && st.done;
+    p1_lzx_unit<NT, MROOT, LROOT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
+                                  a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
+    if (!was_done) a.ustate[slot] = st;
+    if (!st.done) atomicAdd(a.not_done, 1u);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *save)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    if (ti >= count) return;
+    uint32_t slot = order[ti];
+    QtmThread<NT> t;
+    t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
+    MsUnitState st = a.ustate[slot];
+    bool was_done = st.started && st.done;
+    p1_qtm_unit<NT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
+                    a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
+    if (!was_done) a.ustate[slot] = st;
+    if (!st.done) atomicAdd(a.not_done, 1u);
+}
+
+#define P2_WARPS 8
+__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, uint32_t nslots)
+{
+    __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t slot = blockIdx.x * P2_WARPS + warp;
+    if (slot >= nslots) return;
+    uint8_t *unit_out = a.out_base + a.units[slot].out_off;
+    for (int f = 0; f < a.F; f++) {
+        MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
+        if (!fi.valid || fi.size == 0) continue;
+        p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
+                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, uint32_t count, const int32_t *e8info, const uint32_t *e8base)
+{
+    uint32_t ti = blockIdx.x * 8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    if (ti >= count) return;
+    uint32_t slot = order[ti];
+    const msgpu_unit u = a.units[slot];
+    uint32_t produced = a.ustate[slot].produced, nfr = (u.out_len + MS_FRAME - 1) / MS_FRAME;
+    uint8_t *unit_out = a.out_base + u.out_off;
+    for (uint32_t f = 0; f < nfr; f++) {
+        uint32_t start = f * MS_FRAME, size = u.out_len - start < MS_FRAME ? u.out_len - start : MS_FRAME;
+        if (start + size > produced) break;
+        int32_t fs = e8info[e8base[ti] + f];
+        if (fs) e8_translate_frame(lane, unit_out + start, size, (int32_t) start, fs);
+    }
+}
+
+__global__ void k_status(const MsUnitState *ustate, uint32_t nslots, int32_t *status)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots) status[i] = ustate[i].status;
+}
+
+__global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t *val, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) status[idx[i]] = val[i];
+}
+
+/* ------------------------------------------------------------------------------------------ host side */
+#define ZIP_NT 128
+#define ZIP_LROOT 9
+#define ZIP_DROOT 8
+#define LZX_NT 128
+#define LZX_MROOT 9
+#define LZX_LROOT 7
+#define QTM_NT 128
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct msgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> evs;        /* pairs (start, end) per wave, reused */
+    size_t ev_used = 0;                  /* events of the most recent batch */
+    std::string err;
+    uint64_t launches = 0;
+    size_t scratch_budget = 0;
+    DevBuf units, ustate, recs, lits, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
+    uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
+    size_t bytes_held() const {
+        return units.cap + ustate.cap + recs.cap + lits.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
+               save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap;
+    }
+};
+
+static int fail(msgpu_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    if (c) c->err = buf;
+    return code;
+}
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, MSGPU_ERR_NOMEMORY, what, e_); } while (0)
+
+extern "C" const char *msgpu_version(void) { return "libmspack_b200 msgpu 0.1 (sm_100a)"; }
+
+extern "C" msgpu_ctx *msgpu_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;   /* no CPU fallback */
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    msgpu_ctx *c = new msgpu_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 64) != cudaSuccess) { delete c; return nullptr; }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const char *env = getenv("MSGPU_SCRATCH_MB");
+    c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
+    cudaFuncSetAttribute(k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>));
+    cudaFuncSetAttribute(k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>));
+    cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
+    return c;
+}
+
+extern "C" void msgpu_destroy(msgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->lits, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
+                       &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status };
+    for (DevBuf *b : bufs) b->release();
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *msgpu_last_error(const msgpu_ctx *c) { return c ? c->err.c_str() : "no context"; }
+extern "C" uint64_t msgpu_launch_count(const msgpu_ctx *c) { return c ? c->launches : 0; }
+extern "C" size_t msgpu_scratch_bytes(const msgpu_ctx *c) { return c ? c->bytes_held() : 0; }
+
+extern "C" float msgpu_last_kernel_ms(msgpu_ctx *c) {
+    if (!c || c->ev_used == 0) return -1.0f;
+    float total = 0.0f;
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(c->evs[i + 1]) != cudaSuccess) return -1.0f;
+        if (cudaEventElapsedTime(&ms, c->evs[i], c->evs[i + 1]) != cudaSuccess) return -1.0f;
+        total += ms;
+    }
+    return total;
+}
+
+static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_FRAME - 1) / MS_FRAME; }
+
+/* Decode one wave: units[lo, hi) of the host array (already validated). */
+static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t hi, const void *d_in, void *d_out,
+                    int32_t *d_status, cudaStream_t s)
+{
+    const uint32_t n = (uint32_t) (hi - lo);
+    std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base;
+    uint32_t maxfr = 1, e8total = 0; bool any_zip = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const msgpu_unit &u = h_units[lo + i];
+        ord[u.codec].push_back(i);
+        uint32_t fr = frames_of(u); if (fr > maxfr) maxfr = fr;
+        if (u.codec == MSGPU_CODEC_LZX) { e8base.push_back(e8total); e8total += fr ? fr : 1; }
+        if (u.codec == MSGPU_CODEC_MSZIP) any_zip = true;
+    }
+    const int F = maxfr >= 2 ? 2 : 1;
+    const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
+
+    CK(ctx->units.reserve((size_t) n * sizeof(msgpu_unit)), "alloc units");
+    CK(ctx->ustate.reserve((size_t) n * sizeof(MsUnitState)), "alloc state");
+    CK(ctx->recs.reserve((size_t) n * F * MS_MAXREC * sizeof(MsRec)), "alloc records");
+    CK(ctx->lits.reserve((size_t) n * F * MS_LITCAP + 64), "alloc literals");
+    CK(ctx->finfo.reserve((size_t) n * F * sizeof(MsFrameInfo)), "alloc frame info");
+    CK(ctx->misc.reserve(256), "alloc misc");
+    CK(ctx->order.reserve((size_t) (n + 3) * sizeof(uint32_t)), "alloc order");
+    if (nz) CK(ctx->aux_zip.reserve((size_t) ((nz + 31) / 32) * ZIP_AUX_BYTES), "alloc mszip aux");
+    if (nl) {
+        CK(ctx->aux_lzx.reserve((size_t) ((nl + 31) / 32) * LZX_AUX_BYTES), "alloc lzx aux");
+        CK(ctx->e8info.reserve((size_t) (e8total + 1) * sizeof(int32_t)), "alloc e8 info");
+        CK(ctx->e8base.reserve((size_t) nl * sizeof(uint32_t)), "alloc e8 base");
+    }
+    if (nq) CK(ctx->save_qtm.reserve((size_t) nq * QTM_SAVE_BYTES), "alloc quantum save");
+
+    uint32_t *d_order = reinterpret_cast<uint32_t *>(ctx->order.p);
+    uint32_t *d_ord_z = d_order, *d_ord_q = d_order + nz, *d_ord_l = d_order + nz + nq;
+    CK(cudaMemcpyAsync(ctx->units.p, h_units + lo, (size_t) n * sizeof(msgpu_unit), cudaMemcpyHostToDevice, s), "copy units");
+    if (nz) CK(cudaMemcpyAsync(d_ord_z, ord[1].data(), nz * 4, cudaMemcpyHostToDevice, s), "copy order");
+    if (nq) CK(cudaMemcpyAsync(d_ord_q, ord[2].data(), nq * 4, cudaMemcpyHostToDevice, s), "copy order");
+    if (nl) {
+        CK(cudaMemcpyAsync(d_ord_l, ord[3].data(), nl * 4, cudaMemcpyHostToDevice, s), "copy order");
+        CK(cudaMemcpyAsync(ctx->e8base.p, e8base.data(), nl * 4, cudaMemcpyHostToDevice, s), "copy e8 base");
+        CK(cudaMemsetAsync(ctx->e8info.p, 0, (size_t) (e8total + 1) * sizeof(int32_t), s), "clear e8 info");
+    }
+    CK(cudaMemsetAsync(ctx->ustate.p, 0, (size_t) n * sizeof(MsUnitState), s), "clear state");
+    /* the pageable host vectors above must outlive the async copies */
+    CK(cudaStreamSynchronize(s), "sync uploads");
+
+    WaveArgs a;
+    a.units = reinterpret_cast<const msgpu_unit *>(ctx->units.p); a.in_base = reinterpret_cast<const uint8_t *>(d_in);
+    a.out_base = reinterpret_cast<uint8_t *>(d_out); a.ustate = reinterpret_cast<MsUnitState *>(ctx->ustate.p);
+    a.recs = reinterpret_cast<MsRec *>(ctx->recs.p); a.lits = reinterpret_cast<uint8_t *>(ctx->lits.p);
+    a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.F = F;
+
+    while (ctx->evs.size() < ctx->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e), "event create"); ctx->evs.push_back(e); }
+    cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
+    CK(cudaEventRecord(ev0, s), "event");
+    uint32_t rounds_planned = (maxfr + F - 1) / F;
+    for (uint32_t round = 0;; round++) {
+        bool check = (round + 1 >= rounds_planned) && (any_zip || round + 1 > rounds_planned);
+        if (check) CK(cudaMemsetAsync(a.not_done, 0, 4, s), "clear counter");
+        if (nz) { k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT><<<(nz + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>), s>>>(a, d_ord_z, nz, reinterpret_cast<uint8_t *>(ctx->aux_zip.p)); ctx->launches++; }
+        if (nl) { k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT><<<(nl + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>), s>>>(a, d_ord_l, nl, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
+        if (nq) { k_p1_qtm<QTM_NT><<<(nq + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), s>>>(a, d_ord_q, nq, reinterpret_cast<uint8_t *>(ctx->save_qtm.p)); ctx->launches++; }
+        k_p2_resolve<<<(n + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, s>>>(a, n); ctx->launches++;
+        CK(cudaGetLastError(), "kernel launch");
+        if (round + 1 < rounds_planned) continue;
+        if (!any_zip && round + 1 == rounds_planned) break;      /* LZX / Quantum frame counts are exact */
+        CK(cudaMemcpyAsync(ctx->h_pinned, a.not_done, 4, cudaMemcpyDeviceToHost, s), "read counter");
+        CK(cudaStreamSynchronize(s), "sync");
+        if (ctx->h_pinned[0] == 0) break;
+        if (round > (1u << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
+    }
+    if (nl) { k_e8<<<(nl + 7) / 8, 256, 0, s>>>(a, d_ord_l, nl, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
+    if (d_status) { k_status<<<(n + 255) / 256, 256, 0, s>>>(a.ustate, n, d_status + lo); ctx->launches++; }
+    CK(cudaEventRecord(ev1, s), "event");
+    ctx->ev_used += 2;
+    CK(cudaGetLastError(), "kernel launch");
+    return 0;
+}
+
+extern "C" int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
+                                         void *d_out, size_t out_bytes, int32_t *d_status, void *stream)
+{
+    if (!ctx) return MSGPU_ERR_ARGS;
+    ctx->err.clear();
+    if (n == 0) return 0;
+    if (!units || !d_in || !d_out) return fail(ctx, MSGPU_ERR_ARGS, "null argument");
+    if (n > 0x7FFFFFFFull) return fail(ctx, MSGPU_ERR_ARGS, "too many units");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    for (size_t i = 0; i < n; i++) {
+        const msgpu_unit &u = units[i];
+        if (u.codec < 1 || u.codec > 3) return fail(ctx, MSGPU_ERR_ARGS, "unit with unknown codec");
+        if (u.in_off + u.in_len > in_bytes || u.out_off + u.out_len > out_bytes) return fail(ctx, MSGPU_ERR_ARGS, "unit outside the input/output buffer");
+        if (u.in_len >= 0x7FFFFFF0u) return fail(ctx, MSGPU_ERR_ARGS, "unit input too large");
+        if (u.out_off & 15u) return fail(ctx, MSGPU_ERR_ARGS, "out_off must be a multiple of 16");
+    }
+    /* wave size from the scratch budget */
+    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
+    const int F = maxfr >= 2 ? 2 : 1;
+    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec) + MS_LITCAP) + sizeof(MsUnitState) + 6144;
+    size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
+    ctx->ev_used = 0;
+    for (size_t lo = 0; lo < n; lo += slots) {
+        size_t hi = lo + slots < n ? lo + slots : n;
+        int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s);
+        if (r) return r;
+    }
+    return 0;
+}
+
+extern "C" int msgpu_decode_batch_device_units(msgpu_ctx *ctx, const msgpu_unit *d_units, size_t n, const void *d_in, size_t in_bytes,
+                                               void *d_out, size_t out_bytes, int32_t *d_status, void *stream)
+{
+    if (!ctx) return MSGPU_ERR_ARGS;
+    if (n == 0) return 0;
+    /* wave planning (codec partition, frame counts) needs the descriptors on the host: 32 bytes per unit */
+    std::vector<msgpu_unit> h(n);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    CK(cudaMemcpy(h.data(), d_units, n * sizeof(msgpu_unit), cudaMemcpyDeviceToHost), "copy units to host");
+    return msgpu_decode_batch_device(ctx, h.data(), n, d_in, in_bytes, d_out, out_bytes, d_status, stream);
+}
+
+extern "C" int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *h_in, size_t in_bytes,
+                                       void *h_out, size_t out_bytes, int32_t *status)
+{
+    if (!ctx) return MSGPU_ERR_ARGS;
+    ctx->err.clear();
+    if (n == 0) return 0;
+    if (!units || !h_in || !h_out) return fail(ctx, MSGPU_ERR_ARGS, "null argument");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    cudaStream_t s = ctx->stream;
+    CK(ctx->io_in.reserve(in_bytes + 64), "alloc input");
+    CK(ctx->io_out.reserve(out_bytes + 64), "alloc output");
+    CK(ctx->io_status.reserve(n * sizeof(int32_t)), "alloc status");
+    CK(cudaMemcpyAsync(ctx->io_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, s), "copy input");
+    int r = msgpu_decode_batch_device(ctx, units, n, ctx->io_in.p, in_bytes, ctx->io_out.p, out_bytes,
+                                      reinterpret_cast<int32_t *>(ctx->io_status.p), s);
+    if (r) return r;
+    CK(cudaMemcpyAsync(h_out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s), "copy output");
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "copy status");
+    CK(cudaStreamSynchronize(s), "sync");
+    return 0;
+}

@@ -1,0 +1,261 @@
+/* msgpu_core.cuh - device-side building blocks of the B200 batch decompressor.
+ *
+ * Execution model:
+ *   P1 "entropy" kernels : ONE THREAD per unit walks the serial bitstream (Huffman / arithmetic
+ *        decode) and transcodes it into a byte-aligned intermediate form per 32 KiB frame:
+ *        a literal byte stream plus fixed-size match records {pos, len, off}.  32 units advance
+ *        in lockstep per warp, so every issued instruction does useful work for 32 streams.
+ *        Decode LUTs live in shared memory, interleaved by thread (bank == lane).
+ *   P2 "resolve" kernel  : ONE WARP per unit turns records + literals into output bytes,
+ *        byte-parallel (each lane owns 16 consecutive output bytes of a 512-byte chunk, finds
+ *        their source by binary search over the records and pointer-jumps through in-chunk
+ *        dependencies), and writes coalesced 16-byte stores.
+ *   E8 kernel            : LZX call-translation post-pass (lzxd.c:706-737).
+ *
+ * The reference's behaviour being restated is cited per function (paths relative to
+ * /root/reference/libmspack/mspack/).  Everything here is written from scratch.
+ *
+ * The header also compiles as plain C++ (MSGPU_EMULATE) so tests can run the per-thread logic on
+ * the CPU; the product never does that.
+ */
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/msgpu.h"
+
+#if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
+#define MS_D __device__ __forceinline__
+#define MS_M __device__ __forceinline__      /* member functions */
+#define MS_DN __device__ __noinline__
+#define MS_BREV32(x) __brev(x)
+#define MS_CLZ(x) __clz(x)
+#else
+#define MS_D static inline
+#define MS_M inline
+#define MS_DN static
+static inline uint32_t ms_brev32_host(uint32_t v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+}
+#define MS_BREV32(x) ms_brev32_host(x)
+#define MS_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#endif
+
+#define MS_FRAME      32768u
+#define MS_MAXREC     16400u     /* matches per frame <= 32768/2, + sentinel, padded            */
+#define MS_LITCAP     32768u     /* literal bytes per frame                                     */
+#define MS_WARP       32
+
+#define MS_OK        MSGPU_ERR_OK
+#define MS_EREAD     MSGPU_ERR_READ
+#define MS_EDECRUNCH MSGPU_ERR_DECRUNCH
+#define MS_ENOMEM    MSGPU_ERR_NOMEMORY
+#define MS_EARGS     MSGPU_ERR_ARGS
+
+/* ---- intermediate form ------------------------------------------------------------------ */
+struct MsRec { uint32_t a, b; };            /* a = pos | M << 16, b = off | len << 22 (see emit_match) */
+struct MsFrameInfo {
+    uint32_t nrec;      /* match records (a sentinel {pos = size, len = 0} follows them)          */
+    uint32_t size;      /* bytes this frame contributes to the output (0 = nothing / failed)      */
+    uint32_t g0;        /* unit-relative output position of the frame's first byte                */
+    uint32_t valid;     /* 1 if P2 should resolve it                                              */
+};
+
+/* per-slot decoder state that survives between launches (multi-frame units) */
+struct MsUnitState {
+    uint32_t started, done; int32_t status; uint32_t produced, frame;
+    int32_t ipos; uint32_t bc; uint32_t bb_lo, bb_hi;
+    uint32_t base, bytemode;
+    uint32_t R0, R1, R2, block_type, block_length, block_remaining, header_read, intel_filesize, intel_started;
+    uint32_t length_empty, aligned_lens;
+    uint32_t frame_todo, qH, qL, qC, q_bl, q_fp;
+    uint32_t pad[3];
+};
+
+/* ---- small helpers ------------------------------------------------------------------------ */
+MS_D uint32_t ms_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+/* =============================================================================================
+ * Bit input.  All three readers keep a 64-bit buffer refilled 32 bits at a time from the unit's
+ * bytes (4-byte aligned loads; bytes outside [0, in_len) read as zero) and can report the number
+ * of bits consumed, so the reference's EOF rule can be restated exactly: the reference supplies
+ * two zero bytes once and fails on the next refill (readbits.h:192-214), i.e. needing input byte
+ * index >= in_len + 2 is MSPACK_ERR_READ.
+ * ============================================================================================= */
+struct MsBits {
+    const uint8_t *in;      /* unit's first compressed byte (+ LZX base, see lzx_enter_bits)      */
+    int32_t in_len;         /* bytes available from `in`                                          */
+    int32_t ipos;           /* byte offset (from `in`) of the next 32-bit load                    */
+    int32_t bc;             /* valid bits in bb                                                   */
+    uint64_t bb;
+    int32_t err;
+};
+
+MS_D uint32_t ms_load32(const MsBits &b, int32_t ip) {
+    const uint8_t *p = b.in + ip;
+    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && ip + 4 <= b.in_len) return *reinterpret_cast<const uint32_t *>(p);
+    uint32_t v = 0;                      /* tail of the unit, or a unit that is not 4-byte aligned: bytewise, zero past the end */
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int32_t i = ip + k; if (i < b.in_len) v |= (uint32_t) p[k] << (8 * k); }
+    return v;
+}
+
+/* bits consumed so far, relative to `in` */
+MS_D int64_t ms_bitpos(const MsBits &b) { return (int64_t) b.ipos * 8 - b.bc; }
+
+/* ---- LSB-first (MSZIP: readbits.h:161-166, mszipd.c:23-26).  Next bit = bit 0 of bb. ---- */
+MS_D void lsb_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
+    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
+}
+MS_D void lsb_refill(MsBits &b) {                 /* afterwards bc >= 32 */
+    if (b.bc < 32) { b.bb |= (uint64_t) ms_load32(b, b.ipos) << b.bc; b.ipos += 4; b.bc += 32; }
+}
+MS_D uint32_t lsb_peek(const MsBits &b, int n) { return (uint32_t) b.bb & ((1u << n) - 1u); }
+MS_D void lsb_drop(MsBits &b, int n) { b.bb >>= n; b.bc -= n; }
+/* would the reference's ENSURE_BITS(n) at this position run past in_len + 2 bytes? */
+MS_D void lsb_check(MsBits &b, int n) {
+    if (b.ipos + 8 > b.in_len) { if (((int64_t) (b.ipos - b.in_len)) * 8 - b.bc + n > 16) b.err = MS_EREAD; }
+}
+MS_D uint32_t lsb_read(MsBits &b, int n) {        /* READ_BITS, 0 <= n <= 16; caller refilled */
+    lsb_check(b, n);
+    uint32_t v = lsb_peek(b, n); lsb_drop(b, n); return v;
+}
+MS_D void lsb_align_byte(MsBits &b) { int r = b.bc & 7; lsb_drop(b, r); }   /* bc == -p mod 8 since ipos*8 is a multiple of 8 */
+
+/* ---- MSB-first over 16-bit little-endian words (LZX: readbits.h:155-160, lzxd.c:86-91).
+ *      Next bit = bit 63 of bb. ---- */
+MS_D uint32_t msb16le_swz(uint32_t x) { return (x << 16) | (x >> 16); }   /* two LE words -> 32 stream bits, first word on top */
+MS_D void lzx_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
+    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
+}
+MS_D void lzx_refill(MsBits &b) {                 /* afterwards bc >= 32 */
+    if (b.bc < 32) { b.bb |= (uint64_t) msb16le_swz(ms_load32(b, b.ipos)) << (32 - b.bc); b.ipos += 4; b.bc += 32; }
+}
+MS_D uint32_t msb_peek(const MsBits &b, int n) { return (uint32_t) (b.bb >> (64 - n)); }     /* 1 <= n <= 32 */
+MS_D void msb_drop(MsBits &b, int n) { b.bb <<= n; b.bc -= n; }
+/* ENSURE_BITS(n) fetches whole words: fails iff p + n > floor16(8 * (in_len + 2)) */
+MS_D void lzx_check(MsBits &b, int n) {
+    if (b.ipos + 8 > b.in_len) {
+        int64_t x = ((int64_t) (b.in_len - b.ipos)) * 8 + 16 + b.bc - n;    /* 8(in_len+2) - (p+n) */
+        if (x < ((b.in_len & 1) ? 8 : 0)) b.err = MS_EREAD;
+    }
+}
+MS_D uint32_t lzx_read(MsBits &b, int n) {        /* READ_BITS, 1 <= n <= 17; caller refilled */
+    lzx_check(b, n);
+    uint32_t v = msb_peek(b, n); msb_drop(b, n); return v;
+}
+
+/* ---- MSB-first plain big-endian bit stream (Quantum: qtmd.c:30-35) ---- */
+MS_D uint32_t ms_bswap32(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); }
+MS_D void qtm_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
+    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
+}
+MS_D void qtm_refill(MsBits &b) {
+    if (b.bc < 32) { b.bb |= (uint64_t) ms_bswap32(ms_load32(b, b.ipos)) << (32 - b.bc); b.ipos += 4; b.bc += 32; }
+}
+
+/* =============================================================================================
+ * Canonical Huffman tables.
+ *
+ * LUT (shared memory, one per thread, interleaved: entry e of thread t at lut[e * NT + t]):
+ *     u16 = sym << 4 | len   for codes of len <= ROOT,   0 for the prefix of a longer code.
+ * Longer codes take the slow path: per-length limit[] / offs[] and the symbols in canonical order
+ * (sorted[]) live in global scratch, interleaved by lane so that the warp's accesses coalesce.
+ *
+ * make_decode_table's acceptance rule is restated (readhuff.h:83-176): ok iff the codes no longer
+ * than the reference's TABLEBITS fill the table exactly (longer codes are then unreachable and are
+ * dropped), or else all codes <= 16 bits have Kraft sum exactly 1.  Lengths above 16 (possible in
+ * LZX, lzxd.c:169-171) never take part.
+ * ============================================================================================= */
+struct MsHuffAux {          /* pointers already offset by lane; stride MS_WARP elements */
+    uint32_t *limit;        /* limit[l], l = 0..16 : exclusive upper bound of l-bit codes, left-aligned to 16 bits */
+    uint16_t *offs;         /* offs[l]  : index in sorted[] of the first l-bit symbol */
+    uint16_t *sorted;       /* symbols in canonical order */
+};
+
+/* Build.  lens(i) gives the code length of symbol i (functor); cnt is a 17-entry u16 scratch
+ * array in shared memory for this thread with stride cstride.  Returns 0 on success. */
+template <int ROOT, bool LSB, int NT, class LensFn>
+MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut, const MsHuffAux &aux,
+                       uint16_t *cnt, int cstride, int *maxlen_out)
+{
+#pragma unroll 1
+    for (int l = 0; l <= 16; l++) cnt[l * cstride] = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsyms; s++) { uint32_t l = lens(s); if (l >= 1 && l <= 16) cnt[l * cstride]++; }
+    uint32_t sum_short = 0, sum_all = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 16; l++) { sum_all += (uint32_t) cnt[l * cstride] << (16 - l); if (l <= ref_tablebits) sum_short = sum_all; }
+    int maxlen = 16;
+    if (sum_short > 65536u) return 1;
+    if (sum_short == 65536u) maxlen = ref_tablebits;
+    else if (sum_all != 65536u) return 1;
+    *maxlen_out = maxlen;
+    uint32_t lim = 0, off = 0;
+    aux.limit[0] = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 16; l++) {
+        uint32_t c = (l <= maxlen) ? cnt[l * cstride] : 0;
+        aux.offs[l * MS_WARP] = (uint16_t) off;
+        cnt[l * cstride] = (uint16_t) off;                  /* becomes the running index of the next l-bit symbol */
+        lim += c << (16 - l); aux.limit[l * MS_WARP] = lim; off += c;
+    }
+#pragma unroll 1
+    for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsyms; s++) {
+        int l = (int) lens(s);
+        if (l < 1 || l > maxlen) continue;
+        uint32_t k = cnt[l * cstride]; cnt[l * cstride] = (uint16_t) (k + 1);
+        aux.sorted[k * MS_WARP] = (uint16_t) s;
+        if (l <= ROOT) {
+            uint32_t code = (aux.limit[(l - 1) * MS_WARP] >> (16 - l)) + (k - aux.offs[l * MS_WARP]);   /* l-bit canonical code */
+            uint16_t ent = (uint16_t) ((s << 4) | l);
+            if (LSB) {
+                uint32_t idx = MS_BREV32(code) >> (32 - l);                                            /* first stream bit = code MSB = index bit 0 */
+                for (; idx < (1u << ROOT); idx += (1u << l)) lut[idx * NT] = ent;
+            }
+            else {
+                uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
+                for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = ent;
+            }
+        }
+    }
+    return 0;
+}
+
+/* slow path: v16 = next 16 stream bits, first bit in bit 15 */
+template <int ROOT>
+MS_D uint32_t ms_huff_slow(uint32_t v16, const MsHuffAux &aux, int maxlen, int *len) {
+    int l = ROOT + 1;
+#pragma unroll 1
+    for (; l < maxlen; l++) if (v16 < aux.limit[l * MS_WARP]) break;
+    *len = l;
+    uint32_t idx = aux.offs[l * MS_WARP] + ((v16 - aux.limit[(l - 1) * MS_WARP]) >> (16 - l));
+    return aux.sorted[idx * MS_WARP];
+}
+
+/* =============================================================================================
+ * Record / literal emission (P1 -> P2 intermediate form)
+ * ============================================================================================= */
+struct MsEmit {
+    MsRec *rec;             /* this frame's record array */
+    uint8_t *lit;           /* this frame's literal stream (4-byte aligned) */
+    uint32_t nrec, nlit, litacc, mbytes;
+};
+MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *lit) { e.rec = rec; e.lit = lit; e.nrec = 0; e.nlit = 0; e.litacc = 0; e.mbytes = 0; }
+MS_D void emit_literal(MsEmit &e, uint32_t byte) {
+    e.litacc |= byte << (8 * (e.nlit & 3)); e.nlit++;
+    if ((e.nlit & 3) == 0) { *reinterpret_cast<uint32_t *>(e.lit + e.nlit - 4) = e.litacc; e.litacc = 0; }
+}
+/* record: a = pos | M << 16 (M = match bytes before this record), b = off | len << 22 */
+MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
+    MsRec r; r.a = pos | (e.mbytes << 16); r.b = off | (len << 22); e.rec[e.nrec++] = r; e.mbytes += len;
+}
+MS_D void emit_end(MsEmit &e, uint32_t frame_size) {
+    if (e.nlit & 3) *reinterpret_cast<uint32_t *>(e.lit + (e.nlit & ~3u)) = e.litacc;
+    MsRec r; r.a = frame_size | (e.mbytes << 16); r.b = 0; e.rec[e.nrec] = r;       /* sentinel: pos = size, len = 0 */
+}

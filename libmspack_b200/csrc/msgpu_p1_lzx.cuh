@@ -1,0 +1,344 @@
+/* msgpu_p1_lzx.cuh - P1 entropy stage for LZX units: one thread walks one unit's bitstream
+ * (lzxd.c:388-771 lzxd_decompress, :138-183 lzxd_read_lens, :257-270 lzxd_reset_state) and emits
+ * literal bytes + match records per 32 KiB frame.  Window-relative checks are restated for a
+ * linear output buffer: the reference's window_posn is (bytes decoded) mod window_size and its
+ * lzx->offset is the frame's start (see oracle/port/mspack_port.c for the same restatement on the CPU).
+ */
+#pragma once
+#include "msgpu_core.cuh"
+
+#define LZX_MAIN_MAX   2576                   /* LZX_MAINTREE_MAXSYMBOLS, lzx.h:38 */
+#define LZX_MAIN_ALLOC (LZX_MAIN_MAX + 64)    /* + LZX_LENTABLE_SAFETY, lzx.h:44 */
+#define LZX_LEN_SYMS   250                    /* LZX_LENGTH_MAXSYMBOLS */
+#define LZX_LEN_ALLOC  320
+#define LZX_MSORT_N    768                    /* coded main symbols <= 256 + 400 + 51 for window_bits <= 21 */
+
+#define LZX_AUX_MAINLEN  0                                         /* u8  [2640][32] */
+#define LZX_AUX_LENLEN   (LZX_AUX_MAINLEN + LZX_MAIN_ALLOC * 32)   /* u8  [320][32]  */
+#define LZX_AUX_MSORT    (LZX_AUX_LENLEN + LZX_LEN_ALLOC * 32)     /* u16 [768][32]  */
+#define LZX_AUX_LSORT    (LZX_AUX_MSORT + LZX_MSORT_N * 32 * 2)    /* u16 [256][32]  */
+#define LZX_AUX_PSORT    (LZX_AUX_LSORT + 256 * 32 * 2)            /* u16 [32][32]   */
+#define LZX_AUX_ASORT    (LZX_AUX_PSORT + 32 * 32 * 2)             /* u16 [16][32]   */
+#define LZX_AUX_LIMIT    (LZX_AUX_ASORT + 16 * 32 * 2)             /* u32 [4][20][32] */
+#define LZX_AUX_OFFS     (LZX_AUX_LIMIT + 4 * 20 * 32 * 4)         /* u16 [4][20][32] */
+#define LZX_AUX_BYTES    (LZX_AUX_OFFS + 4 * 20 * 32 * 2)
+
+template <int NT, int MROOT, int LROOT>
+struct LzxShared {
+    uint16_t mlut[(1 << MROOT) * NT];
+    uint16_t llut[(1 << LROOT) * NT];     /* LENGTH tree; hosts the pretree LUT while code lengths are being read */
+    uint16_t alut[128 * NT];
+    uint16_t cnt[17 * NT];
+};
+
+template <int NT, int MROOT, int LROOT>
+struct LzxThread {
+    MsBits b;
+    uint16_t *mlut, *llut, *alut, *cnt;
+    uint8_t *main_len, *len_len;
+    MsHuffAux ma, la, pa, aa;
+    int mmax, lmax, pmax, amax;
+    uint32_t R0, R1, R2, block_type, block_length, block_remaining, header_read, intel_started, length_empty, aligned_lens;
+    int32_t intel_filesize;
+    uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
+    int32_t bytepos;                      /* valid in bytemode: next raw byte (relative to b.in) */
+
+    MS_M void bind(LzxShared<NT, MROOT, LROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
+        mlut = sh->mlut + tid; llut = sh->llut + tid; alut = sh->alut + tid; cnt = sh->cnt + tid;
+        main_len = aux_warp + LZX_AUX_MAINLEN + lane; len_len = aux_warp + LZX_AUX_LENLEN + lane;
+        ma.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_MSORT) + lane;
+        la.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_LSORT) + lane;
+        pa.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_PSORT) + lane;
+        aa.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_ASORT) + lane;
+        uint32_t *lim = reinterpret_cast<uint32_t *>(aux_warp + LZX_AUX_LIMIT) + lane;
+        uint16_t *off = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_OFFS) + lane;
+        ma.limit = lim; la.limit = lim + 20 * 32; pa.limit = lim + 40 * 32; aa.limit = lim + 60 * 32;
+        ma.offs = off; la.offs = off + 20 * 32; pa.offs = off + 40 * 32; aa.offs = off + 60 * 32;
+    }
+
+    MS_M void reset_state() {                 /* lzxd.c:257-270 */
+        R0 = R1 = R2 = 1; header_read = 0; block_remaining = 0; block_type = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < nsyms_eff; i++) main_len[i * 32] = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < LZX_LEN_SYMS; i++) len_len[i * 32] = 0;
+    }
+
+    /* READ_HUFFSYM, MSB-first; caller guarantees >= 16 buffered bits */
+    template <int ROOT>
+    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, int maxlen) {
+        lzx_check(b, 16);
+        uint32_t e = lut[msb_peek(b, ROOT) * NT];
+        int len = (int) (e & 15); uint32_t sym = e >> 4;
+        if (len == 0) sym = ms_huff_slow<ROOT>(msb_peek(b, 16), aux, maxlen, &len);
+        msb_drop(b, len);
+        return sym;
+    }
+
+    /* raw byte access for uncompressed blocks; READ_IF_NEEDED semantics (readbits.h:182-214) */
+    MS_M uint32_t raw_byte() {
+        if (bytepos > b.in_len + 1) { b.err = MS_EREAD; return 0; }
+        uint32_t v = bytepos < b.in_len ? b.in[bytepos] : 0u;
+        bytepos++;
+        return v;
+    }
+
+    /* the reference's bit buffer is empty and its byte pointer is at bytepos: go back to bit reading.
+     * An odd byte pointer (odd-sized uncompressed block whose pad byte was not skipped because a reset
+     * cleared block_type first, lzxd.c:257-270 vs :469-474) moves the 16-bit word grid by one byte. */
+    MS_M void enter_bits() {
+        if (!bytemode) return;
+        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; }
+        b.ipos = bytepos & ~3; b.bb = 0; b.bc = 0;
+        lzx_refill(b);
+        if (bytepos & 2) msb_drop(b, 16);
+        bytemode = 0;
+    }
+
+    /* lzxd.c:138-183: pretree-delta coded lengths; runs are not clamped to `last` */
+    MS_M int read_lens(uint8_t *lens, uint32_t first, uint32_t last) {
+        uint64_t plo = 0; uint32_t phi = 0;
+#pragma unroll 1
+        for (int x = 0; x < 20; x++) {
+            lzx_refill(b);
+            uint32_t y = lzx_read(b, 4);
+            if (x < 16) plo |= (uint64_t) y << (4 * x); else phi |= y << (4 * (x - 16));
+        }
+        if (b.err) return b.err;
+        if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
+                                            20, 6, llut, pa, cnt, NT, &pmax)) return MS_EDECRUNCH;
+#pragma unroll 1
+        for (uint32_t x = first; x < last;) {
+            lzx_refill(b);
+            int z = (int) huffsym<LROOT>(llut, pa, pmax);
+            if (b.err) return b.err;
+            if (z == 17) { uint32_t y = lzx_read(b, 4) + 4; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
+            else if (z == 18) { uint32_t y = lzx_read(b, 5) + 20; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
+            else if (z == 19) {
+                uint32_t y = lzx_read(b, 1) + 4;
+                lzx_refill(b);
+                z = (int) huffsym<LROOT>(llut, pa, pmax);
+                if (b.err) return b.err;
+                z = (int) lens[x * 32] - z; if (z < 0) z += 17;
+                while (y--) { lens[x * 32] = (uint8_t) z; x++; }
+            }
+            else { z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
+        }
+        return 0;
+    }
+
+    MS_M int build_main() {
+        uint8_t *l = main_len;
+        return ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax) ? MS_EDECRUNCH : 0;
+    }
+    MS_M int build_length() {                 /* BUILD_TABLE_MAYBE_EMPTY, lzxd.c:111-125 */
+        uint8_t *l = len_len;
+        length_empty = 0;
+        if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, llut, la, cnt, NT, &lmax)) {
+#pragma unroll 1
+            for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
+            length_empty = 1;
+        }
+        return 0;
+    }
+    MS_M int build_aligned() {
+        uint32_t al = aligned_lens;
+        return ms_huff_build<7, false, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, alut, aa, cnt, NT, &amax) ? MS_EDECRUNCH : 0;
+    }
+
+    /* lzxd.c:465-523: read a block header.  Returns 0 or an MSPACK_ERR_* */
+    MS_M int block_header() {
+        if (block_type == 3 && (block_length & 1)) { (void) raw_byte(); if (b.err) return b.err; }     /* :469-474 */
+        enter_bits();
+        lzx_refill(b);
+        block_type = lzx_read(b, 3);
+        uint32_t i = lzx_read(b, 16);
+        lzx_refill(b);
+        uint32_t j = lzx_read(b, 8);
+        if (b.err) return b.err;
+        block_remaining = block_length = (i << 8) | j;
+        if (block_type == 2) {
+            uint32_t al = 0;
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) { lzx_refill(b); al |= lzx_read(b, 3) << (3 * k); }
+            if (b.err) return b.err;
+            aligned_lens = al;
+            int e = build_aligned(); if (e) return e;
+        }
+        if (block_type == 1 || block_type == 2) {
+            int e;
+            if ((e = read_lens(main_len, 0, 256))) return e;
+            if ((e = read_lens(main_len, 256, 256 + num_offsets))) return e;
+            if ((e = build_main())) return e;
+            if (main_len[0xE8 * 32] != 0) intel_started = 1;                                           /* :495 */
+            if ((e = read_lens(len_len, 0, 249))) return e;
+            if ((e = build_length())) return e;
+            return 0;
+        }
+        if (block_type == 3) {
+            intel_started = 1;                                                                         /* :503 */
+            /* :505-507 discard 1..16 bits up to the next 16-bit word */
+            int r = b.bc & 15;
+            if (r == 0) { lzx_refill(b); lzx_check(b, 16); if (b.err) return b.err; r = 16; }
+            msb_drop(b, r);
+            bytepos = b.ipos - (b.bc >> 3); bytemode = 1;
+            uint32_t v[3];
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) { uint32_t x = raw_byte(); x |= raw_byte() << 8; x |= raw_byte() << 16; x |= raw_byte() << 24; v[k] = x; }
+            if (b.err) return b.err;
+            R0 = v[0]; R1 = v[1]; R2 = v[2];
+            return 0;
+        }
+        return MS_EDECRUNCH;                                                                           /* :519-522 */
+    }
+
+    /* Decode one frame of frame_size bytes starting at unit position frame_start. */
+    MS_M int decode_frame(MsEmit &em, uint32_t frame_start, uint32_t frame_size) {
+        int32_t bytes_todo = (int32_t) frame_size;
+        uint32_t q = 0;
+#pragma unroll 1
+        while (bytes_todo > 0) {
+            if (block_remaining == 0) { int e = block_header(); if (e) return e; }
+            int32_t this_run = (int32_t) block_remaining;
+            if (this_run > bytes_todo) this_run = bytes_todo;
+            bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
+            if (block_type == 1 || block_type == 2) {
+                const bool aligned = (block_type == 2);
+#pragma unroll 1
+                while (this_run > 0) {
+                    lzx_refill(b);
+                    uint32_t sym = huffsym<MROOT>(mlut, ma, mmax);
+                    if (b.err) return b.err;
+                    if (sym < 256) { emit_literal(em, sym); q++; this_run--; continue; }
+                    sym -= 256;
+                    uint32_t ml = sym & 7, slot = sym >> 3, off;
+                    if (ml == 7) {
+                        if (length_empty) return MS_EDECRUNCH;                          /* :555-558 */
+                        ml += huffsym<LROOT>(llut, la, lmax);
+                        if (b.err) return b.err;
+                    }
+                    ml += 2;
+                    if (slot == 0) off = R0;
+                    else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
+                    else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
+                    else {
+                        /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
+                        uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                        uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                        off = pbase - 2;
+                        lzx_refill(b);
+                        if (aligned && extra >= 3) {
+                            if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
+                            off += huffsym<7>(alut, aa, amax);
+                        }
+                        else if (extra) off += lzx_read(b, (int) extra);
+                        if (b.err) return b.err;
+                        R2 = R1; R1 = R0; R0 = off;
+                    }
+                    /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame_start) */
+                    uint32_t G = frame_start + q, wpr = G & (window_size - 1), eff = off;
+                    if (wpr + ml > window_size) return MS_EDECRUNCH;
+                    if (off > wpr) {
+                        if (off > frame_start) return MS_EDECRUNCH;
+                        if (off - wpr > window_size) return MS_EDECRUNCH;
+                        if (off > window_size) eff = off - window_size;
+                    }
+                    if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
+                    if ((int32_t) ml > this_run) return MS_EDECRUNCH;                   /* :678-693 every overrun ends in an error */
+                    emit_match(em, q, ml, eff);
+                    q += ml; this_run -= (int32_t) ml;
+                }
+            }
+            else if (block_type == 3) {
+#pragma unroll 1
+                while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
+                if (b.err) return b.err;
+            }
+            else return MS_EDECRUNCH;
+        }
+        /* :696-697 re-align; after raw bytes the reference's bit buffer is empty and nothing happens */
+        if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) return b.err; msb_drop(b, b.bc & 15); }
+        return 0;
+    }
+};
+
+
+template <int NT, int MROOT, int LROOT>
+MS_D void p1_lzx_unit(LzxThread<NT, MROOT, LROOT> &t, const msgpu_unit &u, const uint8_t *in_base,
+                      MsUnitState &st, MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int32_t *e8info, int max_frames)
+{
+    const int wb = u.window_bits;
+    const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u : 50u;
+    t.window_size = 1u << (wb & 31); t.num_offsets = slots << 3;
+    t.nsyms_eff = 256 + t.num_offsets + 51; if (t.nsyms_eff > LZX_MAIN_MAX) t.nsyms_eff = LZX_MAIN_MAX;
+    if (!st.started) {
+        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
+        if (wb < 15 || wb > 21) { st.status = MS_ENOMEM; st.done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
+        lzx_bits_init(t.b, in_base + u.in_off, u.in_len);
+        t.base = 0; t.bytemode = 0; t.bytepos = 0; t.intel_filesize = 0; t.intel_started = 0; t.length_empty = 0; t.aligned_lens = 0;
+        t.mmax = t.lmax = t.pmax = t.amax = 16;
+        if (!st.done) t.reset_state();
+        if (u.out_len == 0) st.done = 1;
+    }
+    else {
+        t.base = st.base;
+        t.b.in = in_base + u.in_off + t.base; t.b.in_len = (int32_t) (u.in_len - t.base); t.b.err = 0;
+        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
+        t.bytemode = st.bytemode; t.bytepos = st.ipos;
+        t.R0 = st.R0; t.R1 = st.R1; t.R2 = st.R2; t.block_type = st.block_type; t.block_length = st.block_length;
+        t.block_remaining = st.block_remaining; t.header_read = st.header_read; t.intel_filesize = (int32_t) st.intel_filesize;
+        t.intel_started = st.intel_started; t.length_empty = st.length_empty; t.aligned_lens = st.aligned_lens;
+        if (!st.done && t.block_remaining > 0 && (t.block_type == 1 || t.block_type == 2)) {
+            /* the shared-memory tables do not survive a launch: rebuild them from the stored lengths */
+            (void) t.build_main(); (void) t.build_length();
+            if (t.block_type == 2) (void) t.build_aligned();
+        }
+    }
+#pragma unroll 1
+    for (int f = 0; f < max_frames; f++) {
+        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
+        if (!st.done) {
+            int err = 0;
+            uint32_t frame_start = st.produced;
+            if (u.reset_interval && (st.frame % u.reset_interval) == 0) t.reset_state();              /* :423-438 */
+            if (!t.header_read) {                                                                   /* :447-453 */
+                t.enter_bits();
+                lzx_refill(t.b);
+                uint32_t hi = 0, lo = 0;
+                if (lzx_read(t.b, 1)) { lzx_refill(t.b); hi = lzx_read(t.b, 16); lzx_refill(t.b); lo = lzx_read(t.b, 16); }
+                if (t.b.err) err = t.b.err;
+                t.intel_filesize = (int32_t) ((hi << 16) | lo); t.header_read = 1;
+            }
+            uint32_t frame_size = ms_min(MS_FRAME, u.out_len - frame_start);                         /* :458-461 */
+            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+            if (!err) err = t.decode_frame(em, frame_start, frame_size);
+            if (err) { st.status = err; st.done = 1; }
+            else {
+                emit_end(em, frame_size);
+                fi.nrec = em.nrec; fi.size = frame_size; fi.valid = 1;
+                e8info[st.frame] = (t.intel_started && t.intel_filesize && st.frame < 32768 && frame_size > 10) ? t.intel_filesize : 0;   /* :706-709 */
+                st.produced += frame_size; st.frame++;
+                if (st.produced >= u.out_len) {
+                    st.done = 1;
+                    /* lzxd.c:419: a request ending exactly on a frame boundary runs one more zero-sized frame
+                     * pass; at a reset point that re-reads the intel header and tops the bit buffer up (see
+                     * oracle/port/mspack_port.c) - the only effect is MSPACK_ERR_READ on an exactly-cut unit */
+                    if ((u.out_len % MS_FRAME) == 0 && u.reset_interval && (st.frame % u.reset_interval) == 0) {
+                        int32_t bp;
+                        if (t.bytemode) { if (t.bytepos & 1) { t.b.in += 1; t.b.in_len -= 1; t.bytepos -= 1; } bp = t.bytepos; }
+                        else bp = t.b.ipos - (t.b.bc >> 3);
+                        uint32_t hb = (bp + 1 < t.b.in_len) ? t.b.in[bp + 1] : 0u;
+                        int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
+                        if (bp + 2 > t.b.in_len + 2 || need > t.b.in_len + 2) st.status = MS_EREAD;
+                    }
+                }
+            }
+        }
+        finfo[f] = fi;
+    }
+    st.base = t.base; st.bytemode = t.bytemode;
+    st.ipos = t.bytemode ? t.bytepos : t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
+    st.R0 = t.R0; st.R1 = t.R1; st.R2 = t.R2; st.block_type = t.block_type; st.block_length = t.block_length;
+    st.block_remaining = t.block_remaining; st.header_read = t.header_read; st.intel_filesize = (uint32_t) t.intel_filesize;
+    st.intel_started = t.intel_started; st.length_empty = t.length_empty; st.aligned_lens = t.aligned_lens;
+}

@@ -1,0 +1,208 @@
+/* msgpu_p1_mszip.cuh - P1 entropy stage for MSZIP units: one thread inflates one unit's "CK" blocks
+ * (mszipd.c:154-316 inflate, :91-151 zip_read_lens, :377-460 mszipd_decompress) into literal bytes +
+ * match records.  Each CK block (<= 32 KiB of output) is one "frame" of the intermediate form.
+ */
+#pragma once
+#include "msgpu_core.cuh"
+
+/* per-warp auxiliary block in global scratch (interleaved by lane) */
+#define ZIP_AUX_LENS      0                              /* u8  [320][32]  literal/length + distance code lengths */
+#define ZIP_AUX_LSORT     (ZIP_AUX_LENS + 320 * 32)      /* u16 [288][32] */
+#define ZIP_AUX_DSORT     (ZIP_AUX_LSORT + 288 * 32 * 2) /* u16 [32][32]  */
+#define ZIP_AUX_BSORT     (ZIP_AUX_DSORT + 32 * 32 * 2)  /* u16 [32][32]  */
+#define ZIP_AUX_LIMIT     (ZIP_AUX_BSORT + 32 * 32 * 2)  /* u32 [3][20][32] */
+#define ZIP_AUX_OFFS      (ZIP_AUX_LIMIT + 3 * 20 * 32 * 4) /* u16 [3][20][32] */
+#define ZIP_AUX_BYTES     (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)
+
+template <int NT, int LROOT, int DROOT>
+struct ZipShared {
+    uint16_t llut[(1 << LROOT) * NT];
+    uint16_t dlut[(1 << DROOT) * NT];     /* also hosts the 7-bit code-length-code LUT while lengths are read (DROOT >= 7) */
+    uint16_t cnt[17 * NT];
+};
+
+template <int NT, int LROOT, int DROOT>
+struct ZipThread {
+    MsBits b;
+    uint16_t *llut, *dlut, *cnt;          /* this thread's column of the shared tables */
+    uint8_t *lens;                        /* aux, stride 32 */
+    MsHuffAux la, da, ba;
+    int lmax, dmax;
+
+    MS_M void bind(ZipShared<NT, LROOT, DROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
+        llut = sh->llut + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
+        lens = aux_warp + ZIP_AUX_LENS + lane;
+        la.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_LSORT) + lane;
+        da.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_DSORT) + lane;
+        ba.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_BSORT) + lane;
+        uint32_t *lim = reinterpret_cast<uint32_t *>(aux_warp + ZIP_AUX_LIMIT) + lane;
+        uint16_t *off = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_OFFS) + lane;
+        la.limit = lim; da.limit = lim + 20 * 32; ba.limit = lim + 40 * 32;
+        la.offs = off; da.offs = off + 20 * 32; ba.offs = off + 40 * 32;
+    }
+
+    /* READ_HUFFSYM (readhuff.h:39-46) on an LSB-first stream; caller refilled (>= 32 bits) */
+    template <int ROOT>
+    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, int maxlen) {
+        lsb_check(b, 16);
+        uint32_t e = lut[lsb_peek(b, ROOT) * NT];
+        int len = (int) (e & 15); uint32_t sym = e >> 4;
+        if (len == 0) sym = ms_huff_slow<ROOT>(MS_BREV32((uint32_t) b.bb) >> 16, aux, maxlen, &len);
+        lsb_drop(b, len);
+        return sym;
+    }
+
+    /* mszipd.c:91-151.  Returns 0 or an MSPACK_ERR_* */
+    MS_M int read_lens() {
+        const uint8_t order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+        lsb_refill(b);
+        uint32_t lit_codes = lsb_read(b, 5) + 257, dist_codes = lsb_read(b, 5) + 1, bl_codes = lsb_read(b, 4) + 4;
+        if (b.err) return b.err;
+        if (lit_codes > 288 || dist_codes > 32) return MS_EDECRUNCH;
+        /* 19 code-length-code lengths, 3 bits each, packed into a 64-bit register (never indexed dynamically in memory) */
+        uint64_t bl = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < bl_codes; i++) { lsb_refill(b); bl |= (uint64_t) lsb_read(b, 3) << (3 * order[i]); }
+        if (b.err) return b.err;
+        int blmax;
+        if (ms_huff_build<7, true, NT>([&](int s) { return (uint32_t) (bl >> (3 * s)) & 7u; }, 19, 7, dlut, ba, cnt, NT, &blmax)) return MS_EDECRUNCH;
+        uint32_t total = lit_codes + dist_codes, last_code = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < total;) {
+            lsb_refill(b);
+            lsb_check(b, 7);                                   /* :117 ENSURE_BITS(7) */
+            uint32_t e = dlut[lsb_peek(b, 7) * NT];
+            uint32_t code = e >> 4; lsb_drop(b, (int) (e & 15));
+            if (b.err) return b.err;
+            if (code < 16) { lens[i * 32] = (uint8_t) code; last_code = code; i++; }
+            else {
+                uint32_t run, val;
+                if (code == 16) { run = lsb_read(b, 2) + 3; val = last_code; }
+                else if (code == 17) { run = lsb_read(b, 3) + 3; val = 0; }
+                else if (code == 18) { run = lsb_read(b, 7) + 11; val = 0; }
+                else return MS_EDECRUNCH;
+                if (b.err) return b.err;
+                if (i + run > total) return MS_EDECRUNCH;      /* INF_ERR_BITOVERRUN */
+                while (run--) { lens[i * 32] = (uint8_t) val; i++; }
+            }
+        }
+        /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
+        uint8_t *l = lens;
+        if (ms_huff_build<LROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, llut, la, cnt, NT, &lmax)) return MS_EDECRUNCH;
+        if (ms_huff_build<DROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) dist_codes ? l[(lit_codes + s) * 32] : 0); }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
+        return 0;
+    }
+
+    /* mszipd.c:154-316: inflate one CK block into (lit, rec).  *out_bytes = bytes the block produced. */
+    MS_M int inflate(MsEmit &em, uint32_t *out_bytes) {
+        uint32_t q = 0, last_block;
+        do {
+            lsb_refill(b);
+            last_block = lsb_read(b, 1);
+            uint32_t type = lsb_read(b, 2);
+            if (b.err) return b.err;
+            if (type == 0) {
+                /* stored block :165-207 */
+                lsb_align_byte(b);
+                lsb_refill(b); uint32_t len = lsb_read(b, 16);
+                lsb_refill(b); uint32_t clen = lsb_read(b, 16);
+                if (b.err) return b.err;
+                if (len != (~clen & 0xFFFFu)) return MS_EDECRUNCH;
+#pragma unroll 1
+                for (uint32_t k = 0; k < len; k++) {
+                    lsb_refill(b);
+                    uint32_t v = lsb_read(b, 8);
+                    if (b.err) return b.err;
+                    if (q < MS_FRAME) emit_literal(em, v);
+                    if (++q >= 2 * MS_FRAME) return MS_EDECRUNCH;   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
+                }
+            }
+            else if (type == 1 || type == 2) {
+                if (type == 1) {
+                    /* fixed codes :212-220 */
+                    if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax)) return MS_EDECRUNCH;
+                    if (ms_huff_build<DROOT, true, NT>([](int) { return 5u; }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
+                }
+                else { int e = read_lens(); if (e) return e; }
+#pragma unroll 1
+                for (;;) {
+                    lsb_refill(b);
+                    uint32_t sym = huffsym<LROOT>(llut, la, lmax);
+                    if (b.err) return b.err;
+                    if (sym < 256) { if (q < MS_FRAME) emit_literal(em, sym); if (++q >= 2 * MS_FRAME) return MS_EDECRUNCH; }
+                    else if (sym == 256) break;
+                    else {
+                        uint32_t c = sym - 257, eb, length, dist;
+                        if (c >= 29) return MS_EDECRUNCH;                       /* :255 */
+                        if (c < 8) { eb = 0; length = c + 3; }                   /* lit_lengths / lit_extrabits, :47-62 */
+                        else if (c == 28) { eb = 0; length = 258; }
+                        else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
+                        if (eb) length += lsb_read(b, (int) eb);
+                        lsb_refill(b);
+                        uint32_t d = huffsym<DROOT>(dlut, da, dmax);
+                        if (b.err) return b.err;
+                        if (d >= 30) return MS_EDECRUNCH;                       /* :260 */
+                        if (d < 4) { eb = 0; dist = d + 1; }                     /* dist_offsets / dist_extrabits, :53-68 */
+                        else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
+                        if (eb) dist += lsb_read(b, (int) eb);
+                        if (b.err) return b.err;
+                        if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
+                        q += length;
+                        if (q >= 2 * MS_FRAME) return MS_EDECRUNCH;
+                    }
+                }
+            }
+            else return MS_EDECRUNCH;
+        } while (!last_block);
+        /* a block that grew past 32 KiB keeps being decoded by the reference (so a read error can still win)
+         * and only fails at its next window flush (:308-311, :323-333) */
+        if (q > MS_FRAME) return MS_EDECRUNCH;
+        *out_bytes = q;
+        return 0;
+    }
+};
+
+/* Advance one unit by up to `max_frames` CK blocks.  Shared by the CUDA kernel and the host
+ * emulation used in tests. */
+template <int NT, int LROOT, int DROOT>
+MS_D void p1_mszip_unit(ZipThread<NT, LROOT, DROOT> &t, const msgpu_unit &u, const uint8_t *in_base,
+                        MsUnitState &st, MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int max_frames)
+{
+    if (!st.started) {
+        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
+        lsb_init(t.b, in_base + u.in_off, u.in_len);
+        if (u.out_len == 0) st.done = 1;
+    }
+    else {
+        t.b.in = in_base + u.in_off; t.b.in_len = (int32_t) u.in_len; t.b.err = 0;
+        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
+    }
+#pragma unroll 1
+    for (int f = 0; f < max_frames; f++) {
+        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
+        if (!st.done) {
+            /* :405-413 align to a byte, skip to the next 'C','K' */
+            int err = 0, state = 0;
+            lsb_align_byte(t.b);
+            do {
+                lsb_refill(t.b);
+                uint32_t c = lsb_read(t.b, 8);
+                if (t.b.err) { err = t.b.err; break; }
+                if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
+            } while (state != 2);
+            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+            uint32_t produced = 0;
+            if (!err) err = t.inflate(em, &produced);
+            if (err) { st.status = err; st.done = 1; }
+            else {
+                uint32_t n = ms_min(u.out_len - st.produced, produced);
+                emit_end(em, produced);
+                fi.nrec = em.nrec; fi.size = n; fi.valid = 1;
+                st.produced += n; st.frame++;
+                if (st.produced >= u.out_len) st.done = 1;
+            }
+        }
+        finfo[f] = fi;
+    }
+    st.ipos = t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
+}

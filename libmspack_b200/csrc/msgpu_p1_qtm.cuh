@@ -1,0 +1,262 @@
+/* msgpu_p1_qtm.cuh - P1 entropy stage for Quantum units: one thread runs one unit's adaptive
+ * arithmetic decoder (qtmd.c:92-123 GET_SYMBOL, :125-166 qtmd_update_model, :257-479 qtmd_decompress)
+ * and emits literal bytes + match records per 32 KiB frame.  The nine frequency models live in shared
+ * memory, interleaved by thread.  Integer widths follow the reference: H, L, C and symf are 16-bit,
+ * range and the products are 32-bit unsigned.
+ */
+#pragma once
+#include "msgpu_core.cuh"
+
+#define QTM_ENT   401         /* 7+1, 4 x (64+1), 24+1, 36+1, 42+1, 27+1 model entries incl. sentinels */
+#define QM7   0
+#define QM0   8
+#define QM1   73
+#define QM2   138
+#define QM3   203
+#define QM4   268
+#define QM5   293
+#define QM6   330
+#define QM6L  373
+#define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8, padded */
+
+template <int NT>
+struct QtmShared {
+    uint16_t cum[QTM_ENT * NT];
+    uint8_t  sym[QTM_ENT * NT];
+    uint8_t  shl[9 * NT];
+};
+
+template <int NT>
+struct QtmThread {
+    MsBits b;
+    uint16_t *cum; uint8_t *sym, *shl;
+    uint32_t H, L, C;                 /* 16-bit values */
+    int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
+    int ent4, ent5, ent6;
+
+    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; sym = sh->sym + tid; shl = sh->shl + tid; }
+
+    MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182 */
+        shl[midx * NT] = 4;
+#pragma unroll 1
+        for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (len - i); }
+    }
+
+    /* READ_BYTES bookkeeping: two more bytes fetched; fails past in_len + 2 (readbits.h:192-214) */
+    MS_M void fetch2() { if (fp + 2 > b.in_len + 2) b.err = MS_EREAD; fp += 2; bl += 16; }
+
+    MS_M void update_model(int base, int midx, int entries) {             /* qtmd.c:125-166 */
+        uint32_t s = shl[midx * NT] - 1u;
+        if (s) {
+            shl[midx * NT] = (uint8_t) s;
+            uint32_t next = cum[(base + entries) * NT];
+#pragma unroll 1
+            for (int i = entries - 1; i >= 0; i--) {
+                uint32_t c = cum[(base + i) * NT] >> 1;
+                if (c <= next) c = next + 1;
+                cum[(base + i) * NT] = (uint16_t) c; next = c;
+            }
+        }
+        else {
+            shl[midx * NT] = 50;
+#pragma unroll 1
+            for (int i = 0; i < entries; i++) {
+                uint32_t c = (uint32_t) cum[(base + i) * NT] - cum[(base + i + 1) * NT];
+                c = (uint16_t) (c + 1); c >>= 1;
+                cum[(base + i) * NT] = (uint16_t) c;
+            }
+            /* the reference's in-place exchange sort; its (in)stability is part of the format (:148-150) */
+#pragma unroll 1
+            for (int i = 0; i < entries - 1; i++) {
+                uint32_t ci = cum[(base + i) * NT], si = sym[(base + i) * NT];
+#pragma unroll 1
+                for (int j = i + 1; j < entries; j++) {
+                    uint32_t cj = cum[(base + j) * NT];
+                    if (ci < cj) {
+                        uint32_t sj = sym[(base + j) * NT];
+                        cum[(base + j) * NT] = (uint16_t) ci; sym[(base + j) * NT] = (uint8_t) si;
+                        ci = cj; si = sj;
+                    }
+                }
+                cum[(base + i) * NT] = (uint16_t) ci; sym[(base + i) * NT] = (uint8_t) si;
+            }
+#pragma unroll 1
+            for (int i = entries - 1; i >= 0; i--) cum[(base + i) * NT] = (uint16_t) (cum[(base + i) * NT] + cum[(base + i + 1) * NT]);
+        }
+    }
+
+    /* GET_SYMBOL, qtmd.c:92-123.  The scan for the symbol and the "+8 to everything in front of it"
+     * update are one pass. */
+    MS_M uint32_t get_symbol(int base, int midx, int entries) {
+        uint32_t range = ((H - L) & 0xFFFFu) + 1u;
+        uint32_t c0 = cum[base * NT];
+        uint32_t symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
+        uint32_t prev = c0, cur; int i = 1;
+#pragma unroll 1
+        for (;; i++) {
+            cur = cum[(base + i) * NT];
+            if (i >= entries || cur <= symf) break;
+            cum[(base + i - 1) * NT] = (uint16_t) (prev + 8); prev = cur;
+        }
+        cum[(base + i - 1) * NT] = (uint16_t) (prev + 8);
+        uint32_t s = sym[(base + i - 1) * NT];
+        range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
+        uint32_t Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
+        uint32_t Ln = (L + (cur * range) / c0) & 0xFFFFu;
+        H = Hn; L = Ln;
+        if (((c0 + 8) & 0xFFFFu) > 3800) update_model(base, midx, entries);
+        qtm_refill(b);
+#pragma unroll 1
+        for (;;) {
+            if ((L & 0x8000u) != (H & 0x8000u)) {
+                if ((L & 0x4000u) && !(H & 0x4000u)) { C ^= 0x4000u; L &= 0x3FFFu; H |= 0x4000u; }
+                else break;
+            }
+            L = (L << 1) & 0xFFFFu; H = ((H << 1) | 1u) & 0xFFFFu;
+            if (bl < 1) fetch2();
+            bl -= 1;
+            if (b.bc < 1) qtm_refill(b);
+            C = ((C << 1) | msb_peek(b, 1)) & 0xFFFFu; msb_drop(b, 1);
+        }
+        return s;
+    }
+
+    MS_M uint32_t read_many(int n) {                                      /* READ_MANY_BITS, readbits.h:143-153 */
+        if (n == 0) return 0;
+        int needed = n;
+        while (needed > 0) { if (bl <= 16) fetch2(); int run = bl < needed ? bl : needed; bl -= run; needed -= run; }
+        qtm_refill(b);
+        uint32_t v = msb_peek(b, n); msb_drop(b, n);
+        return v;
+    }
+    MS_M uint32_t read_bits(int n) {                                      /* READ_BITS, 1 <= n <= 16 */
+        while (bl < n) fetch2();
+        bl -= n;
+        qtm_refill(b);
+        uint32_t v = msb_peek(b, n); msb_drop(b, n);
+        return v;
+    }
+
+    /* One frame.  limit = bytes of this frame the request still wants (<= frame_todo). */
+    MS_M int decode_frame(MsEmit &em, uint32_t frame_start, uint32_t limit, uint32_t &frame_todo, uint32_t window_size, uint32_t out_len) {
+        uint32_t q = 0;
+#pragma unroll 1
+        while (q < limit) {
+            uint32_t selector = get_symbol(QM7, 8, 7);
+            if (b.err) return b.err;
+            if (selector < 4) {
+                uint32_t s = get_symbol(QM0 + 65 * (int) selector, (int) selector, 64);
+                if (b.err) return b.err;
+                emit_literal(em, s); q++; frame_todo--;
+                continue;
+            }
+            uint32_t ml, off, s, extra;
+            if (selector == 4) { s = get_symbol(QM4, 4, ent4); ml = 3; }
+            else if (selector == 5) { s = get_symbol(QM5, 5, ent5); ml = 4; }
+            else if (selector == 6) {
+                s = get_symbol(QM6L, 7, 27);
+                if (b.err) return b.err;
+                /* length_base[] / length_extra[] (qtmd.c:76-83) in closed form */
+                uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
+                uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
+                extra = read_many((int) le);
+                ml = lb + extra + 5;
+                s = get_symbol(QM6, 6, ent6);
+            }
+            else return MS_EDECRUNCH;
+            if (b.err) return b.err;
+            {   /* position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
+                uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
+                uint32_t pb = s < 2 ? s : (2u + (s & 1)) << pe;
+                extra = read_many((int) pe);
+                off = pb + extra + 1;
+            }
+            if (b.err) return b.err;
+            uint32_t G = frame_start + q, window_posn = G & (window_size - 1);
+            if (ml > frame_todo) return MS_EDECRUNCH;                       /* :424-427 overshot frame alignment */
+            frame_todo -= ml;
+            if (window_posn + ml > window_size) {
+                /* :358-390 the reference flushes the whole window first and bails out if that is more than requested */
+                uint32_t lap_start = G - window_posn;
+                if ((uint64_t) lap_start + window_size > out_len) return MS_EDECRUNCH;
+            }
+            uint32_t emit_len = ml < limit - q ? ml : limit - q;
+            emit_match(em, q, emit_len, off);
+            q += ml;
+        }
+        return 0;
+    }
+};
+
+template <int NT>
+MS_D void p1_qtm_unit(QtmThread<NT> &t, const msgpu_unit &u, const uint8_t *in_base, MsUnitState &st,
+                      MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int max_frames, uint8_t *save = nullptr)
+{
+    const int wb = u.window_bits, wb2 = wb * 2;
+    t.ent4 = wb2 > 24 ? 24 : wb2; t.ent5 = wb2 > 36 ? 36 : wb2; t.ent6 = wb2;
+    uint32_t header_read = 0, frame_todo = MS_FRAME;
+    if (!st.started) {
+        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
+        qtm_bits_init(t.b, in_base + u.in_off, u.in_len);
+        t.H = 0; t.L = 0; t.C = 0; t.bl = 0; t.fp = 0;
+        if (wb < 10 || wb > 21) { st.status = MS_ENOMEM; st.done = 1; }      /* qtmd_init returns NULL */
+        else {
+            t.init_model(QM0, 0, 0, 64); t.init_model(QM1, 1, 64, 64); t.init_model(QM2, 2, 128, 64); t.init_model(QM3, 3, 192, 64);
+            t.init_model(QM4, 4, 0, t.ent4); t.init_model(QM5, 5, 0, t.ent5); t.init_model(QM6, 6, 0, t.ent6);
+            t.init_model(QM6L, 7, 0, 27); t.init_model(QM7, 8, 0, 7);
+        }
+        if (u.out_len == 0) st.done = 1;
+    }
+    else {
+        t.b.in = in_base + u.in_off; t.b.in_len = (int32_t) u.in_len; t.b.err = 0;
+        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
+        t.H = st.qH; t.L = st.qL; t.C = st.qC; t.bl = (int32_t) st.q_bl; t.fp = (int32_t) st.q_fp;
+        header_read = st.header_read; frame_todo = st.frame_todo;
+        if (save && !st.done) {
+#pragma unroll 1
+            for (int i = 0; i < QTM_ENT; i++) { t.cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; t.sym[i * NT] = save[QTM_ENT * 2 + i]; }
+#pragma unroll 1
+            for (int i = 0; i < 9; i++) t.shl[i * NT] = save[QTM_ENT * 3 + i];
+        }
+    }
+    const uint32_t window_size = 1u << (wb & 31);
+#pragma unroll 1
+    for (int f = 0; f < max_frames; f++) {
+        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
+        if (!st.done) {
+            int err = 0;
+            if (!header_read) {                                                /* qtmd.c:290-295 */
+                t.H = 0xFFFF; t.L = 0; t.C = t.read_bits(16);
+                if (t.b.err) err = t.b.err;
+                header_read = 1;
+            }
+            uint32_t frame_start = st.produced;
+            uint32_t limit = ms_min(frame_todo, u.out_len - frame_start);
+            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+            if (!err) err = t.decode_frame(em, frame_start, limit, frame_todo, window_size, u.out_len);
+            if (!err && frame_todo == 0) {                                     /* :430-442 re-align, then scan for the 0xFF trailer */
+                int r = t.bl & 7; t.bl -= r; msb_drop(t.b, t.b.bc & 7);
+                uint32_t c;
+                do { c = t.read_bits(8); if (t.b.err) { err = t.b.err; break; } } while (c != 0xFF);
+                header_read = 0; frame_todo = MS_FRAME;
+            }
+            if (err) { st.status = err; st.done = 1; }
+            else {
+                emit_end(em, limit);
+                fi.nrec = em.nrec; fi.size = limit; fi.valid = 1;
+                st.produced += limit; st.frame++;
+                if (st.produced >= u.out_len) st.done = 1;
+            }
+        }
+        finfo[f] = fi;
+    }
+    st.ipos = t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
+    st.qH = t.H; st.qL = t.L; st.qC = t.C; st.q_bl = (uint32_t) t.bl; st.q_fp = (uint32_t) t.fp;
+    st.header_read = header_read; st.frame_todo = frame_todo;
+    if (save && !st.done) {
+#pragma unroll 1
+        for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = t.cum[i * NT]; save[QTM_ENT * 2 + i] = t.sym[i * NT]; }
+#pragma unroll 1
+        for (int i = 0; i < 9; i++) save[QTM_ENT * 3 + i] = t.shl[i * NT];
+    }
+}

@@ -1,0 +1,108 @@
+/* emul.cpp - TEST-ONLY host emulation of the device code paths.
+ *
+ * Compiles libmspack_b200/csrc/*.cuh as plain C++ (MSGPU_EMULATE) and runs the SAME per-thread P1
+ * functions and per-lane P2 functions the CUDA kernels call, one unit at a time, so the decoder logic
+ * can be checked against the oracle on a machine without a GPU (`-m "not gpu"` tests).  It is not part of
+ * the product: libmspack_b200 never loads it, and the C-ABI library (libmsgpu.so) has no CPU path.
+ */
+#define MSGPU_EMULATE 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../libmspack_b200/csrc/msgpu_core.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p1_mszip.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p1_lzx.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p1_qtm.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p2.cuh"
+
+/* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks) */
+static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits, uint32_t size, uint8_t *unit_out, uint32_t g0) {
+    std::vector<uint32_t> wa(P2_WIN), wb(P2_WIN);
+    uint32_t wbase = 0, wcover = 0; bool loaded = false;
+    for (uint32_t c = 0; c < size; c += P2_CHUNK) {
+        if (!loaded || (c + P2_CHUNK > wcover && wcover < size)) {
+            if (loaded) wbase += (uint32_t) p2_search(wa.data(), wb.data(), c);
+            for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
+            wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
+        }
+        uint32_t w[32][4];
+        for (int lane = 0; lane < 32; lane++) p2_lane16(c + 16u * lane, c, size, wa.data(), wb.data(), lits, unit_out, g0, w[lane]);
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t q0 = c + 16u * lane;
+            for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+static void emul_e8_frame(uint8_t *data, uint32_t frame_size, int32_t curpos0, int32_t filesize) {
+    /* same candidate rule as e8_translate_frame: an E8 swallows the four bytes after it */
+    if (frame_size <= 10) return;
+    uint32_t end = frame_size - 10, next_ok = 0;
+    for (uint32_t p = 0; p < end; p++) {
+        if (data[p] != 0xE8 || p < next_ok) continue;
+        next_ok = p + 5;
+        int32_t curpos = curpos0 + (int32_t) p;
+        int32_t abs_off = (int32_t) ((uint32_t) data[p + 1] | ((uint32_t) data[p + 2] << 8) | ((uint32_t) data[p + 3] << 16) | ((uint32_t) data[p + 4] << 24));
+        if (abs_off >= -curpos && abs_off < filesize) {
+            int32_t rel = (abs_off >= 0) ? abs_off - curpos : abs_off + filesize;
+            data[p + 1] = (uint8_t) rel; data[p + 2] = (uint8_t) (rel >> 8); data[p + 3] = (uint8_t) (rel >> 16); data[p + 4] = (uint8_t) (rel >> 24);
+        }
+    }
+}
+
+extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
+    const int F = frames_per_round > 0 ? frames_per_round : 1;
+    std::vector<MsRec> recs((size_t) F * MS_MAXREC);
+    std::vector<uint8_t> lits((size_t) F * MS_LITCAP + 16);
+    std::vector<MsFrameInfo> finfo(F);
+    MsUnitState st; memset(&st, 0, sizeof(st));
+    uint8_t *unit_out = out_base + u->out_off;
+    uint32_t nframes_total = (u->out_len + MS_FRAME - 1) / MS_FRAME;
+    std::vector<int32_t> e8info(nframes_total + 2, 0);
+
+    if (u->codec == MSGPU_CODEC_MSZIP) {
+        typedef ZipShared<1, 9, 8> SH; typedef ZipThread<1, 9, 8> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
+        TH t; t.bind(sh, 0, aux, 0);
+        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
+            p1_mszip_unit<1, 9, 8>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
+                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        }
+        free(sh); free(aux);
+    }
+    else if (u->codec == MSGPU_CODEC_LZX) {
+        typedef LzxShared<1, 10, 8> SH; typedef LzxThread<1, 10, 8> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
+        TH t; t.bind(sh, 0, aux, 0);
+        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
+            p1_lzx_unit<1, 10, 8>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
+            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
+                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        }
+        for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
+            uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
+            if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) start, e8info[f]);
+        }
+        free(sh); free(aux);
+    }
+    else if (u->codec == MSGPU_CODEC_QUANTUM) {
+        typedef QtmShared<1> SH; typedef QtmThread<1> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH));
+        TH t; t.bind(sh, 0);
+        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
+            p1_qtm_unit<1>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
+                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        }
+        free(sh);
+    }
+    else return MS_EARGS;
+    return st.status;
+}
+
+extern "C" void emul_decode_batch(const msgpu_unit *units, size_t n, const uint8_t *in_base, uint8_t *out_base, int32_t *status, int frames_per_round) {
+    for (size_t i = 0; i < n; i++) status[i] = emul_decode_unit(&units[i], in_base, out_base, frames_per_round);
+}

@@ -1,0 +1,25 @@
+"""Quick device-resident timing of one codec batch (development aid; bench.py is the contract)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from libmspack_b200 import gen
+from libmspack_b200.codec import BatchDecoder
+
+codec = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+kw = {}
+if len(sys.argv) > 4:
+    kw = eval(sys.argv[4])
+t0 = time.time(); b = gen.make_batch(codec, n, keep_raw=(codec != 3 or True), **kw); tg = time.time() - t0
+dec = BatchDecoder(0)
+d_in = torch.from_numpy(b.comp).cuda(); d_out = torch.zeros(b.out_bytes, dtype=torch.uint8, device="cuda"); d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
+stream = torch.cuda.current_stream()
+best = 1e9
+for it in range(iters):
+    dec.decode_device(b.units, d_in, d_out, d_st, stream)
+    torch.cuda.synchronize()
+    ms = dec.last_kernel_ms(); best = min(best, ms)
+    print(f"iter {it}: kernels {ms:.3f} ms  -> {b.out_bytes/ms/1e6:.1f} GB/s out")
+ok = bool((d_st == 0).all().item()) and np.array_equal(d_out.cpu().numpy().reshape(n, -1)[:, :b.units['out_len'][0]].reshape(-1), b.raw)
+print(f"codec {codec} n {n} gen {tg:.1f}s ratio {b.in_bytes/(n*int(b.units['out_len'][0])):.3f} best {best:.3f} ms = {b.out_bytes/best/1e6:.1f} GB/s  roundtrip_ok={ok} launches={dec.launches} scratch={dec.scratch_bytes/2**30:.2f} GiB")
