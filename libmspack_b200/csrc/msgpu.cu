@@ -34,21 +34,40 @@ struct WaveArgs {
     int F;
 };
 
+/* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
+ * warp is guaranteed to be converged on the hot step() loop; lanes leave it together as soon as one of
+ * them needs service (a block header, a frame boundary) and come back once that is done. */
+template <class Lane>
+__device__ __forceinline__ void p1_run(Lane &t)
+{
+    for (;;) {
+        t.service();
+        if (!MS_BALLOT(t.phase == PH_DECODE)) break;
+        uint32_t need, dec;
+        do {
+            if (t.phase == PH_DECODE) t.step();
+            need = MS_BALLOT(t.phase >= PH_FRAME); dec = MS_BALLOT(t.phase == PH_DECODE);
+        } while (!need && dec);
+    }
+}
+
 template <int NT, int LROOT, int DROOT>
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = blockIdx.x * NT + threadIdx.x;
-    if (ti >= count) return;
-    uint32_t slot = order[ti];
-    ZipThread<NT, LROOT, DROOT> t;
-    t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
-    MsUnitState st = a.ustate[slot];
-    bool was_done = st.started && st.done;
-    p1_mszip_unit<NT, LROOT, DROOT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
-                                    a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, a.F);
-    if (!was_done) a.ustate[slot] = st;
-    if (!st.done) atomicAdd(a.not_done, 1u);
+    const bool valid = ti < count;
+    uint32_t slot = valid ? order[ti] : 0;
+    ZipLane<NT, LROOT, DROOT> t; t.phase = PH_IDLE;
+    MsUnitState st;
+    if (valid) {
+        t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
+        st = a.ustate[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+                a.finfo + (size_t) slot * a.F, a.F);
+    }
+    p1_run(t);
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
 }
 
 template <int NT, int MROOT, int LROOT>
@@ -57,16 +76,18 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = blockIdx.x * NT + threadIdx.x;
-    if (ti >= count) return;
-    uint32_t slot = order[ti];
-    LzxThread<NT, MROOT, LROOT> t;
-    t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
-    MsUnitState st = a.ustate[slot];
-    bool was_done = st.started && st.done;
-    p1_lzx_unit<NT, MROOT, LROOT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
-                                  a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
-    if (!was_done) a.ustate[slot] = st;
-    if (!st.done) atomicAdd(a.not_done, 1u);
+    const bool valid = ti < count;
+    uint32_t slot = valid ? order[ti] : 0;
+    LzxLane<NT, MROOT, LROOT> t; t.phase = PH_IDLE;
+    MsUnitState st;
+    if (valid) {
+        t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
+        st = a.ustate[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+                a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
+    }
+    p1_run(t);
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
 }
 
 template <int NT>
@@ -74,22 +95,25 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = blockIdx.x * NT + threadIdx.x;
-    if (ti >= count) return;
-    uint32_t slot = order[ti];
-    QtmThread<NT> t;
-    t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
-    MsUnitState st = a.ustate[slot];
-    bool was_done = st.started && st.done;
-    p1_qtm_unit<NT>(t, a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC,
-                    a.lits + (size_t) slot * a.F * MS_LITCAP, a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
-    if (!was_done) a.ustate[slot] = st;
-    if (!st.done) atomicAdd(a.not_done, 1u);
+    const bool valid = ti < count;
+    uint32_t slot = valid ? order[ti] : 0;
+    QtmLane<NT> t; t.phase = PH_IDLE;
+    MsUnitState st;
+    if (valid) {
+        t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
+        st = a.ustate[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+                a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
+    }
+    p1_run(t);
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
 }
 
 #define P2_WARPS 8
 __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
+    __shared__ uint16_t s_rid[P2_WARPS][P2_CHUNK];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t slot = blockIdx.x * P2_WARPS + warp;
     if (slot >= nslots) return;
@@ -98,7 +122,7 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, uint32
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
         p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
-                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp]);
+                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_rid[warp]);
     }
 }
 

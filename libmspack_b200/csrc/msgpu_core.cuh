@@ -29,6 +29,9 @@
 #define MS_DN __device__ __noinline__
 #define MS_BREV32(x) __brev(x)
 #define MS_CLZ(x) __clz(x)
+#define MS_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
+#define MS_SYNCWARP() __syncwarp()
+#define MS_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
 #define MS_D static inline
 #define MS_M inline
@@ -42,7 +45,19 @@ static inline uint32_t ms_brev32_host(uint32_t v) {
 }
 #define MS_BREV32(x) ms_brev32_host(x)
 #define MS_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#define MS_BALLOT(p) ((p) ? 1u : 0u)      /* emulation runs one lane at a time */
+#define MS_SYNCWARP() do { } while (0)
+#define MS_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
+
+/* lane phases of the warp-synchronous P1 state machines: every lane of a warp loops
+ *     service() -> [hot loop: step() while nobody needs service] -> service() ...
+ * with full-mask votes in between, so the 32 streams stay converged on the hot loop */
+#define PH_IDLE   0u      /* nothing (more) to do in this launch */
+#define PH_DECODE 1u      /* inside a Huffman / arithmetic coded run: step() */
+#define PH_FRAME  2u      /* start the next frame */
+#define PH_BLOCK  3u      /* read the next block header / continue the frame */
+#define PH_END    4u      /* finish the current frame */
 
 #define MS_FRAME      32768u
 #define MS_MAXREC     16400u     /* matches per frame <= 32768/2, + sentinel, padded            */
@@ -86,11 +101,13 @@ MS_D uint32_t ms_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
  * index >= in_len + 2 is MSPACK_ERR_READ.
  * ============================================================================================= */
 struct MsBits {
-    const uint8_t *in;      /* unit's first compressed byte (+ LZX base, see lzx_enter_bits)      */
+    const uint8_t *in;      /* unit's first compressed byte (+ LZX base, see LzxLane::enter_bits)  */
     int32_t in_len;         /* bytes available from `in`                                          */
-    int32_t ipos;           /* byte offset (from `in`) of the next 32-bit load                    */
+    int32_t ipos;           /* byte offset (from `in`) of the word held in nextw                  */
     int32_t bc;             /* valid bits in bb                                                   */
     uint64_t bb;
+    uint32_t nextw;         /* the 32-bit word at ipos, loaded one refill ahead of its use so that the load
+                             * latency overlaps a whole decode step instead of stalling it             */
     int32_t err;
 };
 
@@ -102,22 +119,25 @@ MS_D uint32_t ms_load32(const MsBits &b, int32_t ip) {
     for (int k = 0; k < 4; k++) { int32_t i = ip + k; if (i < b.in_len) v |= (uint32_t) p[k] << (8 * k); }
     return v;
 }
+/* (re)position the reader: the next stream bit is the first bit of the word at byte offset ip */
+MS_D void ms_bits_seek(MsBits &b, int32_t ip) { b.ipos = ip; b.bb = 0; b.bc = 0; b.nextw = ms_load32(b, ip); }
+MS_D void ms_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) { b.in = in; b.in_len = (int32_t) in_len; b.err = 0; ms_bits_seek(b, 0); }
+MS_D void ms_bits_restore(MsBits &b, const uint8_t *in, uint32_t in_len, int32_t ipos, int32_t bc, uint64_t bb) {
+    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = ipos; b.bc = bc; b.bb = bb; b.nextw = ms_load32(b, ipos);
+}
 
 /* bits consumed so far, relative to `in` */
 MS_D int64_t ms_bitpos(const MsBits &b) { return (int64_t) b.ipos * 8 - b.bc; }
 
 /* ---- LSB-first (MSZIP: readbits.h:161-166, mszipd.c:23-26).  Next bit = bit 0 of bb. ---- */
-MS_D void lsb_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
-    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
-}
 MS_D void lsb_refill(MsBits &b) {                 /* afterwards bc >= 32 */
-    if (b.bc < 32) { b.bb |= (uint64_t) ms_load32(b, b.ipos) << b.bc; b.ipos += 4; b.bc += 32; }
+    if (b.bc < 32) { b.bb |= (uint64_t) b.nextw << b.bc; b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
 MS_D uint32_t lsb_peek(const MsBits &b, int n) { return (uint32_t) b.bb & ((1u << n) - 1u); }
 MS_D void lsb_drop(MsBits &b, int n) { b.bb >>= n; b.bc -= n; }
 /* would the reference's ENSURE_BITS(n) at this position run past in_len + 2 bytes? */
 MS_D void lsb_check(MsBits &b, int n) {
-    if (b.ipos + 8 > b.in_len) { if (((int64_t) (b.ipos - b.in_len)) * 8 - b.bc + n > 16) b.err = MS_EREAD; }
+    if (MS_UNLIKELY(b.ipos + 8 > b.in_len)) { if (((int64_t) (b.ipos - b.in_len)) * 8 - b.bc + n > 16) b.err = MS_EREAD; }
 }
 MS_D uint32_t lsb_read(MsBits &b, int n) {        /* READ_BITS, 0 <= n <= 16; caller refilled */
     lsb_check(b, n);
@@ -128,17 +148,14 @@ MS_D void lsb_align_byte(MsBits &b) { int r = b.bc & 7; lsb_drop(b, r); }   /* b
 /* ---- MSB-first over 16-bit little-endian words (LZX: readbits.h:155-160, lzxd.c:86-91).
  *      Next bit = bit 63 of bb. ---- */
 MS_D uint32_t msb16le_swz(uint32_t x) { return (x << 16) | (x >> 16); }   /* two LE words -> 32 stream bits, first word on top */
-MS_D void lzx_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
-    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
-}
 MS_D void lzx_refill(MsBits &b) {                 /* afterwards bc >= 32 */
-    if (b.bc < 32) { b.bb |= (uint64_t) msb16le_swz(ms_load32(b, b.ipos)) << (32 - b.bc); b.ipos += 4; b.bc += 32; }
+    if (b.bc < 32) { b.bb |= (uint64_t) msb16le_swz(b.nextw) << (32 - b.bc); b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
 MS_D uint32_t msb_peek(const MsBits &b, int n) { return (uint32_t) (b.bb >> (64 - n)); }     /* 1 <= n <= 32 */
 MS_D void msb_drop(MsBits &b, int n) { b.bb <<= n; b.bc -= n; }
 /* ENSURE_BITS(n) fetches whole words: fails iff p + n > floor16(8 * (in_len + 2)) */
 MS_D void lzx_check(MsBits &b, int n) {
-    if (b.ipos + 8 > b.in_len) {
+    if (MS_UNLIKELY(b.ipos + 8 > b.in_len)) {
         int64_t x = ((int64_t) (b.in_len - b.ipos)) * 8 + 16 + b.bc - n;    /* 8(in_len+2) - (p+n) */
         if (x < ((b.in_len & 1) ? 8 : 0)) b.err = MS_EREAD;
     }
@@ -150,11 +167,8 @@ MS_D uint32_t lzx_read(MsBits &b, int n) {        /* READ_BITS, 1 <= n <= 17; ca
 
 /* ---- MSB-first plain big-endian bit stream (Quantum: qtmd.c:30-35) ---- */
 MS_D uint32_t ms_bswap32(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); }
-MS_D void qtm_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) {
-    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = 0; b.bb = 0; b.bc = 0;
-}
 MS_D void qtm_refill(MsBits &b) {
-    if (b.bc < 32) { b.bb |= (uint64_t) ms_bswap32(ms_load32(b, b.ipos)) << (32 - b.bc); b.ipos += 4; b.bc += 32; }
+    if (b.bc < 32) { b.bb |= (uint64_t) ms_bswap32(b.nextw) << (32 - b.bc); b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
 
 /* =============================================================================================
@@ -227,16 +241,25 @@ MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut,
     return 0;
 }
 
-/* slow path: v16 = next 16 stream bits, first bit in bit 15 */
+/* Codes longer than ROOT: per-length limits and sorted[] offsets held in REGISTERS (the P1 kernels are
+ * shared-memory bound at 128 threads per SM, so registers are free), the symbol itself comes from the
+ * canonical-order array in global scratch.  v16 = next 16 stream bits, first bit in bit 15. */
 template <int ROOT>
-MS_D uint32_t ms_huff_slow(uint32_t v16, const MsHuffAux &aux, int maxlen, int *len) {
-    int l = ROOT + 1;
-#pragma unroll 1
-    for (; l < maxlen; l++) if (v16 < aux.limit[l * MS_WARP]) break;
-    *len = l;
-    uint32_t idx = aux.offs[l * MS_WARP] + ((v16 - aux.limit[(l - 1) * MS_WARP]) >> (16 - l));
-    return aux.sorted[idx * MS_WARP];
-}
+struct MsHuffLong {
+    uint32_t lim[17 - ROOT];      /* lim[j] = limit[ROOT + j] */
+    uint32_t off[17 - ROOT];      /* off[j] = offs[ROOT + j]  */
+    MS_M void load(const MsHuffAux &aux) {
+#pragma unroll
+        for (int j = 0; j <= 16 - ROOT; j++) { lim[j] = aux.limit[(ROOT + j) * MS_WARP]; off[j] = aux.offs[(ROOT + j) * MS_WARP]; }
+    }
+    MS_M uint32_t decode(uint32_t v16, const MsHuffAux &aux, int *len) const {
+        int l = ROOT + 1; uint32_t base = lim[0], o = off[1];
+#pragma unroll
+        for (int j = 1; j < 16 - ROOT; j++) if (v16 >= lim[j]) { l = ROOT + j + 1; base = lim[j]; o = off[j + 1]; }
+        *len = l;
+        return aux.sorted[(o + ((v16 - base) >> (16 - l))) * MS_WARP];
+    }
+};
 
 /* =============================================================================================
  * Record / literal emission (P1 -> P2 intermediate form)

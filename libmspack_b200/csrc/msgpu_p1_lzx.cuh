@@ -1,4 +1,4 @@
-/* msgpu_p1_lzx.cuh - P1 entropy stage for LZX units: one thread walks one unit's bitstream
+/* msgpu_p1_lzx.cuh - P1 entropy stage for LZX units: one lane walks one unit's bitstream
  * (lzxd.c:388-771 lzxd_decompress, :138-183 lzxd_read_lens, :257-270 lzxd_reset_state) and emits
  * literal bytes + match records per 32 KiB frame.  Window-relative checks are restated for a
  * linear output buffer: the reference's window_posn is (bytes decoded) mod window_size and its
@@ -32,16 +32,22 @@ struct LzxShared {
 };
 
 template <int NT, int MROOT, int LROOT>
-struct LzxThread {
+struct LzxLane {
     MsBits b;
     uint16_t *mlut, *llut, *alut, *cnt;
     uint8_t *main_len, *len_len;
     MsHuffAux ma, la, pa, aa;
-    int mmax, lmax, pmax, amax;
+    MsHuffLong<MROOT> ml_long;
+    MsHuffLong<LROOT> ll_long, pl_long;
     uint32_t R0, R1, R2, block_type, block_length, block_remaining, header_read, intel_started, length_empty, aligned_lens;
     int32_t intel_filesize;
     uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
     int32_t bytepos;                      /* valid in bytemode: next raw byte (relative to b.in) */
+    /* unit / launch context */
+    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; int32_t *e8info;
+    MsEmit em;
+    uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
+    int f, max_frames;
 
     MS_M void bind(LzxShared<NT, MROOT, LROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
         mlut = sh->mlut + tid; llut = sh->llut + tid; alut = sh->alut + tid; cnt = sh->cnt + tid;
@@ -66,13 +72,19 @@ struct LzxThread {
 
     /* READ_HUFFSYM, MSB-first; caller guarantees >= 16 buffered bits */
     template <int ROOT>
-    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, int maxlen) {
+    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, const MsHuffLong<ROOT> &lg) {
         lzx_check(b, 16);
         uint32_t e = lut[msb_peek(b, ROOT) * NT];
         int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = ms_huff_slow<ROOT>(msb_peek(b, 16), aux, maxlen, &len);
+        if (len == 0) sym = lg.decode(msb_peek(b, 16), aux, &len);
         msb_drop(b, len);
         return sym;
+    }
+    MS_M uint32_t aligned_sym() {             /* 7-bit LUT covers every aligned-offset code (3-bit lengths) */
+        lzx_check(b, 16);
+        uint32_t e = alut[msb_peek(b, 7) * NT];
+        msb_drop(b, (int) (e & 15));
+        return e >> 4;
     }
 
     /* raw byte access for uncompressed blocks; READ_IF_NEEDED semantics (readbits.h:182-214) */
@@ -89,7 +101,7 @@ struct LzxThread {
     MS_M void enter_bits() {
         if (!bytemode) return;
         if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; }
-        b.ipos = bytepos & ~3; b.bb = 0; b.bc = 0;
+        ms_bits_seek(b, bytepos & ~3);
         lzx_refill(b);
         if (bytepos & 2) msb_drop(b, 16);
         bytemode = 0;
@@ -97,7 +109,7 @@ struct LzxThread {
 
     /* lzxd.c:138-183: pretree-delta coded lengths; runs are not clamped to `last` */
     MS_M int read_lens(uint8_t *lens, uint32_t first, uint32_t last) {
-        uint64_t plo = 0; uint32_t phi = 0;
+        uint64_t plo = 0; uint32_t phi = 0; int pmax;
 #pragma unroll 1
         for (int x = 0; x < 20; x++) {
             lzx_refill(b);
@@ -107,17 +119,18 @@ struct LzxThread {
         if (b.err) return b.err;
         if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
                                             20, 6, llut, pa, cnt, NT, &pmax)) return MS_EDECRUNCH;
+        pl_long.load(pa);
 #pragma unroll 1
         for (uint32_t x = first; x < last;) {
             lzx_refill(b);
-            int z = (int) huffsym<LROOT>(llut, pa, pmax);
+            int z = (int) huffsym<LROOT>(llut, pa, pl_long);
             if (b.err) return b.err;
             if (z == 17) { uint32_t y = lzx_read(b, 4) + 4; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
             else if (z == 18) { uint32_t y = lzx_read(b, 5) + 20; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
             else if (z == 19) {
                 uint32_t y = lzx_read(b, 1) + 4;
                 lzx_refill(b);
-                z = (int) huffsym<LROOT>(llut, pa, pmax);
+                z = (int) huffsym<LROOT>(llut, pa, pl_long);
                 if (b.err) return b.err;
                 z = (int) lens[x * 32] - z; if (z < 0) z += 17;
                 while (y--) { lens[x * 32] = (uint8_t) z; x++; }
@@ -128,21 +141,24 @@ struct LzxThread {
     }
 
     MS_M int build_main() {
-        uint8_t *l = main_len;
-        return ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax) ? MS_EDECRUNCH : 0;
+        uint8_t *l = main_len; int mmax;
+        if (ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax)) return MS_EDECRUNCH;
+        ml_long.load(ma);
+        return 0;
     }
     MS_M int build_length() {                 /* BUILD_TABLE_MAYBE_EMPTY, lzxd.c:111-125 */
-        uint8_t *l = len_len;
+        uint8_t *l = len_len; int lmax;
         length_empty = 0;
         if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, llut, la, cnt, NT, &lmax)) {
 #pragma unroll 1
             for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
             length_empty = 1;
         }
+        else ll_long.load(la);
         return 0;
     }
     MS_M int build_aligned() {
-        uint32_t al = aligned_lens;
+        uint32_t al = aligned_lens; int amax;
         return ms_huff_build<7, false, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, alut, aa, cnt, NT, &amax) ? MS_EDECRUNCH : 0;
     }
 
@@ -192,153 +208,164 @@ struct LzxThread {
         return MS_EDECRUNCH;                                                                           /* :519-522 */
     }
 
-    /* Decode one frame of frame_size bytes starting at unit position frame_start. */
-    MS_M int decode_frame(MsEmit &em, uint32_t frame_start, uint32_t frame_size) {
-        int32_t bytes_todo = (int32_t) frame_size;
-        uint32_t q = 0;
-#pragma unroll 1
-        while (bytes_todo > 0) {
-            if (block_remaining == 0) { int e = block_header(); if (e) return e; }
-            int32_t this_run = (int32_t) block_remaining;
-            if (this_run > bytes_todo) this_run = bytes_todo;
-            bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
-            if (block_type == 1 || block_type == 2) {
-                const bool aligned = (block_type == 2);
-#pragma unroll 1
-                while (this_run > 0) {
-                    lzx_refill(b);
-                    uint32_t sym = huffsym<MROOT>(mlut, ma, mmax);
-                    if (b.err) return b.err;
-                    if (sym < 256) { emit_literal(em, sym); q++; this_run--; continue; }
-                    sym -= 256;
-                    uint32_t ml = sym & 7, slot = sym >> 3, off;
-                    if (ml == 7) {
-                        if (length_empty) return MS_EDECRUNCH;                          /* :555-558 */
-                        ml += huffsym<LROOT>(llut, la, lmax);
-                        if (b.err) return b.err;
-                    }
-                    ml += 2;
-                    if (slot == 0) off = R0;
-                    else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
-                    else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
-                    else {
-                        /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
-                        uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
-                        uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
-                        off = pbase - 2;
-                        lzx_refill(b);
-                        if (aligned && extra >= 3) {
-                            if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
-                            off += huffsym<7>(alut, aa, amax);
-                        }
-                        else if (extra) off += lzx_read(b, (int) extra);
-                        if (b.err) return b.err;
-                        R2 = R1; R1 = R0; R0 = off;
-                    }
-                    /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame_start) */
-                    uint32_t G = frame_start + q, wpr = G & (window_size - 1), eff = off;
-                    if (wpr + ml > window_size) return MS_EDECRUNCH;
-                    if (off > wpr) {
-                        if (off > frame_start) return MS_EDECRUNCH;
-                        if (off - wpr > window_size) return MS_EDECRUNCH;
-                        if (off > window_size) eff = off - window_size;
-                    }
-                    if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
-                    if ((int32_t) ml > this_run) return MS_EDECRUNCH;                   /* :678-693 every overrun ends in an error */
-                    emit_match(em, q, ml, eff);
-                    q += ml; this_run -= (int32_t) ml;
-                }
-            }
-            else if (block_type == 3) {
-#pragma unroll 1
-                while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
-                if (b.err) return b.err;
-            }
-            else return MS_EDECRUNCH;
+    MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
+
+    /* lzxd.c:419-461: frame prologue (reset interval, intel header, frame size) */
+    MS_M void frame_start() {
+        frame_start_pos = produced;
+        if (u->reset_interval && (frame % u->reset_interval) == 0) reset_state();                     /* :423-438 */
+        if (!header_read) {                                                                          /* :447-453 */
+            enter_bits();
+            lzx_refill(b);
+            uint32_t hi = 0, lo = 0;
+            if (lzx_read(b, 1)) { lzx_refill(b); hi = lzx_read(b, 16); lzx_refill(b); lo = lzx_read(b, 16); }
+            if (b.err) { fail(b.err); return; }
+            intel_filesize = (int32_t) ((hi << 16) | lo); header_read = 1;
         }
+        frame_size = ms_min(MS_FRAME, u->out_len - produced);                                        /* :458-461 */
+        bytes_todo = (int32_t) frame_size; q = 0;
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        phase = PH_BLOCK;
+    }
+
+    /* lzxd.c:463-532 + :654-671: next run of the frame; uncompressed runs are copied right here */
+    MS_M void next_run() {
+        if (bytes_todo <= 0) { phase = PH_END; return; }
+        if (block_remaining == 0) { int e = block_header(); if (e) { fail(e); return; } }
+        this_run = (int32_t) block_remaining;
+        if (this_run > bytes_todo) this_run = bytes_todo;
+        bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
+        if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
+        if (block_type == 3) {
+#pragma unroll 1
+            while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
+            if (b.err) fail(b.err);
+            return;
+        }
+        fail(MS_EDECRUNCH);
+    }
+
+    MS_M void frame_end() {
         /* :696-697 re-align; after raw bytes the reference's bit buffer is empty and nothing happens */
-        if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) return b.err; msb_drop(b, b.bc & 15); }
-        return 0;
+        if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) { fail(b.err); return; } msb_drop(b, b.bc & 15); }
+        emit_end(em, frame_size);
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = frame_size; fi.g0 = frame_start_pos; fi.valid = 1;
+        finfo[f] = fi;
+        e8info[frame] = (intel_started && intel_filesize && frame < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 */
+        produced += frame_size; frame++; f++;
+        if (produced >= u->out_len) {
+            done = 1; phase = PH_IDLE;
+            /* lzxd.c:419: a request ending exactly on a frame boundary runs one more zero-sized frame pass; at a
+             * reset point that re-reads the intel header and tops the bit buffer up (see oracle/port/mspack_port.c) -
+             * the only effect is MSPACK_ERR_READ on an exactly-cut unit */
+            if ((u->out_len % MS_FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
+                int32_t bp;
+                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; } bp = bytepos; }
+                else bp = b.ipos - (b.bc >> 3);
+                uint32_t hb = (bp + 1 < b.in_len) ? b.in[bp + 1] : 0u;
+                int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
+                if (bp + 2 > b.in_len + 2 || need > b.in_len + 2) status = MS_EREAD;
+            }
+        }
+        else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+    }
+
+    MS_M void service() {
+#pragma unroll 1
+        while (phase >= PH_FRAME) {
+            if (phase == PH_FRAME) frame_start();
+            else if (phase == PH_BLOCK) next_run();
+            else frame_end();
+        }
+    }
+
+    /* the hot step (lzxd.c:538-651): one main-tree symbol; a match also takes its length / offset fields */
+    MS_M void step() {
+        lzx_refill(b);
+        uint32_t sym = huffsym<MROOT>(mlut, ma, ml_long);
+        if (sym < 256) { emit_literal(em, sym); q++; this_run--; }
+        else {
+            sym -= 256;
+            uint32_t ml = sym & 7, slot = sym >> 3, off;
+            if (ml == 7) {
+                if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
+                ml += huffsym<LROOT>(llut, la, ll_long);
+            }
+            ml += 2;
+            if (slot == 0) off = R0;
+            else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
+            else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
+            else {
+                /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
+                uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                off = pbase - 2;
+                lzx_refill(b);
+                if (block_type == 2 && extra >= 3) {
+                    if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
+                    off += aligned_sym();
+                }
+                else if (extra) off += lzx_read(b, (int) extra);
+                R2 = R1; R1 = R0; R0 = off;
+            }
+            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start) */
+            uint32_t G = frame_start_pos + q, wpr = G & (window_size - 1), eff = off;
+            bool bad = (wpr + ml > window_size);
+            if (off > wpr) {
+                bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
+                if (off > window_size) eff = off - window_size;
+            }
+            if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
+            bad = bad || ((int32_t) ml > this_run);   /* :678-693 every overrun ends in an error */
+            if (MS_UNLIKELY(bad)) { fail(MS_EDECRUNCH); return; }
+            emit_match(em, q, ml, eff);
+            q += ml; this_run -= (int32_t) ml;
+        }
+        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (this_run <= 0) phase = PH_BLOCK;
+    }
+
+    MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
+                    int32_t *e8, int nframes) {
+        u = unit; recs = r; lits = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;
+        frame_start_pos = 0; frame_size = 0;
+#pragma unroll 1
+        for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
+        const int wb = unit->window_bits;
+        const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u : 50u;   /* position_slots[], lzxd.c:209-211 */
+        window_size = 1u << (wb & 31); num_offsets = slots << 3;
+        nsyms_eff = 256 + num_offsets + 51; if (nsyms_eff > LZX_MAIN_MAX) nsyms_eff = LZX_MAIN_MAX;
+        if (!st.started) {
+            done = 0; status = 0; produced = 0; frame = 0;
+            if (wb < 15 || wb > 21) { status = MS_ENOMEM; done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
+            ms_bits_init(b, in_base + unit->in_off, unit->in_len);
+            base = 0; bytemode = 0; bytepos = 0; intel_filesize = 0; intel_started = 0; length_empty = 0; aligned_lens = 0;
+            R0 = R1 = R2 = 1; header_read = 0; block_remaining = 0; block_type = 0; block_length = 0;
+            if (!done) reset_state();
+            if (unit->out_len == 0) done = 1;
+        }
+        else {
+            done = st.done; status = st.status; produced = st.produced; frame = st.frame;
+            base = st.base; bytemode = st.bytemode; bytepos = st.ipos;
+            ms_bits_restore(b, in_base + unit->in_off + base, unit->in_len - base, bytemode ? 0 : st.ipos, (int32_t) st.bc, ((uint64_t) st.bb_hi << 32) | st.bb_lo);
+            R0 = st.R0; R1 = st.R1; R2 = st.R2; block_type = st.block_type; block_length = st.block_length;
+            block_remaining = st.block_remaining; header_read = st.header_read; intel_filesize = (int32_t) st.intel_filesize;
+            intel_started = st.intel_started; length_empty = st.length_empty; aligned_lens = st.aligned_lens;
+            if (!done && block_remaining > 0 && (block_type == 1 || block_type == 2)) {
+                /* the shared-memory tables do not survive a launch: rebuild them from the stored lengths */
+                (void) build_main(); (void) build_length();
+                if (block_type == 2) (void) build_aligned();
+            }
+        }
+        phase = done ? PH_IDLE : PH_FRAME;
+    }
+    MS_M void end(MsUnitState &st) {
+        st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
+        st.base = base; st.bytemode = bytemode;
+        st.ipos = bytemode ? bytepos : b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
+        st.R0 = R0; st.R1 = R1; st.R2 = R2; st.block_type = block_type; st.block_length = block_length;
+        st.block_remaining = block_remaining; st.header_read = header_read; st.intel_filesize = (uint32_t) intel_filesize;
+        st.intel_started = intel_started; st.length_empty = length_empty; st.aligned_lens = aligned_lens;
     }
 };
-
-
-template <int NT, int MROOT, int LROOT>
-MS_D void p1_lzx_unit(LzxThread<NT, MROOT, LROOT> &t, const msgpu_unit &u, const uint8_t *in_base,
-                      MsUnitState &st, MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int32_t *e8info, int max_frames)
-{
-    const int wb = u.window_bits;
-    const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u : 50u;
-    t.window_size = 1u << (wb & 31); t.num_offsets = slots << 3;
-    t.nsyms_eff = 256 + t.num_offsets + 51; if (t.nsyms_eff > LZX_MAIN_MAX) t.nsyms_eff = LZX_MAIN_MAX;
-    if (!st.started) {
-        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
-        if (wb < 15 || wb > 21) { st.status = MS_ENOMEM; st.done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
-        lzx_bits_init(t.b, in_base + u.in_off, u.in_len);
-        t.base = 0; t.bytemode = 0; t.bytepos = 0; t.intel_filesize = 0; t.intel_started = 0; t.length_empty = 0; t.aligned_lens = 0;
-        t.mmax = t.lmax = t.pmax = t.amax = 16;
-        if (!st.done) t.reset_state();
-        if (u.out_len == 0) st.done = 1;
-    }
-    else {
-        t.base = st.base;
-        t.b.in = in_base + u.in_off + t.base; t.b.in_len = (int32_t) (u.in_len - t.base); t.b.err = 0;
-        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
-        t.bytemode = st.bytemode; t.bytepos = st.ipos;
-        t.R0 = st.R0; t.R1 = st.R1; t.R2 = st.R2; t.block_type = st.block_type; t.block_length = st.block_length;
-        t.block_remaining = st.block_remaining; t.header_read = st.header_read; t.intel_filesize = (int32_t) st.intel_filesize;
-        t.intel_started = st.intel_started; t.length_empty = st.length_empty; t.aligned_lens = st.aligned_lens;
-        if (!st.done && t.block_remaining > 0 && (t.block_type == 1 || t.block_type == 2)) {
-            /* the shared-memory tables do not survive a launch: rebuild them from the stored lengths */
-            (void) t.build_main(); (void) t.build_length();
-            if (t.block_type == 2) (void) t.build_aligned();
-        }
-    }
-#pragma unroll 1
-    for (int f = 0; f < max_frames; f++) {
-        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
-        if (!st.done) {
-            int err = 0;
-            uint32_t frame_start = st.produced;
-            if (u.reset_interval && (st.frame % u.reset_interval) == 0) t.reset_state();              /* :423-438 */
-            if (!t.header_read) {                                                                   /* :447-453 */
-                t.enter_bits();
-                lzx_refill(t.b);
-                uint32_t hi = 0, lo = 0;
-                if (lzx_read(t.b, 1)) { lzx_refill(t.b); hi = lzx_read(t.b, 16); lzx_refill(t.b); lo = lzx_read(t.b, 16); }
-                if (t.b.err) err = t.b.err;
-                t.intel_filesize = (int32_t) ((hi << 16) | lo); t.header_read = 1;
-            }
-            uint32_t frame_size = ms_min(MS_FRAME, u.out_len - frame_start);                         /* :458-461 */
-            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
-            if (!err) err = t.decode_frame(em, frame_start, frame_size);
-            if (err) { st.status = err; st.done = 1; }
-            else {
-                emit_end(em, frame_size);
-                fi.nrec = em.nrec; fi.size = frame_size; fi.valid = 1;
-                e8info[st.frame] = (t.intel_started && t.intel_filesize && st.frame < 32768 && frame_size > 10) ? t.intel_filesize : 0;   /* :706-709 */
-                st.produced += frame_size; st.frame++;
-                if (st.produced >= u.out_len) {
-                    st.done = 1;
-                    /* lzxd.c:419: a request ending exactly on a frame boundary runs one more zero-sized frame
-                     * pass; at a reset point that re-reads the intel header and tops the bit buffer up (see
-                     * oracle/port/mspack_port.c) - the only effect is MSPACK_ERR_READ on an exactly-cut unit */
-                    if ((u.out_len % MS_FRAME) == 0 && u.reset_interval && (st.frame % u.reset_interval) == 0) {
-                        int32_t bp;
-                        if (t.bytemode) { if (t.bytepos & 1) { t.b.in += 1; t.b.in_len -= 1; t.bytepos -= 1; } bp = t.bytepos; }
-                        else bp = t.b.ipos - (t.b.bc >> 3);
-                        uint32_t hb = (bp + 1 < t.b.in_len) ? t.b.in[bp + 1] : 0u;
-                        int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
-                        if (bp + 2 > t.b.in_len + 2 || need > t.b.in_len + 2) st.status = MS_EREAD;
-                    }
-                }
-            }
-        }
-        finfo[f] = fi;
-    }
-    st.base = t.base; st.bytemode = t.bytemode;
-    st.ipos = t.bytemode ? t.bytepos : t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
-    st.R0 = t.R0; st.R1 = t.R1; st.R2 = t.R2; st.block_type = t.block_type; st.block_length = t.block_length;
-    st.block_remaining = t.block_remaining; st.header_read = t.header_read; st.intel_filesize = (uint32_t) t.intel_filesize;
-    st.intel_started = t.intel_started; st.length_empty = t.length_empty; st.aligned_lens = t.aligned_lens;
-}

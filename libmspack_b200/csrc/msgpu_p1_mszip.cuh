@@ -1,6 +1,11 @@
-/* msgpu_p1_mszip.cuh - P1 entropy stage for MSZIP units: one thread inflates one unit's "CK" blocks
+/* msgpu_p1_mszip.cuh - P1 entropy stage for MSZIP units: one lane inflates one unit's "CK" blocks
  * (mszipd.c:154-316 inflate, :91-151 zip_read_lens, :377-460 mszipd_decompress) into literal bytes +
  * match records.  Each CK block (<= 32 KiB of output) is one "frame" of the intermediate form.
+ *
+ * The lane is a state machine (phases in msgpu_core.cuh): service() does the rare, divergent work
+ * (CK signature scan, deflate block headers, code-length tables, stored blocks, frame bookkeeping);
+ * step() decodes ONE literal/length symbol (plus its distance) and is what the warp executes in
+ * lockstep.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -22,12 +27,18 @@ struct ZipShared {
 };
 
 template <int NT, int LROOT, int DROOT>
-struct ZipThread {
+struct ZipLane {
     MsBits b;
-    uint16_t *llut, *dlut, *cnt;          /* this thread's column of the shared tables */
+    uint16_t *llut, *dlut, *cnt;          /* this lane's column of the shared tables */
     uint8_t *lens;                        /* aux, stride 32 */
     MsHuffAux la, da, ba;
-    int lmax, dmax;
+    MsHuffLong<LROOT> ll;
+    MsHuffLong<DROOT> dl;
+    /* unit / launch context */
+    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo;
+    MsEmit em;
+    uint32_t phase, q, last_block, produced, frame, done; int32_t status;
+    int f, max_frames;
 
     MS_M void bind(ZipShared<NT, LROOT, DROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
         llut = sh->llut + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
@@ -43,11 +54,11 @@ struct ZipThread {
 
     /* READ_HUFFSYM (readhuff.h:39-46) on an LSB-first stream; caller refilled (>= 32 bits) */
     template <int ROOT>
-    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, int maxlen) {
+    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, const MsHuffLong<ROOT> &lg) {
         lsb_check(b, 16);
         uint32_t e = lut[lsb_peek(b, ROOT) * NT];
         int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = ms_huff_slow<ROOT>(MS_BREV32((uint32_t) b.bb) >> 16, aux, maxlen, &len);
+        if (len == 0) sym = lg.decode(MS_BREV32((uint32_t) b.bb) >> 16, aux, &len);
         lsb_drop(b, len);
         return sym;
     }
@@ -59,7 +70,7 @@ struct ZipThread {
         uint32_t lit_codes = lsb_read(b, 5) + 257, dist_codes = lsb_read(b, 5) + 1, bl_codes = lsb_read(b, 4) + 4;
         if (b.err) return b.err;
         if (lit_codes > 288 || dist_codes > 32) return MS_EDECRUNCH;
-        /* 19 code-length-code lengths, 3 bits each, packed into a 64-bit register (never indexed dynamically in memory) */
+        /* 19 code-length-code lengths, 3 bits each, packed into a 64-bit register */
         uint64_t bl = 0;
 #pragma unroll 1
         for (uint32_t i = 0; i < bl_codes; i++) { lsb_refill(b); bl |= (uint64_t) lsb_read(b, 3) << (3 * order[i]); }
@@ -87,122 +98,138 @@ struct ZipThread {
             }
         }
         /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
-        uint8_t *l = lens;
+        uint8_t *l = lens; int lmax, dmax;
         if (ms_huff_build<LROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, llut, la, cnt, NT, &lmax)) return MS_EDECRUNCH;
         if (ms_huff_build<DROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) dist_codes ? l[(lit_codes + s) * 32] : 0); }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
         return 0;
     }
 
-    /* mszipd.c:154-316: inflate one CK block into (lit, rec).  *out_bytes = bytes the block produced. */
-    MS_M int inflate(MsEmit &em, uint32_t *out_bytes) {
-        uint32_t q = 0, last_block;
+    MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
+
+    /* mszipd.c:159-241: one deflate block header.  Stored blocks are copied right here. */
+    MS_M void block_header() {
+        lsb_refill(b);
+        last_block = lsb_read(b, 1);
+        uint32_t type = lsb_read(b, 2);
+        if (b.err) { fail(b.err); return; }
+        if (type == 0) {
+            /* stored block :165-207 */
+            lsb_align_byte(b);
+            lsb_refill(b); uint32_t len = lsb_read(b, 16);
+            lsb_refill(b); uint32_t clen = lsb_read(b, 16);
+            if (b.err) { fail(b.err); return; }
+            if (len != (~clen & 0xFFFFu)) { fail(MS_EDECRUNCH); return; }
+#pragma unroll 1
+            for (uint32_t k = 0; k < len; k++) {
+                lsb_refill(b);
+                uint32_t v = lsb_read(b, 8);
+                if (b.err) { fail(b.err); return; }
+                if (q < MS_FRAME) emit_literal(em, v);
+                if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
+            }
+            phase = last_block ? PH_END : PH_BLOCK;
+            return;
+        }
+        if (type == 3) { fail(MS_EDECRUNCH); return; }
+        int e = 0;
+        if (type == 1) {
+            /* fixed codes :212-220 */
+            int lmax, dmax;
+            if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax)) e = MS_EDECRUNCH;
+            else if (ms_huff_build<DROOT, true, NT>([](int) { return 5u; }, 32, 6, dlut, da, cnt, NT, &dmax)) e = MS_EDECRUNCH;
+        }
+        else e = read_lens();
+        if (e) { fail(e); return; }
+        ll.load(la); dl.load(da);
+        phase = PH_DECODE;
+    }
+
+    /* :405-413 align to a byte, skip to the next 'C','K'; then the frame's emit state */
+    MS_M void frame_start() {
+        int state = 0;
+        lsb_align_byte(b);
         do {
             lsb_refill(b);
-            last_block = lsb_read(b, 1);
-            uint32_t type = lsb_read(b, 2);
-            if (b.err) return b.err;
-            if (type == 0) {
-                /* stored block :165-207 */
-                lsb_align_byte(b);
-                lsb_refill(b); uint32_t len = lsb_read(b, 16);
-                lsb_refill(b); uint32_t clen = lsb_read(b, 16);
-                if (b.err) return b.err;
-                if (len != (~clen & 0xFFFFu)) return MS_EDECRUNCH;
-#pragma unroll 1
-                for (uint32_t k = 0; k < len; k++) {
-                    lsb_refill(b);
-                    uint32_t v = lsb_read(b, 8);
-                    if (b.err) return b.err;
-                    if (q < MS_FRAME) emit_literal(em, v);
-                    if (++q >= 2 * MS_FRAME) return MS_EDECRUNCH;   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
-                }
-            }
-            else if (type == 1 || type == 2) {
-                if (type == 1) {
-                    /* fixed codes :212-220 */
-                    if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax)) return MS_EDECRUNCH;
-                    if (ms_huff_build<DROOT, true, NT>([](int) { return 5u; }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
-                }
-                else { int e = read_lens(); if (e) return e; }
-#pragma unroll 1
-                for (;;) {
-                    lsb_refill(b);
-                    uint32_t sym = huffsym<LROOT>(llut, la, lmax);
-                    if (b.err) return b.err;
-                    if (sym < 256) { if (q < MS_FRAME) emit_literal(em, sym); if (++q >= 2 * MS_FRAME) return MS_EDECRUNCH; }
-                    else if (sym == 256) break;
-                    else {
-                        uint32_t c = sym - 257, eb, length, dist;
-                        if (c >= 29) return MS_EDECRUNCH;                       /* :255 */
-                        if (c < 8) { eb = 0; length = c + 3; }                   /* lit_lengths / lit_extrabits, :47-62 */
-                        else if (c == 28) { eb = 0; length = 258; }
-                        else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
-                        if (eb) length += lsb_read(b, (int) eb);
-                        lsb_refill(b);
-                        uint32_t d = huffsym<DROOT>(dlut, da, dmax);
-                        if (b.err) return b.err;
-                        if (d >= 30) return MS_EDECRUNCH;                       /* :260 */
-                        if (d < 4) { eb = 0; dist = d + 1; }                     /* dist_offsets / dist_extrabits, :53-68 */
-                        else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
-                        if (eb) dist += lsb_read(b, (int) eb);
-                        if (b.err) return b.err;
-                        if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
-                        q += length;
-                        if (q >= 2 * MS_FRAME) return MS_EDECRUNCH;
-                    }
-                }
-            }
-            else return MS_EDECRUNCH;
-        } while (!last_block);
+            uint32_t c = lsb_read(b, 8);
+            if (b.err) { fail(b.err); return; }
+            if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
+        } while (state != 2);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        q = 0;
+        phase = PH_BLOCK;
+    }
+
+    MS_M void frame_end() {
         /* a block that grew past 32 KiB keeps being decoded by the reference (so a read error can still win)
          * and only fails at its next window flush (:308-311, :323-333) */
-        if (q > MS_FRAME) return MS_EDECRUNCH;
-        *out_bytes = q;
-        return 0;
+        if (q > MS_FRAME) { fail(MS_EDECRUNCH); return; }
+        uint32_t n = ms_min(u->out_len - produced, q);
+        emit_end(em, q);
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced; fi.valid = 1;
+        finfo[f] = fi;
+        produced += n; frame++; f++;
+        if (produced >= u->out_len) { done = 1; phase = PH_IDLE; }
+        else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+    }
+
+    /* the rare, divergent work: run until the lane is decoding symbols or has nothing left to do */
+    MS_M void service() {
+#pragma unroll 1
+        while (phase >= PH_FRAME) {
+            if (phase == PH_FRAME) frame_start();
+            else if (phase == PH_BLOCK) block_header();
+            else frame_end();
+        }
+    }
+
+    /* the hot step: one literal/length symbol, plus the distance of a match (mszipd.c:243-300) */
+    MS_M void step() {
+        lsb_refill(b);
+        uint32_t sym = huffsym<LROOT>(llut, la, ll);
+        if (sym < 256) {
+            if (q < MS_FRAME) emit_literal(em, sym);
+            q++;
+        }
+        else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
+        else {
+            uint32_t c = sym - 257, eb, length, dist;
+            if (c >= 29) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :255 */
+            if (c < 8) { eb = 0; length = c + 3; }                             /* lit_lengths / lit_extrabits, :47-62 */
+            else if (c == 28) { eb = 0; length = 258; }
+            else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
+            if (eb) length += lsb_read(b, (int) eb);
+            if (b.err) { fail(b.err); return; }
+            lsb_refill(b);
+            uint32_t d = huffsym<DROOT>(dlut, da, dl);
+            if (d >= 30) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :260 */
+            if (d < 4) { eb = 0; dist = d + 1; }                               /* dist_offsets / dist_extrabits, :53-68 */
+            else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
+            if (eb) dist += lsb_read(b, (int) eb);
+            if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
+            q += length;
+        }
+        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (MS_UNLIKELY(q >= 2 * MS_FRAME)) fail(MS_EDECRUNCH);
+    }
+
+    /* load the unit's state for this launch */
+    MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi, int nframes) {
+        u = unit; recs = r; lits = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
+#pragma unroll 1
+        for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
+        if (!st.started) {
+            done = 0; status = 0; produced = 0; frame = 0;
+            ms_bits_init(b, in_base + unit->in_off, unit->in_len);
+            if (unit->out_len == 0) done = 1;
+        }
+        else {
+            done = st.done; status = st.status; produced = st.produced; frame = st.frame;
+            ms_bits_restore(b, in_base + unit->in_off, unit->in_len, st.ipos, (int32_t) st.bc, ((uint64_t) st.bb_hi << 32) | st.bb_lo);
+        }
+        phase = done ? PH_IDLE : PH_FRAME;
+    }
+    MS_M void end(MsUnitState &st) {
+        st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
+        st.ipos = b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
     }
 };
-
-/* Advance one unit by up to `max_frames` CK blocks.  Shared by the CUDA kernel and the host
- * emulation used in tests. */
-template <int NT, int LROOT, int DROOT>
-MS_D void p1_mszip_unit(ZipThread<NT, LROOT, DROOT> &t, const msgpu_unit &u, const uint8_t *in_base,
-                        MsUnitState &st, MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int max_frames)
-{
-    if (!st.started) {
-        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
-        lsb_init(t.b, in_base + u.in_off, u.in_len);
-        if (u.out_len == 0) st.done = 1;
-    }
-    else {
-        t.b.in = in_base + u.in_off; t.b.in_len = (int32_t) u.in_len; t.b.err = 0;
-        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
-    }
-#pragma unroll 1
-    for (int f = 0; f < max_frames; f++) {
-        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
-        if (!st.done) {
-            /* :405-413 align to a byte, skip to the next 'C','K' */
-            int err = 0, state = 0;
-            lsb_align_byte(t.b);
-            do {
-                lsb_refill(t.b);
-                uint32_t c = lsb_read(t.b, 8);
-                if (t.b.err) { err = t.b.err; break; }
-                if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
-            } while (state != 2);
-            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
-            uint32_t produced = 0;
-            if (!err) err = t.inflate(em, &produced);
-            if (err) { st.status = err; st.done = 1; }
-            else {
-                uint32_t n = ms_min(u.out_len - st.produced, produced);
-                emit_end(em, produced);
-                fi.nrec = em.nrec; fi.size = n; fi.valid = 1;
-                st.produced += n; st.frame++;
-                if (st.produced >= u.out_len) st.done = 1;
-            }
-        }
-        finfo[f] = fi;
-    }
-    st.ipos = t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
-}

@@ -1,4 +1,4 @@
-/* msgpu_p1_qtm.cuh - P1 entropy stage for Quantum units: one thread runs one unit's adaptive
+/* msgpu_p1_qtm.cuh - P1 entropy stage for Quantum units: one lane runs one unit's adaptive
  * arithmetic decoder (qtmd.c:92-123 GET_SYMBOL, :125-166 qtmd_update_model, :257-479 qtmd_decompress)
  * and emits literal bytes + match records per 32 KiB frame.  The nine frequency models live in shared
  * memory, interleaved by thread.  Integer widths follow the reference: H, L, C and symf are 16-bit,
@@ -27,7 +27,7 @@ struct QtmShared {
 };
 
 template <int NT>
-struct QtmThread {
+struct QtmLane {
     MsBits b;
     uint16_t *cum; uint8_t *sym, *shl;
     uint32_t H, L, C;                 /* 16-bit values */
@@ -137,25 +137,63 @@ struct QtmThread {
         return v;
     }
 
-    /* One frame.  limit = bytes of this frame the request still wants (<= frame_todo). */
-    MS_M int decode_frame(MsEmit &em, uint32_t frame_start, uint32_t limit, uint32_t &frame_todo, uint32_t window_size, uint32_t out_len) {
-        uint32_t q = 0;
+    /* unit / launch context */
+    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; uint8_t *save;
+    MsEmit em;
+    uint32_t phase, q, limit, produced, frame, done, header_read, frame_todo, window_size, frame_start_pos; int32_t status;
+    int f, max_frames;
+
+    MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
+
+    MS_M void frame_start() {
+        if (!header_read) {                                                /* qtmd.c:290-295 */
+            H = 0xFFFF; L = 0; C = read_bits(16);
+            if (b.err) { fail(b.err); return; }
+            header_read = 1;
+        }
+        frame_start_pos = produced;
+        limit = ms_min(frame_todo, u->out_len - produced);                 /* bytes of this frame the request still wants */
+        q = 0;
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        phase = limit ? PH_DECODE : PH_END;
+    }
+
+    MS_M void frame_end() {
+        if (frame_todo == 0) {                                             /* :430-442 re-align, then scan for the 0xFF trailer */
+            int r = bl & 7; bl -= r; msb_drop(b, b.bc & 7);
+            uint32_t c;
+            do { c = read_bits(8); if (b.err) { fail(b.err); return; } } while (c != 0xFF);
+            header_read = 0; frame_todo = MS_FRAME;
+        }
+        emit_end(em, limit);
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = limit; fi.g0 = frame_start_pos; fi.valid = 1;
+        finfo[f] = fi;
+        produced += limit; frame++; f++;
+        if (produced >= u->out_len) { done = 1; phase = PH_IDLE; }
+        else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+    }
+
+    MS_M void service() {
 #pragma unroll 1
-        while (q < limit) {
-            uint32_t selector = get_symbol(QM7, 8, 7);
-            if (b.err) return b.err;
-            if (selector < 4) {
-                uint32_t s = get_symbol(QM0 + 65 * (int) selector, (int) selector, 64);
-                if (b.err) return b.err;
-                emit_literal(em, s); q++; frame_todo--;
-                continue;
-            }
+        while (phase >= PH_FRAME) {
+            if (phase == PH_FRAME) frame_start();
+            else frame_end();
+        }
+    }
+
+    /* the hot step (qtmd.c:307-417): one selector symbol and whatever it introduces */
+    MS_M void step() {
+        uint32_t selector = get_symbol(QM7, 8, 7);
+        if (selector < 4) {
+            uint32_t s = get_symbol(QM0 + 65 * (int) selector, (int) selector, 64);
+            emit_literal(em, s); q++; frame_todo--;
+        }
+        else {
             uint32_t ml, off, s, extra;
             if (selector == 4) { s = get_symbol(QM4, 4, ent4); ml = 3; }
             else if (selector == 5) { s = get_symbol(QM5, 5, ent5); ml = 4; }
             else if (selector == 6) {
                 s = get_symbol(QM6L, 7, 27);
-                if (b.err) return b.err;
                 /* length_base[] / length_extra[] (qtmd.c:76-83) in closed form */
                 uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
                 uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
@@ -163,100 +201,74 @@ struct QtmThread {
                 ml = lb + extra + 5;
                 s = get_symbol(QM6, 6, ent6);
             }
-            else return MS_EDECRUNCH;
-            if (b.err) return b.err;
+            else { fail(b.err ? b.err : MS_EDECRUNCH); return; }
             {   /* position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
                 uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
                 uint32_t pb = s < 2 ? s : (2u + (s & 1)) << pe;
                 extra = read_many((int) pe);
                 off = pb + extra + 1;
             }
-            if (b.err) return b.err;
-            uint32_t G = frame_start + q, window_posn = G & (window_size - 1);
-            if (ml > frame_todo) return MS_EDECRUNCH;                       /* :424-427 overshot frame alignment */
+            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+            uint32_t G = frame_start_pos + q, window_posn = G & (window_size - 1);
+            if (ml > frame_todo) { fail(MS_EDECRUNCH); return; }           /* :424-427 overshot frame alignment */
             frame_todo -= ml;
             if (window_posn + ml > window_size) {
                 /* :358-390 the reference flushes the whole window first and bails out if that is more than requested */
                 uint32_t lap_start = G - window_posn;
-                if ((uint64_t) lap_start + window_size > out_len) return MS_EDECRUNCH;
+                if ((uint64_t) lap_start + window_size > u->out_len) { fail(MS_EDECRUNCH); return; }
             }
             uint32_t emit_len = ml < limit - q ? ml : limit - q;
             emit_match(em, q, emit_len, off);
             q += ml;
         }
-        return 0;
+        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (q >= limit) phase = PH_END;
+    }
+
+    MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
+                    int nframes, uint8_t *save_area) {
+        u = unit; recs = r; lits = l; finfo = fi; max_frames = nframes; save = save_area; f = 0; q = 0; limit = 0; frame_start_pos = 0;
+#pragma unroll 1
+        for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
+        const int wb = unit->window_bits, wb2 = wb * 2;
+        ent4 = wb2 > 24 ? 24 : wb2; ent5 = wb2 > 36 ? 36 : wb2; ent6 = wb2;
+        window_size = 1u << (wb & 31);
+        if (!st.started) {
+            done = 0; status = 0; produced = 0; frame = 0; header_read = 0; frame_todo = MS_FRAME;
+            ms_bits_init(b, in_base + unit->in_off, unit->in_len);
+            H = 0; L = 0; C = 0; bl = 0; fp = 0;
+            if (wb < 10 || wb > 21) { status = MS_ENOMEM; done = 1; }      /* qtmd_init returns NULL */
+            else {
+                init_model(QM0, 0, 0, 64); init_model(QM1, 1, 64, 64); init_model(QM2, 2, 128, 64); init_model(QM3, 3, 192, 64);
+                init_model(QM4, 4, 0, ent4); init_model(QM5, 5, 0, ent5); init_model(QM6, 6, 0, ent6);
+                init_model(QM6L, 7, 0, 27); init_model(QM7, 8, 0, 7);
+            }
+            if (unit->out_len == 0) done = 1;
+        }
+        else {
+            done = st.done; status = st.status; produced = st.produced; frame = st.frame;
+            ms_bits_restore(b, in_base + unit->in_off, unit->in_len, st.ipos, (int32_t) st.bc, ((uint64_t) st.bb_hi << 32) | st.bb_lo);
+            H = st.qH; L = st.qL; C = st.qC; bl = (int32_t) st.q_bl; fp = (int32_t) st.q_fp;
+            header_read = st.header_read; frame_todo = st.frame_todo;
+            if (save && !done) {
+#pragma unroll 1
+                for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; sym[i * NT] = save[QTM_ENT * 2 + i]; }
+#pragma unroll 1
+                for (int i = 0; i < 9; i++) shl[i * NT] = save[QTM_ENT * 3 + i];
+            }
+        }
+        phase = done ? PH_IDLE : PH_FRAME;
+    }
+    MS_M void end(MsUnitState &st) {
+        st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
+        st.ipos = b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
+        st.qH = H; st.qL = L; st.qC = C; st.q_bl = (uint32_t) bl; st.q_fp = (uint32_t) fp;
+        st.header_read = header_read; st.frame_todo = frame_todo;
+        if (save && !done) {
+#pragma unroll 1
+            for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; save[QTM_ENT * 2 + i] = sym[i * NT]; }
+#pragma unroll 1
+            for (int i = 0; i < 9; i++) save[QTM_ENT * 3 + i] = shl[i * NT];
+        }
     }
 };
-
-template <int NT>
-MS_D void p1_qtm_unit(QtmThread<NT> &t, const msgpu_unit &u, const uint8_t *in_base, MsUnitState &st,
-                      MsRec *recs, uint8_t *lits, MsFrameInfo *finfo, int max_frames, uint8_t *save = nullptr)
-{
-    const int wb = u.window_bits, wb2 = wb * 2;
-    t.ent4 = wb2 > 24 ? 24 : wb2; t.ent5 = wb2 > 36 ? 36 : wb2; t.ent6 = wb2;
-    uint32_t header_read = 0, frame_todo = MS_FRAME;
-    if (!st.started) {
-        st.started = 1; st.done = 0; st.status = 0; st.produced = 0; st.frame = 0;
-        qtm_bits_init(t.b, in_base + u.in_off, u.in_len);
-        t.H = 0; t.L = 0; t.C = 0; t.bl = 0; t.fp = 0;
-        if (wb < 10 || wb > 21) { st.status = MS_ENOMEM; st.done = 1; }      /* qtmd_init returns NULL */
-        else {
-            t.init_model(QM0, 0, 0, 64); t.init_model(QM1, 1, 64, 64); t.init_model(QM2, 2, 128, 64); t.init_model(QM3, 3, 192, 64);
-            t.init_model(QM4, 4, 0, t.ent4); t.init_model(QM5, 5, 0, t.ent5); t.init_model(QM6, 6, 0, t.ent6);
-            t.init_model(QM6L, 7, 0, 27); t.init_model(QM7, 8, 0, 7);
-        }
-        if (u.out_len == 0) st.done = 1;
-    }
-    else {
-        t.b.in = in_base + u.in_off; t.b.in_len = (int32_t) u.in_len; t.b.err = 0;
-        t.b.ipos = st.ipos; t.b.bc = (int32_t) st.bc; t.b.bb = ((uint64_t) st.bb_hi << 32) | st.bb_lo;
-        t.H = st.qH; t.L = st.qL; t.C = st.qC; t.bl = (int32_t) st.q_bl; t.fp = (int32_t) st.q_fp;
-        header_read = st.header_read; frame_todo = st.frame_todo;
-        if (save && !st.done) {
-#pragma unroll 1
-            for (int i = 0; i < QTM_ENT; i++) { t.cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; t.sym[i * NT] = save[QTM_ENT * 2 + i]; }
-#pragma unroll 1
-            for (int i = 0; i < 9; i++) t.shl[i * NT] = save[QTM_ENT * 3 + i];
-        }
-    }
-    const uint32_t window_size = 1u << (wb & 31);
-#pragma unroll 1
-    for (int f = 0; f < max_frames; f++) {
-        MsFrameInfo fi; fi.nrec = 0; fi.size = 0; fi.g0 = st.produced; fi.valid = 0;
-        if (!st.done) {
-            int err = 0;
-            if (!header_read) {                                                /* qtmd.c:290-295 */
-                t.H = 0xFFFF; t.L = 0; t.C = t.read_bits(16);
-                if (t.b.err) err = t.b.err;
-                header_read = 1;
-            }
-            uint32_t frame_start = st.produced;
-            uint32_t limit = ms_min(frame_todo, u.out_len - frame_start);
-            MsEmit em; emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
-            if (!err) err = t.decode_frame(em, frame_start, limit, frame_todo, window_size, u.out_len);
-            if (!err && frame_todo == 0) {                                     /* :430-442 re-align, then scan for the 0xFF trailer */
-                int r = t.bl & 7; t.bl -= r; msb_drop(t.b, t.b.bc & 7);
-                uint32_t c;
-                do { c = t.read_bits(8); if (t.b.err) { err = t.b.err; break; } } while (c != 0xFF);
-                header_read = 0; frame_todo = MS_FRAME;
-            }
-            if (err) { st.status = err; st.done = 1; }
-            else {
-                emit_end(em, limit);
-                fi.nrec = em.nrec; fi.size = limit; fi.valid = 1;
-                st.produced += limit; st.frame++;
-                if (st.produced >= u.out_len) st.done = 1;
-            }
-        }
-        finfo[f] = fi;
-    }
-    st.ipos = t.b.ipos; st.bc = (uint32_t) t.b.bc; st.bb_lo = (uint32_t) t.b.bb; st.bb_hi = (uint32_t) (t.b.bb >> 32);
-    st.qH = t.H; st.qL = t.L; st.qC = t.C; st.q_bl = (uint32_t) t.bl; st.q_fp = (uint32_t) t.fp;
-    st.header_read = header_read; st.frame_todo = frame_todo;
-    if (save && !st.done) {
-#pragma unroll 1
-        for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = t.cum[i * NT]; save[QTM_ENT * 2 + i] = t.sym[i * NT]; }
-#pragma unroll 1
-        for (int i = 0; i < 9; i++) save[QTM_ENT * 3 + i] = t.shl[i * NT];
-    }
-}

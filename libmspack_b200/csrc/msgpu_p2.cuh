@@ -6,10 +6,12 @@
  *     match    byte (q - off) of the output   otherwise, where for an overlapping match (off < len) the
  *              source folds back into the off bytes in front of the match (the byte-serial copy of
  *              lzxd.c:636-646 / mszipd.c:271-296 / qtmd.c:391-416 replicates that seed pattern).
- * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Sources in earlier chunks are
- * read back from the output buffer (it is the sliding window); a source inside the current
- * chunk is followed to ITS source until it leaves the chunk or hits a literal (pointer jumping;
- * positions strictly decrease so it terminates).  The chunk is then stored with 16-byte stores.
+ * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Pass A maps every position of the
+ * chunk to its record (one binary search per lane, then a walk); pass B fetches the bytes: sources in
+ * earlier chunks are read back from the output buffer (it is the sliding window); a source inside the
+ * current chunk is followed through the position map to ITS source until it leaves the chunk or hits
+ * a literal (pointer jumping; positions strictly decrease so it terminates).  The chunk is then
+ * stored with 16-byte stores.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -33,40 +35,47 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
     return lo;
 }
 
-/* Value of the output byte at frame position q (q >= chunk start c, q < size). */
-MS_D uint32_t p2_byte(uint32_t q, int i, uint32_t c, const uint32_t *wa, const uint32_t *wb,
-                      const uint8_t *lits, const uint8_t *unit_out, uint32_t g0)
+/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> owning record (window index) into rid[]. */
+MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint16_t *rid)
 {
-#pragma unroll 1
-    for (;;) {
-        uint32_t a = wa[i], b = wb[i], pos = rec_pos(a);
-        if (q < pos) return lits[q - rec_M(a)];
-        uint32_t off = rec_off(b), len = rec_len(b), k = q - pos;
-        int64_t s;                                            /* frame-relative source position, may be negative */
-        if (off < len && k >= off) s = (int64_t) pos - off + (k % off);
-        else s = (int64_t) q - off;
-        if (s < (int64_t) c) {
-            int64_t g = (int64_t) g0 + s;                     /* unit-relative */
-            return g >= 0 ? unit_out[g] : 0u;                 /* before the unit's first byte: defined as zero */
-        }
-        q = (uint32_t) s;
-        i = p2_search(wa, wb, q);
-    }
-}
-
-/* The 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words. */
-MS_D void p2_lane16(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb,
-                    const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
-{
-    w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
     int i = p2_search(wa, wb, q0);
-#pragma unroll 1
+#pragma unroll 4
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t q = q0 + k;
         if (q >= size) break;
         while (rec_pos(wa[i]) + rec_len(wb[i]) <= q) i++;
-        uint32_t v = p2_byte(q, i, c, wa, wb, lits, unit_out, g0);
+        rid[q - c] = (uint16_t) i;
+    }
+}
+
+/* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.
+ * A source inside the current chunk is followed through rid[] to ITS source (pointer jumping). */
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, const uint16_t *rid,
+                    const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
+{
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (q0 >= size) return;
+#pragma unroll 4
+    for (uint32_t k = 0; k < 16; k++) {
+        uint32_t q = q0 + k, v;
+        if (q >= size) break;
+#pragma unroll 1
+        for (;;) {
+            int i = rid[q - c];
+            uint32_t a = wa[i], b = wb[i], pos = rec_pos(a);
+            if (q < pos) { v = lits[q - rec_M(a)]; break; }
+            uint32_t off = rec_off(b), len = rec_len(b), kk = q - pos;
+            int32_t s;                                        /* frame-relative source position, may be negative */
+            if (off < len && kk >= off) s = (int32_t) (pos - off + (kk % off));
+            else s = (int32_t) q - (int32_t) off;
+            if (s < (int32_t) c) {
+                int64_t g = (int64_t) g0 + s;                 /* unit-relative */
+                v = g >= 0 ? unit_out[g] : 0u;                /* before the unit's first byte: defined as zero */
+                break;
+            }
+            q = (uint32_t) s;
+        }
         w[k >> 2] |= v << (8 * (k & 3));
     }
 }
@@ -75,7 +84,7 @@ MS_D void p2_lane16(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, 
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, const uint8_t *lits,
                                                  uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb)
+                                                 uint32_t *wa, uint32_t *wb, uint16_t *rid)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -90,7 +99,9 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
-        p2_lane16(q0, c, size, wa, wb, lits, unit_out, g0, w);
+        p2_pass_a(q0, c, size, wa, wb, rid);
+        __syncwarp();
+        p2_pass_b(q0, c, size, wa, wb, rid, lits, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -27,8 +27,9 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits,
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t w[32][4];
-        for (int lane = 0; lane < 32; lane++) p2_lane16(c + 16u * lane, c, size, wa.data(), wb.data(), lits, unit_out, g0, w[lane]);
+        uint32_t w[32][4]; uint16_t rid[P2_CHUNK];
+        for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), rid);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, wa.data(), wb.data(), rid, lits, unit_out, g0, w[lane]);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
@@ -52,6 +53,19 @@ static void emul_e8_frame(uint8_t *data, uint32_t frame_size, int32_t curpos0, i
     }
 }
 
+template <class Lane>
+static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for a "warp" of one lane */
+    for (;;) {
+        t.service();
+        if (!MS_BALLOT(t.phase == PH_DECODE)) break;
+        uint32_t need, dec;
+        do {
+            if (t.phase == PH_DECODE) t.step();
+            need = MS_BALLOT(t.phase >= PH_FRAME); dec = MS_BALLOT(t.phase == PH_DECODE);
+        } while (!need && dec);
+    }
+}
+
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     const int F = frames_per_round > 0 ? frames_per_round : 1;
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
@@ -61,26 +75,28 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     uint8_t *unit_out = out_base + u->out_off;
     uint32_t nframes_total = (u->out_len + MS_FRAME - 1) / MS_FRAME;
     std::vector<int32_t> e8info(nframes_total + 2, 0);
+    auto resolve = [&]() {
+        for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
+            emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+    };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
-        typedef ZipShared<1, 9, 8> SH; typedef ZipThread<1, 9, 8> TH;
+        typedef ZipShared<1, 9, 8> SH; typedef ZipLane<1, 9, 8> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
-        TH t; t.bind(sh, 0, aux, 0);
-        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
-            p1_mszip_unit<1, 9, 8>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
-            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
-                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            TH t; t.bind(sh, 0, aux, 0);
+            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            emul_run(t); t.end(st); resolve();
         }
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
-        typedef LzxShared<1, 10, 8> SH; typedef LzxThread<1, 10, 8> TH;
+        typedef LzxShared<1, 9, 7> SH; typedef LzxLane<1, 9, 7> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
-        TH t; t.bind(sh, 0, aux, 0);
-        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
-            p1_lzx_unit<1, 10, 8>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
-            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
-                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            TH t; t.bind(sh, 0, aux, 0);
+            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
+            emul_run(t); t.end(st); resolve();
         }
         for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
             uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
@@ -89,15 +105,14 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_QUANTUM) {
-        typedef QtmShared<1> SH; typedef QtmThread<1> TH;
-        SH *sh = (SH *) calloc(1, sizeof(SH));
-        TH t; t.bind(sh, 0);
-        for (int guard = 0; !st.done && guard < 1 << 20; guard++) {
-            p1_qtm_unit<1>(t, *u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
-            for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
-                emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+        typedef QtmShared<1> SH; typedef QtmLane<1> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
+        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            TH t; t.bind(sh, 0);
+            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F, save);
+            emul_run(t); t.end(st); resolve();
         }
-        free(sh);
+        free(sh); free(save);
     }
     else return MS_EARGS;
     return st.status;
