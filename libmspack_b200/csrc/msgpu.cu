@@ -14,6 +14,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
@@ -30,8 +31,8 @@ struct WaveArgs {
     MsRec *recs;                 /* [slots][F][MS_MAXREC] */
     uint8_t *lits;               /* [slots][F][MS_LITCAP] */
     MsFrameInfo *finfo;          /* [slots][F] */
-    uint32_t *not_done;
-    int F;
+    uint32_t *not_done;          /* per sub-wave counters; a kernel adds to not_done[sub] */
+    int F, sub;
 };
 
 /* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
@@ -42,20 +43,17 @@ __device__ __forceinline__ void p1_run(Lane &t)
 {
     for (;;) {
         t.service();
-        if (!MS_BALLOT(t.phase == PH_DECODE)) break;
-        uint32_t need, dec;
-        do {
-            if (t.phase == PH_DECODE) t.step();
-            need = MS_BALLOT(t.phase >= PH_FRAME); dec = MS_BALLOT(t.phase == PH_DECODE);
-        } while (!need && dec);
+        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
+        if (!m0) break;
+        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
     }
 }
 
 template <int NT, int LROOT, int DROOT>
-__global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *aux)
+__global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;      /* index into the wave's MSZIP list; `first` is a multiple of 32 */
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
     ZipLane<NT, LROOT, DROOT> t; t.phase = PH_IDLE;
@@ -67,15 +65,15 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
                 a.finfo + (size_t) slot * a.F, a.F);
     }
     p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
 template <int NT, int MROOT, int LROOT>
-__global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *aux,
+__global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                int32_t *e8info, const uint32_t *e8base)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
     LzxLane<NT, MROOT, LROOT> t; t.phase = PH_IDLE;
@@ -87,14 +85,14 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
     p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t count, uint8_t *save)
+__global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *save)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t ti = blockIdx.x * NT + threadIdx.x;
+    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
     QtmLane<NT> t; t.phase = PH_IDLE;
@@ -106,29 +104,31 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
                 a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
     }
     p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done, 1u); }
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
 #define P2_WARPS 8
-__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, uint32_t nslots)
+__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
     __shared__ uint16_t s_rid[P2_WARPS][P2_CHUNK];
+    __shared__ __align__(16) uint8_t s_stage[P2_WARPS][32 * P2_STAGE_STRIDE];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t slot = blockIdx.x * P2_WARPS + warp;
-    if (slot >= nslots) return;
+    uint32_t si = first + blockIdx.x * P2_WARPS + warp;
+    if (si >= nslots) return;
+    uint32_t slot = slots[si];
     uint8_t *unit_out = a.out_base + a.units[slot].out_off;
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
         p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
-                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_rid[warp]);
+                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_rid[warp], s_stage[warp]);
     }
 }
 
-__global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, uint32_t count, const int32_t *e8info, const uint32_t *e8base)
+__global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, const int32_t *e8info, const uint32_t *e8base)
 {
-    uint32_t ti = blockIdx.x * 8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    uint32_t ti = first + blockIdx.x * 8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (ti >= count) return;
     uint32_t slot = order[ti];
     const msgpu_unit u = a.units[slot];
@@ -160,7 +160,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 #define ZIP_DROOT 8
 #define LZX_NT 128
 #define LZX_MROOT 9
-#define LZX_LROOT 7
+#define LZX_LROOT 6
 #define QTM_NT 128
 
 struct DevBuf {
@@ -179,6 +179,8 @@ struct DevBuf {
 struct msgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t sub[3] = { nullptr, nullptr, nullptr };   /* sub-waves alternate over these so P1 of one overlaps P2 of another */
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
     std::vector<cudaEvent_t> evs;        /* pairs (start, end) per wave, reused */
     size_t ev_used = 0;                  /* events of the most recent batch */
     std::string err;
@@ -210,7 +212,12 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     msgpu_ctx *c = new msgpu_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 64) != cudaSuccess) { delete c; return nullptr; }
+        cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 4096) != cudaSuccess) { delete c; return nullptr; }
+    for (int i = 0; i < 3; i++) {
+        if (cudaStreamCreateWithFlags(&c->sub[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
+    }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
@@ -229,6 +236,8 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+    for (int i = 0; i < 3; i++) { if (c->sub[i]) cudaStreamDestroy(c->sub[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -252,6 +261,12 @@ extern "C" float msgpu_last_kernel_ms(msgpu_ctx *c) {
 static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_FRAME - 1) / MS_FRAME; }
 
 /* Decode one wave: units[lo, hi) of the host array (already validated). */
+/* Decode one wave: units[lo, hi) of the host array (already validated).
+ *
+ * The wave is cut into sub-waves of MSGPU_SUBWAVE units (default 148 x 128 = one resident P1 CTA per SM).
+ * Sub-wave i runs entirely on internal stream i % 3: P1 (one thread per unit, shared-memory bound, latency
+ * bound, IPC ~0.2) of one sub-wave then shares the SMs with P2 (one warp per unit, issue bound) of the
+ * previous one, instead of the two kernels running back to back. */
 static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t hi, const void *d_in, void *d_out,
                     int32_t *d_status, cudaStream_t s)
 {
@@ -267,14 +282,20 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     }
     const int F = maxfr >= 2 ? 2 : 1;
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
+    const char *env = getenv("MSGPU_SUBWAVE");
+    uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * 128u;
+    subsz = (subsz + 127u) & ~127u; if (subsz < 128) subsz = 128;
+    const uint32_t nmaxc = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
+    const uint32_t nsub = (nmaxc + subsz - 1) / subsz;
+    if (nsub > 1000) return fail(ctx, MSGPU_ERR_ARGS, "too many sub-waves");
 
     CK(ctx->units.reserve((size_t) n * sizeof(msgpu_unit)), "alloc units");
     CK(ctx->ustate.reserve((size_t) n * sizeof(MsUnitState)), "alloc state");
     CK(ctx->recs.reserve((size_t) n * F * MS_MAXREC * sizeof(MsRec)), "alloc records");
     CK(ctx->lits.reserve((size_t) n * F * MS_LITCAP + 64), "alloc literals");
     CK(ctx->finfo.reserve((size_t) n * F * sizeof(MsFrameInfo)), "alloc frame info");
-    CK(ctx->misc.reserve(256), "alloc misc");
-    CK(ctx->order.reserve((size_t) (n + 3) * sizeof(uint32_t)), "alloc order");
+    CK(ctx->misc.reserve(4096), "alloc misc");
+    CK(ctx->order.reserve((size_t) (2 * n + 3) * sizeof(uint32_t)), "alloc order");
     if (nz) CK(ctx->aux_zip.reserve((size_t) ((nz + 31) / 32) * ZIP_AUX_BYTES), "alloc mszip aux");
     if (nl) {
         CK(ctx->aux_lzx.reserve((size_t) ((nl + 31) / 32) * LZX_AUX_BYTES), "alloc lzx aux");
@@ -294,6 +315,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         CK(cudaMemsetAsync(ctx->e8info.p, 0, (size_t) (e8total + 1) * sizeof(int32_t), s), "clear e8 info");
     }
     CK(cudaMemsetAsync(ctx->ustate.p, 0, (size_t) n * sizeof(MsUnitState), s), "clear state");
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, s), "clear counters");
     /* the pageable host vectors above must outlive the async copies */
     CK(cudaStreamSynchronize(s), "sync uploads");
 
@@ -301,28 +323,64 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     a.units = reinterpret_cast<const msgpu_unit *>(ctx->units.p); a.in_base = reinterpret_cast<const uint8_t *>(d_in);
     a.out_base = reinterpret_cast<uint8_t *>(d_out); a.ustate = reinterpret_cast<MsUnitState *>(ctx->ustate.p);
     a.recs = reinterpret_cast<MsRec *>(ctx->recs.p); a.lits = reinterpret_cast<uint8_t *>(ctx->lits.p);
-    a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.F = F;
+    a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.F = F; a.sub = 0;
 
     while (ctx->evs.size() < ctx->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e), "event create"); ctx->evs.push_back(e); }
     cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
     CK(cudaEventRecord(ev0, s), "event");
-    uint32_t rounds_planned = (maxfr + F - 1) / F;
-    for (uint32_t round = 0;; round++) {
-        bool check = (round + 1 >= rounds_planned) && (any_zip || round + 1 > rounds_planned);
-        if (check) CK(cudaMemsetAsync(a.not_done, 0, 4, s), "clear counter");
-        if (nz) { k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT><<<(nz + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>), s>>>(a, d_ord_z, nz, reinterpret_cast<uint8_t *>(ctx->aux_zip.p)); ctx->launches++; }
-        if (nl) { k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT><<<(nl + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>), s>>>(a, d_ord_l, nl, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
-        if (nq) { k_p1_qtm<QTM_NT><<<(nq + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), s>>>(a, d_ord_q, nq, reinterpret_cast<uint8_t *>(ctx->save_qtm.p)); ctx->launches++; }
-        k_p2_resolve<<<(n + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, s>>>(a, n); ctx->launches++;
-        CK(cudaGetLastError(), "kernel launch");
-        if (round + 1 < rounds_planned) continue;
-        if (!any_zip && round + 1 == rounds_planned) break;      /* LZX / Quantum frame counts are exact */
-        CK(cudaMemcpyAsync(ctx->h_pinned, a.not_done, 4, cudaMemcpyDeviceToHost, s), "read counter");
-        CK(cudaStreamSynchronize(s), "sync");
-        if (ctx->h_pinned[0] == 0) break;
-        if (round > (1u << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
+    CK(cudaEventRecord(ctx->ev_fork, s), "event");
+    const int NS = nsub > 1 ? 3 : 1;
+    for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
+
+    /* sub-wave k = entries [k * subsz, (k + 1) * subsz) of EACH codec's list (subsz is a multiple of the CTA
+     * size, so warps and their aux blocks never straddle two sub-waves); P2 walks the same list ranges */
+    const uint32_t rounds_planned = (maxfr + F - 1) / F;
+    auto launch_round = [&](uint32_t sub, cudaStream_t st) {
+        uint32_t f0 = sub * subsz, f1;
+        WaveArgs w = a; w.sub = (int) sub;
+        if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
+            k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; }
+        if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
+            k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; }
+        if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
+            k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_q, f0, f1); ctx->launches += 2; }
+    };
+    auto launch_tail = [&](uint32_t sub, cudaStream_t st) {
+        uint32_t f0 = sub * subsz, f1;
+        if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
+            k_e8<<<(f1 - f0 + 7) / 8, 256, 0, st>>>(a, d_ord_l, f0, f1, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
+    };
+    for (uint32_t sub = 0; sub < nsub; sub++) {
+        cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
+        for (uint32_t round = 0; round < rounds_planned; round++) {
+            if (round + 1 == rounds_planned && any_zip) CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
+            launch_round(sub, st);
+        }
+        if (!any_zip) launch_tail(sub, st);
     }
-    if (nl) { k_e8<<<(nl + 7) / 8, 256, 0, s>>>(a, d_ord_l, nl, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
+    CK(cudaGetLastError(), "kernel launch");
+    if (any_zip) {
+        /* MSZIP blocks may be shorter than 32 KiB, so a folder can need more rounds than its size suggests:
+         * read the per-sub-wave "units still running" counters back and finish the stragglers */
+        for (int guard = 0;; guard++) {
+            for (int i = 0; i < NS; i++) CK(cudaStreamSynchronize(NS == 1 ? s : ctx->sub[i]), "sync");
+            CK(cudaMemcpy(ctx->h_pinned, a.not_done, nsub * 4, cudaMemcpyDeviceToHost), "read counters");
+            bool again = false;
+            for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
+                cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
+                again = true;
+                CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
+                launch_round(sub, st);
+            }
+            if (!again) break;
+            if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
+        }
+        for (uint32_t sub = 0; sub < nsub; sub++) launch_tail(sub, NS == 1 ? s : ctx->sub[sub % 3]);
+    }
+    if (NS > 1) for (int i = 0; i < NS; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->sub[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[i], 0), "stream wait"); }
     if (d_status) { k_status<<<(n + 255) / 256, 256, 0, s>>>(a.ustate, n, d_status + lo); ctx->launches++; }
     CK(cudaEventRecord(ev1, s), "event");
     ctx->ev_used += 2;

@@ -194,7 +194,7 @@ struct MsHuffAux {          /* pointers already offset by lane; stride MS_WARP e
  * array in shared memory for this thread with stride cstride.  Returns 0 on success. */
 template <int ROOT, bool LSB, int NT, class LensFn>
 MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut, const MsHuffAux &aux,
-                       uint16_t *cnt, int cstride, int *maxlen_out)
+                       uint16_t *cnt, int cstride, int *maxlen_out, uint16_t *lcache = nullptr, uint32_t lcache_n = 0)
 {
 #pragma unroll 1
     for (int l = 0; l <= 16; l++) cnt[l * cstride] = 0;
@@ -217,6 +217,7 @@ MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut,
         cnt[l * cstride] = (uint16_t) off;                  /* becomes the running index of the next l-bit symbol */
         lim += c << (16 - l); aux.limit[l * MS_WARP] = lim; off += c;
     }
+    const uint32_t first_long = (ROOT < 16) ? aux.offs[(ROOT + 1) * MS_WARP] : 0;
 #pragma unroll 1
     for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
 #pragma unroll 1
@@ -225,6 +226,10 @@ MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut,
         if (l < 1 || l > maxlen) continue;
         uint32_t k = cnt[l * cstride]; cnt[l * cstride] = (uint16_t) (k + 1);
         aux.sorted[k * MS_WARP] = (uint16_t) s;
+        if (l > ROOT) {                                     /* the first lcache_n long-code symbols also go to shared memory */
+            uint32_t rel = k - first_long;
+            if (rel < lcache_n) lcache[rel * NT] = (uint16_t) s;
+        }
         if (l <= ROOT) {
             uint32_t code = (aux.limit[(l - 1) * MS_WARP] >> (16 - l)) + (k - aux.offs[l * MS_WARP]);   /* l-bit canonical code */
             uint16_t ent = (uint16_t) ((s << 4) | l);
@@ -258,6 +263,18 @@ struct MsHuffLong {
         for (int j = 1; j < 16 - ROOT; j++) if (v16 >= lim[j]) { l = ROOT + j + 1; base = lim[j]; o = off[j + 1]; }
         *len = l;
         return aux.sorted[(o + ((v16 - base) >> (16 - l))) * MS_WARP];
+    }
+    /* same, with the first cache_n long-code symbols (canonical order: the shortest, most frequent ones) in
+     * shared memory at cache[rel * NT] */
+    template <int NT>
+    MS_M uint32_t decode_cached(uint32_t v16, const MsHuffAux &aux, const uint16_t *cache, uint32_t cache_n, int *len) const {
+        int l = ROOT + 1; uint32_t base = lim[0], o = off[1];
+#pragma unroll
+        for (int j = 1; j < 16 - ROOT; j++) if (v16 >= lim[j]) { l = ROOT + j + 1; base = lim[j]; o = off[j + 1]; }
+        *len = l;
+        uint32_t idx = o + ((v16 - base) >> (16 - l)), rel = idx - off[1];
+        if (rel < cache_n) return cache[rel * NT];
+        return aux.sorted[idx * MS_WARP];
     }
 };
 

@@ -19,9 +19,16 @@
 #define ZIP_AUX_OFFS      (ZIP_AUX_LIMIT + 3 * 20 * 32 * 4) /* u16 [3][20][32] */
 #define ZIP_AUX_BYTES     (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)
 
+#ifndef ZIP_LCACHE
+#define ZIP_LCACHE 120                    /* literal/length symbols with codes longer than LROOT kept in shared memory */
+#endif
+#ifndef ZIP_LITBATCH
+#define ZIP_LITBATCH 3
+#endif
 template <int NT, int LROOT, int DROOT>
 struct ZipShared {
     uint16_t llut[(1 << LROOT) * NT];
+    uint16_t lsym[ZIP_LCACHE * NT];       /* the first ZIP_LCACHE long-code literal/length symbols in canonical order */
     uint16_t dlut[(1 << DROOT) * NT];     /* also hosts the 7-bit code-length-code LUT while lengths are read (DROOT >= 7) */
     uint16_t cnt[17 * NT];
 };
@@ -29,7 +36,7 @@ struct ZipShared {
 template <int NT, int LROOT, int DROOT>
 struct ZipLane {
     MsBits b;
-    uint16_t *llut, *dlut, *cnt;          /* this lane's column of the shared tables */
+    uint16_t *llut, *lsym, *dlut, *cnt;   /* this lane's column of the shared tables */
     uint8_t *lens;                        /* aux, stride 32 */
     MsHuffAux la, da, ba;
     MsHuffLong<LROOT> ll;
@@ -41,7 +48,7 @@ struct ZipLane {
     int f, max_frames;
 
     MS_M void bind(ZipShared<NT, LROOT, DROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
-        llut = sh->llut + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
+        llut = sh->llut + tid; lsym = sh->lsym + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
         lens = aux_warp + ZIP_AUX_LENS + lane;
         la.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_LSORT) + lane;
         da.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_DSORT) + lane;
@@ -99,7 +106,7 @@ struct ZipLane {
         }
         /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
         uint8_t *l = lens; int lmax, dmax;
-        if (ms_huff_build<LROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, llut, la, cnt, NT, &lmax)) return MS_EDECRUNCH;
+        if (ms_huff_build<LROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, llut, la, cnt, NT, &lmax, lsym, ZIP_LCACHE)) return MS_EDECRUNCH;
         if (ms_huff_build<DROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) dist_codes ? l[(lit_codes + s) * 32] : 0); }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
         return 0;
     }
@@ -135,7 +142,7 @@ struct ZipLane {
         if (type == 1) {
             /* fixed codes :212-220 */
             int lmax, dmax;
-            if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax)) e = MS_EDECRUNCH;
+            if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax, lsym, ZIP_LCACHE)) e = MS_EDECRUNCH;
             else if (ms_huff_build<DROOT, true, NT>([](int) { return 5u; }, 32, 6, dlut, da, cnt, NT, &dmax)) e = MS_EDECRUNCH;
         }
         else e = read_lens();
@@ -182,15 +189,32 @@ struct ZipLane {
         }
     }
 
-    /* the hot step: one literal/length symbol, plus the distance of a match (mszipd.c:243-300) */
+    MS_M uint32_t litlen_sym() {
+        lsb_check(b, 16);
+        uint32_t e = llut[lsb_peek(b, LROOT) * NT];
+        int len = (int) (e & 15); uint32_t sym = e >> 4;
+        if (len == 0) sym = ll.template decode_cached<NT>(MS_BREV32((uint32_t) b.bb) >> 16, la, lsym, ZIP_LCACHE, &len);
+        lsb_drop(b, len);
+        return sym;
+    }
+
+    /* the hot step (mszipd.c:243-300): up to ZIP_LITBATCH literals, or one match (length + distance), or the
+     * end-of-block code */
     MS_M void step() {
-        lsb_refill(b);
-        uint32_t sym = huffsym<LROOT>(llut, la, ll);
-        if (sym < 256) {
+        uint32_t sym;
+#pragma unroll 1
+        for (int rep = 0;;) {
+            lsb_refill(b);
+            sym = litlen_sym();
+            if (sym >= 256) break;
             if (q < MS_FRAME) emit_literal(em, sym);
             q++;
+            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+            if (MS_UNLIKELY(q >= 2 * MS_FRAME)) { fail(MS_EDECRUNCH); return; }
+            if (++rep == ZIP_LITBATCH) return;
         }
-        else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
+        if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
+
         else {
             uint32_t c = sym - 257, eb, length, dist;
             if (c >= 29) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :255 */

@@ -27,12 +27,12 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits,
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t w[32][4]; uint16_t rid[P2_CHUNK];
+        uint8_t stage[32 * P2_STAGE_STRIDE]; uint16_t rid[P2_CHUNK];
         for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), rid);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, wa.data(), wb.data(), rid, lits, unit_out, g0, w[lane]);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, wa.data(), wb.data(), rid, lits, unit_out, g0, stage + lane * P2_STAGE_STRIDE);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
-            for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
+            for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = stage[lane * P2_STAGE_STRIDE + k];
         }
     }
 }
@@ -57,12 +57,9 @@ template <class Lane>
 static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for a "warp" of one lane */
     for (;;) {
         t.service();
-        if (!MS_BALLOT(t.phase == PH_DECODE)) break;
-        uint32_t need, dec;
-        do {
-            if (t.phase == PH_DECODE) t.step();
-            need = MS_BALLOT(t.phase >= PH_FRAME); dec = MS_BALLOT(t.phase == PH_DECODE);
-        } while (!need && dec);
+        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
+        if (!m0) break;
+        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
     }
 }
 
@@ -91,7 +88,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
-        typedef LzxShared<1, 9, 7> SH; typedef LzxLane<1, 9, 7> TH;
+        typedef LzxShared<1, 9, 6> SH; typedef LzxLane<1, 9, 6> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
