@@ -49,17 +49,17 @@ __device__ __forceinline__ void p1_run(Lane &t)
     }
 }
 
-template <int NT, int LROOT, int DROOT>
+template <int NT, int LROOT, int DROOT, int LCACHE>
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;      /* index into the wave's MSZIP list; `first` is a multiple of 32 */
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    ZipLane<NT, LROOT, DROOT> t; t.phase = PH_IDLE;
+    ZipLane<NT, LROOT, DROOT, LCACHE> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
-        t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
+        t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT, LCACHE> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
                 a.finfo + (size_t) slot * a.F, a.F);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT, int MROOT, int LROOT>
+template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                int32_t *e8info, const uint32_t *e8base)
 {
@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLane<NT, MROOT, LROOT> t; t.phase = PH_IDLE;
+    LzxLane<NT, MROOT, LROOT, LCACHE, LITB> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
-        t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
+        t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
     __shared__ uint16_t s_rid[P2_WARPS][P2_CHUNK];
-    __shared__ __align__(16) uint8_t s_stage[P2_WARPS][32 * P2_STAGE_STRIDE];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t si = first + blockIdx.x * P2_WARPS + warp;
     if (si >= nslots) return;
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
         p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
-                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_rid[warp], s_stage[warp]);
+                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_rid[warp]);
     }
 }
 
@@ -155,12 +154,12 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 }
 
 /* ------------------------------------------------------------------------------------------ host side */
-#define ZIP_NT 128
-#define ZIP_LROOT 9
-#define ZIP_DROOT 8
-#define LZX_NT 128
-#define LZX_MROOT 9
-#define LZX_LROOT 6
+/* MSZIP P1 variants (threads per CTA, literal/length LUT bits, distance LUT bits, long-symbol cache entries);
+ * MSGPU_ZIP_VARIANT picks one (default 0) */
+#define ZIP_VARIANTS(X) X(0, 192, 8, 7, 96) X(1, 128, 9, 8, 48) X(2, 128, 9, 8, 120)
+/* LZX P1 variants (threads per CTA, main LUT bits, length LUT bits, long-symbol cache entries, literals per step);
+ * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
+#define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
 #define QTM_NT 128
 
 struct DevBuf {
@@ -186,6 +185,7 @@ struct msgpu_ctx {
     std::string err;
     uint64_t launches = 0;
     size_t scratch_budget = 0;
+    int lzx_variant = 0, zip_variant = 0;
     DevBuf units, ustate, recs, lits, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     size_t bytes_held() const {
@@ -222,8 +222,14 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
-    cudaFuncSetAttribute(k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>));
-    cudaFuncSetAttribute(k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>));
+#define SETATTRZ(id, nt, lr, dr, lc) cudaFuncSetAttribute(k_p1_mszip<nt, lr, dr, lc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipShared<nt, lr, dr, lc>));
+    ZIP_VARIANTS(SETATTRZ)
+#undef SETATTRZ
+    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 0; }
+#define SETATTR(id, nt, mr, lr, lc, lb) cudaFuncSetAttribute(k_p1_lzx<nt, mr, lr, lc, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<nt, mr, lr, lc, lb>));
+    LZX_VARIANTS(SETATTR)
+#undef SETATTR
+    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 0; }
     cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
     return c;
 }
@@ -283,8 +289,19 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const int F = maxfr >= 2 ? 2 : 1;
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
-    uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * 128u;
-    subsz = (subsz + 127u) & ~127u; if (subsz < 128) subsz = 128;
+    uint32_t lzx_nt = 128, zip_nt = 128;
+#define PICKNT(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
+    LZX_VARIANTS(PICKNT)
+#undef PICKNT
+#define PICKNTZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) zip_nt = nt;
+    ZIP_VARIANTS(PICKNTZ)
+#undef PICKNTZ
+    /* sub-wave size: a multiple of every CTA size in use (32 * 3 * 4 * 7 = 2688 covers 96/128/192/224 threads),
+     * about one resident P1 CTA per SM */
+    const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u;
+    uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
+    subsz = (subsz + gran - 1) / gran * gran;
     const uint32_t nmaxc = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
     const uint32_t nsub = (nmaxc + subsz - 1) / subsz;
     if (nsub > 1000) return fail(ctx, MSGPU_ERR_ARGS, "too many sub-waves");
@@ -339,10 +356,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         uint32_t f0 = sub * subsz, f1;
         WaveArgs w = a; w.sub = (int) sub;
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
-            k_p1_mszip<ZIP_NT, ZIP_LROOT, ZIP_DROOT><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipShared<ZIP_NT, ZIP_LROOT, ZIP_DROOT>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+#define LAUNCHZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) k_p1_mszip<nt, lr, dr, lc><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipShared<nt, lr, dr, lc>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            ZIP_VARIANTS(LAUNCHZ)
+#undef LAUNCHZ
             k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
-            k_p1_lzx<LZX_NT, LZX_MROOT, LZX_LROOT><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxShared<LZX_NT, LZX_MROOT, LZX_LROOT>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCH(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) k_p1_lzx<nt, mr, lr, lc, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxShared<nt, mr, lr, lc, lb>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+            LZX_VARIANTS(LAUNCH)
+#undef LAUNCH
             k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));

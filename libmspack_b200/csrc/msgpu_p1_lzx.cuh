@@ -23,19 +23,17 @@
 #define LZX_AUX_OFFS     (LZX_AUX_LIMIT + 4 * 20 * 32 * 4)         /* u16 [4][20][32] */
 #define LZX_AUX_BYTES    (LZX_AUX_OFFS + 4 * 20 * 32 * 2)
 
-#ifndef LZX_LCACHE
-#define LZX_LCACHE 184                    /* main-tree symbols with codes longer than MROOT kept in shared memory */
-#endif
-template <int NT, int MROOT, int LROOT>
+/* LCACHE = main-tree symbols with codes longer than MROOT kept in shared memory; LITB = literals per step() */
+template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
 struct LzxShared {
     uint16_t mlut[(1 << MROOT) * NT];
-    uint16_t lsym[LZX_LCACHE * NT];       /* the first LZX_LCACHE long-code main symbols in canonical order */
+    uint16_t lsym[LCACHE * NT];           /* the first LCACHE long-code main symbols in canonical order */
     uint16_t llut[(1 << LROOT) * NT];     /* LENGTH tree; hosts the pretree LUT while code lengths are being read */
     uint16_t alut[128 * NT];
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int MROOT, int LROOT>
+template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
 struct LzxLane {
     MsBits b;
     uint16_t *mlut, *lsym, *llut, *alut, *cnt;
@@ -53,7 +51,7 @@ struct LzxLane {
     uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
     int f, max_frames;
 
-    MS_M void bind(LzxShared<NT, MROOT, LROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
+    MS_M void bind(LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *sh, int tid, uint8_t *aux_warp, int lane) {
         mlut = sh->mlut + tid; lsym = sh->lsym + tid; llut = sh->llut + tid; alut = sh->alut + tid; cnt = sh->cnt + tid;
         main_len = aux_warp + LZX_AUX_MAINLEN + lane; len_len = aux_warp + LZX_AUX_LENLEN + lane;
         ma.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_MSORT) + lane;
@@ -146,7 +144,7 @@ struct LzxLane {
 
     MS_M int build_main() {
         uint8_t *l = main_len; int mmax;
-        if (ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax, lsym, LZX_LCACHE)) return MS_EDECRUNCH;
+        if (ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax, lsym, LCACHE)) return MS_EDECRUNCH;
         ml_long.load(ma);
         return 0;
     }
@@ -288,17 +286,14 @@ struct LzxLane {
         lzx_check(b, 16);
         uint32_t e = mlut[msb_peek(b, MROOT) * NT];
         int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = ml_long.template decode_cached<NT>(msb_peek(b, 16), ma, lsym, LZX_LCACHE, &len);
+        if (len == 0) sym = ml_long.template decode_cached<NT>(msb_peek(b, 16), ma, lsym, LCACHE, &len);
         msb_drop(b, len);
         return sym;
     }
 
-    /* the hot step (lzxd.c:538-651): up to LZX_LITBATCH literals, or one match with its length / offset
+    /* the hot step (lzxd.c:538-651): up to LITB literals, or one match with its length / offset
      * fields.  Batching literals keeps the lanes that are inside a literal run busy while the others
      * handle a match, which is the longer path. */
-#ifndef LZX_LITBATCH
-#define LZX_LITBATCH 3
-#endif
     MS_M void step() {
         uint32_t sym;
 #pragma unroll 1
@@ -309,7 +304,7 @@ struct LzxLane {
             emit_literal(em, sym); q++; this_run--;
             if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
             if (this_run <= 0) { phase = PH_BLOCK; return; }
-            if (++rep == LZX_LITBATCH) return;
+            if (++rep == LITB) return;
         }
         {
             sym -= 256;

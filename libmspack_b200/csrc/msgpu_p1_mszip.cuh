@@ -19,13 +19,11 @@
 #define ZIP_AUX_OFFS      (ZIP_AUX_LIMIT + 3 * 20 * 32 * 4) /* u16 [3][20][32] */
 #define ZIP_AUX_BYTES     (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)
 
-#ifndef ZIP_LCACHE
-#define ZIP_LCACHE 120                    /* literal/length symbols with codes longer than LROOT kept in shared memory */
-#endif
 #ifndef ZIP_LITBATCH
-#define ZIP_LITBATCH 3
+#define ZIP_LITBATCH 1
 #endif
-template <int NT, int LROOT, int DROOT>
+/* ZIP_LCACHE = literal/length symbols with codes longer than LROOT kept in shared memory */
+template <int NT, int LROOT, int DROOT, int ZIP_LCACHE>
 struct ZipShared {
     uint16_t llut[(1 << LROOT) * NT];
     uint16_t lsym[ZIP_LCACHE * NT];       /* the first ZIP_LCACHE long-code literal/length symbols in canonical order */
@@ -33,7 +31,7 @@ struct ZipShared {
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int LROOT, int DROOT>
+template <int NT, int LROOT, int DROOT, int ZIP_LCACHE>
 struct ZipLane {
     MsBits b;
     uint16_t *llut, *lsym, *dlut, *cnt;   /* this lane's column of the shared tables */
@@ -47,7 +45,7 @@ struct ZipLane {
     uint32_t phase, q, last_block, produced, frame, done; int32_t status;
     int f, max_frames;
 
-    MS_M void bind(ZipShared<NT, LROOT, DROOT> *sh, int tid, uint8_t *aux_warp, int lane) {
+    MS_M void bind(ZipShared<NT, LROOT, DROOT, ZIP_LCACHE> *sh, int tid, uint8_t *aux_warp, int lane) {
         llut = sh->llut + tid; lsym = sh->lsym + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
         lens = aux_warp + ZIP_AUX_LENS + lane;
         la.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_LSORT) + lane;

@@ -71,49 +71,20 @@ MS_D uint32_t p2_chase(uint32_t q, uint32_t c, const uint32_t *wa, const uint32_
     }
 }
 
-#define P2_STAGE_STRIDE 20       /* bytes per lane in the staging row: 16 + 4 so that rows fall into different banks */
-
-/* Pass B: the 16 bytes [q0, q0+16) of the frame into this lane's staging row (bytes >= size untouched).
- * The lane walks the SEGMENTS that cover its 16 positions - a literal run or (part of) a match - so the
- * record decode is paid once per segment; a segment whose source lies before the chunk is a plain copy. */
+/* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.
+ * Every lane runs the same per-byte loop (keeps the warp converged); a source inside the current chunk
+ * is chased through the position map. */
 MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, const uint16_t *rid,
-                    const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint8_t *row)
+                    const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
+    w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
-    const uint32_t end16 = q0 + 16 < size ? q0 + 16 : size;
-    uint32_t q = q0; int i = rid[q0 - c];
-#pragma unroll 1
-    while (q < end16) {
-        uint32_t a = wa[i], b = wb[i], pos = rec_pos(a);
-        if (q < pos) {                                        /* literal run up to the record's match */
-            uint32_t n = (pos < end16 ? pos : end16) - q;
-            const uint8_t *src = lits + (q - rec_M(a));
-#pragma unroll 1
-            for (uint32_t j = 0; j < n; j++) row[q - q0 + j] = src[j];
-            q += n;
-            continue;
-        }
-        uint32_t off = rec_off(b), len = rec_len(b), mend = pos + len;
-        uint32_t n = (mend < end16 ? mend : end16) - q;
-        int32_t s = (int32_t) q - (int32_t) off;
-        if (off >= len && s + (int32_t) n <= (int32_t) c) {   /* plain match whose source is already in the output */
-            int64_t g = (int64_t) g0 + s;
-            if (g >= 0) {
-                const uint8_t *src = unit_out + g;
-#pragma unroll 1
-                for (uint32_t j = 0; j < n; j++) row[q - q0 + j] = src[j];
-            }
-            else {
-#pragma unroll 1
-                for (uint32_t j = 0; j < n; j++) row[q - q0 + j] = (g + j >= 0) ? unit_out[g + j] : (uint8_t) 0;
-            }
-        }
-        else {                                                /* overlapping match, or a source inside this chunk */
-#pragma unroll 1
-            for (uint32_t j = 0; j < n; j++) row[q - q0 + j] = (uint8_t) p2_chase(q + j, c, wa, wb, rid, lits, unit_out, g0);
-        }
-        q += n;
-        if (q == mend) i++;
+#pragma unroll 4
+    for (uint32_t k = 0; k < 16; k++) {
+        uint32_t q = q0 + k;
+        if (q >= size) break;
+        uint32_t v = p2_chase(q, c, wa, wb, rid, lits, unit_out, g0);
+        w[k >> 2] |= v << (8 * (k & 3));
     }
 }
 
@@ -121,7 +92,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, 
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, const uint8_t *lits,
                                                  uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint16_t *rid, uint8_t *stage)
+                                                 uint32_t *wa, uint32_t *wb, uint16_t *rid)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -136,12 +107,9 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
-        uint8_t *row = stage + lane * P2_STAGE_STRIDE;
         p2_pass_a(q0, c, size, wa, wb, rid);
         __syncwarp();
-        p2_pass_b(q0, c, size, wa, wb, rid, lits, unit_out, g0, row);
-        const uint32_t *roww = reinterpret_cast<const uint32_t *>(row);
-        w[0] = roww[0]; w[1] = roww[1]; w[2] = roww[2]; w[3] = roww[3];
+        p2_pass_b(q0, c, size, wa, wb, rid, lits, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -27,12 +27,12 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits,
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint8_t stage[32 * P2_STAGE_STRIDE]; uint16_t rid[P2_CHUNK];
+        uint32_t w[32][4]; uint16_t rid[P2_CHUNK];
         for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), rid);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, wa.data(), wb.data(), rid, lits, unit_out, g0, stage + lane * P2_STAGE_STRIDE);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, wa.data(), wb.data(), rid, lits, unit_out, g0, w[lane]);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
-            for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = stage[lane * P2_STAGE_STRIDE + k];
+            for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
         }
     }
 }
@@ -78,7 +78,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
-        typedef ZipShared<1, 9, 8> SH; typedef ZipLane<1, 9, 8> TH;
+        typedef ZipShared<1, 8, 7, 96> SH; typedef ZipLane<1, 8, 7, 96> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
@@ -88,7 +88,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
-        typedef LzxShared<1, 9, 6> SH; typedef LzxLane<1, 9, 6> TH;
+        typedef LzxShared<1, 8, 5, 96, 1> SH; typedef LzxLane<1, 8, 5, 96, 1> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
