@@ -101,6 +101,12 @@ size_t msgpu_scratch_bytes(const msgpu_ctx *ctx);
  * events on the launching stream (valid after the stream is synchronised; < 0 if none). */
 float msgpu_last_kernel_ms(msgpu_ctx *ctx);
 
+/* Stage timing (measurement aid): when on, the stages of the next batches run back to back on one stream,
+ * each launch bracketed by CUDA events; msgpu_stage_ms(ctx, stage) then returns the summed duration of
+ * stage 0 = P1 entropy kernels, 1 = P2 resolve kernel, 2 = E8 kernel for the most recent batch. */
+int   msgpu_set_stage_timing(msgpu_ctx *ctx, int on);
+float msgpu_stage_ms(msgpu_ctx *ctx, int stage);
+
 /* Library version string. */
 const char *msgpu_version(void);
 

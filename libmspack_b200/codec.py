@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(PKG, "libmsgpu.so")
 ABI_SYMBOLS = [
     "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
     "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
-    "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_version",
+    "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version",
 ]
 
 _lib = None
@@ -54,6 +54,10 @@ def load_library() -> ctypes.CDLL:
     lib.msgpu_scratch_bytes.argtypes = [vp]
     lib.msgpu_last_kernel_ms.restype = ctypes.c_float
     lib.msgpu_last_kernel_ms.argtypes = [vp]
+    lib.msgpu_set_stage_timing.restype = ctypes.c_int
+    lib.msgpu_set_stage_timing.argtypes = [vp, ctypes.c_int]
+    lib.msgpu_stage_ms.restype = ctypes.c_float
+    lib.msgpu_stage_ms.argtypes = [vp, ctypes.c_int]
     lib.msgpu_version.restype = ctypes.c_char_p
     lib.msgpu_version.argtypes = []
     _lib = lib
@@ -95,6 +99,12 @@ class BatchDecoder:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.msgpu_last_kernel_ms(self.ctx))
+
+    def set_stage_timing(self, on: bool) -> None:
+        self.lib.msgpu_set_stage_timing(self.ctx, 1 if on else 0)
+
+    def stage_ms(self, stage: int) -> float:
+        return float(self.lib.msgpu_stage_ms(self.ctx, stage))
 
     def decode_device(self, units: np.ndarray, d_in, d_out, d_status=None, stream=None) -> None:
         """Inputs already resident: d_in / d_out / d_status are torch CUDA tensors (uint8 / uint8 / int32)."""

@@ -186,6 +186,9 @@ struct msgpu_ctx {
     uint64_t launches = 0;
     size_t scratch_budget = 0;
     int lzx_variant = 0, zip_variant = 0;
+    int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
+    std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
+    std::vector<cudaEvent_t> stage_pool;
     DevBuf units, ustate, recs, lits, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     size_t bytes_held() const {
@@ -242,6 +245,7 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->stage_pool) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) { if (c->sub[i]) cudaStreamDestroy(c->sub[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -262,6 +266,25 @@ extern "C" float msgpu_last_kernel_ms(msgpu_ctx *c) {
         total += ms;
     }
     return total;
+}
+
+extern "C" int msgpu_set_stage_timing(msgpu_ctx *c, int on) { if (!c) return MSGPU_ERR_ARGS; c->stage_timing = on ? 1 : 0; return 0; }
+
+extern "C" float msgpu_stage_ms(msgpu_ctx *c, int stage) {
+    if (!c || stage < 0 || stage > 2) return -1.0f;
+    float total = 0.0f;
+    for (size_t i = 0; i + 1 < c->stage_evs[stage].size(); i += 2) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(c->stage_evs[stage][i + 1]) != cudaSuccess) return -1.0f;
+        if (cudaEventElapsedTime(&ms, c->stage_evs[stage][i], c->stage_evs[stage][i + 1]) != cudaSuccess) return -1.0f;
+        total += ms;
+    }
+    return total;
+}
+
+static cudaEvent_t stage_event(msgpu_ctx *c, size_t &used) {
+    while (c->stage_pool.size() <= used) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; c->stage_pool.push_back(e); }
+    return c->stage_pool[used++];
 }
 
 static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_FRAME - 1) / MS_FRAME; }
@@ -346,33 +369,46 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
-    const int NS = nsub > 1 ? 3 : 1;
+    const int NS = (nsub > 1 && !ctx->stage_timing) ? 3 : 1;
+    size_t sev_used = ctx->stage_evs[0].size() + ctx->stage_evs[1].size() + ctx->stage_evs[2].size();
     for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
 
     /* sub-wave k = entries [k * subsz, (k + 1) * subsz) of EACH codec's list (subsz is a multiple of the CTA
      * size, so warps and their aux blocks never straddle two sub-waves); P2 walks the same list ranges */
     const uint32_t rounds_planned = (maxfr + F - 1) / F;
+    auto mark = [&](int stage, cudaStream_t st) {      /* stage timing: an event on either side of a launch */
+        if (!ctx->stage_timing) return;
+        cudaEvent_t e = stage_event(ctx, sev_used);
+        if (e) { cudaEventRecord(e, st); ctx->stage_evs[stage].push_back(e); }
+    };
     auto launch_round = [&](uint32_t sub, cudaStream_t st) {
         uint32_t f0 = sub * subsz, f1;
         WaveArgs w = a; w.sub = (int) sub;
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
+            mark(0, st);
 #define LAUNCHZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) k_p1_mszip<nt, lr, dr, lc><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipShared<nt, lr, dr, lc>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             ZIP_VARIANTS(LAUNCHZ)
 #undef LAUNCHZ
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; }
+            mark(0, st); mark(1, st);
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
+            mark(0, st);
 #define LAUNCH(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) k_p1_lzx<nt, mr, lr, lc, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxShared<nt, mr, lr, lc, lb>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZX_VARIANTS(LAUNCH)
 #undef LAUNCH
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; }
+            mark(0, st); mark(1, st);
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
+            mark(0, st);
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_q, f0, f1); ctx->launches += 2; }
+            mark(0, st); mark(1, st);
+            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_q, f0, f1); ctx->launches += 2; mark(1, st); }
     };
     auto launch_tail = [&](uint32_t sub, cudaStream_t st) {
         uint32_t f0 = sub * subsz, f1;
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
-            k_e8<<<(f1 - f0 + 7) / 8, 256, 0, st>>>(a, d_ord_l, f0, f1, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; }
+            mark(2, st);
+            k_e8<<<(f1 - f0 + 7) / 8, 256, 0, st>>>(a, d_ord_l, f0, f1, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; mark(2, st); }
     };
     for (uint32_t sub = 0; sub < nsub; sub++) {
         cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
@@ -432,6 +468,7 @@ extern "C" int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units
     size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec) + MS_LITCAP) + sizeof(MsUnitState) + 6144;
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
     ctx->ev_used = 0;
+    for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
     for (size_t lo = 0; lo < n; lo += slots) {
         size_t hi = lo + slots < n ? lo + slots : n;
         int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s);
