@@ -1,0 +1,202 @@
+/* mspack_dropin.c - lzxd_* / qtmd_* / mszipd_* with the reference's signatures, on top of the GPU batch
+ * decoder (include/msgpu.h, n == 1 per stream).  Link this instead of the reference's lzxd.c, qtmd.c and
+ * mszipd.c and cabd.c / chmd.c work unchanged.
+ *
+ * Stream model.  The reference codecs are pull/push state machines: X_decompress(state, n) must deliver
+ * exactly n more bytes to system->write, reading input through system->read as it goes.
+ * A GPU wants the whole unit, so the first X_decompress call slurps the input until read() reports EOF
+ * (for a CAB folder that is also when cabd_sys_read announces the final length through
+ * lzxd_set_output_length, cabd.c:1335-1340), decodes on the device, and the calls then replay the
+ * decoded bytes.  Errors stay lazy like the reference's: if the whole unit does not decode, only the
+ * frames needed for the current request are decoded, so a request that ends before a corrupt frame still
+ * succeeds and the error (sticky, lzxd.c:396) surfaces with the first request that reaches it.
+ *
+ * There is no CPU decoder here: without a CUDA device X_init returns NULL (-> MSPACK_ERR_NOMEMORY in cabd.c:1255).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#include "mspack_dropin.h"
+#include "msgpu.h"
+
+#define FRAME 32768
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;    /* one device context per process, calls serialised */
+static msgpu_ctx *g_ctx;
+
+static msgpu_ctx *ctx_get(void) {
+    if (!g_ctx) {
+        const char *d = getenv("MSGPU_DEVICE");
+        g_ctx = msgpu_create(d ? atoi(d) : 0);
+    }
+    return g_ctx;
+}
+
+struct dstream {                     /* common state; the three public stream types are this struct */
+    struct mspack_system *sys;
+    struct mspack_file *input, *output;
+    int codec, window_bits, reset_interval, repair_mode;
+    off_t length;                    /* LZX: total output length if known (0 = not yet) */
+    off_t offset;                    /* bytes delivered to write() so far */
+    int error;                       /* sticky */
+    unsigned char *in; size_t in_len, in_cap; int in_done;
+    unsigned char *out; size_t out_len;  /* decoded prefix [0, out_len) */
+    int whole_failed;                /* the whole-unit decode failed: fall back to request-sized prefixes */
+};
+
+static struct dstream *ds_new(struct mspack_system *sys, struct mspack_file *in, struct mspack_file *out, int codec) {
+    struct dstream *s;
+    if (!sys) return NULL;
+    pthread_mutex_lock(&g_mu);
+    if (!ctx_get()) { pthread_mutex_unlock(&g_mu); return NULL; }
+    pthread_mutex_unlock(&g_mu);
+    s = (struct dstream *) sys->alloc(sys, sizeof(*s));
+    if (!s) return NULL;
+    memset(s, 0, sizeof(*s));
+    s->sys = sys; s->input = in; s->output = out; s->codec = codec;
+    return s;
+}
+
+static void ds_free(struct dstream *s) {
+    if (!s) return;
+    free(s->in); free(s->out);
+    s->sys->free(s);
+}
+
+/* read the unit's whole input through system->read (mspack.h:329-338: a short read or 0 means EOF) */
+static int ds_slurp(struct dstream *s) {
+    if (s->in_done) return MSPACK_ERR_OK;
+    for (;;) {
+        int got;
+        if (s->in_len + 65536 > s->in_cap) {
+            size_t ncap = s->in_cap ? s->in_cap * 2 : (1u << 18);
+            unsigned char *p = (unsigned char *) realloc(s->in, ncap);
+            if (!p) return MSPACK_ERR_NOMEMORY;
+            s->in = p; s->in_cap = ncap;
+        }
+        got = s->sys->read(s->input, s->in + s->in_len, 65536);
+        if (got < 0) return MSPACK_ERR_READ;
+        if (got == 0) break;
+        s->in_len += (size_t) got;
+    }
+    s->in_done = 1;
+    return MSPACK_ERR_OK;
+}
+
+/* decode the unit's first `want` output bytes on the device */
+static int ds_decode(struct dstream *s, size_t want) {
+    msgpu_unit u; int32_t st = -1; int rc; unsigned char *buf;
+    buf = (unsigned char *) realloc(s->out, want + 64);
+    if (!buf) return MSPACK_ERR_NOMEMORY;
+    s->out = buf;
+    memset(&u, 0, sizeof(u));
+    u.codec = (uint8_t) s->codec; u.window_bits = (uint8_t) s->window_bits; u.reset_interval = (uint16_t) s->reset_interval;
+    u.flags = s->repair_mode ? MSGPU_FLAG_MSZIP_REPAIR : 0;
+    u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = 0; u.out_len = (uint32_t) want;
+    pthread_mutex_lock(&g_mu);
+    rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len + 0, s->out, want, &st);
+    pthread_mutex_unlock(&g_mu);
+    if (rc) return MSPACK_ERR_NOMEMORY;
+    if (st == MSGPU_ERR_OK) { s->out_len = want; return MSPACK_ERR_OK; }
+    return st;
+}
+
+static int ds_decompress(struct dstream *s, off_t out_bytes) {
+    size_t end; int e;
+    if (!s || out_bytes < 0) return MSPACK_ERR_ARGS;
+    if (s->error) return s->error;
+    if (out_bytes == 0) return MSPACK_ERR_OK;
+    if ((e = ds_slurp(s))) return s->error = e;
+    if (s->in_len >= 0x7FFFFFF0u || (uint64_t) s->offset + (uint64_t) out_bytes > 0xFFFFFFFFu) return s->error = MSPACK_ERR_DECRUNCH;
+    end = (size_t) (s->offset + out_bytes);
+    if (end > s->out_len) {
+        /* first try the whole unit (its length is known for LZX once the input has been read) ... */
+        if (!s->whole_failed) {
+            size_t whole = (s->codec == MSGPU_CODEC_LZX && s->length > 0 && (size_t) s->length >= end) ? (size_t) s->length : end;
+            e = ds_decode(s, whole);
+            if (e && whole > end) { s->whole_failed = 1; e = -1; }
+        }
+        else e = -1;
+        /* ... and if that fails, just the frames this request needs (errors stay as lazy as the reference's) */
+        if (e == -1) {
+            size_t want = (end + FRAME - 1) / FRAME * FRAME;
+            if (s->codec == MSGPU_CODEC_LZX && s->length > 0 && want > (size_t) s->length) want = (size_t) s->length;
+            if (s->codec != MSGPU_CODEC_LZX) want = end;
+            e = ds_decode(s, want);
+        }
+        if (e) return s->error = e;
+    }
+    /* replay: exactly out_bytes more bytes to write() (mspack.h:346-355 write must return the count) */
+    while (out_bytes > 0) {
+        int n = out_bytes > (1 << 20) ? (1 << 20) : (int) out_bytes;
+        if (s->sys->write(s->output, s->out + s->offset, n) != n) return s->error = MSPACK_ERR_WRITE;
+        s->offset += n; out_bytes -= n;
+    }
+    return MSPACK_ERR_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ LZX */
+struct lzxd_stream *lzxd_init(struct mspack_system *system, struct mspack_file *input, struct mspack_file *output,
+                              int window_bits, int reset_interval, int input_buffer_size, off_t output_length, char is_delta)
+{
+    struct dstream *s;
+    if (is_delta) return NULL;                                   /* LZX DELTA (oabd.c) is outside the GPU path: SURVEY.md 8(f4) */
+    if (window_bits < 15 || window_bits > 21) return NULL;       /* lzxd.c:294-296 */
+    if (reset_interval < 0 || output_length < 0) return NULL;    /* :298-301 */
+    input_buffer_size = (input_buffer_size + 1) & -2;
+    if (input_buffer_size < 2) return NULL;                      /* :304-305 */
+    if (reset_interval > 0xFFFF) return NULL;
+    s = ds_new(system, input, output, MSGPU_CODEC_LZX);
+    if (!s) return NULL;
+    s->window_bits = window_bits; s->reset_interval = reset_interval; s->length = output_length;
+    return (struct lzxd_stream *) s;
+}
+void lzxd_set_output_length(struct lzxd_stream *lzx, off_t out_bytes) {     /* lzxd.c:384-386 */
+    struct dstream *s = (struct dstream *) lzx;
+    if (s && out_bytes > 0) s->length = out_bytes;
+}
+int lzxd_set_reference_data(struct lzxd_stream *lzx, struct mspack_system *system, struct mspack_file *input, unsigned int length) {
+    (void) system; (void) input; (void) length;
+    return lzx ? MSPACK_ERR_ARGS : MSPACK_ERR_ARGS;              /* lzxd.c:355-358: only LZX DELTA streams take reference data */
+}
+int lzxd_decompress(struct lzxd_stream *lzx, off_t out_bytes) { return ds_decompress((struct dstream *) lzx, out_bytes); }
+void lzxd_free(struct lzxd_stream *lzx) { ds_free((struct dstream *) lzx); }
+
+/* ------------------------------------------------------------------------------------------ Quantum */
+struct qtmd_stream *qtmd_init(struct mspack_system *system, struct mspack_file *input, struct mspack_file *output,
+                              int window_bits, int input_buffer_size)
+{
+    struct dstream *s;
+    if (window_bits < 10 || window_bits > 21) return NULL;       /* qtmd.c:199 */
+    input_buffer_size = (input_buffer_size + 1) & -2;
+    if (input_buffer_size < 2) return NULL;
+    s = ds_new(system, input, output, MSGPU_CODEC_QUANTUM);
+    if (!s) return NULL;
+    s->window_bits = window_bits;
+    return (struct qtmd_stream *) s;
+}
+int qtmd_decompress(struct qtmd_stream *qtm, off_t out_bytes) { return ds_decompress((struct dstream *) qtm, out_bytes); }
+void qtmd_free(struct qtmd_stream *qtm) { ds_free((struct dstream *) qtm); }
+
+/* ------------------------------------------------------------------------------------------ MSZIP */
+struct mszipd_stream *mszipd_init(struct mspack_system *system, struct mspack_file *input, struct mspack_file *output,
+                                  int input_buffer_size, int repair_mode)
+{
+    struct dstream *s;
+    input_buffer_size = (input_buffer_size + 1) & -2;
+    if (input_buffer_size < 2) return NULL;                      /* mszipd.c:345-347 */
+    if (repair_mode) return NULL;                                /* repair mode (cabd fix_mszip) is not implemented on the device yet */
+    s = ds_new(system, input, output, MSGPU_CODEC_MSZIP);
+    if (!s) return NULL;
+    s->repair_mode = repair_mode;
+    return (struct mszipd_stream *) s;
+}
+int mszipd_decompress(struct mszipd_stream *zip, off_t out_bytes) { return ds_decompress((struct dstream *) zip, out_bytes); }
+int mszipd_decompress_kwaj(struct mszipd_stream *zip) {
+    /* KWAJ framing (kwajd.c:320-322, mszipd.c:462-495) is outside the CAB-folder hot path; the symbol exists so
+     * that kwajd.c links, the call reports a format error */
+    return zip ? MSPACK_ERR_DATAFORMAT : MSPACK_ERR_ARGS;
+}
+void mszipd_free(struct mszipd_stream *zip) { ds_free((struct dstream *) zip); }
