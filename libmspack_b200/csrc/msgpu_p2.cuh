@@ -6,12 +6,12 @@
  *     match    byte (q - off) of the output   otherwise, where for an overlapping match (off < len) the
  *              source folds back into the off bytes in front of the match (the byte-serial copy of
  *              lzxd.c:636-646 / mszipd.c:271-296 / qtmd.c:391-416 replicates that seed pattern).
- * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Pass A maps every position of the
- * chunk to its record (one binary search per lane, then a walk); pass B fetches the bytes: sources in
- * earlier chunks are read back from the output buffer (it is the sliding window); a source inside the
- * current chunk is followed through the position map to ITS source until it leaves the chunk or hits
- * a literal (pointer jumping; positions strictly decrease so it terminates).  The chunk is then
- * stored with 16-byte stores.
+ * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Pass A turns every position of the chunk
+ * into a source descriptor (one binary search per lane, then a walk along the records); pass B fetches the
+ * bytes: sources in earlier chunks are read back from the output buffer (it is the sliding window); a
+ * source inside the current chunk is followed through the descriptors to ITS source until it leaves the
+ * chunk or hits a literal (pointer jumping; positions strictly decrease so it terminates).  The chunk is
+ * then stored with 16-byte stores.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -35,55 +35,62 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
     return lo;
 }
 
-/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> owning record (window index) into rid[]. */
-MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint16_t *rid)
+/* Per-byte source descriptor (pass A -> pass B), one u32 per position of the chunk:
+ *     bit 31 set : literal, low bits = index into the frame's literal stream
+ *     else       : match,   value   = (frame-relative source position) + P2_SBIAS   (the source may lie in
+ *                  earlier frames of the unit, i.e. be negative; overlapping matches are already folded) */
+#define P2_SBIAS (1 << 22)
+
+/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors.  One binary search per
+ * lane, then a walk along the records; the record is decoded once per segment, not per byte. */
+MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint32_t *src)
 {
     if (q0 >= size) return;
+    const uint32_t end16 = q0 + 16 < size ? q0 + 16 : size;
     int i = p2_search(wa, wb, q0);
-#pragma unroll 4
-    for (uint32_t k = 0; k < 16; k++) {
-        uint32_t q = q0 + k;
-        if (q >= size) break;
-        while (rec_pos(wa[i]) + rec_len(wb[i]) <= q) i++;
-        rid[q - c] = (uint16_t) i;
-    }
-}
-
-/* One output byte whose source may lie inside the current chunk: follow the position map to ITS source
- * until a literal or an already-written byte is reached (positions strictly decrease). */
-MS_D uint32_t p2_chase(uint32_t q, uint32_t c, const uint32_t *wa, const uint32_t *wb, const uint16_t *rid,
-                       const uint8_t *lits, const uint8_t *unit_out, uint32_t g0)
-{
+    uint32_t q = q0;
 #pragma unroll 1
-    for (;;) {
-        int i = rid[q - c];
-        uint32_t a = wa[i], b = wb[i], pos = rec_pos(a);
-        if (q < pos) return lits[q - rec_M(a)];
-        uint32_t off = rec_off(b), len = rec_len(b), kk = q - pos;
-        int32_t s;                                            /* frame-relative source position, may be negative */
-        if (off < len && kk >= off) s = (int32_t) (pos - off + (kk % off));
-        else s = (int32_t) q - (int32_t) off;
-        if (s < (int32_t) c) {
-            int64_t g = (int64_t) g0 + s;                     /* unit-relative */
-            return g >= 0 ? unit_out[g] : 0u;                 /* before the unit's first byte: defined as zero */
+    while (q < end16) {
+        uint32_t a = wa[i], b = wb[i], pos = rec_pos(a), len = rec_len(b), mend = pos + len;
+        if (q >= mend) { i++; continue; }
+        if (q < pos) {                                        /* literal run up to the match */
+            uint32_t e = pos < end16 ? pos : end16, li = (q - rec_M(a)) | 0x80000000u;
+#pragma unroll 1
+            for (; q < e; q++, li++) src[q - c] = li;
+            continue;
         }
-        q = (uint32_t) s;
+        uint32_t off = rec_off(b), e = mend < end16 ? mend : end16;
+        if (off >= len) {                                     /* plain match: consecutive sources */
+            uint32_t sv = q - off + P2_SBIAS;
+#pragma unroll 1
+            for (; q < e; q++, sv++) src[q - c] = sv;
+        }
+        else {                                                /* overlapping match: fold onto the off seed bytes in front of it */
+            uint32_t kk = (q - pos) % off, seed = pos - off + P2_SBIAS;
+#pragma unroll 1
+            for (; q < e; q++) { src[q - c] = seed + kk; if (++kk == off) kk = 0; }
+        }
     }
 }
 
-/* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.
- * Every lane runs the same per-byte loop (keeps the warp converged); a source inside the current chunk
- * is chased through the position map. */
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, const uint16_t *rid,
+/* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.  A source
+ * inside the current chunk is followed through the descriptors to ITS source (pointer jumping; positions
+ * strictly decrease so it terminates). */
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
                     const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
+    const int64_t gbase = (int64_t) g0 - P2_SBIAS;
 #pragma unroll 4
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t q = q0 + k;
         if (q >= size) break;
-        uint32_t v = p2_chase(q, c, wa, wb, rid, lits, unit_out, g0);
+        uint32_t d = src[q - c], v;
+#pragma unroll 1
+        while (!(d & 0x80000000u) && d >= c + P2_SBIAS) d = src[d - P2_SBIAS - c];    /* chase inside the chunk */
+        if (d & 0x80000000u) v = lits[d & 0x7FFFFFFFu];
+        else { int64_t g = gbase + d; v = g >= 0 ? unit_out[g] : 0u; }               /* before the unit's first byte: zero */
         w[k >> 2] |= v << (8 * (k & 3));
     }
 }
@@ -92,7 +99,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, 
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, const uint8_t *lits,
                                                  uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint16_t *rid)
+                                                 uint32_t *wa, uint32_t *wb, uint32_t *src)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -107,9 +114,9 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
-        p2_pass_a(q0, c, size, wa, wb, rid);
+        p2_pass_a(q0, c, size, wa, wb, src);
         __syncwarp();
-        p2_pass_b(q0, c, size, wa, wb, rid, lits, unit_out, g0, w);
+        p2_pass_b(q0, c, size, src, lits, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
