@@ -40,6 +40,9 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
  *     else       : match,   value   = (frame-relative source position) + P2_SBIAS   (the source may lie in
  *                  earlier frames of the unit, i.e. be negative; overlapping matches are already folded) */
 #define P2_SBIAS (1 << 22)
+/* descriptor of chunk position p (0..511) lives at P2_SIDX(p): transposed (byte-in-lane major, lane minor) so
+ * that the 32 lanes, which all touch "their k-th byte" at the same time, hit 32 different banks */
+#define P2_SIDX(p) ((((p) & 15u) << 5) | ((p) >> 4))
 
 /* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors.  One binary search per
  * lane, then a walk along the records; the record is decoded once per segment, not per byte. */
@@ -56,19 +59,19 @@ MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, 
         if (q < pos) {                                        /* literal run up to the match */
             uint32_t e = pos < end16 ? pos : end16, li = (q - rec_M(a)) | 0x80000000u;
 #pragma unroll 1
-            for (; q < e; q++, li++) src[q - c] = li;
+            for (; q < e; q++, li++) src[P2_SIDX(q - c)] = li;
             continue;
         }
         uint32_t off = rec_off(b), e = mend < end16 ? mend : end16;
         if (off >= len) {                                     /* plain match: consecutive sources */
             uint32_t sv = q - off + P2_SBIAS;
 #pragma unroll 1
-            for (; q < e; q++, sv++) src[q - c] = sv;
+            for (; q < e; q++, sv++) src[P2_SIDX(q - c)] = sv;
         }
         else {                                                /* overlapping match: fold onto the off seed bytes in front of it */
             uint32_t kk = (q - pos) % off, seed = pos - off + P2_SBIAS;
 #pragma unroll 1
-            for (; q < e; q++) { src[q - c] = seed + kk; if (++kk == off) kk = 0; }
+            for (; q < e; q++) { src[P2_SIDX(q - c)] = seed + kk; if (++kk == off) kk = 0; }
         }
     }
 }
@@ -86,9 +89,9 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t q = q0 + k;
         if (q >= size) break;
-        uint32_t d = src[q - c], v;
+        uint32_t d = src[P2_SIDX(q - c)], v;
 #pragma unroll 1
-        while (!(d & 0x80000000u) && d >= c + P2_SBIAS) d = src[d - P2_SBIAS - c];    /* chase inside the chunk */
+        while (!(d & 0x80000000u) && d >= c + P2_SBIAS) d = src[P2_SIDX(d - P2_SBIAS - c)];    /* chase inside the chunk */
         if (d & 0x80000000u) v = lits[d & 0x7FFFFFFFu];
         else { int64_t g = gbase + d; v = g >= 0 ? unit_out[g] : 0u; }               /* before the unit's first byte: zero */
         w[k >> 2] |= v << (8 * (k & 3));
