@@ -19,6 +19,7 @@
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
 #include "msgpu_p1_lzx.cuh"
+#include "msgpu_p1_lzx_c.cuh"
 #include "msgpu_p1_qtm.cuh"
 #include "msgpu_p2.cuh"
 
@@ -80,6 +81,26 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
+        st = a.ustate[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+                a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
+    }
+    p1_run(t);
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
+}
+
+template <int NT, int HEADN>
+__global__ void __launch_bounds__(NT) k_p1_lzx_c(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
+                                                 int32_t *e8info, const uint32_t *e8base)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
+    const bool valid = ti < count;
+    uint32_t slot = valid ? order[ti] : 0;
+    LzxLaneC<NT, HEADN> t; t.phase = PH_IDLE;
+    MsUnitState st;
+    if (valid) {
+        t.bind(reinterpret_cast<LzxSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
@@ -160,6 +181,8 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 /* LZX P1 variants (threads per CTA, main LUT bits, length LUT bits, long-symbol cache entries, literals per step);
  * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
 #define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
+/* table-free canonical LZX lanes (id, threads per CTA, shared-memory head entries) */
+#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64) X(14, 448, 32)
 #define QTM_NT 128
 
 struct DevBuf {
@@ -232,6 +255,9 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTR(id, nt, mr, lr, lc, lb) cudaFuncSetAttribute(k_p1_lzx<nt, mr, lr, lc, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<nt, mr, lr, lc, lb>));
     LZX_VARIANTS(SETATTR)
 #undef SETATTR
+#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx_c<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
+    LZXC_VARIANTS(SETATTRC)
+#undef SETATTRC
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 0; }
     cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
     return c;
@@ -316,13 +342,16 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNT(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZX_VARIANTS(PICKNT)
 #undef PICKNT
+#define PICKNTC(id, nt, hn) if (ctx->lzx_variant == id) lzx_nt = nt;
+    LZXC_VARIANTS(PICKNTC)
+#undef PICKNTC
 #define PICKNTZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) zip_nt = nt;
     ZIP_VARIANTS(PICKNTZ)
 #undef PICKNTZ
     /* sub-wave size: a multiple of every CTA size in use (32 * 3 * 4 * 7 = 2688 covers 96/128/192/224 threads),
      * about one resident P1 CTA per SM */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
-    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u;
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* 10752 = lcm(96..512 CTA sizes in use) */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     subsz = (subsz + gran - 1) / gran * gran;
     const uint32_t nmaxc = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
@@ -396,6 +425,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define LAUNCH(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) k_p1_lzx<nt, mr, lr, lc, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxShared<nt, mr, lr, lc, lb>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZX_VARIANTS(LAUNCH)
 #undef LAUNCH
+#define LAUNCHC(id, nt, hn) if (ctx->lzx_variant == id) k_p1_lzx_c<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+            LZXC_VARIANTS(LAUNCHC)
+#undef LAUNCHC
             mark(0, st); mark(1, st);
             k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;

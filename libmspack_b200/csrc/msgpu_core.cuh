@@ -279,6 +279,89 @@ struct MsHuffLong {
 };
 
 /* =============================================================================================
+ * Table-free canonical decoding ("C" lanes).
+ *
+ * The LUT lanes above need ~1 KB of shared memory per lane, which caps a B200 SM at ~6 warps and leaves the
+ * entropy kernels latency bound.  A canonical code needs no table at all to find a code's LENGTH: with
+ * limit[l] = left-aligned upper bound of the l-bit codes,  len = 1 + #{ l in 1..15 : v16 >= limit[l] }
+ * - fifteen independent compares against values kept in REGISTERS.  The symbol is then
+ * sorted[offs[len] + ((v16 - limit[len-1]) >> (16 - len))]: a 17-entry base/offset table in shared memory
+ * (64 B per lane), the first HEADN symbols of the canonical order (the shortest = most frequent codes) in
+ * shared memory, the rest in lane-interleaved global scratch.  ~0.4 KB per lane -> 14-16 warps per SM.
+ * ============================================================================================= */
+
+/* Build.  bo[l * NT] (l = 1..16) = limit[l-1] >> 1 | offs[l] << 16; limv[l-1] = limit[l]; sorted[k * 32] and
+ * head[k * NT] (k < headn) receive the symbols in canonical order; an optional ROOT-bit MSB-first LUT
+ * (u16 = sym << 4 | len, 0 = longer code) is filled as well.  Returns 0 iff make_decode_table would succeed
+ * (same acceptance rule as ms_huff_build). */
+template <int ROOT, int NT, class LensFn>
+MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
+                        uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
+{
+#pragma unroll 1
+    for (int l = 0; l <= 16; l++) cnt[l * NT] = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsyms; s++) { uint32_t l = lens(s); if (l >= 1 && l <= 16) cnt[l * NT]++; }
+    uint32_t sum_short = 0, sum_all = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 16; l++) { sum_all += (uint32_t) cnt[l * NT] << (16 - l); if (l <= ref_tablebits) sum_short = sum_all; }
+    int maxlen = 16;
+    if (sum_short > 65536u) return 1;
+    if (sum_short == 65536u) maxlen = ref_tablebits;
+    else if (sum_all != 65536u) return 1;
+    uint32_t lim = 0, off = 0;
+#pragma unroll
+    for (int l = 1; l <= 16; l++) {
+        uint32_t c = (l <= maxlen) ? cnt[l * NT] : 0;
+        bo[l * NT] = (lim >> 1) | (off << 16);
+        cnt[l * NT] = (uint16_t) off;                       /* running index of the next l-bit symbol */
+        lim += c << (16 - l); limv[l - 1] = lim; off += c;
+    }
+    if (ROOT > 0) {
+#pragma unroll 1
+        for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
+    }
+#pragma unroll 1
+    for (int s = 0; s < nsyms; s++) {
+        int l = (int) lens(s);
+        if (l < 1 || l > maxlen) continue;
+        uint32_t k = cnt[l * NT]; cnt[l * NT] = (uint16_t) (k + 1);
+        sorted[k * MS_WARP] = (uint16_t) s;
+        if (k < headn) head[k * NT] = (uint16_t) s;
+        if (ROOT > 0 && l <= ROOT) {
+            uint32_t b = bo[l * NT];
+            uint32_t code = (((b & 0xFFFFu) << 1) >> (16 - l)) + (k - (b >> 16));
+            uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
+            for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = (uint16_t) ((s << 4) | l);
+        }
+    }
+    return 0;
+}
+
+/* code length from limits in registers: lim[j] = limit[j + 1] */
+MS_D int ms_canon_len(const uint32_t lim[15], uint32_t v16) {
+    int len = 1;
+#pragma unroll
+    for (int j = 0; j < 15; j++) len += (v16 >= lim[j]) ? 1 : 0;
+    return len;
+}
+/* code length from limits in shared memory (rarely used trees): lim16[(j) * NT] = limit[j + 1] >> 1 (limits of
+ * lengths <= 15 are even, so the halved compare is exact) */
+template <int NT>
+MS_D int ms_canon_len_smem(const uint16_t *lim16, uint32_t v16) {
+    int len = 1; uint32_t h = v16 >> 1;
+#pragma unroll
+    for (int j = 0; j < 15; j++) len += (h >= lim16[j * NT]) ? 1 : 0;
+    return len;
+}
+/* canonical index of the code v16 of length len */
+template <int NT>
+MS_D uint32_t ms_canon_index(const uint32_t *bo, uint32_t v16, int len) {
+    uint32_t b = bo[len * NT];
+    return (b >> 16) + ((v16 - ((b & 0xFFFFu) << 1)) >> (16 - len));
+}
+
+/* =============================================================================================
  * Record / literal emission (P1 -> P2 intermediate form)
  * ============================================================================================= */
 struct MsEmit {

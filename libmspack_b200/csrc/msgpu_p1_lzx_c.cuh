@@ -1,0 +1,396 @@
+/* msgpu_p1_lzx_c.cuh - P1 entropy stage for LZX units, table-free canonical variant ("C" lanes).
+ *
+ * Same state machine, same bitstream semantics and the same reference citations as msgpu_p1_lzx.cuh
+ * (lzxd.c:388-771); only the Huffman machinery differs: no per-lane decode LUT for the main tree, code
+ * lengths come from 15 register-resident limits, symbols from a small shared-memory head + global scratch
+ * (msgpu_core.cuh "Table-free canonical decoding").  ~0.4 KB of shared memory per lane instead of ~1 KB, so
+ * 14-16 warps per SM instead of 6.
+ */
+#pragma once
+#include "msgpu_core.cuh"
+#include "msgpu_p1_lzx.cuh"      /* LZX_AUX_* layout, constants */
+
+/* HEADN = main-tree symbols (shortest codes first) kept in shared memory */
+template <int NT, int HEADN>
+struct LzxSharedC {
+    uint32_t mbo[17 * NT];                /* main tree: limit[l-1] >> 1 | offs[l] << 16 */
+    uint32_t lbo[17 * NT];                /* LENGTH tree; hosts the pretree while code lengths are being read */
+    uint32_t abo[17 * NT];                /* aligned-offset tree */
+    uint16_t mhead[HEADN * NT];           /* first HEADN main symbols in canonical order */
+    uint16_t llim[16 * NT];               /* LENGTH / pretree limits >> 1 */
+    uint16_t alim[16 * NT];               /* aligned tree limits >> 1 */
+    uint16_t llut[32 * NT];               /* 5-bit LUT of the LENGTH tree */
+    uint16_t cnt[17 * NT];
+};
+
+template <int NT, int HEADN>
+struct LzxLaneC {
+    MsBits b;
+    uint32_t *mbo, *lbo, *abo;
+    uint16_t *mhead, *llim, *alim, *llut, *cnt;
+    uint8_t *main_len, *len_len;
+    MsHuffAux ma, la, pa, aa;             /* only .sorted is used (global scratch) */
+    uint32_t mlim[15];                    /* main tree limit[1..15], registers */
+    uint32_t R0, R1, R2, block_type, block_length, block_remaining, header_read, intel_started, length_empty, aligned_lens;
+    int32_t intel_filesize;
+    uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
+    int32_t bytepos;                      /* valid in bytemode: next raw byte (relative to b.in) */
+    /* unit / launch context */
+    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; int32_t *e8info;
+    MsEmit em;
+    uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
+    int f, max_frames;
+
+    MS_M void bind(LzxSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
+        mbo = sh->mbo + tid; lbo = sh->lbo + tid; abo = sh->abo + tid; mhead = sh->mhead + tid;
+        llim = sh->llim + tid; alim = sh->alim + tid; llut = sh->llut + tid; cnt = sh->cnt + tid;
+        main_len = aux_warp + LZX_AUX_MAINLEN + lane; len_len = aux_warp + LZX_AUX_LENLEN + lane;
+        ma.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_MSORT) + lane;
+        la.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_LSORT) + lane;
+        pa.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_PSORT) + lane;
+        aa.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_ASORT) + lane;
+        uint32_t *lim = reinterpret_cast<uint32_t *>(aux_warp + LZX_AUX_LIMIT) + lane;
+        uint16_t *off = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_OFFS) + lane;
+        ma.limit = lim; la.limit = lim + 20 * 32; pa.limit = lim + 40 * 32; aa.limit = lim + 60 * 32;
+        ma.offs = off; la.offs = off + 20 * 32; pa.offs = off + 40 * 32; aa.offs = off + 60 * 32;
+    }
+
+    MS_M void reset_state() {                 /* lzxd.c:257-270 */
+        R0 = R1 = R2 = 1; header_read = 0; block_remaining = 0; block_type = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < nsyms_eff; i++) main_len[i * 32] = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < LZX_LEN_SYMS; i++) len_len[i * 32] = 0;
+    }
+
+    /* READ_HUFFSYM for a tree whose limits live in shared memory (pretree, LENGTH slow path, aligned tree) */
+    MS_M uint32_t sym_smem(const uint16_t *lim16, const uint32_t *bo, const uint16_t *sorted) {
+        lzx_check(b, 16);
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len_smem<NT>(lim16, v16);
+        uint32_t idx = ms_canon_index<NT>(bo, v16, len);
+        msb_drop(b, len);
+        return sorted[idx * MS_WARP];
+    }
+    MS_M uint32_t length_sym() {              /* LENGTH tree: 5-bit LUT, then the canonical path */
+        lzx_check(b, 16);
+        uint32_t e = llut[msb_peek(b, 5) * NT];
+        if (e & 15) { msb_drop(b, (int) (e & 15)); return e >> 4; }
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len_smem<NT>(llim, v16);
+        uint32_t idx = ms_canon_index<NT>(lbo, v16, len);
+        msb_drop(b, len);
+        return la.sorted[idx * MS_WARP];
+    }
+
+    /* raw byte access for uncompressed blocks; READ_IF_NEEDED semantics (readbits.h:182-214) */
+    MS_M uint32_t raw_byte() {
+        if (bytepos > b.in_len + 1) { b.err = MS_EREAD; return 0; }
+        uint32_t v = bytepos < b.in_len ? b.in[bytepos] : 0u;
+        bytepos++;
+        return v;
+    }
+
+    /* the reference's bit buffer is empty and its byte pointer is at bytepos: go back to bit reading.
+     * An odd byte pointer (odd-sized uncompressed block whose pad byte was not skipped because a reset
+     * cleared block_type first, lzxd.c:257-270 vs :469-474) moves the 16-bit word grid by one byte. */
+    MS_M void enter_bits() {
+        if (!bytemode) return;
+        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; }
+        ms_bits_seek(b, bytepos & ~3);
+        lzx_refill(b);
+        if (bytepos & 2) msb_drop(b, 16);
+        bytemode = 0;
+    }
+
+    /* lzxd.c:138-183: pretree-delta coded lengths; runs are not clamped to `last` */
+    MS_M int read_lens(uint8_t *lens, uint32_t first, uint32_t last) {
+        uint64_t plo = 0; uint32_t phi = 0; uint32_t lv[16];
+#pragma unroll 1
+        for (int x = 0; x < 20; x++) {
+            lzx_refill(b);
+            uint32_t y = lzx_read(b, 4);
+            if (x < 16) plo |= (uint64_t) y << (4 * x); else phi |= y << (4 * (x - 16));
+        }
+        if (b.err) return b.err;
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
+                                  20, 6, lbo, cnt, pa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
+#pragma unroll 1
+        for (uint32_t x = first; x < last;) {
+            lzx_refill(b);
+            int z = (int) sym_smem(llim, lbo, pa.sorted);
+            if (b.err) return b.err;
+            if (z == 17) { uint32_t y = lzx_read(b, 4) + 4; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
+            else if (z == 18) { uint32_t y = lzx_read(b, 5) + 20; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
+            else if (z == 19) {
+                uint32_t y = lzx_read(b, 1) + 4;
+                lzx_refill(b);
+                z = (int) sym_smem(llim, lbo, pa.sorted);
+                if (b.err) return b.err;
+                z = (int) lens[x * 32] - z; if (z < 0) z += 17;
+                while (y--) { lens[x * 32] = (uint8_t) z; x++; }
+            }
+            else { z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
+        }
+        return 0;
+    }
+
+    MS_M int build_main() {
+        uint8_t *l = main_len; uint32_t lv[16];
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted, mhead, HEADN,
+                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) mlim[j] = lv[j];
+        return 0;
+    }
+    MS_M int build_length() {                 /* BUILD_TABLE_MAYBE_EMPTY, lzxd.c:111-125 */
+        uint8_t *l = len_len; uint32_t lv[16];
+        length_empty = 0;
+        if (ms_canon_build<5, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted, (uint16_t *) nullptr, 0, llut, lv)) {
+#pragma unroll 1
+            for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
+            length_empty = 1;
+        }
+        else {
+#pragma unroll
+            for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
+        }
+        return 0;
+    }
+    MS_M int build_aligned() {
+        uint32_t al = aligned_lens; uint32_t lv[16];
+        if (ms_canon_build<0, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, abo, cnt, aa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) alim[j * NT] = (uint16_t) (lv[j] >> 1);
+        return 0;
+    }
+
+    /* lzxd.c:465-523: read a block header.  Returns 0 or an MSPACK_ERR_* */
+    MS_M int block_header() {
+        if (block_type == 3 && (block_length & 1)) { (void) raw_byte(); if (b.err) return b.err; }     /* :469-474 */
+        enter_bits();
+        lzx_refill(b);
+        block_type = lzx_read(b, 3);
+        uint32_t i = lzx_read(b, 16);
+        lzx_refill(b);
+        uint32_t j = lzx_read(b, 8);
+        if (b.err) return b.err;
+        block_remaining = block_length = (i << 8) | j;
+        if (block_type == 2) {
+            uint32_t al = 0;
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) { lzx_refill(b); al |= lzx_read(b, 3) << (3 * k); }
+            if (b.err) return b.err;
+            aligned_lens = al;
+            int e = build_aligned(); if (e) return e;
+        }
+        if (block_type == 1 || block_type == 2) {
+            int e;
+            if ((e = read_lens(main_len, 0, 256))) return e;
+            if ((e = read_lens(main_len, 256, 256 + num_offsets))) return e;
+            if ((e = build_main())) return e;
+            if (main_len[0xE8 * 32] != 0) intel_started = 1;                                           /* :495 */
+            if ((e = read_lens(len_len, 0, 249))) return e;
+            if ((e = build_length())) return e;
+            return 0;
+        }
+        if (block_type == 3) {
+            intel_started = 1;                                                                         /* :503 */
+            /* :505-507 discard 1..16 bits up to the next 16-bit word */
+            int r = b.bc & 15;
+            if (r == 0) { lzx_refill(b); lzx_check(b, 16); if (b.err) return b.err; r = 16; }
+            msb_drop(b, r);
+            bytepos = b.ipos - (b.bc >> 3); bytemode = 1;
+            uint32_t v[3];
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) { uint32_t x = raw_byte(); x |= raw_byte() << 8; x |= raw_byte() << 16; x |= raw_byte() << 24; v[k] = x; }
+            if (b.err) return b.err;
+            R0 = v[0]; R1 = v[1]; R2 = v[2];
+            return 0;
+        }
+        return MS_EDECRUNCH;                                                                           /* :519-522 */
+    }
+
+    MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
+
+    /* lzxd.c:419-461: frame prologue (reset interval, intel header, frame size) */
+    MS_M void frame_start() {
+        frame_start_pos = produced;
+        if (u->reset_interval && (frame % u->reset_interval) == 0) reset_state();                     /* :423-438 */
+        if (!header_read) {                                                                          /* :447-453 */
+            enter_bits();
+            lzx_refill(b);
+            uint32_t hi = 0, lo = 0;
+            if (lzx_read(b, 1)) { lzx_refill(b); hi = lzx_read(b, 16); lzx_refill(b); lo = lzx_read(b, 16); }
+            if (b.err) { fail(b.err); return; }
+            intel_filesize = (int32_t) ((hi << 16) | lo); header_read = 1;
+        }
+        frame_size = ms_min(MS_FRAME, u->out_len - produced);                                        /* :458-461 */
+        bytes_todo = (int32_t) frame_size; q = 0;
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        phase = PH_BLOCK;
+    }
+
+    /* lzxd.c:463-532 + :654-671: next run of the frame; uncompressed runs are copied right here */
+    MS_M void next_run() {
+        if (bytes_todo <= 0) { phase = PH_END; return; }
+        if (block_remaining == 0) { int e = block_header(); if (e) { fail(e); return; } }
+        this_run = (int32_t) block_remaining;
+        if (this_run > bytes_todo) this_run = bytes_todo;
+        bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
+        if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
+        if (block_type == 3) {
+#pragma unroll 1
+            while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
+            if (b.err) fail(b.err);
+            return;
+        }
+        fail(MS_EDECRUNCH);
+    }
+
+    MS_M void frame_end() {
+        /* :696-697 re-align; after raw bytes the reference's bit buffer is empty and nothing happens */
+        if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) { fail(b.err); return; } msb_drop(b, b.bc & 15); }
+        emit_end(em, frame_size);
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = frame_size; fi.g0 = frame_start_pos; fi.valid = 1;
+        finfo[f] = fi;
+        e8info[frame] = (intel_started && intel_filesize && frame < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 */
+        produced += frame_size; frame++; f++;
+        if (produced >= u->out_len) {
+            done = 1; phase = PH_IDLE;
+            /* lzxd.c:419: a request ending exactly on a frame boundary runs one more zero-sized frame pass; at a
+             * reset point that re-reads the intel header and tops the bit buffer up (see oracle/port/mspack_port.c) -
+             * the only effect is MSPACK_ERR_READ on an exactly-cut unit */
+            if ((u->out_len % MS_FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
+                int32_t bp;
+                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; } bp = bytepos; }
+                else bp = b.ipos - (b.bc >> 3);
+                uint32_t hb = (bp + 1 < b.in_len) ? b.in[bp + 1] : 0u;
+                int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
+                if (bp + 2 > b.in_len + 2 || need > b.in_len + 2) status = MS_EREAD;
+            }
+        }
+        else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+    }
+
+    MS_M void service() {
+#pragma unroll 1
+        while (phase >= PH_FRAME) {
+            if (phase == PH_FRAME) frame_start();
+            else if (phase == PH_BLOCK) next_run();
+            else frame_end();
+        }
+    }
+
+    /* main-tree symbol: length from the register limits, symbol from the shared-memory head or global scratch */
+    MS_M uint32_t main_sym() {
+        lzx_check(b, 16);
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len(mlim, v16);
+        uint32_t idx = ms_canon_index<NT>(mbo, v16, len);
+        msb_drop(b, len);
+        return idx < (uint32_t) HEADN ? (uint32_t) mhead[idx * NT] : (uint32_t) ma.sorted[idx * MS_WARP];
+    }
+
+    /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset
+     * fields.  Batching literals keeps the lanes that are inside a literal run busy while the others
+     * handle a match, which is the longer path. */
+    MS_M void step() {
+        uint32_t sym;
+#pragma unroll 1
+        for (int rep = 0;; ) {
+            lzx_refill(b);
+            sym = main_sym();
+            if (sym >= 256) break;
+            emit_literal(em, sym); q++; this_run--;
+            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+            if (this_run <= 0) { phase = PH_BLOCK; return; }
+            if (++rep == 1) return;
+        }
+        {
+            sym -= 256;
+            uint32_t ml = sym & 7, slot = sym >> 3, off;
+            if (ml == 7) {
+                if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
+                ml += length_sym();
+            }
+            ml += 2;
+            if (slot == 0) off = R0;
+            else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
+            else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
+            else {
+                /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
+                uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                off = pbase - 2;
+                lzx_refill(b);
+                if (block_type == 2 && extra >= 3) {
+                    if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
+                    off += sym_smem(alim, abo, aa.sorted);
+                }
+                else if (extra) off += lzx_read(b, (int) extra);
+                R2 = R1; R1 = R0; R0 = off;
+            }
+            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start) */
+            uint32_t G = frame_start_pos + q, wpr = G & (window_size - 1), eff = off;
+            bool bad = (wpr + ml > window_size);
+            if (off > wpr) {
+                bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
+                if (off > window_size) eff = off - window_size;
+            }
+            if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
+            bad = bad || ((int32_t) ml > this_run);   /* :678-693 every overrun ends in an error */
+            if (MS_UNLIKELY(bad)) { fail(MS_EDECRUNCH); return; }
+            emit_match(em, q, ml, eff);
+            q += ml; this_run -= (int32_t) ml;
+        }
+        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (this_run <= 0) phase = PH_BLOCK;
+    }
+
+    MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
+                    int32_t *e8, int nframes) {
+        u = unit; recs = r; lits = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;
+        frame_start_pos = 0; frame_size = 0;
+#pragma unroll 1
+        for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
+        const int wb = unit->window_bits;
+        const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u : 50u;   /* position_slots[], lzxd.c:209-211 */
+        window_size = 1u << (wb & 31); num_offsets = slots << 3;
+        nsyms_eff = 256 + num_offsets + 51; if (nsyms_eff > LZX_MAIN_MAX) nsyms_eff = LZX_MAIN_MAX;
+        if (!st.started) {
+            done = 0; status = 0; produced = 0; frame = 0;
+            if (wb < 15 || wb > 21) { status = MS_ENOMEM; done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
+            ms_bits_init(b, in_base + unit->in_off, unit->in_len);
+            base = 0; bytemode = 0; bytepos = 0; intel_filesize = 0; intel_started = 0; length_empty = 0; aligned_lens = 0;
+            R0 = R1 = R2 = 1; header_read = 0; block_remaining = 0; block_type = 0; block_length = 0;
+            if (!done) reset_state();
+            if (unit->out_len == 0) done = 1;
+        }
+        else {
+            done = st.done; status = st.status; produced = st.produced; frame = st.frame;
+            base = st.base; bytemode = st.bytemode; bytepos = st.ipos;
+            ms_bits_restore(b, in_base + unit->in_off + base, unit->in_len - base, bytemode ? 0 : st.ipos, (int32_t) st.bc, ((uint64_t) st.bb_hi << 32) | st.bb_lo);
+            R0 = st.R0; R1 = st.R1; R2 = st.R2; block_type = st.block_type; block_length = st.block_length;
+            block_remaining = st.block_remaining; header_read = st.header_read; intel_filesize = (int32_t) st.intel_filesize;
+            intel_started = st.intel_started; length_empty = st.length_empty; aligned_lens = st.aligned_lens;
+            if (!done && block_remaining > 0 && (block_type == 1 || block_type == 2)) {
+                /* the shared-memory tables do not survive a launch: rebuild them from the stored lengths */
+                (void) build_main(); (void) build_length();
+                if (block_type == 2) (void) build_aligned();
+            }
+        }
+        phase = done ? PH_IDLE : PH_FRAME;
+    }
+    MS_M void end(MsUnitState &st) {
+        st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
+        st.base = base; st.bytemode = bytemode;
+        st.ipos = bytemode ? bytepos : b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
+        st.R0 = R0; st.R1 = R1; st.R2 = R2; st.block_type = block_type; st.block_length = block_length;
+        st.block_remaining = block_remaining; st.header_read = header_read; st.intel_filesize = (uint32_t) intel_filesize;
+        st.intel_started = intel_started; st.length_empty = length_empty; st.aligned_lens = aligned_lens;
+    }
+};

@@ -14,6 +14,7 @@
 #include "../../libmspack_b200/csrc/msgpu_core.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_mszip.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_lzx.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p1_lzx_c.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_qtm.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
@@ -84,6 +85,20 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
             TH t; t.bind(sh, 0, aux, 0);
             t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
             emul_run(t); t.end(st); resolve();
+        }
+        free(sh); free(aux);
+    }
+    else if (u->codec == MSGPU_CODEC_LZX && getenv("MSGPU_EMUL_LZXC")) {          /* table-free canonical lanes */
+        typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
+        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            TH t; t.bind(sh, 0, aux, 0);
+            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
+            emul_run(t); t.end(st); resolve();
+        }
+        for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
+            uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
+            if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) start, e8info[f]);
         }
         free(sh); free(aux);
     }
