@@ -258,7 +258,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx_c<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
-    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 0; }
+    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 11; }
     cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
     return c;
 }

@@ -44,56 +44,55 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
  * that the 32 lanes, which all touch "their k-th byte" at the same time, hit 32 different banks */
 #define P2_SIDX(p) ((((p) & 15u) << 5) | ((p) >> 4))
 
-/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors.  One binary search per
- * lane, then a walk along the records; the record is decoded once per segment, not per byte. */
+/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors.  One binary search per lane,
+ * then the same 16-iteration loop in every lane (the current record's fields stay in registers; stepping to the
+ * next record is the only data-dependent part), so the warp stays converged. */
 MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint32_t *src)
 {
     if (q0 >= size) return;
-    const uint32_t end16 = q0 + 16 < size ? q0 + 16 : size;
     int i = p2_search(wa, wb, q0);
-    uint32_t q = q0;
-#pragma unroll 1
-    while (q < end16) {
-        uint32_t a = wa[i], b = wb[i], pos = rec_pos(a), len = rec_len(b), mend = pos + len;
-        if (q >= mend) { i++; continue; }
-        if (q < pos) {                                        /* literal run up to the match */
-            uint32_t e = pos < end16 ? pos : end16, li = (q - rec_M(a)) | 0x80000000u;
-#pragma unroll 1
-            for (; q < e; q++, li++) src[P2_SIDX(q - c)] = li;
-            continue;
+    uint32_t a = wa[i], b = wb[i];
+    uint32_t pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b), mend = pos + len;
+#pragma unroll 4
+    for (uint32_t k = 0; k < 16; k++) {
+        uint32_t q = q0 + k, d;
+        if (q >= size) break;
+        while (q >= mend) { i++; a = wa[i]; b = wb[i]; pos = rec_pos(a); M = rec_M(a); off = rec_off(b); len = rec_len(b); mend = pos + len; }
+        if (q < pos) d = (q - M) | 0x80000000u;                               /* literal */
+        else {
+            uint32_t kk = q - pos;
+            if (off >= len || kk < off) d = q - off + P2_SBIAS;                /* plain match byte */
+            else d = pos - off + (kk % off) + P2_SBIAS;                        /* overlapping match: fold onto the seed bytes in front of it */
         }
-        uint32_t off = rec_off(b), e = mend < end16 ? mend : end16;
-        if (off >= len) {                                     /* plain match: consecutive sources */
-            uint32_t sv = q - off + P2_SBIAS;
-#pragma unroll 1
-            for (; q < e; q++, sv++) src[P2_SIDX(q - c)] = sv;
-        }
-        else {                                                /* overlapping match: fold onto the off seed bytes in front of it */
-            uint32_t kk = (q - pos) % off, seed = pos - off + P2_SBIAS;
-#pragma unroll 1
-            for (; q < e; q++) { src[P2_SIDX(q - c)] = seed + kk; if (++kk == off) kk = 0; }
-        }
+        src[P2_SIDX(q - c)] = d;
     }
 }
 
 /* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.  A source
  * inside the current chunk is followed through the descriptors to ITS source (pointer jumping; positions
- * strictly decrease so it terminates). */
+ * strictly decrease so it terminates).  Descriptors first, then all byte loads, so the loads overlap. */
 MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
                     const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
     const int64_t gbase = (int64_t) g0 - P2_SBIAS;
-#pragma unroll 4
+    const uint32_t n = size - q0 < 16 ? size - q0 : 16;
+    uint32_t d[16];
+#pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t q = q0 + k;
-        if (q >= size) break;
-        uint32_t d = src[P2_SIDX(q - c)], v;
+        uint32_t x = (k < n) ? src[P2_SIDX(q0 + k - c)] : 0x80000000u;
 #pragma unroll 1
-        while (!(d & 0x80000000u) && d >= c + P2_SBIAS) d = src[P2_SIDX(d - P2_SBIAS - c)];    /* chase inside the chunk */
-        if (d & 0x80000000u) v = lits[d & 0x7FFFFFFFu];
-        else { int64_t g = gbase + d; v = g >= 0 ? unit_out[g] : 0u; }               /* before the unit's first byte: zero */
+        while (!(x & 0x80000000u) && x >= c + P2_SBIAS) x = src[P2_SIDX(x - P2_SBIAS - c)];    /* chase inside the chunk */
+        d[k] = x;
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) {
+        uint32_t v = 0;
+        if (k < n) {
+            if (d[k] & 0x80000000u) v = lits[d[k] & 0x7FFFFFFFu];
+            else { int64_t g = gbase + d[k]; v = g >= 0 ? unit_out[g] : 0u; }   /* before the unit's first byte: zero */
+        }
         w[k >> 2] |= v << (8 * (k & 3));
     }
 }
