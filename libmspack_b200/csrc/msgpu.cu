@@ -18,6 +18,7 @@
 
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
+#include "msgpu_p1_mszip_c.cuh"
 #include "msgpu_p1_lzx.cuh"
 #include "msgpu_p1_lzx_c.cuh"
 #include "msgpu_p1_qtm.cuh"
@@ -61,6 +62,25 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT, LCACHE> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
+        st = a.ustate[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+                a.finfo + (size_t) slot * a.F, a.F);
+    }
+    p1_run(t);
+    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
+}
+
+template <int NT, int HEADN>
+__global__ void __launch_bounds__(NT) k_p1_mszip_c(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
+    const bool valid = ti < count;
+    uint32_t slot = valid ? order[ti] : 0;
+    ZipLaneC<NT, HEADN> t; t.phase = PH_IDLE;
+    MsUnitState st;
+    if (valid) {
+        t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
                 a.finfo + (size_t) slot * a.F, a.F);
@@ -178,6 +198,8 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 /* MSZIP P1 variants (threads per CTA, literal/length LUT bits, distance LUT bits, long-symbol cache entries);
  * MSGPU_ZIP_VARIANT picks one (default 0) */
 #define ZIP_VARIANTS(X) X(0, 192, 8, 7, 96) X(1, 128, 9, 8, 48) X(2, 128, 9, 8, 120)
+/* table-free canonical MSZIP lanes (id, threads per CTA, shared-memory head entries) */
+#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64)
 /* LZX P1 variants (threads per CTA, main LUT bits, length LUT bits, long-symbol cache entries, literals per step);
  * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
 #define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
@@ -251,7 +273,10 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRZ(id, nt, lr, dr, lc) cudaFuncSetAttribute(k_p1_mszip<nt, lr, dr, lc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipShared<nt, lr, dr, lc>));
     ZIP_VARIANTS(SETATTRZ)
 #undef SETATTRZ
-    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 0; }
+#define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip_c<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
+    ZIPC_VARIANTS(SETATTRZC)
+#undef SETATTRZC
+    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 11; }
 #define SETATTR(id, nt, mr, lr, lc, lb) cudaFuncSetAttribute(k_p1_lzx<nt, mr, lr, lc, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<nt, mr, lr, lc, lb>));
     LZX_VARIANTS(SETATTR)
 #undef SETATTR
@@ -348,6 +373,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNTZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) zip_nt = nt;
     ZIP_VARIANTS(PICKNTZ)
 #undef PICKNTZ
+#define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
+    ZIPC_VARIANTS(PICKNTZC)
+#undef PICKNTZC
     /* sub-wave size: a multiple of every CTA size in use (32 * 3 * 4 * 7 = 2688 covers 96/128/192/224 threads),
      * about one resident P1 CTA per SM */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
@@ -418,6 +446,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define LAUNCHZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) k_p1_mszip<nt, lr, dr, lc><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipShared<nt, lr, dr, lc>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             ZIP_VARIANTS(LAUNCHZ)
 #undef LAUNCHZ
+#define LAUNCHZC(id, nt, hn) if (ctx->zip_variant == id) k_p1_mszip_c<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            ZIPC_VARIANTS(LAUNCHZC)
+#undef LAUNCHZC
             mark(0, st); mark(1, st);
             k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;

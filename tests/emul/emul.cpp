@@ -13,6 +13,7 @@
 
 #include "../../libmspack_b200/csrc/msgpu_core.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_mszip.cuh"
+#include "../../libmspack_b200/csrc/msgpu_p1_mszip_c.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_lzx.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_lzx_c.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_qtm.cuh"
@@ -78,7 +79,17 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
             emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
     };
 
-    if (u->codec == MSGPU_CODEC_MSZIP) {
+    if (u->codec == MSGPU_CODEC_MSZIP && !getenv("MSGPU_EMUL_LUT")) {               /* table-free canonical lanes (the default kernels) */
+        typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH;
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
+        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            TH t; t.bind(sh, 0, aux, 0);
+            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            emul_run(t); t.end(st); resolve();
+        }
+        free(sh); free(aux);
+    }
+    else if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipShared<1, 8, 7, 96> SH; typedef ZipLane<1, 8, 7, 96> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
@@ -88,7 +99,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         }
         free(sh); free(aux);
     }
-    else if (u->codec == MSGPU_CODEC_LZX && getenv("MSGPU_EMUL_LZXC")) {          /* table-free canonical lanes */
+    else if (u->codec == MSGPU_CODEC_LZX && !getenv("MSGPU_EMUL_LUT")) {          /* table-free canonical lanes (the default kernels) */
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {

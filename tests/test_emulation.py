@@ -22,7 +22,12 @@ def emul():
     lib = ctypes.CDLL(so)
     lib.emul_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 
-    def run(units, comp, out_bytes, frames_per_round=1):
+    def run(units, comp, out_bytes, frames_per_round=1, lut_lanes=False):
+        # two decode engines ship: table-free canonical lanes (default kernels) and LUT lanes (MSGPU_*_VARIANT < 10)
+        if lut_lanes:
+            os.environ["MSGPU_EMUL_LUT"] = "1"
+        else:
+            os.environ.pop("MSGPU_EMUL_LUT", None)
         units = np.ascontiguousarray(units)
         comp = np.concatenate([np.ascontiguousarray(comp, dtype=np.uint8), np.zeros(64, np.uint8)])
         out = np.zeros(out_bytes + 64, np.uint8)
@@ -34,9 +39,10 @@ def emul():
 
 @pytest.mark.parametrize("entry", golden_manifest(), ids=lambda e: e["name"])
 @pytest.mark.parametrize("frames_per_round", [1, 2])
-def test_device_logic_on_golden_vectors(emul, entry, frames_per_round):
+@pytest.mark.parametrize("lut_lanes", [False, True], ids=["canonical", "lut"])
+def test_device_logic_on_golden_vectors(emul, entry, frames_per_round, lut_lanes):
     u, comp = golden_unit(entry)
-    out, st = emul(u, comp, entry["out_len"], frames_per_round)
+    out, st = emul(u, comp, entry["out_len"], frames_per_round, lut_lanes)
     assert int(st[0]) == entry["err"]
     if entry["err"] == 0:
         assert hashlib.md5(out.tobytes()).hexdigest() == entry["md5"]
@@ -53,8 +59,9 @@ def test_device_logic_matches_oracle(emul, oracle_ref, codec, kw):
     b = gen.make_batch(codec, 20, **kw)
     o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
     for fpr in (1, 2):
-        o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr)
-        assert_same(b.units, o1, s1, o2, s2, f"emulation {codec} {kw} F={fpr}")
+        for lut in (False, True):
+            o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr, lut)
+            assert_same(b.units, o1, s1, o2, s2, f"emulation {codec} {kw} F={fpr} lut={lut}")
 
 
 def test_device_logic_on_corrupt_streams(emul, oracle_ref):
@@ -69,5 +76,6 @@ def test_device_logic_on_corrupt_streams(emul, oracle_ref):
             else:
                 b.units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
         o1, s1, _ = oracle_ref.decode_batch(b.units, comp, b.out_bytes)
-        o2, s2 = emul(b.units, comp, b.out_bytes)
-        assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec}")
+        for lut in (False, True):
+            o2, s2 = emul(b.units, comp, b.out_bytes, 1, lut)
+            assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec} lut={lut}")
