@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
-    __shared__ uint32_t s_src[P2_WARPS][P2_CHUNK];
+    __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t si = first + blockIdx.x * P2_WARPS + warp;
     if (si >= nslots) return;

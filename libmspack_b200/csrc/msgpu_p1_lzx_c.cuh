@@ -64,16 +64,16 @@ struct LzxLaneC {
     }
 
     /* READ_HUFFSYM for a tree whose limits live in shared memory (pretree, LENGTH slow path, aligned tree) */
-    MS_M uint32_t sym_smem(const uint16_t *lim16, const uint32_t *bo, const uint16_t *sorted) {
-        lzx_check(b, 16);
+    MS_M uint32_t sym_smem(const uint16_t *lim16, const uint32_t *bo, const uint16_t *sorted, bool careful = true) {
+        if (careful) lzx_check(b, 16);
         uint32_t v16 = msb_peek(b, 16);
         int len = ms_canon_len_smem<NT>(lim16, v16);
         uint32_t idx = ms_canon_index<NT>(bo, v16, len);
         msb_drop(b, len);
         return sorted[idx * MS_WARP];
     }
-    MS_M uint32_t length_sym() {              /* LENGTH tree: 5-bit LUT, then the canonical path */
-        lzx_check(b, 16);
+    MS_M uint32_t length_sym(bool careful) {  /* LENGTH tree: 5-bit LUT, then the canonical path */
+        if (careful) lzx_check(b, 16);
         uint32_t e = llut[msb_peek(b, 5) * NT];
         if (e & 15) { msb_drop(b, (int) (e & 15)); return e >> 4; }
         uint32_t v16 = msb_peek(b, 16);
@@ -285,8 +285,8 @@ struct LzxLaneC {
     }
 
     /* main-tree symbol: length from the register limits, symbol from the shared-memory head or global scratch */
-    MS_M uint32_t main_sym() {
-        lzx_check(b, 16);
+    MS_M uint32_t main_sym(bool careful) {
+        if (careful) lzx_check(b, 16);
         uint32_t v16 = msb_peek(b, 16);
         int len = ms_canon_len(mlim, v16);
         uint32_t idx = ms_canon_index<NT>(mbo, v16, len);
@@ -298,23 +298,18 @@ struct LzxLaneC {
      * fields.  Batching literals keeps the lanes that are inside a literal run busy while the others
      * handle a match, which is the longer path. */
     MS_M void step() {
-        uint32_t sym;
-#pragma unroll 1
-        for (int rep = 0;; ) {
-            lzx_refill(b);
-            sym = main_sym();
-            if (sym >= 256) break;
-            emit_literal(em, sym); q++; this_run--;
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            if (this_run <= 0) { phase = PH_BLOCK; return; }
-            if (++rep == 1) return;
-        }
-        {
+        /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
+         * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks evaluated */
+        const bool careful = b.ipos + 24 > b.in_len;
+        lzx_refill(b);
+        uint32_t sym = main_sym(careful);
+        if (sym < 256) { emit_literal(em, sym); q++; this_run--; }
+        else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
             if (ml == 7) {
                 if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
-                ml += length_sym();
+                ml += length_sym(careful);
             }
             ml += 2;
             if (slot == 0) off = R0;
@@ -327,27 +322,31 @@ struct LzxLaneC {
                 off = pbase - 2;
                 lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
-                    if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
-                    off += sym_smem(alim, abo, aa.sorted);
+                    if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
+                    off += sym_smem(alim, abo, aa.sorted, careful);
                 }
-                else if (extra) off += lzx_read(b, (int) extra);
+                else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;
             }
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start) */
-            uint32_t G = frame_start_pos + q, wpr = G & (window_size - 1), eff = off;
-            bool bad = (wpr + ml > window_size);
-            if (off > wpr) {
-                bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
-                if (off > window_size) eff = off - window_size;
+            if (careful && b.err) { fail(b.err); return; }
+            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
+             * inside the unit during the first lap of the window (every unit up to 2^window_bits bytes never leaves it) */
+            uint32_t G = frame_start_pos + q, eff = off;
+            if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
+                uint32_t wpr = G & (window_size - 1);
+                bool bad = (wpr + ml > window_size);
+                if (off > wpr) {
+                    bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
+                    if (off > window_size) eff = off - window_size;
+                }
+                if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
+                if (bad) { fail(MS_EDECRUNCH); return; }
             }
-            if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
-            bad = bad || ((int32_t) ml > this_run);   /* :678-693 every overrun ends in an error */
-            if (MS_UNLIKELY(bad)) { fail(MS_EDECRUNCH); return; }
+            if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return; }   /* :678-693 every overrun ends in an error */
             emit_match(em, q, ml, eff);
             q += ml; this_run -= (int32_t) ml;
         }
-        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (careful && b.err) { fail(b.err); return; }
         if (this_run <= 0) phase = PH_BLOCK;
     }
 

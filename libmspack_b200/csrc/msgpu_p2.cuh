@@ -40,58 +40,69 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
  *     else       : match,   value   = (frame-relative source position) + P2_SBIAS   (the source may lie in
  *                  earlier frames of the unit, i.e. be negative; overlapping matches are already folded) */
 #define P2_SBIAS (1 << 22)
-/* descriptor of chunk position p (0..511) lives at P2_SIDX(p): transposed (byte-in-lane major, lane minor) so
- * that the 32 lanes, which all touch "their k-th byte" at the same time, hit 32 different banks */
-#define P2_SIDX(p) ((((p) & 15u) << 5) | ((p) >> 4))
+/* descriptor of chunk position p (0..511) lives at P2_SIDX(p) = p + p / 16: a row of 17 words per lane, so the 32
+ * lanes, which all touch "their k-th byte" at the same time, hit 32 different banks (17 is odd) */
+#define P2_SIDX(p) ((p) + ((p) >> 4))
+#define P2_SRC_WORDS (P2_CHUNK + P2_CHUNK / 16)
 
-/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors.  One binary search per lane,
+/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors d[0..15] (kept in registers for
+ * the lane's own use AND stored to shared memory for lanes whose sources point here).  One binary search per lane,
  * then the same 16-iteration loop in every lane (the current record's fields stay in registers; stepping to the
  * next record is the only data-dependent part), so the warp stays converged. */
-MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint32_t *src)
+MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint32_t *src, uint32_t d[16])
 {
-    if (q0 >= size) return;
+    if (q0 >= size) {
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) d[k] = 0x80000000u;
+        return;
+    }
     int i = p2_search(wa, wb, q0);
     uint32_t a = wa[i], b = wb[i];
     uint32_t pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b), mend = pos + len;
-#pragma unroll 4
+    uint32_t *row = src + P2_SIDX(q0 - c);
+#pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t q = q0 + k, d;
-        if (q >= size) break;
-        while (q >= mend) { i++; a = wa[i]; b = wb[i]; pos = rec_pos(a); M = rec_M(a); off = rec_off(b); len = rec_len(b); mend = pos + len; }
-        if (q < pos) d = (q - M) | 0x80000000u;                               /* literal */
-        else {
-            uint32_t kk = q - pos;
-            if (off >= len || kk < off) d = q - off + P2_SBIAS;                /* plain match byte */
-            else d = pos - off + (kk % off) + P2_SBIAS;                        /* overlapping match: fold onto the seed bytes in front of it */
+        uint32_t q = q0 + k, x = 0x80000000u;
+        if (q < size) {
+            while (q >= mend) { i++; a = wa[i]; b = wb[i]; pos = rec_pos(a); M = rec_M(a); off = rec_off(b); len = rec_len(b); mend = pos + len; }
+            if (q < pos) x = (q - M) | 0x80000000u;                            /* literal */
+            else {
+                uint32_t kk = q - pos;
+                if (off >= len || kk < off) x = q - off + P2_SBIAS;             /* plain match byte */
+                else x = pos - off + (kk % off) + P2_SBIAS;                     /* overlapping match: fold onto the seed bytes in front of it */
+            }
+            row[k] = x;
         }
-        src[P2_SIDX(q - c)] = d;
+        d[k] = x;
     }
 }
 
-/* Pass B: the 16 bytes [q0, q0+16) of the frame (positions >= size give 0), little-endian in 4 words.  A source
- * inside the current chunk is followed through the descriptors to ITS source (pointer jumping; positions
- * strictly decrease so it terminates).  Descriptors first, then all byte loads, so the loads overlap. */
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
+/* Pass B: fetch the 16 bytes described by d[] (little-endian in 4 words; positions >= size give 0).  A source inside
+ * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
+ * decrease so it terminates).  All chases first, then all byte loads, so the loads overlap. */
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, uint32_t d[16],
                     const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
-    const int64_t gbase = (int64_t) g0 - P2_SBIAS;
     const uint32_t n = size - q0 < 16 ? size - q0 : 16;
-    uint32_t d[16];
+    const uint32_t inchunk = c + P2_SBIAS;
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t x = (k < n) ? src[P2_SIDX(q0 + k - c)] : 0x80000000u;
+        uint32_t x = d[k];
 #pragma unroll 1
-        while (!(x & 0x80000000u) && x >= c + P2_SBIAS) x = src[P2_SIDX(x - P2_SBIAS - c)];    /* chase inside the chunk */
+        while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];    /* literal descriptors are negative as int32 */
         d[k] = x;
     }
+    const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
+    const bool may_underflow = g0 < (uint32_t) P2_SBIAS;                           /* only a unit's first 4 MiB can reach before the unit */
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t v = 0;
+        uint32_t v = 0, x = d[k];
         if (k < n) {
-            if (d[k] & 0x80000000u) v = lits[d[k] & 0x7FFFFFFFu];
-            else { int64_t g = gbase + d[k]; v = g >= 0 ? unit_out[g] : 0u; }   /* before the unit's first byte: zero */
+            if (x & 0x80000000u) v = lits[x & 0x7FFFFFFFu];
+            else if (may_underflow && (int64_t) g0 + (int64_t) x < (int64_t) P2_SBIAS) v = 0;   /* before the unit's first byte: zero */
+            else v = obase[x];
         }
         w[k >> 2] |= v << (8 * (k & 3));
     }
@@ -115,10 +126,10 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             __syncwarp();
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
-        p2_pass_a(q0, c, size, wa, wb, src);
+        uint32_t q0 = c + 16u * (uint32_t) lane, w[4], d[16];
+        p2_pass_a(q0, c, size, wa, wb, src, d);
         __syncwarp();
-        p2_pass_b(q0, c, size, src, lits, unit_out, g0, w);
+        p2_pass_b(q0, c, size, src, d, lits, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -29,9 +29,9 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits,
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t w[32][4]; uint32_t src[P2_CHUNK];
-        for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), src);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, lits, unit_out, g0, w[lane]);
+        uint32_t w[32][4], d[32][16]; uint32_t src[P2_SRC_WORDS];
+        for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), src, d[lane]);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, d[lane], lits, unit_out, g0, w[lane]);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
