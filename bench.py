@@ -173,7 +173,10 @@ def main():
     d_in = torch.from_numpy(b.comp).to(dev)
     d_out = torch.zeros(b.out_bytes, dtype=torch.uint8, device=dev)
     d_st = torch.full((n,), -1, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: its handle is what msgpu_decode_batch_device launches on, so the CUDA events
+    # below really bracket the kernels (a NULL stream would mean "the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -196,12 +199,14 @@ def main():
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    ctx_ms = 0.0
     for _ in range(args.steps):
         dec.decode_device(b.units, d_in, d_out, d_st, stream)
     e1.record(stream)
     barrier()
     clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
+    ctx_ms = dec.last_kernel_ms()          # the library's own events around the last step's kernels (cross-check)
     launches = dec.launches - launches0
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -226,7 +231,7 @@ def main():
                 "traffic": (traffic or {}).get("dram_bytes_per_launch_set"),
                 "algorithmic_bytes_per_step": U + C, "kernel_ms_per_step": round(p1, 3),
                 "p2_resolve_ms_per_step": round(p2, 3), "p2_achieved_gbs": round((2 * U) / (p2 * 1e-3) / 1e9, 2),
-                "hbm_write_fraction": round(value / world / peak, 5),
+                "hbm_write_fraction": round(value / world / peak, 5), "last_step_kernels_ms": round(ctx_ms, 3),
                 "note": "latency/issue bound integer path: the practical limiter is serial symbol decode x resident warps, not DRAM (SURVEY.md 8d)"}
 
     # ---- end to end through the C-ABI with host buffers (pinned), H2D + D2H inside the timed region ----

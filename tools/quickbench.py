@@ -14,7 +14,7 @@ if len(sys.argv) > 4:
 t0 = time.time(); b = gen.make_batch(codec, n, keep_raw=(codec != 3 or True), **kw); tg = time.time() - t0
 dec = BatchDecoder(0)
 d_in = torch.from_numpy(b.comp).cuda(); d_out = torch.zeros(b.out_bytes, dtype=torch.uint8, device="cuda"); d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(); torch.cuda.synchronize()
 best = 1e9
 for it in range(iters):
     dec.decode_device(b.units, d_in, d_out, d_st, stream)
@@ -23,3 +23,12 @@ for it in range(iters):
     print(f"iter {it}: kernels {ms:.3f} ms  -> {b.out_bytes/ms/1e6:.1f} GB/s out")
 ok = bool((d_st == 0).all().item()) and np.array_equal(d_out.cpu().numpy().reshape(n, -1)[:, :b.units['out_len'][0]].reshape(-1), b.raw)
 print(f"codec {codec} n {n} gen {tg:.1f}s ratio {b.in_bytes/(n*int(b.units['out_len'][0])):.3f} best {best:.3f} ms = {b.out_bytes/best/1e6:.1f} GB/s  roundtrip_ok={ok} launches={dec.launches} scratch={dec.scratch_bytes/2**30:.2f} GiB")
+if os.environ.get("QB_STAGE"):
+    for mode in (False, True, False, True):
+        dec.set_stage_timing(mode)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        dec.decode_device(b.units, d_in, d_out, d_st, stream)
+        t1.record(stream)
+        torch.cuda.synchronize()
+        print(f"stage_timing={mode}: outer {t0.elapsed_time(t1):.3f} ms, ctx total {dec.last_kernel_ms():.3f} ms, P1 {dec.stage_ms(0):.3f} P2 {dec.stage_ms(1):.3f} E8 {dec.stage_ms(2):.3f}")
