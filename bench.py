@@ -191,12 +191,15 @@ def main():
         raise SystemExit("bench.py: GPU output differs from the generator's raw data")
 
     # ---- device-resident timing: K steps, CUDA events, max over ranks ----
+    clocks = ClockSampler(local_rank)      # sampling spans the warm-up and the timed steps (nvidia-smi needs ~0.3 s to start)
+    clocks.start()
+    t_w = time.time()
     for _ in range(max(args.warmup, 3)):
+        dec.decode_device(b.units, d_in, d_out, d_st, stream)
+    while time.time() - t_w < 1.0:         # keep the GPU under the same load until the sampler is certainly running
         dec.decode_device(b.units, d_in, d_out, d_st, stream)
     barrier()
     launches0 = dec.launches
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     ctx_ms = 0.0

@@ -348,7 +348,7 @@ static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_F
  * bound, IPC ~0.2) of one sub-wave then shares the SMs with P2 (one warp per unit, issue bound) of the
  * previous one, instead of the two kernels running back to back. */
 static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t hi, const void *d_in, void *d_out,
-                    int32_t *d_status, cudaStream_t s)
+                    int32_t *d_status, cudaStream_t s, const uint8_t *h_in = nullptr, uint8_t *h_out = nullptr)
 {
     const uint32_t n = (uint32_t) (hi - lo);
     std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base;
@@ -381,6 +381,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
     const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* 10752 = lcm(96..512 CTA sizes in use) */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
+    if (h_in && !env) {
+        /* host buffers: cut the wave into ~6 sub-waves so that the H2D copy of one sub-wave, the kernels of another and the
+         * D2H copy of a third overlap (each sub-wave's copies and kernels are ordered on its own stream) */
+        const uint32_t nmax0 = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
+        uint32_t want = (nmax0 + 5) / 6;
+        if (want < 4096) want = 4096;
+        if (want < subsz) subsz = want;
+    }
     subsz = (subsz + gran - 1) / gran * gran;
     const uint32_t nmaxc = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
     const uint32_t nsub = (nmaxc + subsz - 1) / subsz;
@@ -427,6 +435,37 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
     const int NS = (nsub > 1 && !ctx->stage_timing) ? 3 : 1;
+    /* byte range of a sub-wave's units in the input / output buffers (host-buffer path) */
+    auto io_range = [&](const std::vector<uint32_t> &v, uint32_t f0, uint32_t f1, bool out, uint64_t &b0, uint64_t &b1) {
+        b0 = ~0ull; b1 = 0;
+        for (uint32_t k = f0; k < f1; k++) {
+            const msgpu_unit &u = h_units[lo + v[k]];
+            uint64_t a = out ? u.out_off : u.in_off, e = a + (out ? u.out_len : u.in_len);
+            if (a < b0) b0 = a;
+            if (e > b1) b1 = e;
+        }
+    };
+    auto copy_in = [&](uint32_t sub, cudaStream_t st) {
+        if (!h_in) return;
+        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
+        for (int c = 0; c < 3; c++) {
+            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt; uint64_t b0, b1;
+            if (f0 >= cnt) continue;
+            io_range(*lists[c], f0, f1, false, b0, b1);
+            b0 &= ~3ull;                                   /* keep 4-byte loads of the first unit inside the copied range */
+            if (b1 > b0) cudaMemcpyAsync(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(d_in)) + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, st);
+        }
+    };
+    auto copy_out = [&](uint32_t sub, cudaStream_t st) {
+        if (!h_out) return;
+        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
+        for (int c = 0; c < 3; c++) {
+            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt; uint64_t b0, b1;
+            if (f0 >= cnt) continue;
+            io_range(*lists[c], f0, f1, true, b0, b1);
+            if (b1 > b0) cudaMemcpyAsync(h_out + b0, reinterpret_cast<uint8_t *>(d_out) + b0, b1 - b0, cudaMemcpyDeviceToHost, st);
+        }
+    };
     size_t sev_used = ctx->stage_evs[0].size() + ctx->stage_evs[1].size() + ctx->stage_evs[2].size();
     for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
 
@@ -475,11 +514,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     for (uint32_t sub = 0; sub < nsub; sub++) {
         cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
+        copy_in(sub, st);
         for (uint32_t round = 0; round < rounds_planned; round++) {
             if (round + 1 == rounds_planned && any_zip) CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
             launch_round(sub, st);
         }
-        if (!any_zip) launch_tail(sub, st);
+        if (!any_zip) { launch_tail(sub, st); copy_out(sub, st); }
     }
     CK(cudaGetLastError(), "kernel launch");
     if (any_zip) {
@@ -498,7 +538,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
         }
-        for (uint32_t sub = 0; sub < nsub; sub++) launch_tail(sub, NS == 1 ? s : ctx->sub[sub % 3]);
+        for (uint32_t sub = 0; sub < nsub; sub++) { launch_tail(sub, NS == 1 ? s : ctx->sub[sub % 3]); copy_out(sub, NS == 1 ? s : ctx->sub[sub % 3]); }
     }
     if (NS > 1) for (int i = 0; i < NS; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->sub[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[i], 0), "stream wait"); }
     if (d_status) { k_status<<<(n + 255) / 256, 256, 0, s>>>(a.ustate, n, d_status + lo); ctx->launches++; }
@@ -508,8 +548,19 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     return 0;
 }
 
+static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
+                             void *d_out, size_t out_bytes, int32_t *d_status, void *stream, const uint8_t *h_in, uint8_t *h_out);
+
 extern "C" int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
                                          void *d_out, size_t out_bytes, int32_t *d_status, void *stream)
+{
+    return decode_batch_impl(ctx, units, n, d_in, in_bytes, d_out, out_bytes, d_status, stream, nullptr, nullptr);
+}
+
+/* h_in / h_out non-null: the host-buffer path - every sub-wave copies its own input range in before its kernels and its
+ * own output range out after them, on its own stream */
+static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
+                             void *d_out, size_t out_bytes, int32_t *d_status, void *stream, const uint8_t *h_in, uint8_t *h_out)
 {
     if (!ctx) return MSGPU_ERR_ARGS;
     ctx->err.clear();
@@ -534,7 +585,7 @@ extern "C" int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
     for (size_t lo = 0; lo < n; lo += slots) {
         size_t hi = lo + slots < n ? lo + slots : n;
-        int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s);
+        int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, h_in, h_out);
         if (r) return r;
     }
     return 0;
@@ -564,11 +615,10 @@ extern "C" int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, 
     CK(ctx->io_in.reserve(in_bytes + 64), "alloc input");
     CK(ctx->io_out.reserve(out_bytes + 64), "alloc output");
     CK(ctx->io_status.reserve(n * sizeof(int32_t)), "alloc status");
-    CK(cudaMemcpyAsync(ctx->io_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, s), "copy input");
-    int r = msgpu_decode_batch_device(ctx, units, n, ctx->io_in.p, in_bytes, ctx->io_out.p, out_bytes,
-                                      reinterpret_cast<int32_t *>(ctx->io_status.p), s);
+    /* copies are issued per sub-wave inside run_wave so that they overlap the kernels of the other sub-waves */
+    int r = decode_batch_impl(ctx, units, n, ctx->io_in.p, in_bytes, ctx->io_out.p, out_bytes,
+                              reinterpret_cast<int32_t *>(ctx->io_status.p), s, reinterpret_cast<const uint8_t *>(h_in), reinterpret_cast<uint8_t *>(h_out));
     if (r) return r;
-    CK(cudaMemcpyAsync(h_out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s), "copy output");
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "copy status");
     CK(cudaStreamSynchronize(s), "sync");
     return 0;
