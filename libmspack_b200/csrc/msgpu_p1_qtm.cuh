@@ -3,6 +3,13 @@
  * and emits literal bytes + match records per 32 KiB frame.  The nine frequency models live in shared
  * memory, interleaved by thread.  Integer widths follow the reference: H, L, C and symf are 16-bit,
  * range and the products are 32-bit unsigned.
+ *
+ * Representation.  The reference stores cumulative frequencies cum[i] (strictly decreasing, cum[entries] = 0) and
+ * adds 8 to cum[0..i-1] after every symbol - an O(i) update.  Here each model stores the DIFFERENCES
+ * g[i] = cum[i] - cum[i+1] plus the total T = cum[0]: the scan rebuilds cum on the fly (c -= g[i]) and the update is
+ * g[sym] += 8, T += 8.  Rescaling (qtmd.c:130-136) runs on the reconstructed cumulative values, the periodic
+ * re-sort (:138-164) works on frequencies anyway; results are identical to the reference's.
+ * Renormalisation shifts all leading equal bits of L and H at once (clz) instead of one bit per iteration.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -17,11 +24,12 @@
 #define QM5   293
 #define QM6   330
 #define QM6L  373
-#define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8, padded */
+#define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8 + 9 u16, padded */
 
 template <int NT>
 struct QtmShared {
-    uint16_t cum[QTM_ENT * NT];
+    uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
+    uint16_t tot[9 * NT];             /* T = cum[0] per model */
     uint8_t  sym[QTM_ENT * NT];
     uint8_t  shl[9 * NT];
 };
@@ -29,17 +37,17 @@ struct QtmShared {
 template <int NT>
 struct QtmLane {
     MsBits b;
-    uint16_t *cum; uint8_t *sym, *shl;
+    uint16_t *cum, *tot; uint8_t *sym, *shl;
     uint32_t H, L, C;                 /* 16-bit values */
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
 
-    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; sym = sh->sym + tid; shl = sh->shl + tid; }
+    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; }
 
-    MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182 */
-        shl[midx * NT] = 4;
+    MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
+        shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
 #pragma unroll 1
-        for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (len - i); }
+        for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
     }
 
     /* READ_BYTES bookkeeping: two more bytes fetched; fails past in_len + 2 (readbits.h:192-214) */
@@ -48,21 +56,24 @@ struct QtmLane {
     MS_M void update_model(int base, int midx, int entries) {             /* qtmd.c:125-166 */
         uint32_t s = shl[midx * NT] - 1u;
         if (s) {
+            /* :130-136 on cumulative values: cum[i] >>= 1; if (cum[i] <= cum[i+1]) cum[i] = cum[i+1] + 1 */
             shl[midx * NT] = (uint8_t) s;
-            uint32_t next = cum[(base + entries) * NT];
+            uint32_t old = 0, nn = 0;
 #pragma unroll 1
             for (int i = entries - 1; i >= 0; i--) {
-                uint32_t c = cum[(base + i) * NT] >> 1;
-                if (c <= next) c = next + 1;
-                cum[(base + i) * NT] = (uint16_t) c; next = c;
+                old += cum[(base + i) * NT];                               /* the reference's cum[i] before the rescale */
+                uint32_t c = old >> 1;
+                if (c <= nn) c = nn + 1;
+                cum[(base + i) * NT] = (uint16_t) (c - nn); nn = c;
             }
+            tot[midx * NT] = (uint16_t) nn;
         }
         else {
             shl[midx * NT] = 50;
+            uint32_t T = 0;
 #pragma unroll 1
-            for (int i = 0; i < entries; i++) {
-                uint32_t c = (uint32_t) cum[(base + i) * NT] - cum[(base + i + 1) * NT];
-                c = (uint16_t) (c + 1); c >>= 1;
+            for (int i = 0; i < entries; i++) {                            /* :141-146 frequencies, halved, never zero */
+                uint32_t c = (uint16_t) (cum[(base + i) * NT] + 1); c >>= 1;
                 cum[(base + i) * NT] = (uint16_t) c;
             }
             /* the reference's in-place exchange sort; its (in)stability is part of the format (:148-150) */
@@ -81,42 +92,46 @@ struct QtmLane {
                 cum[(base + i) * NT] = (uint16_t) ci; sym[(base + i) * NT] = (uint8_t) si;
             }
 #pragma unroll 1
-            for (int i = entries - 1; i >= 0; i--) cum[(base + i) * NT] = (uint16_t) (cum[(base + i) * NT] + cum[(base + i + 1) * NT]);
+            for (int i = 0; i < entries; i++) T += cum[(base + i) * NT];   /* :162-164 back to cumulative: T = cum[0] */
+            tot[midx * NT] = (uint16_t) T;
         }
     }
 
-    /* GET_SYMBOL, qtmd.c:92-123.  The scan for the symbol and the "+8 to everything in front of it"
-     * update are one pass. */
+    /* GET_SYMBOL, qtmd.c:92-123 */
     MS_M uint32_t get_symbol(int base, int midx, int entries) {
         uint32_t range = ((H - L) & 0xFFFFu) + 1u;
-        uint32_t c0 = cum[base * NT];
+        uint32_t c0 = tot[midx * NT];
         uint32_t symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
-        uint32_t prev = c0, cur; int i = 1;
+        uint32_t prev = c0, cur, gj; int j = 0;
 #pragma unroll 1
-        for (;; i++) {
-            cur = cum[(base + i) * NT];
-            if (i >= entries || cur <= symf) break;
-            cum[(base + i - 1) * NT] = (uint16_t) (prev + 8); prev = cur;
+        for (;; j++) {                                         /* first j with cum[j+1] <= symf (cum[j+1] = cum[j] - g[j]) */
+            gj = cum[(base + j) * NT];
+            cur = prev - gj;
+            if (j + 1 >= entries || cur <= symf) break;
+            prev = cur;
         }
-        cum[(base + i - 1) * NT] = (uint16_t) (prev + 8);
-        uint32_t s = sym[(base + i - 1) * NT];
+        uint32_t s = sym[(base + j) * NT];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
         uint32_t Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
         uint32_t Ln = (L + (cur * range) / c0) & 0xFFFFu;
         H = Hn; L = Ln;
-        if (((c0 + 8) & 0xFFFFu) > 3800) update_model(base, midx, entries);
-        qtm_refill(b);
+        cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
+        c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
+        if (c0 > 3800) update_model(base, midx, entries);
+        /* :109-122 renormalise: all leading equal bits of L and H leave at once; the underflow case goes bit by bit */
 #pragma unroll 1
         for (;;) {
-            if ((L & 0x8000u) != (H & 0x8000u)) {
-                if ((L & 0x4000u) && !(H & 0x4000u)) { C ^= 0x4000u; L &= 0x3FFFu; H |= 0x4000u; }
+            uint32_t x = (L ^ H) & 0xFFFFu; int n;
+            if (x & 0x8000u) {
+                if ((L & 0x4000u) && !(H & 0x4000u)) { C ^= 0x4000u; L &= 0x3FFFu; H |= 0x4000u; n = 1; }
                 else break;
             }
-            L = (L << 1) & 0xFFFFu; H = ((H << 1) | 1u) & 0xFFFFu;
-            if (bl < 1) fetch2();
-            bl -= 1;
-            if (b.bc < 1) qtm_refill(b);
-            C = ((C << 1) | msb_peek(b, 1)) & 0xFFFFu; msb_drop(b, 1);
+            else n = x ? MS_CLZ(x << 16) : 16;
+            L = (L << n) & 0xFFFFu; H = ((H << n) | ((1u << n) - 1u)) & 0xFFFFu;
+            while (bl < n) fetch2();                           /* ENSURE_BITS(1) per shifted bit */
+            bl -= n;
+            if (b.bc < n) qtm_refill(b);
+            C = ((C << n) | msb_peek(b, n)) & 0xFFFFu; msb_drop(b, n);
         }
         return s;
     }
@@ -254,7 +269,7 @@ struct QtmLane {
 #pragma unroll 1
                 for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; sym[i * NT] = save[QTM_ENT * 2 + i]; }
 #pragma unroll 1
-                for (int i = 0; i < 9; i++) shl[i * NT] = save[QTM_ENT * 3 + i];
+                for (int i = 0; i < 9; i++) { shl[i * NT] = save[QTM_ENT * 3 + i]; tot[i * NT] = reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i]; }
             }
         }
         phase = done ? PH_IDLE : PH_FRAME;
@@ -268,7 +283,7 @@ struct QtmLane {
 #pragma unroll 1
             for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; save[QTM_ENT * 2 + i] = sym[i * NT]; }
 #pragma unroll 1
-            for (int i = 0; i < 9; i++) save[QTM_ENT * 3 + i] = shl[i * NT];
+            for (int i = 0; i < 9; i++) { save[QTM_ENT * 3 + i] = shl[i * NT]; reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i] = tot[i * NT]; }
         }
     }
 };
