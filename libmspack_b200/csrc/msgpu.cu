@@ -204,7 +204,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
 #define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
 /* table-free canonical LZX lanes (id, threads per CTA, shared-memory head entries) */
-#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64) X(14, 448, 32)
+#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64) X(14, 448, 32) X(15, 384, 112) X(16, 416, 80) X(17, 448, 76)
 #define QTM_NT 160
 
 struct DevBuf {

@@ -151,8 +151,13 @@ def _pack(codec, window_bits, reset_interval, pieces, unit_bytes, raw):
 def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 21, data: str = "text",
                seed: int = CORPUS_SEED, first_unit: int = 0, threads: int = 0, keep_raw: bool = False,
                reset_interval: int = 0, block_frames: int = 1, split: int = 1, block_mode: int = 0, intel: int = 0,
-               intel_filesize: int = 12000000, chain: int = 24, level: int = 6) -> Batch:
-    """n independent units of `unit_bytes` uncompressed bytes each, all of one codec."""
+               intel_filesize: int = 12000000, chain: int = 24, level: int = 6, slack: int = 0) -> Batch:
+    """n independent units of `unit_bytes` uncompressed bytes each, all of one codec.
+
+    slack: extra bytes added to every unit's in_len (they are the next unit's first bytes, as in a CHM content stream).
+    The reference runs one more, empty, frame pass when a request ends on a frame boundary and at a reset point that
+    pass reads ahead (lzxd.c:419-453, :696-697): a reset-interval unit cut exactly at its last byte decodes completely
+    but returns MSPACK_ERR_READ; 4 bytes of slack avoid that."""
     threads = _threads(threads)
     nfr = (unit_bytes + FRAME - 1) // FRAME
     if codec == CODEC_MSZIP:
@@ -191,7 +196,7 @@ def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 2
         comp[np.repeat(offs, l64) + within] = comp_slots[idx_unit * slot + within]
     units["codec"], units["window_bits"] = codec, window_bits
     units["reset_interval"] = reset_interval if codec == CODEC_LZX else 0
-    units["in_off"], units["in_len"], units["out_len"] = offs, lens, unit_bytes
+    units["in_off"], units["in_len"], units["out_len"] = offs, lens + np.uint32(slack), unit_bytes
     stride = (unit_bytes + 15) & ~15
     units["out_off"] = np.arange(n, dtype=np.uint64) * np.uint64(stride)
     return Batch(units, comp, raw, n * stride)

@@ -48,7 +48,7 @@ LZX_CASES = [
     dict(), dict(block_mode=1), dict(block_mode=2), dict(block_mode=3), dict(block_mode=4, split=3),
     dict(window_bits=15, block_mode=4), dict(window_bits=17), dict(intel=1, data="binary"), dict(intel=1, data="binary", block_mode=4),
     dict(intel=1, intel_filesize=40000, data="binary"), dict(data="zeros"), dict(data="random"),
-    dict(unit_bytes=65536, reset_interval=2), dict(unit_bytes=65536, reset_interval=2, block_frames=2, block_mode=4),
+    dict(unit_bytes=65536, reset_interval=2), dict(unit_bytes=65536, reset_interval=2, slack=4), dict(unit_bytes=65536, reset_interval=2, block_frames=2, block_mode=4),
     dict(unit_bytes=65536, block_frames=2), dict(unit_bytes=131072, reset_interval=1, block_mode=4, intel=1, data="binary"),
     dict(unit_bytes=100000, block_mode=4, split=2), dict(unit_bytes=5000), dict(unit_bytes=1), dict(unit_bytes=32769),
     dict(unit_bytes=163840, window_bits=15, block_mode=4),
