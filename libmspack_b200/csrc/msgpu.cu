@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
     __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
+    __shared__ uint32_t s_longq[P2_WARPS][P2_LONG_MAX + 1];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t si = first + blockIdx.x * P2_WARPS + warp;
     if (si >= nslots) return;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
         p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
-                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_src[warp]);
+                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp]);
     }
 }
 

@@ -338,12 +338,19 @@ MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo,
     return 0;
 }
 
-/* code length from limits in registers: lim[j] = limit[j + 1] */
+/* code length from limits in registers: lim[j] = limit[j + 1], non-decreasing.  len = 1 + #{ j : lim[j] <= v16 },
+ * found by a 4-step binary search over the 15 registers (the register picked at each step is a small select tree on
+ * the earlier outcomes): ~20 instructions and a short dependent chain instead of 15 dependent compare-and-adds. */
 MS_D int ms_canon_len(const uint32_t lim[15], uint32_t v16) {
-    int len = 1;
-#pragma unroll
-    for (int j = 0; j < 15; j++) len += (v16 >= lim[j]) ? 1 : 0;
-    return len;
+    const bool p8 = v16 >= lim[7];
+    const uint32_t a4 = p8 ? lim[11] : lim[3];
+    const bool p4 = v16 >= a4;
+    const uint32_t a2 = p8 ? (p4 ? lim[13] : lim[9]) : (p4 ? lim[5] : lim[1]);
+    const bool p2 = v16 >= a2;
+    const uint32_t lo = p4 ? (p2 ? lim[6] : lim[4]) : (p2 ? lim[2] : lim[0]);
+    const uint32_t hi = p4 ? (p2 ? lim[14] : lim[12]) : (p2 ? lim[10] : lim[8]);
+    const bool p1 = v16 >= (p8 ? hi : lo);
+    return 1 + (p8 ? 8 : 0) + (p4 ? 4 : 0) + (p2 ? 2 : 0) + (p1 ? 1 : 0);
 }
 /* code length from limits in shared memory (rarely used trees): lim16[(j) * NT] = limit[j + 1] >> 1 (limits of
  * lengths <= 15 are even, so the halved compare is exact) */

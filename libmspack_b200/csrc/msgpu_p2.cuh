@@ -45,51 +45,85 @@ MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
 #define P2_SIDX(p) ((p) + ((p) >> 4))
 #define P2_SRC_WORDS (P2_CHUNK + P2_CHUNK / 16)
 
-/* Pass A of a chunk: this lane's 16 positions [q0, q0+16) -> source descriptors d[0..15] (kept in registers for
- * the lane's own use AND stored to shared memory for lanes whose sources point here).  One binary search per lane,
- * then the same 16-iteration loop in every lane (the current record's fields stay in registers; stepping to the
- * next record is the only data-dependent part), so the warp stays converged. */
-MS_D void p2_pass_a(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *wa, const uint32_t *wb, uint32_t *src, uint32_t d[16])
+/* descriptor of frame position p for record (pos, M, off, len): literal before the match, else (folded) match source */
+MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t M, uint32_t off, uint32_t len) {
+    if (p < pos) return (p - M) | 0x80000000u;
+    uint32_t kk = p - pos;
+    if (off >= len || kk < off) return p - off + P2_SBIAS;
+    return pos - off + (kk % off) + P2_SBIAS;              /* overlapping match: fold onto the seed bytes in front of it */
+}
+
+#define P2_LONG      48      /* a record covering at least this many positions of the chunk is filled by the whole warp */
+#define P2_LONG_MAX  16
+
+/* Pass A of a chunk, RECORD-parallel: the records that intersect the chunk [c, cend) are dealt out to the lanes
+ * (r_lo + lane, + 32, ...); a lane writes the descriptors of "its" record - the literal run in front of the match
+ * and the match - for the positions inside the chunk.  The record is decoded once, the per-position work is a store.
+ * Records with a long span (long literal runs of stored data, 257-byte matches of repetitive data) are queued in
+ * shared memory and filled by all 32 lanes together.  longq[0] = count, longq[1..] = window indices. */
+MS_D void p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb,
+                            uint32_t *src, uint32_t *longq)
 {
-    if (q0 >= size) {
-#pragma unroll
-        for (uint32_t k = 0; k < 16; k++) d[k] = 0x80000000u;
-        return;
-    }
-    int i = p2_search(wa, wb, q0);
-    uint32_t a = wa[i], b = wb[i];
-    uint32_t pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b), mend = pos + len;
-    uint32_t *row = src + P2_SIDX(q0 - c);
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) {
-        uint32_t q = q0 + k, x = 0x80000000u;
-        if (q < size) {
-            while (q >= mend) { i++; a = wa[i]; b = wb[i]; pos = rec_pos(a); M = rec_M(a); off = rec_off(b); len = rec_len(b); mend = pos + len; }
-            if (q < pos) x = (q - M) | 0x80000000u;                            /* literal */
-            else {
-                uint32_t kk = q - pos;
-                if (off >= len || kk < off) x = q - off + P2_SBIAS;             /* plain match byte */
-                else x = pos - off + (kk % off) + P2_SBIAS;                     /* overlapping match: fold onto the seed bytes in front of it */
-            }
-            row[k] = x;
+#pragma unroll 1
+    for (int r = r_lo + lane; r < P2_WIN; r += 32) {
+        uint32_t lit0 = (r == 0) ? c : rec_pos(wa[r - 1]) + rec_len(wb[r - 1]);     /* window[0]'s predecessors all end at or before c */
+        if (lit0 >= cend) break;
+        uint32_t a = wa[r], b = wb[r], pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b);
+        uint32_t p0 = lit0 > c ? lit0 : c, p1 = pos + len < cend ? pos + len : cend;
+        if (p1 <= p0) continue;
+        if (p1 - p0 >= P2_LONG) {
+#if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
+            uint32_t slot = atomicAdd(&longq[0], 1u);
+#else
+            uint32_t slot = longq[0]++;
+#endif
+            if (slot < P2_LONG_MAX) { longq[1 + slot] = (uint32_t) r; continue; }
         }
-        d[k] = x;
+        uint32_t le = pos < p1 ? pos : p1, p = p0;
+        uint32_t li = (p - M) | 0x80000000u;
+#pragma unroll 1
+        for (; p < le; p++, li++) src[P2_SIDX(p - c)] = li;                           /* literal run */
+        if (off >= len) {
+            uint32_t sv = p - off + P2_SBIAS;
+#pragma unroll 1
+            for (; p < p1; p++, sv++) src[P2_SIDX(p - c)] = sv;                       /* plain match */
+        }
+        else {
+#pragma unroll 1
+            for (; p < p1; p++) src[P2_SIDX(p - c)] = p2_desc(p, pos, M, off, len);   /* overlapping match */
+        }
+    }
+}
+/* second half of pass A: the queued long records, all lanes together (call after a warp sync) */
+MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src, const uint32_t *longq)
+{
+    uint32_t nl = longq[0] < P2_LONG_MAX ? longq[0] : P2_LONG_MAX;
+#pragma unroll 1
+    for (uint32_t i = 0; i < nl; i++) {
+        int r = (int) longq[1 + i];
+        uint32_t lit0 = (r == 0) ? c : rec_pos(wa[r - 1]) + rec_len(wb[r - 1]);
+        uint32_t a = wa[r], b = wb[r], pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b);
+        uint32_t p0 = lit0 > c ? lit0 : c, p1 = pos + len < cend ? pos + len : cend;
+#pragma unroll 1
+        for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc(p, pos, M, off, len);
     }
 }
 
-/* Pass B: fetch the 16 bytes described by d[] (little-endian in 4 words; positions >= size give 0).  A source inside
+/* Pass B: fetch this lane's 16 bytes [q0, q0+16) (little-endian in 4 words; positions >= size give 0).  A source inside
  * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
  * decrease so it terminates).  All chases first, then all byte loads, so the loads overlap. */
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, uint32_t d[16],
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
                     const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
     const uint32_t n = size - q0 < 16 ? size - q0 : 16;
     const uint32_t inchunk = c + P2_SBIAS;
+    const uint32_t *row = src + P2_SIDX(q0 - c);
+    uint32_t d[16];
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t x = d[k];
+        uint32_t x = (k < n) ? row[k] : 0x80000000u;
 #pragma unroll 1
         while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];    /* literal descriptors are negative as int32 */
         d[k] = x;
@@ -112,7 +146,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, const uint8_t *lits,
                                                  uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint32_t *src)
+                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -126,10 +160,16 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             __syncwarp();
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t q0 = c + 16u * (uint32_t) lane, w[4], d[16];
-        p2_pass_a(q0, c, size, wa, wb, src, d);
+        uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
+        const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
+        const int r_lo = p2_search(wa, wb, c);                 /* uniform: first record reaching into the chunk */
+        if (lane == 0) longq[0] = 0;
         __syncwarp();
-        p2_pass_b(q0, c, size, src, d, lits, unit_out, g0, w);
+        p2_pass_a_records(lane, r_lo, c, cend, wa, wb, src, longq);
+        __syncwarp();
+        p2_pass_a_long(lane, c, cend, wa, wb, src, longq);
+        __syncwarp();
+        p2_pass_b(q0, c, size, src, lits, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -29,9 +29,14 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits,
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t w[32][4], d[32][16]; uint32_t src[P2_SRC_WORDS];
-        for (int lane = 0; lane < 32; lane++) p2_pass_a(c + 16u * lane, c, size, wa.data(), wb.data(), src, d[lane]);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, d[lane], lits, unit_out, g0, w[lane]);
+        uint32_t w[32][4]; uint32_t src[P2_SRC_WORDS], longq[P2_LONG_MAX + 1];
+        const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
+        const int r_lo = p2_search(wa.data(), wb.data(), c);
+        longq[0] = 0;
+        for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;     /* a position no record covers would show up as garbage */
+        for (int lane = 0; lane < 32; lane++) p2_pass_a_records(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq);
+        for (int lane = 0; lane < 32; lane++) p2_pass_a_long(lane, c, cend, wa.data(), wb.data(), src, longq);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, lits, unit_out, g0, w[lane]);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
