@@ -144,6 +144,13 @@ MS_D uint32_t lsb_read(MsBits &b, int n) {        /* READ_BITS, 0 <= n <= 16; ca
     uint32_t v = lsb_peek(b, n); lsb_drop(b, n); return v;
 }
 MS_D void lsb_align_byte(MsBits &b) { int r = b.bc & 7; lsb_drop(b, r); }   /* bc == -p mod 8 since ipos*8 is a multiple of 8 */
+/* byte position of the (byte-aligned) reader, and repositioning it to an arbitrary byte */
+MS_D int32_t lsb_bytepos(const MsBits &b) { return b.ipos - (b.bc >> 3); }
+MS_D void lsb_seek_byte(MsBits &b, int32_t bytepos) {
+    ms_bits_seek(b, bytepos & ~3);
+    lsb_refill(b);
+    lsb_drop(b, 8 * (bytepos & 3));
+}
 
 /* ---- MSB-first over 16-bit little-endian words (LZX: readbits.h:155-160, lzxd.c:86-91).
  *      Next bit = bit 63 of bb. ---- */
@@ -380,6 +387,18 @@ MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *lit) { e.rec = rec; e.lit =
 MS_D void emit_literal(MsEmit &e, uint32_t byte) {
     e.litacc |= byte << (8 * (e.nlit & 3)); e.nlit++;
     if ((e.nlit & 3) == 0) { *reinterpret_cast<uint32_t *>(e.lit + e.nlit - 4) = e.litacc; e.litacc = 0; }
+}
+/* n raw input bytes in[bytepos .. bytepos+n) straight into the literal stream (stored / uncompressed blocks): four
+ * bytes per store once the stream is word aligned.  The caller has checked bytepos + n <= in_len. */
+MS_D void emit_raw(MsEmit &e, const uint8_t *in, int32_t bytepos, uint32_t n) {
+    const uint8_t *p = in + bytepos;
+#pragma unroll 1
+    while (n && (e.nlit & 3)) { emit_literal(e, *p++); n--; }
+#pragma unroll 1
+    for (; n >= 4; n -= 4, p += 4, e.nlit += 4)
+        *reinterpret_cast<uint32_t *>(e.lit + e.nlit) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+#pragma unroll 1
+    while (n) { emit_literal(e, *p++); n--; }
 }
 /* record: a = pos | M << 16 (M = match bytes before this record), b = off | len << 22 */
 MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {

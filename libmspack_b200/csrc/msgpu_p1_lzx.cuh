@@ -239,6 +239,10 @@ struct LzxLane {
         bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
+            if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
+                emit_raw(em, b.in, bytepos, (uint32_t) this_run);
+                bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
+            }
 #pragma unroll 1
             while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
             if (b.err) fail(b.err);

@@ -124,6 +124,13 @@ struct ZipLane {
             lsb_refill(b); uint32_t clen = lsb_read(b, 16);
             if (b.err) { fail(b.err); return; }
             if (len != (~clen & 0xFFFFu)) { fail(MS_EDECRUNCH); return; }
+            {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
+                int32_t bp = lsb_bytepos(b);
+                if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
+                    emit_raw(em, b.in, bp, len);
+                    q += len; lsb_seek_byte(b, bp + (int32_t) len); len = 0;
+                }
+            }
 #pragma unroll 1
             for (uint32_t k = 0; k < len; k++) {
                 lsb_refill(b);
