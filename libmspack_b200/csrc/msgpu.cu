@@ -31,7 +31,6 @@ struct WaveArgs {
     uint8_t *out_base;
     MsUnitState *ustate;         /* [slots] */
     MsRec *recs;                 /* [slots][F][MS_MAXREC] */
-    uint8_t *lits;               /* [slots][F][MS_LITCAP] */
     MsFrameInfo *finfo;          /* [slots][F] */
     uint32_t *not_done;          /* per sub-wave counters; a kernel adds to not_done[sub] */
     int F, sub;
@@ -63,7 +62,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     if (valid) {
         t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT, LCACHE> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F);
     }
     p1_run(t);
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip_c(WaveArgs a, const uint32_t *o
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F);
     }
     p1_run(t);
@@ -102,14 +101,14 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     if (valid) {
         t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
     p1_run(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT, int HEADN>
+template <int NT, int HEADN, int MODE>
 __global__ void __launch_bounds__(NT) k_p1_lzx_c(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
@@ -117,12 +116,12 @@ __global__ void __launch_bounds__(NT) k_p1_lzx_c(WaveArgs a, const uint32_t *ord
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN> t; t.phase = PH_IDLE;
+    LzxLaneC<NT, HEADN, MODE> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<LzxSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
     p1_run(t);
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
     if (valid) {
         t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.lits + (size_t) slot * a.F * MS_LITCAP,
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
     }
     p1_run(t);
@@ -162,8 +161,8 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
-        p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, a.lits + ((size_t) slot * a.F + f) * MS_LITCAP,
-                         fi.size, unit_out, fi.g0, s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp]);
+        p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+                         s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp]);
     }
 }
 
@@ -205,7 +204,8 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
 #define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
 /* table-free canonical LZX lanes (id, threads per CTA, shared-memory head entries) */
-#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64) X(14, 448, 32) X(15, 384, 112) X(16, 416, 80) X(17, 448, 76)
+/* (id, threads per CTA, shared-memory head entries, step mode: 0 plain, 1 look-ahead) */
+#define LZXC_VARIANTS(X) X(10, 512, 32, 0) X(11, 448, 48, 0) X(12, 384, 64, 0) X(18, 448, 48, 1)
 #define QTM_NT 160
 
 struct DevBuf {
@@ -235,10 +235,10 @@ struct msgpu_ctx {
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
-    DevBuf units, ustate, recs, lits, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
+    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     size_t bytes_held() const {
-        return units.cap + ustate.cap + recs.cap + lits.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
+        return units.cap + ustate.cap + recs.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
                save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap;
     }
 };
@@ -281,7 +281,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTR(id, nt, mr, lr, lc, lb) cudaFuncSetAttribute(k_p1_lzx<nt, mr, lr, lc, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<nt, mr, lr, lc, lb>));
     LZX_VARIANTS(SETATTR)
 #undef SETATTR
-#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx_c<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
+#define SETATTRC(id, nt, hn, md) cudaFuncSetAttribute(k_p1_lzx_c<nt, hn, md>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 11; }
@@ -292,7 +292,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 extern "C" void msgpu_destroy(msgpu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->lits, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
+    DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
                        &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status };
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -368,7 +368,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNT(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZX_VARIANTS(PICKNT)
 #undef PICKNT
-#define PICKNTC(id, nt, hn) if (ctx->lzx_variant == id) lzx_nt = nt;
+#define PICKNTC(id, nt, hn, md) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
 #define PICKNTZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) zip_nt = nt;
@@ -398,7 +398,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(ctx->units.reserve((size_t) n * sizeof(msgpu_unit)), "alloc units");
     CK(ctx->ustate.reserve((size_t) n * sizeof(MsUnitState)), "alloc state");
     CK(ctx->recs.reserve((size_t) n * F * MS_MAXREC * sizeof(MsRec)), "alloc records");
-    CK(ctx->lits.reserve((size_t) n * F * MS_LITCAP + 64), "alloc literals");
     CK(ctx->finfo.reserve((size_t) n * F * sizeof(MsFrameInfo)), "alloc frame info");
     CK(ctx->misc.reserve(4096), "alloc misc");
     CK(ctx->order.reserve((size_t) (2 * n + 3) * sizeof(uint32_t)), "alloc order");
@@ -428,7 +427,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     WaveArgs a;
     a.units = reinterpret_cast<const msgpu_unit *>(ctx->units.p); a.in_base = reinterpret_cast<const uint8_t *>(d_in);
     a.out_base = reinterpret_cast<uint8_t *>(d_out); a.ustate = reinterpret_cast<MsUnitState *>(ctx->ustate.p);
-    a.recs = reinterpret_cast<MsRec *>(ctx->recs.p); a.lits = reinterpret_cast<uint8_t *>(ctx->lits.p);
+    a.recs = reinterpret_cast<MsRec *>(ctx->recs.p);
     a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.F = F; a.sub = 0;
 
     while (ctx->evs.size() < ctx->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e), "event create"); ctx->evs.push_back(e); }
@@ -496,7 +495,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define LAUNCH(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) k_p1_lzx<nt, mr, lr, lc, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxShared<nt, mr, lr, lc, lb>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZX_VARIANTS(LAUNCH)
 #undef LAUNCH
-#define LAUNCHC(id, nt, hn) if (ctx->lzx_variant == id) k_p1_lzx_c<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCHC(id, nt, hn, md) if (ctx->lzx_variant == id) k_p1_lzx_c<nt, hn, md><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZXC_VARIANTS(LAUNCHC)
 #undef LAUNCHC
             mark(0, st); mark(1, st);
@@ -580,7 +579,7 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
     /* wave size from the scratch budget */
     uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
     const int F = maxfr >= 2 ? 2 : 1;
-    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec) + MS_LITCAP) + sizeof(MsUnitState) + 6144;
+    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec)) + sizeof(MsUnitState) + 6144;
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();

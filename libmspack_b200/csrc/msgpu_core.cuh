@@ -61,7 +61,6 @@ static inline uint32_t ms_brev32_host(uint32_t v) {
 
 #define MS_FRAME      32768u
 #define MS_MAXREC     16400u     /* matches per frame <= 32768/2, + sentinel, padded            */
-#define MS_LITCAP     32768u     /* literal bytes per frame                                     */
 #define MS_WARP       32
 
 #define MS_OK        MSGPU_ERR_OK
@@ -71,7 +70,7 @@ static inline uint32_t ms_brev32_host(uint32_t v) {
 #define MS_EARGS     MSGPU_ERR_ARGS
 
 /* ---- intermediate form ------------------------------------------------------------------ */
-struct MsRec { uint32_t a, b; };            /* a = pos | M << 16, b = off | len << 22 (see emit_match) */
+struct alignas(8) MsRec { uint32_t a, b; };            /* a = pos, b = off | len << 22 (see emit_match) */
 struct MsFrameInfo {
     uint32_t nrec;      /* match records (a sentinel {pos = size, len = 0} follows them)          */
     uint32_t size;      /* bytes this frame contributes to the output (0 = nothing / failed)      */
@@ -109,11 +108,16 @@ struct MsBits {
     uint32_t nextw;         /* the 32-bit word at ipos, loaded one refill ahead of its use so that the load
                              * latency overlaps a whole decode step instead of stalling it             */
     int32_t err;
+    int32_t fast_end;       /* last byte offset a whole aligned word can be loaded from (in_len - 4), or a negative
+                             * number when `in` is not 4-byte aligned; ipos is always a multiple of 4             */
 };
+
+/* call after changing b.in / b.in_len */
+MS_D void ms_bits_rebase(MsBits &b) { b.fast_end = (reinterpret_cast<uintptr_t>(b.in) & 3u) == 0 ? b.in_len - 4 : -0x40000000; }
 
 MS_D uint32_t ms_load32(const MsBits &b, int32_t ip) {
     const uint8_t *p = b.in + ip;
-    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && ip + 4 <= b.in_len) return *reinterpret_cast<const uint32_t *>(p);
+    if (ip <= b.fast_end) return *reinterpret_cast<const uint32_t *>(p);
     uint32_t v = 0;                      /* tail of the unit, or a unit that is not 4-byte aligned: bytewise, zero past the end */
 #pragma unroll
     for (int k = 0; k < 4; k++) { int32_t i = ip + k; if (i < b.in_len) v |= (uint32_t) p[k] << (8 * k); }
@@ -121,9 +125,9 @@ MS_D uint32_t ms_load32(const MsBits &b, int32_t ip) {
 }
 /* (re)position the reader: the next stream bit is the first bit of the word at byte offset ip */
 MS_D void ms_bits_seek(MsBits &b, int32_t ip) { b.ipos = ip; b.bb = 0; b.bc = 0; b.nextw = ms_load32(b, ip); }
-MS_D void ms_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) { b.in = in; b.in_len = (int32_t) in_len; b.err = 0; ms_bits_seek(b, 0); }
+MS_D void ms_bits_init(MsBits &b, const uint8_t *in, uint32_t in_len) { b.in = in; b.in_len = (int32_t) in_len; b.err = 0; ms_bits_rebase(b); ms_bits_seek(b, 0); }
 MS_D void ms_bits_restore(MsBits &b, const uint8_t *in, uint32_t in_len, int32_t ipos, int32_t bc, uint64_t bb) {
-    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; b.ipos = ipos; b.bc = bc; b.bb = bb; b.nextw = ms_load32(b, ipos);
+    b.in = in; b.in_len = (int32_t) in_len; b.err = 0; ms_bits_rebase(b); b.ipos = ipos; b.bc = bc; b.bb = bb; b.nextw = ms_load32(b, ipos);
 }
 
 /* bits consumed so far, relative to `in` */
@@ -380,31 +384,32 @@ MS_D uint32_t ms_canon_index(const uint32_t *bo, uint32_t v16, int len) {
  * ============================================================================================= */
 struct MsEmit {
     MsRec *rec;             /* this frame's record array */
-    uint8_t *lit;           /* this frame's literal stream (4-byte aligned) */
-    uint32_t nrec, nlit, litacc, mbytes;
+    uint8_t *out;           /* the frame's first byte in the unit's output buffer: literals are stored in place */
+    uint32_t nrec, limit;   /* limit = bytes of this frame that exist in the output buffer */
 };
-MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *lit) { e.rec = rec; e.lit = lit; e.nrec = 0; e.nlit = 0; e.litacc = 0; e.mbytes = 0; }
-MS_D void emit_literal(MsEmit &e, uint32_t byte) {
-    e.litacc |= byte << (8 * (e.nlit & 3)); e.nlit++;
-    if ((e.nlit & 3) == 0) { *reinterpret_cast<uint32_t *>(e.lit + e.nlit - 4) = e.litacc; e.litacc = 0; }
+MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *out, uint32_t limit) { e.rec = rec; e.out = out; e.nrec = 0; e.limit = limit; }
+/* literal byte at frame position q.  LZX and Quantum never decode past the frame (q < limit by construction); MSZIP
+ * blocks can inflate past what the unit asked for, hence the checked flavour. */
+MS_D void emit_literal(MsEmit &e, uint32_t q, uint32_t byte) { e.out[q] = (uint8_t) byte; }
+MS_D void emit_literal_checked(MsEmit &e, uint32_t q, uint32_t byte) { if (q < e.limit) e.out[q] = (uint8_t) byte; }
+/* n raw input bytes in[bytepos .. bytepos+n) to frame positions q.. (stored / uncompressed blocks), clipped to the frame:
+ * four bytes per store once the destination is word aligned.  The caller has checked bytepos + n <= in_len. */
+MS_D void emit_raw(MsEmit &e, uint32_t q, const uint8_t *in, int32_t bytepos, uint32_t n) {
+    if (q >= e.limit) return;
+    if (n > e.limit - q) n = e.limit - q;
+    const uint8_t *p = in + bytepos; uint8_t *d = e.out + q;
+#pragma unroll 1
+    while (n && (reinterpret_cast<uintptr_t>(d) & 3u)) { *d++ = *p++; n--; }
+#pragma unroll 1
+    for (; n >= 4; n -= 4, p += 4, d += 4)
+        *reinterpret_cast<uint32_t *>(d) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+#pragma unroll 1
+    while (n) { *d++ = *p++; n--; }
 }
-/* n raw input bytes in[bytepos .. bytepos+n) straight into the literal stream (stored / uncompressed blocks): four
- * bytes per store once the stream is word aligned.  The caller has checked bytepos + n <= in_len. */
-MS_D void emit_raw(MsEmit &e, const uint8_t *in, int32_t bytepos, uint32_t n) {
-    const uint8_t *p = in + bytepos;
-#pragma unroll 1
-    while (n && (e.nlit & 3)) { emit_literal(e, *p++); n--; }
-#pragma unroll 1
-    for (; n >= 4; n -= 4, p += 4, e.nlit += 4)
-        *reinterpret_cast<uint32_t *>(e.lit + e.nlit) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
-#pragma unroll 1
-    while (n) { emit_literal(e, *p++); n--; }
-}
-/* record: a = pos | M << 16 (M = match bytes before this record), b = off | len << 22 */
+/* record: a = pos, b = off | len << 22 */
 MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
-    MsRec r; r.a = pos | (e.mbytes << 16); r.b = off | (len << 22); e.rec[e.nrec++] = r; e.mbytes += len;
+    MsRec r; r.a = pos; r.b = off | (len << 22); e.rec[e.nrec++] = r;
 }
 MS_D void emit_end(MsEmit &e, uint32_t frame_size) {
-    if (e.nlit & 3) *reinterpret_cast<uint32_t *>(e.lit + (e.nlit & ~3u)) = e.litacc;
-    MsRec r; r.a = frame_size | (e.mbytes << 16); r.b = 0; e.rec[e.nrec] = r;       /* sentinel: pos = size, len = 0 */
+    MsRec r; r.a = frame_size; r.b = 0; e.rec[e.nrec] = r;       /* sentinel: pos = size, len = 0 */
 }

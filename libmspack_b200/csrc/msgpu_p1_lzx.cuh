@@ -46,7 +46,7 @@ struct LzxLane {
     uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
     int32_t bytepos;                      /* valid in bytemode: next raw byte (relative to b.in) */
     /* unit / launch context */
-    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; int32_t *e8info;
+    const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo; int32_t *e8info;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
     int f, max_frames;
@@ -102,7 +102,7 @@ struct LzxLane {
      * cleared block_type first, lzxd.c:257-270 vs :469-474) moves the 16-bit word grid by one byte. */
     MS_M void enter_bits() {
         if (!bytemode) return;
-        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; }
+        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; ms_bits_rebase(b); }
         ms_bits_seek(b, bytepos & ~3);
         lzx_refill(b);
         if (bytepos & 2) msb_drop(b, 16);
@@ -226,7 +226,7 @@ struct LzxLane {
         }
         frame_size = ms_min(MS_FRAME, u->out_len - produced);                                        /* :458-461 */
         bytes_todo = (int32_t) frame_size; q = 0;
-        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, frame_size);
         phase = PH_BLOCK;
     }
 
@@ -240,11 +240,11 @@ struct LzxLane {
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
             if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
-                emit_raw(em, b.in, bytepos, (uint32_t) this_run);
+                emit_raw(em, q, b.in, bytepos, (uint32_t) this_run);
                 bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
             }
 #pragma unroll 1
-            while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
+            while (this_run > 0) { emit_literal(em, q, raw_byte()); q++; this_run--; }
             if (b.err) fail(b.err);
             return;
         }
@@ -266,7 +266,7 @@ struct LzxLane {
              * the only effect is MSPACK_ERR_READ on an exactly-cut unit */
             if ((u->out_len % MS_FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
                 int32_t bp;
-                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; } bp = bytepos; }
+                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; ms_bits_rebase(b); } bp = bytepos; }
                 else bp = b.ipos - (b.bc >> 3);
                 uint32_t hb = (bp + 1 < b.in_len) ? b.in[bp + 1] : 0u;
                 int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
@@ -305,7 +305,7 @@ struct LzxLane {
             lzx_refill(b);
             sym = main_sym();
             if (sym >= 256) break;
-            emit_literal(em, sym); q++; this_run--;
+            emit_literal(em, q, sym); q++; this_run--;
             if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
             if (this_run <= 0) { phase = PH_BLOCK; return; }
             if (++rep == LITB) return;
@@ -354,7 +354,7 @@ struct LzxLane {
 
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int32_t *e8, int nframes) {
-        u = unit; recs = r; lits = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;
+        u = unit; recs = r; uout = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;
         frame_start_pos = 0; frame_size = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }

@@ -23,7 +23,7 @@ struct LzxSharedC {
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int HEADN>
+template <int NT, int HEADN, int MODE = 0>
 struct LzxLaneC {
     MsBits b;
     uint32_t *mbo, *lbo, *abo;
@@ -36,10 +36,11 @@ struct LzxLaneC {
     uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
     int32_t bytepos;                      /* valid in bytemode: next raw byte (relative to b.in) */
     /* unit / launch context */
-    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; int32_t *e8info;
+    const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo; int32_t *e8info;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
     int f, max_frames;
+    uint32_t next_sym; bool have_next;      /* look-ahead of step_t(); never live across a run boundary */
 
     MS_M void bind(LzxSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
         mbo = sh->mbo + tid; lbo = sh->lbo + tid; abo = sh->abo + tid; mhead = sh->mhead + tid;
@@ -96,7 +97,7 @@ struct LzxLaneC {
      * cleared block_type first, lzxd.c:257-270 vs :469-474) moves the 16-bit word grid by one byte. */
     MS_M void enter_bits() {
         if (!bytemode) return;
-        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; }
+        if (bytepos & 1) { b.in += 1; b.in_len -= 1; base += 1; bytepos -= 1; ms_bits_rebase(b); }
         ms_bits_seek(b, bytepos & ~3);
         lzx_refill(b);
         if (bytepos & 2) msb_drop(b, 16);
@@ -229,7 +230,7 @@ struct LzxLaneC {
         }
         frame_size = ms_min(MS_FRAME, u->out_len - produced);                                        /* :458-461 */
         bytes_todo = (int32_t) frame_size; q = 0;
-        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, frame_size);
         phase = PH_BLOCK;
     }
 
@@ -243,11 +244,11 @@ struct LzxLaneC {
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
             if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
-                emit_raw(em, b.in, bytepos, (uint32_t) this_run);
+                emit_raw(em, q, b.in, bytepos, (uint32_t) this_run);
                 bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
             }
 #pragma unroll 1
-            while (this_run > 0) { emit_literal(em, raw_byte()); q++; this_run--; }
+            while (this_run > 0) { emit_literal(em, q, raw_byte()); q++; this_run--; }
             if (b.err) fail(b.err);
             return;
         }
@@ -269,7 +270,7 @@ struct LzxLaneC {
              * the only effect is MSPACK_ERR_READ on an exactly-cut unit */
             if ((u->out_len % MS_FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
                 int32_t bp;
-                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; } bp = bytepos; }
+                if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; ms_bits_rebase(b); } bp = bytepos; }
                 else bp = b.ipos - (b.bc >> 3);
                 uint32_t hb = (bp + 1 < b.in_len) ? b.in[bp + 1] : 0u;
                 int32_t need = (hb & 0x80) ? bp + 8 : bp + 4;
@@ -303,11 +304,15 @@ struct LzxLaneC {
      * handle a match, which is the longer path. */
     MS_M void step() {
         /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
-         * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks evaluated */
-        const bool careful = b.ipos + 24 > b.in_len;
+         * three 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
+        if (MODE == 1) { if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_ahead<true>(); else step_ahead<false>(); }
+        else           { if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_plain<true>(); else step_plain<false>(); }
+    }
+    /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
+    template <bool careful> MS_M void step_plain() {
         lzx_refill(b);
         uint32_t sym = main_sym(careful);
-        if (sym < 256) { emit_literal(em, sym); q++; this_run--; }
+        if (sym < 256) { emit_literal(em, q, sym); q++; this_run--; }
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
@@ -316,9 +321,11 @@ struct LzxLaneC {
                 ml += length_sym(careful);
             }
             ml += 2;
-            if (slot == 0) off = R0;
-            else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
-            else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
+            if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
+                const uint32_t r0 = R0;
+                off = slot == 0 ? r0 : (slot == 1 ? R1 : R2);
+                R1 = slot == 1 ? r0 : R1; R2 = slot == 2 ? r0 : R2; R0 = off;
+            }
             else {
                 /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
                 uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
@@ -333,22 +340,74 @@ struct LzxLaneC {
                 R2 = R1; R1 = R0; R0 = off;
             }
             if (careful && b.err) { fail(b.err); return; }
-            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
-             * inside the unit during the first lap of the window (every unit up to 2^window_bits bytes never leaves it) */
-            uint32_t G = frame_start_pos + q, eff = off;
-            if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
-                uint32_t wpr = G & (window_size - 1);
-                bool bad = (wpr + ml > window_size);
-                if (off > wpr) {
-                    bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
-                    if (off > window_size) eff = off - window_size;
-                }
-                if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
-                if (bad) { fail(MS_EDECRUNCH); return; }
+            if (!resolve_match(ml, off)) return;
+        }
+        if (careful && b.err) { fail(b.err); return; }
+        if (this_run <= 0) phase = PH_BLOCK;
+    }
+    /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
+     * inside the unit during the first lap of the window (every unit up to 2^window_bits bytes never leaves it) */
+    MS_M bool resolve_match(uint32_t ml, uint32_t off) {
+        uint32_t G = frame_start_pos + q, eff = off;
+        if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
+            uint32_t wpr = G & (window_size - 1);
+            bool bad = (wpr + ml > window_size);
+            if (off > wpr) {
+                bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
+                if (off > window_size) eff = off - window_size;
             }
-            if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return; }   /* :678-693 every overrun ends in an error */
-            emit_match(em, q, ml, eff);
-            q += ml; this_run -= (int32_t) ml;
+            if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
+            if (bad) { fail(MS_EDECRUNCH); return false; }
+        }
+        if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return false; }   /* :678-693 every overrun ends in an error */
+        emit_match(em, q, ml, eff);
+        q += ml; this_run -= (int32_t) ml;
+        return true;
+    }
+    /* Software-pipelined: the NEXT main symbol is decoded (its load issued) as soon as this symbol's last bit is known, and
+     * the validation + emit work of this symbol runs underneath that load's latency (the symbol array lives in L2).  The
+     * look-ahead never crosses a run boundary (block / frame end, where the stream may realign or the trees change) and
+     * is switched off near the end of the input, so it reads exactly the bits the reference would read next. */
+    template <bool careful> MS_M void step_ahead() {
+        uint32_t sym;
+        if (have_next) sym = next_sym;
+        else { lzx_refill(b); sym = main_sym(careful); }
+        const bool is_lit = sym < 256;
+        uint32_t ml = 1, off = 0, slot = 0;
+        if (!is_lit) {
+            sym -= 256;
+            ml = sym & 7; slot = sym >> 3;
+            if (ml == 7) {
+                if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
+                ml += length_sym(careful);
+            }
+            ml += 2;
+            if (slot >= 3) {
+                /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
+                uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                off = pbase - 2;
+                lzx_refill(b);
+                if (block_type == 2 && extra >= 3) {
+                    if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
+                    off += sym_smem(alim, abo, aa.sorted, careful);
+                }
+                else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
+            }
+            if (careful && b.err) { fail(b.err); return; }
+        }
+        /* look-ahead (a failing match below ends the lane, so a wasted look-ahead is harmless) */
+        have_next = !careful && (int32_t) ml < this_run;
+        if (have_next) { lzx_refill(b); next_sym = main_sym(false); }
+        if (is_lit) { emit_literal(em, q, sym); q++; this_run--; }
+        else {
+            if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
+                const uint32_t r0 = R0;
+                off = slot == 0 ? r0 : (slot == 1 ? R1 : R2);
+                R1 = slot == 1 ? r0 : R1; R2 = slot == 2 ? r0 : R2; R0 = off;
+            }
+            else { R2 = R1; R1 = R0; R0 = off; }
+            if (!resolve_match(ml, off)) return;
         }
         if (careful && b.err) { fail(b.err); return; }
         if (this_run <= 0) phase = PH_BLOCK;
@@ -356,7 +415,7 @@ struct LzxLaneC {
 
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int32_t *e8, int nframes) {
-        u = unit; recs = r; lits = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;
+        u = unit; recs = r; uout = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0; have_next = false; next_sym = 0;
         frame_start_pos = 0; frame_size = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }

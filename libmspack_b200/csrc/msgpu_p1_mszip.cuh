@@ -40,7 +40,7 @@ struct ZipLane {
     MsHuffLong<LROOT> ll;
     MsHuffLong<DROOT> dl;
     /* unit / launch context */
-    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo;
+    const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, last_block, produced, frame, done; int32_t status;
     int f, max_frames;
@@ -127,7 +127,7 @@ struct ZipLane {
             {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
                 int32_t bp = lsb_bytepos(b);
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
-                    emit_raw(em, b.in, bp, len);
+                    emit_raw(em, q, b.in, bp, len);
                     q += len; lsb_seek_byte(b, bp + (int32_t) len); len = 0;
                 }
             }
@@ -136,7 +136,7 @@ struct ZipLane {
                 lsb_refill(b);
                 uint32_t v = lsb_read(b, 8);
                 if (b.err) { fail(b.err); return; }
-                if (q < MS_FRAME) emit_literal(em, v);
+                emit_literal_checked(em, q, v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
             phase = last_block ? PH_END : PH_BLOCK;
@@ -166,7 +166,7 @@ struct ZipLane {
             if (b.err) { fail(b.err); return; }
             if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
         } while (state != 2);
-        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, ms_min(MS_FRAME, u->out_len - produced));
         q = 0;
         phase = PH_BLOCK;
     }
@@ -212,7 +212,7 @@ struct ZipLane {
             lsb_refill(b);
             sym = litlen_sym();
             if (sym >= 256) break;
-            if (q < MS_FRAME) emit_literal(em, sym);
+            emit_literal_checked(em, q, sym);
             q++;
             if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
             if (MS_UNLIKELY(q >= 2 * MS_FRAME)) { fail(MS_EDECRUNCH); return; }
@@ -243,7 +243,7 @@ struct ZipLane {
 
     /* load the unit's state for this launch */
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi, int nframes) {
-        u = unit; recs = r; lits = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
+        u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         if (!st.started) {

@@ -28,7 +28,7 @@ struct ZipLaneC {
     MsHuffAux la, da, ba;                 /* only .sorted is used (global scratch) */
     uint32_t llim[15], dlim[15];          /* limit[1..15] of the two trees, registers */
     /* unit / launch context */
-    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo;
+    const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, last_block, produced, frame, done; int32_t status;
     int f, max_frames;
@@ -117,7 +117,7 @@ struct ZipLaneC {
             {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
                 int32_t bp = lsb_bytepos(b);
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
-                    emit_raw(em, b.in, bp, len);
+                    emit_raw(em, q, b.in, bp, len);
                     q += len; lsb_seek_byte(b, bp + (int32_t) len); len = 0;
                 }
             }
@@ -126,7 +126,7 @@ struct ZipLaneC {
                 lsb_refill(b);
                 uint32_t v = lsb_read(b, 8);
                 if (b.err) { fail(b.err); return; }
-                if (q < MS_FRAME) emit_literal(em, v);
+                emit_literal_checked(em, q, v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
             phase = last_block ? PH_END : PH_BLOCK;
@@ -162,7 +162,7 @@ struct ZipLaneC {
             if (b.err) { fail(b.err); return; }
             if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
         } while (state != 2);
-        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, ms_min(MS_FRAME, u->out_len - produced));
         q = 0;
         phase = PH_BLOCK;
     }
@@ -190,64 +190,60 @@ struct ZipLaneC {
         }
     }
 
-    MS_M uint32_t litlen_sym() {
-        lsb_check(b, 16);
+    template <bool careful> MS_M uint32_t litlen_sym() {
+        if (careful) lsb_check(b, 16);
         uint32_t v = v16();
         int len = ms_canon_len(llim, v);
         uint32_t idx = ms_canon_index<NT>(lbo, v, len);
         lsb_drop(b, len);
         return idx < (uint32_t) HEADN ? (uint32_t) lhead[idx * NT] : (uint32_t) la.sorted[idx * MS_WARP];
     }
-    MS_M uint32_t dist_sym() {
-        lsb_check(b, 16);
+    template <bool careful> MS_M uint32_t dist_sym() {
+        if (careful) lsb_check(b, 16);
         uint32_t v = v16();
         int len = ms_canon_len(dlim, v);
         uint32_t idx = ms_canon_index<NT>(dbo, v, len);
         lsb_drop(b, len);
         return dhead[(idx & 31u) * NT];
     }
+    template <bool careful> MS_M uint32_t extra_bits(int n) {
+        if (careful) return lsb_read(b, n);
+        uint32_t v = lsb_peek(b, n); lsb_drop(b, n); return v;
+    }
 
-    /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the
-     * end-of-block code */
-    MS_M void step() {
-        uint32_t sym;
-#pragma unroll 1
-        for (int rep = 0;;) {
-            lsb_refill(b);
-            sym = litlen_sym();
-            if (sym >= 256) break;
-            if (q < MS_FRAME) emit_literal(em, sym);
-            q++;
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            if (MS_UNLIKELY(q >= 2 * MS_FRAME)) { fail(MS_EDECRUNCH); return; }
-            if (++rep == 1) return;
-        }
-        if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
-
+    /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the end-of-block code.
+     * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
+     * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
+    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_t<true>(); else step_t<false>(); }
+    template <bool careful> MS_M void step_t() {
+        lsb_refill(b);
+        uint32_t sym = litlen_sym<careful>();
+        if (sym < 256) { emit_literal_checked(em, q, sym); q++; }
+        else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
         else {
             uint32_t c = sym - 257, eb, length, dist;
             if (c >= 29) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :255 */
             if (c < 8) { eb = 0; length = c + 3; }                             /* lit_lengths / lit_extrabits, :47-62 */
             else if (c == 28) { eb = 0; length = 258; }
             else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
-            if (eb) length += lsb_read(b, (int) eb);
-            if (b.err) { fail(b.err); return; }
+            if (eb) length += extra_bits<careful>((int) eb);
+            if (careful && b.err) { fail(b.err); return; }
             lsb_refill(b);
-            uint32_t d = dist_sym();
+            uint32_t d = dist_sym<careful>();
             if (d >= 30) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :260 */
             if (d < 4) { eb = 0; dist = d + 1; }                               /* dist_offsets / dist_extrabits, :53-68 */
             else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
-            if (eb) dist += lsb_read(b, (int) eb);
+            if (eb) dist += extra_bits<careful>((int) eb);
             if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
             q += length;
         }
-        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (careful && b.err) { fail(b.err); return; }
         if (MS_UNLIKELY(q >= 2 * MS_FRAME)) fail(MS_EDECRUNCH);
     }
 
     /* load the unit's state for this launch */
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi, int nframes) {
-        u = unit; recs = r; lits = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
+        u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         if (!st.started) {

@@ -153,7 +153,7 @@ struct QtmLane {
     }
 
     /* unit / launch context */
-    const msgpu_unit *u; MsRec *recs; uint8_t *lits; MsFrameInfo *finfo; uint8_t *save;
+    const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo; uint8_t *save;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, limit, produced, frame, done, header_read, frame_todo, window_size, frame_start_pos; int32_t status;
     int f, max_frames;
@@ -169,7 +169,8 @@ struct QtmLane {
         frame_start_pos = produced;
         limit = ms_min(frame_todo, u->out_len - produced);                 /* bytes of this frame the request still wants */
         q = 0;
-        emit_begin(em, recs + (size_t) f * MS_MAXREC, lits + (size_t) f * MS_LITCAP);
+        emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, limit);
+        next_selector();
         phase = limit ? PH_DECODE : PH_END;
     }
 
@@ -196,33 +197,41 @@ struct QtmLane {
         }
     }
 
-    /* the hot step (qtmd.c:307-417): one selector symbol and whatever it introduces */
+    /* The hot step (qtmd.c:307-417), cut into micro-steps of ONE model symbol each so that every lane of the warp sits in the
+     * same GET_SYMBOL code whatever its symbol is doing: a literal is selector -> literal model, a match is selector ->
+     * [length model ->] offset model.  `mst` says what the next model symbol means; m_base / m_idx / m_ent name its model.
+     * A frame can only end after a complete symbol, so the micro-state never has to survive a launch. */
+    enum { QS_SELECTOR = 0, QS_LITERAL = 1, QS_LENGTH = 2, QS_OFFSET = 3 };
+    uint32_t mst, m_ml; int m_base, m_idx, m_ent;
+
+    MS_M void next_selector() { mst = QS_SELECTOR; m_base = QM7; m_idx = 8; m_ent = 7; }
+
     MS_M void step() {
-        uint32_t selector = get_symbol(QM7, 8, 7);
-        if (selector < 4) {
-            uint32_t s = get_symbol(QM0 + 65 * (int) selector, (int) selector, 64);
-            emit_literal(em, s); q++; frame_todo--;
+        uint32_t s = get_symbol(m_base, m_idx, m_ent);
+        if (mst == QS_SELECTOR) {
+            if (s < 4) { mst = QS_LITERAL; m_base = QM0 + 65 * (int) s; m_idx = (int) s; m_ent = 64; }
+            else if (s == 4) { mst = QS_OFFSET; m_ml = 3; m_base = QM4; m_idx = 4; m_ent = ent4; }
+            else if (s == 5) { mst = QS_OFFSET; m_ml = 4; m_base = QM5; m_idx = 5; m_ent = ent5; }
+            else if (s == 6) { mst = QS_LENGTH; m_base = QM6L; m_idx = 7; m_ent = 27; }
+            else { fail(b.err ? b.err : MS_EDECRUNCH); return; }
+            if (MS_UNLIKELY(b.err)) fail(b.err);
+            return;
+        }
+        if (mst == QS_LITERAL) { emit_literal(em, q, s); q++; frame_todo--; }
+        else if (mst == QS_LENGTH) {
+            /* length_base[] / length_extra[] (qtmd.c:76-83) in closed form */
+            uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
+            uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
+            m_ml = lb + read_many((int) le) + 5;
+            mst = QS_OFFSET; m_base = QM6; m_idx = 6; m_ent = ent6;
+            if (MS_UNLIKELY(b.err)) fail(b.err);
+            return;
         }
         else {
-            uint32_t ml, off, s, extra;
-            if (selector == 4) { s = get_symbol(QM4, 4, ent4); ml = 3; }
-            else if (selector == 5) { s = get_symbol(QM5, 5, ent5); ml = 4; }
-            else if (selector == 6) {
-                s = get_symbol(QM6L, 7, 27);
-                /* length_base[] / length_extra[] (qtmd.c:76-83) in closed form */
-                uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
-                uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
-                extra = read_many((int) le);
-                ml = lb + extra + 5;
-                s = get_symbol(QM6, 6, ent6);
-            }
-            else { fail(b.err ? b.err : MS_EDECRUNCH); return; }
-            {   /* position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
-                uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
-                uint32_t pb = s < 2 ? s : (2u + (s & 1)) << pe;
-                extra = read_many((int) pe);
-                off = pb + extra + 1;
-            }
+            /* position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
+            uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
+            uint32_t pb = s < 2 ? s : (2u + (s & 1)) << pe;
+            uint32_t off = pb + read_many((int) pe) + 1, ml = m_ml;
             if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
             uint32_t G = frame_start_pos + q, window_posn = G & (window_size - 1);
             if (ml > frame_todo) { fail(MS_EDECRUNCH); return; }           /* :424-427 overshot frame alignment */
@@ -236,13 +245,14 @@ struct QtmLane {
             emit_match(em, q, emit_len, off);
             q += ml;
         }
+        next_selector();
         if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
         if (q >= limit) phase = PH_END;
     }
 
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int nframes, uint8_t *save_area) {
-        u = unit; recs = r; lits = l; finfo = fi; max_frames = nframes; save = save_area; f = 0; q = 0; limit = 0; frame_start_pos = 0;
+        u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; save = save_area; f = 0; q = 0; limit = 0; frame_start_pos = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         const int wb = unit->window_bits, wb2 = wb * 2;

@@ -1,17 +1,17 @@
 /* msgpu_p2.cuh - P2 "resolve" stage (one warp per unit) and the LZX E8 post-pass.
  *
- * Input per frame: match records sorted by position + a literal byte stream (msgpu_core.cuh).
- * The byte at frame position q is
- *     literal  lits[q - M_i]                  if q lies before record i's match (M_i = match bytes before i)
- *     match    byte (q - off) of the output   otherwise, where for an overlapping match (off < len) the
+ * Input per frame: the match records sorted by position; the literal bytes already sit at their final positions in
+ * the output buffer (P1 stores them in place).  The byte at frame position q is
+ *     literal  what P1 stored at q                if no record covers q
+ *     match    byte (q - off) of the output       otherwise, where for an overlapping match (off < len) the
  *              source folds back into the off bytes in front of the match (the byte-serial copy of
  *              lzxd.c:636-646 / mszipd.c:271-296 / qtmd.c:391-416 replicates that seed pattern).
- * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Pass A turns every position of the chunk
- * into a source descriptor (one binary search per lane, then a walk along the records); pass B fetches the
- * bytes: sources in earlier chunks are read back from the output buffer (it is the sliding window); a
- * source inside the current chunk is followed through the descriptors to ITS source until it leaves the
- * chunk or hits a literal (pointer jumping; positions strictly decrease so it terminates).  The chunk is
- * then stored with 16-byte stores.
+ * Each lane resolves 16 consecutive bytes of a 512-byte chunk.  Pass A turns every position of the chunk into a source
+ * descriptor in shared memory (lanes first mark their own 16 positions "literal", then the records that reach into the
+ * chunk are dealt out to the lanes and overwrite the positions they cover); pass B fetches the bytes: sources in earlier
+ * chunks are read back from the output buffer (it is the sliding window); a source inside the current chunk is followed
+ * through the descriptors to ITS source until it leaves the chunk or hits a literal (pointer jumping; positions strictly
+ * decrease so it terminates).  The chunk is then stored with 16-byte stores.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -20,58 +20,55 @@
 #define P2_CHUNK 512u
 
 MS_D uint32_t rec_pos(uint32_t a) { return a & 0xFFFFu; }
-MS_D uint32_t rec_M(uint32_t a)   { return a >> 16; }
 MS_D uint32_t rec_off(uint32_t b) { return b & 0x3FFFFFu; }
 MS_D uint32_t rec_len(uint32_t b) { return b >> 22; }
 
-/* first window index whose match END lies beyond q (ends are non-decreasing; the last entry's end is > q) */
-MS_D int p2_search(const uint32_t *wa, const uint32_t *wb, uint32_t q) {
-    int lo = 0, hi = P2_WIN - 1;
-#pragma unroll 1
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (rec_pos(wa[mid]) + rec_len(wb[mid]) > q) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
 /* Per-byte source descriptor (pass A -> pass B), one u32 per position of the chunk:
- *     bit 31 set : literal, low bits = index into the frame's literal stream
- *     else       : match,   value   = (frame-relative source position) + P2_SBIAS   (the source may lie in
- *                  earlier frames of the unit, i.e. be negative; overlapping matches are already folded) */
+ *     value & 0x7FFFFFFF = (frame-relative position of the byte to copy) + P2_SBIAS; the position may lie in earlier frames
+ *                          of the unit, i.e. be negative; overlapping matches are already folded
+ *     bit 31 set         : final - the byte is a literal P1 stored at that very position (never followed further) */
 #define P2_SBIAS (1 << 22)
+#define P2_LIT   0x80000000u
 /* descriptor of chunk position p (0..511) lives at P2_SIDX(p) = p + p / 16: a row of 17 words per lane, so the 32
  * lanes, which all touch "their k-th byte" at the same time, hit 32 different banks (17 is odd) */
 #define P2_SIDX(p) ((p) + ((p) >> 4))
 #define P2_SRC_WORDS (P2_CHUNK + P2_CHUNK / 16)
 
-/* descriptor of frame position p for record (pos, M, off, len): literal before the match, else (folded) match source */
-MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t M, uint32_t off, uint32_t len) {
-    if (p < pos) return (p - M) | 0x80000000u;
+/* descriptor of frame position p inside the match (pos, off, len) */
+MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t off, uint32_t len) {
     uint32_t kk = p - pos;
     if (off >= len || kk < off) return p - off + P2_SBIAS;
     return pos - off + (kk % off) + P2_SBIAS;              /* overlapping match: fold onto the seed bytes in front of it */
 }
 
-#define P2_LONG      48      /* a record covering at least this many positions of the chunk is filled by the whole warp */
+#define P2_LONG      48      /* a match covering at least this many positions of the chunk is filled by the whole warp */
 #define P2_LONG_MAX  16
 
-/* Pass A of a chunk, RECORD-parallel: the records that intersect the chunk [c, cend) are dealt out to the lanes
- * (r_lo + lane, + 32, ...); a lane writes the descriptors of "its" record - the literal run in front of the match
- * and the match - for the positions inside the chunk.  The record is decoded once, the per-position work is a store.
- * Records with a long span (long literal runs of stored data, 257-byte matches of repetitive data) are queued in
- * shared memory and filled by all 32 lanes together.  longq[0] = count, longq[1..] = window indices. */
-MS_D void p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb,
-                            uint32_t *src, uint32_t *longq)
+/* Pass A, step 1: every lane marks its own 16 positions as literals (call before a warp sync) */
+MS_D void p2_pass_a_literals(uint32_t q0, uint32_t c, uint32_t *src) {
+    uint32_t *row = src + P2_SIDX(q0 - c);
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) row[k] = P2_LIT | (q0 + k + P2_SBIAS);
+}
+
+/* Pass A, step 2, RECORD-parallel: the records that intersect the chunk [c, cend) are dealt out to the lanes
+ * (r_lo + lane, + 32, ...); a lane overwrites the descriptors of the positions "its" match covers inside the chunk.
+ * The record is decoded once, the per-position work is a store.  Matches with a long span (257-byte matches of repetitive
+ * data) are queued in shared memory and filled by all 32 lanes together.  longq[0] = count, longq[1..] = window indices.
+ * Returns the first window index this lane saw whose match ends beyond cend (P2_WIN if none): the minimum over the warp is
+ * the next chunk's r_lo. */
+MS_D int p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb,
+                           uint32_t *src, uint32_t *longq)
 {
+    int next_lo = P2_WIN;
 #pragma unroll 1
     for (int r = r_lo + lane; r < P2_WIN; r += 32) {
-        uint32_t lit0 = (r == 0) ? c : rec_pos(wa[r - 1]) + rec_len(wb[r - 1]);     /* window[0]'s predecessors all end at or before c */
-        if (lit0 >= cend) break;
-        uint32_t a = wa[r], b = wb[r], pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b);
-        uint32_t p0 = lit0 > c ? lit0 : c, p1 = pos + len < cend ? pos + len : cend;
-        if (p1 <= p0) continue;
-        if (p1 - p0 >= P2_LONG) {
+        uint32_t pos = rec_pos(wa[r]), b = wb[r], off = rec_off(b), len = rec_len(b), end = pos + len;
+        if (pos >= cend) { if (next_lo == P2_WIN) next_lo = r; break; }               /* (the sentinel has pos >= size >= cend) */
+        if (end > cend && next_lo == P2_WIN) next_lo = r;
+        uint32_t p = pos > c ? pos : c, p1 = end < cend ? end : cend;
+        if (p1 <= p) continue;
+        if (p1 - p >= P2_LONG) {
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
             uint32_t slot = atomicAdd(&longq[0], 1u);
 #else
@@ -79,10 +76,6 @@ MS_D void p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const
 #endif
             if (slot < P2_LONG_MAX) { longq[1 + slot] = (uint32_t) r; continue; }
         }
-        uint32_t le = pos < p1 ? pos : p1, p = p0;
-        uint32_t li = (p - M) | 0x80000000u;
-#pragma unroll 1
-        for (; p < le; p++, li++) src[P2_SIDX(p - c)] = li;                           /* literal run */
         if (off >= len) {
             uint32_t sv = p - off + P2_SBIAS;
 #pragma unroll 1
@@ -90,30 +83,30 @@ MS_D void p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const
         }
         else {
 #pragma unroll 1
-            for (; p < p1; p++) src[P2_SIDX(p - c)] = p2_desc(p, pos, M, off, len);   /* overlapping match */
+            for (; p < p1; p++) src[P2_SIDX(p - c)] = p2_desc(p, pos, off, len);      /* overlapping match */
         }
     }
+    return next_lo;
 }
-/* second half of pass A: the queued long records, all lanes together (call after a warp sync) */
+/* Pass A, step 3: the queued long matches, all lanes together (call after a warp sync) */
 MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src, const uint32_t *longq)
 {
     uint32_t nl = longq[0] < P2_LONG_MAX ? longq[0] : P2_LONG_MAX;
 #pragma unroll 1
     for (uint32_t i = 0; i < nl; i++) {
         int r = (int) longq[1 + i];
-        uint32_t lit0 = (r == 0) ? c : rec_pos(wa[r - 1]) + rec_len(wb[r - 1]);
-        uint32_t a = wa[r], b = wb[r], pos = rec_pos(a), M = rec_M(a), off = rec_off(b), len = rec_len(b);
-        uint32_t p0 = lit0 > c ? lit0 : c, p1 = pos + len < cend ? pos + len : cend;
+        uint32_t pos = rec_pos(wa[r]), b = wb[r], off = rec_off(b), len = rec_len(b);
+        uint32_t p0 = pos > c ? pos : c, p1 = pos + len < cend ? pos + len : cend;
 #pragma unroll 1
-        for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc(p, pos, M, off, len);
+        for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc(p, pos, off, len);
     }
 }
 
 /* Pass B: fetch this lane's 16 bytes [q0, q0+16) (little-endian in 4 words; positions >= size give 0).  A source inside
  * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
- * decrease so it terminates).  All chases first, then all byte loads, so the loads overlap. */
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
-                    const uint8_t *lits, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
+ * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
+ * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero. */
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
@@ -123,35 +116,31 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
     uint32_t d[16];
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t x = (k < n) ? row[k] : 0x80000000u;
+        uint32_t x = (k < n) ? row[k] : P2_LIT;
 #pragma unroll 1
-        while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];    /* literal descriptors are negative as int32 */
-        d[k] = x;
+        while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];
+        d[k] = x & ~P2_LIT;
     }
     const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
-    const bool may_underflow = g0 < (uint32_t) P2_SBIAS;                           /* only a unit's first 4 MiB can reach before the unit */
+    const uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
-        if (k < n) {
-            if (x & 0x80000000u) v = lits[x & 0x7FFFFFFFu];
-            else if (may_underflow && (int64_t) g0 + (int64_t) x < (int64_t) P2_SBIAS) v = 0;   /* before the unit's first byte: zero */
-            else v = obase[x];
-        }
+        if (k < n && x >= ulim) v = obase[x];
         w[k >> 2] |= v << (8 * (k & 3));
     }
 }
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-__device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, const uint8_t *lits,
-                                                 uint32_t size, uint8_t *unit_out, uint32_t g0,
+__device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
+    int r_lo = 0;                                              /* first window record ending beyond the chunk start */
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
         if (!loaded || (c + P2_CHUNK > wcover && wcover < size)) {
-            if (loaded) wbase += (uint32_t) p2_search(wa, wb, c);
+            wbase += (uint32_t) r_lo; r_lo = 0;
             __syncwarp();
             for (int j = lane; j < P2_WIN; j += 32) {
                 uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec;      /* nrec = the sentinel */
@@ -162,14 +151,15 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         }
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
-        const int r_lo = p2_search(wa, wb, c);                 /* uniform: first record reaching into the chunk */
         if (lane == 0) longq[0] = 0;
+        p2_pass_a_literals(q0, c, src);
         __syncwarp();
-        p2_pass_a_records(lane, r_lo, c, cend, wa, wb, src, longq);
+        int nlo = p2_pass_a_records(lane, r_lo, c, cend, wa, wb, src, longq);
+        r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);            /* also orders the descriptor stores (it is a warp sync) */
         __syncwarp();
         p2_pass_a_long(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b(q0, c, size, src, lits, unit_out, g0, w);
+        p2_pass_b(q0, c, size, src, unit_out, g0, w);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <type_traits>
 
 #include "../../libmspack_b200/csrc/msgpu_core.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_mszip.cuh"
@@ -19,24 +20,26 @@
 #include "../../libmspack_b200/csrc/msgpu_p1_qtm.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
-/* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks) */
-static void emul_p2_frame(const MsRec *recs, uint32_t nrec, const uint8_t *lits, uint32_t size, uint8_t *unit_out, uint32_t g0) {
+/* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
+static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0) {
     std::vector<uint32_t> wa(P2_WIN), wb(P2_WIN);
-    uint32_t wbase = 0, wcover = 0; bool loaded = false;
+    uint32_t wbase = 0, wcover = 0; bool loaded = false; int r_lo = 0;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
         if (!loaded || (c + P2_CHUNK > wcover && wcover < size)) {
-            if (loaded) wbase += (uint32_t) p2_search(wa.data(), wb.data(), c);
+            wbase += (uint32_t) r_lo; r_lo = 0;
             for (int j = 0; j < P2_WIN; j++) { uint32_t r = wbase + (uint32_t) j; if (r > nrec) r = nrec; wa[j] = recs[r].a; wb[j] = recs[r].b; }
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
         uint32_t w[32][4]; uint32_t src[P2_SRC_WORDS], longq[P2_LONG_MAX + 1];
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
-        const int r_lo = p2_search(wa.data(), wb.data(), c);
         longq[0] = 0;
-        for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;     /* a position no record covers would show up as garbage */
-        for (int lane = 0; lane < 32; lane++) p2_pass_a_records(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq);
+        for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;
+        for (int lane = 0; lane < 32; lane++) p2_pass_a_literals(c + 16u * lane, c, src);
+        int nlo = P2_WIN;
+        for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
+        r_lo = nlo;
         for (int lane = 0; lane < 32; lane++) p2_pass_a_long(lane, c, cend, wa.data(), wb.data(), src, longq);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, lits, unit_out, g0, w[lane]);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, unit_out, g0, w[lane]);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
@@ -73,7 +76,6 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     const int F = frames_per_round > 0 ? frames_per_round : 1;
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
-    std::vector<uint8_t> lits((size_t) F * MS_LITCAP + 16);
     std::vector<MsFrameInfo> finfo(F);
     MsUnitState st; memset(&st, 0, sizeof(st));
     uint8_t *unit_out = out_base + u->out_off;
@@ -81,7 +83,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     std::vector<int32_t> e8info(nframes_total + 2, 0);
     auto resolve = [&]() {
         for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
-            emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, lits.data() + (size_t) f * MS_LITCAP, finfo[f].size, unit_out, finfo[f].g0);
+            emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0);
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP && !getenv("MSGPU_EMUL_LUT")) {               /* table-free canonical lanes (the default kernels) */
@@ -89,7 +91,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F);
             emul_run(t); t.end(st); resolve();
         }
         free(sh); free(aux);
@@ -99,19 +101,24 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F);
+            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F);
             emul_run(t); t.end(st); resolve();
         }
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_LZX && !getenv("MSGPU_EMUL_LUT")) {          /* table-free canonical lanes (the default kernels) */
-        typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32> TH;
+        typedef LzxSharedC<1, 32> SH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
-        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
-            emul_run(t); t.end(st); resolve();
-        }
+        auto run = [&](auto *tag) {
+            typedef typename std::remove_pointer<decltype(tag)>::type TH;
+            for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+                TH t; t.bind(sh, 0, aux, 0);
+                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F);
+                emul_run(t); t.end(st); resolve();
+            }
+        };
+        if (getenv("MSGPU_EMUL_AHEAD")) run((LzxLaneC<1, 32, 1> *) nullptr);       /* look-ahead step (MSGPU_LZX_VARIANT=18) */
+        else run((LzxLaneC<1, 32, 0> *) nullptr);
         for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
             uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
             if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) start, e8info[f]);
@@ -123,7 +130,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), e8info.data(), F);
+            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F);
             emul_run(t); t.end(st); resolve();
         }
         for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
@@ -137,7 +144,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0);
-            t.begin(u, in_base, st, recs.data(), lits.data(), finfo.data(), F, save);
+            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
             emul_run(t); t.end(st); resolve();
         }
         free(sh); free(save);

@@ -79,3 +79,22 @@ def test_device_logic_on_corrupt_streams(emul, oracle_ref):
         for lut in (False, True):
             o2, s2 = emul(b.units, comp, b.out_bytes, 1, lut)
             assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec} lut={lut}")
+
+
+def _shifted(b, shift):
+    """The same batch with every unit's input moved `shift` bytes (unit inputs no longer 4-byte aligned)."""
+    comp = np.concatenate([np.zeros(shift, np.uint8), b.comp])
+    units = b.units.copy()
+    units["in_off"] += np.uint64(shift)
+    return units, comp
+
+
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_device_logic_unaligned_input(emul, oracle_ref, shift):
+    """Unit inputs at any byte offset: the word loads of the bit readers fall back to byte loads."""
+    for codec, kw in ((CODEC_LZX, dict(block_mode=4, split=2)), (CODEC_MSZIP, dict(data="random", unit_bytes=40000)), (CODEC_QUANTUM, dict())):
+        b = gen.make_batch(codec, 12, **kw)
+        units, comp = _shifted(b, shift)
+        o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
+        o2, s2 = emul(units, comp, b.out_bytes, 1, False)
+        assert_same(units, o1, s1, o2, s2, f"unaligned {codec} shift {shift}")

@@ -103,6 +103,17 @@ def test_corrupt_streams_same_error_class(decoder, oracle_ref):
         assert_same(b.units, out_o, st_o, out_g, st_g, f"corrupt codec {codec}")
 
 
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_unaligned_input(decoder, oracle_ref, shift):
+    """Unit inputs at any byte offset (CFDATA payloads inside a cabinet are not aligned)."""
+    for codec, kw in ((CODEC_LZX, dict(block_mode=4, split=2)), (CODEC_LZX, dict(block_mode=3)), (CODEC_MSZIP, dict(data="random", unit_bytes=40000)),
+                      (CODEC_MSZIP, dict()), (CODEC_QUANTUM, dict())):
+        b = gen.make_batch(codec, 64, **kw)
+        b.comp = np.concatenate([np.zeros(shift, np.uint8), b.comp])
+        b.units["in_off"] += np.uint64(shift)
+        _check_batch(decoder, oracle_ref, b, f"unaligned {codec} {kw} shift {shift}")
+
+
 def test_full_size_lzx_properties(decoder):
     """BASELINE config 3 at a quarter of full size (16 384 LZX wb21 units, 512 MiB): round trip against the
     generator's raw data - the size-independent property decode(encode(x)) == x; bench.py checks the
