@@ -18,9 +18,7 @@
 
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
-#include "msgpu_p1_mszip_c.cuh"
 #include "msgpu_p1_lzx.cuh"
-#include "msgpu_p1_lzx_c.cuh"
 #include "msgpu_p1_qtm.cuh"
 #include "msgpu_p2.cuh"
 
@@ -50,27 +48,8 @@ __device__ __forceinline__ void p1_run(Lane &t)
     }
 }
 
-template <int NT, int LROOT, int DROOT, int LCACHE>
-__global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;      /* index into the wave's MSZIP list; `first` is a multiple of 32 */
-    const bool valid = ti < count;
-    uint32_t slot = valid ? order[ti] : 0;
-    ZipLane<NT, LROOT, DROOT, LCACHE> t; t.phase = PH_IDLE;
-    MsUnitState st;
-    if (valid) {
-        t.bind(reinterpret_cast<ZipShared<NT, LROOT, DROOT, LCACHE> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
-        st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
-                a.finfo + (size_t) slot * a.F, a.F);
-    }
-    p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
-}
-
 template <int NT, int HEADN>
-__global__ void __launch_bounds__(NT) k_p1_mszip_c(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
+__global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
@@ -88,35 +67,15 @@ __global__ void __launch_bounds__(NT) k_p1_mszip_c(WaveArgs a, const uint32_t *o
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
+template <int NT, int HEADN>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
-                                               int32_t *e8info, const uint32_t *e8base)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
-    const bool valid = ti < count;
-    uint32_t slot = valid ? order[ti] : 0;
-    LzxLane<NT, MROOT, LROOT, LCACHE, LITB> t; t.phase = PH_IDLE;
-    MsUnitState st;
-    if (valid) {
-        t.bind(reinterpret_cast<LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
-        st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
-                a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
-    }
-    p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
-}
-
-template <int NT, int HEADN, int MODE>
-__global__ void __launch_bounds__(NT) k_p1_lzx_c(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN, MODE> t; t.phase = PH_IDLE;
+    LzxLaneC<NT, HEADN> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<LzxSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
@@ -195,17 +154,10 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 }
 
 /* ------------------------------------------------------------------------------------------ host side */
-/* MSZIP P1 variants (threads per CTA, literal/length LUT bits, distance LUT bits, long-symbol cache entries);
- * MSGPU_ZIP_VARIANT picks one (default 0) */
-#define ZIP_VARIANTS(X) X(0, 192, 8, 7, 96) X(1, 128, 9, 8, 48) X(2, 128, 9, 8, 120)
-/* table-free canonical MSZIP lanes (id, threads per CTA, shared-memory head entries) */
-#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 256, 64)
-/* LZX P1 variants (threads per CTA, main LUT bits, length LUT bits, long-symbol cache entries, literals per step);
- * all are sized to fill the 227 KiB of shared memory of one SM.  MSGPU_LZX_VARIANT picks one (default 0). */
-#define LZX_VARIANTS(X) X(0, 192, 8, 5, 96, 1) X(1, 128, 9, 6, 184, 1) X(2, 128, 9, 6, 48, 1) X(3, 224, 8, 5, 32, 1)
-/* table-free canonical LZX lanes (id, threads per CTA, shared-memory head entries) */
-/* (id, threads per CTA, shared-memory head entries, step mode: 0 plain, 1 look-ahead) */
-#define LZXC_VARIANTS(X) X(10, 512, 32, 0) X(11, 448, 48, 0) X(12, 384, 64, 0) X(18, 448, 48, 1)
+/* P1 kernel shapes (id, threads per CTA, shared-memory head entries); MSGPU_ZIP_VARIANT / MSGPU_LZX_VARIANT pick one.
+ * 448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident wave. */
+#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64)
+#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64)
 #define QTM_NT 160
 
 struct DevBuf {
@@ -271,17 +223,11 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
-#define SETATTRZ(id, nt, lr, dr, lc) cudaFuncSetAttribute(k_p1_mszip<nt, lr, dr, lc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipShared<nt, lr, dr, lc>));
-    ZIP_VARIANTS(SETATTRZ)
-#undef SETATTRZ
-#define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip_c<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
+#define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
     ZIPC_VARIANTS(SETATTRZC)
 #undef SETATTRZC
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 11; }
-#define SETATTR(id, nt, mr, lr, lc, lb) cudaFuncSetAttribute(k_p1_lzx<nt, mr, lr, lc, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxShared<nt, mr, lr, lc, lb>));
-    LZX_VARIANTS(SETATTR)
-#undef SETATTR
-#define SETATTRC(id, nt, hn, md) cudaFuncSetAttribute(k_p1_lzx_c<nt, hn, md>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
+#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 11; }
@@ -365,15 +311,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
     uint32_t lzx_nt = 128, zip_nt = 128;
-#define PICKNT(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
-    LZX_VARIANTS(PICKNT)
-#undef PICKNT
-#define PICKNTC(id, nt, hn, md) if (ctx->lzx_variant == id) lzx_nt = nt;
+#define PICKNTC(id, nt, hn) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
-#define PICKNTZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) zip_nt = nt;
-    ZIP_VARIANTS(PICKNTZ)
-#undef PICKNTZ
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
@@ -482,20 +422,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         WaveArgs w = a; w.sub = (int) sub;
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
             mark(0, st);
-#define LAUNCHZ(id, nt, lr, dr, lc) if (ctx->zip_variant == id) k_p1_mszip<nt, lr, dr, lc><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipShared<nt, lr, dr, lc>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            ZIP_VARIANTS(LAUNCHZ)
-#undef LAUNCHZ
-#define LAUNCHZC(id, nt, hn) if (ctx->zip_variant == id) k_p1_mszip_c<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+#define LAUNCHZC(id, nt, hn) if (ctx->zip_variant == id) k_p1_mszip<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             ZIPC_VARIANTS(LAUNCHZC)
 #undef LAUNCHZC
             mark(0, st); mark(1, st);
             k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
-#define LAUNCH(id, nt, mr, lr, lc, lb) if (ctx->lzx_variant == id) k_p1_lzx<nt, mr, lr, lc, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxShared<nt, mr, lr, lc, lb>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
-            LZX_VARIANTS(LAUNCH)
-#undef LAUNCH
-#define LAUNCHC(id, nt, hn, md) if (ctx->lzx_variant == id) k_p1_lzx_c<nt, hn, md><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCHC(id, nt, hn) if (ctx->lzx_variant == id) k_p1_lzx<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZXC_VARIANTS(LAUNCHC)
 #undef LAUNCHC
             mark(0, st); mark(1, st);

@@ -32,7 +32,9 @@
 #define MS_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
 #define MS_SYNCWARP() __syncwarp()
 #define MS_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define MS_STORE4(p, a, b, c, d) (*reinterpret_cast<uint4 *>(p) = make_uint4((a), (b), (c), (d)))      /* p 16-byte aligned */
 #else
+#define MS_STORE4(p, a, b, c, d) do { uint32_t *p_ = reinterpret_cast<uint32_t *>(p); p_[0] = (a); p_[1] = (b); p_[2] = (c); p_[3] = (d); } while (0)
 #define MS_D static inline
 #define MS_M inline
 #define MS_DN static
@@ -183,128 +185,32 @@ MS_D void qtm_refill(MsBits &b) {
 }
 
 /* =============================================================================================
- * Canonical Huffman tables.
+ * Canonical Huffman decoding without decode tables.
  *
- * LUT (shared memory, one per thread, interleaved: entry e of thread t at lut[e * NT + t]):
- *     u16 = sym << 4 | len   for codes of len <= ROOT,   0 for the prefix of a longer code.
- * Longer codes take the slow path: per-length limit[] / offs[] and the symbols in canonical order
- * (sorted[]) live in global scratch, interleaved by lane so that the warp's accesses coalesce.
+ * A per-lane decode LUT costs ~1 KB of shared memory per lane, which caps a B200 SM at ~6 warps and leaves the entropy
+ * kernels latency bound (the first iterations of this code worked that way).  A canonical code needs no table at all to
+ * find a code's LENGTH: with limit[l] = left-aligned exclusive upper bound of the l-bit codes,
+ *     len = 1 + #{ l in 1..15 : v16 >= limit[l] }          (limit[] is non-decreasing: a 4-step binary search)
+ * against fifteen values kept in REGISTERS.  The symbol is then
+ *     sorted[offs[len] + ((v16 - limit[len-1]) >> (16 - len))]:
+ * a 17-entry base/offset table in shared memory (64 B per lane), the first HEADN symbols of the canonical order (the
+ * shortest = most frequent codes) in shared memory, the rest in lane-interleaved global scratch (interleaved so that
+ * the warp's accesses share sectors).  ~0.4 KB per lane -> 14 warps per SM.
  *
- * make_decode_table's acceptance rule is restated (readhuff.h:83-176): ok iff the codes no longer
- * than the reference's TABLEBITS fill the table exactly (longer codes are then unreachable and are
- * dropped), or else all codes <= 16 bits have Kraft sum exactly 1.  Lengths above 16 (possible in
- * LZX, lzxd.c:169-171) never take part.
+ * make_decode_table's acceptance rule is restated (readhuff.h:83-176): ok iff the codes no longer than the
+ * reference's TABLEBITS fill the table exactly (longer codes are then unreachable and are dropped), or else all codes
+ * <= 16 bits have Kraft sum exactly 1.  Lengths above 16 (possible in LZX, lzxd.c:169-171) never take part.
  * ============================================================================================= */
 struct MsHuffAux {          /* pointers already offset by lane; stride MS_WARP elements */
-    uint32_t *limit;        /* limit[l], l = 0..16 : exclusive upper bound of l-bit codes, left-aligned to 16 bits */
-    uint16_t *offs;         /* offs[l]  : index in sorted[] of the first l-bit symbol */
+    uint32_t *limit;        /* (unused by the kernels; kept so the scratch layout stays self-describing) */
+    uint16_t *offs;
     uint16_t *sorted;       /* symbols in canonical order */
 };
-
-/* Build.  lens(i) gives the code length of symbol i (functor); cnt is a 17-entry u16 scratch
- * array in shared memory for this thread with stride cstride.  Returns 0 on success. */
-template <int ROOT, bool LSB, int NT, class LensFn>
-MS_D int ms_huff_build(LensFn lens, int nsyms, int ref_tablebits, uint16_t *lut, const MsHuffAux &aux,
-                       uint16_t *cnt, int cstride, int *maxlen_out, uint16_t *lcache = nullptr, uint32_t lcache_n = 0)
-{
-#pragma unroll 1
-    for (int l = 0; l <= 16; l++) cnt[l * cstride] = 0;
-#pragma unroll 1
-    for (int s = 0; s < nsyms; s++) { uint32_t l = lens(s); if (l >= 1 && l <= 16) cnt[l * cstride]++; }
-    uint32_t sum_short = 0, sum_all = 0;
-#pragma unroll 1
-    for (int l = 1; l <= 16; l++) { sum_all += (uint32_t) cnt[l * cstride] << (16 - l); if (l <= ref_tablebits) sum_short = sum_all; }
-    int maxlen = 16;
-    if (sum_short > 65536u) return 1;
-    if (sum_short == 65536u) maxlen = ref_tablebits;
-    else if (sum_all != 65536u) return 1;
-    *maxlen_out = maxlen;
-    uint32_t lim = 0, off = 0;
-    aux.limit[0] = 0;
-#pragma unroll 1
-    for (int l = 1; l <= 16; l++) {
-        uint32_t c = (l <= maxlen) ? cnt[l * cstride] : 0;
-        aux.offs[l * MS_WARP] = (uint16_t) off;
-        cnt[l * cstride] = (uint16_t) off;                  /* becomes the running index of the next l-bit symbol */
-        lim += c << (16 - l); aux.limit[l * MS_WARP] = lim; off += c;
-    }
-    const uint32_t first_long = (ROOT < 16) ? aux.offs[(ROOT + 1) * MS_WARP] : 0;
-#pragma unroll 1
-    for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
-#pragma unroll 1
-    for (int s = 0; s < nsyms; s++) {
-        int l = (int) lens(s);
-        if (l < 1 || l > maxlen) continue;
-        uint32_t k = cnt[l * cstride]; cnt[l * cstride] = (uint16_t) (k + 1);
-        aux.sorted[k * MS_WARP] = (uint16_t) s;
-        if (l > ROOT) {                                     /* the first lcache_n long-code symbols also go to shared memory */
-            uint32_t rel = k - first_long;
-            if (rel < lcache_n) lcache[rel * NT] = (uint16_t) s;
-        }
-        if (l <= ROOT) {
-            uint32_t code = (aux.limit[(l - 1) * MS_WARP] >> (16 - l)) + (k - aux.offs[l * MS_WARP]);   /* l-bit canonical code */
-            uint16_t ent = (uint16_t) ((s << 4) | l);
-            if (LSB) {
-                uint32_t idx = MS_BREV32(code) >> (32 - l);                                            /* first stream bit = code MSB = index bit 0 */
-                for (; idx < (1u << ROOT); idx += (1u << l)) lut[idx * NT] = ent;
-            }
-            else {
-                uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
-                for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = ent;
-            }
-        }
-    }
-    return 0;
-}
-
-/* Codes longer than ROOT: per-length limits and sorted[] offsets held in REGISTERS (the P1 kernels are
- * shared-memory bound at 128 threads per SM, so registers are free), the symbol itself comes from the
- * canonical-order array in global scratch.  v16 = next 16 stream bits, first bit in bit 15. */
-template <int ROOT>
-struct MsHuffLong {
-    uint32_t lim[17 - ROOT];      /* lim[j] = limit[ROOT + j] */
-    uint32_t off[17 - ROOT];      /* off[j] = offs[ROOT + j]  */
-    MS_M void load(const MsHuffAux &aux) {
-#pragma unroll
-        for (int j = 0; j <= 16 - ROOT; j++) { lim[j] = aux.limit[(ROOT + j) * MS_WARP]; off[j] = aux.offs[(ROOT + j) * MS_WARP]; }
-    }
-    MS_M uint32_t decode(uint32_t v16, const MsHuffAux &aux, int *len) const {
-        int l = ROOT + 1; uint32_t base = lim[0], o = off[1];
-#pragma unroll
-        for (int j = 1; j < 16 - ROOT; j++) if (v16 >= lim[j]) { l = ROOT + j + 1; base = lim[j]; o = off[j + 1]; }
-        *len = l;
-        return aux.sorted[(o + ((v16 - base) >> (16 - l))) * MS_WARP];
-    }
-    /* same, with the first cache_n long-code symbols (canonical order: the shortest, most frequent ones) in
-     * shared memory at cache[rel * NT] */
-    template <int NT>
-    MS_M uint32_t decode_cached(uint32_t v16, const MsHuffAux &aux, const uint16_t *cache, uint32_t cache_n, int *len) const {
-        int l = ROOT + 1; uint32_t base = lim[0], o = off[1];
-#pragma unroll
-        for (int j = 1; j < 16 - ROOT; j++) if (v16 >= lim[j]) { l = ROOT + j + 1; base = lim[j]; o = off[j + 1]; }
-        *len = l;
-        uint32_t idx = o + ((v16 - base) >> (16 - l)), rel = idx - off[1];
-        if (rel < cache_n) return cache[rel * NT];
-        return aux.sorted[idx * MS_WARP];
-    }
-};
-
-/* =============================================================================================
- * Table-free canonical decoding ("C" lanes).
- *
- * The LUT lanes above need ~1 KB of shared memory per lane, which caps a B200 SM at ~6 warps and leaves the
- * entropy kernels latency bound.  A canonical code needs no table at all to find a code's LENGTH: with
- * limit[l] = left-aligned upper bound of the l-bit codes,  len = 1 + #{ l in 1..15 : v16 >= limit[l] }
- * - fifteen independent compares against values kept in REGISTERS.  The symbol is then
- * sorted[offs[len] + ((v16 - limit[len-1]) >> (16 - len))]: a 17-entry base/offset table in shared memory
- * (64 B per lane), the first HEADN symbols of the canonical order (the shortest = most frequent codes) in
- * shared memory, the rest in lane-interleaved global scratch.  ~0.4 KB per lane -> 14-16 warps per SM.
- * ============================================================================================= */
 
 /* Build.  bo[l * NT] (l = 1..16) = limit[l-1] >> 1 | offs[l] << 16; limv[l-1] = limit[l]; sorted[k * 32] and
  * head[k * NT] (k < headn) receive the symbols in canonical order; an optional ROOT-bit MSB-first LUT
  * (u16 = sym << 4 | len, 0 = longer code) is filled as well.  Returns 0 iff make_decode_table would succeed
- * (same acceptance rule as ms_huff_build). */
+ */
 template <int ROOT, int NT, class LensFn>
 MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
                         uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
@@ -383,33 +289,69 @@ MS_D uint32_t ms_canon_index(const uint32_t *bo, uint32_t v16, int len) {
  * Record / literal emission (P1 -> P2 intermediate form)
  * ============================================================================================= */
 struct MsEmit {
-    MsRec *rec;             /* this frame's record array */
+    MsRec *rec;             /* this frame's record array (16-byte aligned) */
     uint8_t *out;           /* the frame's first byte in the unit's output buffer: literals are stored in place */
     uint32_t nrec, limit;   /* limit = bytes of this frame that exist in the output buffer */
+    /* Stores of a lane-per-unit kernel never coalesce (32 lanes, 32 different sectors), so their number matters:
+     * literals are gathered per aligned 4-byte word of the frame and leave as one word store (the other bytes of the
+     * word are match positions, which P2 overwrites anyway, or literals still to come ... which is why the word is
+     * flushed only once the frame position has left it); records leave in pairs as one 16-byte store. */
+    uint32_t accw, acc;     /* word index (frame position / 4) being gathered, 0xFFFFFFFF = none; its bytes */
+    uint32_t wlimit;        /* words [0, wlimit) may be stored as words (aligned and inside the frame) */
+    uint32_t pa, pb;        /* first record of an unfinished pair (valid when nrec is odd) */
 };
-MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *out, uint32_t limit) { e.rec = rec; e.out = out; e.nrec = 0; e.limit = limit; }
-/* literal byte at frame position q.  LZX and Quantum never decode past the frame (q < limit by construction); MSZIP
- * blocks can inflate past what the unit asked for, hence the checked flavour. */
-MS_D void emit_literal(MsEmit &e, uint32_t q, uint32_t byte) { e.out[q] = (uint8_t) byte; }
-MS_D void emit_literal_checked(MsEmit &e, uint32_t q, uint32_t byte) { if (q < e.limit) e.out[q] = (uint8_t) byte; }
-/* n raw input bytes in[bytepos .. bytepos+n) to frame positions q.. (stored / uncompressed blocks), clipped to the frame:
- * four bytes per store once the destination is word aligned.  The caller has checked bytepos + n <= in_len. */
+MS_D void emit_begin(MsEmit &e, MsRec *rec, uint8_t *out, uint32_t limit) {
+    e.rec = rec; e.out = out; e.nrec = 0; e.limit = limit; e.accw = 0xFFFFFFFFu; e.acc = 0; e.pa = e.pb = 0;
+    e.wlimit = (reinterpret_cast<uintptr_t>(out) & 3u) == 0 ? limit >> 2 : 0u;
+}
+MS_D void emit_flush_literals(MsEmit &e) {
+    if (e.accw == 0xFFFFFFFFu) return;
+    uint8_t *d = e.out + 4u * e.accw;
+    if (e.accw < e.wlimit) *reinterpret_cast<uint32_t *>(d) = e.acc;
+    else {
+#pragma unroll 1
+        for (uint32_t k = 0; k < 4; k++) if (4u * e.accw + k < e.limit) d[k] = (uint8_t) (e.acc >> (8 * k));
+    }
+    e.accw = 0xFFFFFFFFu;
+}
+/* literal byte at frame position q (positions are emitted in increasing order).  LZX and Quantum never decode past the
+ * frame (q < limit by construction); MSZIP blocks can inflate past what the unit asked for, hence the checked flavour. */
+MS_D void emit_literal(MsEmit &e, uint32_t q, uint32_t byte) {
+    const uint32_t w = q >> 2;
+    if (w != e.accw) { emit_flush_literals(e); e.accw = w; e.acc = 0; }
+    e.acc |= byte << (8 * (q & 3));
+}
+MS_D void emit_literal_checked(MsEmit &e, uint32_t q, uint32_t byte) { if (q < e.limit) emit_literal(e, q, byte); }
+/* n raw input bytes in[bytepos .. bytepos+n) to frame positions q.. (stored / uncompressed blocks), clipped to the frame.
+ * Whole words of the frame are stored directly, the ragged ends go through the literal gatherer (their words may be
+ * shared with literals before / after the run).  The caller has checked bytepos + n <= in_len. */
 MS_D void emit_raw(MsEmit &e, uint32_t q, const uint8_t *in, int32_t bytepos, uint32_t n) {
     if (q >= e.limit) return;
     if (n > e.limit - q) n = e.limit - q;
-    const uint8_t *p = in + bytepos; uint8_t *d = e.out + q;
+    const uint8_t *p = in + bytepos;
 #pragma unroll 1
-    while (n && (reinterpret_cast<uintptr_t>(d) & 3u)) { *d++ = *p++; n--; }
+    for (; n && (q & 3u); n--, q++, p++) emit_literal(e, q, *p);
+    if (n >= 4) {
+        emit_flush_literals(e);
 #pragma unroll 1
-    for (; n >= 4; n -= 4, p += 4, d += 4)
-        *reinterpret_cast<uint32_t *>(d) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+        for (; n >= 4; n -= 4, p += 4, q += 4) {
+            if ((q >> 2) < e.wlimit)
+                *reinterpret_cast<uint32_t *>(e.out + q) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+            else { e.out[q] = p[0]; e.out[q + 1] = p[1]; e.out[q + 2] = p[2]; e.out[q + 3] = p[3]; }
+        }
+    }
 #pragma unroll 1
-    while (n) { *d++ = *p++; n--; }
+    for (; n; n--, q++, p++) emit_literal(e, q, *p);
 }
 /* record: a = pos, b = off | len << 22 */
 MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
-    MsRec r; r.a = pos; r.b = off | (len << 22); e.rec[e.nrec++] = r;
+    const uint32_t a = pos, b = off | (len << 22);
+    if (e.nrec & 1u) MS_STORE4(e.rec + e.nrec - 1, e.pa, e.pb, a, b);
+    else { e.pa = a; e.pb = b; }
+    e.nrec++;
 }
 MS_D void emit_end(MsEmit &e, uint32_t frame_size) {
-    MsRec r; r.a = frame_size; r.b = 0; e.rec[e.nrec] = r;       /* sentinel: pos = size, len = 0 */
+    emit_flush_literals(e);
+    if (e.nrec & 1u) MS_STORE4(e.rec + e.nrec - 1, e.pa, e.pb, frame_size, 0u);
+    else { MsRec r; r.a = frame_size; r.b = 0; e.rec[e.nrec] = r; }              /* sentinel: pos = size, len = 0 */
 }

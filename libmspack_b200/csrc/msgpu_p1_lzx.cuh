@@ -1,8 +1,13 @@
 /* msgpu_p1_lzx.cuh - P1 entropy stage for LZX units: one lane walks one unit's bitstream
- * (lzxd.c:388-771 lzxd_decompress, :138-183 lzxd_read_lens, :257-270 lzxd_reset_state) and emits
- * literal bytes + match records per 32 KiB frame.  Window-relative checks are restated for a
- * linear output buffer: the reference's window_posn is (bytes decoded) mod window_size and its
+ * (lzxd.c:388-771 lzxd_decompress, :138-183 lzxd_read_lens, :257-270 lzxd_reset_state), stores the literal bytes
+ * at their output positions and emits one match record per match, per 32 KiB frame.  Window-relative checks are
+ * restated for a linear output buffer: the reference's window_posn is (bytes decoded) mod window_size and its
  * lzx->offset is the frame's start (see oracle/port/mspack_port.c for the same restatement on the CPU).
+ *
+ * Huffman decoding is table-free ("canonical lanes"): no per-lane decode LUT for the main tree, code lengths come
+ * from 15 register-resident limits, symbols from a small shared-memory head + global scratch (msgpu_core.cuh
+ * "Table-free canonical decoding").  ~0.45 KB of shared memory per lane, so 14 warps per SM; the LUT-based lanes of
+ * the first iterations needed ~1 KB per lane (6 warps per SM) and were 2.4x slower.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -23,24 +28,27 @@
 #define LZX_AUX_OFFS     (LZX_AUX_LIMIT + 4 * 20 * 32 * 4)         /* u16 [4][20][32] */
 #define LZX_AUX_BYTES    (LZX_AUX_OFFS + 4 * 20 * 32 * 2)
 
-/* LCACHE = main-tree symbols with codes longer than MROOT kept in shared memory; LITB = literals per step() */
-template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
-struct LzxShared {
-    uint16_t mlut[(1 << MROOT) * NT];
-    uint16_t lsym[LCACHE * NT];           /* the first LCACHE long-code main symbols in canonical order */
-    uint16_t llut[(1 << LROOT) * NT];     /* LENGTH tree; hosts the pretree LUT while code lengths are being read */
-    uint16_t alut[128 * NT];
+/* HEADN = main-tree symbols (shortest codes first) kept in shared memory */
+template <int NT, int HEADN>
+struct LzxSharedC {
+    uint32_t mbo[17 * NT];                /* main tree: limit[l-1] >> 1 | offs[l] << 16 */
+    uint32_t lbo[17 * NT];                /* LENGTH tree; hosts the pretree while code lengths are being read */
+    uint32_t abo[17 * NT];                /* aligned-offset tree */
+    uint16_t mhead[HEADN * NT];           /* first HEADN main symbols in canonical order */
+    uint16_t llim[16 * NT];               /* LENGTH / pretree limits >> 1 */
+    uint16_t alim[16 * NT];               /* aligned tree limits >> 1 */
+    uint16_t llut[32 * NT];               /* 5-bit LUT of the LENGTH tree */
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int MROOT, int LROOT, int LCACHE, int LITB>
-struct LzxLane {
+template <int NT, int HEADN>
+struct LzxLaneC {
     MsBits b;
-    uint16_t *mlut, *lsym, *llut, *alut, *cnt;
+    uint32_t *mbo, *lbo, *abo;
+    uint16_t *mhead, *llim, *alim, *llut, *cnt;
     uint8_t *main_len, *len_len;
-    MsHuffAux ma, la, pa, aa;
-    MsHuffLong<MROOT> ml_long;
-    MsHuffLong<LROOT> ll_long, pl_long;
+    MsHuffAux ma, la, pa, aa;             /* only .sorted is used (global scratch) */
+    uint32_t mlim[15];                    /* main tree limit[1..15], registers */
     uint32_t R0, R1, R2, block_type, block_length, block_remaining, header_read, intel_started, length_empty, aligned_lens;
     int32_t intel_filesize;
     uint32_t window_size, num_offsets, nsyms_eff, bytemode, base;
@@ -51,8 +59,9 @@ struct LzxLane {
     uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
     int f, max_frames;
 
-    MS_M void bind(LzxShared<NT, MROOT, LROOT, LCACHE, LITB> *sh, int tid, uint8_t *aux_warp, int lane) {
-        mlut = sh->mlut + tid; lsym = sh->lsym + tid; llut = sh->llut + tid; alut = sh->alut + tid; cnt = sh->cnt + tid;
+    MS_M void bind(LzxSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
+        mbo = sh->mbo + tid; lbo = sh->lbo + tid; abo = sh->abo + tid; mhead = sh->mhead + tid;
+        llim = sh->llim + tid; alim = sh->alim + tid; llut = sh->llut + tid; cnt = sh->cnt + tid;
         main_len = aux_warp + LZX_AUX_MAINLEN + lane; len_len = aux_warp + LZX_AUX_LENLEN + lane;
         ma.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_MSORT) + lane;
         la.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_LSORT) + lane;
@@ -72,21 +81,24 @@ struct LzxLane {
         for (uint32_t i = 0; i < LZX_LEN_SYMS; i++) len_len[i * 32] = 0;
     }
 
-    /* READ_HUFFSYM, MSB-first; caller guarantees >= 16 buffered bits */
-    template <int ROOT>
-    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, const MsHuffLong<ROOT> &lg) {
-        lzx_check(b, 16);
-        uint32_t e = lut[msb_peek(b, ROOT) * NT];
-        int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = lg.decode(msb_peek(b, 16), aux, &len);
+    /* READ_HUFFSYM for a tree whose limits live in shared memory (pretree, LENGTH slow path, aligned tree) */
+    MS_M uint32_t sym_smem(const uint16_t *lim16, const uint32_t *bo, const uint16_t *sorted, bool careful = true) {
+        if (careful) lzx_check(b, 16);
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len_smem<NT>(lim16, v16);
+        uint32_t idx = ms_canon_index<NT>(bo, v16, len);
         msb_drop(b, len);
-        return sym;
+        return sorted[idx * MS_WARP];
     }
-    MS_M uint32_t aligned_sym() {             /* 7-bit LUT covers every aligned-offset code (3-bit lengths) */
-        lzx_check(b, 16);
-        uint32_t e = alut[msb_peek(b, 7) * NT];
-        msb_drop(b, (int) (e & 15));
-        return e >> 4;
+    MS_M uint32_t length_sym(bool careful) {  /* LENGTH tree: 5-bit LUT, then the canonical path */
+        if (careful) lzx_check(b, 16);
+        uint32_t e = llut[msb_peek(b, 5) * NT];
+        if (e & 15) { msb_drop(b, (int) (e & 15)); return e >> 4; }
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len_smem<NT>(llim, v16);
+        uint32_t idx = ms_canon_index<NT>(lbo, v16, len);
+        msb_drop(b, len);
+        return la.sorted[idx * MS_WARP];
     }
 
     /* raw byte access for uncompressed blocks; READ_IF_NEEDED semantics (readbits.h:182-214) */
@@ -111,7 +123,7 @@ struct LzxLane {
 
     /* lzxd.c:138-183: pretree-delta coded lengths; runs are not clamped to `last` */
     MS_M int read_lens(uint8_t *lens, uint32_t first, uint32_t last) {
-        uint64_t plo = 0; uint32_t phi = 0; int pmax;
+        uint64_t plo = 0; uint32_t phi = 0; uint32_t lv[16];
 #pragma unroll 1
         for (int x = 0; x < 20; x++) {
             lzx_refill(b);
@@ -119,20 +131,21 @@ struct LzxLane {
             if (x < 16) plo |= (uint64_t) y << (4 * x); else phi |= y << (4 * (x - 16));
         }
         if (b.err) return b.err;
-        if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
-                                            20, 6, llut, pa, cnt, NT, &pmax)) return MS_EDECRUNCH;
-        pl_long.load(pa);
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
+                                  20, 6, lbo, cnt, pa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
 #pragma unroll 1
         for (uint32_t x = first; x < last;) {
             lzx_refill(b);
-            int z = (int) huffsym<LROOT>(llut, pa, pl_long);
+            int z = (int) sym_smem(llim, lbo, pa.sorted);
             if (b.err) return b.err;
             if (z == 17) { uint32_t y = lzx_read(b, 4) + 4; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
             else if (z == 18) { uint32_t y = lzx_read(b, 5) + 20; if (b.err) return b.err; while (y--) { lens[x * 32] = 0; x++; } }
             else if (z == 19) {
                 uint32_t y = lzx_read(b, 1) + 4;
                 lzx_refill(b);
-                z = (int) huffsym<LROOT>(llut, pa, pl_long);
+                z = (int) sym_smem(llim, lbo, pa.sorted);
                 if (b.err) return b.err;
                 z = (int) lens[x * 32] - z; if (z < 0) z += 17;
                 while (y--) { lens[x * 32] = (uint8_t) z; x++; }
@@ -143,25 +156,33 @@ struct LzxLane {
     }
 
     MS_M int build_main() {
-        uint8_t *l = main_len; int mmax;
-        if (ms_huff_build<MROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mlut, ma, cnt, NT, &mmax, lsym, LCACHE)) return MS_EDECRUNCH;
-        ml_long.load(ma);
+        uint8_t *l = main_len; uint32_t lv[16];
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted, mhead, HEADN,
+                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) mlim[j] = lv[j];
         return 0;
     }
     MS_M int build_length() {                 /* BUILD_TABLE_MAYBE_EMPTY, lzxd.c:111-125 */
-        uint8_t *l = len_len; int lmax;
+        uint8_t *l = len_len; uint32_t lv[16];
         length_empty = 0;
-        if (ms_huff_build<LROOT, false, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, llut, la, cnt, NT, &lmax)) {
+        if (ms_canon_build<5, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted, (uint16_t *) nullptr, 0, llut, lv)) {
 #pragma unroll 1
             for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
             length_empty = 1;
         }
-        else ll_long.load(la);
+        else {
+#pragma unroll
+            for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
+        }
         return 0;
     }
     MS_M int build_aligned() {
-        uint32_t al = aligned_lens; int amax;
-        return ms_huff_build<7, false, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, alut, aa, cnt, NT, &amax) ? MS_EDECRUNCH : 0;
+        uint32_t al = aligned_lens; uint32_t lv[16];
+        if (ms_canon_build<0, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, abo, cnt, aa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) alim[j * NT] = (uint16_t) (lv[j] >> 1);
+        return 0;
     }
 
     /* lzxd.c:465-523: read a block header.  Returns 0 or an MSPACK_ERR_* */
@@ -285,42 +306,42 @@ struct LzxLane {
         }
     }
 
-    /* main-tree symbol: 9-bit LUT, then the shared-memory cache of long-code symbols, then global scratch */
-    MS_M uint32_t main_sym() {
-        lzx_check(b, 16);
-        uint32_t e = mlut[msb_peek(b, MROOT) * NT];
-        int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = ml_long.template decode_cached<NT>(msb_peek(b, 16), ma, lsym, LCACHE, &len);
+    /* main-tree symbol: length from the register limits, symbol from the shared-memory head or global scratch */
+    MS_M uint32_t main_sym(bool careful) {
+        if (careful) lzx_check(b, 16);
+        uint32_t v16 = msb_peek(b, 16);
+        int len = ms_canon_len(mlim, v16);
+        uint32_t idx = ms_canon_index<NT>(mbo, v16, len);
         msb_drop(b, len);
-        return sym;
+        return idx < (uint32_t) HEADN ? (uint32_t) mhead[idx * NT] : (uint32_t) ma.sorted[idx * MS_WARP];
     }
 
-    /* the hot step (lzxd.c:538-651): up to LITB literals, or one match with its length / offset
+    /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset
      * fields.  Batching literals keeps the lanes that are inside a literal run busy while the others
      * handle a match, which is the longer path. */
     MS_M void step() {
-        uint32_t sym;
-#pragma unroll 1
-        for (int rep = 0;; ) {
-            lzx_refill(b);
-            sym = main_sym();
-            if (sym >= 256) break;
-            emit_literal(em, q, sym); q++; this_run--;
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            if (this_run <= 0) { phase = PH_BLOCK; return; }
-            if (++rep == LITB) return;
-        }
-        {
+        /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
+         * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
+        if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_plain<true>(); else step_plain<false>();
+    }
+    /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
+    template <bool careful> MS_M void step_plain() {
+        lzx_refill(b);
+        uint32_t sym = main_sym(careful);
+        if (sym < 256) { emit_literal(em, q, sym); q++; this_run--; }
+        else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
             if (ml == 7) {
                 if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
-                ml += huffsym<LROOT>(llut, la, ll_long);
+                ml += length_sym(careful);
             }
             ml += 2;
-            if (slot == 0) off = R0;
-            else if (slot == 1) { off = R1; R1 = R0; R0 = off; }
-            else if (slot == 2) { off = R2; R2 = R0; R0 = off; }
+            if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
+                const uint32_t r0 = R0;
+                off = slot == 0 ? r0 : (slot == 1 ? R1 : R2);
+                R1 = slot == 1 ? r0 : R1; R2 = slot == 2 ? r0 : R2; R0 = off;
+            }
             else {
                 /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
                 uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
@@ -328,30 +349,37 @@ struct LzxLane {
                 off = pbase - 2;
                 lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
-                    if (extra > 3) off += lzx_read(b, (int) extra - 3) << 3;
-                    off += aligned_sym();
+                    if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
+                    off += sym_smem(alim, abo, aa.sorted, careful);
                 }
-                else if (extra) off += lzx_read(b, (int) extra);
+                else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;
             }
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start) */
-            uint32_t G = frame_start_pos + q, wpr = G & (window_size - 1), eff = off;
+            if (careful && b.err) { fail(b.err); return; }
+            if (!resolve_match(ml, off)) return;
+        }
+        if (careful && b.err) { fail(b.err); return; }
+        if (this_run <= 0) phase = PH_BLOCK;
+    }
+    /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
+     * inside the unit during the first lap of the window (every unit up to 2^window_bits bytes never leaves it) */
+    MS_M bool resolve_match(uint32_t ml, uint32_t off) {
+        uint32_t G = frame_start_pos + q, eff = off;
+        if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
+            uint32_t wpr = G & (window_size - 1);
             bool bad = (wpr + ml > window_size);
             if (off > wpr) {
                 bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
                 if (off > window_size) eff = off - window_size;
             }
             if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
-            bad = bad || ((int32_t) ml > this_run);   /* :678-693 every overrun ends in an error */
-            if (MS_UNLIKELY(bad)) { fail(MS_EDECRUNCH); return; }
-            emit_match(em, q, ml, eff);
-            q += ml; this_run -= (int32_t) ml;
+            if (bad) { fail(MS_EDECRUNCH); return false; }
         }
-        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-        if (this_run <= 0) phase = PH_BLOCK;
+        if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return false; }   /* :678-693 every overrun ends in an error */
+        emit_match(em, q, ml, eff);
+        q += ml; this_run -= (int32_t) ml;
+        return true;
     }
-
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int32_t *e8, int nframes) {
         u = unit; recs = r; uout = l; finfo = fi; e8info = e8; max_frames = nframes; f = 0; q = 0; this_run = 0; bytes_todo = 0;

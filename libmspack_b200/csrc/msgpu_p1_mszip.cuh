@@ -1,11 +1,13 @@
 /* msgpu_p1_mszip.cuh - P1 entropy stage for MSZIP units: one lane inflates one unit's "CK" blocks
- * (mszipd.c:154-316 inflate, :91-151 zip_read_lens, :377-460 mszipd_decompress) into literal bytes +
- * match records.  Each CK block (<= 32 KiB of output) is one "frame" of the intermediate form.
+ * (mszipd.c:154-316 inflate, :91-151 zip_read_lens, :377-460 mszipd_decompress), stores the literal bytes at their
+ * output positions and emits one match record per match.  Each CK block (<= 32 KiB of output) is one "frame" of the
+ * intermediate form.
  *
- * The lane is a state machine (phases in msgpu_core.cuh): service() does the rare, divergent work
- * (CK signature scan, deflate block headers, code-length tables, stored blocks, frame bookkeeping);
- * step() decodes ONE literal/length symbol (plus its distance) and is what the warp executes in
- * lockstep.
+ * The lane is a state machine (phases in msgpu_core.cuh): service() does the rare, divergent work (CK signature scan,
+ * deflate block headers, code-length tables, stored blocks, frame bookkeeping); step() decodes ONE literal/length
+ * symbol (plus its distance) and is what the warp executes in lockstep.  Huffman decoding is table-free: code lengths
+ * of the literal/length and distance trees come from 2 x 15 register-resident limits, symbols from a small
+ * shared-memory head / global scratch (msgpu_core.cuh "Table-free canonical decoding"); ~0.35 KB of shared memory per lane.
  */
 #pragma once
 #include "msgpu_core.cuh"
@@ -19,34 +21,32 @@
 #define ZIP_AUX_OFFS      (ZIP_AUX_LIMIT + 3 * 20 * 32 * 4) /* u16 [3][20][32] */
 #define ZIP_AUX_BYTES     (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)
 
-#ifndef ZIP_LITBATCH
-#define ZIP_LITBATCH 1
-#endif
-/* ZIP_LCACHE = literal/length symbols with codes longer than LROOT kept in shared memory */
-template <int NT, int LROOT, int DROOT, int ZIP_LCACHE>
-struct ZipShared {
-    uint16_t llut[(1 << LROOT) * NT];
-    uint16_t lsym[ZIP_LCACHE * NT];       /* the first ZIP_LCACHE long-code literal/length symbols in canonical order */
-    uint16_t dlut[(1 << DROOT) * NT];     /* also hosts the 7-bit code-length-code LUT while lengths are read (DROOT >= 7) */
+/* HEADN = literal/length symbols (shortest codes first) kept in shared memory */
+template <int NT, int HEADN>
+struct ZipSharedC {
+    uint32_t lbo[17 * NT];                /* literal/length tree: limit[l-1] >> 1 | offs[l] << 16 */
+    uint32_t dbo[17 * NT];                /* distance tree; hosts the code-length-code tree while lengths are read */
+    uint16_t lhead[HEADN * NT];
+    uint16_t dhead[32 * NT];              /* all distance symbols in canonical order */
+    uint16_t blim[16 * NT];               /* code-length-code tree limits >> 1 */
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int LROOT, int DROOT, int ZIP_LCACHE>
-struct ZipLane {
+template <int NT, int HEADN>
+struct ZipLaneC {
     MsBits b;
-    uint16_t *llut, *lsym, *dlut, *cnt;   /* this lane's column of the shared tables */
+    uint32_t *lbo, *dbo; uint16_t *lhead, *dhead, *blim, *cnt;   /* this lane's columns of the shared tables */
     uint8_t *lens;                        /* aux, stride 32 */
-    MsHuffAux la, da, ba;
-    MsHuffLong<LROOT> ll;
-    MsHuffLong<DROOT> dl;
+    MsHuffAux la, da, ba;                 /* only .sorted is used (global scratch) */
+    uint32_t llim[15], dlim[15];          /* limit[1..15] of the two trees, registers */
     /* unit / launch context */
     const msgpu_unit *u; MsRec *recs; uint8_t *uout; MsFrameInfo *finfo;   /* uout = the unit's output buffer */
     MsEmit em;
     uint32_t phase, q, last_block, produced, frame, done; int32_t status;
     int f, max_frames;
 
-    MS_M void bind(ZipShared<NT, LROOT, DROOT, ZIP_LCACHE> *sh, int tid, uint8_t *aux_warp, int lane) {
-        llut = sh->llut + tid; lsym = sh->lsym + tid; dlut = sh->dlut + tid; cnt = sh->cnt + tid;
+    MS_M void bind(ZipSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
+        lbo = sh->lbo + tid; dbo = sh->dbo + tid; lhead = sh->lhead + tid; dhead = sh->dhead + tid; blim = sh->blim + tid; cnt = sh->cnt + tid;
         lens = aux_warp + ZIP_AUX_LENS + lane;
         la.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_LSORT) + lane;
         da.sorted = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_DSORT) + lane;
@@ -57,16 +57,8 @@ struct ZipLane {
         la.offs = off; da.offs = off + 20 * 32; ba.offs = off + 40 * 32;
     }
 
-    /* READ_HUFFSYM (readhuff.h:39-46) on an LSB-first stream; caller refilled (>= 32 bits) */
-    template <int ROOT>
-    MS_M uint32_t huffsym(const uint16_t *lut, const MsHuffAux &aux, const MsHuffLong<ROOT> &lg) {
-        lsb_check(b, 16);
-        uint32_t e = lut[lsb_peek(b, ROOT) * NT];
-        int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = lg.decode(MS_BREV32((uint32_t) b.bb) >> 16, aux, &len);
-        lsb_drop(b, len);
-        return sym;
-    }
+    /* next 16 stream bits, first bit on top (deflate packs Huffman codes starting at the code's MSB) */
+    MS_M uint32_t v16() const { return MS_BREV32((uint32_t) b.bb) >> 16; }
 
     /* mszipd.c:91-151.  Returns 0 or an MSPACK_ERR_* */
     MS_M int read_lens() {
@@ -80,15 +72,19 @@ struct ZipLane {
 #pragma unroll 1
         for (uint32_t i = 0; i < bl_codes; i++) { lsb_refill(b); bl |= (uint64_t) lsb_read(b, 3) << (3 * order[i]); }
         if (b.err) return b.err;
-        int blmax;
-        if (ms_huff_build<7, true, NT>([&](int s) { return (uint32_t) (bl >> (3 * s)) & 7u; }, 19, 7, dlut, ba, cnt, NT, &blmax)) return MS_EDECRUNCH;
+        uint32_t lv[16];
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (bl >> (3 * s)) & 7u; }, 19, 7, dbo, cnt, ba.sorted, (uint16_t *) nullptr, 0,
+                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) blim[j * NT] = (uint16_t) (lv[j] >> 1);
         uint32_t total = lit_codes + dist_codes, last_code = 0;
 #pragma unroll 1
         for (uint32_t i = 0; i < total;) {
             lsb_refill(b);
             lsb_check(b, 7);                                   /* :117 ENSURE_BITS(7) */
-            uint32_t e = dlut[lsb_peek(b, 7) * NT];
-            uint32_t code = e >> 4; lsb_drop(b, (int) (e & 15));
+            uint32_t v = v16();
+            int cl = ms_canon_len_smem<NT>(blim, v);
+            uint32_t code = ba.sorted[ms_canon_index<NT>(dbo, v, cl) * MS_WARP]; lsb_drop(b, cl);
             if (b.err) return b.err;
             if (code < 16) { lens[i * 32] = (uint8_t) code; last_code = code; i++; }
             else {
@@ -103,9 +99,15 @@ struct ZipLane {
             }
         }
         /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
-        uint8_t *l = lens; int lmax, dmax;
-        if (ms_huff_build<LROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, llut, la, cnt, NT, &lmax, lsym, ZIP_LCACHE)) return MS_EDECRUNCH;
-        if (ms_huff_build<DROOT, true, NT>([&](int s) { return (uint32_t) (s < (int) dist_codes ? l[(lit_codes + s) * 32] : 0); }, 32, 6, dlut, da, cnt, NT, &dmax)) return MS_EDECRUNCH;
+        uint8_t *l = lens;
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
+                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) llim[j] = lv[j];
+        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < (int) dist_codes ? l[(lit_codes + s) * 32] : 0); }, 32, 6, dbo, cnt, da.sorted, dhead, 32,
+                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+        for (int j = 0; j < 15; j++) dlim[j] = lv[j];
         return 0;
     }
 
@@ -146,13 +148,19 @@ struct ZipLane {
         int e = 0;
         if (type == 1) {
             /* fixed codes :212-220 */
-            int lmax, dmax;
-            if (ms_huff_build<LROOT, true, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, llut, la, cnt, NT, &lmax, lsym, ZIP_LCACHE)) e = MS_EDECRUNCH;
-            else if (ms_huff_build<DROOT, true, NT>([](int) { return 5u; }, 32, 6, dlut, da, cnt, NT, &dmax)) e = MS_EDECRUNCH;
+            uint32_t lv[16];
+            if (ms_canon_build<0, NT>([](int s) { return (uint32_t) (s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8))); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
+                                      (uint16_t *) nullptr, lv)) e = MS_EDECRUNCH;
+            else {
+#pragma unroll
+                for (int j = 0; j < 15; j++) llim[j] = lv[j];
+                if (ms_canon_build<0, NT>([](int) { return 5u; }, 32, 6, dbo, cnt, da.sorted, dhead, 32, (uint16_t *) nullptr, lv)) e = MS_EDECRUNCH;
+#pragma unroll
+                for (int j = 0; j < 15; j++) dlim[j] = lv[j];
+            }
         }
         else e = read_lens();
         if (e) { fail(e); return; }
-        ll.load(la); dl.load(da);
         phase = PH_DECODE;
     }
 
@@ -194,50 +202,54 @@ struct ZipLane {
         }
     }
 
-    MS_M uint32_t litlen_sym() {
-        lsb_check(b, 16);
-        uint32_t e = llut[lsb_peek(b, LROOT) * NT];
-        int len = (int) (e & 15); uint32_t sym = e >> 4;
-        if (len == 0) sym = ll.template decode_cached<NT>(MS_BREV32((uint32_t) b.bb) >> 16, la, lsym, ZIP_LCACHE, &len);
+    template <bool careful> MS_M uint32_t litlen_sym() {
+        if (careful) lsb_check(b, 16);
+        uint32_t v = v16();
+        int len = ms_canon_len(llim, v);
+        uint32_t idx = ms_canon_index<NT>(lbo, v, len);
         lsb_drop(b, len);
-        return sym;
+        return idx < (uint32_t) HEADN ? (uint32_t) lhead[idx * NT] : (uint32_t) la.sorted[idx * MS_WARP];
+    }
+    template <bool careful> MS_M uint32_t dist_sym() {
+        if (careful) lsb_check(b, 16);
+        uint32_t v = v16();
+        int len = ms_canon_len(dlim, v);
+        uint32_t idx = ms_canon_index<NT>(dbo, v, len);
+        lsb_drop(b, len);
+        return dhead[(idx & 31u) * NT];
+    }
+    template <bool careful> MS_M uint32_t extra_bits(int n) {
+        if (careful) return lsb_read(b, n);
+        uint32_t v = lsb_peek(b, n); lsb_drop(b, n); return v;
     }
 
-    /* the hot step (mszipd.c:243-300): up to ZIP_LITBATCH literals, or one match (length + distance), or the
-     * end-of-block code */
-    MS_M void step() {
-        uint32_t sym;
-#pragma unroll 1
-        for (int rep = 0;;) {
-            lsb_refill(b);
-            sym = litlen_sym();
-            if (sym >= 256) break;
-            emit_literal_checked(em, q, sym);
-            q++;
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            if (MS_UNLIKELY(q >= 2 * MS_FRAME)) { fail(MS_EDECRUNCH); return; }
-            if (++rep == ZIP_LITBATCH) return;
-        }
-        if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
-
+    /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the end-of-block code.
+     * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
+     * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
+    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_t<true>(); else step_t<false>(); }
+    template <bool careful> MS_M void step_t() {
+        lsb_refill(b);
+        uint32_t sym = litlen_sym<careful>();
+        if (sym < 256) { emit_literal_checked(em, q, sym); q++; }
+        else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
         else {
             uint32_t c = sym - 257, eb, length, dist;
             if (c >= 29) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :255 */
             if (c < 8) { eb = 0; length = c + 3; }                             /* lit_lengths / lit_extrabits, :47-62 */
             else if (c == 28) { eb = 0; length = 258; }
             else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
-            if (eb) length += lsb_read(b, (int) eb);
-            if (b.err) { fail(b.err); return; }
+            if (eb) length += extra_bits<careful>((int) eb);
+            if (careful && b.err) { fail(b.err); return; }
             lsb_refill(b);
-            uint32_t d = huffsym<DROOT>(dlut, da, dl);
+            uint32_t d = dist_sym<careful>();
             if (d >= 30) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :260 */
             if (d < 4) { eb = 0; dist = d + 1; }                               /* dist_offsets / dist_extrabits, :53-68 */
             else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
-            if (eb) dist += lsb_read(b, (int) eb);
+            if (eb) dist += extra_bits<careful>((int) eb);
             if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
             q += length;
         }
-        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (careful && b.err) { fail(b.err); return; }
         if (MS_UNLIKELY(q >= 2 * MS_FRAME)) fail(MS_EDECRUNCH);
     }
 

@@ -10,13 +10,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include <type_traits>
 
 #include "../../libmspack_b200/csrc/msgpu_core.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_mszip.cuh"
-#include "../../libmspack_b200/csrc/msgpu_p1_mszip_c.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_lzx.cuh"
-#include "../../libmspack_b200/csrc/msgpu_p1_lzx_c.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p1_qtm.cuh"
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
@@ -86,7 +83,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
             emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0);
     };
 
-    if (u->codec == MSGPU_CODEC_MSZIP && !getenv("MSGPU_EMUL_LUT")) {               /* table-free canonical lanes (the default kernels) */
+    if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
@@ -96,37 +93,8 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         }
         free(sh); free(aux);
     }
-    else if (u->codec == MSGPU_CODEC_MSZIP) {
-        typedef ZipShared<1, 8, 7, 96> SH; typedef ZipLane<1, 8, 7, 96> TH;
-        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
-        for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F);
-            emul_run(t); t.end(st); resolve();
-        }
-        free(sh); free(aux);
-    }
-    else if (u->codec == MSGPU_CODEC_LZX && !getenv("MSGPU_EMUL_LUT")) {          /* table-free canonical lanes (the default kernels) */
-        typedef LzxSharedC<1, 32> SH;
-        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
-        auto run = [&](auto *tag) {
-            typedef typename std::remove_pointer<decltype(tag)>::type TH;
-            for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-                TH t; t.bind(sh, 0, aux, 0);
-                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F);
-                emul_run(t); t.end(st); resolve();
-            }
-        };
-        if (getenv("MSGPU_EMUL_AHEAD")) run((LzxLaneC<1, 32, 1> *) nullptr);       /* look-ahead step (MSGPU_LZX_VARIANT=18) */
-        else run((LzxLaneC<1, 32, 0> *) nullptr);
-        for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
-            uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
-            if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) start, e8info[f]);
-        }
-        free(sh); free(aux);
-    }
     else if (u->codec == MSGPU_CODEC_LZX) {
-        typedef LzxShared<1, 8, 5, 96, 1> SH; typedef LzxLane<1, 8, 5, 96, 1> TH;
+        typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32> TH;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);

@@ -22,12 +22,7 @@ def emul():
     lib = ctypes.CDLL(so)
     lib.emul_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 
-    def run(units, comp, out_bytes, frames_per_round=1, lut_lanes=False):
-        # two decode engines ship: table-free canonical lanes (default kernels) and LUT lanes (MSGPU_*_VARIANT < 10)
-        if lut_lanes:
-            os.environ["MSGPU_EMUL_LUT"] = "1"
-        else:
-            os.environ.pop("MSGPU_EMUL_LUT", None)
+    def run(units, comp, out_bytes, frames_per_round=1):
         units = np.ascontiguousarray(units)
         comp = np.concatenate([np.ascontiguousarray(comp, dtype=np.uint8), np.zeros(64, np.uint8)])
         out = np.zeros(out_bytes + 64, np.uint8)
@@ -39,10 +34,9 @@ def emul():
 
 @pytest.mark.parametrize("entry", golden_manifest(), ids=lambda e: e["name"])
 @pytest.mark.parametrize("frames_per_round", [1, 2])
-@pytest.mark.parametrize("lut_lanes", [False, True], ids=["canonical", "lut"])
-def test_device_logic_on_golden_vectors(emul, entry, frames_per_round, lut_lanes):
+def test_device_logic_on_golden_vectors(emul, entry, frames_per_round):
     u, comp = golden_unit(entry)
-    out, st = emul(u, comp, entry["out_len"], frames_per_round, lut_lanes)
+    out, st = emul(u, comp, entry["out_len"], frames_per_round)
     assert int(st[0]) == entry["err"]
     if entry["err"] == 0:
         assert hashlib.md5(out.tobytes()).hexdigest() == entry["md5"]
@@ -59,9 +53,8 @@ def test_device_logic_matches_oracle(emul, oracle_ref, codec, kw):
     b = gen.make_batch(codec, 20, **kw)
     o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
     for fpr in (1, 2):
-        for lut in (False, True):
-            o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr, lut)
-            assert_same(b.units, o1, s1, o2, s2, f"emulation {codec} {kw} F={fpr} lut={lut}")
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr)
+        assert_same(b.units, o1, s1, o2, s2, f"emulation {codec} {kw} F={fpr}")
 
 
 def test_device_logic_on_corrupt_streams(emul, oracle_ref):
@@ -76,9 +69,8 @@ def test_device_logic_on_corrupt_streams(emul, oracle_ref):
             else:
                 b.units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
         o1, s1, _ = oracle_ref.decode_batch(b.units, comp, b.out_bytes)
-        for lut in (False, True):
-            o2, s2 = emul(b.units, comp, b.out_bytes, 1, lut)
-            assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec} lut={lut}")
+        o2, s2 = emul(b.units, comp, b.out_bytes, 1)
+        assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec}")
 
 
 def _shifted(b, shift):
@@ -96,5 +88,5 @@ def test_device_logic_unaligned_input(emul, oracle_ref, shift):
         b = gen.make_batch(codec, 12, **kw)
         units, comp = _shifted(b, shift)
         o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
-        o2, s2 = emul(units, comp, b.out_bytes, 1, False)
+        o2, s2 = emul(units, comp, b.out_bytes, 1)
         assert_same(units, o1, s1, o2, s2, f"unaligned {codec} shift {shift}")
