@@ -41,7 +41,7 @@ extern "C" {
 #define MSGPU_ERR_DECRUNCH   11
 
 /* unit flags */
-#define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:422-433 */
+#define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:422-433: reserved, not implemented */
 
 /* One independent compressed unit.  32 bytes, no padding. */
 typedef struct msgpu_unit {
@@ -52,7 +52,10 @@ typedef struct msgpu_unit {
     uint64_t in_off;          /* byte offset of the unit's compressed bytes           */
     uint32_t in_len;          /* compressed byte count                                */
     uint32_t out_len;         /* bytes to produce == X_decompress(state, out_len)     */
-    uint64_t out_off;         /* byte offset of the unit's output; multiple of 16     */
+    uint64_t out_off;         /* byte offset of the unit's output; multiple of 16.  The unit owns
+                               * [out_off, out_off + out_len); the buffer doubles as its sliding window and is
+                               * written in two passes (literals, then matches), so on a unit that FAILS the
+                               * bytes after its last completely decoded frame are unspecified */
 } msgpu_unit;
 
 typedef struct msgpu_ctx msgpu_ctx;

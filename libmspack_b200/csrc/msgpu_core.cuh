@@ -2,14 +2,14 @@
  *
  * Execution model:
  *   P1 "entropy" kernels : ONE THREAD per unit walks the serial bitstream (Huffman / arithmetic
- *        decode) and transcodes it into a byte-aligned intermediate form per 32 KiB frame:
- *        a literal byte stream plus fixed-size match records {pos, len, off}.  32 units advance
- *        in lockstep per warp, so every issued instruction does useful work for 32 streams.
- *        Decode LUTs live in shared memory, interleaved by thread (bank == lane).
- *   P2 "resolve" kernel  : ONE WARP per unit turns records + literals into output bytes,
- *        byte-parallel (each lane owns 16 consecutive output bytes of a 512-byte chunk, finds
- *        their source by binary search over the records and pointer-jumps through in-chunk
- *        dependencies), and writes coalesced 16-byte stores.
+ *        decode); literal bytes are stored at their final positions in the output buffer, every
+ *        match becomes a fixed-size record {pos, len, off} per 32 KiB frame.  32 units advance in
+ *        lockstep per warp, so every issued instruction does useful work for 32 streams.  Per-lane
+ *        tables live in shared memory, interleaved by thread (bank == lane).
+ *   P2 "resolve" kernel  : ONE WARP per unit fills in the match bytes, byte-parallel (each lane owns
+ *        16 consecutive output bytes of a 512-byte chunk; a per-byte source descriptor is built in
+ *        shared memory from the records, in-chunk dependencies are followed by pointer jumping), and
+ *        writes coalesced 16-byte stores.
  *   E8 kernel            : LZX call-translation post-pass (lzxd.c:706-737).
  *
  * The reference's behaviour being restated is cited per function (paths relative to

@@ -32,3 +32,16 @@ if os.environ.get("QB_STAGE"):
         t1.record(stream)
         torch.cuda.synchronize()
         print(f"stage_timing={mode}: outer {t0.elapsed_time(t1):.3f} ms, ctx total {dec.last_kernel_ms():.3f} ms, P1 {dec.stage_ms(0):.3f} P2 {dec.stage_ms(1):.3f} E8 {dec.stage_ms(2):.3f}")
+if os.environ.get("QB_HOST"):
+    # host-buffer path (msgpu_decode_batch_host): pinned buffers, H2D + kernels + D2H; plus the raw copy times for scale
+    h_in = torch.from_numpy(b.comp).pin_memory(); h_out = torch.empty(b.out_bytes, dtype=torch.uint8).pin_memory()
+    h_st = np.zeros(n, np.int32)
+    for it in range(4):
+        t0 = time.perf_counter()
+        dec.decode_host_into(b.units, h_in.data_ptr(), h_in.numel(), h_out.data_ptr(), h_out.numel(), h_st)
+        dt = time.perf_counter() - t0
+        print(f"host path iter {it}: {dt*1e3:.2f} ms = {b.out_bytes/dt/1e9:.1f} GB/s  ok={bool((h_st == 0).all())}")
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+    e0.record(); d_in.copy_(h_in, non_blocking=True); e1.record(); h_out.copy_(d_out, non_blocking=True); e2.record(); torch.cuda.synchronize()
+    print(f"raw copies: H2D {h_in.numel()/1e6:.0f} MB in {e0.elapsed_time(e1):.2f} ms ({h_in.numel()/e0.elapsed_time(e1)/1e6:.1f} GB/s), "
+          f"D2H {h_out.numel()/1e6:.0f} MB in {e1.elapsed_time(e2):.2f} ms ({h_out.numel()/e1.elapsed_time(e2)/1e6:.1f} GB/s)")
