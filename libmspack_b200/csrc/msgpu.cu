@@ -176,8 +176,12 @@ struct DevBuf {
 struct msgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t sub[3] = { nullptr, nullptr, nullptr };   /* sub-waves alternate over these so P1 of one overlaps P2 of another */
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
+    enum { NSUB = 8 };
+    cudaStream_t sub[NSUB] = {};          /* sub-waves alternate over these so P1 of one overlaps P2 of another (device buffers: the
+                                           * first 3; host buffers: all 8, the copies run on cp_in / cp_out) */
+    cudaStream_t cp_in = nullptr, cp_out = nullptr;     /* host-buffer path: H2D and D2H copy queues */
+    cudaEvent_t ev_fork = nullptr, ev_join[NSUB + 2] = {};
+    std::vector<cudaEvent_t> io_evs;      /* host-buffer path: "input of sub-wave k is on the device" / "its output is complete" */
     std::vector<cudaEvent_t> evs;        /* pairs (start, end) per wave, reused */
     size_t ev_used = 0;                  /* events of the most recent batch */
     std::string err;
@@ -214,8 +218,9 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 4096) != cudaSuccess) { delete c; return nullptr; }
-    for (int i = 0; i < 3; i++) {
-        if (cudaStreamCreateWithFlags(&c->sub[i], cudaStreamNonBlocking) != cudaSuccess ||
+    for (int i = 0; i < msgpu_ctx::NSUB + 2; i++) {
+        cudaStream_t *sp = i < msgpu_ctx::NSUB ? &c->sub[i] : (i == msgpu_ctx::NSUB ? &c->cp_in : &c->cp_out);
+        if (cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
     }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
@@ -244,7 +249,11 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
     for (cudaEvent_t e : c->stage_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 3; i++) { if (c->sub[i]) cudaStreamDestroy(c->sub[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    for (cudaEvent_t e : c->io_evs) cudaEventDestroy(e);
+    for (int i = 0; i < msgpu_ctx::NSUB; i++) if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
+    if (c->cp_in) cudaStreamDestroy(c->cp_in);
+    if (c->cp_out) cudaStreamDestroy(c->cp_out);
+    for (int i = 0; i < msgpu_ctx::NSUB + 2; i++) if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -323,11 +332,13 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* 10752 = lcm(96..512 CTA sizes in use) */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     if (h_in && !env) {
-        /* host buffers: cut the wave into ~6 sub-waves so that the H2D copy of one sub-wave, the kernels of another and the
-         * D2H copy of a third overlap (each sub-wave's copies and kernels are ordered on its own stream) */
+        /* host buffers: cut the wave into ~16 sub-waves; their H2D copies queue on one copy stream, their kernels run on
+         * eight compute streams as soon as "their" input has landed, their D2H copies queue on a second copy stream as soon as
+         * "their" output is complete - so the D2H engine, which carries twice the bytes of everything else, starts after one
+         * sub-wave's latency and then never idles */
         const uint32_t nmax0 = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
-        uint32_t want = (nmax0 + 5) / 6;
-        if (want < 4096) want = 4096;
+        uint32_t want = (nmax0 + 15) / 16;
+        if (want < 2048) want = 2048;
         if (want < subsz) subsz = want;
     }
     subsz = (subsz + gran - 1) / gran * gran;
@@ -374,7 +385,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
-    const int NS = (nsub > 1 && !ctx->stage_timing) ? 3 : 1;
+    const bool hostpipe = h_in && h_out && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above */
+    const int NS = (nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : 3) : 1;
+    auto kstream = [&](uint32_t sub) { return NS == 1 ? s : ctx->sub[sub % (uint32_t) NS]; };
+    if (hostpipe) {
+        while (ctx->io_evs.size() < 2 * (size_t) nsub) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->io_evs.push_back(e); }
+        CK(cudaStreamWaitEvent(ctx->cp_in, ctx->ev_fork, 0), "stream wait");
+        CK(cudaStreamWaitEvent(ctx->cp_out, ctx->ev_fork, 0), "stream wait");
+    }
     /* byte range of a sub-wave's units in the input / output buffers (host-buffer path) */
     auto io_range = [&](const std::vector<uint32_t> &v, uint32_t f0, uint32_t f1, bool out, uint64_t &b0, uint64_t &b1) {
         b0 = ~0ull; b1 = 0;
@@ -405,6 +423,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             io_range(*lists[c], f0, f1, true, b0, b1);
             if (b1 > b0) cudaMemcpyAsync(h_out + b0, reinterpret_cast<uint8_t *>(d_out) + b0, b1 - b0, cudaMemcpyDeviceToHost, st);
         }
+    };
+    /* the sub-wave's output is complete on stream st: send it home */
+    auto finish_out = [&](uint32_t sub, cudaStream_t st) -> int {
+        if (!hostpipe) { copy_out(sub, st); return 0; }
+        CK(cudaEventRecord(ctx->io_evs[2 * sub + 1], st), "event");
+        CK(cudaStreamWaitEvent(ctx->cp_out, ctx->io_evs[2 * sub + 1], 0), "stream wait");
+        copy_out(sub, ctx->cp_out);
+        return 0;
     };
     size_t sev_used = ctx->stage_evs[0].size() + ctx->stage_evs[1].size() + ctx->stage_evs[2].size();
     for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
@@ -447,13 +473,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             k_e8<<<(f1 - f0 + 7) / 8, 256, 0, st>>>(a, d_ord_l, f0, f1, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; mark(2, st); }
     };
     for (uint32_t sub = 0; sub < nsub; sub++) {
-        cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
-        copy_in(sub, st);
+        cudaStream_t st = kstream(sub);
+        if (hostpipe) { copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[2 * sub], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(st, ctx->io_evs[2 * sub], 0), "stream wait"); }
+        else copy_in(sub, st);
         for (uint32_t round = 0; round < rounds_planned; round++) {
             if (round + 1 == rounds_planned && any_zip) CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
             launch_round(sub, st);
         }
-        if (!any_zip) { launch_tail(sub, st); copy_out(sub, st); }
+        if (!any_zip) { launch_tail(sub, st); finish_out(sub, st); }
     }
     CK(cudaGetLastError(), "kernel launch");
     if (any_zip) {
@@ -464,7 +491,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             CK(cudaMemcpy(ctx->h_pinned, a.not_done, nsub * 4, cudaMemcpyDeviceToHost), "read counters");
             bool again = false;
             for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
-                cudaStream_t st = NS == 1 ? s : ctx->sub[sub % 3];
+                cudaStream_t st = kstream(sub);
                 again = true;
                 CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
                 launch_round(sub, st);
@@ -472,9 +499,13 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
         }
-        for (uint32_t sub = 0; sub < nsub; sub++) { launch_tail(sub, NS == 1 ? s : ctx->sub[sub % 3]); copy_out(sub, NS == 1 ? s : ctx->sub[sub % 3]); }
+        for (uint32_t sub = 0; sub < nsub; sub++) { launch_tail(sub, kstream(sub)); finish_out(sub, kstream(sub)); }
     }
     if (NS > 1) for (int i = 0; i < NS; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->sub[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[i], 0), "stream wait"); }
+    if (hostpipe) {
+        CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB], 0), "stream wait");
+        CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB + 1], ctx->cp_out), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB + 1], 0), "stream wait");
+    }
     if (d_status) { k_status<<<(n + 255) / 256, 256, 0, s>>>(a.ustate, n, d_status + lo); ctx->launches++; }
     CK(cudaEventRecord(ev1, s), "event");
     ctx->ev_used += 2;

@@ -114,6 +114,19 @@ def test_unaligned_input(decoder, oracle_ref, shift):
         _check_batch(decoder, oracle_ref, b, f"unaligned {codec} {kw} shift {shift}")
 
 
+def test_host_pipeline_many_subwaves(decoder, oracle_ref):
+    """Batches large enough for the host-buffer path to cut them into several sub-waves (copy queues + compute streams,
+    msgpu.cu run_wave): one codec (many small sub-waves) and a mixed batch with multi-block MSZIP units (straggler rounds)."""
+    b = gen.make_batch(CODEC_LZX, 6000, unit_bytes=8192, block_mode=4, split=2)
+    _check_batch(decoder, oracle_ref, b, "host pipeline lzx")
+    parts = [gen.make_batch(CODEC_MSZIP, 11000, unit_bytes=3000), gen.make_batch(CODEC_MSZIP, 200, unit_bytes=70000, first_unit=20000),
+             gen.make_batch(CODEC_LZX, 11000, unit_bytes=3000, first_unit=40000), gen.make_batch(CODEC_QUANTUM, 11000, unit_bytes=2000, first_unit=60000)]
+    m = gen.concat_batches(parts)
+    perm = np.random.default_rng(11).permutation(m.n)
+    m.units = m.units[perm].copy()
+    _check_batch(decoder, oracle_ref, m, "host pipeline mixed")
+
+
 def test_full_size_lzx_properties(decoder):
     """BASELINE config 3 at a quarter of full size (16 384 LZX wb21 units, 512 MiB): round trip against the
     generator's raw data - the size-independent property decode(encode(x)) == x; bench.py checks the
