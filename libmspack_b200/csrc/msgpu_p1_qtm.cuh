@@ -102,13 +102,20 @@ struct QtmLane {
         uint32_t range = ((H - L) & 0xFFFFu) + 1u;
         uint32_t c0 = tot[midx * NT];
         uint32_t symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
+        /* first j with cum[j+1] <= symf, or the last entry (cum[j+1] = cum[j] - g[j]).  Four entries per round: the four
+         * shared-memory loads are independent, so a round costs one load latency instead of four (the kernel is latency
+         * bound: 5 warps per SM).  Entries past the model's end may be read (they lie inside the shared arrays) but are
+         * never selected. */
         uint32_t prev = c0, cur, gj; int j = 0;
 #pragma unroll 1
-        for (;; j++) {                                         /* first j with cum[j+1] <= symf (cum[j+1] = cum[j] - g[j]) */
-            gj = cum[(base + j) * NT];
-            cur = prev - gj;
-            if (j + 1 >= entries || cur <= symf) break;
-            prev = cur;
+        for (;; j += 4) {
+            const uint32_t g0 = cum[(base + j) * NT], g1 = cum[(base + j + 1) * NT], g2 = cum[(base + j + 2) * NT], g3 = cum[(base + j + 3) * NT];
+            const uint32_t c1 = prev - g0, c2 = c1 - g1, c3 = c2 - g2, c4 = c3 - g3;
+            if (j + 1 >= entries || c1 <= symf) { gj = g0; cur = c1; break; }
+            if (j + 2 >= entries || c2 <= symf) { gj = g1; cur = c2; prev = c1; j += 1; break; }
+            if (j + 3 >= entries || c3 <= symf) { gj = g2; cur = c3; prev = c2; j += 2; break; }
+            if (j + 4 >= entries || c4 <= symf) { gj = g3; cur = c4; prev = c3; j += 3; break; }
+            prev = c4;
         }
         uint32_t s = sym[(base + j) * NT];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
