@@ -1,0 +1,274 @@
+/* msgpu_cab.cu - cabinet front end (include/msgpu_cab.h): header scan on the host,
+ * CFDATA framing + checksums on the device, then one msgpu_decode_batch_device() call for all folders.
+ * Written from the format description in the reference's cab.h / cabd.c (cited per function); no reference code is used. */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <new>
+
+#include "../../include/msgpu_cab.h"
+
+/* ---------------------------------------------------------------------------------------------- host: scan */
+struct msgpu_cab_plan {
+    std::vector<msgpu_cab_folder> folders;
+    std::vector<msgpu_cab_block> blocks;
+    std::vector<msgpu_cab_file> files;
+    size_t out_bytes = 0, packed_bytes = 0;
+};
+
+namespace {
+inline uint32_t le16(const uint8_t *p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8); }
+inline uint32_t le32(const uint8_t *p) { return le16(p) | (le16(p + 2) << 16); }
+
+/* cabd_read_string (cabd.c:506-548): a NUL within the next 256 bytes, optionally non-empty.  Returns the new position or 0. */
+size_t read_string(const uint8_t *img, size_t n, size_t pos, bool permit_empty, int *err) {
+    if (pos >= n) { *err = MSGPU_ERR_READ; return 0; }
+    size_t lim = n - pos < 256 ? n - pos : 256, i = 0;
+    while (i < lim && img[pos + i]) i++;
+    if (i == lim || (i == 0 && !permit_empty)) { *err = MSGPU_ERR_DATAFORMAT; return 0; }
+    return pos + i + 1;
+}
+}
+
+extern "C" msgpu_cab_plan *msgpu_cab_scan(const void *image, size_t n, int *err_out)
+{
+    int err_dummy; int &err = err_out ? *err_out : err_dummy;
+    err = 0;
+    const uint8_t *img = reinterpret_cast<const uint8_t *>(image);
+    if (!img) { err = MSGPU_ERR_ARGS; return nullptr; }
+    /* CFHEADER, cab.h:16-26 / cabd.c:342-378 */
+    if (n < 0x24) { err = MSGPU_ERR_READ; return nullptr; }
+    if (le32(img) != 0x4643534Du) { err = MSGPU_ERR_SIGNATURE; return nullptr; }
+    const uint32_t num_folders = le16(img + 0x1A), num_files = le16(img + 0x1C), flags = le16(img + 0x1E);
+    if (num_folders == 0 || num_files == 0) { err = MSGPU_ERR_DATAFORMAT; return nullptr; }
+    size_t pos = 0x24;
+    uint32_t folder_resv = 0, block_resv = 0;
+    if (flags & 0x0004u) {                                                 /* cfheadRESERVE_PRESENT, cabd.c:381-401 */
+        if (pos + 4 > n) { err = MSGPU_ERR_READ; return nullptr; }
+        const uint32_t header_resv = le16(img + pos);
+        folder_resv = img[pos + 2]; block_resv = img[pos + 3];
+        pos += 4 + header_resv;                                            /* seeking past the end is not an error by itself */
+    }
+    if (flags & 0x0001u) {                                                 /* previous cabinet: name, info (cabd.c:409-415) */
+        if (!(pos = read_string(img, n, pos, false, &err))) return nullptr;
+        if (!(pos = read_string(img, n, pos, true, &err))) return nullptr;
+    }
+    if (flags & 0x0002u) {                                                 /* next cabinet (cabd.c:417-423) */
+        if (!(pos = read_string(img, n, pos, false, &err))) return nullptr;
+        if (!(pos = read_string(img, n, pos, true, &err))) return nullptr;
+    }
+    msgpu_cab_plan *plan = new (std::nothrow) msgpu_cab_plan();
+    if (!plan) { err = MSGPU_ERR_NOMEMORY; return nullptr; }
+    try {
+        /* CFFOLDER table, cabd.c:425-453 */
+        std::vector<uint32_t> data_off(num_folders), hdr_blocks(num_folders);
+        for (uint32_t i = 0; i < num_folders; i++) {
+            if (pos + 8 > n) { err = MSGPU_ERR_READ; delete plan; return nullptr; }
+            msgpu_cab_folder f; memset(&f, 0, sizeof(f));
+            data_off[i] = le32(img + pos); hdr_blocks[i] = le16(img + pos + 4);
+            f.comp_type = (uint16_t) le16(img + pos + 6);
+            f.codec = (uint8_t) (f.comp_type & 0x000Fu);                    /* cffoldCOMPTYPE_MASK; 1 MSZIP, 2 Quantum, 3 LZX == MSGPU_CODEC_* */
+            f.window_bits = (uint8_t) ((f.comp_type >> 8) & 0x1Fu);         /* cabd.c:1244,1249 */
+            plan->folders.push_back(f);
+            pos += 8 + folder_resv;
+        }
+        /* CFFILE table, cabd.c:551-634: read from right behind the folders; a bad name or folder index fails the open */
+        std::vector<uint8_t> split(num_folders, 0);
+        for (uint32_t i = 0; i < num_files; i++) {
+            if (pos + 16 > n) { err = MSGPU_ERR_READ; delete plan; return nullptr; }
+            msgpu_cab_file fi;
+            fi.length = le32(img + pos); fi.offset = le32(img + pos + 4);
+            const uint32_t fidx = le16(img + pos + 8);
+            fi.folder = fidx;
+            bool bad_folder = false;
+            if (fidx >= 0xFFFDu) {                                          /* continued from / to another cabinet of a set */
+                if (fidx == 0xFFFEu || fidx == 0xFFFFu) { split[num_folders - 1] = 1; fi.folder = 0xFFFFFFFFu; }
+                if (fidx == 0xFFFDu || fidx == 0xFFFFu) { split[0] = 1; fi.folder = 0xFFFFFFFFu; }
+            }
+            else if (fidx >= num_folders) bad_folder = true;
+            fi.name_off = (uint32_t) (pos + 16);
+            int serr = 0;
+            size_t np = read_string(img, n, pos + 16, false, &serr);
+            if (!np || bad_folder) { err = serr ? serr : MSGPU_ERR_DATAFORMAT; delete plan; return nullptr; }
+            pos = np;
+            plan->files.push_back(fi);
+        }
+        /* CFDATA walk per folder (cabd.c:1362-1418): only the 8-byte headers are touched here */
+        size_t out = 0, packed = 0;
+        for (uint32_t i = 0; i < num_folders; i++) {
+            msgpu_cab_folder &f = plan->folders[i];
+            f.first_block = (uint32_t) plan->blocks.size();
+            f.out_off = out; f.in_off = packed;
+            const bool stored = f.codec == 0, qtm = f.codec == MSGPU_CODEC_QUANTUM;
+            if (f.codec > 3) { f.scan_status = MSGPU_ERR_DATAFORMAT; continue; }           /* cabd.c:1251-1253 */
+            if (split[i]) f.scan_status = MSGPU_ERR_DATAFORMAT;                            /* needs the other cabinets of the set */
+            size_t p = data_off[i];
+            for (uint32_t b = 0; b < hdr_blocks[i]; b++) {
+                if (p + 8 > n) { if (!f.scan_status) { f.scan_status = MSGPU_ERR_READ; f.bad_block = b; } break; }
+                msgpu_cab_block bl; memset(&bl, 0, sizeof(bl));
+                bl.checksum = le32(img + p); bl.comp_len = (uint16_t) le16(img + p + 4); bl.uncomp_len = (uint16_t) le16(img + p + 6);
+                bl.folder = i; bl.flags = (qtm ? 1u : 0u) | (stored ? 2u : 0u);
+                bl.payload_off = p + 8 + block_resv;
+                if (bl.comp_len > MSGPU_CAB_INPUTMAX || bl.uncomp_len > MSGPU_CAB_BLOCKMAX) {     /* cabd.c:1386-1398 */
+                    if (!f.scan_status) { f.scan_status = MSGPU_ERR_DATAFORMAT; f.bad_block = b; }
+                    break;
+                }
+                if (bl.payload_off + bl.comp_len > n) { if (!f.scan_status) { f.scan_status = MSGPU_ERR_READ; f.bad_block = b; } break; }
+                if (bl.uncomp_len == 0) {                                                  /* block continues in the next cabinet, cabd.c:1421-1428 */
+                    if (!f.scan_status) { f.scan_status = MSGPU_ERR_DATAFORMAT; f.bad_block = b; }
+                    break;
+                }
+                bl.dst_off = stored ? f.out_off + f.out_len : f.in_off + f.in_len;
+                f.in_len += (uint64_t) bl.comp_len + (qtm ? 1u : 0u);
+                f.out_len += stored ? bl.comp_len : bl.uncomp_len;          /* a stored block IS its payload (noned_decompress) */
+                plan->blocks.push_back(bl);
+                f.num_blocks++;
+                p = bl.payload_off + bl.comp_len;
+            }
+            if (f.out_len > 0xFFFFFFFFull) { f.scan_status = MSGPU_ERR_DATAFORMAT; f.out_len = 0; }
+            if (!stored) packed += (f.in_len + 15) & ~(uint64_t) 15;
+            out += (f.out_len + 15) & ~(uint64_t) 15;
+        }
+        plan->out_bytes = out; plan->packed_bytes = packed + 16;
+    }
+    catch (const std::bad_alloc &) { err = MSGPU_ERR_NOMEMORY; delete plan; return nullptr; }
+    return plan;
+}
+
+extern "C" void msgpu_cab_free(msgpu_cab_plan *p) { delete p; }
+extern "C" size_t msgpu_cab_num_folders(const msgpu_cab_plan *p) { return p ? p->folders.size() : 0; }
+extern "C" size_t msgpu_cab_num_blocks(const msgpu_cab_plan *p) { return p ? p->blocks.size() : 0; }
+extern "C" size_t msgpu_cab_num_files(const msgpu_cab_plan *p) { return p ? p->files.size() : 0; }
+extern "C" const msgpu_cab_folder *msgpu_cab_folders(const msgpu_cab_plan *p) { return p ? p->folders.data() : nullptr; }
+extern "C" const msgpu_cab_block *msgpu_cab_blocks(const msgpu_cab_plan *p) { return p ? p->blocks.data() : nullptr; }
+extern "C" const msgpu_cab_file *msgpu_cab_files(const msgpu_cab_plan *p) { return p ? p->files.data() : nullptr; }
+extern "C" size_t msgpu_cab_out_bytes(const msgpu_cab_plan *p) { return p ? p->out_bytes : 0; }
+extern "C" size_t msgpu_cab_packed_bytes(const msgpu_cab_plan *p) { return p ? p->packed_bytes : 0; }
+
+/* ---------------------------------------------------------------------------------------------- device: gather */
+/* One warp per CFDATA block: copy the payload to its place in the packed codec input (or, for a stored folder, in the
+ * output), append the Quantum trailer byte (cabd.c:1330-1332) and verify the stored checksum (cabd.c:1412-1419):
+ *   sum = XOR of the payload's little-endian 32-bit words, the 1-3 tail bytes packed as b0<<16 | b1<<8 | b2 (3), b0<<8 | b1 (2),
+ *   b0 (1) (cabd_checksum, cabd.c:1456-1479), then XORed with header bytes 4..7 (cbData | cbUncomp << 16).
+ * ok[block] = 1 unless a non-zero stored checksum disagrees. */
+__global__ void __launch_bounds__(256) k_cab_gather(const uint8_t *__restrict__ image, const msgpu_cab_block *__restrict__ blocks, uint32_t nblocks,
+                                                    uint8_t *packed, uint8_t *out, uint8_t *ok)
+{
+    const uint32_t b = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (b >= nblocks) return;
+    const msgpu_cab_block bl = blocks[b];
+    const uint8_t *src = image + bl.payload_off;
+    uint8_t *dst = ((bl.flags & 2u) ? out : packed) + bl.dst_off;
+    const uint32_t len = bl.comp_len, words = len >> 2;
+    uint32_t sum = 0;
+    for (uint32_t w = lane; w < words; w += 32) {
+        const uint8_t *p = src + 4u * w;
+        const uint32_t v = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+        sum ^= v;
+        uint8_t *d = dst + 4u * w;
+        d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+    }
+    if (lane == 0) {
+        const uint8_t *p = src + 4u * words; uint8_t *d = dst + 4u * words;
+        uint32_t ul = 0;
+        switch (len & 3u) {
+        case 3: ul = ((uint32_t) p[0] << 16) | ((uint32_t) p[1] << 8) | p[2]; d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; break;
+        case 2: ul = ((uint32_t) p[0] << 8) | p[1]; d[0] = p[0]; d[1] = p[1]; break;
+        case 1: ul = p[0]; d[0] = p[0]; break;
+        default: break;
+        }
+        sum ^= ul;
+        if (bl.flags & 1u) dst[len] = 0xFF;
+    }
+    for (int o = 16; o; o >>= 1) sum ^= __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) {
+        sum ^= (uint32_t) bl.comp_len | ((uint32_t) bl.uncomp_len << 16);
+        ok[b] = (bl.checksum == 0 || bl.checksum == sum) ? 1 : 0;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- host: decode */
+namespace {
+struct Bufs {
+    void *image = nullptr, *packed = nullptr, *out = nullptr, *blocks = nullptr, *ok = nullptr, *status = nullptr;
+    cudaStream_t st = nullptr;
+    ~Bufs() {
+        for (void *p : { image, packed, out, blocks, ok, status }) if (p) cudaFree(p);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+}
+#define CKC(call) do { if ((call) != cudaSuccess) return MSGPU_ERR_NOMEMORY; } while (0)
+
+extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan, const void *image, size_t image_bytes,
+                                     void *h_out, size_t out_bytes, int32_t *folder_status)
+{
+    if (!ctx || !plan || !image || (!h_out && plan->out_bytes)) return MSGPU_ERR_ARGS;
+    if (out_bytes < plan->out_bytes) return MSGPU_ERR_ARGS;
+    const size_t nf = plan->folders.size(), nb = plan->blocks.size();
+    std::vector<int32_t> fstat(nf, 0);
+    for (size_t i = 0; i < nf; i++) fstat[i] = plan->folders[i].scan_status;
+    Bufs B;
+    CKC(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&B.image, image_bytes + 16));
+    CKC(cudaMalloc(&B.packed, plan->packed_bytes + 16));
+    CKC(cudaMalloc(&B.out, plan->out_bytes + 16));
+    CKC(cudaMalloc(&B.blocks, (nb + 1) * sizeof(msgpu_cab_block)));
+    CKC(cudaMalloc(&B.ok, nb + 1));
+    CKC(cudaMalloc(&B.status, (nf + 1) * sizeof(int32_t)));
+    CKC(cudaMemcpyAsync(B.image, image, image_bytes, cudaMemcpyHostToDevice, B.st));
+    CKC(cudaMemsetAsync(B.packed, 0, plan->packed_bytes + 16, B.st));
+    std::vector<uint8_t> ok(nb, 1);
+    if (nb) {
+        CKC(cudaMemcpyAsync(B.blocks, plan->blocks.data(), nb * sizeof(msgpu_cab_block), cudaMemcpyHostToDevice, B.st));
+        k_cab_gather<<<(unsigned) ((nb + 7) / 8), 256, 0, B.st>>>(reinterpret_cast<const uint8_t *>(B.image), reinterpret_cast<const msgpu_cab_block *>(B.blocks),
+                                                                  (uint32_t) nb, reinterpret_cast<uint8_t *>(B.packed), reinterpret_cast<uint8_t *>(B.out),
+                                                                  reinterpret_cast<uint8_t *>(B.ok));
+        CKC(cudaGetLastError());
+        CKC(cudaMemcpyAsync(ok.data(), B.ok, nb, cudaMemcpyDeviceToHost, B.st));
+    }
+    CKC(cudaStreamSynchronize(B.st));
+    /* unit table: one unit per codec folder; its input ends in front of the first block the reference would refuse to
+     * hand to the codec (bad checksum, or the block the scan stopped at), so the codec runs exactly as far as the
+     * reference's would and reports MSGPU_ERR_READ when it wants more */
+    std::vector<msgpu_unit> units; std::vector<size_t> unit_folder; std::vector<int32_t> block_err(nf, 0);
+    for (size_t i = 0; i < nf; i++) {
+        const msgpu_cab_folder &f = plan->folders[i];
+        if (f.codec > 3) continue;                                              /* unknown method: scan_status says so */
+        uint64_t in_len = f.in_len;
+        for (uint32_t b = 0; b < f.num_blocks; b++) if (!ok[f.first_block + b]) {
+            block_err[i] = MSGPU_ERR_CHECKSUM;
+            in_len = plan->blocks[f.first_block + b].dst_off - f.in_off;        /* packed bytes in front of the bad block */
+            break;
+        }
+        if (!block_err[i] && f.scan_status) block_err[i] = f.scan_status;       /* the scan stopped in front of its bad block already */
+        if (f.codec == 0) { fstat[i] = block_err[i]; continue; }               /* stored: the gather kernel was the decoder */
+        if (f.out_len == 0) { fstat[i] = block_err[i] ? block_err[i] : MSGPU_ERR_DATAFORMAT; continue; }
+        msgpu_unit u; memset(&u, 0, sizeof(u));
+        u.codec = f.codec; u.window_bits = f.window_bits; u.reset_interval = 0; u.flags = 0;
+        u.in_off = f.in_off; u.in_len = (uint32_t) in_len; u.out_off = f.out_off; u.out_len = (uint32_t) f.out_len;
+        units.push_back(u); unit_folder.push_back(i);
+    }
+    std::vector<int32_t> ustat(units.size(), 0);
+    if (!units.empty()) {
+        int r = msgpu_decode_batch_device(ctx, units.data(), units.size(), B.packed, plan->packed_bytes + 16, B.out, plan->out_bytes + 16,
+                                          reinterpret_cast<int32_t *>(B.status), B.st);
+        if (r) return r;
+        CKC(cudaMemcpyAsync(ustat.data(), B.status, units.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, B.st));
+    }
+    if (plan->out_bytes) CKC(cudaMemcpyAsync(h_out, B.out, plan->out_bytes, cudaMemcpyDeviceToHost, B.st));
+    CKC(cudaStreamSynchronize(B.st));
+    for (size_t k = 0; k < units.size(); k++) {
+        const size_t i = unit_folder[k];
+        int32_t s = ustat[k];
+        /* cabd.c:1198: the codec's MSPACK_ERR_READ is replaced by the reason the input ended - the refused block's error,
+         * or DATAFORMAT when the folder simply has no more blocks (cabd.c:1311-1318) */
+        if (s == MSGPU_ERR_READ) s = block_err[i] ? block_err[i] : MSGPU_ERR_DATAFORMAT;
+        else if (s == 0 && block_err[i]) s = block_err[i];          /* decoded what the good blocks hold; the folder still is not whole */
+        fstat[i] = s;
+    }
+    if (folder_status) for (size_t i = 0; i < nf; i++) folder_status[i] = fstat[i];
+    return 0;
+}

@@ -61,3 +61,46 @@ def parse_cab(data: bytes) -> List[CabFolder]:
             p += csize
         folders.append(f)
     return folders
+
+
+# ------------------------------------------------------------------------------------------------------------
+# A writer, for the cabinet-level tests: single cabinet, no reserved areas.
+
+def cab_checksum(data: bytes, seed: int = 0) -> int:
+    """cabd_checksum (cabd.c:1456-1479): XOR of the little-endian 32-bit words, the 1-3 tail bytes packed
+    b0<<16 | b1<<8 | b2 (3), b0<<8 | b1 (2), b0 (1)."""
+    import numpy as np
+    n = len(data) & ~3
+    s = seed
+    if n:
+        s ^= int(np.bitwise_xor.reduce(np.frombuffer(data[:n], dtype="<u4")))
+    t = data[n:]
+    ul = 0
+    if len(t) == 3:
+        ul = (t[0] << 16) | (t[1] << 8) | t[2]
+    elif len(t) == 2:
+        ul = (t[0] << 8) | t[1]
+    elif len(t) == 1:
+        ul = t[0]
+    return (s ^ ul) & 0xFFFFFFFF
+
+
+def build_cab(folders, with_checksums: bool = True) -> bytes:
+    """folders: list of dicts {comp_type, blocks: [(payload bytes, uncompressed size)], files: [(name, offset, length)]}."""
+    nfiles = sum(len(f["files"]) for f in folders)
+    hdr_len = 0x24 + 8 * len(folders)
+    files_blob = b""
+    for i, f in enumerate(folders):
+        for name, off, length in f["files"]:
+            files_blob += struct.pack("<IIHHHH", length, off, i, 0x2A21, 0x6000, 0x20) + name.encode() + b"\0"
+    data_off = hdr_len + len(files_blob)
+    fold_blob, data_blob = b"", b""
+    for f in folders:
+        fold_blob += struct.pack("<IHH", data_off + len(data_blob), len(f["blocks"]), f["comp_type"])
+        for payload, usize in f["blocks"]:
+            tail = struct.pack("<HH", len(payload), usize)
+            csum = cab_checksum(tail, cab_checksum(payload)) if with_checksums else 0
+            data_blob += struct.pack("<I", csum) + tail + payload
+    total = data_off + len(data_blob)
+    head = struct.pack("<4sIIIIIBBHHHHH", b"MSCF", 0, total, 0, hdr_len, 0, 3, 1, len(folders), nfiles, 0, 0x1234, 0)
+    return head + fold_blob + files_blob + data_blob

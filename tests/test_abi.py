@@ -22,6 +22,18 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in codec.load_library().msgpu_version()
 
 
+def test_library_exports_cabinet_front_end():
+    """include/msgpu_cab.h: every declared entry point is exported; struct layouts match the binding."""
+    from libmspack_b200 import cab, codec
+    lib = ctypes.CDLL(codec.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "msgpu_cab.h")).read()
+    declared = set(re.findall(r"\b(msgpu_cab_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(cab.CAB_SYMBOLS), declared ^ set(cab.CAB_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert (cab.FOLDER_DTYPE.itemsize, cab.BLOCK_DTYPE.itemsize, cab.FILE_DTYPE.itemsize) == (56, 32, 16)
+
+
 def test_unit_descriptor_layout_matches_header():
     from libmspack_b200.units import UNIT_DTYPE
     assert UNIT_DTYPE.itemsize == 32
