@@ -66,7 +66,9 @@ def _expected_folder_status(entry, plan):
             continue
         errs = [r["err"] for r in recs if r["err"]]
         end = max(r["offset"] + r["length"] for r in recs)
-        over = any(r["offset"] + r["length"] > int(plan.folders["num_blocks"][fi]) * 32768 for r in recs)   # cabd.c:1071-1079 file-level check
+        # cabd.c:1071-1079 refuses a file that cannot fit the folder's blocks before decoding anything (a file-level check; when
+        # the scan stopped early, num_blocks is what it found, not the header's count, and the check does not apply)
+        over = int(plan.folders["scan_status"][fi]) == 0 and any(r["offset"] + r["length"] > int(plan.folders["num_blocks"][fi]) * 32768 for r in recs)
         res[fi] = (errs[0] if errs else 0, (end == out_len or bool(errs)) and not over)
     return res
 
