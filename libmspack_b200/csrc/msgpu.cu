@@ -157,7 +157,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 /* P1 kernel shapes (id, threads per CTA, shared-memory head entries); MSGPU_ZIP_VARIANT / MSGPU_LZX_VARIANT pick one.
  * 448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident wave. */
 #define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64)
-#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 64)
+#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 72) X(12, 384, 64) X(13, 448, 48)
 #define QTM_NT 160
 
 struct DevBuf {
