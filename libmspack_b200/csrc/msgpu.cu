@@ -296,13 +296,13 @@ static cudaEvent_t stage_event(msgpu_ctx *c, size_t &used) {
 
 static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_FRAME - 1) / MS_FRAME; }
 
-/* Decode one wave: units[lo, hi) of the host array (already validated). */
 /* Decode one wave: units[lo, hi) of the host array (already validated).
  *
- * The wave is cut into sub-waves of MSGPU_SUBWAVE units (default 148 x 128 = one resident P1 CTA per SM).
- * Sub-wave i runs entirely on internal stream i % 3: P1 (one thread per unit, shared-memory bound, latency
- * bound, IPC ~0.2) of one sub-wave then shares the SMs with P2 (one warp per unit, issue bound) of the
- * previous one, instead of the two kernels running back to back. */
+ * The wave is cut into sub-waves of MSGPU_SUBWAVE units (default 148 x the P1 CTA size = one resident P1 CTA per SM;
+ * the 65 536-unit headline batch is a single sub-wave).  Device buffers: sub-wave i runs entirely on internal stream
+ * i % 3, so P1 (one thread per unit, latency bound) of one sub-wave can share the SMs with P2 (one warp per unit, issue
+ * bound) of another.  Host buffers (h_in / h_out): ~16 sub-waves, copies on two dedicated streams, kernels on eight
+ * (see `hostpipe` below). */
 static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t hi, const void *d_in, void *d_out,
                     int32_t *d_status, cudaStream_t s, const uint8_t *h_in = nullptr, uint8_t *h_out = nullptr)
 {
@@ -326,10 +326,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
-    /* sub-wave size: a multiple of every CTA size in use (32 * 3 * 4 * 7 = 2688 covers 96/128/192/224 threads),
-     * about one resident P1 CTA per SM */
+    /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
+     * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
-    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* 10752 = lcm(96..512 CTA sizes in use) */
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* mixed batches: 10752 = lcm of the 384/448/512-lane CTA shapes */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     if (h_in && !env) {
         /* host buffers: cut the wave into ~16 sub-waves; their H2D copies queue on one copy stream, their kernels run on

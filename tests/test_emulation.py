@@ -22,13 +22,14 @@ def emul():
     lib = ctypes.CDLL(so)
     lib.emul_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 
-    def run(units, comp, out_bytes, frames_per_round=1):
+    def run(units, comp, out_bytes, frames_per_round=1, out_shift=0):
         units = np.ascontiguousarray(units)
         comp = np.concatenate([np.ascontiguousarray(comp, dtype=np.uint8), np.zeros(64, np.uint8)])
-        out = np.zeros(out_bytes + 64, np.uint8)
+        out = np.zeros(out_bytes + 128, np.uint8)
+        base = (-out.ctypes.data) % 16 + out_shift               # 16-byte aligned + the requested misalignment
         st = np.full(len(units), -1, np.int32)
-        lib.emul_decode_batch(units.ctypes.data, len(units), comp.ctypes.data, out.ctypes.data, st.ctypes.data, frames_per_round)
-        return out[:out_bytes], st
+        lib.emul_decode_batch(units.ctypes.data, len(units), comp.ctypes.data, out.ctypes.data + base, st.ctypes.data, frames_per_round)
+        return out[base:base + out_bytes], st
     return run
 
 
@@ -90,3 +91,14 @@ def test_device_logic_unaligned_input(emul, oracle_ref, shift):
         o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
         o2, s2 = emul(units, comp, b.out_bytes, 1)
         assert_same(units, o1, s1, o2, s2, f"unaligned {codec} shift {shift}")
+
+
+@pytest.mark.parametrize("shift", [1, 2])
+def test_device_logic_unaligned_output(emul, oracle_ref, shift):
+    """An output base that is not 4/16-byte aligned: literal words and resolved 16-byte groups fall back to byte stores."""
+    for codec, kw in ((CODEC_LZX, dict(block_mode=4, split=2, unit_bytes=40000)), (CODEC_MSZIP, dict(data="random", unit_bytes=40000)),
+                      (CODEC_MSZIP, dict()), (CODEC_QUANTUM, dict())):
+        b = gen.make_batch(codec, 8, **kw)
+        o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, 1, out_shift=shift)
+        assert_same(b.units, o1, s1, o2, s2, f"unaligned output {codec} shift {shift}")
