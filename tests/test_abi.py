@@ -32,6 +32,12 @@ def test_library_exports_cabinet_front_end():
     for name in declared:
         assert hasattr(lib, name), name
     assert (cab.FOLDER_DTYPE.itemsize, cab.BLOCK_DTYPE.itemsize, cab.FILE_DTYPE.itemsize) == (56, 32, 16)
+    from libmspack_b200 import chm
+    hdr = open(os.path.join(ROOT, "include", "msgpu_chm.h")).read()
+    declared = set(re.findall(r"\b(msgpu_chm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(chm.CHM_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
 
 
 def test_unit_descriptor_layout_matches_header():
