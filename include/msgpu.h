@@ -42,11 +42,17 @@ extern "C" {
 
 /* unit flags */
 #define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:422-433: reserved, not implemented */
+#define MSGPU_FLAG_LZX_DELTA    0x2u  /* lzxd_init(is_delta=1): LZX DELTA stream (lzxd.c:289-296, :441-444, :589-611), window_bits 17..25 */
+#define MSGPU_FLAG_REF_SHIFT    6     /* flags >> 6 = bytes of LZX DELTA reference data (lzxd_set_reference_data, lzxd.c:348-382;
+                                       * <= the window size).  The caller stores them in the OUTPUT buffer directly in front
+                                       * of the unit, at [out_off - n, out_off): the reference preloads them at the end of its
+                                       * window, i.e. logically just before the first output byte */
+#define MSGPU_UNIT_REF_BYTES(u) ((u)->flags >> MSGPU_FLAG_REF_SHIFT)
 
 /* One independent compressed unit.  32 bytes, no padding. */
 typedef struct msgpu_unit {
     uint8_t  codec;           /* MSGPU_CODEC_*                                        */
-    uint8_t  window_bits;     /* LZX 15..21 (lzxd.c:294), Quantum 10..21 (qtmd.c:199) */
+    uint8_t  window_bits;     /* LZX 15..21, LZX DELTA 17..25 (lzxd.c:289-296), Quantum 10..21 (qtmd.c:199) */
     uint16_t reset_interval;  /* LZX: frames between resets, 0 = never (lzxd.c:423)   */
     uint32_t flags;           /* MSGPU_FLAG_*                                         */
     uint64_t in_off;          /* byte offset of the unit's compressed bytes           */

@@ -116,11 +116,15 @@ class BatchDecoder:
             ctypes.c_void_p(d_status.data_ptr()) if d_status is not None else None, sp)
         self._check(rc)
 
-    def decode_host(self, units: np.ndarray, comp: np.ndarray, out_bytes: int):
-        """Host buffers in, host buffers out (H2D + decode + D2H inside the call)."""
+    def decode_host(self, units: np.ndarray, comp: np.ndarray, out_bytes: int, out_init: np.ndarray | None = None):
+        """Host buffers in, host buffers out (H2D + decode + D2H inside the call).
+        out_init: initial contents of the output buffer - LZX DELTA units expect their reference data in front of their
+        output (include/msgpu.h MSGPU_FLAG_REF_SHIFT); the call uploads those bytes."""
         units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
         comp = np.ascontiguousarray(comp, dtype=np.uint8)
         out = np.empty(max(out_bytes, 1), dtype=np.uint8)
+        if out_init is not None:
+            out[:len(out_init)] = out_init
         status = np.full(len(units), -1, dtype=np.int32)
         rc = self.lib.msgpu_decode_batch_host(self.ctx, units.ctypes.data, len(units), comp.ctypes.data, comp.size,
                                               out.ctypes.data, out_bytes, status.ctypes.data)

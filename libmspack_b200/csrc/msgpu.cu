@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT, int HEADN>
+/* DELTA = the instantiation for waves that hold LZX DELTA units (it decodes plain LZX units as well) */
+template <int NT, int HEADN, bool DELTA>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN> t; t.phase = PH_IDLE;
+    LzxLaneC<NT, HEADN, DELTA> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<LzxSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
@@ -107,6 +108,8 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 }
 
 #define P2_WARPS 8
+/* WIDE = the instantiation for waves that hold LZX DELTA units: 26-bit match offsets, reference data in front of the unit */
+template <bool WIDE>
 __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
@@ -117,11 +120,12 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
     if (si >= nslots) return;
     uint32_t slot = slots[si];
     uint8_t *unit_out = a.out_base + a.units[slot].out_off;
+    const uint32_t ref_len = (WIDE && a.units[slot].codec == MSGPU_CODEC_LZX) ? MSGPU_UNIT_REF_BYTES(&a.units[slot]) : 0u;
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (!fi.valid || fi.size == 0) continue;
-        p2_resolve_frame(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
-                         s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp]);
+        p2_resolve_frame<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+                               s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
     }
 }
 
@@ -159,6 +163,8 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 #define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64)
 #define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 72) X(12, 384, 64) X(13, 448, 48)
 #define QTM_NT 160
+#define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
+#define LZXD_HEADN 72
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -232,9 +238,10 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     ZIPC_VARIANTS(SETATTRZC)
 #undef SETATTRZC
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 11; }
-#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
+#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
+    cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 11; }
     cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
     return c;
@@ -308,10 +315,11 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 {
     const uint32_t n = (uint32_t) (hi - lo);
     std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base;
-    uint32_t maxfr = 1, e8total = 0; bool any_zip = false;
+    uint32_t maxfr = 1, e8total = 0; bool any_zip = false, any_delta = false;
     for (uint32_t i = 0; i < n; i++) {
         const msgpu_unit &u = h_units[lo + i];
         ord[u.codec].push_back(i);
+        if (u.codec == MSGPU_CODEC_LZX && ((u.flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(&u))) any_delta = true;
         uint32_t fr = frames_of(u); if (fr > maxfr) maxfr = fr;
         if (u.codec == MSGPU_CODEC_LZX) { e8base.push_back(e8total); e8total += fr ? fr : 1; }
         if (u.codec == MSGPU_CODEC_MSZIP) any_zip = true;
@@ -323,6 +331,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNTC(id, nt, hn) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
+    if (any_delta) lzx_nt = LZXD_NT;
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
@@ -372,6 +381,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     }
     CK(cudaMemsetAsync(ctx->ustate.p, 0, (size_t) n * sizeof(MsUnitState), s), "clear state");
     CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, s), "clear counters");
+    if (any_delta && h_out) {
+        /* host buffers: the reference data of the LZX DELTA units lives in the caller's output buffer, in front of each unit */
+        for (uint32_t i = 0; i < n; i++) {
+            const msgpu_unit &u = h_units[lo + i]; const uint32_t rl = MSGPU_UNIT_REF_BYTES(&u);
+            if (u.codec == MSGPU_CODEC_LZX && rl)
+                CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + u.out_off - rl, h_out + u.out_off - rl, rl, cudaMemcpyHostToDevice, s), "copy reference data");
+        }
+    }
     /* the pageable host vectors above must outlive the async copies */
     CK(cudaStreamSynchronize(s), "sync uploads");
 
@@ -443,6 +460,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         cudaEvent_t e = stage_event(ctx, sev_used);
         if (e) { cudaEventRecord(e, st); ctx->stage_evs[stage].push_back(e); }
     };
+    auto p2_launch = [&](const WaveArgs &w, const uint32_t *list, uint32_t f0, uint32_t f1, cudaStream_t st) {
+        if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
+        else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
+    };
     auto launch_round = [&](uint32_t sub, cudaStream_t st) {
         uint32_t f0 = sub * subsz, f1;
         WaveArgs w = a; w.sub = (int) sub;
@@ -452,19 +473,20 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             ZIPC_VARIANTS(LAUNCHZC)
 #undef LAUNCHZC
             mark(0, st); mark(1, st);
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches += 2; mark(1, st); }
+            p2_launch(w, d_ord_z, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
-#define LAUNCHC(id, nt, hn) if (ctx->lzx_variant == id) k_p1_lzx<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCHC(id, nt, hn) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZXC_VARIANTS(LAUNCHC)
 #undef LAUNCHC
+            if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_l, f0, f1); ctx->launches += 2; mark(1, st); }
+            p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             mark(0, st);
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);
-            k_p2_resolve<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_q, f0, f1); ctx->launches += 2; mark(1, st); }
+            p2_launch(w, d_ord_q, f0, f1, st); ctx->launches += 2; mark(1, st); }
     };
     auto launch_tail = [&](uint32_t sub, cudaStream_t st) {
         uint32_t f0 = sub * subsz, f1;
@@ -540,11 +562,12 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
         if (u.in_off + u.in_len > in_bytes || u.out_off + u.out_len > out_bytes) return fail(ctx, MSGPU_ERR_ARGS, "unit outside the input/output buffer");
         if (u.in_len >= 0x7FFFFFF0u) return fail(ctx, MSGPU_ERR_ARGS, "unit input too large");
         if (u.out_off & 15u) return fail(ctx, MSGPU_ERR_ARGS, "out_off must be a multiple of 16");
+        if (u.codec == MSGPU_CODEC_LZX && MSGPU_UNIT_REF_BYTES(&u) > u.out_off) return fail(ctx, MSGPU_ERR_ARGS, "LZX DELTA reference data must lie in front of the unit inside the output buffer");
     }
     /* wave size from the scratch budget */
     uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
     const int F = maxfr >= 2 ? 2 : 1;
-    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec)) + sizeof(MsUnitState) + 6144;
+    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec)) + sizeof(MsUnitState) + 10240;      /* + the largest per-lane aux share (LZX_AUX_BYTES / 32) */
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();

@@ -350,6 +350,14 @@ MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
     else { e.pa = a; e.pb = b; }
     e.nrec++;
 }
+/* LZX DELTA: offsets up to 2^25 (bits 22.. of the offset travel in a's upper half) and lengths up to a whole frame (cut into
+ * pieces of at most 1023 bytes with the same offset, which copies the same bytes as the one long match) */
+MS_D void emit_match_wide(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
+    const uint32_t hi = (off >> 22) << 16, lo = off & 0x3FFFFFu;
+#pragma unroll 1
+    while (len > 1023u) { emit_match(e, pos | hi, 1023u, lo); pos += 1023u; len -= 1023u; }
+    emit_match(e, pos | hi, len, lo);
+}
 MS_D void emit_end(MsEmit &e, uint32_t frame_size) {
     emit_flush_literals(e);
     if (e.nrec & 1u) MS_STORE4(e.rec + e.nrec - 1, e.pa, e.pb, frame_size, 0u);

@@ -16,11 +16,11 @@
 #define LZX_MAIN_ALLOC (LZX_MAIN_MAX + 64)    /* + LZX_LENTABLE_SAFETY, lzx.h:44 */
 #define LZX_LEN_SYMS   250                    /* LZX_LENGTH_MAXSYMBOLS */
 #define LZX_LEN_ALLOC  320
-#define LZX_MSORT_N    768                    /* coded main symbols <= 256 + 400 + 51 for window_bits <= 21 */
+#define LZX_MSORT_N    2592                   /* coded main symbols <= 2576 (window_bits 25, LZX DELTA) */
 
 #define LZX_AUX_MAINLEN  0                                         /* u8  [2640][32] */
 #define LZX_AUX_LENLEN   (LZX_AUX_MAINLEN + LZX_MAIN_ALLOC * 32)   /* u8  [320][32]  */
-#define LZX_AUX_MSORT    (LZX_AUX_LENLEN + LZX_LEN_ALLOC * 32)     /* u16 [768][32]  */
+#define LZX_AUX_MSORT    (LZX_AUX_LENLEN + LZX_LEN_ALLOC * 32)     /* u16 [2592][32] */
 #define LZX_AUX_LSORT    (LZX_AUX_MSORT + LZX_MSORT_N * 32 * 2)    /* u16 [256][32]  */
 #define LZX_AUX_PSORT    (LZX_AUX_LSORT + 256 * 32 * 2)            /* u16 [32][32]   */
 #define LZX_AUX_ASORT    (LZX_AUX_PSORT + 32 * 32 * 2)             /* u16 [16][32]   */
@@ -28,7 +28,10 @@
 #define LZX_AUX_OFFS     (LZX_AUX_LIMIT + 4 * 20 * 32 * 4)         /* u16 [4][20][32] */
 #define LZX_AUX_BYTES    (LZX_AUX_OFFS + 4 * 20 * 32 * 2)
 
-/* HEADN = main-tree symbols (shortest codes first) kept in shared memory */
+/* HEADN = main-tree symbols (shortest codes first) kept in shared memory.
+ * DELTA = the instantiation that also understands LZX DELTA units (MSGPU_FLAG_LZX_DELTA: window_bits up to 25, a 16-bit
+ * chunk size per frame lzxd.c:441-444, match lengths beyond 257 :589-611, reference data in front of the unit :348-382
+ * and :622-628); batches without such units run the plain instantiation, whose code is unchanged by all of this */
 template <int NT, int HEADN>
 struct LzxSharedC {
     uint32_t mbo[17 * NT];                /* main tree: limit[l-1] >> 1 | offs[l] << 16 */
@@ -41,9 +44,10 @@ struct LzxSharedC {
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int HEADN>
+template <int NT, int HEADN, bool DELTA = false>
 struct LzxLaneC {
     MsBits b;
+    uint32_t is_delta, ref_len;           /* DELTA only: this unit is an LZX DELTA stream; bytes of reference data in front of it */
     uint32_t *mbo, *lbo, *abo;
     uint16_t *mhead, *llim, *alim, *llut, *cnt;
     uint8_t *main_len, *len_len;
@@ -233,10 +237,19 @@ struct LzxLaneC {
 
     MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
 
+    /* lzxd.c:441-444: LZX DELTA, the 16-bit chunk size in front of every frame: ENSURE_BITS(16), REMOVE_BITS(16).  With an
+     * empty bit buffer (after the raw bytes of an uncompressed block) that is one two-byte fetch at the byte pointer, wherever
+     * it stands, and the buffer is empty again afterwards */
+    MS_M void skip_chunk_size() {
+        if (bytemode) { (void) raw_byte(); (void) raw_byte(); }
+        else { lzx_refill(b); lzx_check(b, 16); msb_drop(b, 16); }
+    }
+
     /* lzxd.c:419-461: frame prologue (reset interval, intel header, frame size) */
     MS_M void frame_start() {
         frame_start_pos = produced;
         if (u->reset_interval && (frame % u->reset_interval) == 0) reset_state();                     /* :423-438 */
+        if (DELTA && is_delta) { skip_chunk_size(); if (b.err) { fail(b.err); return; } }             /* :441-444 */
         if (!header_read) {                                                                          /* :447-453 */
             enter_bits();
             lzx_refill(b);
@@ -285,6 +298,10 @@ struct LzxLaneC {
             /* lzxd.c:419: a request ending exactly on a frame boundary runs one more zero-sized frame pass; at a
              * reset point that re-reads the intel header and tops the bit buffer up (see oracle/port/mspack_port.c) -
              * the only effect is MSPACK_ERR_READ on an exactly-cut unit */
+            if (DELTA && is_delta && (u->out_len % MS_FRAME) == 0) {          /* the extra pass reads its chunk size too */
+                skip_chunk_size();
+                if (b.err) { status = b.err; return; }
+            }
             if ((u->out_len % MS_FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
                 int32_t bp;
                 if (bytemode) { if (bytepos & 1) { b.in += 1; b.in_len -= 1; bytepos -= 1; ms_bits_rebase(b); } bp = bytepos; }
@@ -322,7 +339,7 @@ struct LzxLaneC {
     MS_M void step() {
         /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
          * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
-        if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_plain<true>(); else step_plain<false>();
+        if (MS_UNLIKELY(b.ipos + (DELTA ? 32 : 24) > b.in_len)) step_plain<true>(); else step_plain<false>();     /* DELTA: one more refill */
     }
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
     template <bool careful> MS_M void step_plain() {
@@ -355,6 +372,16 @@ struct LzxLaneC {
                 else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;
             }
+            if (DELTA && is_delta && ml == 257) {                    /* lzxd.c:589-611: the longest length announces more */
+                lzx_refill(b);
+                if (careful) lzx_check(b, 3);
+                const uint32_t p3 = msb_peek(b, 3);
+                const int pre = p3 < 4 ? 1 : (p3 < 6 ? 2 : 3), nb = p3 < 4 ? 8 : (p3 < 6 ? 10 : (p3 == 6 ? 12 : 15));
+                msb_drop(b, pre);
+                if (careful) lzx_check(b, nb);
+                ml += msb_peek(b, nb) + (p3 < 4 ? 0u : (p3 < 6 ? 0x100u : (p3 == 6 ? 0x500u : 0u)));
+                msb_drop(b, nb);
+            }
             if (careful && b.err) { fail(b.err); return; }
             if (!resolve_match(ml, off)) return;
         }
@@ -369,14 +396,15 @@ struct LzxLaneC {
             uint32_t wpr = G & (window_size - 1);
             bool bad = (wpr + ml > window_size);
             if (off > wpr) {
-                bad = bad || (off > frame_start_pos) || (off - wpr > window_size);
+                /* :622-628: beyond the decoded data is fine only inside the reference data (DELTA) */
+                bad = bad || (off > frame_start_pos && (!DELTA || off - wpr > ref_len)) || (off - wpr > window_size);
                 if (off > window_size) eff = off - window_size;
             }
             if (eff == 0) eff = window_size;          /* source == destination: the bytes one window lap back */
             if (bad) { fail(MS_EDECRUNCH); return false; }
         }
         if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return false; }   /* :678-693 every overrun ends in an error */
-        emit_match(em, q, ml, eff);
+        if (DELTA) emit_match_wide(em, q, ml, eff); else emit_match(em, q, ml, eff);
         q += ml; this_run -= (int32_t) ml;
         return true;
     }
@@ -387,12 +415,15 @@ struct LzxLaneC {
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         const int wb = unit->window_bits;
-        const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u : 50u;   /* position_slots[], lzxd.c:209-211 */
+        is_delta = (DELTA && (unit->flags & MSGPU_FLAG_LZX_DELTA)) ? 1u : 0u; ref_len = DELTA ? MSGPU_UNIT_REF_BYTES(unit) : 0u;
+        const uint32_t slots = wb == 15 ? 30u : wb == 16 ? 32u : wb == 17 ? 34u : wb == 18 ? 36u : wb == 19 ? 38u : wb == 20 ? 42u :
+                               (DELTA && wb > 21) ? (wb == 22 ? 66u : wb == 23 ? 98u : wb == 24 ? 162u : 290u) : 50u;     /* position_slots[], lzxd.c:209-211 */
         window_size = 1u << (wb & 31); num_offsets = slots << 3;
         nsyms_eff = 256 + num_offsets + 51; if (nsyms_eff > LZX_MAIN_MAX) nsyms_eff = LZX_MAIN_MAX;
         if (!st.started) {
             done = 0; status = 0; produced = 0; frame = 0;
-            if (wb < 15 || wb > 21) { status = MS_ENOMEM; done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
+            if (DELTA && is_delta ? (wb < 17 || wb > 25) : (wb < 15 || wb > 21)) { status = MS_ENOMEM; done = 1; }      /* lzxd_init returns NULL -> cabd.c:1255 */
+            else if (DELTA && ref_len && (!is_delta || ref_len > (1u << wb))) { status = MS_EARGS; done = 1; }              /* lzxd.c:355-366 */
             ms_bits_init(b, in_base + unit->in_off, unit->in_len);
             base = 0; bytemode = 0; bytepos = 0; intel_filesize = 0; intel_started = 0; length_empty = 0; aligned_lens = 0;
             R0 = R1 = R2 = 1; header_read = 0; block_remaining = 0; block_type = 0; block_length = 0;

@@ -21,13 +21,15 @@
 
 MS_D uint32_t rec_pos(uint32_t a) { return a & 0xFFFFu; }
 MS_D uint32_t rec_off(uint32_t b) { return b & 0x3FFFFFu; }
+/* WIDE (batches with LZX DELTA units, window up to 2^25): offset bits 22.. travel in the upper half of a (emit_match_wide) */
+template <bool WIDE> MS_D uint32_t rec_off_w(uint32_t a, uint32_t b) { return WIDE ? ((b & 0x3FFFFFu) | ((a >> 16) << 22)) : (b & 0x3FFFFFu); }
 MS_D uint32_t rec_len(uint32_t b) { return b >> 22; }
 
 /* Per-byte source descriptor (pass A -> pass B), one u32 per position of the chunk:
  *     value & 0x7FFFFFFF = (frame-relative position of the byte to copy) + P2_SBIAS; the position may lie in earlier frames
  *                          of the unit, i.e. be negative; overlapping matches are already folded
  *     bit 31 set         : final - the byte is a literal P1 stored at that very position (never followed further) */
-#define P2_SBIAS (1 << 22)
+#define P2_SBIAS ((WIDE) ? (1 << 26) : (1 << 22))          /* > the largest match offset: 2^21, or 2^25 with LZX DELTA units (WIDE) */
 #define P2_LIT   0x80000000u
 /* descriptor of chunk position p (0..511) lives at P2_SIDX(p) = p + p / 16: a row of 17 words per lane, so the 32
  * lanes, which all touch "their k-th byte" at the same time, hit 32 different banks (17 is odd) */
@@ -35,6 +37,7 @@ MS_D uint32_t rec_len(uint32_t b) { return b >> 22; }
 #define P2_SRC_WORDS (P2_CHUNK + P2_CHUNK / 16)
 
 /* descriptor of frame position p inside the match (pos, off, len) */
+template <bool WIDE>
 MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t off, uint32_t len) {
     uint32_t kk = p - pos;
     if (off >= len || kk < off) return p - off + P2_SBIAS;
@@ -45,6 +48,7 @@ MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t off, uint32_t len) {
 #define P2_LONG_MAX  16
 
 /* Pass A, step 1: every lane marks its own 16 positions as literals (call before a warp sync) */
+template <bool WIDE>
 MS_D void p2_pass_a_literals(uint32_t q0, uint32_t c, uint32_t *src) {
     uint32_t *row = src + P2_SIDX(q0 - c);
 #pragma unroll
@@ -57,13 +61,14 @@ MS_D void p2_pass_a_literals(uint32_t q0, uint32_t c, uint32_t *src) {
  * data) are queued in shared memory and filled by all 32 lanes together.  longq[0] = count, longq[1..] = window indices.
  * Returns the first window index this lane saw whose match ends beyond cend (P2_WIN if none): the minimum over the warp is
  * the next chunk's r_lo. */
+template <bool WIDE>
 MS_D int p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb,
                            uint32_t *src, uint32_t *longq)
 {
     int next_lo = P2_WIN;
 #pragma unroll 1
     for (int r = r_lo + lane; r < P2_WIN; r += 32) {
-        uint32_t pos = rec_pos(wa[r]), b = wb[r], off = rec_off(b), len = rec_len(b), end = pos + len;
+        uint32_t a = wa[r], pos = rec_pos(a), b = wb[r], off = rec_off_w<WIDE>(a, b), len = rec_len(b), end = pos + len;
         if (pos >= cend) { if (next_lo == P2_WIN) next_lo = r; break; }               /* (the sentinel has pos >= size >= cend) */
         if (end > cend && next_lo == P2_WIN) next_lo = r;
         uint32_t p = pos > c ? pos : c, p1 = end < cend ? end : cend;
@@ -83,30 +88,33 @@ MS_D int p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const 
         }
         else {
 #pragma unroll 1
-            for (; p < p1; p++) src[P2_SIDX(p - c)] = p2_desc(p, pos, off, len);      /* overlapping match */
+            for (; p < p1; p++) src[P2_SIDX(p - c)] = p2_desc<WIDE>(p, pos, off, len);      /* overlapping match */
         }
     }
     return next_lo;
 }
 /* Pass A, step 3: the queued long matches, all lanes together (call after a warp sync) */
+template <bool WIDE>
 MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src, const uint32_t *longq)
 {
     uint32_t nl = longq[0] < P2_LONG_MAX ? longq[0] : P2_LONG_MAX;
 #pragma unroll 1
     for (uint32_t i = 0; i < nl; i++) {
         int r = (int) longq[1 + i];
-        uint32_t pos = rec_pos(wa[r]), b = wb[r], off = rec_off(b), len = rec_len(b);
+        uint32_t a = wa[r], pos = rec_pos(a), b = wb[r], off = rec_off_w<WIDE>(a, b), len = rec_len(b);
         uint32_t p0 = pos > c ? pos : c, p1 = pos + len < cend ? pos + len : cend;
 #pragma unroll 1
-        for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc(p, pos, off, len);
+        for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc<WIDE>(p, pos, off, len);
     }
 }
 
 /* Pass B: fetch this lane's 16 bytes [q0, q0+16) (little-endian in 4 words; positions >= size give 0).  A source inside
  * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
  * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
- * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero. */
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4])
+ * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero - except for the ref_len bytes
+ * directly in front of the unit, the reference data of an LZX DELTA unit (WIDE only). */
+template <bool WIDE>
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0)
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
@@ -122,7 +130,8 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
         d[k] = x & ~P2_LIT;
     }
     const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
-    const uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
+    uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
+    if (WIDE) ulim = ulim > ref_len ? ulim - ref_len : 0u;
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
@@ -133,8 +142,9 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
+template <bool WIDE>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq)
+                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     int r_lo = 0;                                              /* first window record ending beyond the chunk start */
@@ -152,14 +162,14 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         if (lane == 0) longq[0] = 0;
-        p2_pass_a_literals(q0, c, src);
+        p2_pass_a_literals<WIDE>(q0, c, src);
         __syncwarp();
-        int nlo = p2_pass_a_records(lane, r_lo, c, cend, wa, wb, src, longq);
+        int nlo = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa, wb, src, longq);
         r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);            /* also orders the descriptor stores (it is a warp sync) */
         __syncwarp();
-        p2_pass_a_long(lane, c, cend, wa, wb, src, longq);
+        p2_pass_a_long<WIDE>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b(q0, c, size, src, unit_out, g0, w);
+        p2_pass_b<WIDE>(q0, c, size, src, unit_out, g0, w, ref_len);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

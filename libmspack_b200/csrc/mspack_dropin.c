@@ -37,7 +37,9 @@ static msgpu_ctx *ctx_get(void) {
 struct dstream {                     /* common state; the three public stream types are this struct */
     struct mspack_system *sys;
     struct mspack_file *input, *output;
-    int codec, window_bits, reset_interval, repair_mode;
+    int codec, window_bits, reset_interval, repair_mode, is_delta;
+    unsigned char *ref; size_t ref_len;  /* LZX DELTA reference data (lzxd_set_reference_data) */
+    size_t out_base;                 /* the unit's first output byte inside `out` (the reference data sits in front of it) */
     off_t length;                    /* LZX: total output length if known (0 = not yet) */
     off_t offset;                    /* bytes delivered to write() so far */
     int error;                       /* sticky */
@@ -61,7 +63,7 @@ static struct dstream *ds_new(struct mspack_system *sys, struct mspack_file *in,
 
 static void ds_free(struct dstream *s) {
     if (!s) return;
-    free(s->in); free(s->out);
+    free(s->in); free(s->out); free(s->ref);
     s->sys->free(s);
 }
 
@@ -88,15 +90,18 @@ static int ds_slurp(struct dstream *s) {
 /* decode the unit's first `want` output bytes on the device */
 static int ds_decode(struct dstream *s, size_t want) {
     msgpu_unit u; int32_t st = -1; int rc; unsigned char *buf;
-    buf = (unsigned char *) realloc(s->out, want + 64);
+    const size_t rpad = (s->ref_len + 15) & ~(size_t) 15;      /* the batch ABI wants the reference data right in front of the output */
+    buf = (unsigned char *) realloc(s->out, rpad + want + 64);
     if (!buf) return MSPACK_ERR_NOMEMORY;
-    s->out = buf;
+    s->out = buf; s->out_base = rpad;
+    if (s->ref_len) memcpy(s->out + rpad - s->ref_len, s->ref, s->ref_len);
     memset(&u, 0, sizeof(u));
     u.codec = (uint8_t) s->codec; u.window_bits = (uint8_t) s->window_bits; u.reset_interval = (uint16_t) s->reset_interval;
     u.flags = s->repair_mode ? MSGPU_FLAG_MSZIP_REPAIR : 0;
-    u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = 0; u.out_len = (uint32_t) want;
+    if (s->is_delta) u.flags |= MSGPU_FLAG_LZX_DELTA | ((uint32_t) s->ref_len << MSGPU_FLAG_REF_SHIFT);
+    u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = rpad; u.out_len = (uint32_t) want;
     pthread_mutex_lock(&g_mu);
-    rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len + 0, s->out, want, &st);
+    rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len + 0, s->out, rpad + want, &st);
     pthread_mutex_unlock(&g_mu);
     if (rc) return MSPACK_ERR_NOMEMORY;
     if (st == MSGPU_ERR_OK) { s->out_len = want; return MSPACK_ERR_OK; }
@@ -131,7 +136,7 @@ static int ds_decompress(struct dstream *s, off_t out_bytes) {
     /* replay: exactly out_bytes more bytes to write() (mspack.h:346-355 write must return the count) */
     while (out_bytes > 0) {
         int n = out_bytes > (1 << 20) ? (1 << 20) : (int) out_bytes;
-        if (s->sys->write(s->output, s->out + s->offset, n) != n) return s->error = MSPACK_ERR_WRITE;
+        if (s->sys->write(s->output, s->out + s->out_base + s->offset, n) != n) return s->error = MSPACK_ERR_WRITE;
         s->offset += n; out_bytes -= n;
     }
     return MSPACK_ERR_OK;
@@ -142,15 +147,15 @@ struct lzxd_stream *lzxd_init(struct mspack_system *system, struct mspack_file *
                               int window_bits, int reset_interval, int input_buffer_size, off_t output_length, char is_delta)
 {
     struct dstream *s;
-    if (is_delta) return NULL;                                   /* LZX DELTA (oabd.c) is outside the GPU path: SURVEY.md 8(f4) */
-    if (window_bits < 15 || window_bits > 21) return NULL;       /* lzxd.c:294-296 */
+    /* lzxd.c:289-296: LZX DELTA windows are 2^17..2^25 bytes, regular LZX windows 2^15..2^21 */
+    if (is_delta ? (window_bits < 17 || window_bits > 25) : (window_bits < 15 || window_bits > 21)) return NULL;
     if (reset_interval < 0 || output_length < 0) return NULL;    /* :298-301 */
     input_buffer_size = (input_buffer_size + 1) & -2;
     if (input_buffer_size < 2) return NULL;                      /* :304-305 */
     if (reset_interval > 0xFFFF) return NULL;
     s = ds_new(system, input, output, MSGPU_CODEC_LZX);
     if (!s) return NULL;
-    s->window_bits = window_bits; s->reset_interval = reset_interval; s->length = output_length;
+    s->window_bits = window_bits; s->reset_interval = reset_interval; s->length = output_length; s->is_delta = is_delta ? 1 : 0;
     return (struct lzxd_stream *) s;
 }
 void lzxd_set_output_length(struct lzxd_stream *lzx, off_t out_bytes) {     /* lzxd.c:384-386 */
@@ -158,8 +163,21 @@ void lzxd_set_output_length(struct lzxd_stream *lzx, off_t out_bytes) {     /* l
     if (s && out_bytes > 0) s->length = out_bytes;
 }
 int lzxd_set_reference_data(struct lzxd_stream *lzx, struct mspack_system *system, struct mspack_file *input, unsigned int length) {
-    (void) system; (void) input; (void) length;
-    return lzx ? MSPACK_ERR_ARGS : MSPACK_ERR_ARGS;              /* lzxd.c:355-358: only LZX DELTA streams take reference data */
+    struct dstream *s = (struct dstream *) lzx;                  /* lzxd.c:348-382, same checks in the same order */
+    if (!s) return MSPACK_ERR_ARGS;
+    if (!s->is_delta) return MSPACK_ERR_ARGS;                    /* only LZX DELTA streams support reference data */
+    if (s->offset) return MSPACK_ERR_ARGS;                       /* too late once decoding has started */
+    if (length > (1u << s->window_bits)) return MSPACK_ERR_ARGS; /* longer than the window */
+    if (length > 0 && (!system || !input)) return MSPACK_ERR_ARGS;
+    free(s->ref); s->ref = NULL; s->ref_len = length;
+    if (length > 0) {
+        int bytes;
+        if (!(s->ref = (unsigned char *) malloc(length))) { s->ref_len = 0; return MSPACK_ERR_NOMEMORY; }
+        bytes = system->read(input, s->ref, (int) length);
+        if (bytes < (int) length) return MSPACK_ERR_READ;
+    }
+    s->out_len = 0;                                              /* anything decoded before used other reference data */
+    return MSPACK_ERR_OK;
 }
 int lzxd_decompress(struct lzxd_stream *lzx, off_t out_bytes) { return ds_decompress((struct dstream *) lzx, out_bytes); }
 void lzxd_free(struct lzxd_stream *lzx) { ds_free((struct dstream *) lzx); }

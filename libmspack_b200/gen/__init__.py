@@ -27,7 +27,8 @@ DATA_KINDS = {"text": 0, "binary": 1, "zeros": 2, "random": 3}
 class _LzxParams(ctypes.Structure):
     _fields_ = [("window_bits", ctypes.c_int), ("reset_interval", ctypes.c_int), ("block_frames", ctypes.c_int),
                 ("split", ctypes.c_int), ("block_mode", ctypes.c_int), ("intel", ctypes.c_int),
-                ("intel_filesize", ctypes.c_uint32), ("chain", ctypes.c_int), ("seed", ctypes.c_uint32)]
+                ("intel_filesize", ctypes.c_uint32), ("chain", ctypes.c_int), ("seed", ctypes.c_uint32),
+                ("delta", ctypes.c_int), ("ref_len", ctypes.c_uint32)]
 
 
 class _QtmParams(ctypes.Structure):
@@ -55,6 +56,9 @@ def _lib():
         _LIB.msgen_generate.restype = ctypes.c_int
         _LIB.msgen_generate.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int]
+        _LIB.msgen_generate_ref.restype = ctypes.c_int
+        _LIB.msgen_generate_ref.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int]
         _LIB.msgen_fill_raw.restype = ctypes.c_int
         _LIB.msgen_fill_raw.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]
         _LIB.msgen_lzx_encode.restype = ctypes.c_size_t
@@ -80,12 +84,14 @@ def raw_units(n: int, unit_bytes: int = FRAME, data: str = "text", seed: int = C
 
 
 def lzx_encode(data: bytes, window_bits: int = 21, reset_interval: int = 0, block_frames: int = 1, split: int = 1,
-               block_mode: int = 0, intel: int = 0, intel_filesize: int = 12000000, chain: int = 24, seed: int = 1) -> bytes:
-    src = np.frombuffer(bytes(data), dtype=np.uint8)
+               block_mode: int = 0, intel: int = 0, intel_filesize: int = 12000000, chain: int = 24, seed: int = 1,
+               delta: int = 0, ref: bytes = b"") -> bytes:
+    """One LZX stream.  delta=1: LZX DELTA (16-bit chunk size per frame, long matches); `ref` = its reference data."""
+    src = np.frombuffer(bytes(ref) + bytes(data), dtype=np.uint8)
     cap = len(data) + len(data) // 8 + 4096
     dst = np.empty(cap, dtype=np.uint8)
-    p = _LzxParams(window_bits, reset_interval, block_frames, split, block_mode, intel, intel_filesize, chain, seed)
-    r = _lib().msgen_lzx_encode(src.ctypes.data, len(data), dst.ctypes.data, cap, ctypes.byref(p))
+    p = _LzxParams(window_bits, reset_interval, block_frames, split, block_mode, intel, intel_filesize, chain, seed, delta, len(ref))
+    r = _lib().msgen_lzx_encode(src.ctypes.data + len(ref), len(data), dst.ctypes.data, cap, ctypes.byref(p))
     if r == 0 and len(data):
         raise RuntimeError("lzx_encode overflow")
     return dst[:r].tobytes()
@@ -119,8 +125,16 @@ def mszip_encode(data: bytes, level: int = 6, history: bool = True) -> bytes:
 class Batch:
     """A batch of independent units: descriptors, packed compressed bytes, optional raw data."""
 
-    def __init__(self, units: np.ndarray, comp: np.ndarray, raw: np.ndarray | None, out_bytes: int):
+    def __init__(self, units: np.ndarray, comp: np.ndarray, raw: np.ndarray | None, out_bytes: int,
+                 out_init: np.ndarray | None = None):
         self.units, self.comp, self.raw, self.out_bytes = units, comp, raw, out_bytes
+        # LZX DELTA: initial contents of the output buffer - each unit's reference data sits in front of its output
+        # (include/msgpu.h MSGPU_FLAG_REF_SHIFT); None for every other kind of batch
+        self.out_init = out_init
+
+    def unit_output(self, out: np.ndarray, i: int) -> np.ndarray:
+        lo, n = int(self.units["out_off"][i]), int(self.units["out_len"][i])
+        return out[lo:lo + n]
 
     @property
     def n(self):
@@ -151,13 +165,16 @@ def _pack(codec, window_bits, reset_interval, pieces, unit_bytes, raw):
 def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 21, data: str = "text",
                seed: int = CORPUS_SEED, first_unit: int = 0, threads: int = 0, keep_raw: bool = False,
                reset_interval: int = 0, block_frames: int = 1, split: int = 1, block_mode: int = 0, intel: int = 0,
-               intel_filesize: int = 12000000, chain: int = 24, level: int = 6, slack: int = 0) -> Batch:
+               intel_filesize: int = 12000000, chain: int = 24, level: int = 6, slack: int = 0,
+               delta: int = 0, ref_bytes: int = 0) -> Batch:
     """n independent units of `unit_bytes` uncompressed bytes each, all of one codec.
 
     slack: extra bytes added to every unit's in_len (they are the next unit's first bytes, as in a CHM content stream).
     The reference runs one more, empty, frame pass when a request ends on a frame boundary and at a reset point that
     pass reads ahead (lzxd.c:419-453, :696-697): a reset-interval unit cut exactly at its last byte decodes completely
-    but returns MSPACK_ERR_READ; 4 bytes of slack avoid that."""
+    but returns MSPACK_ERR_READ; 4 bytes of slack avoid that.
+    delta / ref_bytes: LZX DELTA units (window_bits 17..25), each with ref_bytes of reference data - an older version of
+    the unit's own data - stored in front of its output (Batch.out_init holds the output buffer's initial contents)."""
     threads = _threads(threads)
     nfr = (unit_bytes + FRAME - 1) // FRAME
     if codec == CODEC_MSZIP:
@@ -175,13 +192,17 @@ def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 2
         slot = unit_bytes * 2 + 2048
     b = _Batch(codec=codec, data_kind=DATA_KINDS[data], seed=seed, first_block=first_unit * nfr,
                unit_bytes=unit_bytes, slot_bytes=slot)
-    b.lzx = _LzxParams(window_bits, reset_interval, block_frames, split, block_mode, intel, intel_filesize, chain, seed & 0xFFFFFFFF)
+    if codec != CODEC_LZX or not delta:
+        delta, ref_bytes = 0, 0
+    b.lzx = _LzxParams(window_bits, reset_interval, block_frames, split, block_mode, intel, intel_filesize, chain, seed & 0xFFFFFFFF,
+                       delta, ref_bytes)
     b.qtm = _QtmParams(window_bits, chain)
     raw = np.empty(n * unit_bytes, dtype=np.uint8) if keep_raw else None
+    ref = np.empty(n * ref_bytes, dtype=np.uint8) if ref_bytes else None
     comp_slots = np.empty(n * slot, dtype=np.uint8)
     lens = np.zeros(n, dtype=np.uint32)
-    _lib().msgen_generate(ctypes.byref(b), n, raw.ctypes.data if keep_raw else None, comp_slots.ctypes.data,
-                          lens.ctypes.data, threads)
+    _lib().msgen_generate_ref(ctypes.byref(b), n, raw.ctypes.data if keep_raw else None, ref.ctypes.data if ref_bytes else None,
+                              comp_slots.ctypes.data, lens.ctypes.data, threads)
     if n and int(lens.min()) == 0:
         raise RuntimeError("encoder overflowed its slot")
     units = np.zeros(n, dtype=UNIT_DTYPE)
@@ -198,6 +219,16 @@ def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 2
     units["reset_interval"] = reset_interval if codec == CODEC_LZX else 0
     units["in_off"], units["in_len"], units["out_len"] = offs, lens + np.uint32(slack), unit_bytes
     stride = (unit_bytes + 15) & ~15
+    if delta:
+        units["flags"] = 0x2 | (ref_bytes << 6)                       # MSGPU_FLAG_LZX_DELTA | reference bytes << MSGPU_FLAG_REF_SHIFT
+        rpad = (ref_bytes + 15) & ~15
+        stride += rpad
+        units["out_off"] = np.arange(n, dtype=np.uint64) * np.uint64(stride) + np.uint64(rpad)
+        out_init = None
+        if ref_bytes:
+            out_init = np.zeros(n * stride, dtype=np.uint8)
+            out_init.reshape(n, stride)[:, rpad - ref_bytes:rpad] = ref.reshape(n, ref_bytes)
+        return Batch(units, comp, raw, n * stride, out_init)
     units["out_off"] = np.arange(n, dtype=np.uint64) * np.uint64(stride)
     return Batch(units, comp, raw, n * stride)
 
@@ -205,7 +236,11 @@ def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 2
 def concat_batches(batches) -> Batch:
     """Concatenate batches (e.g. a mixed-codec batch) re-basing the offsets."""
     units, comps, in_base, out_base = [], [], 0, 0
+    any_init = any(b.out_init is not None for b in batches)
+    inits = []
     for b in batches:
+        if any_init:
+            inits.append(b.out_init if b.out_init is not None else np.zeros(b.out_bytes, dtype=np.uint8))
         u = b.units.copy()
         u["in_off"] += np.uint64(in_base)
         u["out_off"] += np.uint64(out_base)
@@ -213,4 +248,4 @@ def concat_batches(batches) -> Batch:
         comps.append(b.comp)
         in_base += len(b.comp)
         out_base += b.out_bytes
-    return Batch(np.concatenate(units), np.concatenate(comps), None, out_base)
+    return Batch(np.concatenate(units), np.concatenate(comps), None, out_base, np.concatenate(inits) if any_init else None)

@@ -117,17 +117,20 @@ typedef struct {
 #define HBITS 15
 static inline uint32_t hash3(const uint8_t *p) { return ((uint32_t) (p[0] | (p[1] << 8) | (p[2] << 16)) * 0x9E3779B1u) >> (32 - HBITS); }
 
-/* greedy hash-chain parse of src[0..n); matches never cross a 32 KiB frame boundary */
-static size_t lz_parse(const uint8_t *src, size_t n, const lzparams *lp, token *tok, uint32_t reset_bytes) {
+/* greedy hash-chain parse of src[start..n); matches never cross a 32 KiB frame boundary (frames counted from `start`).
+ * src[0..start) is history only (LZX DELTA reference data): it is indexed but produces no tokens */
+static size_t lz_parse(const uint8_t *src, size_t n, const lzparams *lp, token *tok, uint32_t reset_bytes, size_t start) {
     uint32_t *head = (uint32_t *) malloc(sizeof(uint32_t) << HBITS), *prev = (uint32_t *) malloc(sizeof(uint32_t) * (n + 1));
     size_t pos = 0, nt = 0; uint32_t R[3] = { 1, 1, 1 };
     memset(head, 0xFF, sizeof(uint32_t) << HBITS);
+    for (; pos < start; pos++) if (pos + 3 <= n) { uint32_t h = hash3(src + pos); prev[pos] = head[h]; head[h] = (uint32_t) pos; }
     while (pos < n) {
-        uint32_t frame_left = FRAME - (uint32_t) (pos & (FRAME - 1)), maxl = lp->max_match, best = 0, boff = 0, lowest = 0;
+        const size_t rel = pos - start;
+        uint32_t frame_left = FRAME - (uint32_t) (rel & (FRAME - 1)), maxl = lp->max_match, best = 0, boff = 0, lowest = 0;
         if (maxl > frame_left) maxl = frame_left;
         if (maxl > n - pos) maxl = (uint32_t) (n - pos);
-        if (reset_bytes && (pos % reset_bytes) == 0) { R[0] = R[1] = R[2] = 1; }
-        if (lp->confine) lowest = (uint32_t) (pos - pos % lp->confine);
+        if (reset_bytes && (rel % reset_bytes) == 0) { R[0] = R[1] = R[2] = 1; }
+        if (lp->confine) lowest = (uint32_t) (pos - rel % lp->confine);
         if (lp->use_rep && maxl >= 2) {
             int r;
             for (r = 0; r < 3; r++) {
@@ -247,17 +250,22 @@ typedef struct {
     uint32_t intel_filesize;
     int chain;              /* hash chain depth */
     uint32_t seed;
+    int delta;              /* LZX DELTA (lzxd.c:441-444, :589-611): window_bits 17..25, a 16-bit chunk size in front of every
+                             * frame, matches longer than 257 bytes */
+    uint32_t ref_len;       /* DELTA: src[-ref_len .. 0) is the reference data (lzxd.c:348-382) matches may reach into */
 } msgen_lzx_params;
 
-static const uint8_t lzx_slots[7] = { 30, 32, 34, 36, 38, 42, 50 };
-static uint32_t lzx_base[52]; static uint8_t lzx_ebits[52]; static int lzx_ready;
-static void lzx_init_tables(void) { unsigned i; uint32_t b = 0; for (i = 0; i < 52; i++) { unsigned e = i < 4 ? 0 : (i < 36 ? i / 2 - 1 : 17); lzx_ebits[i] = (uint8_t) e; lzx_base[i] = b; b += 1u << e; } lzx_ready = 1; }
+#define LZX_NSLOTS 292
+#define LZX_MAINMAX (256 + 290 * 8 + 64)
+static const uint16_t lzx_slots[11] = { 30, 32, 34, 36, 38, 42, 50, 66, 98, 162, 290 };      /* lzxd.c:209-211 */
+static uint32_t lzx_base[LZX_NSLOTS]; static uint8_t lzx_ebits[LZX_NSLOTS]; static int lzx_ready;
+static void lzx_init_tables(void) { unsigned i; uint32_t b = 0; for (i = 0; i < LZX_NSLOTS; i++) { unsigned e = i < 4 ? 0 : (i < 36 ? i / 2 - 1 : 17); lzx_ebits[i] = (uint8_t) e; lzx_base[i] = b; b += 1u << e; } lzx_ready = 1; }
 
-typedef struct { uint16_t main_sym; int16_t len_sym; uint8_t ebits; uint32_t eval; } lzxsym;
+typedef struct { uint16_t main_sym; int16_t len_sym; uint8_t ebits; uint32_t eval; int32_t xlen; } lzxsym;   /* xlen: DELTA extra length, -1 = none */
 
 /* pretree-coded delta lengths for lens[first..last) against prev[] (lzxd.c:138-183) */
 static void lzx_write_lens(lzxw *w, const uint8_t *lens, uint8_t *prev, int first, int last) {
-    uint8_t syms[1024]; uint8_t arg[1024]; uint8_t arg2[1024]; int ns = 0, x = first, i;
+    uint8_t syms[LZX_MAINMAX]; uint8_t arg[LZX_MAINMAX]; uint8_t arg2[LZX_MAINMAX]; int ns = 0, x = first, i;
     uint32_t freq[20]; uint8_t plen[20]; uint16_t pcode[20];
     memset(freq, 0, sizeof(freq));
     while (x < last) {
@@ -285,28 +293,34 @@ static void lzx_write_lens(lzxw *w, const uint8_t *lens, uint8_t *prev, int firs
     memcpy(prev + first, lens + first, (size_t) (last - first));
 }
 
-/* Encode src[0..n) as one LZX stream.  Returns bytes written (even), or 0 on overflow. */
+/* DELTA: the 16-bit chunk size in front of frame `fr` (lzxd.c:441-444 skips it unread), written once per frame */
+#define LZX_CHUNK(fr) do { if (P->delta && (fr) >= next_chunk) { lzxw_put(&w, (uint32_t) (splitmix64(&rng) & 0xFFFF), 16); next_chunk = (fr) + 1; } } while (0)
+
+/* Encode src[0..n) as one LZX stream (DELTA: src[-ref_len..0) is the reference data).  Returns bytes written, or 0 on overflow. */
 size_t msgen_lzx_encode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, const msgen_lzx_params *P) {
     lzparams lp; token *tok; lzxsym *ls; size_t nt, t0 = 0, pos = 0; lzxw w; uint64_t rng = P->seed * 0x9E3779B97F4A7C15ull + 12345;
-    uint32_t R[3] = { 1, 1, 1 }, frame = 0, num_offsets, main_syms, reset_bytes = (uint32_t) P->reset_interval * FRAME;
-    uint8_t prev_main[720], prev_len[256];
+    uint32_t R[3] = { 1, 1, 1 }, frame = 0, num_offsets, main_syms, reset_bytes = (uint32_t) P->reset_interval * FRAME, next_chunk = 0;
+    static __thread uint8_t prev_main[LZX_MAINMAX], prev_len[256];
+    static __thread uint32_t fmain[LZX_MAINMAX]; static __thread uint8_t lmain[LZX_MAINMAX]; static __thread uint16_t cmain[LZX_MAINMAX];
     int block_frames = P->block_frames > 0 ? P->block_frames : 1, split = P->split > 0 ? P->split : 1;
+    const size_t ref_len = P->delta ? P->ref_len : 0;
     if (!lzx_ready) lzx_init_tables();
     num_offsets = (uint32_t) lzx_slots[P->window_bits - 15] << 3; main_syms = 256 + num_offsets;
     memset(&lp, 0, sizeof(lp));
-    lp.min_match = 2; lp.max_match = 257; lp.max_offset = (1u << P->window_bits) - 3; lp.chain = P->chain > 0 ? P->chain : 24; lp.use_rep = 1;
+    lp.min_match = 2; lp.max_match = P->delta ? FRAME : 257; lp.max_offset = (1u << P->window_bits) - 3; lp.chain = P->chain > 0 ? P->chain : 24; lp.use_rep = 1;
     lp.confine = reset_bytes;
     tok = (token *) malloc(sizeof(token) * (n + 1)); ls = (lzxsym *) malloc(sizeof(lzxsym) * (n + 1));
-    nt = lz_parse(src, n, &lp, tok, reset_bytes);
+    nt = lz_parse(src - ref_len, n + ref_len, &lp, tok, reset_bytes, ref_len);
     memset(&w, 0, sizeof(w)); w.buf = dst; w.cap = cap;
     memset(prev_main, 0, sizeof(prev_main)); memset(prev_len, 0, sizeof(prev_len));
 
     while (pos < n) {
         /* ---- choose the extent of the next block: [pos, bend) ---- */
         size_t bend, t1, t; uint32_t blen; int mode = P->block_mode, aligned;
-        uint32_t fmain[720], flen[256], falign[8]; uint8_t lmain[720], llen[256], lalign[8]; uint16_t cmain[720], clen[256], calign[8];
+        uint32_t flen[256], falign[8]; uint8_t llen[256], lalign[8]; uint16_t clen[256], calign[8];
         if ((pos & (FRAME - 1)) == 0) {
             frame = (uint32_t) (pos / FRAME);
+            LZX_CHUNK(frame);
             if (frame == 0 || (P->reset_interval && frame % (uint32_t) P->reset_interval == 0)) {
                 if (frame) { R[0] = R[1] = R[2] = 1; memset(prev_main, 0, sizeof(prev_main)); memset(prev_len, 0, sizeof(prev_len)); }
                 if (P->intel) { lzxw_put(&w, 1, 1); lzxw_put(&w, P->intel_filesize >> 16, 16); lzxw_put(&w, P->intel_filesize & 0xFFFF, 16); }
@@ -331,7 +345,13 @@ size_t msgen_lzx_encode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, 
             if (w.nacc == 0) lzxw_put(&w, 0, 16); else lzxw_align16(&w);           /* lzxd.c:505-507: 1..16 pad bits */
             /* the decoder keeps R0-R2 from the block header: simulate the matches we skip */
             for (k = 0; k < 3; k++) { lzxw_byte(&w, (uint8_t) R[k]); lzxw_byte(&w, (uint8_t) (R[k] >> 8)); lzxw_byte(&w, (uint8_t) (R[k] >> 16)); lzxw_byte(&w, (uint8_t) (R[k] >> 24)); }
-            for (k = pos; k < bend; k++) lzxw_byte(&w, src[k]);
+            for (k = pos; k < bend; k++) {
+                /* DELTA: a frame boundary inside the block - the decoder takes the chunk size from the raw bytes */
+                if (k > pos && (k & (FRAME - 1)) == 0) LZX_CHUNK((uint32_t) (k / FRAME));
+                lzxw_byte(&w, src[k]);
+            }
+            /* the pad byte of an odd-sized block is skipped by the NEXT block header, i.e. after the next frame's chunk size */
+            if (bend < n && (bend & (FRAME - 1)) == 0) LZX_CHUNK((uint32_t) (bend / FRAME));
             if (blen & 1) lzxw_byte(&w, 0);
             pos = bend; t0 = t1;
             continue;
@@ -341,13 +361,15 @@ size_t msgen_lzx_encode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, 
         memset(fmain, 0, sizeof(fmain)); memset(flen, 0, sizeof(flen)); memset(falign, 0, sizeof(falign));
         for (t = t0; t < t1; t++) {
             lzxsym *s = &ls[t];
+            s->xlen = -1;
             if (tok[t].len == 0) { s->main_sym = tok[t].lit; s->len_sym = -1; s->ebits = 0; s->eval = 0; }
             else {
-                uint32_t o = tok[t].off, lh = tok[t].len - 2u, slot;
+                uint32_t o = tok[t].off, lh = (tok[t].len > 257u ? 257u : tok[t].len) - 2u, slot;
+                if (P->delta && tok[t].len >= 257u) s->xlen = (int32_t) (tok[t].len - 257u);       /* lzxd.c:589-611 */
                 if (o == R[0]) slot = 0;
                 else if (o == R[1]) { slot = 1; R[1] = R[0]; R[0] = o; }
                 else if (o == R[2]) { slot = 2; R[2] = R[0]; R[0] = o; }
-                else { uint32_t f = o + 2; slot = 3; while (slot + 1 < 52 && lzx_base[slot + 1] <= f) slot++; s->eval = f - lzx_base[slot]; R[2] = R[1]; R[1] = R[0]; R[0] = o; }
+                else { uint32_t f = o + 2; slot = 3; while (slot + 1 < LZX_NSLOTS && lzx_base[slot + 1] <= f) slot++; s->eval = f - lzx_base[slot]; R[2] = R[1]; R[1] = R[0]; R[0] = o; }
                 s->ebits = slot >= 3 ? lzx_ebits[slot] : 0; if (slot < 3) s->eval = 0;
                 s->main_sym = (uint16_t) (256 + (slot << 3) + (lh < 7 ? lh : 7));
                 s->len_sym = (int16_t) (lh >= 7 ? (int) (lh - 7) : -1);
@@ -380,8 +402,18 @@ size_t msgen_lzx_encode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, 
                 }
                 else lzxw_put(&w, s->eval, s->ebits);
             }
+            if (s->xlen >= 0) {                                                   /* DELTA extra length, lzxd.c:589-611 */
+                uint32_t x = (uint32_t) s->xlen;
+                if (x < 0x100) { lzxw_put(&w, 0, 1); lzxw_put(&w, x, 8); }
+                else if (x < 0x500) { lzxw_put(&w, 2, 2); lzxw_put(&w, x - 0x100, 10); }
+                else if (x < 0x1500) { lzxw_put(&w, 6, 3); lzxw_put(&w, x - 0x500, 12); }
+                else { lzxw_put(&w, 7, 3); lzxw_put(&w, x, 15); }
+            }
             pos += tok[t].len ? tok[t].len : 1;
-            if ((pos & (FRAME - 1)) == 0 || pos == n) lzxw_align16(&w);          /* lzxd.c:696-697 frame end */
+            if ((pos & (FRAME - 1)) == 0 || pos == n) {                           /* lzxd.c:696-697 frame end */
+                lzxw_align16(&w);
+                if (pos < n && t + 1 < t1) LZX_CHUNK((uint32_t) (pos / FRAME));   /* the block goes on into the next frame */
+            }
         }
         t0 = t1;
     }
@@ -446,7 +478,7 @@ size_t msgen_qtm_encode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, 
     lp.min_match = 3; lp.max_match = 259; lp.max_offset = 1u << P->window_bits; lp.chain = P->chain > 0 ? P->chain : 24; lp.use_rep = 0;
     { int s4 = wb2 > 24 ? 24 : wb2, s5 = wb2 > 36 ? 36 : wb2; lp.len3_max_offset = q_pbase[s4 - 1] + (1u << q_ebits[s4 - 1]); lp.len4_max_offset = q_pbase[s5 - 1] + (1u << q_ebits[s5 - 1]); }
     tok = (token *) malloc(sizeof(token) * (n + 1));
-    nt = lz_parse(src, n, &lp, tok, 0);
+    nt = lz_parse(src, n, &lp, tok, 0, 0);
     qm_init(&m0, 0, 64); qm_init(&m1, 64, 64); qm_init(&m2, 128, 64); qm_init(&m3, 192, 64);
     qm_init(&m4, 0, wb2 > 24 ? 24 : wb2); qm_init(&m5, 0, wb2 > 36 ? 36 : wb2); qm_init(&m6, 0, wb2); qm_init(&m6len, 0, 27); qm_init(&m7, 0, 7);
     memset(&e, 0, sizeof(e));
@@ -507,7 +539,7 @@ typedef struct {
     msgen_lzx_params lzx; msgen_qtm_params qtm;
 } msgen_batch;
 
-typedef struct { const msgen_batch *b; size_t lo, hi; uint8_t *raw, *comp; uint32_t *comp_len; } gen_job;
+typedef struct { const msgen_batch *b; size_t lo, hi; uint8_t *raw, *comp, *ref; uint32_t *comp_len; } gen_job;
 
 static void fill_unit(const msgen_batch *b, size_t i, uint8_t *raw) {
     uint32_t nfr = (b->unit_bytes + FRAME - 1) / FRAME, f;
@@ -522,11 +554,24 @@ static void fill_unit(const msgen_batch *b, size_t i, uint8_t *raw) {
     }
 }
 
+/* LZX DELTA reference data for unit i: an "older version" of the unit's own data - the same bytes moved by a few
+ * positions with a byte changed every few thousand, so that the encoder finds long matches reaching into it */
+static void make_ref(const msgen_batch *b, size_t i, const uint8_t *raw, uint8_t *ref, uint32_t ref_len) {
+    uint64_t s = b->seed ^ (0xD1B54A32D192ED03ull * (i + 1)); uint32_t k, shift = (uint32_t) (splitmix64(&s) % 97), next = (uint32_t) (splitmix64(&s) % 700);
+    for (k = 0; k < ref_len; k++) {
+        ref[k] = raw[(k + shift) % b->unit_bytes];
+        if (k == next) { ref[k] ^= (uint8_t) (1 + (splitmix64(&s) % 255)); next += 1 + (uint32_t) (splitmix64(&s) % 5000); }
+    }
+}
+
 static void *gen_worker(void *arg) {
-    gen_job *j = (gen_job *) arg; size_t i; uint8_t *tmp = j->raw ? NULL : (uint8_t *) malloc(j->b->unit_bytes + 16);
+    gen_job *j = (gen_job *) arg; size_t i; const uint32_t ref_len = (j->b->codec == 3 && j->b->lzx.delta) ? j->b->lzx.ref_len : 0;
+    uint8_t *tmp = (uint8_t *) malloc((size_t) ref_len + j->b->unit_bytes + 16);
     for (i = j->lo; i < j->hi; i++) {
-        uint8_t *raw = j->raw ? j->raw + i * (size_t) j->b->unit_bytes : tmp, *dst = j->comp + i * (size_t) j->b->slot_bytes; size_t r;
+        uint8_t *raw = tmp + ref_len, *dst = j->comp + i * (size_t) j->b->slot_bytes; size_t r;
         fill_unit(j->b, i, raw);
+        if (ref_len) { make_ref(j->b, i, raw, tmp, ref_len); if (j->ref) memcpy(j->ref + i * (size_t) ref_len, tmp, ref_len); }
+        if (j->raw) memcpy(j->raw + i * (size_t) j->b->unit_bytes, raw, j->b->unit_bytes);
         if (j->b->codec == 3) { msgen_lzx_params p = j->b->lzx; p.seed ^= (uint32_t) (i * 2654435761u); r = msgen_lzx_encode(raw, j->b->unit_bytes, dst, j->b->slot_bytes, &p); }
         else r = msgen_qtm_encode(raw, j->b->unit_bytes, dst, j->b->slot_bytes, &j->b->qtm);
         j->comp_len[i] = (uint32_t) r;
@@ -537,7 +582,12 @@ static void *gen_worker(void *arg) {
 
 /* Generate n units.  raw (n * unit_bytes, may be NULL) receives the uncompressed data, comp
  * (n * slot_bytes) the compressed units, comp_len[i] their sizes (0 = slot too small). */
+int msgen_generate_ref(const msgen_batch *b, size_t n, uint8_t *raw, uint8_t *ref, uint8_t *comp, uint32_t *comp_len, int threads);
 int msgen_generate(const msgen_batch *b, size_t n, uint8_t *raw, uint8_t *comp, uint32_t *comp_len, int threads) {
+    return msgen_generate_ref(b, n, raw, NULL, comp, comp_len, threads);
+}
+/* Same; ref (n * lzx.ref_len, may be NULL) receives the LZX DELTA reference data of every unit */
+int msgen_generate_ref(const msgen_batch *b, size_t n, uint8_t *raw, uint8_t *ref, uint8_t *comp, uint32_t *comp_len, int threads) {
     pthread_t *tid; gen_job *jobs; int t;
     vocab_init(b->seed);
     if (threads < 1) threads = 1;
@@ -545,7 +595,7 @@ int msgen_generate(const msgen_batch *b, size_t n, uint8_t *raw, uint8_t *comp, 
     tid = (pthread_t *) calloc((size_t) threads, sizeof(*tid)); jobs = (gen_job *) calloc((size_t) threads, sizeof(*jobs));
     for (t = 0; t < threads; t++) {
         jobs[t].b = b; jobs[t].lo = n * (size_t) t / (size_t) threads; jobs[t].hi = n * (size_t) (t + 1) / (size_t) threads;
-        jobs[t].raw = raw; jobs[t].comp = comp; jobs[t].comp_len = comp_len;
+        jobs[t].raw = raw; jobs[t].ref = ref; jobs[t].comp = comp; jobs[t].comp_len = comp_len;
         if (threads == 1) gen_worker(&jobs[t]); else pthread_create(&tid[t], NULL, gen_worker, &jobs[t]);
     }
     if (threads > 1) for (t = 0; t < threads; t++) pthread_join(tid[t], NULL);

@@ -13,6 +13,8 @@ assert UNIT_DTYPE.itemsize == 32
 
 CODEC_MSZIP, CODEC_QUANTUM, CODEC_LZX = 1, 2, 3
 FLAG_MSZIP_REPAIR = 0x1
+FLAG_LZX_DELTA = 0x2          # include/msgpu.h MSGPU_FLAG_LZX_DELTA
+FLAG_REF_SHIFT = 6            # flags >> 6 = LZX DELTA reference bytes stored in front of the unit's output
 
 # MSPACK_ERR_* (libmspack/mspack/mspack.h:485-507)
 ERR_OK, ERR_ARGS, ERR_OPEN, ERR_READ, ERR_WRITE, ERR_SEEK, ERR_NOMEMORY = 0, 1, 2, 3, 4, 5, 6

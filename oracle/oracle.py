@@ -49,13 +49,16 @@ class Oracle:
                                 ctypes.c_void_p, ctypes.c_int]
 
     def decode_batch(self, units: np.ndarray, in_bytes: np.ndarray, out_size: int | None = None,
-                     threads: int = 1):
-        """Decode every unit.  Returns (out uint8[out_size], status int32[n], seconds)."""
+                     threads: int = 1, out_init: np.ndarray | None = None):
+        """Decode every unit.  Returns (out uint8[out_size], status int32[n], seconds).
+        out_init: initial contents of the output buffer (LZX DELTA reference data in front of the units)."""
         units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
         in_bytes = np.ascontiguousarray(in_bytes, dtype=np.uint8)
         if out_size is None:
             out_size = int((units["out_off"] + units["out_len"]).max()) if len(units) else 0
         out = np.zeros(max(out_size, 1), dtype=np.uint8)
+        if out_init is not None:
+            out[:len(out_init)] = out_init
         status = np.full(len(units), -1, dtype=np.int32)
         secs = self._batch(units.ctypes.data, len(units), in_bytes.ctypes.data, out.ctypes.data,
                            status.ctypes.data, int(threads))

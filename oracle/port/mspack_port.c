@@ -383,7 +383,7 @@ out:
 /* ==========================================================================================
  * LZX  (lzxd.c)
  * ========================================================================================== */
-static const uint8_t lzx_position_slots[7] = { 30, 32, 34, 36, 38, 42, 50 };          /* lzxd.c:209-211 (wb 15..21) */
+static const uint16_t lzx_position_slots[11] = { 30, 32, 34, 36, 38, 42, 50, 66, 98, 162, 290 };   /* lzxd.c:209-211 (wb 15..25) */
 static uint32_t lzx_position_base[290]; static uint8_t lzx_extra_bits[290]; static int lzx_tables_ready;
 static void lzx_make_tables(void) {         /* lzxd.c:199-207: the rule the static tables were generated by */
     unsigned i; uint32_t base = 0;
@@ -463,11 +463,24 @@ static void lzx_e8_frame(uint8_t *data, uint32_t frame_size, int32_t curpos, int
     }
 }
 
+/* lzxd.c:441-444: LZX DELTA has a 16-bit chunk size in front of every frame; ENSURE_BITS(16) + REMOVE_BITS(16).  With an
+ * empty bit buffer (after the raw bytes of an uncompressed block) that is one two-byte fetch from the byte pointer,
+ * wherever it stands, and the buffer is empty again afterwards */
+static int lzx_skip_chunk_size(bitin *b) {
+    if (b->bytemode) { if (!fetch_ok(b, (b->p >> 3) + 2)) return 0; b->p += 16; return 1; }
+    if (!lzx_ensure(b, 16)) return 0;
+    b->p += 16; return 1;
+}
+
 /* lzxd.c:388-771 lzxd_decompress for one whole unit: fresh state, output_length == out_len */
 static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32_t *produced) {
     lzxst *s; lzxframe *frames = NULL; uint32_t nframes_cap, nframes = 0, G = 0, frame = 0, f;
     int ret = ERR_OK;
-    if (u->window_bits < 15 || u->window_bits > 21) return ERR_NOMEM;   /* lzxd_init returns NULL; cabd.c:1255 */
+    const int is_delta = (u->flags & MSGPU_FLAG_LZX_DELTA) != 0;
+    const uint32_t ref_len = MSGPU_UNIT_REF_BYTES(u);                   /* lzxd_set_reference_data, lzxd.c:348-382: sits at out[-ref_len..0) */
+    /* lzxd_init returns NULL (cabd.c:1255 turns that into NOMEMORY): lzxd.c:289-296 */
+    if (is_delta ? (u->window_bits < 17 || u->window_bits > 25) : (u->window_bits < 15 || u->window_bits > 21)) return ERR_NOMEM;
+    if (ref_len && (!is_delta || ref_len > (1u << u->window_bits))) return ERR_ARGS;          /* lzxd.c:355-366 */
     if (!lzx_tables_ready) lzx_make_tables();
     s = (lzxst *) calloc(1, sizeof(lzxst));
     nframes_cap = u->out_len / FRAME + 2;
@@ -482,6 +495,7 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
         uint32_t frame_start = G, frame_size, window_posn_ref;
         int32_t bytes_todo;
         if (u->reset_interval && (frame % u->reset_interval) == 0) lzx_reset_state(s);   /* :423-438 */
+        if (is_delta && !lzx_skip_chunk_size(&s->b)) { ret = ERR_READ; goto out; }      /* :441-444 */
         if (!s->header_read) {                                                          /* :447-453 */
             uint32_t i = 0, j = 0;
             lzx_enter_bits(&s->b);
@@ -575,18 +589,29 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
                             if (s->b.err) { ret = ERR_READ; goto out; }
                             s->R2 = s->R1; s->R1 = s->R0; s->R0 = match_offset;
                         }
+                        if (is_delta && match_length == 257) {                          /* :589-611 longer matches */
+                            uint32_t extra_len;
+                            if (!lzx_ensure(&s->b, 3)) { ret = ERR_READ; goto out; }
+                            if (lzx_peek(&s->b, 1) == 0) { s->b.p += 1; extra_len = lzx_read(&s->b, 8); }
+                            else if (lzx_peek(&s->b, 2) == 2) { s->b.p += 2; extra_len = lzx_read(&s->b, 10) + 0x100; }
+                            else if (lzx_peek(&s->b, 3) == 6) { s->b.p += 3; extra_len = lzx_read(&s->b, 12) + 0x500; }
+                            else { s->b.p += 3; extra_len = lzx_read(&s->b, 15); }
+                            if (s->b.err) { ret = ERR_READ; goto out; }
+                            match_length += extra_len;
+                        }
                         /* :613-634 bounds checks, restated for a linear output buffer: the reference's
                          * window_posn is G modulo the window size, its lzx->offset is frame_start */
                         window_posn_ref = G & (s->window_size - 1);
                         if (window_posn_ref + match_length > s->window_size) { ret = ERR_DECRUNCH; goto out; }
                         eff = match_offset;
                         if (match_offset > window_posn_ref) {
-                            if (match_offset > frame_start) { ret = ERR_DECRUNCH; goto out; }      /* :622-628, no reference data */
+                            if (match_offset > frame_start && match_offset - window_posn_ref > ref_len) { ret = ERR_DECRUNCH; goto out; }   /* :622-628 */
                             if (match_offset - window_posn_ref > s->window_size) { ret = ERR_DECRUNCH; goto out; }
                             if (match_offset > s->window_size) eff = match_offset - s->window_size; /* lands in the current lap */
                         }
                         if ((uint64_t) G + match_length > u->out_len) { ret = ERR_DECRUNCH; goto out; } /* frame overrun, :689-693 */
-                        for (k = 0; k < match_length; k++) { out[G] = (eff <= G) ? out[G - eff] : 0; G++; }
+                        /* bytes in front of the unit: the reference data (the end of the reference's window), zero before that */
+                        for (k = 0; k < match_length; k++) { out[G] = (eff <= G || eff - G <= ref_len) ? *(out + G - eff) : 0; G++; }
                         this_run -= (int32_t) match_length;
                     }
                 }
@@ -618,6 +643,10 @@ static int port_lzx(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32
      * reset point it re-reads the intel header (1 or 33 bits, :447-453) and then tops the bit buffer up to
      * re-align (:696-697) - two places where a unit cut exactly at its last byte reports MSPACK_ERR_READ
      * although every output byte has been produced. */
+    if ((u->out_len % FRAME) == 0 && u->out_len && is_delta) {
+        if (u->reset_interval && (frame % u->reset_interval) == 0) lzx_reset_state(s);
+        if (!lzx_skip_chunk_size(&s->b)) { ret = ERR_READ; goto e8; }                   /* the extra pass reads its chunk size too */
+    }
     if ((u->out_len % FRAME) == 0 && u->reset_interval && (frame % u->reset_interval) == 0) {
         uint64_t bp;
         lzx_enter_bits(&s->b);

@@ -93,10 +93,20 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
         break;
     }
     case MSGPU_CODEC_LZX: {
+        int delta = (u->flags & MSGPU_FLAG_LZX_DELTA) ? 1 : 0;
+        uint32_t ref_len = MSGPU_UNIT_REF_BYTES(u);
         struct lzxd_stream *l = lzxd_init(&mem_system, (struct mspack_file *) &f,
                                           (struct mspack_file *) &f, u->window_bits,
-                                          u->reset_interval, 4096, (off_t) u->out_len, 0);
+                                          u->reset_interval, 4096, (off_t) u->out_len, (char) delta);
         if (!l) { err = MSPACK_ERR_NOMEMORY; break; }
+        if (ref_len) {
+            /* LZX DELTA reference data (oabd.c:336-350): the batch ABI keeps it in front of the unit's output */
+            struct mem_file rf;
+            rf.rdata = out_base + u->out_off - ref_len; rf.rlen = ref_len; rf.rpos = 0;
+            rf.wdata = NULL; rf.wcap = 0; rf.wpos = 0;
+            err = lzxd_set_reference_data(l, &mem_system, (struct mspack_file *) &rf, ref_len);
+            if (err) { lzxd_free(l); break; }
+        }
         err = lzxd_decompress(l, (off_t) u->out_len);
         lzxd_free(l);
         break;

@@ -18,7 +18,8 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
-static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0) {
+template <bool WIDE>
+static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len) {
     std::vector<uint32_t> wa(P2_WIN), wb(P2_WIN);
     uint32_t wbase = 0, wcover = 0; bool loaded = false; int r_lo = 0;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -31,12 +32,12 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         longq[0] = 0;
         for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;
-        for (int lane = 0; lane < 32; lane++) p2_pass_a_literals(c + 16u * lane, c, src);
+        for (int lane = 0; lane < 32; lane++) p2_pass_a_literals<WIDE>(c + 16u * lane, c, src);
         int nlo = P2_WIN;
-        for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
+        for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
         r_lo = nlo;
-        for (int lane = 0; lane < 32; lane++) p2_pass_a_long(lane, c, cend, wa.data(), wb.data(), src, longq);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b(c + 16u * lane, c, size, src, unit_out, g0, w[lane]);
+        for (int lane = 0; lane < 32; lane++) p2_pass_a_long<WIDE>(lane, c, cend, wa.data(), wb.data(), src, longq);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
@@ -71,16 +72,22 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
 }
 
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
-    const int F = frames_per_round > 0 ? frames_per_round : 1;
+    const int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
+    const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
     std::vector<MsFrameInfo> finfo(F);
     MsUnitState st; memset(&st, 0, sizeof(st));
     uint8_t *unit_out = out_base + u->out_off;
     uint32_t nframes_total = (u->out_len + MS_FRAME - 1) / MS_FRAME;
     std::vector<int32_t> e8info(nframes_total + 2, 0);
+    /* the kernels' rule (msgpu.cu run_wave): a wave with LZX DELTA units runs the DELTA / WIDE instantiations, any other
+     * wave the plain ones */
+    const bool wide = force_wide || (u->codec == MSGPU_CODEC_LZX && ((u->flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(u)));
     auto resolve = [&]() {
-        for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size)
-            emul_p2_frame(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0);
+        for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size) {
+            if (wide) emul_p2_frame<true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, MSGPU_UNIT_REF_BYTES(u));
+            else emul_p2_frame<false>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0);
+        }
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
@@ -94,12 +101,12 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
-        typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32> TH;
+        typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F);
-            emul_run(t); t.end(st); resolve();
+            if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            resolve();
         }
         for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
             uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;

@@ -22,11 +22,13 @@ def emul():
     lib = ctypes.CDLL(so)
     lib.emul_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 
-    def run(units, comp, out_bytes, frames_per_round=1, out_shift=0):
+    def run(units, comp, out_bytes, frames_per_round=1, out_shift=0, out_init=None):
         units = np.ascontiguousarray(units)
         comp = np.concatenate([np.ascontiguousarray(comp, dtype=np.uint8), np.zeros(64, np.uint8)])
         out = np.zeros(out_bytes + 128, np.uint8)
         base = (-out.ctypes.data) % 16 + out_shift               # 16-byte aligned + the requested misalignment
+        if out_init is not None:
+            out[base:base + len(out_init)] = out_init
         st = np.full(len(units), -1, np.int32)
         lib.emul_decode_batch(units.ctypes.data, len(units), comp.ctypes.data, out.ctypes.data + base, st.ctypes.data, frames_per_round)
         return out[base:base + out_bytes], st
@@ -102,3 +104,59 @@ def test_device_logic_unaligned_output(emul, oracle_ref, shift):
         o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
         o2, s2 = emul(b.units, b.comp, b.out_bytes, 1, out_shift=shift)
         assert_same(b.units, o1, s1, o2, s2, f"unaligned output {codec} shift {shift}")
+
+
+DELTA_CASES = [dict(window_bits=17), dict(window_bits=17, ref_bytes=20000), dict(window_bits=22, ref_bytes=100000, unit_bytes=100000, block_mode=4, split=2),
+               dict(window_bits=25, unit_bytes=70000, ref_bytes=50000, data="binary", intel=1), dict(window_bits=18, data="zeros", unit_bytes=65536),
+               dict(window_bits=17, unit_bytes=196608, ref_bytes=131072, block_mode=4, block_frames=2), dict(window_bits=17, unit_bytes=196685, ref_bytes=1000, block_mode=3),
+               dict(window_bits=17, unit_bytes=327680, ref_bytes=70000, block_mode=4), dict(window_bits=17, unit_bytes=131072, ref_bytes=1000, reset_interval=1, block_mode=4),
+               dict(window_bits=17, unit_bytes=131072, ref_bytes=1000, reset_interval=1, block_mode=4, slack=4)]
+
+
+@pytest.mark.parametrize("kw", DELTA_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
+def test_device_logic_lzx_delta(emul, oracle_ref, kw):
+    """LZX DELTA units (lzxd_init(is_delta=1), lzxd.c:441-444 chunk sizes, :589-611 long matches, :348-382 + :622-628
+    reference data; windows up to 2^25, units longer than the window): the DELTA / WIDE instantiations against the
+    reference, intact and corrupted."""
+    b = gen.make_batch(CODEC_LZX, 10, delta=1, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4, out_init=b.out_init)
+    for fpr in (1, 2):
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr, out_init=b.out_init)
+        assert_same(b.units, o1, s1, o2, s2, f"delta {kw} F={fpr}")
+    rng = np.random.default_rng(3)
+    comp, units = b.comp.copy(), b.units.copy()
+    for i, u in enumerate(units):
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        if i % 2 == 0:
+            comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4, out_init=b.out_init)
+    o2, s2 = emul(units, comp, b.out_bytes, 1, out_init=b.out_init)
+    assert_same(units, o1, s1, o2, s2, f"corrupt delta {kw}")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(block_mode=4, split=3), dict(unit_bytes=65536, reset_interval=2, block_mode=4), dict(window_bits=15, unit_bytes=100000, block_mode=4)],
+                         ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
+def test_plain_lzx_through_the_delta_instantiation(emul, oracle_ref, kw):
+    """A wave that holds LZX DELTA units runs every LZX unit through the DELTA kernels (msgpu.cu run_wave)."""
+    b = gen.make_batch(CODEC_LZX, 10, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+    o2, s2 = emul(b.units, b.comp, b.out_bytes, 0x101)
+    assert_same(b.units, o1, s1, o2, s2, f"forced wide {kw}")
+
+
+def test_delta_argument_errors(emul, oracle_ref):
+    """lzxd_init refuses window_bits outside 17..25 for DELTA (NULL -> NOMEMORY), lzxd_set_reference_data refuses reference data
+    on a plain stream or longer than the window (ARGS)."""
+    b = gen.make_batch(CODEC_LZX, 4, delta=1, window_bits=17, ref_bytes=4096)
+    u = b.units.copy()
+    u["window_bits"][0] = 16
+    u["window_bits"][1] = 26
+    u["flags"][2] = (4096 << 6)                      # reference data without the DELTA flag
+    u["flags"][3] = 0x2 | ((1 << 17) + 16 << 6)      # longer than the window
+    u["out_off"][3] += (1 << 17) + 16
+    o1, s1, _ = oracle_ref.decode_batch(u, b.comp, b.out_bytes + (1 << 18), threads=1, out_init=b.out_init)
+    o2, s2 = emul(u, b.comp, b.out_bytes + (1 << 18), 1, out_init=b.out_init)
+    assert list(s1) == [6, 6, 1, 1]
+    assert list(s2) == list(s1)

@@ -74,3 +74,29 @@ def test_port_matches_reference_on_corrupt_streams(oracle_ref, oracle_port):
         o1, s1, _ = oracle_ref.decode_batch(b.units, comp, b.out_bytes)
         o2, s2, _ = oracle_port.decode_batch(b.units, comp, b.out_bytes)
         assert_same(b.units, o1, s1, o2, s2, f"corrupt {codec}")
+
+
+DELTA_CASES = [dict(window_bits=17, ref_bytes=20000), dict(window_bits=25, unit_bytes=70000, ref_bytes=50000, data="binary", intel=1),
+               dict(window_bits=18, data="zeros", unit_bytes=65536), dict(window_bits=17, unit_bytes=327680, ref_bytes=70000, block_mode=4, block_frames=2),
+               dict(window_bits=17, unit_bytes=131072, ref_bytes=1000, reset_interval=1, block_mode=4)]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs the reference oracle")
+@pytest.mark.parametrize("kw", DELTA_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
+def test_port_matches_reference_lzx_delta(oracle_ref, oracle_port, kw):
+    """LZX DELTA (is_delta=1 + lzxd_set_reference_data): the port against the reference, intact and corrupted."""
+    b = gen.make_batch(CODEC_LZX, 12, delta=1, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4, out_init=b.out_init)
+    o2, s2, _ = oracle_port.decode_batch(b.units, b.comp, b.out_bytes, threads=4, out_init=b.out_init)
+    assert_same(b.units, o1, s1, o2, s2, f"delta {kw}")
+    rng = np.random.default_rng(13)
+    comp, units = b.comp.copy(), b.units.copy()
+    for i, u in enumerate(units):
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        if i % 2 == 0:
+            comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4, out_init=b.out_init)
+    o2, s2, _ = oracle_port.decode_batch(units, comp, b.out_bytes, threads=4, out_init=b.out_init)
+    assert_same(units, o1, s1, o2, s2, f"corrupt delta {kw}")
