@@ -48,6 +48,8 @@ __device__ __forceinline__ void p1_run(Lane &t)
     }
 }
 
+#define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
+#define MISC_RING  1024u
 template <int NT, int HEADN>
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
@@ -64,7 +66,10 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
                 a.finfo + (size_t) slot * a.F, a.F);
     }
     p1_run(t);
-    if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
+    if (valid) {
+        t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u);
+        if (t.f > 0 && a.finfo[(size_t) slot * a.F + t.f - 1].valid == 2u) a.not_done[MISC_RING + a.sub] = 1u;          /* frames for k_p2_ring (ring is sticky) */
+    }
 }
 
 /* DELTA = the instantiation for waves that hold LZX DELTA units (it decodes plain LZX units as well) */
@@ -123,9 +128,36 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const 
     const uint32_t ref_len = (WIDE && a.units[slot].codec == MSGPU_CODEC_LZX) ? MSGPU_UNIT_REF_BYTES(&a.units[slot]) : 0u;
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
-        if (!fi.valid || fi.size == 0) continue;
+        if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
         p2_resolve_frame<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
+    }
+}
+
+/* MSZIP frames decoded after a block shorter than 32 KiB (MsFrameInfo::valid == 2): the same resolve, with sources in front of
+ * the frame looked up through the ring history P1 attached to the frame (msgpu_p2.cuh "MSZIP ring history").  Runs after
+ * k_p2_resolve on the same stream; leaves at once unless P1 flagged such frames in this sub-wave. */
+__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_ring(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
+{
+    __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
+    __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
+    __shared__ uint32_t s_longq[P2_WARPS][P2_LONG_MAX + 1];
+    __shared__ uint32_t s_hist[P2_WARPS][P2_HIST_WORDS + 15];
+    if (a.not_done[MISC_RING + a.sub] == 0) return;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t si = first + blockIdx.x * P2_WARPS + warp;
+    if (si >= nslots) return;
+    uint32_t slot = slots[si];
+    uint8_t *unit_out = a.out_base + a.units[slot].out_off;
+    for (int f = 0; f < a.F; f++) {
+        MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
+        if (fi.valid != 2u || fi.size == 0) continue;
+        __syncwarp();
+        const uint32_t *sn = reinterpret_cast<const uint32_t *>(a.recs + ((size_t) slot * a.F + f) * MS_MAXREC + P2_HIST_REC);
+        for (int j = lane; j < (int) P2_HIST_WORDS; j += 32) s_hist[warp][j] = sn[j];
+        __syncwarp();
+        p2_resolve_frame<false, true>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+                                      s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], 0u, s_hist[warp]);
     }
 }
 
@@ -359,7 +391,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(ctx->ustate.reserve((size_t) n * sizeof(MsUnitState)), "alloc state");
     CK(ctx->recs.reserve((size_t) n * F * MS_MAXREC * sizeof(MsRec)), "alloc records");
     CK(ctx->finfo.reserve((size_t) n * F * sizeof(MsFrameInfo)), "alloc frame info");
-    CK(ctx->misc.reserve(4096), "alloc misc");
+    CK(ctx->misc.reserve(MISC_WORDS * 4), "alloc misc");
     CK(ctx->order.reserve((size_t) (2 * n + 3) * sizeof(uint32_t)), "alloc order");
     if (nz) CK(ctx->aux_zip.reserve((size_t) ((nz + 31) / 32) * ZIP_AUX_BYTES), "alloc mszip aux");
     if (nl) {
@@ -380,7 +412,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         CK(cudaMemsetAsync(ctx->e8info.p, 0, (size_t) (e8total + 1) * sizeof(int32_t), s), "clear e8 info");
     }
     CK(cudaMemsetAsync(ctx->ustate.p, 0, (size_t) n * sizeof(MsUnitState), s), "clear state");
-    CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, s), "clear counters");
+    CK(cudaMemsetAsync(ctx->misc.p, 0, MISC_WORDS * 4, s), "clear counters");
     if (any_delta && h_out) {
         /* host buffers: the reference data of the LZX DELTA units lives in the caller's output buffer, in front of each unit */
         for (uint32_t i = 0; i < n; i++) {
@@ -473,7 +505,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             ZIPC_VARIANTS(LAUNCHZC)
 #undef LAUNCHZC
             mark(0, st); mark(1, st);
-            p2_launch(w, d_ord_z, f0, f1, st); ctx->launches += 2; mark(1, st); }
+            p2_launch(w, d_ord_z, f0, f1, st);
+            k_p2_ring<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
+            ctx->launches += 3; mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
 #define LAUNCHC(id, nt, hn) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));

@@ -11,6 +11,7 @@
  */
 #pragma once
 #include "msgpu_core.cuh"
+#include "msgpu_p2.cuh"        /* P2_HIST_K: the ring history handed to the resolve stage */
 
 /* per-warp auxiliary block in global scratch (interleaved by lane) */
 #define ZIP_AUX_LENS      0                              /* u8  [320][32]  literal/length + distance code lengths */
@@ -19,7 +20,8 @@
 #define ZIP_AUX_BSORT     (ZIP_AUX_DSORT + 32 * 32 * 2)  /* u16 [32][32]  */
 #define ZIP_AUX_LIMIT     (ZIP_AUX_BSORT + 32 * 32 * 2)  /* u32 [3][20][32] */
 #define ZIP_AUX_OFFS      (ZIP_AUX_LIMIT + 3 * 20 * 32 * 4) /* u16 [3][20][32] */
-#define ZIP_AUX_BYTES     (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)
+#define ZIP_AUX_HIST      (ZIP_AUX_OFFS + 3 * 20 * 32 * 2)  /* u32 [2 * P2_HIST_K + 1][32]  ring history {len, g0}, most recent first; then n | ring << 8 */
+#define ZIP_AUX_BYTES     (ZIP_AUX_HIST + (2 * P2_HIST_K + 1) * 32 * 4)
 
 /* HEADN = literal/length symbols (shortest codes first) kept in shared memory */
 template <int NT, int HEADN>
@@ -44,6 +46,14 @@ struct ZipLaneC {
     MsEmit em;
     uint32_t phase, q, last_block, produced, frame, done; int32_t status;
     int f, max_frames;
+    /* The ring history of the reference's 32 KiB window (msgpu_p2.cuh "MSZIP ring history") lives entirely in the lane's aux
+     * memory - it is touched at frame boundaries only and must not cost the decode loop a register: entries {len, g0}, most
+     * recent block first, then one word n | ring << 8; ring = a block shorter than 32 KiB has been followed by another one, from
+     * then on every frame carries a snapshot of the history (in the spare tail of its record array) for k_p2_ring */
+    MS_M uint32_t *hist_ptr() const {       /* the aux block is 32-byte aligned and lens = aux + lane */
+        const uintptr_t lane = reinterpret_cast<uintptr_t>(lens) & 31u;
+        return reinterpret_cast<uint32_t *>(lens - lane + ZIP_AUX_HIST) + lane;
+    }
 
     MS_M void bind(ZipSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
         lbo = sh->lbo + tid; dbo = sh->dbo + tid; lhead = sh->lhead + tid; dhead = sh->dhead + tid; blim = sh->blim + tid; cnt = sh->cnt + tid;
@@ -55,6 +65,45 @@ struct ZipLaneC {
         uint16_t *off = reinterpret_cast<uint16_t *>(aux_warp + ZIP_AUX_OFFS) + lane;
         la.limit = lim; da.limit = lim + 20 * 32; ba.limit = lim + 40 * 32;
         la.offs = off; da.offs = off + 20 * 32; ba.offs = off + 40 * 32;
+    }
+
+    /* the block that just ended wrote window[0, len): it shadows every earlier block that was not longer */
+    MS_M bool hist_push(uint32_t len, uint32_t g0) {
+        if (len == 0) return true;
+        uint32_t *hist = hist_ptr();
+        const uint32_t stw = hist[2 * P2_HIST_K * 32], hist_n = stw & 0xFFu, ring = stw & ~0xFFu;
+        if (len >= MS_FRAME) { hist[0] = len; hist[32] = g0; hist[2 * P2_HIST_K * 32] = ring | 1u; return true; }      /* the usual case: nothing older shows through */
+        /* lengths grow with the index, so the entries that stay (longer than the new block) are a suffix [j0, hist_n):
+         * new history = {len, g0} followed by that suffix */
+        uint32_t j0 = 0;
+#pragma unroll 1
+        while (j0 < hist_n && hist[2 * j0 * 32] <= len) j0++;
+        const uint32_t keep = hist_n - j0;
+        if (keep + 1 > P2_HIST_K) { fail(MS_EDECRUNCH); return false; }        /* deeper than the history can describe: refuse rather than guess */
+        if (j0 == 0) {
+#pragma unroll 1
+            for (uint32_t k = keep; k > 0; k--) { hist[2 * k * 32] = hist[2 * (k - 1) * 32]; hist[(2 * k + 1) * 32] = hist[(2 * (k - 1) + 1) * 32]; }
+        }
+        else if (j0 > 1) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < keep; k++) { hist[2 * (k + 1) * 32] = hist[2 * (j0 + k) * 32]; hist[(2 * (k + 1) + 1) * 32] = hist[(2 * (j0 + k) + 1) * 32]; }
+        }
+        hist[0] = len; hist[32] = g0;
+        hist[2 * P2_HIST_K * 32] = ring | (keep + 1);
+        return true;
+    }
+    /* frame prologue: does this frame need the ring instantiation of the resolve stage?  If so leave it a snapshot */
+    MS_M uint32_t hist_snapshot(MsRec *frame_recs) {
+        uint32_t *hist = hist_ptr();
+        uint32_t stw = hist[2 * P2_HIST_K * 32]; const uint32_t hist_n = stw & 0xFFu;
+        if (hist_n && !(hist_n == 1 && hist[0] >= MS_FRAME)) stw |= 0x100u;       /* an earlier block was short: sticky */
+        if (!(stw & 0x100u)) return 0;
+        hist[2 * P2_HIST_K * 32] = stw;
+        uint32_t *sn = reinterpret_cast<uint32_t *>(frame_recs + P2_HIST_REC);
+        sn[0] = hist_n;
+#pragma unroll 1
+        for (uint32_t j = 0; j < 2 * hist_n; j++) sn[1 + j] = hist[j * 32];
+        return 1;
     }
 
     /* next 16 stream bits, first bit on top (deflate packs Huffman codes starting at the code's MSB) */
@@ -185,11 +234,13 @@ struct ZipLaneC {
         if (q > MS_FRAME) { fail(MS_EDECRUNCH); return; }
         uint32_t n = ms_min(u->out_len - produced, q);
         emit_end(em, q);
-        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced; fi.valid = 1;
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced;
+        fi.valid = (frame && hist_snapshot(recs + (size_t) f * MS_MAXREC)) ? 2u : 1u;                    /* 2: resolved by k_p2_ring */
         finfo[f] = fi;
+        const uint32_t g0 = produced;
         produced += n; frame++; f++;
         if (produced >= u->out_len) { done = 1; phase = PH_IDLE; }
-        else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+        else if (hist_push(q, g0)) phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
     }
 
     /* the rare, divergent work: run until the lane is decoding symbols or has nothing left to do */
@@ -260,6 +311,7 @@ struct ZipLaneC {
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         if (!st.started) {
             done = 0; status = 0; produced = 0; frame = 0;
+            hist_ptr()[2 * P2_HIST_K * 32] = 0;
             ms_bits_init(b, in_base + unit->in_off, unit->in_len);
             if (unit->out_len == 0) done = 1;
         }

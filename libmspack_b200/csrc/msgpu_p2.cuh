@@ -44,6 +44,23 @@ MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t off, uint32_t len) {
     return pos - off + (kk % off) + P2_SBIAS;              /* overlapping match: fold onto the seed bytes in front of it */
 }
 
+/* MSZIP ring history (RING instantiation).  The reference's MSZIP window is a 32 KiB ring that every CK block starts
+ * writing at index 0 (mszipd.c:416-417), and a match that reaches in front of its block reads window[32768 + posn - dist]
+ * (:267-268): whatever the most recent EARLIER block that was long enough left at that index.  As long as every earlier
+ * block is a full 32 KiB that is simply the previous block, i.e. the bytes in front of the frame in the linear output; after
+ * a shorter block it is not.  P1 (ZipLaneC::frame_start) gives every frame decoded after a short block a snapshot of the
+ * ring's history: n entries {len, g0}, most recent block first, lengths strictly increasing - index i belongs to the first
+ * entry with len > i and lives at unit position g0 + i; an index no entry covers was never written (reads as zero). */
+#define P2_HIST_K     16        /* more than 16 blocks in a row, each shorter than the one before: the unit fails */
+#define P2_HIST_WORDS (1 + 2 * P2_HIST_K)      /* n, then {len, g0} pairs */
+#define P2_HIST_REC   (MS_MAXREC - 17)         /* the snapshot sits in the spare tail of the frame's record array (an MSZIP frame has at
+                                                * most 32768 / 3 records) */
+MS_D uint32_t p2_ring_lookup(const uint32_t *hist, uint32_t i, const uint8_t *unit_out) {
+    const uint32_t n = hist[0];
+    for (uint32_t j = 0; j < n; j++) if (hist[1 + 2 * j] > i) return unit_out[(size_t) hist[2 + 2 * j] + i];
+    return 0;
+}
+
 #define P2_LONG      48      /* a match covering at least this many positions of the chunk is filled by the whole warp */
 #define P2_LONG_MAX  16
 
@@ -113,8 +130,9 @@ MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa
  * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
  * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero - except for the ref_len bytes
  * directly in front of the unit, the reference data of an LZX DELTA unit (WIDE only). */
-template <bool WIDE>
-MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0)
+template <bool WIDE, bool RING = false>
+MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0,
+                    const uint32_t *hist = nullptr)
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
@@ -135,16 +153,20 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
-        if (k < n && x >= ulim) v = obase[x];
+        if (RING) {
+            /* a source in front of the frame is the ring index 32768 + (position - frame start), see p2_ring_lookup */
+            if (k < n) v = x >= (uint32_t) P2_SBIAS ? obase[x] : p2_ring_lookup(hist, MS_FRAME + x - (uint32_t) P2_SBIAS, unit_out);
+        }
+        else if (k < n && x >= ulim) v = obase[x];
         w[k >> 2] |= v << (8 * (k & 3));
     }
 }
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-template <bool WIDE>
+template <bool WIDE, bool RING = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len)
+                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     int r_lo = 0;                                              /* first window record ending beyond the chunk start */
@@ -169,7 +191,7 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         __syncwarp();
         p2_pass_a_long<WIDE>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b<WIDE>(q0, c, size, src, unit_out, g0, w, ref_len);
+        p2_pass_b<WIDE, RING>(q0, c, size, src, unit_out, g0, w, ref_len, hist);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);

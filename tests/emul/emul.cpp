@@ -18,8 +18,8 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
-template <bool WIDE>
-static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len) {
+template <bool WIDE, bool RING = false>
+static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr) {
     std::vector<uint32_t> wa(P2_WIN), wb(P2_WIN);
     uint32_t wbase = 0, wcover = 0; bool loaded = false; int r_lo = 0;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -37,7 +37,7 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
         r_lo = nlo;
         for (int lane = 0; lane < 32; lane++) p2_pass_a_long<WIDE>(lane, c, cend, wa.data(), wb.data(), src, longq);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE, RING>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
@@ -84,15 +84,18 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
      * wave the plain ones */
     const bool wide = force_wide || (u->codec == MSGPU_CODEC_LZX && ((u->flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(u)));
     auto resolve = [&]() {
-        for (int f = 0; f < F; f++) if (finfo[f].valid && finfo[f].size) {
+        /* k_p2_resolve takes the frames with valid == 1, then k_p2_ring those with valid == 2 */
+        for (int f = 0; f < F; f++) if (finfo[f].valid == 1 && finfo[f].size) {
             if (wide) emul_p2_frame<true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, MSGPU_UNIT_REF_BYTES(u));
             else emul_p2_frame<false>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0);
         }
+        for (int f = 0; f < F; f++) if (finfo[f].valid == 2 && finfo[f].size)
+            emul_p2_frame<false, true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0, reinterpret_cast<const uint32_t *>(recs.data() + (size_t) f * MS_MAXREC + P2_HIST_REC));
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH;
-        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, ZIP_AUX_BYTES);
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) aligned_alloc(64, (ZIP_AUX_BYTES + 63) & ~(size_t) 63); memset(aux, 0, ZIP_AUX_BYTES);   /* 32-byte aligned like the device's */
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             TH t; t.bind(sh, 0, aux, 0);
             t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F);

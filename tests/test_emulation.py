@@ -10,7 +10,7 @@ import pytest
 
 from libmspack_b200 import gen
 from libmspack_b200.units import CODEC_LZX, CODEC_MSZIP, CODEC_QUANTUM
-from util import assert_same, golden_manifest, golden_unit
+from util import RING_CASES, assert_same, golden_manifest, golden_unit, ring_batch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -160,3 +160,19 @@ def test_delta_argument_errors(emul, oracle_ref):
     o2, s2 = emul(u, b.comp, b.out_bytes + (1 << 18), 1, out_init=b.out_init)
     assert list(s1) == [6, 6, 1, 1]
     assert list(s2) == list(s1)
+
+
+def test_device_logic_mszip_short_blocks(emul, oracle_ref):
+    """MSZIP folders with blocks shorter than 32 KiB in the middle: matches that reach in front of their block see the
+    reference's 32 KiB ring (mszipd.c:267-268), not the linear output (msgpu_p2.cuh "MSZIP ring history", k_p2_ring)."""
+    b, raws = ring_batch(RING_CASES)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+    assert (s1 == 0).all()
+    for i, r in enumerate(raws):
+        assert b.unit_output(o1, i).tobytes() == r                  # the construction is what the reference decodes
+    for fpr in (1, 2):
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr)
+        deep = len(RING_CASES) - 1                                  # beyond the history depth the device refuses loudly
+        assert int(s2[deep]) == 11
+        s2[deep] = 0
+        assert_same(b.units[:deep], o1, s1[:deep], o2, s2[:deep], f"ring F={fpr}")

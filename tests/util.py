@@ -41,3 +41,46 @@ def assert_same(units, out_a, st_a, out_b, st_b, what=""):
         if not np.array_equal(out_a[lo:lo + n], out_b[lo:lo + n]):
             d = np.nonzero(out_a[lo:lo + n] != out_b[lo:lo + n])[0]
             raise AssertionError(f"{what}: unit {i} differs at byte {d[0]} ({len(d)} bytes differ)")
+
+
+def mszip_ring_folder(lens, seed=0):
+    """One MSZIP folder whose CK blocks inflate to the given lengths (<= 32768 each) and reference each other across block
+    boundaries the way the reference's window allows: a block starts writing the 32 KiB ring at index 0 (mszipd.c:416-417)
+    and a match reaching in front of the block reads window[32768 + posn - dist] (:267-268), i.e. after a SHORT block the
+    bytes older blocks left further up the ring, not the end of the previous block.  Returns (compressed, expected output)."""
+    import zlib
+    from libmspack_b200 import gen
+    raw = gen.raw_units(1, int(sum(lens)) + 1, data="text", first_unit=seed).tobytes()
+    win, comp, out, pos = bytearray(32768), b"", b"", 0
+    for k, n in enumerate(lens):
+        data = raw[pos:pos + n]
+        pos += n
+        kw = {"zdict": bytes(win)} if k else {}      # distance d at position 0 reads win[32768 - d]: the ring, read linearly
+        c = zlib.compressobj(6, zlib.DEFLATED, -15, **kw)
+        comp += b"CK" + c.compress(data) + c.flush()
+        out += data
+        win[0:n] = data
+    return comp, out
+
+
+def ring_batch(cases):
+    """A batch of mszip_ring_folder() units."""
+    from libmspack_b200.units import UNIT_DTYPE
+    from libmspack_b200 import gen
+    units = np.zeros(len(cases), dtype=UNIT_DTYPE)
+    comps, raws, ioff, ooff = [], [], 0, 0
+    for i, lens in enumerate(cases):
+        comp, out = mszip_ring_folder([int(x) for x in lens], seed=i)
+        units[i] = (1, 0, 0, 0, ioff, len(comp), len(out), ooff)
+        pad = (-len(comp)) % 4
+        comps.append(comp + b"\0" * pad)
+        raws.append(out)
+        ioff += len(comp) + pad
+        ooff += (len(out) + 15) & ~15
+    comp = np.frombuffer(b"".join(comps) + b"\0" * 16, dtype=np.uint8).copy()
+    return gen.Batch(units, comp, None, ooff), raws
+
+
+RING_CASES = [[32768, 100, 32768], [32768, 100, 50, 20000, 32768, 7], [500, 400, 300, 200, 100, 50, 25, 12, 6, 3, 32768, 1000], [32768, 32768, 1, 32768],
+              [15506, 16772, 24746, 31145, 1143, 4724, 9000, 32768, 32768, 31, 4000], [1, 2, 3, 4, 5, 32768, 5, 4, 3, 2, 1, 30000],
+              [3000 - 100 * k for k in range(20)] + [32768]]       # the last one: 20 blocks, each shorter than the one before (deeper than P2_HIST_K)
