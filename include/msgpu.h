@@ -48,6 +48,18 @@ extern "C" {
                                        * of the unit, at [out_off - n, out_off): the reference preloads them at the end of its
                                        * window, i.e. logically just before the first output byte */
 #define MSGPU_UNIT_REF_BYTES(u) ((u)->flags >> MSGPU_FLAG_REF_SHIFT)
+/* MSZIP block chains (intra-folder parallelism).  The CK blocks of one MSZIP folder are independent
+ * bitstreams - only their match SOURCES reach into the previous block's 32 KiB (mszipd.c:267-268) - so a caller that knows
+ * where every block starts (a cabinet's CFDATA table does) can hand them over as consecutive units: CHAIN_FIRST for the first
+ * block, CHAIN_NEXT for each following one.  The entropy stage then decodes all blocks in parallel; the resolve stage walks a
+ * chain in order.  Rules (msgpu_decode_batch_* returns MSGPU_ERR_ARGS otherwise): codec MSZIP; a NEXT unit directly follows
+ * its predecessor in the unit array; every unit but the chain's last produces exactly 32768 bytes; out_off continues where
+ * the predecessor's output ends.  Each unit must be exactly one CK block that uses up exactly its in_len bytes and produces
+ * exactly out_len bytes; a unit for which that does not hold (or that fails in any other way) reports
+ * MSGPU_ERR_CHAIN, and the caller decodes the folder as ONE plain unit to get the reference's result (msgpu_cab.cu does). */
+#define MSGPU_FLAG_CHAIN_FIRST  0x4u
+#define MSGPU_FLAG_CHAIN_NEXT   0x8u
+#define MSGPU_ERR_CHAIN         100   /* not an MSPACK_ERR_*: "decode this chain as one stream instead" */
 
 /* One independent compressed unit.  32 bytes, no padding. */
 typedef struct msgpu_unit {

@@ -161,6 +161,30 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_ring(WaveArgs a, const uin
     }
 }
 
+/* MSZIP block chains (include/msgpu.h MSGPU_FLAG_CHAIN_*): one warp resolves the blocks of one chain in order - block k's
+ * matches may reach into block k-1's 32 KiB, which lies directly in front of it in the output.  chains[2i] = position of the
+ * chain's first unit in the MSZIP list, chains[2i+1] = number of units.  A chain stops at its first unit that did not come out
+ * of P1 as a chain frame (the whole chain is then decoded again as one stream by the caller). */
+__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_chain(WaveArgs a, const uint32_t *slots, const uint32_t *chains, uint32_t nchains)
+{
+    __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
+    __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
+    __shared__ uint32_t s_longq[P2_WARPS][P2_LONG_MAX + 1];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ci = blockIdx.x * P2_WARPS + warp;
+    if (ci >= nchains) return;
+    const uint32_t first = chains[2 * ci], count = chains[2 * ci + 1];
+    for (uint32_t k = 0; k < count; k++) {
+        const uint32_t slot = slots[first + k];
+        MsFrameInfo fi = a.finfo[(size_t) slot * a.F];
+        if (fi.valid != 3u) break;
+        if (fi.size == 0) continue;
+        p2_resolve_frame<true>(lane, a.recs + (size_t) slot * a.F * MS_MAXREC, fi.nrec, fi.size, a.out_base + a.units[slot].out_off, fi.g0,
+                               s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], k ? MS_FRAME : 0u);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, const int32_t *e8info, const uint32_t *e8base)
 {
     uint32_t ti = first + blockIdx.x * 8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
@@ -229,11 +253,11 @@ struct msgpu_ctx {
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
-    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status;
+    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     size_t bytes_held() const {
         return units.cap + ustate.cap + recs.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
-               save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap;
+               save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap + chains.cap;
     }
 };
 
@@ -283,7 +307,7 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
-                       &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status };
+                       &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status, &c->chains };
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
@@ -346,12 +370,16 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
                     int32_t *d_status, cudaStream_t s, const uint8_t *h_in = nullptr, uint8_t *h_out = nullptr)
 {
     const uint32_t n = (uint32_t) (hi - lo);
-    std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base;
+    std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base, chains;
     uint32_t maxfr = 1, e8total = 0; bool any_zip = false, any_delta = false;
     for (uint32_t i = 0; i < n; i++) {
         const msgpu_unit &u = h_units[lo + i];
         ord[u.codec].push_back(i);
         if (u.codec == MSGPU_CODEC_LZX && ((u.flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(&u))) any_delta = true;
+        if (u.codec == MSGPU_CODEC_MSZIP) {          /* block chains: runs of consecutive entries of the MSZIP list */
+            if (u.flags & MSGPU_FLAG_CHAIN_FIRST) { chains.push_back((uint32_t) ord[1].size() - 1); chains.push_back(1); }
+            else if ((u.flags & MSGPU_FLAG_CHAIN_NEXT) && !chains.empty()) chains.back()++;
+        }
         uint32_t fr = frames_of(u); if (fr > maxfr) maxfr = fr;
         if (u.codec == MSGPU_CODEC_LZX) { e8base.push_back(e8total); e8total += fr ? fr : 1; }
         if (u.codec == MSGPU_CODEC_MSZIP) any_zip = true;
@@ -372,7 +400,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
     const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* mixed batches: 10752 = lcm of the 384/448/512-lane CTA shapes */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
-    if (h_in && !env) {
+    const uint32_t nchains = (uint32_t) (chains.size() / 2);
+    if (nchains) subsz = 0x40000000u;          /* a chain is resolved in order after ALL its blocks left P1: one sub-wave */
+    if (h_in && !env && !nchains) {
         /* host buffers: cut the wave into ~16 sub-waves; their H2D copies queue on one copy stream, their kernels run on
          * eight compute streams as soon as "their" input has landed, their D2H copies queue on a second copy stream as soon as
          * "their" output is complete - so the D2H engine, which carries twice the bytes of everything else, starts after one
@@ -394,6 +424,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(ctx->misc.reserve(MISC_WORDS * 4), "alloc misc");
     CK(ctx->order.reserve((size_t) (2 * n + 3) * sizeof(uint32_t)), "alloc order");
     if (nz) CK(ctx->aux_zip.reserve((size_t) ((nz + 31) / 32) * ZIP_AUX_BYTES), "alloc mszip aux");
+    if (nchains) CK(ctx->chains.reserve(chains.size() * sizeof(uint32_t)), "alloc chains");
     if (nl) {
         CK(ctx->aux_lzx.reserve((size_t) ((nl + 31) / 32) * LZX_AUX_BYTES), "alloc lzx aux");
         CK(ctx->e8info.reserve((size_t) (e8total + 1) * sizeof(int32_t)), "alloc e8 info");
@@ -405,6 +436,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     uint32_t *d_ord_z = d_order, *d_ord_q = d_order + nz, *d_ord_l = d_order + nz + nq;
     CK(cudaMemcpyAsync(ctx->units.p, h_units + lo, (size_t) n * sizeof(msgpu_unit), cudaMemcpyHostToDevice, s), "copy units");
     if (nz) CK(cudaMemcpyAsync(d_ord_z, ord[1].data(), nz * 4, cudaMemcpyHostToDevice, s), "copy order");
+    if (nchains) CK(cudaMemcpyAsync(ctx->chains.p, chains.data(), chains.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s), "copy chains");
     if (nq) CK(cudaMemcpyAsync(d_ord_q, ord[2].data(), nq * 4, cudaMemcpyHostToDevice, s), "copy order");
     if (nl) {
         CK(cudaMemcpyAsync(d_ord_l, ord[3].data(), nl * 4, cudaMemcpyHostToDevice, s), "copy order");
@@ -507,7 +539,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);
             k_p2_ring<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
-            ctx->launches += 3; mark(1, st); }
+            ctx->launches += 3;
+            if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
+            mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
 #define LAUNCHC(id, nt, hn) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
@@ -597,6 +631,15 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
         if (u.in_len >= 0x7FFFFFF0u) return fail(ctx, MSGPU_ERR_ARGS, "unit input too large");
         if (u.out_off & 15u) return fail(ctx, MSGPU_ERR_ARGS, "out_off must be a multiple of 16");
         if (u.codec == MSGPU_CODEC_LZX && MSGPU_UNIT_REF_BYTES(&u) > u.out_off) return fail(ctx, MSGPU_ERR_ARGS, "LZX DELTA reference data must lie in front of the unit inside the output buffer");
+        if (u.flags & (MSGPU_FLAG_CHAIN_FIRST | MSGPU_FLAG_CHAIN_NEXT)) {           /* MSZIP block chains, include/msgpu.h */
+            if (u.codec != MSGPU_CODEC_MSZIP || (u.flags & MSGPU_FLAG_CHAIN_FIRST && u.flags & MSGPU_FLAG_CHAIN_NEXT)) return fail(ctx, MSGPU_ERR_ARGS, "bad chain flags");
+            if (u.flags & MSGPU_FLAG_CHAIN_NEXT) {
+                if (i == 0) return fail(ctx, MSGPU_ERR_ARGS, "chain without a first unit");
+                const msgpu_unit &p = units[i - 1];
+                if (!(p.flags & (MSGPU_FLAG_CHAIN_FIRST | MSGPU_FLAG_CHAIN_NEXT)) || p.codec != MSGPU_CODEC_MSZIP || p.out_len != MS_FRAME || u.out_off != p.out_off + MS_FRAME)
+                    return fail(ctx, MSGPU_ERR_ARGS, "a chain unit must directly follow a 32768-byte unit of its chain");
+            }
+        }
     }
     /* wave size from the scratch budget */
     uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
@@ -605,10 +648,13 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
-    for (size_t lo = 0; lo < n; lo += slots) {
+    for (size_t lo = 0; lo < n;) {
         size_t hi = lo + slots < n ? lo + slots : n;
+        while (hi < n && hi > lo && (units[hi].flags & MSGPU_FLAG_CHAIN_NEXT)) hi--;       /* a chain stays inside one wave */
+        if (hi == lo) return fail(ctx, MSGPU_ERR_NOMEMORY, "a block chain does not fit the scratch budget");
         int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, h_in, h_out);
         if (r) return r;
+        lo = hi;
     }
     return 0;
 }

@@ -217,7 +217,7 @@ extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan,
     CKC(cudaMalloc(&B.out, plan->out_bytes + 16));
     CKC(cudaMalloc(&B.blocks, (nb + 1) * sizeof(msgpu_cab_block)));
     CKC(cudaMalloc(&B.ok, nb + 1));
-    CKC(cudaMalloc(&B.status, (nf + 1) * sizeof(int32_t)));
+    CKC(cudaMalloc(&B.status, (nf + nb + 1) * sizeof(int32_t)));         /* one per unit: a folder, or a block of a chain */
     CKC(cudaMemcpyAsync(B.image, image, image_bytes, cudaMemcpyHostToDevice, B.st));
     CKC(cudaMemsetAsync(B.packed, 0, plan->packed_bytes + 16, B.st));
     std::vector<uint8_t> ok(nb, 1);
@@ -233,7 +233,14 @@ extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan,
     /* unit table: one unit per codec folder; its input ends in front of the first block the reference would refuse to
      * hand to the codec (bad checksum, or the block the scan stopped at), so the codec runs exactly as far as the
      * reference's would and reports MSGPU_ERR_READ when it wants more */
+    /* MSZIP folders of several CFDATA blocks go in as block chains (include/msgpu.h MSGPU_FLAG_CHAIN_*): every
+     * CFDATA block of a well-formed folder is one CK block, so the entropy stage decodes all blocks of all folders at once
+     * instead of one block after the other.  Only a folder whose every block decodes as exactly one CK block is accepted that
+     * way; any other folder (and every folder the scan or a checksum already objects to) is decoded as ONE stream, which is
+     * the reference's own way of reading it and yields the reference's error codes. */
+    const bool use_chains = !getenv("MSGPU_CAB_NOCHAIN");
     std::vector<msgpu_unit> units; std::vector<size_t> unit_folder; std::vector<int32_t> block_err(nf, 0);
+    std::vector<uint8_t> chained(nf, 0);
     for (size_t i = 0; i < nf; i++) {
         const msgpu_cab_folder &f = plan->folders[i];
         if (f.codec > 3) continue;                                              /* unknown method: scan_status says so */
@@ -248,6 +255,19 @@ extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan,
         if (f.out_len == 0) { fstat[i] = block_err[i] ? block_err[i] : MSGPU_ERR_DATAFORMAT; continue; }
         msgpu_unit u; memset(&u, 0, sizeof(u));
         u.codec = f.codec; u.window_bits = f.window_bits; u.reset_interval = 0; u.flags = 0;
+        bool chain = use_chains && f.codec == MSGPU_CODEC_MSZIP && f.num_blocks >= 2 && !block_err[i];
+        for (uint32_t b = 0; chain && b + 1 < f.num_blocks; b++) if (plan->blocks[f.first_block + b].uncomp_len != MSGPU_CAB_BLOCKMAX) chain = false;
+        if (chain) {
+            chained[i] = 1;
+            for (uint32_t b = 0; b < f.num_blocks; b++) {
+                const msgpu_cab_block &bl = plan->blocks[f.first_block + b];
+                u.flags = b ? MSGPU_FLAG_CHAIN_NEXT : MSGPU_FLAG_CHAIN_FIRST;
+                u.in_off = bl.dst_off; u.in_len = bl.comp_len;
+                u.out_off = f.out_off + (uint64_t) b * MSGPU_CAB_BLOCKMAX; u.out_len = bl.uncomp_len;
+                units.push_back(u); unit_folder.push_back(i);
+            }
+            continue;
+        }
         u.in_off = f.in_off; u.in_len = (uint32_t) in_len; u.out_off = f.out_off; u.out_len = (uint32_t) f.out_len;
         units.push_back(u); unit_folder.push_back(i);
     }
@@ -257,11 +277,34 @@ extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan,
                                           reinterpret_cast<int32_t *>(B.status), B.st);
         if (r) return r;
         CKC(cudaMemcpyAsync(ustat.data(), B.status, units.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, B.st));
+        CKC(cudaStreamSynchronize(B.st));
+        /* chains with a block that is not "exactly one CK block" (or that failed): once more, as one stream per folder */
+        std::vector<uint8_t> redo(nf, 0); bool any_redo = false;
+        for (size_t k = 0; k < units.size(); k++) if (chained[unit_folder[k]] && ustat[k] != 0) { redo[unit_folder[k]] = 1; any_redo = true; }
+        if (any_redo) {
+            std::vector<msgpu_unit> u2; std::vector<size_t> f2;
+            for (size_t i = 0; i < nf; i++) if (redo[i]) {
+                const msgpu_cab_folder &f = plan->folders[i];
+                msgpu_unit u; memset(&u, 0, sizeof(u));
+                u.codec = f.codec; u.in_off = f.in_off; u.in_len = (uint32_t) f.in_len; u.out_off = f.out_off; u.out_len = (uint32_t) f.out_len;
+                u2.push_back(u); f2.push_back(i);
+            }
+            std::vector<int32_t> s2(u2.size(), 0);
+            r = msgpu_decode_batch_device(ctx, u2.data(), u2.size(), B.packed, plan->packed_bytes + 16, B.out, plan->out_bytes + 16,
+                                          reinterpret_cast<int32_t *>(B.status), B.st);
+            if (r) return r;
+            CKC(cudaMemcpyAsync(s2.data(), B.status, u2.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, B.st));
+            CKC(cudaStreamSynchronize(B.st));
+            /* fold the result back: the folder's units all take the stream's status */
+            for (size_t k = 0; k < units.size(); k++) if (redo[unit_folder[k]])
+                for (size_t j = 0; j < u2.size(); j++) if (f2[j] == unit_folder[k]) ustat[k] = s2[j];
+        }
     }
     if (plan->out_bytes) CKC(cudaMemcpyAsync(h_out, B.out, plan->out_bytes, cudaMemcpyDeviceToHost, B.st));
     CKC(cudaStreamSynchronize(B.st));
     for (size_t k = 0; k < units.size(); k++) {
         const size_t i = unit_folder[k];
+        if (k && unit_folder[k - 1] == i) continue;                /* a chain's blocks share the folder's result: all OK, or the one-stream status */
         int32_t s = ustat[k];
         /* cabd.c:1198: the codec's MSPACK_ERR_READ is replaced by the reason the input ended - the refused block's error,
          * or DATAFORMAT when the folder simply has no more blocks (cabd.c:1311-1318) */

@@ -236,6 +236,13 @@ struct ZipLaneC {
         emit_end(em, q);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced;
         fi.valid = (frame && hist_snapshot(recs + (size_t) f * MS_MAXREC)) ? 2u : 1u;                    /* 2: resolved by k_p2_ring */
+        if (u->flags & (MSGPU_FLAG_CHAIN_FIRST | MSGPU_FLAG_CHAIN_NEXT)) {
+            /* one block of a chain (include/msgpu.h): it stands for a stretch of ONE stream only if it is exactly one CK block
+             * that ends with its input and fills its output; anything else is for the caller to decode as one stream */
+            const int64_t used = (ms_bitpos(b) + 7) >> 3;
+            if (q != u->out_len || frame != 0 || used != (int64_t) b.in_len) { fail(MSGPU_ERR_CHAIN); return; }
+            fi.valid = 3u;                                                                               /* 3: resolved by k_p2_chain, in chain order */
+        }
         finfo[f] = fi;
         const uint32_t g0 = produced;
         produced += n; frame++; f++;

@@ -89,6 +89,9 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
             if (wide) emul_p2_frame<true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, MSGPU_UNIT_REF_BYTES(u));
             else emul_p2_frame<false>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0);
         }
+        /* k_p2_chain: a block of an MSZIP chain; the units of a batch run one after the other here, i.e. in chain order */
+        if (finfo[0].valid == 3 && finfo[0].size)
+            emul_p2_frame<true>(recs.data(), finfo[0].nrec, finfo[0].size, unit_out, finfo[0].g0, (u->flags & MSGPU_FLAG_CHAIN_NEXT) ? MS_FRAME : 0u);
         for (int f = 0; f < F; f++) if (finfo[f].valid == 2 && finfo[f].size)
             emul_p2_frame<false, true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0, reinterpret_cast<const uint32_t *>(recs.data() + (size_t) f * MS_MAXREC + P2_HIST_REC));
     };

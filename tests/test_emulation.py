@@ -10,7 +10,7 @@ import pytest
 
 from libmspack_b200 import gen
 from libmspack_b200.units import CODEC_LZX, CODEC_MSZIP, CODEC_QUANTUM
-from util import RING_CASES, assert_same, golden_manifest, golden_unit, ring_batch
+from util import RING_CASES, assert_same, chain_batch, golden_manifest, golden_unit, ring_batch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -176,3 +176,36 @@ def test_device_logic_mszip_short_blocks(emul, oracle_ref):
         assert int(s2[deep]) == 11
         s2[deep] = 0
         assert_same(b.units[:deep], o1, s1[:deep], o2, s2[:deep], f"ring F={fpr}")
+
+
+def test_device_logic_mszip_block_chains(emul, oracle_ref):
+    """the CK blocks of an MSZIP folder as a chain of units (entropy stage per block, resolve stage in chain
+    order) produce what the reference produces for the folder as one stream."""
+    chain, plain, raws = chain_batch([32768 * 4 + 1000, 32768 * 2, 32768 + 1, 100000])
+    o1, s1, _ = oracle_ref.decode_batch(plain.units, plain.comp, plain.out_bytes, threads=4)
+    assert (s1 == 0).all()
+    o2, s2 = emul(chain.units, chain.comp, chain.out_bytes, 1)
+    assert (s2 == 0).all()
+    assert np.array_equal(o1, o2)
+    for k, r in enumerate(raws):
+        assert plain.unit_output(o2, k).tobytes() == r
+
+
+def test_device_logic_chain_blocks_that_are_not_one_ck_block(emul):
+    """A chain unit that is not exactly one CK block using exactly its input reports MSGPU_ERR_CHAIN (100): the caller then
+    decodes the folder as one stream (msgpu_cab.cu) - trailing bytes, a short or long block, a stream that runs out."""
+    def damage(k, b, piece):
+        if k == 0 and b == 1:
+            return piece + b"\0"                  # trailing byte: the one-stream decoder would scan it for the next CK
+        if k == 1 and b == 0:
+            return piece[:-3]                       # runs into the next block's bytes
+        if k == 2 and b == 1:
+            return piece + piece                    # two CK blocks in one unit
+        return piece
+    chain, plain, raws = chain_batch([32768 * 3, 32768 * 2 + 5, 32768 * 3, 32768 * 2], damage=damage)
+    o2, s2 = emul(chain.units, chain.comp, chain.out_bytes, 1)
+    first = np.nonzero(chain.units["flags"] == 4)[0]
+    assert s2[first[0] + 1] == 100 and s2[first[0]] == 0
+    assert s2[first[1]] != 0
+    assert s2[first[2] + 1] == 100
+    assert (s2[first[3]:] == 0).all()

@@ -54,3 +54,82 @@ def test_lzx_delta_mixed_with_plain_units(decoder, oracle_ref):
     perm = np.random.default_rng(5).permutation(m.n)
     m.units = m.units[perm].copy()
     _check_batch(decoder, oracle_ref, m, "delta mixed")
+
+
+def test_mszip_block_chains(decoder, oracle_ref):
+    """MSZIP folders handed over as block chains (one unit per CK block; entropy stage per block, k_p2_chain in
+    chain order) decode to what the reference decodes from each folder as ONE stream; chains and ordinary units in one batch."""
+    from util import chain_batch
+    sizes = [32768 * 4 + 1000, 32768 * 2, 32768 + 1, 100000, 32768 * 40 + 7] + [32768 * 3 + 11 * k for k in range(60)]
+    chain, plain, raws = chain_batch(sizes)
+    o1, s1, _ = oracle_ref.decode_batch(plain.units, plain.comp, plain.out_bytes, threads=8)
+    assert (s1 == 0).all()
+    extra = gen.make_batch(CODEC_MSZIP, 100, unit_bytes=50000, first_unit=900)
+    m = gen.concat_batches([chain, extra])
+    out, st = decoder.decode_host(m.units, m.comp, m.out_bytes)
+    assert (st == 0).all()
+    assert np.array_equal(out[:chain.out_bytes], o1)
+    oe, se, _ = oracle_ref.decode_batch(extra.units, extra.comp, extra.out_bytes, threads=8)
+    assert np.array_equal(out[chain.out_bytes:], oe)
+
+
+def test_chain_units_that_are_not_one_ck_block(decoder):
+    """MSGPU_ERR_CHAIN (100) for a chain unit with trailing bytes / a stream that runs out / two CK blocks; malformed chains are
+    refused by the call itself."""
+    from util import chain_batch
+
+    def damage(k, b, piece):
+        if k == 0 and b == 1:
+            return piece + b"\0"
+        if k == 1 and b == 0:
+            return piece[:-3]
+        if k == 2 and b == 1:
+            return piece + piece
+        return piece
+    chain, plain, raws = chain_batch([32768 * 3, 32768 * 2 + 5, 32768 * 3, 32768 * 2], damage=damage)
+    out, st = decoder.decode_host(chain.units, chain.comp, chain.out_bytes)
+    first = np.nonzero(chain.units["flags"] == 4)[0]
+    assert st[first[0] + 1] == 100 and st[first[0]] == 0
+    assert st[first[1]] != 0
+    assert st[first[2] + 1] == 100
+    assert (st[first[3]:] == 0).all()
+    assert plain.unit_output(out, 3).tobytes() == raws[3]
+    bad = chain.units.copy()
+    bad["flags"][0] = 0x8                                 # a NEXT unit without a predecessor
+    with pytest.raises(RuntimeError):
+        decoder.decode_host(bad, chain.comp, chain.out_bytes)
+    bad = chain.units.copy()
+    bad["out_off"][1] += 16                               # not contiguous with its predecessor
+    with pytest.raises(RuntimeError):
+        decoder.decode_host(bad, chain.comp, chain.out_bytes)
+
+
+def test_cabinet_with_long_mszip_folders(decoder, monkeypatch):
+    """Cabinet front end: multi-block MSZIP folders go through the block chains; same bytes and statuses as with
+    MSGPU_CAB_NOCHAIN=1 (every folder one stream), including a folder with a corrupt block (falls back to one stream)."""
+    import zlib
+    from libmspack_b200 import cab
+    from cabfile import build_cab
+    folders, raws = [], []
+    for k, n in enumerate([32768 * 50 + 123, 32768 * 3, 40000, 32768 * 8]):
+        raw = gen.raw_units(1, n, data="text" if k != 1 else "binary", first_unit=50 * k).tobytes()
+        blocks = []
+        for off in range(0, n, 32768):
+            kw = {"zdict": raw[off - 32768:off]} if off else {}
+            c = zlib.compressobj(6, zlib.DEFLATED, -15, **kw)
+            blocks.append((b"CK" + c.compress(raw[off:off + 32768]) + c.flush(), len(raw[off:off + 32768])))
+        folders.append(dict(comp_type=1, blocks=blocks, files=[(f"f{k}.bin", 0, n)]))
+        raws.append(raw)
+    p3, u3 = folders[3]["blocks"][4]
+    folders[3]["blocks"][4] = (p3[:200] + bytes([p3[200] ^ 0x20]) + p3[201:], u3)          # corrupt, checksums off below
+    img = build_cab(folders, with_checksums=False)
+    plan = cab.scan(img)
+    out_c, st_c = plan.decode(decoder)
+    monkeypatch.setenv("MSGPU_CAB_NOCHAIN", "1")
+    out_s, st_s = plan.decode(decoder)
+    assert list(st_c) == list(st_s)
+    assert list(st_c[:3]) == [0, 0, 0] and st_c[3] != 0
+    for k in range(3):
+        base, n = int(plan.folders["out_off"][k]), int(plan.folders["out_len"][k])
+        assert out_c[base:base + n].tobytes() == raws[k]
+        assert out_s[base:base + n].tobytes() == raws[k]

@@ -84,3 +84,37 @@ def ring_batch(cases):
 RING_CASES = [[32768, 100, 32768], [32768, 100, 50, 20000, 32768, 7], [500, 400, 300, 200, 100, 50, 25, 12, 6, 3, 32768, 1000], [32768, 32768, 1, 32768],
               [15506, 16772, 24746, 31145, 1143, 4724, 9000, 32768, 32768, 31, 4000], [1, 2, 3, 4, 5, 32768, 5, 4, 3, 2, 1, 30000],
               [3000 - 100 * k for k in range(20)] + [32768]]       # the last one: 20 blocks, each shorter than the one before (deeper than P2_HIST_K)
+
+
+def chain_batch(folder_bytes, data="text", damage=None):
+    """MSZIP folders handed over as block chains (include/msgpu.h MSGPU_FLAG_CHAIN_*): one unit per CK block.  Returns
+    (chain batch, the same folders as one plain unit each, raw data per folder).  damage(k, b, block) may alter block b of
+    folder k (bytes -> bytes)."""
+    import zlib
+    from libmspack_b200.units import UNIT_DTYPE
+    from libmspack_b200 import gen
+    cu, pu, comps, raws, ioff, ooff = [], [], [], [], 0, 0
+    for k, n in enumerate(folder_bytes):
+        raw = gen.raw_units(1, n, data=data, first_unit=10 * k).tobytes()
+        raws.append(raw)
+        fin, first = ioff, True
+        for b, off in enumerate(range(0, n, 32768)):
+            blk = raw[off:off + 32768]
+            kw = {"zdict": raw[off - 32768:off]} if off else {}
+            c = zlib.compressobj(6, zlib.DEFLATED, -15, **kw)
+            piece = b"CK" + c.compress(blk) + c.flush()
+            if damage:
+                piece = damage(k, b, piece)
+            cu.append((1, 0, 0, 0x4 if first else 0x8, ioff, len(piece), len(blk), ooff + off))
+            comps.append(piece)
+            ioff += len(piece)
+            first = False
+        pu.append((1, 0, 0, 0, fin, ioff - fin, n, ooff))
+        pad = (-ioff) % 4
+        comps.append(b"\0" * pad)
+        ioff += pad
+        ooff += (n + 15) & ~15
+    comp = np.frombuffer(b"".join(comps) + b"\0" * 16, dtype=np.uint8).copy()
+    chain = gen.Batch(np.array(cu, dtype=UNIT_DTYPE), comp, None, ooff)
+    plain = gen.Batch(np.array(pu, dtype=UNIT_DTYPE), comp, None, ooff)
+    return chain, plain, raws
