@@ -17,7 +17,7 @@ def test_reference_test_program_passes_on_the_dropin(binary, expect):
     exe = os.path.join(ROOT, "oracle", "_ref", binary)
     if not os.path.exists(exe):
         pytest.skip(f"{exe} not built (needs /root/reference at build time)")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, cwd=ROOT)   # fixture paths are relative to the repo root
-    tail = (r.stdout + r.stderr)[-2000:]
-    assert r.returncode == 0, tail
-    assert expect in r.stdout, tail
+    r = subprocess.run([exe], capture_output=True, timeout=900, cwd=ROOT)   # fixture paths are relative to the repo root
+    out = (r.stdout + r.stderr).decode("utf-8", "replace")                   # (the programs print raw member names)
+    assert r.returncode == 0, out[-2000:]
+    assert expect in out, out[-2000:]
