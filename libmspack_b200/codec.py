@@ -14,7 +14,7 @@ import numpy as np
 from .units import UNIT_DTYPE
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmsgpu.so")
+LIB_PATH = os.environ.get("MSGPU_LIB") or os.path.join(PKG, "libmsgpu.so")      # MSGPU_LIB: an experimental build (tools/variant_bench.py)
 
 # every symbol include/msgpu.h declares
 ABI_SYMBOLS = [

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
 }
 
 /* DELTA = the instantiation for waves that hold LZX DELTA units (it decodes plain LZX units as well) */
-template <int NT, int HEADN, bool DELTA>
+template <int NT, int HEADN, bool DELTA, int H8LB>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
@@ -81,10 +81,10 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN, DELTA> t; t.phase = PH_IDLE;
+    LzxLaneC<NT, HEADN, DELTA, H8LB> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
-        t.bind(reinterpret_cast<LzxSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
+        t.bind(reinterpret_cast<typename LzxSharedSel<NT, HEADN, H8LB>::type *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
@@ -114,8 +114,13 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 
 #define P2_WARPS 8
 /* WIDE = the instantiation for waves that hold LZX DELTA units: 26-bit match offsets, reference data in front of the unit */
+#ifdef P2_MINBLOCKS
+#define P2_BOUNDS __launch_bounds__(P2_WARPS * 32, P2_MINBLOCKS)
+#else
+#define P2_BOUNDS __launch_bounds__(P2_WARPS * 32)
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(P2_WARPS * 32) k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
+__global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
     __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
@@ -215,9 +220,13 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 
 /* ------------------------------------------------------------------------------------------ host side */
 /* P1 kernel shapes (id, threads per CTA, shared-memory head entries); MSGPU_ZIP_VARIANT / MSGPU_LZX_VARIANT pick one.
- * 448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident wave. */
-#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64)
-#define LZXC_VARIANTS(X) X(10, 512, 32) X(11, 448, 72) X(12, 384, 64) X(13, 448, 48)
+ * 448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident wave.
+ * Defaults (measured on the B200, headline batches): MSZIP 14 (124-entry head: every coded symbol of a text block, 9.70 -> 8.81 ms),
+ * LZX 30 (LzxSharedQ: 256-entry packed head + LENGTH head, 10.59 -> 8.97 ms; 20-22 = LzxSharedP steps on the way, 11 = the
+ * 72-entry 16-bit head of the first round-1 measurements). */
+#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 96) X(14, 448, 124)
+/* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
+#define LZXC_VARIANTS(X) X(10, 512, 32, 0) X(11, 448, 72, 0) X(12, 384, 64, 0) X(20, 448, 208, 5) X(21, 448, 224, 4) X(22, 448, 240, 4) X(30, 448, 256, 104)
 #define QTM_NT 160
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
@@ -293,12 +302,23 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
     ZIPC_VARIANTS(SETATTRZC)
 #undef SETATTRZC
-    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 11; }
-#define SETATTRC(id, nt, hn) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<nt, hn>));
+    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
+#define SETATTRC(id, nt, hn, lb) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
-    cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
-    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 11; }
+    cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
+    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
+    {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
+        bool okz = false, okl = false;
+#define CHKZ(id, nt, hn) if (c->zip_variant == id) okz = true;
+        ZIPC_VARIANTS(CHKZ)
+#undef CHKZ
+#define CHKL(id, nt, hn, lb) if (c->lzx_variant == id) okl = true;
+        LZXC_VARIANTS(CHKL)
+#undef CHKL
+        if (!okz) c->zip_variant = 14;
+        if (!okl) c->lzx_variant = 30;
+    }
     cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
     return c;
 }
@@ -388,7 +408,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
     uint32_t lzx_nt = 128, zip_nt = 128;
-#define PICKNTC(id, nt, hn) if (ctx->lzx_variant == id) lzx_nt = nt;
+#define PICKNTC(id, nt, hn, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
     if (any_delta) lzx_nt = LZXD_NT;
@@ -544,10 +564,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
-#define LAUNCHC(id, nt, hn) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedC<nt, hn>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCHC(id, nt, hn, lb) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedSel<nt, hn, lb>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZXC_VARIANTS(LAUNCHC)
 #undef LAUNCHC
-            if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+            if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;

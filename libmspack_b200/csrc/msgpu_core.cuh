@@ -211,9 +211,36 @@ struct MsHuffAux {          /* pointers already offset by lane; stride MS_WARP e
  * head[k * NT] (k < headn) receive the symbols in canonical order; an optional ROOT-bit MSB-first LUT
  * (u16 = sym << 4 | len, 0 = longer code) is filled as well.  Returns 0 iff make_decode_table would succeed
  */
-template <int ROOT, int NT, class LensFn>
-MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
-                        uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
+/* The per-length base of a canonical code, two storage forms (BoT of ms_canon_build_h):
+ *   MsBo32  one word per length: limit[l-1] >> 1 | offs[l] << 16                      index = offs + ((v16 - limit[l-1]) >> (16 - l))
+ *   MsBoK   16 bits per length:  K[l] = offs[l] - (limit[l-1] >> (16 - l))             index = (v16 >> (16 - l)) + K[l]
+ *           (limit[l-1] is a multiple of 2^(16-l), so that is the same number).  |K[l]| < 2^15 for l <= 15; K[16] needs 17 bits and is
+ *           split over slot 16 (low half) and the otherwise unused slot 0 (high half). */
+template <int NT> struct MsBo32 {
+    uint32_t *p;
+    MS_M void put(int l, uint32_t lim_prev, uint32_t off) const { p[l * NT] = (lim_prev >> 1) | (off << 16); }
+    MS_M uint32_t code_of(int l, uint32_t k) const { uint32_t b = p[l * NT]; return (((b & 0xFFFFu) << 1) >> (16 - l)) + (k - (b >> 16)); }
+    MS_M uint32_t index(uint32_t v16, int len) const { uint32_t b = p[len * NT]; return (b >> 16) + ((v16 - ((b & 0xFFFFu) << 1)) >> (16 - len)); }
+};
+template <int NT> struct MsBoK {
+    uint16_t *p;
+    MS_M void put(int l, uint32_t lim_prev, uint32_t off) const {
+        const uint32_t k = off - (lim_prev >> (16 - l));
+        p[l * NT] = (uint16_t) k;
+        if (l == 16) p[0] = (uint16_t) (k >> 16);
+    }
+    MS_M uint32_t kval(int l) const {
+        uint32_t k = (uint32_t) (int32_t) (int16_t) p[l * NT];
+        if (MS_UNLIKELY(l == 16)) k = (uint32_t) p[16 * NT] | ((uint32_t) p[0] << 16);
+        return k;
+    }
+    MS_M uint32_t code_of(int l, uint32_t k) const { return k - kval(l); }
+    MS_M uint32_t index(uint32_t v16, int len) const { return (v16 >> (16 - len)) + kval(len); }
+};
+
+template <int ROOT, int NT, class LensFn, class HeadFn, class BoT>
+MS_D int ms_canon_build_h(LensFn lens, int nsyms, int ref_tablebits, BoT bo, uint16_t *cnt, uint16_t *sorted,
+                          HeadFn put_head, uint16_t *lut, uint32_t limv[16])
 {
 #pragma unroll 1
     for (int l = 0; l <= 16; l++) cnt[l * NT] = 0;
@@ -230,7 +257,7 @@ MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo,
 #pragma unroll
     for (int l = 1; l <= 16; l++) {
         uint32_t c = (l <= maxlen) ? cnt[l * NT] : 0;
-        bo[l * NT] = (lim >> 1) | (off << 16);
+        bo.put(l, lim, off);
         cnt[l * NT] = (uint16_t) off;                       /* running index of the next l-bit symbol */
         lim += c << (16 - l); limv[l - 1] = lim; off += c;
     }
@@ -244,15 +271,22 @@ MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo,
         if (l < 1 || l > maxlen) continue;
         uint32_t k = cnt[l * NT]; cnt[l * NT] = (uint16_t) (k + 1);
         sorted[k * MS_WARP] = (uint16_t) s;
-        if (k < headn) head[k * NT] = (uint16_t) s;
+        put_head(k, (uint32_t) s);
         if (ROOT > 0 && l <= ROOT) {
-            uint32_t b = bo[l * NT];
-            uint32_t code = (((b & 0xFFFFu) << 1) >> (16 - l)) + (k - (b >> 16));
+            uint32_t code = bo.code_of(l, k);
             uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
             for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = (uint16_t) ((s << 4) | l);
         }
     }
     return 0;
+}
+
+template <int ROOT, int NT, class LensFn>
+MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
+                        uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
+{
+    return ms_canon_build_h<ROOT, NT>(lens, nsyms, ref_tablebits, MsBo32<NT>{ bo }, cnt, sorted,
+                                      [=](uint32_t k, uint32_t s) { if (k < headn) head[k * NT] = (uint16_t) s; }, lut, limv);
 }
 
 /* code length from limits in registers: lim[j] = limit[j + 1], non-decreasing.  len = 1 + #{ j : lim[j] <= v16 },

@@ -10,6 +10,7 @@
  * the first iterations needed ~1 KB per lane (6 warps per SM) and were 2.4x slower.
  */
 #pragma once
+#include <type_traits>
 #include "msgpu_core.cuh"
 
 #define LZX_MAIN_MAX   2576                   /* LZX_MAINTREE_MAXSYMBOLS, lzx.h:38 */
@@ -44,11 +45,53 @@ struct LzxSharedC {
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int HEADN, bool DELTA = false>
+/* The packed layout (H8LB = 5 or 4, the LENGTH tree's LUT bits).  Measured on the headline batch the main tree of a 32 KiB text
+ * frame has ~250 coded symbols with codes of 6-8 bits: a 72-symbol head misses for 29 % of the symbols, i.e. in every step some
+ * lane of the warp goes to L2 for its symbol and the whole warp waits.  A main symbol is < 656 (window_bits <= 21): 10 bits, kept
+ * as a byte plus two bits (16 per word), so ~1.25 bytes per head entry instead of 2; the aligned-offset tree (8 symbols, codes
+ * <= 7 bits) shrinks from 100 bytes to 4 words, and the builder's counters share the LENGTH limits' array (never live together).
+ * Same shared memory per lane, 208-240 head entries instead of 72. */
+template <int NT, int HEADN, int LB>
+struct LzxSharedP {
+    uint32_t mbo[17 * NT];                /* main tree: limit[l-1] >> 1 | offs[l] << 16 */
+    uint32_t lbo[17 * NT];                /* LENGTH tree; hosts the pretree while code lengths are being read */
+    uint32_t atree[4 * NT];               /* aligned-offset tree: limits 1-4 | limits 5-7 | offs (4 bits each) | symbols (3 bits each) */
+    uint32_t mhi[(HEADN / 16) * NT];      /* bits 8-9 of the head symbols, 16 per word */
+    uint16_t llim[17 * NT];               /* LENGTH / pretree limits >> 1; while a tree is being built: the builder's counters */
+    uint16_t llut[(1 << LB) * NT];        /* LB-bit LUT of the LENGTH tree */
+    static constexpr int ROW = HEADN > 224 ? NT : NT + 4;      /* rows of NT + 4 bytes spread the banks (where the space allows) */
+    uint8_t mlo[HEADN * ROW];             /* low bytes of the head symbols */
+};
+/* The packed layout with 16-bit per-length bases (MsBoK) instead of one word per length: 64 bytes less for the two big trees,
+ * spent on a full 256-entry main head and a 40-entry byte head of the LENGTH tree's symbols (the LENGTH symbols the LUT
+ * misses were the other L2 round trip the profile showed: ~10 % of the steps had a lane there).  H8LB = 100 + LUT bits. */
+#define LZX_LHEAD 40
+template <int NT, int HEADN, int LB>
+struct LzxSharedQ {
+    uint32_t atree[4 * NT];
+    uint32_t mhi[(HEADN / 16) * NT];
+    uint16_t mbo[17 * NT];                /* main tree, K form */
+    uint16_t lbo[17 * NT];                /* LENGTH tree / pretree, K form */
+    uint16_t llim[17 * NT];
+    uint16_t llut[(1 << LB) * NT];
+    uint8_t lhead[LZX_LHEAD * NT];        /* first LENGTH symbols in canonical order */
+    static constexpr int ROW = NT;
+    uint8_t mlo[HEADN * ROW];
+};
+template <int NT, int HEADN, int H8LB> struct LzxSharedSel { typedef typename std::conditional<(H8LB >= 100), LzxSharedQ<NT, HEADN, H8LB - 100>, LzxSharedP<NT, HEADN, H8LB>>::type type; };
+template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxSharedC<NT, HEADN> type; };
+
+template <int NT, int HEADN, bool DELTA = false, int H8LB = 0>
 struct LzxLaneC {
+    typedef typename LzxSharedSel<NT, HEADN, H8LB>::type Shared;
+    static constexpr bool H8 = H8LB != 0;
+    static constexpr bool QL = H8LB >= 100;                     /* 16-bit bases + LENGTH head (LzxSharedQ) */
+    static constexpr int LUTB = H8 ? (QL ? H8LB - 100 : H8LB) : 5;
+    typedef typename std::conditional<QL, MsBoK<NT>, MsBo32<NT>>::type Bo;
     MsBits b;
+    uint32_t *atree, *mhi; uint8_t *mlo, *lhead;  /* packed layouts only */
     uint32_t is_delta, ref_len;           /* DELTA only: this unit is an LZX DELTA stream; bytes of reference data in front of it */
-    uint32_t *mbo, *lbo, *abo;
+    Bo mbo, lbo; uint32_t *abo;
     uint16_t *mhead, *llim, *alim, *llut, *cnt;
     uint8_t *main_len, *len_len;
     MsHuffAux ma, la, pa, aa;             /* only .sorted is used (global scratch) */
@@ -63,9 +106,11 @@ struct LzxLaneC {
     uint32_t phase, q, produced, frame, done, frame_start_pos, frame_size; int32_t status, bytes_todo, this_run;
     int f, max_frames;
 
-    MS_M void bind(LzxSharedC<NT, HEADN> *sh, int tid, uint8_t *aux_warp, int lane) {
-        mbo = sh->mbo + tid; lbo = sh->lbo + tid; abo = sh->abo + tid; mhead = sh->mhead + tid;
-        llim = sh->llim + tid; alim = sh->alim + tid; llut = sh->llut + tid; cnt = sh->cnt + tid;
+    MS_M void bind(Shared *sh, int tid, uint8_t *aux_warp, int lane) {
+        mbo.p = sh->mbo + tid; lbo.p = sh->lbo + tid; llim = sh->llim + tid; llut = sh->llut + tid;
+        if constexpr (QL) lhead = sh->lhead + tid; else lhead = nullptr;
+        if constexpr (H8) { atree = sh->atree + tid; mhi = sh->mhi + tid; mlo = sh->mlo + tid; cnt = llim; abo = nullptr; mhead = nullptr; alim = nullptr; }
+        else { abo = sh->abo + tid; mhead = sh->mhead + tid; alim = sh->alim + tid; cnt = sh->cnt + tid; }
         main_len = aux_warp + LZX_AUX_MAINLEN + lane; len_len = aux_warp + LZX_AUX_LENLEN + lane;
         ma.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_MSORT) + lane;
         la.sorted = reinterpret_cast<uint16_t *>(aux_warp + LZX_AUX_LSORT) + lane;
@@ -86,22 +131,37 @@ struct LzxLaneC {
     }
 
     /* READ_HUFFSYM for a tree whose limits live in shared memory (pretree, LENGTH slow path, aligned tree) */
-    MS_M uint32_t sym_smem(const uint16_t *lim16, const uint32_t *bo, const uint16_t *sorted, bool careful = true) {
+    template <class BoT>
+    MS_M uint32_t sym_smem(const uint16_t *lim16, BoT bo, const uint16_t *sorted, bool careful = true) {
         if (careful) lzx_check(b, 16);
         uint32_t v16 = msb_peek(b, 16);
         int len = ms_canon_len_smem<NT>(lim16, v16);
-        uint32_t idx = ms_canon_index<NT>(bo, v16, len);
+        uint32_t idx = bo.index(v16, len);
         msb_drop(b, len);
         return sorted[idx * MS_WARP];
     }
+    /* READ_HUFFSYM(ALIGNED) from the four-word tree of the packed layout (build_aligned) */
+    MS_M uint32_t aligned_sym(bool careful) {
+        if (careful) lzx_check(b, 16);
+        const uint32_t v7 = msb_peek(b, 7), w0 = atree[0], w1 = atree[NT], w2 = atree[2 * NT], w3 = atree[3 * NT];
+        const uint64_t lims = (uint64_t) w0 | ((uint64_t) w1 << 32);          /* limit[l] at bits 8 (l - 1) */
+        uint32_t len = 1;
+#pragma unroll
+        for (int l = 1; l <= 6; l++) len += (v7 >= ((uint32_t) (lims >> (8 * (l - 1))) & 0xFFu)) ? 1u : 0u;
+        const uint32_t below = len > 1 ? (uint32_t) (lims >> (8 * (len - 2))) & 0xFFu : 0u;
+        const uint32_t idx = ((w2 >> (4 * (len - 1))) & 15u) + ((v7 - below) >> (7 - len));
+        msb_drop(b, (int) len);
+        return (w3 >> (3 * idx)) & 7u;
+    }
     MS_M uint32_t length_sym(bool careful) {  /* LENGTH tree: 5-bit LUT, then the canonical path */
         if (careful) lzx_check(b, 16);
-        uint32_t e = llut[msb_peek(b, 5) * NT];
+        uint32_t e = llut[msb_peek(b, LUTB) * NT];
         if (e & 15) { msb_drop(b, (int) (e & 15)); return e >> 4; }
         uint32_t v16 = msb_peek(b, 16);
         int len = ms_canon_len_smem<NT>(llim, v16);
-        uint32_t idx = ms_canon_index<NT>(lbo, v16, len);
+        uint32_t idx = lbo.index(v16, len);
         msb_drop(b, len);
+        if constexpr (QL) { if (idx < (uint32_t) LZX_LHEAD) return lhead[idx * NT]; }
         return la.sorted[idx * MS_WARP];
     }
 
@@ -135,8 +195,8 @@ struct LzxLaneC {
             if (x < 16) plo |= (uint64_t) y << (4 * x); else phi |= y << (4 * (x - 16));
         }
         if (b.err) return b.err;
-        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
-                                  20, 6, lbo, cnt, pa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        if (ms_canon_build_h<0, NT>([&](int s) { return (uint32_t) (s < 16 ? (plo >> (4 * s)) : (uint64_t) (phi >> (4 * (s - 16)))) & 15u; },
+                                    20, 6, lbo, cnt, pa.sorted, [](uint32_t, uint32_t) { }, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
 #pragma unroll
         for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
 #pragma unroll 1
@@ -161,8 +221,20 @@ struct LzxLaneC {
 
     MS_M int build_main() {
         uint8_t *l = main_len; uint32_t lv[16];
-        if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted, mhead, HEADN,
-                                  (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        if constexpr (H8) {
+#pragma unroll 1
+            for (int w = 0; w < HEADN / 16; w++) mhi[w * NT] = 0;
+            uint8_t *lo = mlo; uint32_t *hi = mhi;
+            if (ms_canon_build_h<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
+                                        [=](uint32_t k, uint32_t sym) {
+                                            if (k < (uint32_t) HEADN) { lo[k * Shared::ROW] = (uint8_t) sym; hi[(k >> 4) * NT] |= (sym >> 8) << ((k & 15u) * 2u); }
+                                        }, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        }
+        else {
+            uint16_t *hd = mhead;
+            if (ms_canon_build_h<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
+                                        [=](uint32_t k, uint32_t sym) { if (k < (uint32_t) HEADN) hd[k * NT] = (uint16_t) sym; }, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        }
 #pragma unroll
         for (int j = 0; j < 15; j++) mlim[j] = lv[j];
         return 0;
@@ -170,7 +242,9 @@ struct LzxLaneC {
     MS_M int build_length() {                 /* BUILD_TABLE_MAYBE_EMPTY, lzxd.c:111-125 */
         uint8_t *l = len_len; uint32_t lv[16];
         length_empty = 0;
-        if (ms_canon_build<5, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted, (uint16_t *) nullptr, 0, llut, lv)) {
+        uint8_t *lh = lhead;
+        if (ms_canon_build_h<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
+                                       [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv)) {
 #pragma unroll 1
             for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
             length_empty = 1;
@@ -183,10 +257,31 @@ struct LzxLaneC {
     }
     MS_M int build_aligned() {
         uint32_t al = aligned_lens; uint32_t lv[16];
-        if (ms_canon_build<0, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, abo, cnt, aa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        if constexpr (H8) {
+            /* 8 symbols, lengths 0..7: everything fits four words.  make_decode_table (readhuff.h:83-176, 7 table bits)
+             * accepts exactly the complete codes */
+            uint32_t c[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
-        for (int j = 0; j < 15; j++) alim[j * NT] = (uint16_t) (lv[j] >> 1);
-        return 0;
+            for (int k = 0; k < 8; k++) c[(al >> (3 * k)) & 7u]++;
+            uint32_t lim = 0, off = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0, n = 0;
+#pragma unroll
+            for (int len = 1; len <= 7; len++) {
+                w2 |= off << (4 * (len - 1));
+                lim += c[len] << (7 - len); off += c[len];
+                if (len <= 4) w0 |= lim << (8 * (len - 1)); else w1 |= lim << (8 * (len - 5));
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (((al >> (3 * k)) & 7u) == (uint32_t) len) { w3 |= (uint32_t) k << (3 * n); n++; }
+            }
+            if (lim != 128u) return MS_EDECRUNCH;
+            atree[0] = w0; atree[NT] = w1; atree[2 * NT] = w2; atree[3 * NT] = w3;
+            return 0;
+        }
+        else {
+            if (ms_canon_build<0, NT>([&](int s) { return (al >> (3 * s)) & 7u; }, 8, 7, abo, cnt, aa.sorted, (uint16_t *) nullptr, 0, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+#pragma unroll
+            for (int j = 0; j < 15; j++) alim[j * NT] = (uint16_t) (lv[j] >> 1);
+            return 0;
+        }
     }
 
     /* lzxd.c:465-523: read a block header.  Returns 0 or an MSPACK_ERR_* */
@@ -328,9 +423,13 @@ struct LzxLaneC {
         if (careful) lzx_check(b, 16);
         uint32_t v16 = msb_peek(b, 16);
         int len = ms_canon_len(mlim, v16);
-        uint32_t idx = ms_canon_index<NT>(mbo, v16, len);
+        uint32_t idx = mbo.index(v16, len);
         msb_drop(b, len);
-        return idx < (uint32_t) HEADN ? (uint32_t) mhead[idx * NT] : (uint32_t) ma.sorted[idx * MS_WARP];
+        if constexpr (H8) {
+            if (idx < (uint32_t) HEADN) return (uint32_t) mlo[idx * Shared::ROW] | (((mhi[(idx >> 4) * NT] >> ((idx & 15u) * 2u)) & 3u) << 8);
+            return (uint32_t) ma.sorted[idx * MS_WARP];
+        }
+        else return idx < (uint32_t) HEADN ? (uint32_t) mhead[idx * NT] : (uint32_t) ma.sorted[idx * MS_WARP];
     }
 
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset
@@ -367,7 +466,7 @@ struct LzxLaneC {
                 lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
                     if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
-                    off += sym_smem(alim, abo, aa.sorted, careful);
+                    if constexpr (H8) off += aligned_sym(careful); else off += sym_smem(alim, MsBo32<NT>{ abo }, aa.sorted, careful);
                 }
                 else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;

@@ -16,7 +16,9 @@
 #pragma once
 #include "msgpu_core.cuh"
 
+#ifndef P2_WIN
 #define P2_WIN   288         /* records held in shared memory per warp; > 257 so one load always covers a chunk */
+#endif
 #define P2_CHUNK 512u
 
 MS_D uint32_t rec_pos(uint32_t a) { return a & 0xFFFFu; }

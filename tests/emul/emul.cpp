@@ -108,9 +108,14 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
-        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
+        typedef LzxSharedP<1, 32, 4> SHP; typedef LzxLaneC<1, 32, false, 4> THP;        /* the packed shared-memory layouts */
+        typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ;
+        const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
+        SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            else if (packed && !wide) { THP t; t.bind((SHP *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            else if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             resolve();
         }

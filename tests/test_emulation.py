@@ -209,3 +209,68 @@ def test_device_logic_chain_blocks_that_are_not_one_ck_block(emul):
     assert s2[first[1]] != 0
     assert s2[first[2] + 1] == 100
     assert (s2[first[3]:] == 0).all()
+
+
+PACKED_CASES = [dict(), dict(block_mode=1), dict(block_mode=2), dict(block_mode=4, split=3), dict(unit_bytes=65536, reset_interval=2, block_mode=4),
+                dict(intel=1, data="binary", unit_bytes=70000, block_mode=2), dict(window_bits=15, unit_bytes=100000, block_mode=4), dict(data="random"),
+                dict(data="zeros"), dict(unit_bytes=131072, block_frames=2, block_mode=2)]
+
+
+@pytest.mark.parametrize("layout", [0x200, 0x400], ids=["P", "Q"])
+@pytest.mark.parametrize("kw", PACKED_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
+def test_device_logic_lzx_packed_layout(emul, oracle_ref, kw, layout):
+    """The packed shared-memory layouts of the LZX lanes (LzxSharedP: byte + two-bit head entries, four-word aligned-offset
+    tree, counters sharing the LENGTH limits' array; LzxSharedQ: also 16-bit per-length bases and a byte head of the LENGTH
+    tree) decode exactly like the plain one - intact and corrupted streams."""
+    b = gen.make_batch(CODEC_LZX, 12, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+    for fpr in (1, 2):
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, layout | fpr)
+        assert_same(b.units, o1, s1, o2, s2, f"packed {kw} F={fpr}")
+    rng = np.random.default_rng(23)
+    comp, units = b.comp.copy(), b.units.copy()
+    for i, u in enumerate(units):
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        if i % 3 != 2:
+            comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
+    o2, s2 = emul(units, comp, b.out_bytes, layout | 1)
+    assert_same(units, o1, s1, o2, s2, f"corrupt packed {kw}")
+
+
+def test_device_logic_packed_layout_on_golden_vectors(emul):
+    import hashlib
+    for entry in golden_manifest():
+        if entry["codec"] != CODEC_LZX:
+            continue
+        u, comp = golden_unit(entry)
+        for layout in (0x200, 0x400):
+            out, st = emul(u, comp, entry["out_len"], layout | 2)
+            assert int(st[0]) == entry["err"], entry["name"]
+            if entry["err"] == 0:
+                assert hashlib.md5(out.tobytes()).hexdigest() == entry["md5"], entry["name"]
+
+
+def test_device_logic_long_codes_all_layouts(emul, oracle_ref):
+    """Main-tree codes up to the 16-bit limit (skewed literals): every storage form of the per-length bases (one word, or 16 bits
+    with the split K[16] of MsBoK) and every head layout decodes them."""
+    from libmspack_b200.units import UNIT_DTYPE
+    rng = np.random.default_rng(9)
+    p = 0.5 ** np.arange(1, 41)
+    p /= p.sum()
+    for trial in range(3):
+        n = 32768
+        data = rng.choice(40, size=n, p=p).astype(np.uint8)
+        idx = rng.integers(0, n, 300)
+        data[idx] = rng.integers(40, 256, 300)
+        comp = gen.lzx_encode(data.tobytes(), window_bits=16, block_mode=1, chain=1)
+        u = np.zeros(1, dtype=UNIT_DTYPE)
+        u["codec"], u["window_bits"], u["in_len"], u["out_len"] = CODEC_LZX, 16, len(comp), n
+        buf = np.frombuffer(comp + b"\0" * 16, dtype=np.uint8)
+        o1, s1, _ = oracle_ref.decode_batch(u, buf, n)
+        assert s1[0] == 0 and o1.tobytes() == data.tobytes()
+        for mode in (1, 0x201, 0x401, 0x101):
+            o2, s2 = emul(u, buf, n, mode)
+            assert s2[0] == 0 and np.array_equal(o2, o1), (trial, hex(mode))
