@@ -37,14 +37,17 @@ struct WaveArgs {
 /* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
  * warp is guaranteed to be converged on the hot step() loop; lanes leave it together as soon as one of
  * them needs service (a block header, a frame boundary) and come back once that is done. */
-template <class Lane>
+template <class Lane, bool TWO = false>
 __device__ __forceinline__ void p1_run(Lane &t)
 {
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
         if (!m0) break;
-        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
+        if (TWO) {      /* experimental: two steps per vote (a lane that left the run after the first one sits the second out) */
+            do { if (t.phase == PH_DECODE) t.step(); if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
+        }
+        else do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
     }
 }
 
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
 }
 
 /* DELTA = the instantiation for waves that hold LZX DELTA units (it decodes plain LZX units as well) */
-template <int NT, int HEADN, bool DELTA, int H8LB>
+template <int NT, int HEADN, bool DELTA, int H8LB, int OPT = 0>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN, DELTA, H8LB> t; t.phase = PH_IDLE;
+    LzxLaneC<NT, HEADN, DELTA, H8LB, OPT> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<typename LzxSharedSel<NT, HEADN, H8LB>::type *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
-    p1_run(t);
+    p1_run<LzxLaneC<NT, HEADN, DELTA, H8LB, OPT>, (OPT & 2) != 0>(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
@@ -226,7 +229,10 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * 72-entry 16-bit head of the first round-1 measurements). */
 #define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 96) X(14, 448, 124)
 /* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
-#define LZXC_VARIANTS(X) X(10, 512, 32, 0) X(11, 448, 72, 0) X(12, 384, 64, 0) X(20, 448, 208, 5) X(21, 448, 224, 4) X(22, 448, 240, 4) X(30, 448, 256, 104)
+/* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
+ * steps per vote, 33 both */
+#define LZXC_VARIANTS(X) X(10, 512, 32, 0, 0) X(11, 448, 72, 0, 0) X(12, 384, 64, 0, 0) X(20, 448, 208, 5, 0) X(21, 448, 224, 4, 0) X(22, 448, 240, 4, 0) \
+    X(30, 448, 256, 104, 0) X(31, 448, 256, 104, 1) X(32, 448, 256, 104, 2) X(33, 448, 256, 104, 3)
 #define QTM_NT 160
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
@@ -303,7 +309,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     ZIPC_VARIANTS(SETATTRZC)
 #undef SETATTRZC
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
-#define SETATTRC(id, nt, hn, lb) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
+#define SETATTRC(id, nt, hn, lb, opt) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb, opt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
     cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
@@ -313,7 +319,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define CHKZ(id, nt, hn) if (c->zip_variant == id) okz = true;
         ZIPC_VARIANTS(CHKZ)
 #undef CHKZ
-#define CHKL(id, nt, hn, lb) if (c->lzx_variant == id) okl = true;
+#define CHKL(id, nt, hn, lb, opt) if (c->lzx_variant == id) okl = true;
         LZXC_VARIANTS(CHKL)
 #undef CHKL
         if (!okz) c->zip_variant = 14;
@@ -408,7 +414,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
     uint32_t lzx_nt = 128, zip_nt = 128;
-#define PICKNTC(id, nt, hn, lb) if (ctx->lzx_variant == id) lzx_nt = nt;
+#define PICKNTC(id, nt, hn, lb, opt) if (ctx->lzx_variant == id) lzx_nt = nt;
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
     if (any_delta) lzx_nt = LZXD_NT;
@@ -564,7 +570,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
-#define LAUNCHC(id, nt, hn, lb) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false, lb><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedSel<nt, hn, lb>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+#define LAUNCHC(id, nt, hn, lb, opt) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false, lb, opt><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedSel<nt, hn, lb>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             LZXC_VARIANTS(LAUNCHC)
 #undef LAUNCHC
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));

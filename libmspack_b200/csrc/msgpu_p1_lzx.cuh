@@ -81,7 +81,10 @@ struct LzxSharedQ {
 template <int NT, int HEADN, int H8LB> struct LzxSharedSel { typedef typename std::conditional<(H8LB >= 100), LzxSharedQ<NT, HEADN, H8LB - 100>, LzxSharedP<NT, HEADN, H8LB>>::type type; };
 template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxSharedC<NT, HEADN> type; };
 
-template <int NT, int HEADN, bool DELTA = false, int H8LB = 0>
+/* OPT (experimental shapes, none of them a default until measured on the B200 - tools/variant_bench.py):
+ *   bit 0  the refill in front of a match's offset bits only when the bits at hand do not cover them (extra + 4 <= 21 bits): with
+ *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them */
+template <int NT, int HEADN, bool DELTA = false, int H8LB = 0, int OPT = 0>
 struct LzxLaneC {
     typedef typename LzxSharedSel<NT, HEADN, H8LB>::type Shared;
     static constexpr bool H8 = H8LB != 0;
@@ -463,7 +466,8 @@ struct LzxLaneC {
                 uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
                 uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
                 off = pbase - 2;
-                lzx_refill(b);
+                if constexpr ((OPT & 1) != 0) { if (b.bc < (int) extra + 4) lzx_refill(b); }      /* (still below 32: the buffer has room) */
+                else lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
                     if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
                     if constexpr (H8) off += aligned_sym(careful); else off += sym_smem(alim, MsBo32<NT>{ abo }, aa.sorted, careful);

@@ -71,6 +71,16 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
     }
 }
 
+template <class Lane>
+static void emul_run2(Lane &t) {      /* p1_run<Lane, TWO = true> */
+    for (;;) {
+        t.service();
+        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
+        if (!m0) break;
+        do { if (t.phase == PH_DECODE) t.step(); if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
+    }
+}
+
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     const int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
@@ -109,11 +119,12 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     else if (u->codec == MSGPU_CODEC_LZX) {
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
         typedef LzxSharedP<1, 32, 4> SHP; typedef LzxLaneC<1, 32, false, 4> THP;        /* the packed shared-memory layouts */
-        typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ;
+        typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ; typedef LzxLaneC<1, 32, false, 104, 1> THQ1;     /* + OPT bit 0 */
         const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
         SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            if (packedq && !wide && (frames_per_round & 0x800)) { THQ1 t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run2(t); t.end(st); }
+            else if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (packed && !wide) { THP t; t.bind((SHP *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
