@@ -83,7 +83,14 @@ template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxShar
 
 /* OPT (experimental shapes, none of them a default until measured on the B200 - tools/variant_bench.py):
  *   bit 0  the refill in front of a match's offset bits only when the bits at hand do not cover them (extra + 4 <= 21 bits): with
- *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them */
+ *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them
+ *   bit 2  extra_bits[] / position_base[] from a 64-entry table in shared memory (one per CTA, lzx_slot_entry) instead of the
+ *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only */
+MS_D uint32_t lzx_slot_entry(uint32_t slot) {          /* extra | (position_base - 2) << 5, lzxd.c:199-255 */
+    const uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+    const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+    return extra | ((pbase - 2u) << 5);
+}
 template <int NT, int HEADN, bool DELTA = false, int H8LB = 0, int OPT = 0>
 struct LzxLaneC {
     typedef typename LzxSharedSel<NT, HEADN, H8LB>::type Shared;
@@ -93,6 +100,7 @@ struct LzxLaneC {
     typedef typename std::conditional<QL, MsBoK<NT>, MsBo32<NT>>::type Bo;
     MsBits b;
     uint32_t *atree, *mhi; uint8_t *mlo, *lhead;  /* packed layouts only */
+    const uint32_t *slot_tab;             /* OPT bit 2: lzx_slot_entry(0..63) */
     uint32_t is_delta, ref_len;           /* DELTA only: this unit is an LZX DELTA stream; bytes of reference data in front of it */
     Bo mbo, lbo; uint32_t *abo;
     uint16_t *mhead, *llim, *alim, *llut, *cnt;
@@ -463,9 +471,13 @@ struct LzxLaneC {
             }
             else {
                 /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
-                uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
-                uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
-                off = pbase - 2;
+                uint32_t extra;
+                if constexpr ((OPT & 4) != 0) { const uint32_t e = slot_tab[slot & 63u]; extra = e & 31u; off = e >> 5; }
+                else {
+                    extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                    const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                    off = pbase - 2;
+                }
                 if constexpr ((OPT & 1) != 0) { if (b.bc < (int) extra + 4) lzx_refill(b); }      /* (still below 32: the buffer has room) */
                 else lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
