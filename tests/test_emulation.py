@@ -274,3 +274,87 @@ def test_device_logic_long_codes_all_layouts(emul, oracle_ref):
         for mode in (1, 0x201, 0x401, 0xC01, 0x101):
             o2, s2 = emul(u, buf, n, mode)
             assert s2[0] == 0 and np.array_equal(o2, o1), (trial, hex(mode))
+
+
+def _compare(emul, oracle_ref, units, comp, out_bytes, what, modes=(1,)):
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, out_bytes, threads=4)
+    for m in modes:
+        o2, s2 = emul(units, comp, out_bytes, m)
+        assert_same(units, o1, s1, o2, s2, f"{what} mode {m:#x}")
+    return s1
+
+
+def test_device_logic_lzx_crafted_repeat_offsets(emul, oracle_ref):
+    """R0-R2 taken from an uncompressed block's header can be anything (lzxd.c:510-515): zero, the window size, beyond it,
+    0xFFFFFFFF.  Units that start with an uncompressed block get such values; the verbatim / aligned blocks after it use them
+    through the repeated-offset slots (eff == 0, off > window, source in front of the unit ...) - same bytes or same error."""
+    import struct
+    rng = np.random.default_rng(7)
+    specials = [0, 1, 2, 3, 100, 32767, 32768, 32769, 65535, 65536, 65537, (1 << 21) - 3, 1 << 21, (1 << 21) + 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF]
+    mutated = 0
+    for wb in (15, 16, 21):
+        b = gen.make_batch(CODEC_LZX, 96, unit_bytes=50000, window_bits=wb, block_mode=4, split=4, first_unit=wb)
+        comp = b.comp.copy()
+        for u in b.units:
+            lo = int(u["in_off"])
+            if ((int(comp[lo]) | (int(comp[lo + 1]) << 8)) >> 12) == 0b0011:        # intel bit 0, block type 3: R0-R2 are bytes 4..15
+                vals = [int(rng.choice(specials)) for _ in range(3)]
+                comp[lo + 4:lo + 16] = np.frombuffer(struct.pack("<III", *vals), dtype=np.uint8)
+                mutated += 1
+        _compare(emul, oracle_ref, b.units, comp, b.out_bytes, f"crafted R wb{wb}", (1, 0x401))
+    assert mutated > 30
+
+
+def test_device_logic_mszip_structural_cases(emul, oracle_ref):
+    """Deflate shapes zlib level 6 never produces by itself: fixed-Huffman and stored blocks, several deflate blocks per CK block
+    (with empty stored ones), Huffman-only and RLE strategies, junk in front of / between CK blocks, empty CK blocks, a block
+    longer than 32 KiB (error), requests that end inside a block, streams a byte short."""
+    import zlib
+    from libmspack_b200.units import UNIT_DTYPE
+    raw = gen.raw_units(1, 400000, data="text").tobytes()
+    rnd = bytes(np.random.default_rng(3).integers(0, 256, 40000, dtype=np.uint8))
+
+    def ck(data, zdict=None, strategy=zlib.Z_DEFAULT_STRATEGY, level=6, flushes=0):
+        kw = {"zdict": zdict} if zdict else {}
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy, **kw)
+        out = b""
+        if flushes:
+            step = max(1, len(data) // (flushes + 1))
+            for k in range(0, len(data), step):
+                out += c.compress(data[k:k + step]) + c.flush(zlib.Z_FULL_FLUSH if (k // step) % 2 else zlib.Z_SYNC_FLUSH)
+        else:
+            out += c.compress(data)
+        return b"CK" + out + c.flush()
+
+    def blk(k, n=32768):
+        return raw[k * 32768:k * 32768 + n]
+    streams = [(ck(blk(0), strategy=zlib.Z_FIXED), 32768), (ck(blk(1), flushes=5), 32768), (ck(blk(2), level=0), 32768),
+               (ck(blk(3)) + b"garbage!!C" + ck(blk(4), zdict=blk(3)), 65536), (b"xxCxK" + ck(blk(5)), 32768),
+               (ck(blk(9)), 20000), (ck(blk(9)) + ck(blk(10), zdict=blk(9)), 40000), (ck(blk(0) + blk(1)[:100]), 32868),
+               (ck(b""), 10), (ck(b"") + ck(blk(2)), 32768), (ck(rnd[:32768], strategy=zlib.Z_HUFFMAN_ONLY), 32768),
+               (ck(blk(3), strategy=zlib.Z_RLE, flushes=2), 32768), (ck(bytes(32768)), 32768), (ck(blk(4))[:-1], 32768),
+               (ck(blk(4)) + b"\0\0\0", 32768)]
+    units = np.zeros(len(streams), dtype=UNIT_DTYPE)
+    comps, ioff, ooff = [], 0, 0
+    for i, (c, n) in enumerate(streams):
+        units[i] = (CODEC_MSZIP, 0, 0, 0, ioff, len(c), n, ooff)
+        pad = (-len(c)) % 4
+        comps.append(c + b"\0" * pad)
+        ioff += len(c) + pad
+        ooff += (n + 15) & ~15
+    comp = np.frombuffer(b"".join(comps) + b"\0" * 16, dtype=np.uint8).copy()
+    s1 = _compare(emul, oracle_ref, units, comp, ooff, "mszip structural", (1, 2))
+    assert list(s1[:7]) == [0] * 7 and s1[7] == 11 and s1[8] == 3          # the long block fails, the lone empty block runs out of input
+
+
+def test_device_logic_quantum_many_window_laps(emul, oracle_ref):
+    """Quantum units much longer than their window (the copy paths at the window's end, qtmd.c:358-416), intact and damaged."""
+    rng = np.random.default_rng(5)
+    for wb, ub in ((10, 100000), (11, 70000), (12, 40000)):
+        b = gen.make_batch(CODEC_QUANTUM, 12, unit_bytes=ub, window_bits=wb)
+        _compare(emul, oracle_ref, b.units, b.comp, b.out_bytes, f"quantum wb{wb}", (1, 2))
+        comp = b.comp.copy()
+        for u in b.units:
+            lo, n = int(u["in_off"]), int(u["in_len"])
+            comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+        _compare(emul, oracle_ref, b.units, comp, b.out_bytes, f"quantum corrupt wb{wb}")
