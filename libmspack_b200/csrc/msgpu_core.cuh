@@ -384,6 +384,17 @@ MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
     else { e.pa = a; e.pb = b; }
     e.nrec++;
 }
+/* experimental (LzxLaneC OPT bit 3): every record leaves by itself as one 8-byte store - no pairing logic in the step, twice the
+ * store instructions.  Same array contents; emit_end_single writes the sentinel. */
+MS_D void emit_match_single(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
+    MsRec r; r.a = pos; r.b = off | (len << 22);
+    e.rec[e.nrec] = r;
+    e.nrec++;
+}
+MS_D void emit_end_single(MsEmit &e, uint32_t frame_size) {
+    emit_flush_literals(e);
+    MsRec r; r.a = frame_size; r.b = 0; e.rec[e.nrec] = r;
+}
 /* LZX DELTA: offsets up to 2^25 (bits 22.. of the offset travel in a's upper half) and lengths up to a whole frame (cut into
  * pieces of at most 1023 bytes with the same offset, which copies the same bytes as the one long match) */
 MS_D void emit_match_wide(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {

@@ -85,7 +85,8 @@ template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxShar
  *   bit 0  the refill in front of a match's offset bits only when the bits at hand do not cover them (extra + 4 <= 21 bits): with
  *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them
  *   bit 2  extra_bits[] / position_base[] from a 64-entry table in shared memory (one per CTA, lzx_slot_entry) instead of the
- *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only */
+ *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only
+ *   bit 3  match records stored one by one (8 bytes each) instead of in pairs */
 MS_D uint32_t lzx_slot_entry(uint32_t slot) {          /* extra | (position_base - 2) << 5, lzxd.c:199-255 */
     const uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
     const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
@@ -394,7 +395,7 @@ struct LzxLaneC {
     MS_M void frame_end() {
         /* :696-697 re-align; after raw bytes the reference's bit buffer is empty and nothing happens */
         if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) { fail(b.err); return; } msb_drop(b, b.bc & 15); }
-        emit_end(em, frame_size);
+        if constexpr ((OPT & 8) != 0 && !DELTA) emit_end_single(em, frame_size); else emit_end(em, frame_size);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = frame_size; fi.g0 = frame_start_pos; fi.valid = 1;
         finfo[f] = fi;
         e8info[frame] = (intel_started && intel_filesize && frame < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 */
@@ -519,7 +520,9 @@ struct LzxLaneC {
             if (bad) { fail(MS_EDECRUNCH); return false; }
         }
         if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return false; }   /* :678-693 every overrun ends in an error */
-        if (DELTA) emit_match_wide(em, q, ml, eff); else emit_match(em, q, ml, eff);
+        if (DELTA) emit_match_wide(em, q, ml, eff);
+        else if constexpr ((OPT & 8) != 0) emit_match_single(em, q, ml, eff);
+        else emit_match(em, q, ml, eff);
         q += ml; this_run -= (int32_t) ml;
         return true;
     }
