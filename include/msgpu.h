@@ -60,6 +60,12 @@ extern "C" {
 #define MSGPU_FLAG_CHAIN_FIRST  0x4u
 #define MSGPU_FLAG_CHAIN_NEXT   0x8u
 #define MSGPU_ERR_CHAIN         100   /* not an MSPACK_ERR_*: "decode this chain as one stream instead" */
+/* MSZIP inside a KWAJ file (mszipd_decompress_kwaj, mszipd.c:462-495; caller kwajd.c:320-322): every block is preceded by a 16-bit
+ * length and the stream ends with a zero length - the amount of output is not known beforehand.  out_len is the CAPACITY of the
+ * unit's output area; the unit ends at the zero length with status 0 and msgpu_last_produced() says how much it produced, or with
+ * MSGPU_ERR_CAPACITY when the area is too small (decode again with a larger one). */
+#define MSGPU_FLAG_MSZIP_KWAJ   0x10u
+#define MSGPU_ERR_CAPACITY      101   /* not an MSPACK_ERR_* */
 
 /* One independent compressed unit.  32 bytes, no padding. */
 typedef struct msgpu_unit {
@@ -111,6 +117,11 @@ int msgpu_decode_batch_device_units(msgpu_ctx *ctx, const msgpu_unit *d_units, s
 int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
                             const void *h_in, size_t in_bytes,
                             void *h_out, size_t out_bytes, int32_t *status);
+
+/* Bytes every unit of the most recent batch produced (complete frames only if the unit failed): produced[0..n).  Valid for a
+ * batch that ran as one wave (n units; up to several thousand units always do, larger ones as far as the scratch budget
+ * reaches); synchronises with the batch.  Returns 0, or MSGPU_ERR_ARGS if the last batch was not a single wave of n units. */
+int msgpu_last_produced(msgpu_ctx *ctx, uint32_t *produced, size_t n);
 
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 uint64_t msgpu_launch_count(const msgpu_ctx *ctx);

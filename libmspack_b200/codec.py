@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("MSGPU_LIB") or os.path.join(PKG, "libmsgpu.so")      
 ABI_SYMBOLS = [
     "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
     "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
-    "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version",
+    "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version", "msgpu_last_produced",
 ]
 
 _lib = None
@@ -48,6 +48,8 @@ def load_library() -> ctypes.CDLL:
     lib.msgpu_decode_batch_device_units.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p, vp]
     lib.msgpu_decode_batch_host.restype = ctypes.c_int
     lib.msgpu_decode_batch_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p]
+    lib.msgpu_last_produced.restype = ctypes.c_int
+    lib.msgpu_last_produced.argtypes = [vp, vp, sz]
     lib.msgpu_launch_count.restype = ctypes.c_uint64
     lib.msgpu_launch_count.argtypes = [vp]
     lib.msgpu_scratch_bytes.restype = ctypes.c_size_t
@@ -130,6 +132,12 @@ class BatchDecoder:
                                               out.ctypes.data, out_bytes, status.ctypes.data)
         self._check(rc)
         return out[:out_bytes], status
+
+    def last_produced(self, n: int) -> np.ndarray:
+        """Bytes each unit of the most recent (single-wave) batch produced - the way to learn a KWAJ unit's size."""
+        out = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.msgpu_last_produced(self.ctx, out.ctypes.data, n))
+        return out
 
     def decode_host_into(self, units: np.ndarray, comp_ptr: int, comp_bytes: int, out_ptr: int, out_bytes: int, status: np.ndarray):
         """Same, with caller-owned (e.g. pinned) host buffers given as raw addresses."""

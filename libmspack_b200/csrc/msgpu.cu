@@ -53,14 +53,14 @@ __device__ __forceinline__ void p1_run(Lane &t)
 
 #define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
 #define MISC_RING  1024u
-template <int NT, int HEADN>
+template <int NT, int HEADN, bool KWAJ = false>
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    ZipLaneC<NT, HEADN> t; t.phase = PH_IDLE;
+    ZipLaneC<NT, HEADN, KWAJ> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
@@ -242,6 +242,8 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
     X(30, 448, 256, 104, 0) X(31, 448, 256, 104, 1) X(32, 448, 256, 104, 2) X(33, 448, 256, 104, 3) X(34, 448, 256, 104, 4) X(35, 448, 256, 104, 7) \
     X(36, 448, 256, 104, 8) X(37, 448, 256, 104, 15) X(40, 448, 224, 105, 0)
 #define QTM_NT 160
+#define ZIPK_NT 448          /* the one shape of the MSZIP instantiation that knows KWAJ framing */
+#define ZIPK_HEADN 124
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
 
@@ -273,6 +275,8 @@ struct msgpu_ctx {
     uint64_t launches = 0;
     size_t scratch_budget = 0;
     int lzx_variant = 0, zip_variant = 0;
+    size_t last_wave_n = 0, last_waves = 0;      /* msgpu_last_produced: units of the most recent wave / waves of the most recent batch */
+    cudaStream_t last_stream = nullptr;
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
@@ -320,6 +324,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRC(id, nt, hn, lb, opt) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb, opt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
+    cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>));
     cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
@@ -372,6 +377,17 @@ extern "C" float msgpu_last_kernel_ms(msgpu_ctx *c) {
     return total;
 }
 
+extern "C" int msgpu_last_produced(msgpu_ctx *ctx, uint32_t *produced, size_t n) {
+    if (!ctx || !produced) return MSGPU_ERR_ARGS;
+    if (ctx->last_waves != 1 || ctx->last_wave_n != n || n == 0) return fail(ctx, MSGPU_ERR_ARGS, "msgpu_last_produced: the last batch was not one wave of n units");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    CK(cudaStreamSynchronize(ctx->last_stream), "sync");
+    /* column `produced` of the state table: one strided copy */
+    CK(cudaMemcpy2D(produced, sizeof(uint32_t), reinterpret_cast<const uint8_t *>(ctx->ustate.p) + offsetof(MsUnitState, produced), sizeof(MsUnitState),
+                    sizeof(uint32_t), n, cudaMemcpyDeviceToHost), "copy produced");
+    return 0;
+}
+
 extern "C" int msgpu_set_stage_timing(msgpu_ctx *c, int on) { if (!c) return MSGPU_ERR_ARGS; c->stage_timing = on ? 1 : 0; return 0; }
 
 extern "C" float msgpu_stage_ms(msgpu_ctx *c, int stage) {
@@ -405,11 +421,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 {
     const uint32_t n = (uint32_t) (hi - lo);
     std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base, chains;
-    uint32_t maxfr = 1, e8total = 0; bool any_zip = false, any_delta = false;
+    uint32_t maxfr = 1, e8total = 0; bool any_zip = false, any_delta = false, any_kwaj = false;
     for (uint32_t i = 0; i < n; i++) {
         const msgpu_unit &u = h_units[lo + i];
         ord[u.codec].push_back(i);
         if (u.codec == MSGPU_CODEC_LZX && ((u.flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(&u))) any_delta = true;
+        if (u.codec == MSGPU_CODEC_MSZIP && (u.flags & MSGPU_FLAG_MSZIP_KWAJ)) any_kwaj = true;
         if (u.codec == MSGPU_CODEC_MSZIP) {          /* block chains: runs of consecutive entries of the MSZIP list */
             if (u.flags & MSGPU_FLAG_CHAIN_FIRST) { chains.push_back((uint32_t) ord[1].size() - 1); chains.push_back(1); }
             else if ((u.flags & MSGPU_FLAG_CHAIN_NEXT) && !chains.empty()) chains.back()++;
@@ -426,6 +443,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
     if (any_delta) lzx_nt = LZXD_NT;
+    if (any_kwaj) zip_nt = ZIPK_NT;
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
@@ -567,9 +585,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         WaveArgs w = a; w.sub = (int) sub;
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
             mark(0, st);
-#define LAUNCHZC(id, nt, hn) if (ctx->zip_variant == id) k_p1_mszip<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+#define LAUNCHZC(id, nt, hn) if (!any_kwaj && ctx->zip_variant == id) k_p1_mszip<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             ZIPC_VARIANTS(LAUNCHZC)
 #undef LAUNCHZC
+            if (any_kwaj) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);
             k_p2_ring<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
@@ -682,12 +701,14 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
+    ctx->last_waves = 0; ctx->last_stream = s;
     for (size_t lo = 0; lo < n;) {
         size_t hi = lo + slots < n ? lo + slots : n;
         while (hi < n && hi > lo && (units[hi].flags & MSGPU_FLAG_CHAIN_NEXT)) hi--;       /* a chain stays inside one wave */
         if (hi == lo) return fail(ctx, MSGPU_ERR_NOMEMORY, "a block chain does not fit the scratch budget");
         int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, h_in, h_out);
         if (r) return r;
+        ctx->last_waves++; ctx->last_wave_n = hi - lo;
         lo = hi;
     }
     return 0;

@@ -34,7 +34,8 @@ struct ZipSharedC {
     uint16_t cnt[17 * NT];
 };
 
-template <int NT, int HEADN>
+/* KWAJ = the instantiation that also understands MSGPU_FLAG_MSZIP_KWAJ units (mszipd_decompress_kwaj, mszipd.c:462-495) */
+template <int NT, int HEADN, bool KWAJ = false>
 struct ZipLaneC {
     MsBits b;
     uint32_t *lbo, *dbo; uint16_t *lhead, *dhead, *blim, *cnt;   /* this lane's columns of the shared tables */
@@ -217,7 +218,22 @@ struct ZipLaneC {
     MS_M void frame_start() {
         int state = 0;
         lsb_align_byte(b);
-        do {
+        if (KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ)) {
+            /* :471-481: a 16-bit block length (0 ends the stream; otherwise its value is not used), then 'C', 'K' right away */
+            lsb_refill(b);
+            uint32_t block_len = lsb_read(b, 8); block_len |= lsb_read(b, 8) << 8;
+            if (b.err) { fail(b.err); return; }
+            if (block_len == 0) { done = 1; phase = PH_IDLE; return; }
+            lsb_refill(b);
+            uint32_t c = lsb_read(b, 8);
+            if (b.err) { fail(b.err); return; }
+            if (c != 'C') { fail(MSGPU_ERR_DATAFORMAT); return; }
+            c = lsb_read(b, 8);
+            if (b.err) { fail(b.err); return; }
+            if (c != 'K') { fail(MSGPU_ERR_DATAFORMAT); return; }
+            state = 2;
+        }
+        else do {
             lsb_refill(b);
             uint32_t c = lsb_read(b, 8);
             if (b.err) { fail(b.err); return; }
@@ -232,6 +248,8 @@ struct ZipLaneC {
         /* a block that grew past 32 KiB keeps being decoded by the reference (so a read error can still win)
          * and only fails at its next window flush (:308-311, :323-333) */
         if (q > MS_FRAME) { fail(MS_EDECRUNCH); return; }
+        const bool kwaj = KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ);
+        if (kwaj && q > u->out_len - produced) { fail(MSGPU_ERR_CAPACITY); return; }        /* out_len is the capacity of the output area */
         uint32_t n = ms_min(u->out_len - produced, q);
         emit_end(em, q);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced;
@@ -246,7 +264,7 @@ struct ZipLaneC {
         finfo[f] = fi;
         const uint32_t g0 = produced;
         produced += n; frame++; f++;
-        if (produced >= u->out_len) { done = 1; phase = PH_IDLE; }
+        if (produced >= u->out_len && !kwaj) { done = 1; phase = PH_IDLE; }               /* (a KWAJ stream ends at its zero length only) */
         else if (hist_push(q, g0)) phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
     }
 
@@ -320,7 +338,7 @@ struct ZipLaneC {
             done = 0; status = 0; produced = 0; frame = 0;
             hist_ptr()[2 * P2_HIST_K * 32] = 0;
             ms_bits_init(b, in_base + unit->in_off, unit->in_len);
-            if (unit->out_len == 0) done = 1;
+            if (unit->out_len == 0 && !(KWAJ && (unit->flags & MSGPU_FLAG_MSZIP_KWAJ))) done = 1;
         }
         else {
             done = st.done; status = st.status; produced = st.produced; frame = st.frame;

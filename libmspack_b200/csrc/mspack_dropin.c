@@ -213,8 +213,40 @@ struct mszipd_stream *mszipd_init(struct mspack_system *system, struct mspack_fi
 }
 int mszipd_decompress(struct mszipd_stream *zip, off_t out_bytes) { return ds_decompress((struct dstream *) zip, out_bytes); }
 int mszipd_decompress_kwaj(struct mszipd_stream *zip) {
-    /* KWAJ framing (kwajd.c:320-322, mszipd.c:462-495) is outside the CAB-folder hot path; the symbol exists so
-     * that kwajd.c links, the call reports a format error */
-    return zip ? MSPACK_ERR_DATAFORMAT : MSPACK_ERR_ARGS;
+    /* KWAJ framing (mszipd.c:462-495; caller kwajd.c:320-322): blocks until a zero length, so the amount of output is only known
+     * afterwards.  The unit gets an output area sized from the input and grows it if the device says MSGPU_ERR_CAPACITY.
+     * Like the reference, whatever decoded before an error has been written when the error is returned. */
+    struct dstream *s = (struct dstream *) zip;
+    size_t cap; int e;
+    if (!s) return MSPACK_ERR_ARGS;
+    if (s->error) return s->error;
+    if ((e = ds_slurp(s))) return s->error = e;
+    if (s->in_len >= 0x7FFFFFF0u) return s->error = MSPACK_ERR_DECRUNCH;
+    cap = s->in_len * 8 + 65536;
+    for (;;) {
+        msgpu_unit u; int32_t st = -1; uint32_t produced = 0; int rc; unsigned char *buf; size_t off;
+        if (cap > 0xFFFF0000u) cap = 0xFFFF0000u;
+        buf = (unsigned char *) realloc(s->out, cap + 64);
+        if (!buf) return s->error = MSPACK_ERR_NOMEMORY;
+        s->out = buf; s->out_base = 0;
+        memset(&u, 0, sizeof(u));
+        u.codec = MSGPU_CODEC_MSZIP; u.flags = MSGPU_FLAG_MSZIP_KWAJ;
+        u.in_len = (uint32_t) s->in_len; u.out_len = (uint32_t) cap;
+        pthread_mutex_lock(&g_mu);
+        rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len, s->out, cap, &st);
+        if (!rc) rc = msgpu_last_produced(ctx_get(), &produced, 1);
+        pthread_mutex_unlock(&g_mu);
+        if (rc) return s->error = MSPACK_ERR_NOMEMORY;
+        if (st == MSGPU_ERR_CAPACITY && cap < 0xFFFF0000u) { cap *= 4; continue; }
+        if (st == MSGPU_ERR_CAPACITY) st = MSPACK_ERR_DECRUNCH;
+        for (off = 0; off < produced;) {              /* mszipd.c:489-491 */
+            int n = produced - off > (1u << 20) ? (1 << 20) : (int) (produced - off);
+            if (s->sys->write(s->output, s->out + off, n) != n) return s->error = MSPACK_ERR_WRITE;
+            off += (size_t) n;
+        }
+        /* (like the reference, a format error in front of a block is returned without becoming sticky, mszipd.c:478-479) */
+        if (st != MSPACK_ERR_OK && st != MSPACK_ERR_DATAFORMAT) s->error = st;
+        return st;
+    }
 }
 void mszipd_free(struct mszipd_stream *zip) { ds_free((struct dstream *) zip); }

@@ -14,6 +14,9 @@ assert UNIT_DTYPE.itemsize == 32
 CODEC_MSZIP, CODEC_QUANTUM, CODEC_LZX = 1, 2, 3
 FLAG_MSZIP_REPAIR = 0x1
 FLAG_LZX_DELTA = 0x2          # include/msgpu.h MSGPU_FLAG_LZX_DELTA
+FLAG_CHAIN_FIRST, FLAG_CHAIN_NEXT = 0x4, 0x8   # MSZIP block chains
+FLAG_MSZIP_KWAJ = 0x10        # MSZIP inside a KWAJ file: out_len is a capacity, the stream ends at a zero block length
+ERR_CHAIN, ERR_CAPACITY = 100, 101
 FLAG_REF_SHIFT = 6            # flags >> 6 = LZX DELTA reference bytes stored in front of the unit's output
 
 # MSPACK_ERR_* (libmspack/mspack/mspack.h:485-507)

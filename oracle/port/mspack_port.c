@@ -349,6 +349,24 @@ static int port_mszip(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint
     uint32_t done = 0; int ret = ERR_OK;
     if (!z) return ERR_NOMEM;
     z->b.in = in; z->b.in_len = u->in_len;
+    if (u->flags & MSGPU_FLAG_MSZIP_KWAJ) {                        /* mszipd.c:462-495 mszipd_decompress_kwaj */
+        for (;;) {
+            uint32_t block_len, c, n; int error;
+            z->b.p = (z->b.p + 7) & ~(uint64_t) 7;
+            block_len = lsb_read(&z->b, 8); block_len |= lsb_read(&z->b, 8) << 8;
+            if (z->b.err) { ret = ERR_READ; goto out; }
+            if (block_len == 0) break;
+            c = lsb_read(&z->b, 8); if (z->b.err) { ret = ERR_READ; goto out; } if (c != 'C') { ret = MSGPU_ERR_DATAFORMAT; goto out; }
+            c = lsb_read(&z->b, 8); if (z->b.err) { ret = ERR_READ; goto out; } if (c != 'K') { ret = MSGPU_ERR_DATAFORMAT; goto out; }
+            z->window_posn = 0; z->bytes_output = 0;
+            error = zip_inflate(z);
+            if (error) { ret = (error > 0) ? error : ERR_DECRUNCH; goto out; }
+            n = z->bytes_output;
+            if (n > u->out_len - done) { memcpy(out + done, z->window, u->out_len - done); done = u->out_len; ret = MSGPU_ERR_CAPACITY; goto out; }
+            memcpy(out + done, z->window, n); done += n;
+        }
+        goto out;
+    }
     while (done < u->out_len) {
         int state = 0, error; uint32_t n;
         z->b.p = (z->b.p + 7) & ~(uint64_t) 7;                    /* :405 align to bytestream */

@@ -80,7 +80,8 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
                                               (struct mspack_file *) &f, 4096,
                                               (u->flags & MSGPU_FLAG_MSZIP_REPAIR) ? 1 : 0);
         if (!z) { err = MSPACK_ERR_NOMEMORY; break; }
-        err = mszipd_decompress(z, (off_t) u->out_len);
+        if (u->flags & MSGPU_FLAG_MSZIP_KWAJ) err = mszipd_decompress_kwaj(z);       /* out_len is only the capacity (mem_write drops the rest) */
+        else err = mszipd_decompress(z, (off_t) u->out_len);
         mszipd_free(z);
         break;
     }

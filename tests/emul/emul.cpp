@@ -81,6 +81,8 @@ static void emul_run2(Lane &t) {      /* p1_run<Lane, TWO = true> */
     }
 }
 
+static uint32_t g_last_produced;
+extern "C" uint32_t emul_last_produced() { return g_last_produced; }
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     const int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
@@ -107,12 +109,13 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
-        typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH;
+        typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH; typedef ZipLaneC<1, 32, true> THK;     /* THK: units with KWAJ framing */
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) aligned_alloc(64, (ZIP_AUX_BYTES + 63) & ~(size_t) 63); memset(aux, 0, ZIP_AUX_BYTES);   /* 32-byte aligned like the device's */
+        const bool kwaj = (u->flags & MSGPU_FLAG_MSZIP_KWAJ) != 0;
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            TH t; t.bind(sh, 0, aux, 0);
-            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F);
-            emul_run(t); t.end(st); resolve();
+            if (kwaj) { THK t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
+            else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
+            resolve();
         }
         free(sh); free(aux);
     }
@@ -148,6 +151,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(save);
     }
     else return MS_EARGS;
+    g_last_produced = st.produced;
     return st.status;
 }
 

@@ -358,3 +358,46 @@ def test_device_logic_quantum_many_window_laps(emul, oracle_ref):
             lo, n = int(u["in_off"]), int(u["in_len"])
             comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
         _compare(emul, oracle_ref, b.units, comp, b.out_bytes, f"quantum corrupt wb{wb}")
+
+
+def test_device_logic_mszip_kwaj_framing(emul, oracle_ref):
+    """mszipd_decompress_kwaj (mszipd.c:462-495): blocks behind 16-bit lengths until a zero length; out_len is only the capacity
+    of the output area.  Same bytes, same produced size, same status as the reference - including a missing terminator (the
+    reference's two free zero bytes at EOF end the stream), a bad signature (DATAFORMAT), a damaged block, a too small area."""
+    import ctypes
+    from libmspack_b200.units import UNIT_DTYPE, FLAG_MSZIP_KWAJ
+    from util import kwaj_mszip_stream
+    cases = [([32768, 32768, 5000], {}), ([100, 32768, 7, 20000], {}), ([32768], dict(terminator=False)), ([3000] * 12, {}), ([], {})]
+    streams = [kwaj_mszip_stream(l, seed=i, **kw) for i, (l, kw) in enumerate(cases)]
+    bad_sig = bytearray(streams[0][0]); bad_sig[2 + 32768 // 8] ^= 0; bad_sig[2] = ord("X")
+    streams.append((bytes(bad_sig), b""))
+    dmg = bytearray(streams[1][0]); dmg[len(dmg) // 2] ^= 0x10
+    streams.append((bytes(dmg), None))
+    units = np.zeros(len(streams) + 1, dtype=UNIT_DTYPE)
+    comps, ioff, ooff = [], 0, 0
+    for i, (c, out) in enumerate(streams + [streams[0]]):
+        cap = 200000 if i < len(streams) else 40000                 # the last one: the area is too small
+        units[i] = (CODEC_MSZIP, 0, 0, FLAG_MSZIP_KWAJ, ioff, len(c), cap, ooff)
+        pad = (-len(c)) % 4
+        comps.append(c + b"\0" * pad)
+        ioff += len(c) + pad
+        ooff += (cap + 15) & ~15
+    comp = np.frombuffer(b"".join(comps) + b"\0" * 16, dtype=np.uint8).copy()
+    ref_decode = oracle_ref._decode
+    for i in range(len(units)):
+        out_ref = np.zeros(ooff, np.uint8)
+        prod = ctypes.c_uint32(0)
+        st_ref = ref_decode(units[i:i + 1].ctypes.data, comp.ctypes.data, out_ref.ctypes.data, ctypes.byref(prod))
+        for fpr in (1, 2):
+            o2, s2 = emul(units[i:i + 1], comp, ooff, fpr)
+            lo = int(units[i]["out_off"])
+            if i == len(units) - 1:
+                assert int(s2[0]) == 101                             # MSGPU_ERR_CAPACITY; the reference's writer just drops the surplus
+                continue
+            assert int(s2[0]) == st_ref, (i, int(s2[0]), st_ref)
+            if st_ref == 0:
+                n = prod.value
+                assert np.array_equal(o2[lo:lo + n], out_ref[lo:lo + n]), i
+                if streams[i][1] is not None:
+                    assert o2[lo:lo + n].tobytes() == streams[i][1]
+    assert ref_decode is not None

@@ -118,3 +118,22 @@ def chain_batch(folder_bytes, data="text", damage=None):
     chain = gen.Batch(np.array(cu, dtype=UNIT_DTYPE), comp, None, ooff)
     plain = gen.Batch(np.array(pu, dtype=UNIT_DTYPE), comp, None, ooff)
     return chain, plain, raws
+
+
+def kwaj_mszip_stream(lens, seed=0, terminator=True):
+    """The MSZIP payload of a KWAJ file (mszipd.c:462-495): per block a 16-bit length, 'CK', a deflate block; a zero length ends it.
+    Blocks may have any length <= 32768 and see the 32 KiB ring like a CAB folder's.  Returns (stream, expected output)."""
+    import zlib
+    from libmspack_b200 import gen
+    raw = gen.raw_units(1, int(sum(lens)) + 1, data="text", first_unit=seed + 77).tobytes()
+    win, comp, out, pos = bytearray(32768), b"", b"", 0
+    for k, n in enumerate(lens):
+        data = raw[pos:pos + n]
+        pos += n
+        kw = {"zdict": bytes(win)} if k else {}
+        c = zlib.compressobj(6, zlib.DEFLATED, -15, **kw)
+        blk = b"CK" + c.compress(data) + c.flush()
+        comp += len(blk).to_bytes(2, "little") + blk
+        out += data
+        win[0:n] = data
+    return comp + (b"\0\0" if terminator else b""), out
