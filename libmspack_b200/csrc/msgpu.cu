@@ -443,10 +443,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     LZXC_VARIANTS(PICKNTC)
 #undef PICKNTC
     if (any_delta) lzx_nt = LZXD_NT;
-    if (any_kwaj) zip_nt = ZIPK_NT;
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
+    if (any_kwaj) zip_nt = ZIPK_NT;
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
