@@ -41,7 +41,10 @@ extern "C" {
 #define MSGPU_ERR_DECRUNCH   11
 
 /* unit flags */
-#define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:422-433: reserved, not implemented */
+#define MSGPU_FLAG_MSZIP_REPAIR 0x1u  /* mszipd_init(repair_mode=1), mszipd.c:420-433: a block that does not inflate is zero-filled to 32 KiB
+                                       * and decoding goes on behind it.  WHERE the reference goes on depends on the size of its input
+                                       * buffer (its stale bit state): flags >> MSGPU_FLAG_REF_SHIFT = that size, 0 = 4096
+                                       * (cabd.c's default) */
 #define MSGPU_FLAG_LZX_DELTA    0x2u  /* lzxd_init(is_delta=1): LZX DELTA stream (lzxd.c:289-296, :441-444, :589-611), window_bits 17..25 */
 #define MSGPU_FLAG_REF_SHIFT    6     /* flags >> 6 = bytes of LZX DELTA reference data (lzxd_set_reference_data, lzxd.c:348-382;
                                        * <= the window size).  The caller stores them in the OUTPUT buffer directly in front

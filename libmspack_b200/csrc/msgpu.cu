@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     p1_run(t);
     if (valid) {
         t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u);
-        if (t.f > 0 && a.finfo[(size_t) slot * a.F + t.f - 1].valid == 2u) a.not_done[MISC_RING + a.sub] = 1u;          /* frames for k_p2_ring (ring is sticky) */
+        if (KWAJ) {          /* (the special instantiation also makes overflow frames, valid == 4, and may use two frame slots for one block) */
+            bool any = false;
+            for (int k = 0; k < t.f; k++) { const uint32_t v = a.finfo[(size_t) slot * a.F + k].valid; any = any || v == 2u || v == 4u; }
+            if (any) a.not_done[MISC_RING + a.sub] = 1u;
+        }
+        else if (t.f > 0 && a.finfo[(size_t) slot * a.F + t.f - 1].valid == 2u) a.not_done[MISC_RING + a.sub] = 1u;          /* frames for k_p2_ring (ring is sticky) */
     }
 }
 
@@ -151,6 +156,9 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
 /* MSZIP frames decoded after a block shorter than 32 KiB (MsFrameInfo::valid == 2): the same resolve, with sources in front of
  * the frame looked up through the ring history P1 attached to the frame (msgpu_p2.cuh "MSZIP ring history").  Runs after
  * k_p2_resolve on the same stream; leaves at once unless P1 flagged such frames in this sub-wave. */
+/* OVF: the same for the overflow frames of repair-mode MSZIP blocks (valid == 4: a ring frame whose literals sit in a plane
+ * inside its record array, ZipLaneC::qbase); launched after k_p2_ring<false> in waves that hold special MSZIP units */
+template <bool OVF>
 __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_ring(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
@@ -165,13 +173,14 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_ring(WaveArgs a, const uin
     uint8_t *unit_out = a.out_base + a.units[slot].out_off;
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
-        if (fi.valid != 2u || fi.size == 0) continue;
+        if (fi.valid != (OVF ? 4u : 2u) || fi.size == 0) continue;
         __syncwarp();
         const uint32_t *sn = reinterpret_cast<const uint32_t *>(a.recs + ((size_t) slot * a.F + f) * MS_MAXREC + P2_HIST_REC);
         for (int j = lane; j < (int) P2_HIST_WORDS; j += 32) s_hist[warp][j] = sn[j];
         __syncwarp();
-        p2_resolve_frame<false, true>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
-                                      s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], 0u, s_hist[warp]);
+        p2_resolve_frame<false, true, OVF>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+                                           s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], 0u, s_hist[warp],
+                                           OVF ? reinterpret_cast<const uint8_t *>(a.recs + ((size_t) slot * a.F + f) * MS_MAXREC + P2_PLANE_REC) : nullptr);
     }
 }
 
@@ -426,7 +435,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         const msgpu_unit &u = h_units[lo + i];
         ord[u.codec].push_back(i);
         if (u.codec == MSGPU_CODEC_LZX && ((u.flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(&u))) any_delta = true;
-        if (u.codec == MSGPU_CODEC_MSZIP && (u.flags & MSGPU_FLAG_MSZIP_KWAJ)) any_kwaj = true;
+        if (u.codec == MSGPU_CODEC_MSZIP && (u.flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR))) any_kwaj = true;      /* the special MSZIP instantiation */
         if (u.codec == MSGPU_CODEC_MSZIP) {          /* block chains: runs of consecutive entries of the MSZIP list */
             if (u.flags & MSGPU_FLAG_CHAIN_FIRST) { chains.push_back((uint32_t) ord[1].size() - 1); chains.push_back(1); }
             else if ((u.flags & MSGPU_FLAG_CHAIN_NEXT) && !chains.empty()) chains.back()++;
@@ -435,7 +444,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (u.codec == MSGPU_CODEC_LZX) { e8base.push_back(e8total); e8total += fr ? fr : 1; }
         if (u.codec == MSGPU_CODEC_MSZIP) any_zip = true;
     }
-    const int F = maxfr >= 2 ? 2 : 1;
+    const int F = (maxfr >= 2 || any_kwaj) ? 2 : 1;            /* (a repair-mode MSZIP block may need two frame slots) */
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
     uint32_t lzx_nt = 128, zip_nt = 128;
@@ -591,8 +600,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (any_kwaj) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);
-            k_p2_ring<<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
+            k_p2_ring<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
             ctx->launches += 3;
+            if (any_kwaj) { k_p2_ring<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches++; }
             if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
             mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
@@ -695,7 +705,7 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
         }
     }
     /* wave size from the scratch budget */
-    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
+    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; if (units[i].codec == MSGPU_CODEC_MSZIP && (units[i].flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR))) maxfr = maxfr < 2 ? 2 : maxfr; }
     const int F = maxfr >= 2 ? 2 : 1;
     size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec)) + sizeof(MsUnitState) + 10240;      /* + the largest per-lane aux share (LZX_AUX_BYTES / 32) */
     size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;

@@ -34,9 +34,29 @@ struct ZipSharedC {
     uint16_t cnt[17 * NT];
 };
 
-/* KWAJ = the instantiation that also understands MSGPU_FLAG_MSZIP_KWAJ units (mszipd_decompress_kwaj, mszipd.c:462-495) */
+/* KWAJ = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
+ * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
 template <int NT, int HEADN, bool KWAJ = false>
 struct ZipLaneC {
+    /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
+     * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
+     * against the reference): the buffered bits are those of the STORE, and the byte pointer is the STORE's only if read_input has
+     * not refilled the input buffer since - a refill resets it to the buffer's start.  So the lane tracks what the reference has
+     * FETCHED (fx: every ENSURE_BITS / READ_IF_NEEDED of the reference is a rd() / ck() here) and remembers position, fetch extent
+     * and buffered bits at every STORE. */
+    int32_t fx, store_fx; int64_t store_p; uint32_t store_val, in_block;
+    /* A block that grows past 32 KiB is not an error yet for the reference: its window position wraps to 0 and the block goes on
+     * OVERWRITING the start of the window until the next flush fails (mszipd.c:38-45, :323-333).  In repair mode that window image
+     * is what gets written, so the overflow is kept as a second frame at the SAME output position (qbase = 32768, records at
+     * q - qbase): to the resolve stage it is an ordinary ring frame whose one history entry is the block's first 32 KiB. */
+    uint32_t qbase;
+    MS_M bool repairing() const { return KWAJ && (u->flags & MSGPU_FLAG_MSZIP_REPAIR); }
+    MS_M void trk(int n) { if (KWAJ) { const int32_t need = (int32_t) ((ms_bitpos(b) + n + 7) >> 3); if (need > fx) fx = need; } }
+    MS_M uint32_t rd(int n) { trk(n); return lsb_read(b, n); }
+    MS_M void ck(int n) { trk(n); lsb_check(b, n); }
+    MS_M void store_bits() {           /* STORE_BITS: position, fetch extent, the bits fetched but not consumed */
+        if (KWAJ) { lsb_refill(b); store_p = ms_bitpos(b); store_fx = fx; const int64_t ns = (int64_t) store_fx * 8 - store_p; store_val = (uint32_t) b.bb & (ns > 0 ? (ns >= 32 ? 0xFFFFFFFFu : ((1u << ns) - 1u)) : 0u); }
+    }
     MsBits b;
     uint32_t *lbo, *dbo; uint16_t *lhead, *dhead, *blim, *cnt;   /* this lane's columns of the shared tables */
     uint8_t *lens;                        /* aux, stride 32 */
@@ -114,13 +134,13 @@ struct ZipLaneC {
     MS_M int read_lens() {
         const uint8_t order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
         lsb_refill(b);
-        uint32_t lit_codes = lsb_read(b, 5) + 257, dist_codes = lsb_read(b, 5) + 1, bl_codes = lsb_read(b, 4) + 4;
+        uint32_t lit_codes = rd(5) + 257, dist_codes = rd(5) + 1, bl_codes = rd(4) + 4;
         if (b.err) return b.err;
         if (lit_codes > 288 || dist_codes > 32) return MS_EDECRUNCH;
         /* 19 code-length-code lengths, 3 bits each, packed into a 64-bit register */
         uint64_t bl = 0;
 #pragma unroll 1
-        for (uint32_t i = 0; i < bl_codes; i++) { lsb_refill(b); bl |= (uint64_t) lsb_read(b, 3) << (3 * order[i]); }
+        for (uint32_t i = 0; i < bl_codes; i++) { lsb_refill(b); bl |= (uint64_t) rd(3) << (3 * order[i]); }
         if (b.err) return b.err;
         uint32_t lv[16];
         if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (bl >> (3 * s)) & 7u; }, 19, 7, dbo, cnt, ba.sorted, (uint16_t *) nullptr, 0,
@@ -131,7 +151,7 @@ struct ZipLaneC {
 #pragma unroll 1
         for (uint32_t i = 0; i < total;) {
             lsb_refill(b);
-            lsb_check(b, 7);                                   /* :117 ENSURE_BITS(7) */
+            ck(7);                                   /* :117 ENSURE_BITS(7) */
             uint32_t v = v16();
             int cl = ms_canon_len_smem<NT>(blim, v);
             uint32_t code = ba.sorted[ms_canon_index<NT>(dbo, v, cl) * MS_WARP]; lsb_drop(b, cl);
@@ -139,9 +159,9 @@ struct ZipLaneC {
             if (code < 16) { lens[i * 32] = (uint8_t) code; last_code = code; i++; }
             else {
                 uint32_t run, val;
-                if (code == 16) { run = lsb_read(b, 2) + 3; val = last_code; }
-                else if (code == 17) { run = lsb_read(b, 3) + 3; val = 0; }
-                else if (code == 18) { run = lsb_read(b, 7) + 11; val = 0; }
+                if (code == 16) { run = rd(2) + 3; val = last_code; }
+                else if (code == 17) { run = rd(3) + 3; val = 0; }
+                else if (code == 18) { run = rd(7) + 11; val = 0; }
                 else return MS_EDECRUNCH;
                 if (b.err) return b.err;
                 if (i + run > total) return MS_EDECRUNCH;      /* INF_ERR_BITOVERRUN */
@@ -161,34 +181,96 @@ struct ZipLaneC {
         return 0;
     }
 
-    MS_M void fail(int err) { status = err; done = 1; phase = PH_IDLE; }
+    MS_M void fail(int err) {
+        if (KWAJ && in_block && repairing()) { repair_block(err); return; }
+        status = err; done = 1; phase = PH_IDLE;
+    }
+
+    /* the block has filled its 32 KiB: close that frame, open the overflow frame in the next slot (same output position) */
+    MS_M void start_overflow() {
+        /* the overflow reads the block's first 32 KiB back; if the unit's out_len cuts that frame short (only its last frame can
+         * be) those bytes have no place to live: refuse loudly rather than read outside the unit (stated deviation) */
+        if (em.limit < MS_FRAME) { in_block = 0; status = MS_EDECRUNCH; done = 1; phase = PH_IDLE; return; }
+        emit_end(em, MS_FRAME);
+        MsFrameInfo fi; fi.nrec = em.nrec; fi.size = ms_min(u->out_len - produced, MS_FRAME); fi.g0 = produced;
+        fi.valid = (frame && hist_snapshot(recs + (size_t) f * MS_MAXREC)) ? 2u : 1u;
+        finfo[f] = fi;
+        /* the overflow frame's literals go to its plane, not to the output (msgpu_p2.cuh P2_PLANE_REC) */
+        emit_begin(em, recs + (size_t) (f + 1) * MS_MAXREC, reinterpret_cast<uint8_t *>(recs + (size_t) (f + 1) * MS_MAXREC + P2_PLANE_REC),
+                   ms_min(MS_FRAME, u->out_len - produced));
+        qbase = MS_FRAME;
+    }
+
+    /* mszipd.c:420-433 + :404: give the block up - keep what it decoded, zero-fill the rest of its 32 KiB, go on behind it */
+    MS_M void repair_block(int err) {
+        in_block = 0;
+        if (qbase) {
+            /* the overflow frame: q - 32768 bytes (at most 32 KiB) on top of the block's first 32 KiB, which is its whole history */
+            const uint32_t nov = ms_min(q - MS_FRAME, MS_FRAME);
+            emit_end(em, nov);
+            uint32_t *sn = reinterpret_cast<uint32_t *>(recs + (size_t) (f + 1) * MS_MAXREC + P2_HIST_REC);
+            sn[0] = 1u; sn[1] = MS_FRAME; sn[2] = produced;
+            MsFrameInfo fi; fi.nrec = em.nrec; fi.size = ms_min(em.limit, nov); fi.g0 = produced; fi.valid = 4u;      /* 4: ring frame with a literal plane */
+            finfo[f + 1] = fi;
+            const uint32_t g0 = produced;
+            produced += ms_min(u->out_len - produced, MS_FRAME); frame++; f += 2; qbase = 0;
+            if (produced >= u->out_len) { done = 1; phase = PH_IDLE; }
+            else if (!hist_push(MS_FRAME, g0)) return;
+        }
+        else {
+#pragma unroll 1
+            for (uint32_t k = q < MS_FRAME ? q : MS_FRAME; k < em.limit; k++) emit_literal(em, k, 0);
+            q = MS_FRAME;
+            if (!finish_frame()) return;
+        }
+        if (err == MS_EREAD) { status = MS_EREAD; done = 1; phase = PH_IDLE; return; }      /* :448 read errors stay fatal (after the frame went out) */
+        if (done) return;
+        /* where the reference goes on: the whole bytes left in the bit buffer of the last STORE_BITS, then its byte pointer - the
+         * STORE's, or the start of the input buffer if that has been refilled since (chunks of `size` bytes of the stream; the two
+         * zero bytes invented at the end of the input are a chunk of their own) */
+        uint32_t size = MSGPU_UNIT_REF_BYTES(u) ? MSGPU_UNIT_REF_BYTES(u) : 4096u; size = (size + 1u) & ~1u;
+        const int32_t cnow = fx - 1 >= b.in_len ? b.in_len : (int32_t) ((uint32_t) (fx - 1) / size * size);
+        const int32_t csto = store_fx - 1 >= b.in_len ? b.in_len : (int32_t) ((uint32_t) (store_fx - 1) / size * size);
+        const int32_t r = (fx > 0 && (store_fx == 0 || cnow != csto)) ? cnow : store_fx;
+        const int64_t ns = (int64_t) store_fx * 8 - store_p;
+        const uint32_t nb = ns > 0 ? (uint32_t) (ns >> 3) : 0u;                               /* :405 drops the ns & 7 odd bits */
+        const uint64_t stale = (uint64_t) (store_val >> (ns & 7)) & ((1ull << (8 * nb)) - 1ull);
+        b.err = 0;
+        lsb_seek_byte(b, r);
+        b.bb = (b.bb << (8 * nb)) | stale; b.bc += (int32_t) (8 * nb);
+        fx = r;
+        phase = (f + 2 <= max_frames) ? PH_FRAME : PH_IDLE;           /* (a repair unit's block may need two frame slots) */
+    }
 
     /* mszipd.c:159-241: one deflate block header.  Stored blocks are copied right here. */
     MS_M void block_header() {
         lsb_refill(b);
-        last_block = lsb_read(b, 1);
-        uint32_t type = lsb_read(b, 2);
+        last_block = rd(1);
+        uint32_t type = rd(2);
         if (b.err) { fail(b.err); return; }
         if (type == 0) {
             /* stored block :165-207 */
             lsb_align_byte(b);
-            lsb_refill(b); uint32_t len = lsb_read(b, 16);
-            lsb_refill(b); uint32_t clen = lsb_read(b, 16);
+            lsb_refill(b); uint32_t len = rd(16);
+            lsb_refill(b); uint32_t clen = rd(16);
             if (b.err) { fail(b.err); return; }
             if (len != (~clen & 0xFFFFu)) { fail(MS_EDECRUNCH); return; }
             {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
                 int32_t bp = lsb_bytepos(b);
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
                     emit_raw(em, q, b.in, bp, len);
-                    q += len; lsb_seek_byte(b, bp + (int32_t) len); len = 0;
+                    q += len; lsb_seek_byte(b, bp + (int32_t) len);
+                    if (KWAJ && bp + (int32_t) len > fx) fx = bp + (int32_t) len;
+                    len = 0;
                 }
             }
 #pragma unroll 1
             for (uint32_t k = 0; k < len; k++) {
                 lsb_refill(b);
-                uint32_t v = lsb_read(b, 8);
+                uint32_t v = rd(8);
                 if (b.err) { fail(b.err); return; }
-                emit_literal_checked(em, q, v);
+                if (KWAJ && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+                emit_literal_checked(em, q - (KWAJ ? qbase : 0u), v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
             phase = last_block ? PH_END : PH_BLOCK;
@@ -209,7 +291,7 @@ struct ZipLaneC {
                 for (int j = 0; j < 15; j++) dlim[j] = lv[j];
             }
         }
-        else e = read_lens();
+        else { store_bits(); e = read_lens(); if (!e) store_bits(); }                     /* mszipd.c:223, :149 */
         if (e) { fail(e); return; }
         phase = PH_DECODE;
     }
@@ -221,26 +303,27 @@ struct ZipLaneC {
         if (KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ)) {
             /* :471-481: a 16-bit block length (0 ends the stream; otherwise its value is not used), then 'C', 'K' right away */
             lsb_refill(b);
-            uint32_t block_len = lsb_read(b, 8); block_len |= lsb_read(b, 8) << 8;
+            uint32_t block_len = rd(8); block_len |= rd(8) << 8;
             if (b.err) { fail(b.err); return; }
             if (block_len == 0) { done = 1; phase = PH_IDLE; return; }
             lsb_refill(b);
-            uint32_t c = lsb_read(b, 8);
+            uint32_t c = rd(8);
             if (b.err) { fail(b.err); return; }
             if (c != 'C') { fail(MSGPU_ERR_DATAFORMAT); return; }
-            c = lsb_read(b, 8);
+            c = rd(8);
             if (b.err) { fail(b.err); return; }
             if (c != 'K') { fail(MSGPU_ERR_DATAFORMAT); return; }
             state = 2;
         }
         else do {
             lsb_refill(b);
-            uint32_t c = lsb_read(b, 8);
+            uint32_t c = rd(8);
             if (b.err) { fail(b.err); return; }
             if (c == 'C') state = 1; else if (state == 1 && c == 'K') state = 2; else state = 0;
         } while (state != 2);
         emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, ms_min(MS_FRAME, u->out_len - produced));
         q = 0;
+        if (KWAJ) { store_bits(); in_block = 1; }                                             /* mszipd.c:419 */
         phase = PH_BLOCK;
     }
 
@@ -248,8 +331,13 @@ struct ZipLaneC {
         /* a block that grew past 32 KiB keeps being decoded by the reference (so a read error can still win)
          * and only fails at its next window flush (:308-311, :323-333) */
         if (q > MS_FRAME) { fail(MS_EDECRUNCH); return; }
+        if (KWAJ) in_block = 0;
+        (void) finish_frame();
+    }
+    /* the block's q bytes become a frame of the intermediate form; false if the unit failed on the way */
+    MS_M bool finish_frame() {
         const bool kwaj = KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ);
-        if (kwaj && q > u->out_len - produced) { fail(MSGPU_ERR_CAPACITY); return; }        /* out_len is the capacity of the output area */
+        if (kwaj && q > u->out_len - produced) { status = MSGPU_ERR_CAPACITY; done = 1; phase = PH_IDLE; return false; }   /* out_len is the capacity of the output area */
         uint32_t n = ms_min(u->out_len - produced, q);
         emit_end(em, q);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = n; fi.g0 = produced;
@@ -258,14 +346,16 @@ struct ZipLaneC {
             /* one block of a chain (include/msgpu.h): it stands for a stretch of ONE stream only if it is exactly one CK block
              * that ends with its input and fills its output; anything else is for the caller to decode as one stream */
             const int64_t used = (ms_bitpos(b) + 7) >> 3;
-            if (q != u->out_len || frame != 0 || used != (int64_t) b.in_len) { fail(MSGPU_ERR_CHAIN); return; }
+            if (q != u->out_len || frame != 0 || used != (int64_t) b.in_len) { status = MSGPU_ERR_CHAIN; done = 1; phase = PH_IDLE; return false; }
             fi.valid = 3u;                                                                               /* 3: resolved by k_p2_chain, in chain order */
         }
         finfo[f] = fi;
         const uint32_t g0 = produced;
         produced += n; frame++; f++;
         if (produced >= u->out_len && !kwaj) { done = 1; phase = PH_IDLE; }               /* (a KWAJ stream ends at its zero length only) */
-        else if (hist_push(q, g0)) phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
+        else if (hist_push(q, g0)) phase = (f + ((KWAJ && repairing()) ? 2 : 1) <= max_frames) ? PH_FRAME : PH_IDLE;
+        else return false;
+        return true;
     }
 
     /* the rare, divergent work: run until the lane is decoding symbols or has nothing left to do */
@@ -279,7 +369,7 @@ struct ZipLaneC {
     }
 
     template <bool careful> MS_M uint32_t litlen_sym() {
-        if (careful) lsb_check(b, 16);
+        if (careful) ck(16);
         uint32_t v = v16();
         int len = ms_canon_len(llim, v);
         uint32_t idx = ms_canon_index<NT>(lbo, v, len);
@@ -287,7 +377,7 @@ struct ZipLaneC {
         return idx < (uint32_t) HEADN ? (uint32_t) lhead[idx * NT] : (uint32_t) la.sorted[idx * MS_WARP];
     }
     template <bool careful> MS_M uint32_t dist_sym() {
-        if (careful) lsb_check(b, 16);
+        if (careful) ck(16);
         uint32_t v = v16();
         int len = ms_canon_len(dlim, v);
         uint32_t idx = ms_canon_index<NT>(dbo, v, len);
@@ -295,18 +385,21 @@ struct ZipLaneC {
         return dhead[(idx & 31u) * NT];
     }
     template <bool careful> MS_M uint32_t extra_bits(int n) {
-        if (careful) return lsb_read(b, n);
+        if (careful) return rd(n);
         uint32_t v = lsb_peek(b, n); lsb_drop(b, n); return v;
     }
 
     /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the end-of-block code.
      * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
      * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
-    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len)) step_t<true>(); else step_t<false>(); }
+    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (KWAJ && repairing())) step_t<true>(); else step_t<false>(); }
     template <bool careful> MS_M void step_t() {
         lsb_refill(b);
         uint32_t sym = litlen_sym<careful>();
-        if (sym < 256) { emit_literal_checked(em, q, sym); q++; }
+        if (sym < 256) {
+            if (KWAJ && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+            emit_literal_checked(em, q - (KWAJ ? qbase : 0u), sym); q++;
+        }
         else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
         else {
             uint32_t c = sym - 257, eb, length, dist;
@@ -323,6 +416,13 @@ struct ZipLaneC {
             else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
             if (eb) dist += extra_bits<careful>((int) eb);
             if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
+            else if (KWAJ && repairing()) {                        /* the match crosses (or lies behind) the 32 KiB mark: see qbase */
+                uint32_t first = q < MS_FRAME ? MS_FRAME - q : 0u, rest = length - first, at = q + first - MS_FRAME;
+                if (first) emit_match(em, q, first, dist);
+                if (!qbase) { start_overflow(); if (done) return; }
+                if (at + rest > MS_FRAME) rest = at < MS_FRAME ? MS_FRAME - at : 0u;       /* (the second wrap fails the block) */
+                if (rest) emit_match(em, at, rest, dist);
+            }
             q += length;
         }
         if (careful && b.err) { fail(b.err); return; }
@@ -331,17 +431,17 @@ struct ZipLaneC {
 
     /* load the unit's state for this launch */
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi, int nframes) {
-        u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0;
+        u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; f = 0; q = 0; last_block = 0; in_block = 0; store_fx = 0; store_p = 0; store_val = 0; qbase = 0;
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         if (!st.started) {
-            done = 0; status = 0; produced = 0; frame = 0;
+            done = 0; status = 0; produced = 0; frame = 0; fx = 0;
             hist_ptr()[2 * P2_HIST_K * 32] = 0;
             ms_bits_init(b, in_base + unit->in_off, unit->in_len);
             if (unit->out_len == 0 && !(KWAJ && (unit->flags & MSGPU_FLAG_MSZIP_KWAJ))) done = 1;
         }
         else {
-            done = st.done; status = st.status; produced = st.produced; frame = st.frame;
+            done = st.done; status = st.status; produced = st.produced; frame = st.frame; fx = (int32_t) st.R0;      /* (an LZX field, free here) */
             ms_bits_restore(b, in_base + unit->in_off, unit->in_len, st.ipos, (int32_t) st.bc, ((uint64_t) st.bb_hi << 32) | st.bb_lo);
         }
         phase = done ? PH_IDLE : PH_FRAME;
@@ -349,5 +449,6 @@ struct ZipLaneC {
     MS_M void end(MsUnitState &st) {
         st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
         st.ipos = b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
+        if (KWAJ) st.R0 = (uint32_t) fx;
     }
 };

@@ -55,6 +55,9 @@ MS_D uint32_t p2_desc(uint32_t p, uint32_t pos, uint32_t off, uint32_t len) {
  * entry with len > i and lives at unit position g0 + i; an index no entry covers was never written (reads as zero). */
 #define P2_HIST_K     16        /* more than 16 blocks in a row, each shorter than the one before: the unit fails */
 #define P2_HIST_WORDS (1 + 2 * P2_HIST_K)      /* n, then {len, g0} pairs */
+#define P2_PLANE_REC  10944                    /* an MSZIP overflow frame (ZipLaneC::qbase) keeps its literal bytes in a 32 KiB plane inside its record
+                                                * array, records [10944, 15040): they may not go to their output positions before the block's first
+                                                * 32 KiB - whose literals live there - has been resolved */
 #define P2_HIST_REC   (MS_MAXREC - 17)         /* the snapshot sits in the spare tail of the frame's record array (an MSZIP frame has at
                                                 * most 32768 / 3 records) */
 MS_D uint32_t p2_ring_lookup(const uint32_t *hist, uint32_t i, const uint8_t *unit_out) {
@@ -132,9 +135,9 @@ MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa
  * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
  * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero - except for the ref_len bytes
  * directly in front of the unit, the reference data of an LZX DELTA unit (WIDE only). */
-template <bool WIDE, bool RING = false>
+template <bool WIDE, bool RING = false, bool PLANE = false>
 MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0,
-                    const uint32_t *hist = nullptr)
+                    const uint32_t *hist = nullptr, const uint8_t *plane = nullptr)
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
@@ -147,7 +150,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
         uint32_t x = (k < n) ? row[k] : P2_LIT;
 #pragma unroll 1
         while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];
-        d[k] = x & ~P2_LIT;
+        d[k] = PLANE ? x : (x & ~P2_LIT);         /* (PLANE keeps the literal flag: an overflow frame's literals sit in its plane) */
     }
     const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
     uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
@@ -155,7 +158,13 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
-        if (RING) {
+        if (RING && PLANE) {
+            const bool lit = (int32_t) x < 0;
+            x &= ~P2_LIT;
+            if (k < n) v = lit ? plane[x - (uint32_t) P2_SBIAS]
+                               : (x >= (uint32_t) P2_SBIAS ? obase[x] : p2_ring_lookup(hist, MS_FRAME + x - (uint32_t) P2_SBIAS, unit_out));
+        }
+        else if (RING) {
             /* a source in front of the frame is the ring index 32768 + (position - frame start), see p2_ring_lookup */
             if (k < n) v = x >= (uint32_t) P2_SBIAS ? obase[x] : p2_ring_lookup(hist, MS_FRAME + x - (uint32_t) P2_SBIAS, unit_out);
         }
@@ -166,9 +175,10 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-template <bool WIDE, bool RING = false>
+template <bool WIDE, bool RING = false, bool PLANE = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
-                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr)
+                                                 uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
+                                                 const uint8_t *plane = nullptr)
 {
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     int r_lo = 0;                                              /* first window record ending beyond the chunk start */
@@ -193,8 +203,9 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         __syncwarp();
         p2_pass_a_long<WIDE>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b<WIDE, RING>(q0, c, size, src, unit_out, g0, w, ref_len, hist);
+        p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
+        if (PLANE) __syncwarp();     /* an MSZIP overflow frame reads the bytes it is about to replace (ZipLaneC::qbase): every load before any store */
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
         }

@@ -37,7 +37,7 @@ static msgpu_ctx *ctx_get(void) {
 struct dstream {                     /* common state; the three public stream types are this struct */
     struct mspack_system *sys;
     struct mspack_file *input, *output;
-    int codec, window_bits, reset_interval, repair_mode, is_delta;
+    int codec, window_bits, reset_interval, repair_mode, is_delta, bufsize;
     unsigned char *ref; size_t ref_len;  /* LZX DELTA reference data (lzxd_set_reference_data) */
     size_t out_base;                 /* the unit's first output byte inside `out` (the reference data sits in front of it) */
     off_t length;                    /* LZX: total output length if known (0 = not yet) */
@@ -97,7 +97,7 @@ static int ds_decode(struct dstream *s, size_t want) {
     if (s->ref_len) memcpy(s->out + rpad - s->ref_len, s->ref, s->ref_len);
     memset(&u, 0, sizeof(u));
     u.codec = (uint8_t) s->codec; u.window_bits = (uint8_t) s->window_bits; u.reset_interval = (uint16_t) s->reset_interval;
-    u.flags = s->repair_mode ? MSGPU_FLAG_MSZIP_REPAIR : 0;
+    u.flags = s->repair_mode ? (MSGPU_FLAG_MSZIP_REPAIR | ((uint32_t) s->bufsize << MSGPU_FLAG_REF_SHIFT)) : 0;
     if (s->is_delta) u.flags |= MSGPU_FLAG_LZX_DELTA | ((uint32_t) s->ref_len << MSGPU_FLAG_REF_SHIFT);
     u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = rpad; u.out_len = (uint32_t) want;
     pthread_mutex_lock(&g_mu);
@@ -205,10 +205,10 @@ struct mszipd_stream *mszipd_init(struct mspack_system *system, struct mspack_fi
     struct dstream *s;
     input_buffer_size = (input_buffer_size + 1) & -2;
     if (input_buffer_size < 2) return NULL;                      /* mszipd.c:345-347 */
-    if (repair_mode) return NULL;                                /* repair mode (cabd fix_mszip) is not implemented on the device yet */
+    if (input_buffer_size > (1 << 24)) input_buffer_size = 1 << 24;      /* (the unit descriptor carries it in 26 bits; repair mode only) */
     s = ds_new(system, input, output, MSGPU_CODEC_MSZIP);
     if (!s) return NULL;
-    s->repair_mode = repair_mode;
+    s->repair_mode = repair_mode; s->bufsize = input_buffer_size;
     return (struct mszipd_stream *) s;
 }
 int mszipd_decompress(struct mszipd_stream *zip, off_t out_bytes) { return ds_decompress((struct dstream *) zip, out_bytes); }

@@ -48,13 +48,23 @@ typedef struct {
     uint32_t base;      /* LZX only: byte offset p is measured from (0 or 1, see lzx_enter_bits) */
     int bytemode;       /* LZX only: the reference's bit buffer is empty and it is reading raw bytes */
     int err;
+    /* MSZIP repair mode only (zero otherwise): after a repaired block the reference goes on with the bits it had buffered at
+     * its last STORE_BITS followed by the bytes at its (possibly refilled) buffer pointer - the stream seen from here on is
+     * stale[0..nstale) followed by in[real0..] */
+    uint8_t stale[4]; uint32_t nstale; uint64_t real0;
+    uint64_t fetched;   /* bytes of that stream the reference has fetched so far (its ENSURE_BITS / READ_IF_NEEDED calls) */
 } bitin;
 
-static inline uint32_t in_byte(const bitin *b, uint64_t i) { i += b->base; return i < b->in_len ? b->in[i] : 0u; }
+static inline uint32_t in_byte(const bitin *b, uint64_t i) {
+    if (i < b->nstale) return b->stale[i];
+    i = i - b->nstale + b->real0 + b->base;
+    return i < b->in_len ? b->in[i] : 0u;
+}
 
 /* the reference would have to fetch input bytes [0, need_bytes) : legal up to in_len + 2 */
 static inline int fetch_ok(bitin *b, uint64_t need_bytes) {
-    if (need_bytes + b->base > (uint64_t) b->in_len + 2u) { b->err = ERR_READ; return 0; }
+    if (need_bytes > b->nstale && need_bytes - b->nstale + b->real0 + b->base > (uint64_t) b->in_len + 2u) { b->err = ERR_READ; return 0; }
+    if (need_bytes > b->fetched) b->fetched = need_bytes;
     return 1;
 }
 
@@ -202,7 +212,9 @@ typedef struct {
     uint32_t window_posn, bytes_output;
     uint8_t lit_len[288], dist_len[32];
     huff lit, dist, bl;
+    uint64_t store_p, store_f;      /* bit position / fetched bytes at the reference's last STORE_BITS (repair mode) */
 } zipst;
+#define ZIP_STORE(z) do { (z)->store_p = (z)->b.p; (z)->store_f = (z)->b.fetched; } while (0)
 
 /* mszipd.c:38-45 FLUSH_IF_NEEDED + :323-333 mszipd_flush_window */
 static inline int zip_flush_if_needed(zipst *z) {
@@ -257,6 +269,7 @@ static int zip_read_lens(zipst *z) {
     (void) err;
     memcpy(z->lit_len, lens, lit_codes); memset(z->lit_len + lit_codes, 0, 288 - lit_codes);
     memcpy(z->dist_len, lens + lit_codes, dist_codes); memset(z->dist_len + dist_codes, 0, 32 - dist_codes);
+    ZIP_STORE(z);                                       /* :149 */
     return 0;
 }
 
@@ -301,7 +314,9 @@ static int zip_inflate(zipst *z) {
                 for (i = 0; i < 32; i++) z->dist_len[i] = 5;
             }
             else {
-                int e = zip_read_lens(z);
+                int e;
+                ZIP_STORE(z);                           /* :223 */
+                e = zip_read_lens(z);
                 if (e) return e;
             }
             if (huff_build(&z->lit, z->lit_len, 288, 9)) return -7;     /* :230-235 */
@@ -343,6 +358,33 @@ static int zip_inflate(zipst *z) {
     return 0;
 }
 
+/* Repair mode, where the reference goes on after a block it gave up (mszipd.c:404 RESTORE_BITS of the state its last STORE_BITS
+ * left, :149 / :223 / :419).  That state is stale in two ways: bit_buffer / bits_left are the bits buffered at the STORE, and
+ * i_ptr is the STORE's pointer only if read_input (readbits.h:192-214) has not refilled the input buffer since - it resets
+ * i_ptr to the buffer's start.  The input buffer holds one read() of input_buffer_size bytes (flags >> 6 here, 4096 if 0): the
+ * chunks are [k * size, (k + 1) * size) of the stream, and the two zero bytes the reference invents at the end of the input form
+ * a last chunk of their own.  The stream from here on: the whole bytes left in the stale bit buffer, then the bytes at i_ptr. */
+static uint64_t zip_chunk_start(const bitin *b, uint64_t size, uint64_t x) {      /* start of the chunk that holds stream byte x */
+    return x >= b->in_len ? b->in_len : x / size * size;
+}
+static void zip_repair_restart(zipst *z, const msgpu_unit *u) {
+    bitin *b = &z->b;
+    uint64_t size = MSGPU_UNIT_REF_BYTES(u) ? MSGPU_UNIT_REF_BYTES(u) : 4096, fr_now, fr_store, r, k;
+    uint32_t ns, nb; uint8_t tmp[4];
+    size = (size + 1) & ~(uint64_t) 1;
+    /* real (stream) fetch pointers now and at the STORE */
+    fr_now = b->real0 + (b->fetched > b->nstale ? b->fetched - b->nstale : 0);
+    fr_store = b->real0 + (z->store_f > b->nstale ? z->store_f - b->nstale : 0);
+    r = fr_store;
+    if (fr_now > 0 && (fr_store == 0 || zip_chunk_start(b, size, fr_now - 1) != zip_chunk_start(b, size, fr_store - 1)))
+        r = zip_chunk_start(b, size, fr_now - 1);
+    ns = (uint32_t) (8 * z->store_f - z->store_p);              /* bits buffered at the STORE; :405 drops ns & 7 of them */
+    nb = ns >> 3; if (nb > 4) nb = 4;                            /* (the reference's buffer is 32 bits) */
+    for (k = 0; k < nb; k++) tmp[k] = (uint8_t) in_byte(b, z->store_f - nb + k);
+    memcpy(b->stale, tmp, nb);
+    b->nstale = nb; b->real0 = r; b->p = 0; b->fetched = nb;
+}
+
 /* mszipd.c:377-460 mszipd_decompress, for one whole unit */
 static int port_mszip(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint32_t *produced) {
     zipst *z = (zipst *) calloc(1, sizeof(zipst));
@@ -378,12 +420,14 @@ static int port_mszip(const msgpu_unit *u, const uint8_t *in, uint8_t *out, uint
             else state = 0;
         } while (state != 2);
         z->window_posn = 0; z->bytes_output = 0;
+        ZIP_STORE(z);                                             /* :419 */
         error = zip_inflate(z);
         if (error) {
             if (u->flags & MSGPU_FLAG_MSZIP_REPAIR) {             /* :420-433 */
                 if (z->bytes_output == 0 && z->window_posn > 0) { z->bytes_output += z->window_posn; }
                 if (z->bytes_output < FRAME) memset(z->window + z->bytes_output, 0, FRAME - z->bytes_output);
                 z->bytes_output = FRAME;
+                if (error < 0) zip_repair_restart(z, u);
             }
             else { ret = (error > 0) ? error : ERR_DECRUNCH; goto out; }
         }

@@ -76,8 +76,11 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
 
     switch (u->codec) {
     case MSGPU_CODEC_MSZIP: {
+        /* repair mode depends on the size of the decoder's input buffer (see oracle/port/mspack_port.c zip_repair_restart):
+         * flags >> 6 carries it, 4096 (cabd's default, cabd.c:155) if zero */
+        int bufsize = ((u->flags & MSGPU_FLAG_MSZIP_REPAIR) && MSGPU_UNIT_REF_BYTES(u)) ? (int) MSGPU_UNIT_REF_BYTES(u) : 4096;
         struct mszipd_stream *z = mszipd_init(&mem_system, (struct mspack_file *) &f,
-                                              (struct mspack_file *) &f, 4096,
+                                              (struct mspack_file *) &f, bufsize,
                                               (u->flags & MSGPU_FLAG_MSZIP_REPAIR) ? 1 : 0);
         if (!z) { err = MSPACK_ERR_NOMEMORY; break; }
         if (u->flags & MSGPU_FLAG_MSZIP_KWAJ) err = mszipd_decompress_kwaj(z);       /* out_len is only the capacity (mem_write drops the rest) */

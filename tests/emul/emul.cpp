@@ -18,8 +18,9 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
-template <bool WIDE, bool RING = false>
-static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr) {
+template <bool WIDE, bool RING = false, bool PLANE = false>
+static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr,
+                          const uint8_t *plane = nullptr) {
     std::vector<uint32_t> wa(P2_WIN), wb(P2_WIN);
     uint32_t wbase = 0, wcover = 0; bool loaded = false; int r_lo = 0;
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
@@ -37,7 +38,7 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
         r_lo = nlo;
         for (int lane = 0; lane < 32; lane++) p2_pass_a_long<WIDE>(lane, c, cend, wa.data(), wb.data(), src, longq);
-        for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE, RING>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist);
+        for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE, RING, PLANE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist, plane);
         for (int lane = 0; lane < 32; lane++) {
             uint32_t q0 = c + 16u * lane;
             for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
@@ -84,7 +85,8 @@ static void emul_run2(Lane &t) {      /* p1_run<Lane, TWO = true> */
 static uint32_t g_last_produced;
 extern "C" uint32_t emul_last_produced() { return g_last_produced; }
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
-    const int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
+    int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
+    if (u->codec == MSGPU_CODEC_MSZIP && (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) && F < 2) F = 2;      /* as run_wave does */
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
     std::vector<MsFrameInfo> finfo(F);
@@ -106,12 +108,16 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
             emul_p2_frame<true>(recs.data(), finfo[0].nrec, finfo[0].size, unit_out, finfo[0].g0, (u->flags & MSGPU_FLAG_CHAIN_NEXT) ? MS_FRAME : 0u);
         for (int f = 0; f < F; f++) if (finfo[f].valid == 2 && finfo[f].size)
             emul_p2_frame<false, true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0, reinterpret_cast<const uint32_t *>(recs.data() + (size_t) f * MS_MAXREC + P2_HIST_REC));
+        /* k_p2_ring<true>: the overflow frames of repair-mode blocks */
+        for (int f = 0; f < F; f++) if (finfo[f].valid == 4 && finfo[f].size)
+            emul_p2_frame<false, true, true>(recs.data() + (size_t) f * MS_MAXREC, finfo[f].nrec, finfo[f].size, unit_out, finfo[f].g0, 0, reinterpret_cast<const uint32_t *>(recs.data() + (size_t) f * MS_MAXREC + P2_HIST_REC),
+                                             reinterpret_cast<const uint8_t *>(recs.data() + (size_t) f * MS_MAXREC + P2_PLANE_REC));
     };
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH; typedef ZipLaneC<1, 32, true> THK;     /* THK: units with KWAJ framing */
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) aligned_alloc(64, (ZIP_AUX_BYTES + 63) & ~(size_t) 63); memset(aux, 0, ZIP_AUX_BYTES);   /* 32-byte aligned like the device's */
-        const bool kwaj = (u->flags & MSGPU_FLAG_MSZIP_KWAJ) != 0;
+        const bool kwaj = (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) != 0;
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             if (kwaj) { THK t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
             else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }

@@ -401,3 +401,16 @@ def test_device_logic_mszip_kwaj_framing(emul, oracle_ref):
                 if streams[i][1] is not None:
                     assert o2[lo:lo + n].tobytes() == streams[i][1]
     assert ref_decode is not None
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_device_logic_mszip_repair_mode(emul, oracle_ref, seed):
+    """mszipd_init(repair_mode = 1) (mszipd.c:420-433, cabd's fix_mszip): a block that does not inflate is zero-filled and decoding
+    goes on with the reference's STALE bit state (last STORE_BITS, input-buffer refills - ZipLaneC::repair_block); a block that
+    overflows 32 KiB overwrites the start of its own window image (ZipLaneC::qbase, k_p2_ring<true>).  Same bytes, same status."""
+    from util import damaged_mszip_batch
+    units, comp, out_bytes = damaged_mszip_batch(100 + seed, level=(6, 1, 0)[seed % 3], data=("text", "binary")[seed % 2])
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, out_bytes, threads=4)
+    for fpr in (1, 2):
+        o2, s2 = emul(units, comp, out_bytes, fpr)
+        assert_same(units, o1, s1, o2, s2, f"repair seed {seed} F={fpr}")

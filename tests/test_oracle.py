@@ -100,3 +100,15 @@ def test_port_matches_reference_lzx_delta(oracle_ref, oracle_port, kw):
     o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4, out_init=b.out_init)
     o2, s2, _ = oracle_port.decode_batch(units, comp, b.out_bytes, threads=4, out_init=b.out_init)
     assert_same(units, o1, s1, o2, s2, f"corrupt delta {kw}")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs the reference oracle")
+@pytest.mark.parametrize("seed", range(6))
+def test_port_matches_reference_mszip_repair_mode(oracle_ref, oracle_port, seed):
+    """Repair mode (mszipd.c:420-433): where the reference goes on after a block it gave up depends on its stale bit state and on
+    refills of its input buffer (oracle/port/mspack_port.c zip_repair_restart) - pinned for buffer sizes from 2 bytes to 4 KiB."""
+    from util import damaged_mszip_batch
+    units, comp, out_bytes = damaged_mszip_batch(200 + seed, level=(6, 1, 0)[seed % 3])
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, out_bytes, threads=4)
+    o2, s2, _ = oracle_port.decode_batch(units, comp, out_bytes, threads=4)
+    assert_same(units, o1, s1, o2, s2, f"repair seed {seed}")

@@ -64,3 +64,17 @@ def test_kwaj_files_decode_through_the_gpu_dropin(tmp_path):
         for name in want:
             assert got[name][0] == want[name][0], name                    # same error code ...
             assert got[name][1] == want[name][1], name                    # ... and the same bytes written before it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_mszip_repair_mode_on_the_gpu(decoder, oracle_ref, seed):
+    """mszipd_init(repair_mode = 1) through the batch ABI (MSGPU_FLAG_MSZIP_REPAIR + the input buffer size): damaged MSZIP folders
+    against the reference in repair mode - zero-filled blocks, stale-state restarts, overflowing blocks."""
+    import numpy as np
+    from util import assert_same, damaged_mszip_batch
+    units, comp, out_bytes = damaged_mszip_batch(300 + seed, n=64, level=(6, 1, 0)[seed % 3], data=("text", "binary")[seed % 2])
+    out_g, st_g = decoder.decode_host(units, comp, out_bytes)
+    out_o, st_o, _ = oracle_ref.decode_batch(units, comp, out_bytes, threads=8)
+    assert_same(units, out_o, st_o, out_g, st_g, f"repair seed {seed}")
+    assert (st_o == 0).any()

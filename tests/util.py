@@ -137,3 +137,29 @@ def kwaj_mszip_stream(lens, seed=0, terminator=True):
         out += data
         win[0:n] = data
     return comp + (b"\0\0" if terminator else b""), out
+
+
+def damaged_mszip_batch(seed, n=16, level=6, data="text"):
+    """MSZIP folders of several blocks with 1-3 damages each (bit flips, overwritten / zeroed stretches, truncation), repair mode on,
+    a random size of the decoder's input buffer (the reference's repair behaviour depends on it): units, compressed bytes, out size."""
+    from libmspack_b200 import gen
+    rng = np.random.default_rng(seed)
+    nblk = int(rng.integers(2, 7))
+    ub = 32768 * nblk         # whole frames: a block that OVERFLOWS inside a frame cut short by out_len is the one stated deviation (DESIGN.md 7)
+    b = gen.make_batch(1, n, unit_bytes=ub, first_unit=int(rng.integers(0, 1 << 20)), data=data, level=level)
+    comp, units = b.comp.copy(), b.units.copy()
+    bufsize = int(rng.choice([4096, 4096, 2048, 512, 64, 16, 6, 2]))
+    units["flags"] = 0x1 | (bufsize << 6)                 # MSGPU_FLAG_MSZIP_REPAIR | input buffer size << MSGPU_FLAG_REF_SHIFT
+    for i, u in enumerate(units):
+        lo, ln = int(u["in_off"]), int(u["in_len"])
+        for _ in range(int(rng.integers(1, 4))):
+            k, pos = int(rng.integers(0, 4)), lo + int(rng.integers(2, ln))
+            if k == 0:
+                comp[pos] ^= 1 << int(rng.integers(0, 8))
+            elif k == 1:
+                comp[pos:pos + 16] = rng.integers(0, 256, min(16, lo + ln - pos), dtype=np.uint8)
+            elif k == 2:
+                comp[pos:min(pos + 300, lo + ln)] = 0
+            else:
+                units["in_len"][i] = max(4, ln - int(rng.integers(1, 3000)))
+    return units, comp, b.out_bytes
