@@ -51,12 +51,12 @@ typedef struct {
     /* MSZIP repair mode only (zero otherwise): after a repaired block the reference goes on with the bits it had buffered at
      * its last STORE_BITS followed by the bytes at its (possibly refilled) buffer pointer - the stream seen from here on is
      * stale[0..nstale) followed by in[real0..] */
-    uint8_t stale[4]; uint32_t nstale; uint64_t real0;
+    uint8_t stale[8]; uint32_t nstale; uint64_t real0;        /* (nstale <= 4) */
     uint64_t fetched;   /* bytes of that stream the reference has fetched so far (its ENSURE_BITS / READ_IF_NEEDED calls) */
 } bitin;
 
 static inline uint32_t in_byte(const bitin *b, uint64_t i) {
-    if (i < b->nstale) return b->stale[i];
+    if (i < b->nstale) return b->stale[i & 7];
     i = i - b->nstale + b->real0 + b->base;
     return i < b->in_len ? b->in[i] : 0u;
 }
