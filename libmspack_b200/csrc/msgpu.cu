@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 #else
 #define P2_BOUNDS __launch_bounds__(P2_WARPS * 32)
 #endif
-template <bool WIDE>
+template <bool WIDE, int PA = 0>
 __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
@@ -148,7 +148,7 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
-        p2_resolve_frame<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        p2_resolve_frame<WIDE, false, false, PA>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
     }
 }
@@ -283,7 +283,7 @@ struct msgpu_ctx {
     std::string err;
     uint64_t launches = 0;
     size_t scratch_budget = 0;
-    int lzx_variant = 0, zip_variant = 0;
+    int lzx_variant = 0, zip_variant = 0, p2_variant = 0;      /* MSGPU_P2_VARIANT=1: the byte-parallel pass A (experimental) */
     size_t last_wave_n = 0, last_waves = 0;      /* msgpu_last_produced: units of the most recent wave / waves of the most recent batch */
     cudaStream_t last_stream = nullptr;
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
@@ -335,6 +335,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #undef SETATTRC
     cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>));
     cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
+    { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
         bool okz = false, okl = false;
@@ -587,6 +588,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     auto p2_launch = [&](const WaveArgs &w, const uint32_t *list, uint32_t f0, uint32_t f1, cudaStream_t st) {
         if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
+        else if (ctx->p2_variant == 1) k_p2_resolve<false, 1><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);     /* experimental pass A */
         else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
     };
     auto launch_round = [&](uint32_t sub, cudaStream_t st) {

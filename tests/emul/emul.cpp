@@ -18,6 +18,7 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
+static bool g_pa2;      /* the experimental byte-parallel pass A for plain frames (frames_per_round bit 0x1000) */
 template <bool WIDE, bool RING = false, bool PLANE = false>
 static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr,
                           const uint8_t *plane = nullptr) {
@@ -33,6 +34,19 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         longq[0] = 0;
         for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;
+        if (g_pa2 && !WIDE && !RING) {
+            int j[32];
+            for (int lane = 0; lane < 32; lane++) { j[lane] = p2_pass_a2_search(c + 16u * lane, wa.data()); p2_pass_a2_zero(c + 16u * lane, c, src); }
+            r_lo = j[0] > 0 ? j[0] : 0;
+            for (int lane = 0; lane < 32; lane++) p2_pass_a2_scatter(lane, j[0], c, cend, wa.data(), wb.data(), src);
+            for (int lane = 0; lane < 32; lane++) p2_pass_a2_walk(c + 16u * lane, c, j[lane], wa.data(), wb.data(), src);
+            for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE, RING, PLANE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist, plane);
+            for (int lane = 0; lane < 32; lane++) {
+                uint32_t q0 = c + 16u * lane;
+                for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
+            }
+            continue;
+        }
         for (int lane = 0; lane < 32; lane++) p2_pass_a_literals<WIDE>(c + 16u * lane, c, src);
         int nlo = P2_WIN;
         for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
@@ -87,6 +101,7 @@ extern "C" uint32_t emul_last_produced() { return g_last_produced; }
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
     if (u->codec == MSGPU_CODEC_MSZIP && (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) && F < 2) F = 2;      /* as run_wave does */
+    g_pa2 = (frames_per_round & 0x1000) != 0;
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
     std::vector<MsFrameInfo> finfo(F);

@@ -414,3 +414,24 @@ def test_device_logic_mszip_repair_mode(emul, oracle_ref, seed):
     for fpr in (1, 2):
         o2, s2 = emul(units, comp, out_bytes, fpr)
         assert_same(units, o1, s1, o2, s2, f"repair seed {seed} F={fpr}")
+
+
+@pytest.mark.parametrize("codec,kw", [(CODEC_LZX, {}), (CODEC_LZX, dict(data="zeros")), (CODEC_LZX, dict(data="binary", unit_bytes=70000, block_mode=4)),
+                                      (CODEC_MSZIP, dict(unit_bytes=100000, data="binary")), (CODEC_MSZIP, dict(data="zeros")), (CODEC_QUANTUM, dict(unit_bytes=40000, window_bits=12)),
+                                      (CODEC_LZX, dict(unit_bytes=5)), (CODEC_LZX, dict(unit_bytes=32769)), (CODEC_MSZIP, dict(unit_bytes=4097))], ids=lambda x: str(x))
+def test_device_logic_experimental_pass_a(emul, oracle_ref, codec, kw):
+    """The byte-parallel pass A of the resolve stage (msgpu_p2.cuh PA = 1, MSGPU_P2_VARIANT=1; experimental): same bytes as the
+    record-parallel one - plain, overlapping and very long matches, ragged last chunks, damaged streams."""
+    b = gen.make_batch(codec, 16, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+    for fpr in (1, 2):
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, 0x1000 | fpr)
+        assert_same(b.units, o1, s1, o2, s2, f"pass A2 {codec} {kw} F={fpr}")
+    rng = np.random.default_rng(29)
+    comp = b.comp.copy()
+    for u in b.units:
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+    o1, s1, _ = oracle_ref.decode_batch(b.units, comp, b.out_bytes, threads=4)
+    o2, s2 = emul(b.units, comp, b.out_bytes, 0x1001)
+    assert_same(b.units, o1, s1, o2, s2, f"pass A2 corrupt {codec} {kw}")

@@ -15,8 +15,10 @@ b = gen.make_batch(codec, n, keep_raw=True, data=data)
 d_in = torch.from_numpy(b.comp).cuda(); d_out = torch.zeros(b.out_bytes, dtype=torch.uint8, device="cuda"); d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
 stream = torch.cuda.Stream(); torch.cuda.synchronize()
 libs = os.environ.get("VB_LIBS", "").split(",") if os.environ.get("VB_LIBS") else [None]
-for lib, v in [(l, v) for l in libs for v in variants]:
+p2s = [int(x) for x in os.environ.get("VB_P2", "0").split(",")]          # MSGPU_P2_VARIANT values (1 = the byte-parallel pass A)
+for lib, v, p2v in [(l, v, q) for l in libs for q in p2s for v in variants]:
     os.environ["MSGPU_LZX_VARIANT" if codec == 3 else "MSGPU_ZIP_VARIANT"] = str(v)
+    os.environ["MSGPU_P2_VARIANT"] = str(p2v)
     if lib:
         _codec._lib = None; _codec.LIB_PATH = os.path.abspath(lib)       # another build of the library (dlopen keeps both)
     dec = BatchDecoder(0)
@@ -31,6 +33,6 @@ for lib, v in [(l, v) for l in libs for v in variants]:
     for it in range(3):
         dec.decode_device(b.units, d_in, d_out, d_st, stream); torch.cuda.synchronize()
         p1 = min(p1, dec.stage_ms(0)); p2 = min(p2, dec.stage_ms(1))
-    print(json.dumps({"lib": lib, "variant": v, "units": n, "data": data, "codec": codec, "best_ms": round(best, 3), "GB_per_s": round(b.out_bytes / best / 1e6, 1),
+    print(json.dumps({"lib": lib, "variant": v, "p2_variant": p2v, "units": n, "data": data, "codec": codec, "best_ms": round(best, 3), "GB_per_s": round(b.out_bytes / best / 1e6, 1),
                       "p1_ms": round(p1, 3), "p2_ms": round(p2, 3), "verified": ok}), flush=True)
     dec.close()
