@@ -86,7 +86,9 @@ template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxShar
  *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them
  *   bit 2  extra_bits[] / position_base[] from a 64-entry table in shared memory (one per CTA, lzx_slot_entry) instead of the
  *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only
- *   bit 3  match records stored one by one (8 bytes each) instead of in pairs */
+ *   bit 3  match records stored one by one (8 bytes each) instead of in pairs
+ *   bit 4  literals stored one byte at a time instead of gathered per aligned word (4 instructions instead of ~20 per literal,
+ *          up to four times the literal stores) */
 MS_D uint32_t lzx_slot_entry(uint32_t slot) {          /* extra | (position_base - 2) << 5, lzxd.c:199-255 */
     const uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
     const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
@@ -456,7 +458,11 @@ struct LzxLaneC {
     template <bool careful> MS_M void step_plain() {
         lzx_refill(b);
         uint32_t sym = main_sym(careful);
-        if (sym < 256) { emit_literal(em, q, sym); q++; this_run--; }
+        if (sym < 256) {
+            if constexpr ((OPT & 16) != 0) em.out[q] = (uint8_t) sym;          /* (q < frame_size by construction) */
+            else emit_literal(em, q, sym);
+            q++; this_run--;
+        }
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
