@@ -382,6 +382,10 @@ struct LzxLaneC {
         bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
+            if constexpr ((OPT & 16) != 0) {       /* byte-wise literal stores: nothing may go through the word gatherer */
+#pragma unroll 1
+                while (this_run > 0) { em.out[q] = (uint8_t) raw_byte(); q++; this_run--; }
+            }
             if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
                 emit_raw(em, q, b.in, bytepos, (uint32_t) this_run);
                 bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
