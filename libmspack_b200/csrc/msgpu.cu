@@ -53,14 +53,14 @@ __device__ __forceinline__ void p1_run(Lane &t)
 
 #define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
 #define MISC_RING  1024u
-template <int NT, int HEADN, bool KWAJ = false>
+template <int NT, int HEADN, bool SPECIAL = false>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC) */
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    ZipLaneC<NT, HEADN, KWAJ> t; t.phase = PH_IDLE;
+    ZipLaneC<NT, HEADN, SPECIAL> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     p1_run(t);
     if (valid) {
         t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u);
-        if (KWAJ) {          /* (the special instantiation also makes overflow frames, valid == 4, and may use two frame slots for one block) */
+        if (SPECIAL) {       /* (the special instantiation also makes overflow frames, valid == 4, and may use two frame slots for one block) */
             bool any = false;
             for (int k = 0; k < t.f; k++) { const uint32_t v = a.finfo[(size_t) slot * a.F + k].valid; any = any || v == 2u || v == 4u; }
             if (any) a.not_done[MISC_RING + a.sub] = 1u;

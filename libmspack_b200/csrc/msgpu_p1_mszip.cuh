@@ -34,9 +34,9 @@ struct ZipSharedC {
     uint16_t cnt[17 * NT];
 };
 
-/* KWAJ = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
+/* SPECIAL = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
  * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
-template <int NT, int HEADN, bool KWAJ = false>
+template <int NT, int HEADN, bool SPECIAL = false>
 struct ZipLaneC {
     /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
      * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
@@ -50,12 +50,12 @@ struct ZipLaneC {
      * is what gets written, so the overflow is kept as a second frame at the SAME output position (qbase = 32768, records at
      * q - qbase): to the resolve stage it is an ordinary ring frame whose one history entry is the block's first 32 KiB. */
     uint32_t qbase;
-    MS_M bool repairing() const { return KWAJ && (u->flags & MSGPU_FLAG_MSZIP_REPAIR); }
-    MS_M void trk(int n) { if (KWAJ) { const int32_t need = (int32_t) ((ms_bitpos(b) + n + 7) >> 3); if (need > fx) fx = need; } }
+    MS_M bool repairing() const { return SPECIAL && (u->flags & MSGPU_FLAG_MSZIP_REPAIR); }
+    MS_M void trk(int n) { if (SPECIAL) { const int32_t need = (int32_t) ((ms_bitpos(b) + n + 7) >> 3); if (need > fx) fx = need; } }
     MS_M uint32_t rd(int n) { trk(n); return lsb_read(b, n); }
     MS_M void ck(int n) { trk(n); lsb_check(b, n); }
     MS_M void store_bits() {           /* STORE_BITS: position, fetch extent, the bits fetched but not consumed */
-        if (KWAJ) { lsb_refill(b); store_p = ms_bitpos(b); store_fx = fx; const int64_t ns = (int64_t) store_fx * 8 - store_p; store_val = (uint32_t) b.bb & (ns > 0 ? (ns >= 32 ? 0xFFFFFFFFu : ((1u << ns) - 1u)) : 0u); }
+        if (SPECIAL) { lsb_refill(b); store_p = ms_bitpos(b); store_fx = fx; const int64_t ns = (int64_t) store_fx * 8 - store_p; store_val = (uint32_t) b.bb & (ns > 0 ? (ns >= 32 ? 0xFFFFFFFFu : ((1u << ns) - 1u)) : 0u); }
     }
     MsBits b;
     uint32_t *lbo, *dbo; uint16_t *lhead, *dhead, *blim, *cnt;   /* this lane's columns of the shared tables */
@@ -182,7 +182,7 @@ struct ZipLaneC {
     }
 
     MS_M void fail(int err) {
-        if (KWAJ && in_block && repairing()) { repair_block(err); return; }
+        if (SPECIAL && in_block && repairing()) { repair_block(err); return; }
         status = err; done = 1; phase = PH_IDLE;
     }
 
@@ -260,7 +260,7 @@ struct ZipLaneC {
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
                     emit_raw(em, q, b.in, bp, len);
                     q += len; lsb_seek_byte(b, bp + (int32_t) len);
-                    if (KWAJ && bp + (int32_t) len > fx) fx = bp + (int32_t) len;
+                    if (SPECIAL && bp + (int32_t) len > fx) fx = bp + (int32_t) len;
                     len = 0;
                 }
             }
@@ -269,8 +269,8 @@ struct ZipLaneC {
                 lsb_refill(b);
                 uint32_t v = rd(8);
                 if (b.err) { fail(b.err); return; }
-                if (KWAJ && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
-                emit_literal_checked(em, q - (KWAJ ? qbase : 0u), v);
+                if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+                emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
             phase = last_block ? PH_END : PH_BLOCK;
@@ -300,7 +300,7 @@ struct ZipLaneC {
     MS_M void frame_start() {
         int state = 0;
         lsb_align_byte(b);
-        if (KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ)) {
+        if (SPECIAL && (u->flags & MSGPU_FLAG_MSZIP_KWAJ)) {
             /* :471-481: a 16-bit block length (0 ends the stream; otherwise its value is not used), then 'C', 'K' right away */
             lsb_refill(b);
             uint32_t block_len = rd(8); block_len |= rd(8) << 8;
@@ -323,7 +323,7 @@ struct ZipLaneC {
         } while (state != 2);
         emit_begin(em, recs + (size_t) f * MS_MAXREC, uout + produced, ms_min(MS_FRAME, u->out_len - produced));
         q = 0;
-        if (KWAJ) { store_bits(); in_block = 1; }                                             /* mszipd.c:419 */
+        if (SPECIAL) { store_bits(); in_block = 1; }                                             /* mszipd.c:419 */
         phase = PH_BLOCK;
     }
 
@@ -331,12 +331,12 @@ struct ZipLaneC {
         /* a block that grew past 32 KiB keeps being decoded by the reference (so a read error can still win)
          * and only fails at its next window flush (:308-311, :323-333) */
         if (q > MS_FRAME) { fail(MS_EDECRUNCH); return; }
-        if (KWAJ) in_block = 0;
+        if (SPECIAL) in_block = 0;
         (void) finish_frame();
     }
     /* the block's q bytes become a frame of the intermediate form; false if the unit failed on the way */
     MS_M bool finish_frame() {
-        const bool kwaj = KWAJ && (u->flags & MSGPU_FLAG_MSZIP_KWAJ);
+        const bool kwaj = SPECIAL && (u->flags & MSGPU_FLAG_MSZIP_KWAJ);
         if (kwaj && q > u->out_len - produced) { status = MSGPU_ERR_CAPACITY; done = 1; phase = PH_IDLE; return false; }   /* out_len is the capacity of the output area */
         uint32_t n = ms_min(u->out_len - produced, q);
         emit_end(em, q);
@@ -353,7 +353,7 @@ struct ZipLaneC {
         const uint32_t g0 = produced;
         produced += n; frame++; f++;
         if (produced >= u->out_len && !kwaj) { done = 1; phase = PH_IDLE; }               /* (a KWAJ stream ends at its zero length only) */
-        else if (hist_push(q, g0)) phase = (f + ((KWAJ && repairing()) ? 2 : 1) <= max_frames) ? PH_FRAME : PH_IDLE;
+        else if (hist_push(q, g0)) phase = (f + ((SPECIAL && repairing()) ? 2 : 1) <= max_frames) ? PH_FRAME : PH_IDLE;
         else return false;
         return true;
     }
@@ -392,13 +392,13 @@ struct ZipLaneC {
     /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the end-of-block code.
      * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
      * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
-    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (KWAJ && repairing())) step_t<true>(); else step_t<false>(); }
+    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>(); }
     template <bool careful> MS_M void step_t() {
         lsb_refill(b);
         uint32_t sym = litlen_sym<careful>();
         if (sym < 256) {
-            if (KWAJ && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
-            emit_literal_checked(em, q - (KWAJ ? qbase : 0u), sym); q++;
+            if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+            emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), sym); q++;
         }
         else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;
         else {
@@ -416,7 +416,7 @@ struct ZipLaneC {
             else { eb = (d >> 1) - 1; dist = ((2 + (d & 1)) << eb) + 1; }
             if (eb) dist += extra_bits<careful>((int) eb);
             if (q + length <= MS_FRAME) emit_match(em, q, length, dist);
-            else if (KWAJ && repairing()) {                        /* the match crosses (or lies behind) the 32 KiB mark: see qbase */
+            else if (SPECIAL && repairing()) {                        /* the match crosses (or lies behind) the 32 KiB mark: see qbase */
                 uint32_t first = q < MS_FRAME ? MS_FRAME - q : 0u, rest = length - first, at = q + first - MS_FRAME;
                 if (first) emit_match(em, q, first, dist);
                 if (!qbase) { start_overflow(); if (done) return; }
@@ -438,7 +438,7 @@ struct ZipLaneC {
             done = 0; status = 0; produced = 0; frame = 0; fx = 0;
             hist_ptr()[2 * P2_HIST_K * 32] = 0;
             ms_bits_init(b, in_base + unit->in_off, unit->in_len);
-            if (unit->out_len == 0 && !(KWAJ && (unit->flags & MSGPU_FLAG_MSZIP_KWAJ))) done = 1;
+            if (unit->out_len == 0 && !(SPECIAL && (unit->flags & MSGPU_FLAG_MSZIP_KWAJ))) done = 1;
         }
         else {
             done = st.done; status = st.status; produced = st.produced; frame = st.frame; fx = (int32_t) st.R0;      /* (an LZX field, free here) */
@@ -449,6 +449,6 @@ struct ZipLaneC {
     MS_M void end(MsUnitState &st) {
         st.started = 1; st.done = done; st.status = status; st.produced = produced; st.frame = frame;
         st.ipos = b.ipos; st.bc = (uint32_t) b.bc; st.bb_lo = (uint32_t) b.bb; st.bb_hi = (uint32_t) (b.bb >> 32);
-        if (KWAJ) st.R0 = (uint32_t) fx;
+        if (SPECIAL) st.R0 = (uint32_t) fx;
     }
 };
