@@ -37,13 +37,20 @@ struct WaveArgs {
 /* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
  * warp is guaranteed to be converged on the hot step() loop; lanes leave it together as soon as one of
  * them needs service (a block header, a frame boundary) and come back once that is done. */
-template <class Lane, bool TWO = false>
+template <class Lane, bool TWO = false, bool SPLIT = false>
 __device__ __forceinline__ void p1_run(Lane &t)
 {
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
         if (!m0) break;
+        if constexpr (SPLIT) {    /* experimental: separate loops for the fast and the careful step (LzxLaneC OPT bit 5) */
+            if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
+                do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
+            else
+                do { if (t.phase == PH_DECODE) t.step_fast(); } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
+            continue;
+        }
         if (TWO) {      /* experimental: two steps per vote (a lane that left the run after the first one sits the second out) */
             do { if (t.phase == PH_DECODE) t.step(); if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
         }
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
-    p1_run<LzxLaneC<NT, HEADN, DELTA, H8LB, OPT>, (OPT & 2) != 0>(t);
+    p1_run<LzxLaneC<NT, HEADN, DELTA, H8LB, OPT>, (OPT & 2) != 0, (OPT & 32) != 0>(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
@@ -246,10 +253,10 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 /* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
 /* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
  * steps per vote, 33 both, 34 slot table in shared memory, 35 all three, 36 unpaired record stores,
- * 37 all four, 38 byte-wise literal stores, 39 all five, 40 = the default layout with a 5-bit LENGTH LUT and 224 head entries */
+ * 37 all four, 38 byte-wise literal stores, 39 all five, 41 fast / careful step in separate loops, 42 = 41 + all but "two steps per vote", 40 = the default layout with a 5-bit LENGTH LUT and 224 head entries */
 #define LZXC_VARIANTS(X) X(10, 512, 32, 0, 0) X(11, 448, 72, 0, 0) X(12, 384, 64, 0, 0) X(20, 448, 208, 5, 0) X(21, 448, 224, 4, 0) X(22, 448, 240, 4, 0) \
     X(30, 448, 256, 104, 0) X(31, 448, 256, 104, 1) X(32, 448, 256, 104, 2) X(33, 448, 256, 104, 3) X(34, 448, 256, 104, 4) X(35, 448, 256, 104, 7) \
-    X(36, 448, 256, 104, 8) X(37, 448, 256, 104, 15) X(38, 448, 256, 104, 16) X(39, 448, 256, 104, 31) X(40, 448, 224, 105, 0)
+    X(36, 448, 256, 104, 8) X(37, 448, 256, 104, 15) X(38, 448, 256, 104, 16) X(39, 448, 256, 104, 31) X(40, 448, 224, 105, 0) X(41, 448, 256, 104, 32) X(42, 448, 256, 104, 61)
 #define QTM_NT 160
 #define ZIPK_NT 448          /* the one shape of the MSZIP instantiation that knows KWAJ framing */
 #define ZIPK_HEADN 124

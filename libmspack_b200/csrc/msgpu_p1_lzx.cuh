@@ -87,6 +87,9 @@ template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxShar
  *   bit 2  extra_bits[] / position_base[] from a 64-entry table in shared memory (one per CTA, lzx_slot_entry) instead of the
  *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only
  *   bit 3  match records stored one by one (8 bytes each) instead of in pairs
+ *   bit 5  (p1_run) the careful step - the one with the end-of-input checks - runs in a loop of its own, entered only while some lane
+ *          of the warp is within 24 bytes of its input's end: the hot loop then holds ONE instantiation of the step instead of two
+ *          joined at its tail (48 of the ~245 warp-instructions per step are register moves at control-flow joins)
  *   bit 4  literals stored one byte at a time instead of gathered per aligned word (4 instructions instead of ~20 per literal,
  *          up to four times the literal stores) */
 MS_D uint32_t lzx_slot_entry(uint32_t slot) {          /* extra | (position_base - 2) << 5, lzxd.c:199-255 */
@@ -458,6 +461,9 @@ struct LzxLaneC {
          * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
         if (MS_UNLIKELY(b.ipos + (DELTA ? 32 : 24) > b.in_len)) step_plain<true>(); else step_plain<false>();     /* DELTA: one more refill */
     }
+    MS_M bool near_end() const { return b.ipos + (DELTA ? 32 : 24) > b.in_len; }
+    MS_M void step_fast() { step_plain<false>(); }
+    MS_M void step_careful() { step_plain<true>(); }
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
     template <bool careful> MS_M void step_plain() {
         lzx_refill(b);

@@ -87,6 +87,18 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
 }
 
 template <class Lane>
+static void emul_run3(Lane &t) {      /* p1_run<Lane, false, SPLIT = true> */
+    for (;;) {
+        t.service();
+        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
+        if (!m0) break;
+        if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
+            do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
+        else
+            do { if (t.phase == PH_DECODE) t.step_fast(); } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
+    }
+}
+template <class Lane>
 static void emul_run2(Lane &t) {      /* p1_run<Lane, TWO = true> */
     for (;;) {
         t.service();
@@ -148,7 +160,8 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
         SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if (packedq && !wide && (frames_per_round & 0x800)) { THQ1 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run2(t); t.end(st); }
+            if (packedq && !wide && (frames_per_round & 0x2000)) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3(t); t.end(st); }
+            else if (packedq && !wide && (frames_per_round & 0x800)) { THQ1 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run2(t); t.end(st); }
             else if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (packed && !wide) { THP t; t.bind((SHP *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }

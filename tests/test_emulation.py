@@ -216,7 +216,7 @@ PACKED_CASES = [dict(), dict(block_mode=1), dict(block_mode=2), dict(block_mode=
                 dict(data="zeros"), dict(unit_bytes=131072, block_frames=2, block_mode=2)]
 
 
-@pytest.mark.parametrize("layout", [0x200, 0x400, 0xC00], ids=["P", "Q", "Q+experiments"])
+@pytest.mark.parametrize("layout", [0x200, 0x400, 0xC00, 0x2400], ids=["P", "Q", "Q+experiments", "Q+split-loops"])
 @pytest.mark.parametrize("kw", PACKED_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
 def test_device_logic_lzx_packed_layout(emul, oracle_ref, kw, layout):
     """The packed shared-memory layouts of the LZX lanes (LzxSharedP: byte + two-bit head entries, four-word aligned-offset
@@ -271,7 +271,7 @@ def test_device_logic_long_codes_all_layouts(emul, oracle_ref):
         buf = np.frombuffer(comp + b"\0" * 16, dtype=np.uint8)
         o1, s1, _ = oracle_ref.decode_batch(u, buf, n)
         assert s1[0] == 0 and o1.tobytes() == data.tobytes()
-        for mode in (1, 0x201, 0x401, 0xC01, 0x101):
+        for mode in (1, 0x201, 0x401, 0xC01, 0x2401, 0x101):
             o2, s2 = emul(u, buf, n, mode)
             assert s2[0] == 0 and np.array_equal(o2, o1), (trial, hex(mode))
 
