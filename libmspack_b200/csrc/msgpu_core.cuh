@@ -164,6 +164,14 @@ MS_D uint32_t msb16le_swz(uint32_t x) { return (x << 16) | (x >> 16); }   /* two
 MS_D void lzx_refill(MsBits &b) {                 /* afterwards bc >= 32 */
     if (b.bc < 32) { b.bb |= (uint64_t) msb16le_swz(b.nextw) << (32 - b.bc); b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
+/* the same without the end-of-input test and without a branch: for callers that know the next word lies inside an aligned
+ * input (LzxLaneC's fast step, OPT bit 6) */
+MS_D void lzx_refill_nocheck(MsBits &b) {
+    const bool need = b.bc < 32;
+    const uint64_t add = (uint64_t) msb16le_swz(b.nextw) << ((32 - b.bc) & 63);
+    b.bb |= need ? add : 0ull; b.bc += need ? 32 : 0; b.ipos += need ? 4 : 0;
+    if (need) b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.ipos);
+}
 MS_D uint32_t msb_peek(const MsBits &b, int n) { return (uint32_t) (b.bb >> (64 - n)); }     /* 1 <= n <= 32 */
 MS_D void msb_drop(MsBits &b, int n) { b.bb <<= n; b.bc -= n; }
 /* ENSURE_BITS(n) fetches whole words: fails iff p + n > floor16(8 * (in_len + 2)) */

@@ -459,14 +459,19 @@ struct LzxLaneC {
     MS_M void step() {
         /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
          * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
+        if constexpr ((OPT & 64) != 0) { if (MS_UNLIKELY(near_end())) step_plain<true>(); else step_plain<false>(); }
+        else
         if (MS_UNLIKELY(b.ipos + (DELTA ? 32 : 24) > b.in_len)) step_plain<true>(); else step_plain<false>();     /* DELTA: one more refill */
     }
-    MS_M bool near_end() const { return b.ipos + (DELTA ? 32 : 24) > b.in_len; }
+    /* (OPT bit 6: the fast step loads its words unchecked, so a unit whose input is not 4-byte aligned - fast_end is then a large
+     * negative number - always takes the careful step) */
+    MS_M bool near_end() const { if constexpr ((OPT & 64) != 0) return b.ipos + (DELTA ? 28 : 20) > b.fast_end; else return b.ipos + (DELTA ? 32 : 24) > b.in_len; }
+    template <bool careful> MS_M void refill() { if constexpr (!careful && (OPT & 64) != 0) lzx_refill_nocheck(b); else lzx_refill(b); }
     MS_M void step_fast() { step_plain<false>(); }
     MS_M void step_careful() { step_plain<true>(); }
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
     template <bool careful> MS_M void step_plain() {
-        lzx_refill(b);
+        refill<careful>();
         uint32_t sym = main_sym(careful);
         if (sym < 256) {
             if constexpr ((OPT & 16) != 0) em.out[q] = (uint8_t) sym;          /* (q < frame_size by construction) */
@@ -495,8 +500,8 @@ struct LzxLaneC {
                     const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
                     off = pbase - 2;
                 }
-                if constexpr ((OPT & 1) != 0) { if (b.bc < (int) extra + 4) lzx_refill(b); }      /* (still below 32: the buffer has room) */
-                else lzx_refill(b);
+                if constexpr ((OPT & 1) != 0) { if (b.bc < (int) extra + 4) refill<careful>(); }      /* (still below 32: the buffer has room) */
+                else refill<careful>();
                 if (block_type == 2 && extra >= 3) {
                     if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
                     if constexpr (H8) off += aligned_sym(careful); else off += sym_smem(alim, MsBo32<NT>{ abo }, aa.sorted, careful);
@@ -505,7 +510,7 @@ struct LzxLaneC {
                 R2 = R1; R1 = R0; R0 = off;
             }
             if (DELTA && is_delta && ml == 257) {                    /* lzxd.c:589-611: the longest length announces more */
-                lzx_refill(b);
+                refill<careful>();
                 if (careful) lzx_check(b, 3);
                 const uint32_t p3 = msb_peek(b, 3);
                 const int pre = p3 < 4 ? 1 : (p3 < 6 ? 2 : 3), nb = p3 < 4 ? 8 : (p3 < 6 ? 10 : (p3 == 6 ? 12 : 15));

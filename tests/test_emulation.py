@@ -93,6 +93,10 @@ def test_device_logic_unaligned_input(emul, oracle_ref, shift):
         o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
         o2, s2 = emul(units, comp, b.out_bytes, 1)
         assert_same(units, o1, s1, o2, s2, f"unaligned {codec} shift {shift}")
+        if codec == CODEC_LZX:       # (the unchecked refill of the experimental shapes must leave such units to the careful step)
+            for layout in (0x4400, 0x6400):
+                o2, s2 = emul(units, comp, b.out_bytes, layout | 1)
+                assert_same(units, o1, s1, o2, s2, f"unaligned {codec} shift {shift} layout {layout:#x}")
 
 
 @pytest.mark.parametrize("shift", [1, 2])
@@ -216,7 +220,7 @@ PACKED_CASES = [dict(), dict(block_mode=1), dict(block_mode=2), dict(block_mode=
                 dict(data="zeros"), dict(unit_bytes=131072, block_frames=2, block_mode=2)]
 
 
-@pytest.mark.parametrize("layout", [0x200, 0x400, 0xC00, 0x2400], ids=["P", "Q", "Q+experiments", "Q+split-loops"])
+@pytest.mark.parametrize("layout", [0x200, 0x400, 0xC00, 0x2400, 0x4400, 0x6400], ids=["P", "Q", "Q+experiments", "Q+split-loops", "Q+unchecked-refill", "Q+unchecked-refill+all"])
 @pytest.mark.parametrize("kw", PACKED_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
 def test_device_logic_lzx_packed_layout(emul, oracle_ref, kw, layout):
     """The packed shared-memory layouts of the LZX lanes (LzxSharedP: byte + two-bit head entries, four-word aligned-offset
@@ -246,7 +250,7 @@ def test_device_logic_packed_layout_on_golden_vectors(emul):
         if entry["codec"] != CODEC_LZX:
             continue
         u, comp = golden_unit(entry)
-        for layout in (0x200, 0x400, 0xC00):
+        for layout in (0x200, 0x400, 0xC00, 0x4400, 0x6400):
             out, st = emul(u, comp, entry["out_len"], layout | 2)
             assert int(st[0]) == entry["err"], entry["name"]
             if entry["err"] == 0:
