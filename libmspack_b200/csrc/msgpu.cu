@@ -60,14 +60,14 @@ __device__ __forceinline__ void p1_run(Lane &t)
 
 #define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
 #define MISC_RING  1024u
-template <int NT, int HEADN, bool SPECIAL = false>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC) */
+template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC); OPT: experimental shapes */
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    ZipLaneC<NT, HEADN, SPECIAL> t; t.phase = PH_IDLE;
+    ZipLaneC<NT, HEADN, SPECIAL, OPT> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
@@ -250,6 +250,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * LZX 30 (LzxSharedQ: 256-entry packed head + LENGTH head, 10.59 -> 8.97 ms; 20-22 = LzxSharedP steps on the way, 11 = the
  * 72-entry 16-bit head of the first round-1 measurements). */
 #define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 96) X(14, 448, 124)
+#define ZIP_VARIANT_OPT1 15   /* experimental, not a default until measured: the shape of 14 with the unchecked branch-free refill (ZipLaneC OPT bit 0) */
 /* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
 /* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
  * steps per vote, 33 both, 34 slot table in shared memory, 35 all three, 36 unpaired record stores,
@@ -337,6 +338,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
     ZIPC_VARIANTS(SETATTRZC)
 #undef SETATTRZC
+    cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>));
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
 #define SETATTRC(id, nt, hn, lb, opt) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb, opt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
     LZXC_VARIANTS(SETATTRC)
@@ -350,6 +352,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define CHKZ(id, nt, hn) if (c->zip_variant == id) okz = true;
         ZIPC_VARIANTS(CHKZ)
 #undef CHKZ
+        if (c->zip_variant == ZIP_VARIANT_OPT1) okz = true;
 #define CHKL(id, nt, hn, lb, opt) if (c->lzx_variant == id) okl = true;
         LZXC_VARIANTS(CHKL)
 #undef CHKL
@@ -464,6 +467,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
+    if (ctx->zip_variant == ZIP_VARIANT_OPT1) zip_nt = ZIPK_NT;
     if (any_kwaj) zip_nt = ZIPK_NT;
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
@@ -607,6 +611,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define LAUNCHZC(id, nt, hn) if (!any_kwaj && ctx->zip_variant == id) k_p1_mszip<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             ZIPC_VARIANTS(LAUNCHZC)
 #undef LAUNCHZC
+            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             if (any_kwaj) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);

@@ -139,6 +139,13 @@ MS_D int64_t ms_bitpos(const MsBits &b) { return (int64_t) b.ipos * 8 - b.bc; }
 MS_D void lsb_refill(MsBits &b) {                 /* afterwards bc >= 32 */
     if (b.bc < 32) { b.bb |= (uint64_t) b.nextw << b.bc; b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
+/* the same without the end-of-input test and without a branch (callers: ZipLaneC's fast step with OPT bit 0; see lzx_refill_nocheck) */
+MS_D void lsb_refill_nocheck(MsBits &b) {
+    const bool need = b.bc < 32;
+    const uint64_t add = (uint64_t) b.nextw << (b.bc & 63);
+    b.bb |= need ? add : 0ull; b.bc += need ? 32 : 0; b.ipos += need ? 4 : 0;
+    if (need) b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.ipos);
+}
 MS_D uint32_t lsb_peek(const MsBits &b, int n) { return (uint32_t) b.bb & ((1u << n) - 1u); }
 MS_D void lsb_drop(MsBits &b, int n) { b.bb >>= n; b.bc -= n; }
 /* would the reference's ENSURE_BITS(n) at this position run past in_len + 2 bytes? */

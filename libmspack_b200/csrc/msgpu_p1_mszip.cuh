@@ -36,7 +36,7 @@ struct ZipSharedC {
 
 /* SPECIAL = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
  * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
-template <int NT, int HEADN, bool SPECIAL = false>
+template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT bit 0 (experimental): unchecked branch-free refill in the fast step */
 struct ZipLaneC {
     /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
      * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
@@ -392,9 +392,14 @@ struct ZipLaneC {
     /* the hot step (mszipd.c:243-300): one literal, or one match (length + distance), or the end-of-block code.
      * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
      * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
-    MS_M void step() { if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>(); }
+    MS_M void step() {
+        if constexpr ((OPT & 1) != 0) { if (MS_UNLIKELY(b.ipos + 20 > b.fast_end) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>(); }    /* (fast_end < 0: input not 4-byte aligned) */
+        else
+        if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>();
+    }
+    template <bool careful> MS_M void refill() { if constexpr (!careful && (OPT & 1) != 0) lsb_refill_nocheck(b); else lsb_refill(b); }
     template <bool careful> MS_M void step_t() {
-        lsb_refill(b);
+        refill<careful>();
         uint32_t sym = litlen_sym<careful>();
         if (sym < 256) {
             if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
@@ -409,7 +414,7 @@ struct ZipLaneC {
             else { eb = (c >> 2) - 1; length = ((4 + (c & 3)) << eb) + 3; }
             if (eb) length += extra_bits<careful>((int) eb);
             if (careful && b.err) { fail(b.err); return; }
-            lsb_refill(b);
+            refill<careful>();
             uint32_t d = dist_sym<careful>();
             if (d >= 30) { fail(b.err ? b.err : MS_EDECRUNCH); return; }     /* :260 */
             if (d < 4) { eb = 0; dist = d + 1; }                               /* dist_offsets / dist_extrabits, :53-68 */

@@ -351,6 +351,26 @@ def test_device_logic_mszip_structural_cases(emul, oracle_ref):
     assert list(s1[:7]) == [0] * 7 and s1[7] == 11 and s1[8] == 3          # the long block fails, the lone empty block runs out of input
 
 
+def test_device_logic_mszip_unchecked_refill(emul, oracle_ref):
+    """The experimental MSZIP shape (ZipLaneC OPT bit 0, MSGPU_ZIP_VARIANT=15: the fast step loads its words unchecked and
+    without a branch) decodes like the default: intact, damaged, truncated and unaligned inputs, several data kinds."""
+    rng = np.random.default_rng(77)
+    for kw in (dict(), dict(data="random", unit_bytes=40000), dict(unit_bytes=65536, level=1), dict(data="zeros"), dict(unit_bytes=100000, data="binary")):
+        b = gen.make_batch(CODEC_MSZIP, 16, **kw)
+        _compare(emul, oracle_ref, b.units, b.comp, b.out_bytes, f"mszip opt {kw}", (0x4001, 0x4002))
+        comp, units = b.comp.copy(), b.units.copy()
+        for i, u in enumerate(units):
+            lo, n = int(u["in_off"]), int(u["in_len"])
+            if i % 2 == 0:
+                comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+            else:
+                units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
+        _compare(emul, oracle_ref, units, comp, b.out_bytes, f"mszip opt corrupt {kw}", (0x4001,))
+        for shift in (1, 2, 3):
+            u2, c2 = _shifted(b, shift)
+            _compare(emul, oracle_ref, u2, c2, b.out_bytes, f"mszip opt shift {shift} {kw}", (0x4001,))
+
+
 def test_device_logic_quantum_many_window_laps(emul, oracle_ref):
     """Quantum units much longer than their window (the copy paths at the window's end, qtmd.c:358-416), intact and damaged."""
     rng = np.random.default_rng(5)
