@@ -471,6 +471,10 @@ struct LzxLaneC {
     MS_M void step_careful() { step_plain<true>(); }
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
     template <bool careful> MS_M void step_plain() {
+        /* OPT bit 7 (fast step only): no exits in the middle of the step - an error is remembered and raised at the end, where every
+         * variable already sits where the loop expects it (the early exits cost ~20 register moves per step at the join) */
+        constexpr bool LATE = !careful && (OPT & 128) != 0;
+        uint32_t bad = 0;
         refill<careful>();
         uint32_t sym = main_sym(careful);
         if (sym < 256) {
@@ -482,8 +486,11 @@ struct LzxLaneC {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
             if (ml == 7) {
+                if constexpr (LATE) { if (MS_UNLIKELY(length_empty)) bad = (uint32_t) (b.err ? b.err : MS_EDECRUNCH); else ml += length_sym(careful); }
+                else {
                 if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
                 ml += length_sym(careful);
+                }
             }
             ml += 2;
             if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
@@ -520,9 +527,12 @@ struct LzxLaneC {
                 msb_drop(b, nb);
             }
             if (careful && b.err) { fail(b.err); return; }
+            if constexpr (LATE) { if (!bad) bad = resolve_match_late(ml, off); }
+            else
             if (!resolve_match(ml, off)) return;
         }
         if (careful && b.err) { fail(b.err); return; }
+        if constexpr (LATE) { if (MS_UNLIKELY(bad)) { fail((int) bad); return; } }
         if (this_run <= 0) phase = PH_BLOCK;
     }
     /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
@@ -546,6 +556,27 @@ struct LzxLaneC {
         else emit_match(em, q, ml, eff);
         q += ml; this_run -= (int32_t) ml;
         return true;
+    }
+    /* the same for OPT bit 7: returns the error instead of raising it, and emits nothing when there is one */
+    MS_M uint32_t resolve_match_late(uint32_t ml, uint32_t off) {
+        uint32_t G = frame_start_pos + q, eff = off; bool bad = false;
+        if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
+            uint32_t wpr = G & (window_size - 1);
+            bad = (wpr + ml > window_size);
+            if (off > wpr) {
+                bad = bad || (off > frame_start_pos && (!DELTA || off - wpr > ref_len)) || (off - wpr > window_size);
+                if (off > window_size) eff = off - window_size;
+            }
+            if (eff == 0) eff = window_size;
+        }
+        bad = bad || (int32_t) ml > this_run;
+        if (!bad) {
+            if (DELTA) emit_match_wide(em, q, ml, eff);
+            else if constexpr ((OPT & 8) != 0) emit_match_single(em, q, ml, eff);
+            else emit_match(em, q, ml, eff);
+        }
+        q += ml; this_run -= (int32_t) ml;
+        return bad ? (uint32_t) MS_EDECRUNCH : 0u;
     }
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int32_t *e8, int nframes) {
