@@ -336,16 +336,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
-#define SETATTRZC(id, nt, hn) cudaFuncSetAttribute(k_p1_mszip<nt, hn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<nt, hn>));
-    ZIPC_VARIANTS(SETATTRZC)
-#undef SETATTRZC
-    cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>));
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
-#define SETATTRC(id, nt, hn, lb, opt) cudaFuncSetAttribute(k_p1_lzx<nt, hn, false, lb, opt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedSel<nt, hn, lb>::type));
-    LZXC_VARIANTS(SETATTRC)
-#undef SETATTRC
-    cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>));
-    cudaFuncSetAttribute(k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>));
     { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
@@ -360,7 +351,21 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
         if (!okz) c->zip_variant = 14;
         if (!okl) c->lzx_variant = 30;
     }
-    cudaFuncSetAttribute(k_p1_qtm<QTM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(QtmShared<QTM_NT>));
+    /* the entropy kernels use most of an SM's shared memory: opt in, for the shapes this context will launch */
+    cudaError_t ae = cudaSuccess;
+#define SETA(kernel, bytes) { cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)); if (e_ != cudaSuccess) ae = e_; }
+#define SETATTRZC(id, nt, hn) if (c->zip_variant == id) SETA((k_p1_mszip<nt, hn>), sizeof(ZipSharedC<nt, hn>))
+    ZIPC_VARIANTS(SETATTRZC)
+#undef SETATTRZC
+    if (c->zip_variant == ZIP_VARIANT_OPT1) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
+#define SETATTRC(id, nt, hn, lb, opt) if (c->lzx_variant == id) SETA((k_p1_lzx<nt, hn, false, lb, opt>), sizeof(LzxSharedSel<nt, hn, lb>::type))
+    LZXC_VARIANTS(SETATTRC)
+#undef SETATTRC
+    SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
+    SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
+    SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
+#undef SETA
+    if (ae != cudaSuccess) { fprintf(stderr, "msgpu_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(ae)); (void) cudaGetLastError(); msgpu_destroy(c); return nullptr; }
     return c;
 }
 
