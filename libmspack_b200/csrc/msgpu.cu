@@ -361,9 +361,10 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define SETATTRC(id, nt, hn, lb, opt) if (c->lzx_variant == id) SETA((k_p1_lzx<nt, hn, false, lb, opt>), sizeof(LzxSharedSel<nt, hn, lb>::type))
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
-    SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
     SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
     SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
+    /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
+    if (cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
 #undef SETA
     if (ae != cudaSuccess) { fprintf(stderr, "msgpu_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(ae)); (void) cudaGetLastError(); msgpu_destroy(c); return nullptr; }
     return c;
