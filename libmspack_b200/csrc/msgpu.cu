@@ -114,17 +114,17 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT>
+template <int NT, int OPT = 0>
 __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *save)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    QtmLane<NT> t; t.phase = PH_IDLE;
+    QtmLane<NT, OPT> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
-        t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
+        t.bind(reinterpret_cast<QtmShared<NT, OPT> *>(smem_raw), (int) threadIdx.x);
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
@@ -293,7 +293,8 @@ struct msgpu_ctx {
     std::string err;
     uint64_t launches = 0;
     size_t scratch_budget = 0;
-    int lzx_variant = 0, zip_variant = 0, p2_variant = 0;      /* MSGPU_P2_VARIANT=1: the byte-parallel pass A (experimental) */
+    int lzx_variant = 0, zip_variant = 0, p2_variant = 0, qtm_variant = 0;      /* MSGPU_QTM_VARIANT=1: two-level model scan (experimental) */
+         /* MSGPU_P2_VARIANT=1: the byte-parallel pass A (experimental) */
     size_t last_wave_n = 0, last_waves = 0;      /* msgpu_last_produced: units of the most recent wave / waves of the most recent batch */
     cudaStream_t last_stream = nullptr;
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
@@ -338,6 +339,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
     { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
+    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && atoi(v) == 1) ? 1 : 0; }
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
         bool okz = false, okl = false;
@@ -362,7 +364,8 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
     SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
-    SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
+    if (c->qtm_variant == 1) SETA((k_p1_qtm<QTM_NT, 1>), sizeof(QtmShared<QTM_NT, 1>))
+    else SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
     /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
     if (cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
 #undef SETA
@@ -637,6 +640,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             mark(0, st);
+            if (ctx->qtm_variant == 1) k_p1_qtm<QTM_NT, 1><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 1>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            else
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_q, f0, f1, st); ctx->launches += 2; mark(1, st); }

@@ -26,28 +26,39 @@
 #define QM6L  373
 #define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8 + 9 u16, padded */
 
-template <int NT>
-struct QtmShared {
+/* OPT bit 0 (experimental, MSGPU_QTM_VARIANT=1; not a default until measured): two-level scan.  The 32 lanes of a warp run
+ * GET_SYMBOL in lockstep, so a scan costs the warp as many rounds as its SLOWEST lane needs: measured on the text workload, 11.2
+ * four-entry rounds per symbol for the warp against 3.0 for a lane alone.  With the sum of every 8 differences kept next to them
+ * (grp[]: 51 sums, +102 bytes per lane) the scan first walks at most 8 group sums, then at most 8 entries: 3.4 rounds per
+ * symbol for the warp on the same data.  The sums follow every change of g[] (symbol update, rescale, re-sort) and are rebuilt
+ * from g[] when a unit's state is reloaded. */
+#define QTM_GRP 56            /* 1 + 4 x 8 + 3 + 5 + 6 + 4 = 51 group sums, padded for the four-wide reads */
+template <int NT, bool ON> struct QtmGroups { uint16_t grp[QTM_GRP * NT]; };
+template <int NT> struct QtmGroups<NT, false> { };
+template <int NT, int OPT = 0>
+struct QtmShared : QtmGroups<NT, (OPT & 1) != 0> {
     uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
     uint16_t tot[9 * NT];             /* T = cum[0] per model */
     uint8_t  sym[QTM_ENT * NT];
     uint8_t  shl[9 * NT];
 };
 
-template <int NT>
+template <int NT, int OPT = 0>
 struct QtmLane {
+    static constexpr bool GRP = (OPT & 1) != 0;
     MsBits b;
     uint16_t *cum, *tot; uint8_t *sym, *shl;
     uint32_t H, L, C;                 /* 16-bit values */
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
 
-    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; }
+    MS_M void bind(QtmShared<NT, OPT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; if constexpr (GRP) grp = sh->grp + tid; else grp = nullptr; }
 
     MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
         shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
 #pragma unroll 1
         for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
+        if constexpr (GRP) regroup(base, midx, len);
     }
 
     /* READ_BYTES bookkeeping: two more bytes fetched; fails past in_len + 2 (readbits.h:192-214) */
@@ -67,6 +78,7 @@ struct QtmLane {
                 cum[(base + i) * NT] = (uint16_t) (c - nn); nn = c;
             }
             tot[midx * NT] = (uint16_t) nn;
+            if constexpr (GRP) regroup(base, midx, entries);
         }
         else {
             shl[midx * NT] = 50;
@@ -94,6 +106,7 @@ struct QtmLane {
 #pragma unroll 1
             for (int i = 0; i < entries; i++) T += cum[(base + i) * NT];   /* :162-164 back to cumulative: T = cum[0] */
             tot[midx * NT] = (uint16_t) T;
+            if constexpr (GRP) regroup(base, midx, entries);
         }
     }
 
@@ -107,6 +120,23 @@ struct QtmLane {
          * bound: 5 warps per SM).  Entries past the model's end may be read (they lie inside the shared arrays) but are
          * never selected. */
         uint32_t prev = c0, cur, gj; int j = 0;
+        uint32_t sg = 0; int gsel = 0;
+        if constexpr (GRP) {
+            /* level 1: the first group whose END (cum[8 (k+1)]) is <= symf, or the last group; prev becomes cum at its start */
+            const int gb = grp_base(midx), ng = (entries + 7) >> 3;
+            int gi = 0;
+#pragma unroll 1
+            for (;; gi += 4) {
+                const uint32_t s0 = grp[(gb + gi) * NT], s1 = grp[(gb + gi + 1) * NT], s2 = grp[(gb + gi + 2) * NT], s3 = grp[(gb + gi + 3) * NT];
+                const uint32_t e1 = prev - s0, e2 = e1 - s1, e3 = e2 - s2, e4 = e3 - s3;
+                if (gi + 1 >= ng || e1 <= symf) { sg = s0; break; }
+                if (gi + 2 >= ng || e2 <= symf) { sg = s1; prev = e1; gi += 1; break; }
+                if (gi + 3 >= ng || e3 <= symf) { sg = s2; prev = e2; gi += 2; break; }
+                if (gi + 4 >= ng || e4 <= symf) { sg = s3; prev = e3; gi += 3; break; }
+                prev = e4;
+            }
+            gsel = gb + gi; j = gi << 3;
+        }
 #pragma unroll 1
         for (;; j += 4) {
             const uint32_t g0 = cum[(base + j) * NT], g1 = cum[(base + j + 1) * NT], g2 = cum[(base + j + 2) * NT], g3 = cum[(base + j + 3) * NT];
@@ -123,6 +153,7 @@ struct QtmLane {
         uint32_t Ln = (L + (cur * range) / c0) & 0xFFFFu;
         H = Hn; L = Ln;
         cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
+        if constexpr (GRP) grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
         if (c0 > 3800) update_model(base, midx, entries);
         /* :109-122 renormalise: all leading equal bits of L and H leave at once; the underflow case goes bit by bit */
@@ -287,6 +318,10 @@ struct QtmLane {
                 for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; sym[i * NT] = save[QTM_ENT * 2 + i]; }
 #pragma unroll 1
                 for (int i = 0; i < 9; i++) { shl[i * NT] = save[QTM_ENT * 3 + i]; tot[i * NT] = reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i]; }
+                if constexpr (GRP) {
+                    regroup(QM0, 0, 64); regroup(QM1, 1, 64); regroup(QM2, 2, 64); regroup(QM3, 3, 64);
+                    regroup(QM4, 4, ent4); regroup(QM5, 5, ent5); regroup(QM6, 6, ent6); regroup(QM6L, 7, 27); regroup(QM7, 8, 7);
+                }
             }
         }
         phase = done ? PH_IDLE : PH_FRAME;
@@ -301,6 +336,19 @@ struct QtmLane {
             for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; save[QTM_ENT * 2 + i] = sym[i * NT]; }
 #pragma unroll 1
             for (int i = 0; i < 9; i++) { save[QTM_ENT * 3 + i] = shl[i * NT]; reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i] = tot[i * NT]; }
+        }
+    }
+
+    uint16_t *grp;
+    /* first group sum of model midx (0-3 literals, 4-6 offsets, 7 length, 8 selector) */
+    MS_M static int grp_base(int midx) { return midx < 4 ? 1 + 8 * midx : (midx == 4 ? 33 : (midx == 5 ? 36 : (midx == 6 ? 41 : (midx == 7 ? 47 : 0)))); }
+    MS_M void regroup(int base, int midx, int entries) {              /* group sums from g[] */
+        const int gb = grp_base(midx);
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int i = 0; i < entries; i++) {
+            acc += cum[(base + i) * NT];
+            if ((i & 7) == 7 || i == entries - 1) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
         }
     }
 };

@@ -181,8 +181,14 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     }
     else if (u->codec == MSGPU_CODEC_QUANTUM) {
         typedef QtmShared<1> SH; typedef QtmLane<1> TH;
-        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
+        SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(QtmShared<1, 1>)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
+            if (frames_per_round & 0x4000) {       /* the experimental two-level model scan */
+                QtmLane<1, 1> t; t.bind((QtmShared<1, 1> *) sh, 0);
+                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
+                emul_run(t); t.end(st); resolve();
+                continue;
+            }
             TH t; t.bind(sh, 0);
             t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
             emul_run(t); t.end(st); resolve();

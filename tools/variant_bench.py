@@ -1,5 +1,6 @@
 """A/B of P1 kernel variants on the headline batch (development aid): one generated batch, one context per MSGPU_LZX_VARIANT,
-stage timing P1 / P2, round trip verified.  usage: variant_bench.py [units] [variant ids...]"""
+stage timing P1 / P2, round trip verified.  usage: variant_bench.py [units] [variant ids...]
+VB_CODEC=1 / 2 / 3 picks MSZIP (MSGPU_ZIP_VARIANT) / Quantum (MSGPU_QTM_VARIANT: 0, 1) / LZX (default)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -17,7 +18,7 @@ stream = torch.cuda.Stream(); torch.cuda.synchronize()
 libs = os.environ.get("VB_LIBS", "").split(",") if os.environ.get("VB_LIBS") else [None]
 p2s = [int(x) for x in os.environ.get("VB_P2", "0").split(",")]          # MSGPU_P2_VARIANT values (1 = the byte-parallel pass A)
 for lib, v, p2v in [(l, v, q) for l in libs for q in p2s for v in variants]:
-    os.environ["MSGPU_LZX_VARIANT" if codec == 3 else "MSGPU_ZIP_VARIANT"] = str(v)
+    os.environ["MSGPU_LZX_VARIANT" if codec == 3 else ("MSGPU_QTM_VARIANT" if codec == 2 else "MSGPU_ZIP_VARIANT")] = str(v)
     os.environ["MSGPU_P2_VARIANT"] = str(p2v)
     if lib:
         _codec._lib = None; _codec.LIB_PATH = os.path.abspath(lib)       # another build of the library (dlopen keeps both)
