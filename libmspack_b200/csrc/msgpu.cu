@@ -339,7 +339,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
     { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
-    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && atoi(v) == 1) ? 1 : 0; }
+    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 0; }      /* QtmLane OPT bits: 1 two-level scan, 2 loop-free renormalisation */
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
         bool okz = false, okl = false;
@@ -365,6 +365,8 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #undef SETATTRC
     SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
     if (c->qtm_variant == 1) SETA((k_p1_qtm<QTM_NT, 1>), sizeof(QtmShared<QTM_NT, 1>))
+    else if (c->qtm_variant == 2) SETA((k_p1_qtm<QTM_NT, 2>), sizeof(QtmShared<QTM_NT, 2>))
+    else if (c->qtm_variant == 3) SETA((k_p1_qtm<QTM_NT, 3>), sizeof(QtmShared<QTM_NT, 3>))
     else SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
     /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
     if (cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
@@ -641,6 +643,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             mark(0, st);
             if (ctx->qtm_variant == 1) k_p1_qtm<QTM_NT, 1><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 1>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            else if (ctx->qtm_variant == 2) k_p1_qtm<QTM_NT, 2><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 2>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            else if (ctx->qtm_variant == 3) k_p1_qtm<QTM_NT, 3><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 3>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             else
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);

@@ -26,7 +26,7 @@
 #define QM6L  373
 #define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8 + 9 u16, padded */
 
-/* OPT bit 0 (experimental, MSGPU_QTM_VARIANT=1; not a default until measured): two-level scan.  The 32 lanes of a warp run
+/* OPT bit 0 (experimental, MSGPU_QTM_VARIANT=1 or 3; not a default until measured): two-level scan.  The 32 lanes of a warp run
  * GET_SYMBOL in lockstep, so a scan costs the warp as many rounds as its SLOWEST lane needs: measured on the text workload, 11.2
  * four-entry rounds per symbol for the warp against 3.0 for a lane alone.  With the sum of every 8 differences kept next to them
  * (grp[]: 51 sums, +102 bytes per lane) the scan first walks at most 8 group sums, then at most 8 entries: 3.4 rounds per
@@ -156,6 +156,33 @@ struct QtmLane {
         if constexpr (GRP) grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
         if (c0 > 3800) update_model(base, midx, entries);
+        if constexpr ((OPT & 2) != 0) {
+            /* OPT bit 1 (experimental): the renormalisation without a loop.  The reference's loop (:109-122) first shifts out the
+             * leading bits L and H share, then - the top bits now being 0 / 1 - the run of "underflow" positions right below
+             * (L bit 1, H bit 0), and stops; the order cannot repeat because an underflow shift leaves the top bits at 0 / 1.  So:
+             * one shift by the count of equal leading bits, one by the length of the underflow run (m shifts of C ^= 0x4000 flip,
+             * in the end, only the bit that lands on top).  In lockstep the loop costs a warp 4.3 iterations per symbol on the text
+             * workload (its slowest lane), these two blocks cost 2. */
+            const uint32_t x = (L ^ H) & 0xFFFFu;
+            if (!(x & 0x8000u)) {
+                const int n = x ? MS_CLZ(x << 16) : 16;
+                L = (L << n) & 0xFFFFu; H = ((H << n) | ((1u << n) - 1u)) & 0xFFFFu;
+                while (bl < n) fetch2();
+                bl -= n;
+                if (b.bc < n) qtm_refill(b);
+                C = ((C << n) | msb_peek(b, n)) & 0xFFFFu; msb_drop(b, n);
+            }
+            const uint32_t u = L & ~H & 0x7FFFu;
+            const int m = MS_CLZ(~(u << 17));                  /* ones from bit 14 downwards: 0..15 */
+            if (m) {
+                L = (L << m) & 0x7FFFu; H = ((H << m) | ((1u << m) - 1u) | 0x8000u) & 0xFFFFu;
+                while (bl < m) fetch2();
+                bl -= m;
+                if (b.bc < m) qtm_refill(b);
+                C = (((C << m) ^ 0x8000u) | msb_peek(b, m)) & 0xFFFFu; msb_drop(b, m);
+            }
+            return s;
+        }
         /* :109-122 renormalise: all leading equal bits of L and H leave at once; the underflow case goes bit by bit */
 #pragma unroll 1
         for (;;) {

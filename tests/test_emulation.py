@@ -373,13 +373,13 @@ def test_device_logic_mszip_unchecked_refill(emul, oracle_ref):
 
 def test_device_logic_quantum_two_level_scan(emul, oracle_ref):
     """The experimental Quantum shape (QtmLane OPT bit 0, MSGPU_QTM_VARIANT=1: group sums over every 8 model entries, scan in two
-    levels) decodes like the default - every window size's model sizes, long units (rescales and re-sorts of every model), state
+    levels; bit 1, MSGPU_QTM_VARIANT=2 / 3: renormalisation in two shifts instead of a loop) decodes like the default - every window size's model sizes, long units (rescales and re-sorts of every model), state
     reloads between launches (F = 1 and 2), damaged streams."""
     rng = np.random.default_rng(41)
     for kw in (dict(), dict(window_bits=10, unit_bytes=100000), dict(window_bits=12, unit_bytes=65536, data="binary"), dict(window_bits=15, unit_bytes=200000),
                dict(window_bits=17, data="random", unit_bytes=40000), dict(window_bits=21, unit_bytes=300000, data="binary"), dict(data="zeros", unit_bytes=70000)):
         b = gen.make_batch(CODEC_QUANTUM, 8, **kw)
-        _compare(emul, oracle_ref, b.units, b.comp, b.out_bytes, f"quantum two-level {kw}", (0x4001, 0x4002))
+        _compare(emul, oracle_ref, b.units, b.comp, b.out_bytes, f"quantum two-level {kw}", (0x4001, 0x4002, 0x2001, 0x6001, 0x6002))
         comp, units = b.comp.copy(), b.units.copy()
         for i, u in enumerate(units):
             lo, n = int(u["in_off"]), int(u["in_len"])
@@ -387,7 +387,7 @@ def test_device_logic_quantum_two_level_scan(emul, oracle_ref):
                 comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
             else:
                 units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
-        _compare(emul, oracle_ref, units, comp, b.out_bytes, f"quantum two-level corrupt {kw}", (0x4001,))
+        _compare(emul, oracle_ref, units, comp, b.out_bytes, f"quantum two-level corrupt {kw}", (0x4001, 0x2001, 0x6001))
 
 
 def test_device_logic_quantum_many_window_laps(emul, oracle_ref):
