@@ -183,6 +183,7 @@ struct QtmLane {
             }
             return s;
         }
+        else {
         /* :109-122 renormalise: all leading equal bits of L and H leave at once; the underflow case goes bit by bit */
 #pragma unroll 1
         for (;;) {
@@ -199,6 +200,7 @@ struct QtmLane {
             C = ((C << n) | msb_peek(b, n)) & 0xFFFFu; msb_drop(b, n);
         }
         return s;
+        }
     }
 
     MS_M uint32_t read_many(int n) {                                      /* READ_MANY_BITS, readbits.h:143-153 */
