@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of the outputs")
     ap.add_argument("--cpu-sample", type=int, default=32768, help="units in the cpu_baseline sample")
+    ap.add_argument("--e2e-inflight", type=int, default=1, choices=[1, 2],
+                    help="2: also measure e2e with two batches in flight (two host threads, one context each; every step still one "
+                         "msgpu_decode_batch_host call with its own H2D and D2H) and report it as e2e.inflight2 - not validated on a GPU yet")
     return ap.parse_args()
 
 
@@ -257,6 +260,45 @@ def main():
     e2e = {"value": round(world * U / float(t_e.item()) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": int(b.comp.size + b.units.nbytes),
            "d2h_bytes_per_step": int(b.out_bytes + h_st.nbytes), "steps": e2e_steps, "verified": e2e_ok,
            "api": "msgpu_decode_batch_host (include/msgpu.h), pinned host buffers"}
+
+    # ---- optional: the same with two batches in flight (the host call is synchronous; a caller with a stream of batches overlaps
+    # one batch's D2H with the next one's H2D + kernels by calling from two threads, one context each) ----
+    if args.e2e_inflight == 2:
+        try:
+            import threading
+            dec2 = BatchDecoder(local_rank)
+            h_out2 = torch.empty(b.out_bytes, dtype=torch.uint8).pin_memory()
+            h_st2 = np.full(n, -1, dtype=np.int32)
+            lanes = [(dec, h_out, h_st, (e2e_steps + 1) // 2), (dec2, h_out2, h_st2, e2e_steps // 2)]
+            dec2.decode_host_into(b.units, h_in.data_ptr(), h_in.numel(), h_out2.data_ptr(), h_out2.numel(), h_st2)
+            errs = []
+
+            def work(d, ho, hs, k):
+                try:
+                    for _ in range(k):
+                        d.decode_host_into(b.units, h_in.data_ptr(), h_in.numel(), ho.data_ptr(), ho.numel(), hs)
+                except Exception as ex:      # noqa: BLE001 - reported below
+                    errs.append(repr(ex))
+            barrier()
+            h_out.zero_(); h_out2.zero_()
+            ths = [threading.Thread(target=work, args=l) for l in lanes]
+            t0 = time.perf_counter()
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            torch.cuda.synchronize()
+            s2 = (time.perf_counter() - t0) / e2e_steps
+            t_2 = torch.tensor([s2], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_2, op=dist.ReduceOp.MAX)
+            raw_t = torch.from_numpy(b.raw)
+            ok2 = not errs and bool((h_st == 0).all()) and bool((h_st2 == 0).all()) and bool(torch.equal(h_out, raw_t)) and bool(torch.equal(h_out2, raw_t))
+            e2e["inflight2"] = {"value": round(world * U / float(t_2.item()) / 1e9, 3), "unit": "GB/s", "steps": e2e_steps, "verified": ok2,
+                                "how": "two host threads, one msgpu context each, alternate steps; every step one msgpu_decode_batch_host call", "errors": errs[:2]}
+            dec2.close()
+        except Exception as ex:      # noqa: BLE001 - the sequential e2e above stands
+            e2e["inflight2"] = {"error": repr(ex)[:300]}
 
     # ---- optional output gather over NCCL (off the data path; reported separately) ----
     gather = None

@@ -13,4 +13,4 @@ VB_P2=0,1 VB_CODEC=1 timeout 150 python tools/variant_bench.py 32768 14 15 > gpu
 VB_CODEC=2 timeout 150 python tools/variant_bench.py 16384 0 1 2 3 > gpurun_out/r2_variants_qtm.log 2>&1; cat gpurun_out/r2_variants_qtm.log      # Quantum: two-level model scan (1), loop-free renormalisation (2), both (3)
 timeout 300 python tools/configs_bench.py 32768 > gpurun_out/r2_configs.log 2>&1; cat gpurun_out/r2_configs.log
 timeout 200 python tools/config4_bench.py 65536 > gpurun_out/r2_config4.log 2>&1; tail -1 gpurun_out/r2_config4.log
-timeout 200 python bench.py > gpurun_out/r2_bench.log 2>&1; grep "^{" gpurun_out/r2_bench.log | cut -c1-300
+timeout 240 python bench.py --e2e-inflight 2 > gpurun_out/r2_bench.log 2>&1; grep "^{" gpurun_out/r2_bench.log | cut -c1-300; grep -o '"e2e": {.*' gpurun_out/r2_bench.log | cut -c1-700
