@@ -296,6 +296,70 @@ MS_D int ms_canon_build_h(LensFn lens, int nsyms, int ref_tablebits, BoT bo, uin
     return 0;
 }
 
+/* ms_canon_build_h for the experimental shapes (LzxLaneC OPT bit 8): both passes over the symbols fetch four code lengths before
+ * they use them - the lengths live in lane-interleaved global scratch and every one of them is an L2 round trip that the plain
+ * loops wait out one by one.  (A function of its own so that the measured kernels compile exactly as before.) */
+template <int ROOT, int NT, class LensFn, class HeadFn, class BoT>
+MS_D int ms_canon_build_h4(LensFn lens, int nsyms, int ref_tablebits, BoT bo, uint16_t *cnt, uint16_t *sorted,
+                          HeadFn put_head, uint16_t *lut, uint32_t limv[16])
+{
+#pragma unroll 1
+    for (int l = 0; l <= 16; l++) cnt[l * NT] = 0;
+    {
+        int s = 0;
+#pragma unroll 1
+        for (; s + 4 <= nsyms; s += 4) {
+            const uint32_t l0 = lens(s), l1 = lens(s + 1), l2 = lens(s + 2), l3 = lens(s + 3);
+            if (l0 >= 1 && l0 <= 16) cnt[l0 * NT]++;
+            if (l1 >= 1 && l1 <= 16) cnt[l1 * NT]++;
+            if (l2 >= 1 && l2 <= 16) cnt[l2 * NT]++;
+            if (l3 >= 1 && l3 <= 16) cnt[l3 * NT]++;
+        }
+#pragma unroll 1
+        for (; s < nsyms; s++) { uint32_t l = lens(s); if (l >= 1 && l <= 16) cnt[l * NT]++; }
+    }
+    uint32_t sum_short = 0, sum_all = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 16; l++) { sum_all += (uint32_t) cnt[l * NT] << (16 - l); if (l <= ref_tablebits) sum_short = sum_all; }
+    int maxlen = 16;
+    if (sum_short > 65536u) return 1;
+    if (sum_short == 65536u) maxlen = ref_tablebits;
+    else if (sum_all != 65536u) return 1;
+    uint32_t lim = 0, off = 0;
+#pragma unroll
+    for (int l = 1; l <= 16; l++) {
+        uint32_t c = (l <= maxlen) ? cnt[l * NT] : 0;
+        bo.put(l, lim, off);
+        cnt[l * NT] = (uint16_t) off;                       /* running index of the next l-bit symbol */
+        lim += c << (16 - l); limv[l - 1] = lim; off += c;
+    }
+    if (ROOT > 0) {
+#pragma unroll 1
+        for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
+    }
+    auto place = [&](int s, int l) {
+        if (l < 1 || l > maxlen) return;
+        uint32_t k = cnt[l * NT]; cnt[l * NT] = (uint16_t) (k + 1);
+        sorted[k * MS_WARP] = (uint16_t) s;
+        put_head(k, (uint32_t) s);
+        if (ROOT > 0 && l <= ROOT) {
+            uint32_t code = bo.code_of(l, k);
+            uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
+            for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = (uint16_t) ((s << 4) | l);
+        }
+    };
+    int s = 0;
+#pragma unroll 1
+    for (; s + 4 <= nsyms; s += 4) {
+        const int l0 = (int) lens(s), l1 = (int) lens(s + 1), l2 = (int) lens(s + 2), l3 = (int) lens(s + 3);
+        place(s, l0); place(s + 1, l1); place(s + 2, l2); place(s + 3, l3);
+    }
+#pragma unroll 1
+    for (; s < nsyms; s++) place(s, (int) lens(s));
+    return 0;
+}
+
+
 template <int ROOT, int NT, class LensFn>
 MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
                         uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])

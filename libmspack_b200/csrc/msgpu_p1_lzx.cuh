@@ -218,6 +218,10 @@ struct LzxLaneC {
         for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
 #pragma unroll 1
         for (uint32_t x = first; x < last;) {
+            /* OPT bit 8: the previous length of symbol x is fetched BEFORE the pretree symbol is decoded (an L2 round trip that the
+             * decode then covers); used by the plain-delta and the run-of-deltas codes below */
+            int prevl = 0;
+            if constexpr ((OPT & 256) != 0) prevl = (int) lens[x * 32];
             lzx_refill(b);
             int z = (int) sym_smem(llim, lbo, pa.sorted);
             if (b.err) return b.err;
@@ -228,10 +232,11 @@ struct LzxLaneC {
                 lzx_refill(b);
                 z = (int) sym_smem(llim, lbo, pa.sorted);
                 if (b.err) return b.err;
+                if constexpr ((OPT & 256) != 0) z = prevl - z; else
                 z = (int) lens[x * 32] - z; if (z < 0) z += 17;
                 while (y--) { lens[x * 32] = (uint8_t) z; x++; }
             }
-            else { z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
+            else { if constexpr ((OPT & 256) != 0) z = prevl - z; else z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
         }
         return 0;
     }
@@ -242,6 +247,13 @@ struct LzxLaneC {
 #pragma unroll 1
             for (int w = 0; w < HEADN / 16; w++) mhi[w * NT] = 0;
             uint8_t *lo = mlo; uint32_t *hi = mhi;
+            if constexpr ((OPT & 256) != 0) {
+            if (ms_canon_build_h4<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
+                                        [=](uint32_t k, uint32_t sym) {
+                                            if (k < (uint32_t) HEADN) { lo[k * Shared::ROW] = (uint8_t) sym; hi[(k >> 4) * NT] |= (sym >> 8) << ((k & 15u) * 2u); }
+                                        }, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+            }
+            else
             if (ms_canon_build_h<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
                                         [=](uint32_t k, uint32_t sym) {
                                             if (k < (uint32_t) HEADN) { lo[k * Shared::ROW] = (uint8_t) sym; hi[(k >> 4) * NT] |= (sym >> 8) << ((k & 15u) * 2u); }
@@ -260,8 +272,14 @@ struct LzxLaneC {
         uint8_t *l = len_len; uint32_t lv[16];
         length_empty = 0;
         uint8_t *lh = lhead;
-        if (ms_canon_build_h<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
-                                       [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv)) {
+        int rc;
+        if constexpr ((OPT & 256) != 0)
+            rc = ms_canon_build_h4<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
+                                       [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv);
+        else
+            rc = ms_canon_build_h<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
+                                       [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv);
+        if (rc) {
 #pragma unroll 1
             for (int i = 0; i < LZX_LEN_SYMS; i++) if (l[i * 32] > 0) return MS_EDECRUNCH;
             length_empty = 1;

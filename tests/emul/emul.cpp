@@ -158,7 +158,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
         typedef LzxSharedP<1, 32, 4> SHP; typedef LzxLaneC<1, 32, false, 4> THP;        /* the packed shared-memory layouts */
         typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ; typedef LzxLaneC<1, 32, false, 104, 29> THQ1;     /* + OPT bits 0, 2, 3 and 4 */
-        typedef LzxLaneC<1, 32, false, 104, 192> THQ6; typedef LzxLaneC<1, 32, false, 104, 253> THQ7;     /* OPT bits 6 and 7 (unchecked refill in the fast step, one exit at its end): alone, and with everything but "two steps" (frames_per_round bit 0x4000) */
+        typedef LzxLaneC<1, 32, false, 104, 448> THQ6; typedef LzxLaneC<1, 32, false, 104, 509> THQ7;     /* OPT bits 6, 7 and 8 (unchecked refill in the fast step, one exit at its end, prefetched code lengths): alone, and with everything but "two steps" (frames_per_round bit 0x4000) */
         static uint32_t slot_tab[64]; for (uint32_t k = 0; k < 64; k++) slot_tab[k] = lzx_slot_entry(k);
         const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
         SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
