@@ -368,6 +368,14 @@ MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo,
                                       [=](uint32_t k, uint32_t s) { if (k < headn) head[k * NT] = (uint16_t) s; }, lut, limv);
 }
 
+template <int ROOT, int NT, class LensFn>
+MS_D int ms_canon_build4(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
+                         uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
+{
+    return ms_canon_build_h4<ROOT, NT>(lens, nsyms, ref_tablebits, MsBo32<NT>{ bo }, cnt, sorted,
+                                       [=](uint32_t k, uint32_t s) { if (k < headn) head[k * NT] = (uint16_t) s; }, lut, limv);
+}
+
 /* code length from limits in registers: lim[j] = limit[j + 1], non-decreasing.  len = 1 + #{ j : lim[j] <= v16 },
  * found by a 4-step binary search over the 15 registers (the register picked at each step is a small select tree on
  * the earlier outcomes): ~20 instructions and a short dependent chain instead of 15 dependent compare-and-adds. */

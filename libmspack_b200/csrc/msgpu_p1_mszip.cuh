@@ -36,7 +36,7 @@ struct ZipSharedC {
 
 /* SPECIAL = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
  * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
-template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT bit 0 (experimental): unchecked branch-free refill in the fast step */
+template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT (experimental): bit 0 unchecked branch-free refill in the fast step, bit 1 prefetching table build */
 struct ZipLaneC {
     /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
      * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
@@ -170,6 +170,11 @@ struct ZipLaneC {
         }
         /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
         uint8_t *l = lens;
+        if constexpr ((OPT & 2) != 0) {      /* (experimental: four code lengths fetched at a time, ms_canon_build_h4) */
+            if (ms_canon_build4<0, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
+                                       (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
+        }
+        else
         if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
                                   (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
 #pragma unroll
