@@ -4,7 +4,7 @@
 #   2. the LZX P1 experiments 31-52 against the default 30, the MSZIP ones (15-17) against 14 (tools/variant_bench.py: one batch, stage timing, verified);
 #   3. the other BASELINE configs at bench size (MSZIP, reset intervals, mixed, Quantum) and a per-GPU share of configs[3];
 #   4. the bench line.
-# usage: gpurun --timeout 900 -- 'bash tools/r2_first_call.sh'      (about 5 minutes of box time)
+# usage: gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'      (about 12-15 minutes of box time)
 mkdir -p gpurun_out
 ( time timeout 300 python -m pytest tests -m gpu -q --durations=10 ) > gpurun_out/r2_pytest_gpu.log 2>&1; tail -8 gpurun_out/r2_pytest_gpu.log
 ( MSGPU_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q -x ) > gpurun_out/r2_pytest_experimental.log 2>&1; tail -5 gpurun_out/r2_pytest_experimental.log
