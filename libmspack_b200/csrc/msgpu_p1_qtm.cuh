@@ -70,6 +70,19 @@ struct QtmLane {
             /* :130-136 on cumulative values: cum[i] >>= 1; if (cum[i] <= cum[i+1]) cum[i] = cum[i+1] + 1 */
             shl[midx * NT] = (uint8_t) s;
             uint32_t old = 0, nn = 0;
+            if constexpr (GRP) {                 /* the same loop, with the group sums rebuilt on the way down */
+                const int gb = grp_base(midx);
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int i = entries - 1; i >= 0; i--) {
+                    old += cum[(base + i) * NT];
+                    uint32_t c = old >> 1;
+                    if (c <= nn) c = nn + 1;
+                    cum[(base + i) * NT] = (uint16_t) (c - nn); acc += c - nn; nn = c;
+                    if ((i & 7) == 0) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
+                }
+            }
+            else
 #pragma unroll 1
             for (int i = entries - 1; i >= 0; i--) {
                 old += cum[(base + i) * NT];                               /* the reference's cum[i] before the rescale */
@@ -78,7 +91,6 @@ struct QtmLane {
                 cum[(base + i) * NT] = (uint16_t) (c - nn); nn = c;
             }
             tot[midx * NT] = (uint16_t) nn;
-            if constexpr (GRP) regroup(base, midx, entries);
         }
         else {
             shl[midx * NT] = 50;
