@@ -250,7 +250,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * LZX 30 (LzxSharedQ: 256-entry packed head + LENGTH head, 10.59 -> 8.97 ms; 20-22 = LzxSharedP steps on the way, 11 = the
  * 72-entry 16-bit head of the first round-1 measurements). */
 #define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 96) X(14, 448, 124)
-#define ZIP_VARIANT_OPT1 15   /* experimental, not defaults until measured: the shape of 14 with ZipLaneC OPT = 1 (unchecked branch-free refill), 16: OPT = 2 (prefetching table build), 17: OPT = 3 */
+#define ZIP_VARIANT_OPT1 15   /* experimental, not defaults until measured: the shape of 14 with ZipLaneC OPT = 1 (unchecked branch-free refill), 16: OPT = 2 (prefetching table build), 17: OPT = 3, 18: OPT = 4 (byte-wise literal stores), 19: OPT = 7 */
 /* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
 /* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
  * steps per vote, 33 both, 34 slot table in shared memory, 35 all three, 36 unpaired record stores,
@@ -347,7 +347,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 #define CHKZ(id, nt, hn) if (c->zip_variant == id) okz = true;
         ZIPC_VARIANTS(CHKZ)
 #undef CHKZ
-        if (c->zip_variant >= ZIP_VARIANT_OPT1 && c->zip_variant <= ZIP_VARIANT_OPT1 + 2) okz = true;
+        if (c->zip_variant >= ZIP_VARIANT_OPT1 && c->zip_variant <= ZIP_VARIANT_OPT1 + 4) okz = true;
 #define CHKL(id, nt, hn, lb, opt) if (c->lzx_variant == id) okl = true;
         LZXC_VARIANTS(CHKL)
 #undef CHKL
@@ -363,6 +363,8 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     if (c->zip_variant == ZIP_VARIANT_OPT1) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
     if (c->zip_variant == ZIP_VARIANT_OPT1 + 1) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 2>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
     if (c->zip_variant == ZIP_VARIANT_OPT1 + 2) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 3>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
+    if (c->zip_variant == ZIP_VARIANT_OPT1 + 3) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 4>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
+    if (c->zip_variant == ZIP_VARIANT_OPT1 + 4) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 7>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
 #define SETATTRC(id, nt, hn, lb, opt) if (c->lzx_variant == id) SETA((k_p1_lzx<nt, hn, false, lb, opt>), sizeof(LzxSharedSel<nt, hn, lb>::type))
     LZXC_VARIANTS(SETATTRC)
 #undef SETATTRC
@@ -482,7 +484,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 #define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
     ZIPC_VARIANTS(PICKNTZC)
 #undef PICKNTZC
-    if (ctx->zip_variant >= ZIP_VARIANT_OPT1 && ctx->zip_variant <= ZIP_VARIANT_OPT1 + 2) zip_nt = ZIPK_NT;
+    if (ctx->zip_variant >= ZIP_VARIANT_OPT1 && ctx->zip_variant <= ZIP_VARIANT_OPT1 + 4) zip_nt = ZIPK_NT;
     if (any_kwaj) zip_nt = ZIPK_NT;
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
@@ -629,6 +631,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 1) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 2><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 2) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 3><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 3) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 4><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 4) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 7><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             if (any_kwaj) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);

@@ -36,7 +36,7 @@ struct ZipSharedC {
 
 /* SPECIAL = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
  * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
-template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT (experimental): bit 0 unchecked branch-free refill in the fast step, bit 1 prefetching table build */
+template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT (experimental): bit 0 unchecked branch-free refill in the fast step, bit 1 prefetching table build, bit 2 byte-wise literal stores */
 struct ZipLaneC {
     /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
      * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
@@ -263,6 +263,8 @@ struct ZipLaneC {
             {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
                 int32_t bp = lsb_bytepos(b);
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
+                    if constexpr ((OPT & 4) != 0) { for (uint32_t k = 0; k < len; k++) lit_bytewise(q + k, b.in[bp + (int32_t) k]); }
+                    else
                     emit_raw(em, q, b.in, bp, len);
                     q += len; lsb_seek_byte(b, bp + (int32_t) len);
                     if (SPECIAL && bp + (int32_t) len > fx) fx = bp + (int32_t) len;
@@ -275,6 +277,7 @@ struct ZipLaneC {
                 uint32_t v = rd(8);
                 if (b.err) { fail(b.err); return; }
                 if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+                if constexpr ((OPT & 4) != 0) lit_bytewise(q, v); else
                 emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
@@ -403,11 +406,17 @@ struct ZipLaneC {
         if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>();
     }
     template <bool careful> MS_M void refill() { if constexpr (!careful && (OPT & 1) != 0) lsb_refill_nocheck(b); else lsb_refill(b); }
+    /* OPT bit 2 (experimental, plain instantiation only): literal bytes go to the output one by one instead of through the word
+     * gatherer (~30 instructions per literal step for the lanes that have one); every literal path of the lane must then do the same,
+     * because a gathered word is stored whole */
+    static_assert(!(SPECIAL && (OPT & 4) != 0), "byte-wise literals are not implemented for the KWAJ / repair instantiation");
+    MS_M void lit_bytewise(uint32_t qq, uint32_t v) { if (qq < em.limit) em.out[qq] = (uint8_t) v; }
     template <bool careful> MS_M void step_t() {
         refill<careful>();
         uint32_t sym = litlen_sym<careful>();
         if (sym < 256) {
             if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
+            if constexpr ((OPT & 4) != 0) lit_bytewise(q, sym); else
             emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), sym); q++;
         }
         else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;

@@ -143,7 +143,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH; typedef ZipLaneC<1, 32, true> THK;     /* THK: units with KWAJ framing */
-        typedef ZipLaneC<1, 32, false, 3> TH1;      /* the experimental unchecked refill (frames_per_round bit 0x4000) */
+        typedef ZipLaneC<1, 32, false, 7> TH1;      /* the experimental unchecked refill (frames_per_round bit 0x4000) */
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) aligned_alloc(64, (ZIP_AUX_BYTES + 63) & ~(size_t) 63); memset(aux, 0, ZIP_AUX_BYTES);   /* 32-byte aligned like the device's */
         const bool kwaj = (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) != 0;
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
