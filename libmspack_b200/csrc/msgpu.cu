@@ -340,7 +340,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
     { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
-    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 0; }      /* QtmLane OPT bits: 1 two-level scan, 2 loop-free renormalisation */
+    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && ((atoi(v) >= 1 && atoi(v) <= 4) || atoi(v) == 7)) ? atoi(v) : 0; }      /* QtmLane OPT bits: 1 two-level scan, 2 loop-free renormalisation, 4 divisions through a float reciprocal */
     { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
     {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
         bool okz = false, okl = false;
@@ -372,6 +372,8 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     if (c->qtm_variant == 1) SETA((k_p1_qtm<QTM_NT, 1>), sizeof(QtmShared<QTM_NT, 1>))
     else if (c->qtm_variant == 2) SETA((k_p1_qtm<QTM_NT, 2>), sizeof(QtmShared<QTM_NT, 2>))
     else if (c->qtm_variant == 3) SETA((k_p1_qtm<QTM_NT, 3>), sizeof(QtmShared<QTM_NT, 3>))
+    else if (c->qtm_variant == 4) SETA((k_p1_qtm<QTM_NT, 4>), sizeof(QtmShared<QTM_NT, 4>))
+    else if (c->qtm_variant == 7) SETA((k_p1_qtm<QTM_NT, 7>), sizeof(QtmShared<QTM_NT, 7>))
     else SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
     /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
     if (cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
@@ -654,6 +656,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (ctx->qtm_variant == 1) k_p1_qtm<QTM_NT, 1><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 1>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             else if (ctx->qtm_variant == 2) k_p1_qtm<QTM_NT, 2><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 2>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             else if (ctx->qtm_variant == 3) k_p1_qtm<QTM_NT, 3><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 3>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            else if (ctx->qtm_variant == 4) k_p1_qtm<QTM_NT, 4><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 4>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+            else if (ctx->qtm_variant == 7) k_p1_qtm<QTM_NT, 7><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 7>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             else
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);

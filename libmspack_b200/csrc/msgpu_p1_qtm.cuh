@@ -33,6 +33,26 @@
  * symbol for the warp on the same data.  The sums follow every change of g[] (symbol update, rescale, re-sort) and are rebuilt
  * from g[] when a unit's state is reloaded. */
 #define QTM_GRP 56            /* 1 + 4 x 8 + 3 + 5 + 6 + 4 = 51 group sums, padded for the four-wide reads */
+/* OPT bit 2 (experimental): the three 32-bit divisions of GET_SYMBOL through a float reciprocal.  Quotients here are small (a
+ * frequency below 2^12, or a 16-bit interval bound), so q = trunc(float(n) * (1 / float(d))) is off by at most one - relative error
+ * of the product < 1.5 * 2^-22 (approximate reciprocal included), times a quotient < 2^20, is < 0.4 - and one remainder test each
+ * way makes it exact; a quotient estimate of 2^20 or more (only a damaged stream gets there) takes the plain division. */
+MS_D float ms_rcpf(uint32_t d) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, (float) d);
+#else
+    return 1.0f / (float) d;
+#endif
+}
+MS_D uint32_t ms_div_rcp(uint32_t n, uint32_t d, float rd) {
+    const float qf = (float) n * rd;
+    if (MS_UNLIKELY(!(qf < 1048576.0f))) return n / d;
+    uint32_t q = (uint32_t) qf;
+    const int32_t r = (int32_t) (n - q * d);
+    if (r < 0) q--;
+    else if ((uint32_t) r >= d) q++;
+    return q;
+}
 template <int NT, bool ON> struct QtmGroups { uint16_t grp[QTM_GRP * NT]; };
 template <int NT> struct QtmGroups<NT, false> { };
 template <int NT, int OPT = 0>
@@ -126,7 +146,9 @@ struct QtmLane {
     MS_M uint32_t get_symbol(int base, int midx, int entries) {
         uint32_t range = ((H - L) & 0xFFFFu) + 1u;
         uint32_t c0 = tot[midx * NT];
-        uint32_t symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
+        uint32_t symf;
+        if constexpr ((OPT & 4) != 0) symf = ms_div_rcp((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1), range, ms_rcpf(range)) & 0xFFFFu;
+        else symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
         /* first j with cum[j+1] <= symf, or the last entry (cum[j+1] = cum[j] - g[j]).  Four entries per round: the four
          * shared-memory loads are independent, so a round costs one load latency instead of four (the kernel is latency
          * bound: 5 warps per SM).  Entries past the model's end may be read (they lie inside the shared arrays) but are
@@ -161,8 +183,16 @@ struct QtmLane {
         }
         uint32_t s = sym[(base + j) * NT];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
-        uint32_t Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
-        uint32_t Ln = (L + (cur * range) / c0) & 0xFFFFu;
+        uint32_t Hn, Ln;
+        if constexpr ((OPT & 4) != 0) {
+            const float rc = ms_rcpf(c0);
+            Hn = (L + ms_div_rcp(prev * range, c0, rc) - 1) & 0xFFFFu;
+            Ln = (L + ms_div_rcp(cur * range, c0, rc)) & 0xFFFFu;
+        }
+        else {
+        Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
+        Ln = (L + (cur * range) / c0) & 0xFFFFu;
+        }
         H = Hn; L = Ln;
         cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
         if constexpr (GRP) grp[gsel * NT] = (uint16_t) (sg + 8);

@@ -184,13 +184,13 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(QtmShared<1, 1>)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             if ((frames_per_round & 0x4000) && (frames_per_round & 0x2000)) {       /* + the loop-free renormalisation */
-                QtmLane<1, 3> t; t.bind((QtmShared<1, 3> *) sh, 0);
+                QtmLane<1, 7> t; t.bind((QtmShared<1, 7> *) sh, 0);
                 t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
                 emul_run(t); t.end(st); resolve();
                 continue;
             }
             if (frames_per_round & 0x2000) {
-                QtmLane<1, 2> t; t.bind((QtmShared<1, 2> *) sh, 0);
+                QtmLane<1, 6> t; t.bind((QtmShared<1, 6> *) sh, 0);
                 t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
                 emul_run(t); t.end(st); resolve();
                 continue;

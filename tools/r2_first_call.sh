@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 timeout 320 python tools/variant_bench.py 65536 30 31 32 33 34 35 36 37 38 39 40 41 42 43 44 45 46 47 48 49 50 51 52 > gpurun_out/r2_variants.log 2>&1; cat gpurun_out/r2_variants.log
 VB_P2=0,1 timeout 100 python tools/variant_bench.py 65536 30 > gpurun_out/r2_variants_p2.log 2>&1; cat gpurun_out/r2_variants_p2.log      # the byte-parallel pass A of P2
 VB_P2=0,1 VB_CODEC=1 timeout 150 python tools/variant_bench.py 32768 14 15 16 17 18 19 > gpurun_out/r2_variants_p2_zip.log 2>&1; cat gpurun_out/r2_variants_p2_zip.log
-VB_CODEC=2 timeout 150 python tools/variant_bench.py 16384 0 1 2 3 > gpurun_out/r2_variants_qtm.log 2>&1; cat gpurun_out/r2_variants_qtm.log      # Quantum: two-level model scan (1), loop-free renormalisation (2), both (3)
+VB_CODEC=2 timeout 150 python tools/variant_bench.py 16384 0 1 2 3 4 7 > gpurun_out/r2_variants_qtm.log 2>&1; cat gpurun_out/r2_variants_qtm.log      # Quantum: two-level model scan (1), loop-free renormalisation (2), both (3), reciprocal divisions (4), all (7)
 timeout 300 python tools/configs_bench.py 32768 > gpurun_out/r2_configs.log 2>&1; cat gpurun_out/r2_configs.log
 timeout 200 python tools/config4_bench.py 65536 > gpurun_out/r2_config4.log 2>&1; tail -1 gpurun_out/r2_config4.log
 timeout 240 python bench.py --e2e-inflight 2 > gpurun_out/r2_bench.log 2>&1; grep "^{" gpurun_out/r2_bench.log | cut -c1-300; grep -o '"e2e": {.*' gpurun_out/r2_bench.log | cut -c1-700
