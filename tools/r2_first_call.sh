@@ -16,3 +16,4 @@ VB_CODEC=2 timeout 240 python tools/variant_bench.py 16384 0 1 2 3 4 7 > gpurun_
 timeout 300 python tools/configs_bench.py 32768 > gpurun_out/r2_configs.log 2>&1; cat gpurun_out/r2_configs.log
 timeout 200 python tools/config4_bench.py 65536 > gpurun_out/r2_config4.log 2>&1; tail -1 gpurun_out/r2_config4.log
 timeout 240 python bench.py --e2e-inflight 2 > gpurun_out/r2_bench.log 2>&1; grep "^{" gpurun_out/r2_bench.log | cut -c1-300; grep -o '"e2e": {.*' gpurun_out/r2_bench.log | cut -c1-700
+python tools/rank_variants.py gpurun_out/r2_variants*.log > gpurun_out/r2_ranking.txt 2>&1; cat gpurun_out/r2_ranking.txt
