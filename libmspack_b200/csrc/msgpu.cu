@@ -48,7 +48,10 @@ __device__ __forceinline__ void p1_run(Lane &t)
             if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
                 do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
             else
-                do { if (t.phase == PH_DECODE) t.step_fast(); } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
+                do {
+                    if (t.phase == PH_DECODE) t.step_fast();
+                    if constexpr (TWO) { if (t.phase == PH_DECODE && !t.near_end()) t.step_fast(); }      /* (both experiments: a second fast step before the vote) */
+                } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
             continue;
         }
         if (TWO) {      /* experimental: two steps per vote (a lane that left the run after the first one sits the second out) */
@@ -254,13 +257,13 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 /* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
 /* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
  * steps per vote, 33 both, 34 slot table in shared memory, 35 all three, 36 unpaired record stores,
- * 37 all four, 38 byte-wise literal stores, 39 all five, 41 fast / careful step in separate loops, 42 = 41 + all but "two steps per vote", 43 unchecked branch-free refill in the fast step, 44 = 43 + 31, 45 = 43 + 41, 46 = 43 + 42, 47 one exit at the end of the fast step, 48 = 43 + 47, 49 = 45 + 47, 50 = 46 + 47, 51 code lengths prefetched in read_lens and in the table builds, 52 = 50 + 51, 40 = the default layout with a 5-bit LENGTH LUT and 224 head entries */
+ * 37 all four, 38 byte-wise literal stores, 39 all five, 41 fast / careful step in separate loops, 42 = 41 + all but "two steps per vote", 43 unchecked branch-free refill in the fast step, 44 = 43 + 31, 45 = 43 + 41, 46 = 43 + 42, 47 one exit at the end of the fast step, 48 = 43 + 47, 49 = 45 + 47, 50 = 46 + 47, 51 code lengths prefetched in read_lens and in the table builds, 52 = 50 + 51, 53 = 52 + two fast steps per vote, 40 = the default layout with a 5-bit LENGTH LUT and 224 head entries */
 #define LZXC_VARIANTS(X) X(10, 512, 32, 0, 0) X(11, 448, 72, 0, 0) X(12, 384, 64, 0, 0) X(20, 448, 208, 5, 0) X(21, 448, 224, 4, 0) X(22, 448, 240, 4, 0) \
     X(30, 448, 256, 104, 0) X(31, 448, 256, 104, 1) X(32, 448, 256, 104, 2) X(33, 448, 256, 104, 3) X(34, 448, 256, 104, 4) X(35, 448, 256, 104, 7) \
     X(36, 448, 256, 104, 8) X(37, 448, 256, 104, 15) X(38, 448, 256, 104, 16) X(39, 448, 256, 104, 31) X(40, 448, 224, 105, 0) X(41, 448, 256, 104, 32) X(42, 448, 256, 104, 61) \
     X(43, 448, 256, 104, 64) X(44, 448, 256, 104, 65) X(45, 448, 256, 104, 96) X(46, 448, 256, 104, 125) \
     X(47, 448, 256, 104, 128) X(48, 448, 256, 104, 192) X(49, 448, 256, 104, 224) X(50, 448, 256, 104, 253) \
-    X(51, 448, 256, 104, 256) X(52, 448, 256, 104, 509)
+    X(51, 448, 256, 104, 256) X(52, 448, 256, 104, 509) X(53, 448, 256, 104, 511)
 #define QTM_NT 160
 #define ZIPK_NT 448          /* the one shape of the MSZIP instantiation that knows KWAJ framing */
 #define ZIPK_HEADN 124

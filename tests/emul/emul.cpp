@@ -86,8 +86,8 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
     }
 }
 
-template <class Lane>
-static void emul_run3(Lane &t) {      /* p1_run<Lane, false, SPLIT = true> */
+template <class Lane, bool TWO = false>
+static void emul_run3(Lane &t) {      /* p1_run<Lane, TWO, SPLIT = true> */
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
@@ -95,7 +95,7 @@ static void emul_run3(Lane &t) {      /* p1_run<Lane, false, SPLIT = true> */
         if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
             do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
         else
-            do { if (t.phase == PH_DECODE) t.step_fast(); } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
+            do { if (t.phase == PH_DECODE) t.step_fast(); if (TWO) { if (t.phase == PH_DECODE && !t.near_end()) t.step_fast(); } } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
     }
 }
 template <class Lane>
@@ -158,12 +158,12 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
         typedef LzxSharedP<1, 32, 4> SHP; typedef LzxLaneC<1, 32, false, 4> THP;        /* the packed shared-memory layouts */
         typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ; typedef LzxLaneC<1, 32, false, 104, 29> THQ1;     /* + OPT bits 0, 2, 3 and 4 */
-        typedef LzxLaneC<1, 32, false, 104, 448> THQ6; typedef LzxLaneC<1, 32, false, 104, 509> THQ7;     /* OPT bits 6, 7 and 8 (unchecked refill in the fast step, one exit at its end, prefetched code lengths): alone, and with everything but "two steps" (frames_per_round bit 0x4000) */
+        typedef LzxLaneC<1, 32, false, 104, 448> THQ6; typedef LzxLaneC<1, 32, false, 104, 511> THQ7;     /* OPT bits 6, 7 and 8 (unchecked refill in the fast step, one exit at its end, prefetched code lengths): alone, and with everything but "two steps" (frames_per_round bit 0x4000) */
         static uint32_t slot_tab[64]; for (uint32_t k = 0; k < 64; k++) slot_tab[k] = lzx_slot_entry(k);
         const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
         SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if (packedq && !wide && (frames_per_round & 0x4000) && (frames_per_round & 0x2000)) { THQ7 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3(t); t.end(st); }
+            if (packedq && !wide && (frames_per_round & 0x4000) && (frames_per_round & 0x2000)) { THQ7 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3<THQ7, true>(t); t.end(st); }
             else if (packedq && !wide && (frames_per_round & 0x4000)) { THQ6 t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (packedq && !wide && (frames_per_round & 0x2000)) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3(t); t.end(st); }
             else if (packedq && !wide && (frames_per_round & 0x800)) { THQ1 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run2(t); t.end(st); }

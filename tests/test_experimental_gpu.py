@@ -1,4 +1,4 @@
-"""The experimental kernel shapes (MSGPU_LZX_VARIANT 31-52, MSGPU_ZIP_VARIANT 15-19, MSGPU_QTM_VARIANT 1-4, 7,
+"""The experimental kernel shapes (MSGPU_LZX_VARIANT 31-53, MSGPU_ZIP_VARIANT 15-19, MSGPU_QTM_VARIANT 1-4, 7,
 MSGPU_P2_VARIANT 1) against the reference's decoders on the GPU: intact, damaged and truncated units, unaligned inputs.
 They are not defaults and have not run on a B200 yet, so this file only runs when MSGPU_TEST_EXPERIMENTAL=1 is set
 (tools/r2_first_call.sh does, under its own timeout) - the default gpu tier never launches an unmeasured kernel."""
@@ -13,7 +13,7 @@ from util import assert_same
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("MSGPU_TEST_EXPERIMENTAL") != "1", reason="set MSGPU_TEST_EXPERIMENTAL=1")]
 
-SHAPES = [("MSGPU_LZX_VARIANT", v, CODEC_LZX) for v in list(range(31, 40)) + list(range(40, 53))] + [("MSGPU_ZIP_VARIANT", v, CODEC_MSZIP) for v in (15, 16, 17, 18, 19)] + \
+SHAPES = [("MSGPU_LZX_VARIANT", v, CODEC_LZX) for v in list(range(31, 40)) + list(range(40, 54))] + [("MSGPU_ZIP_VARIANT", v, CODEC_MSZIP) for v in (15, 16, 17, 18, 19)] + \
          [("MSGPU_QTM_VARIANT", v, CODEC_QUANTUM) for v in (1, 2, 3, 4, 7)] + [("MSGPU_P2_VARIANT", 1, CODEC_LZX), ("MSGPU_P2_VARIANT", 1, CODEC_MSZIP)]
 CASES = {CODEC_LZX: [dict(), dict(block_mode=4, split=3), dict(unit_bytes=65536, reset_interval=2, block_mode=4), dict(intel=1, data="binary", unit_bytes=70000, block_mode=2),
                      dict(window_bits=15, unit_bytes=100000, block_mode=4), dict(data="random"), dict(data="zeros")],
