@@ -37,40 +37,27 @@ struct WaveArgs {
 /* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
  * warp is guaranteed to be converged on the hot step() loop; lanes leave it together as soon as one of
  * them needs service (a block header, a frame boundary) and come back once that is done. */
-template <class Lane, bool TWO = false, bool SPLIT = false>
+template <class Lane>
 __device__ __forceinline__ void p1_run(Lane &t)
 {
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
         if (!m0) break;
-        if constexpr (SPLIT) {    /* experimental: separate loops for the fast and the careful step (LzxLaneC OPT bit 5) */
-            if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
-                do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
-            else
-                do {
-                    if (t.phase == PH_DECODE) t.step_fast();
-                    if constexpr (TWO) { if (t.phase == PH_DECODE && !t.near_end()) t.step_fast(); }      /* (both experiments: a second fast step before the vote) */
-                } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
-            continue;
-        }
-        if (TWO) {      /* experimental: two steps per vote (a lane that left the run after the first one sits the second out) */
-            do { if (t.phase == PH_DECODE) t.step(); if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
-        }
-        else do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
+        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
     }
 }
 
 #define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
 #define MISC_RING  1024u
-template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC); OPT: experimental shapes */
+template <int NT, int HEADN, bool SPECIAL = false>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC) */
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    ZipLaneC<NT, HEADN, SPECIAL, OPT> t; t.phase = PH_IDLE;
+    ZipLaneC<NT, HEADN, SPECIAL> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
@@ -91,7 +78,7 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
 }
 
 /* DELTA = the instantiation for waves that hold LZX DELTA units (it decodes plain LZX units as well) */
-template <int NT, int HEADN, bool DELTA, int H8LB, int OPT = 0>
+template <int NT, int HEADN, bool DELTA, int H8LB>
 __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux,
                                                  int32_t *e8info, const uint32_t *e8base)
 {
@@ -99,13 +86,7 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    LzxLaneC<NT, HEADN, DELTA, H8LB, OPT> t; t.phase = PH_IDLE;
-    if constexpr ((OPT & 4) != 0) {          /* experimental: the slot table, one per CTA */
-        __shared__ uint32_t s_slot[64];
-        if (threadIdx.x < 64) s_slot[threadIdx.x] = lzx_slot_entry(threadIdx.x);
-        __syncthreads();
-        t.slot_tab = s_slot;
-    }
+    LzxLaneC<NT, HEADN, DELTA, H8LB> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<typename LzxSharedSel<NT, HEADN, H8LB>::type *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
@@ -113,21 +94,21 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
     }
-    p1_run<LzxLaneC<NT, HEADN, DELTA, H8LB, OPT>, (OPT & 2) != 0, (OPT & 32) != 0>(t);
+    p1_run(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT, int OPT = 0>
+template <int NT>
 __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *save)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    QtmLane<NT, OPT> t; t.phase = PH_IDLE;
+    QtmLane<NT> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
-        t.bind(reinterpret_cast<QtmShared<NT, OPT> *>(smem_raw), (int) threadIdx.x);
+        t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
@@ -143,7 +124,7 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 #else
 #define P2_BOUNDS __launch_bounds__(P2_WARPS * 32)
 #endif
-template <bool WIDE, int PA = 0>
+template <bool WIDE>
 __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
 {
     __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
@@ -158,7 +139,7 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
-        p2_resolve_frame<WIDE, false, false, PA>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        p2_resolve_frame<WIDE, false, false>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
     }
 }
@@ -247,26 +228,18 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 }
 
 /* ------------------------------------------------------------------------------------------ host side */
-/* P1 kernel shapes (id, threads per CTA, shared-memory head entries); MSGPU_ZIP_VARIANT / MSGPU_LZX_VARIANT pick one.
- * 448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident wave.
- * Defaults (measured on the B200, headline batches): MSZIP 14 (124-entry head: every coded symbol of a text block, 9.70 -> 8.81 ms),
- * LZX 30 (LzxSharedQ: 256-entry packed head + LENGTH head, 10.59 -> 8.97 ms; 20-22 = LzxSharedP steps on the way, 11 = the
- * 72-entry 16-bit head of the first round-1 measurements). */
-#define ZIPC_VARIANTS(X) X(10, 512, 32) X(11, 448, 48) X(12, 384, 64) X(13, 448, 96) X(14, 448, 124)
-#define ZIP_VARIANT_OPT1 15   /* experimental, not defaults until measured: the shape of 14 with ZipLaneC OPT = 1 (unchecked branch-free refill), 16: OPT = 2 (prefetching table build), 17: OPT = 3, 18: OPT = 4 (byte-wise literal stores), 19: OPT = 7 */
-/* (id, lanes per CTA, head entries, 0 = 16-bit head | LENGTH LUT bits of the packed layout LzxSharedP | 100 + LUT bits: LzxSharedQ) */
-/* last column: OPT bits of LzxLaneC / p1_run - experimental shapes, not defaults until measured: 31 exact-need refill, 32 two
- * steps per vote, 33 both, 34 slot table in shared memory, 35 all three, 36 unpaired record stores,
- * 37 all four, 38 byte-wise literal stores, 39 all five, 41 fast / careful step in separate loops, 42 = 41 + all but "two steps per vote", 43 unchecked branch-free refill in the fast step, 44 = 43 + 31, 45 = 43 + 41, 46 = 43 + 42, 47 one exit at the end of the fast step, 48 = 43 + 47, 49 = 45 + 47, 50 = 46 + 47, 51 code lengths prefetched in read_lens and in the table builds, 52 = 50 + 51, 53 = 52 + two fast steps per vote, 40 = the default layout with a 5-bit LENGTH LUT and 224 head entries */
-#define LZXC_VARIANTS(X) X(10, 512, 32, 0, 0) X(11, 448, 72, 0, 0) X(12, 384, 64, 0, 0) X(20, 448, 208, 5, 0) X(21, 448, 224, 4, 0) X(22, 448, 240, 4, 0) \
-    X(30, 448, 256, 104, 0) X(31, 448, 256, 104, 1) X(32, 448, 256, 104, 2) X(33, 448, 256, 104, 3) X(34, 448, 256, 104, 4) X(35, 448, 256, 104, 7) \
-    X(36, 448, 256, 104, 8) X(37, 448, 256, 104, 15) X(38, 448, 256, 104, 16) X(39, 448, 256, 104, 31) X(40, 448, 224, 105, 0) X(41, 448, 256, 104, 32) X(42, 448, 256, 104, 61) \
-    X(43, 448, 256, 104, 64) X(44, 448, 256, 104, 65) X(45, 448, 256, 104, 96) X(46, 448, 256, 104, 125) \
-    X(47, 448, 256, 104, 128) X(48, 448, 256, 104, 192) X(49, 448, 256, 104, 224) X(50, 448, 256, 104, 253) \
-    X(51, 448, 256, 104, 256) X(52, 448, 256, 104, 509) X(53, 448, 256, 104, 511)
+/* P1 kernel shapes.  448 lanes per CTA = 14 warps per SM fills the shared memory of an SM and covers 65 536 units in ONE resident
+ * wave.  Round 2 measured every shape round 1 had prepared (profiles/r2_variants.txt) and kept one per codec:
+ *   MSZIP   448 lanes, 124-entry head, byte-wise literal stores            (round-1 shape 18: P1 8.65 -> 7.89 ms on 32 768 units)
+ *   LZX     448 lanes, LzxSharedQ (256-entry packed head + LENGTH head), exact-need refill   (shape 31: P1 9.02 -> 8.52 ms)
+ *   Quantum 160 lanes, two-level model scan + loop-free renormalisation    (shape 3: P1 77.3 -> 56.0 ms on 16 384 units)
+ * the other 32 shapes and the byte-parallel pass A of P2 (6.77 against 6.20 ms) measured slower or equal and were deleted. */
+#define ZIP_NT 448
+#define ZIP_HEADN 124
+#define LZX_NT 448
+#define LZX_HEADN 256
+#define LZX_H8LB 104
 #define QTM_NT 160
-#define ZIPK_NT 448          /* the one shape of the MSZIP instantiation that knows KWAJ framing */
-#define ZIPK_HEADN 124
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
 
@@ -297,8 +270,6 @@ struct msgpu_ctx {
     std::string err;
     uint64_t launches = 0;
     size_t scratch_budget = 0;
-    int lzx_variant = 0, zip_variant = 0, p2_variant = 0, qtm_variant = 0;      /* MSGPU_QTM_VARIANT=1: two-level model scan (experimental) */
-         /* MSGPU_P2_VARIANT=1: the byte-parallel pass A (experimental) */
     size_t last_wave_n = 0, last_waves = 0;      /* msgpu_last_produced: units of the most recent wave / waves of the most recent batch */
     cudaStream_t last_stream = nullptr;
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
@@ -341,45 +312,15 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
-    { const char *v = getenv("MSGPU_ZIP_VARIANT"); c->zip_variant = v ? atoi(v) : 14; }
-    { const char *v = getenv("MSGPU_P2_VARIANT"); c->p2_variant = v ? atoi(v) : 0; }
-    { const char *v = getenv("MSGPU_QTM_VARIANT"); c->qtm_variant = (v && ((atoi(v) >= 1 && atoi(v) <= 4) || atoi(v) == 7)) ? atoi(v) : 0; }      /* QtmLane OPT bits: 1 two-level scan, 2 loop-free renormalisation, 4 divisions through a float reciprocal */
-    { const char *v = getenv("MSGPU_LZX_VARIANT"); c->lzx_variant = v ? atoi(v) : 30; }
-    {   /* an id that names no compiled shape would launch nothing: fall back to the defaults */
-        bool okz = false, okl = false;
-#define CHKZ(id, nt, hn) if (c->zip_variant == id) okz = true;
-        ZIPC_VARIANTS(CHKZ)
-#undef CHKZ
-        if (c->zip_variant >= ZIP_VARIANT_OPT1 && c->zip_variant <= ZIP_VARIANT_OPT1 + 4) okz = true;
-#define CHKL(id, nt, hn, lb, opt) if (c->lzx_variant == id) okl = true;
-        LZXC_VARIANTS(CHKL)
-#undef CHKL
-        if (!okz) c->zip_variant = 14;
-        if (!okl) c->lzx_variant = 30;
-    }
-    /* the entropy kernels use most of an SM's shared memory: opt in, for the shapes this context will launch */
+    /* the entropy kernels use most of an SM's shared memory: opt in */
     cudaError_t ae = cudaSuccess;
 #define SETA(kernel, bytes) { cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)); if (e_ != cudaSuccess) ae = e_; }
-#define SETATTRZC(id, nt, hn) if (c->zip_variant == id) SETA((k_p1_mszip<nt, hn>), sizeof(ZipSharedC<nt, hn>))
-    ZIPC_VARIANTS(SETATTRZC)
-#undef SETATTRZC
-    if (c->zip_variant == ZIP_VARIANT_OPT1) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
-    if (c->zip_variant == ZIP_VARIANT_OPT1 + 1) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 2>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
-    if (c->zip_variant == ZIP_VARIANT_OPT1 + 2) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 3>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
-    if (c->zip_variant == ZIP_VARIANT_OPT1 + 3) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 4>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
-    if (c->zip_variant == ZIP_VARIANT_OPT1 + 4) SETA((k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 7>), sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>))
-#define SETATTRC(id, nt, hn, lb, opt) if (c->lzx_variant == id) SETA((k_p1_lzx<nt, hn, false, lb, opt>), sizeof(LzxSharedSel<nt, hn, lb>::type))
-    LZXC_VARIANTS(SETATTRC)
-#undef SETATTRC
+    SETA((k_p1_mszip<ZIP_NT, ZIP_HEADN>), sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>))
+    SETA((k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB>), sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type))
     SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
-    if (c->qtm_variant == 1) SETA((k_p1_qtm<QTM_NT, 1>), sizeof(QtmShared<QTM_NT, 1>))
-    else if (c->qtm_variant == 2) SETA((k_p1_qtm<QTM_NT, 2>), sizeof(QtmShared<QTM_NT, 2>))
-    else if (c->qtm_variant == 3) SETA((k_p1_qtm<QTM_NT, 3>), sizeof(QtmShared<QTM_NT, 3>))
-    else if (c->qtm_variant == 4) SETA((k_p1_qtm<QTM_NT, 4>), sizeof(QtmShared<QTM_NT, 4>))
-    else if (c->qtm_variant == 7) SETA((k_p1_qtm<QTM_NT, 7>), sizeof(QtmShared<QTM_NT, 7>))
-    else SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
+    SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
     /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
-    if (cudaFuncSetAttribute(k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
+    if (cudaFuncSetAttribute(k_p1_mszip<ZIP_NT, ZIP_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
 #undef SETA
     if (ae != cudaSuccess) { fprintf(stderr, "msgpu_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(ae)); (void) cudaGetLastError(); msgpu_destroy(c); return nullptr; }
     return c;
@@ -481,20 +422,11 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     const int F = (maxfr >= 2 || any_kwaj) ? 2 : 1;            /* (a repair-mode MSZIP block may need two frame slots) */
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
-    uint32_t lzx_nt = 128, zip_nt = 128;
-#define PICKNTC(id, nt, hn, lb, opt) if (ctx->lzx_variant == id) lzx_nt = nt;
-    LZXC_VARIANTS(PICKNTC)
-#undef PICKNTC
-    if (any_delta) lzx_nt = LZXD_NT;
-#define PICKNTZC(id, nt, hn) if (ctx->zip_variant == id) zip_nt = nt;
-    ZIPC_VARIANTS(PICKNTZC)
-#undef PICKNTZC
-    if (ctx->zip_variant >= ZIP_VARIANT_OPT1 && ctx->zip_variant <= ZIP_VARIANT_OPT1 + 4) zip_nt = ZIPK_NT;
-    if (any_kwaj) zip_nt = ZIPK_NT;
+    const uint32_t lzx_nt = any_delta ? LZXD_NT : LZX_NT, zip_nt = ZIP_NT;
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
-    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2688u * 4u;   /* mixed batches: 10752 = lcm of the 384/448/512-lane CTA shapes */
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2240u;   /* mixed batches: lcm of the 448- and 160-lane CTA shapes */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     const uint32_t nchains = (uint32_t) (chains.size() / 2);
     if (nchains) subsz = 0x40000000u;          /* a chain is resolved in order after ALL its blocks left P1: one sub-wave */
@@ -622,7 +554,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     auto p2_launch = [&](const WaveArgs &w, const uint32_t *list, uint32_t f0, uint32_t f1, cudaStream_t st) {
         if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
-        else if (ctx->p2_variant == 1) k_p2_resolve<false, 1><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);     /* experimental pass A */
         else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
     };
     auto launch_round = [&](uint32_t sub, cudaStream_t st) {
@@ -630,15 +561,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         WaveArgs w = a; w.sub = (int) sub;
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
             mark(0, st);
-#define LAUNCHZC(id, nt, hn) if (!any_kwaj && ctx->zip_variant == id) k_p1_mszip<nt, hn><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(ZipSharedC<nt, hn>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            ZIPC_VARIANTS(LAUNCHZC)
-#undef LAUNCHZC
-            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 1><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 1) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 2><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 2) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 3><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 3) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 4><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            if (!any_kwaj && ctx->zip_variant == ZIP_VARIANT_OPT1 + 4) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, false, 7><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
-            if (any_kwaj) k_p1_mszip<ZIPK_NT, ZIPK_HEADN, true><<<(f1 - f0 + ZIPK_NT - 1) / ZIPK_NT, ZIPK_NT, sizeof(ZipSharedC<ZIPK_NT, ZIPK_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            if (any_kwaj) k_p1_mszip<ZIP_NT, ZIP_HEADN, true><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
+            else k_p1_mszip<ZIP_NT, ZIP_HEADN><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_z, f0, f1, st);
             k_p2_ring<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1);
@@ -648,20 +572,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             mark(1, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
-#define LAUNCHC(id, nt, hn, lb, opt) if (!any_delta && ctx->lzx_variant == id) k_p1_lzx<nt, hn, false, lb, opt><<<(f1 - f0 + nt - 1) / nt, nt, sizeof(LzxSharedSel<nt, hn, lb>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
-            LZXC_VARIANTS(LAUNCHC)
-#undef LAUNCHC
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
+            else k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             mark(0, st);
-            if (ctx->qtm_variant == 1) k_p1_qtm<QTM_NT, 1><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 1>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            else if (ctx->qtm_variant == 2) k_p1_qtm<QTM_NT, 2><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 2>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            else if (ctx->qtm_variant == 3) k_p1_qtm<QTM_NT, 3><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 3>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            else if (ctx->qtm_variant == 4) k_p1_qtm<QTM_NT, 4><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 4>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            else if (ctx->qtm_variant == 7) k_p1_qtm<QTM_NT, 7><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT, 7>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            else
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_q, f0, f1, st); ctx->launches += 2; mark(1, st); }

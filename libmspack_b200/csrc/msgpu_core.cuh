@@ -139,13 +139,6 @@ MS_D int64_t ms_bitpos(const MsBits &b) { return (int64_t) b.ipos * 8 - b.bc; }
 MS_D void lsb_refill(MsBits &b) {                 /* afterwards bc >= 32 */
     if (b.bc < 32) { b.bb |= (uint64_t) b.nextw << b.bc; b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
 }
-/* the same without the end-of-input test and without a branch (callers: ZipLaneC's fast step with OPT bit 0; see lzx_refill_nocheck) */
-MS_D void lsb_refill_nocheck(MsBits &b) {
-    const bool need = b.bc < 32;
-    const uint64_t add = (uint64_t) b.nextw << (b.bc & 63);
-    b.bb |= need ? add : 0ull; b.bc += need ? 32 : 0; b.ipos += need ? 4 : 0;
-    if (need) b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.ipos);
-}
 MS_D uint32_t lsb_peek(const MsBits &b, int n) { return (uint32_t) b.bb & ((1u << n) - 1u); }
 MS_D void lsb_drop(MsBits &b, int n) { b.bb >>= n; b.bc -= n; }
 /* would the reference's ENSURE_BITS(n) at this position run past in_len + 2 bytes? */
@@ -170,14 +163,6 @@ MS_D void lsb_seek_byte(MsBits &b, int32_t bytepos) {
 MS_D uint32_t msb16le_swz(uint32_t x) { return (x << 16) | (x >> 16); }   /* two LE words -> 32 stream bits, first word on top */
 MS_D void lzx_refill(MsBits &b) {                 /* afterwards bc >= 32 */
     if (b.bc < 32) { b.bb |= (uint64_t) msb16le_swz(b.nextw) << (32 - b.bc); b.bc += 32; b.ipos += 4; b.nextw = ms_load32(b, b.ipos); }
-}
-/* the same without the end-of-input test and without a branch: for callers that know the next word lies inside an aligned
- * input (LzxLaneC's fast step, OPT bit 6) */
-MS_D void lzx_refill_nocheck(MsBits &b) {
-    const bool need = b.bc < 32;
-    const uint64_t add = (uint64_t) msb16le_swz(b.nextw) << ((32 - b.bc) & 63);
-    b.bb |= need ? add : 0ull; b.bc += need ? 32 : 0; b.ipos += need ? 4 : 0;
-    if (need) b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.ipos);
 }
 MS_D uint32_t msb_peek(const MsBits &b, int n) { return (uint32_t) (b.bb >> (64 - n)); }     /* 1 <= n <= 32 */
 MS_D void msb_drop(MsBits &b, int n) { b.bb <<= n; b.bc -= n; }
@@ -296,84 +281,12 @@ MS_D int ms_canon_build_h(LensFn lens, int nsyms, int ref_tablebits, BoT bo, uin
     return 0;
 }
 
-/* ms_canon_build_h for the experimental shapes (LzxLaneC OPT bit 8): both passes over the symbols fetch four code lengths before
- * they use them - the lengths live in lane-interleaved global scratch and every one of them is an L2 round trip that the plain
- * loops wait out one by one.  (A function of its own so that the measured kernels compile exactly as before.) */
-template <int ROOT, int NT, class LensFn, class HeadFn, class BoT>
-MS_D int ms_canon_build_h4(LensFn lens, int nsyms, int ref_tablebits, BoT bo, uint16_t *cnt, uint16_t *sorted,
-                          HeadFn put_head, uint16_t *lut, uint32_t limv[16])
-{
-#pragma unroll 1
-    for (int l = 0; l <= 16; l++) cnt[l * NT] = 0;
-    {
-        int s = 0;
-#pragma unroll 1
-        for (; s + 4 <= nsyms; s += 4) {
-            const uint32_t l0 = lens(s), l1 = lens(s + 1), l2 = lens(s + 2), l3 = lens(s + 3);
-            if (l0 >= 1 && l0 <= 16) cnt[l0 * NT]++;
-            if (l1 >= 1 && l1 <= 16) cnt[l1 * NT]++;
-            if (l2 >= 1 && l2 <= 16) cnt[l2 * NT]++;
-            if (l3 >= 1 && l3 <= 16) cnt[l3 * NT]++;
-        }
-#pragma unroll 1
-        for (; s < nsyms; s++) { uint32_t l = lens(s); if (l >= 1 && l <= 16) cnt[l * NT]++; }
-    }
-    uint32_t sum_short = 0, sum_all = 0;
-#pragma unroll 1
-    for (int l = 1; l <= 16; l++) { sum_all += (uint32_t) cnt[l * NT] << (16 - l); if (l <= ref_tablebits) sum_short = sum_all; }
-    int maxlen = 16;
-    if (sum_short > 65536u) return 1;
-    if (sum_short == 65536u) maxlen = ref_tablebits;
-    else if (sum_all != 65536u) return 1;
-    uint32_t lim = 0, off = 0;
-#pragma unroll
-    for (int l = 1; l <= 16; l++) {
-        uint32_t c = (l <= maxlen) ? cnt[l * NT] : 0;
-        bo.put(l, lim, off);
-        cnt[l * NT] = (uint16_t) off;                       /* running index of the next l-bit symbol */
-        lim += c << (16 - l); limv[l - 1] = lim; off += c;
-    }
-    if (ROOT > 0) {
-#pragma unroll 1
-        for (int e = 0; e < (1 << ROOT); e++) lut[e * NT] = 0;
-    }
-    auto place = [&](int s, int l) {
-        if (l < 1 || l > maxlen) return;
-        uint32_t k = cnt[l * NT]; cnt[l * NT] = (uint16_t) (k + 1);
-        sorted[k * MS_WARP] = (uint16_t) s;
-        put_head(k, (uint32_t) s);
-        if (ROOT > 0 && l <= ROOT) {
-            uint32_t code = bo.code_of(l, k);
-            uint32_t idx = code << (ROOT - l), n = 1u << (ROOT - l);
-            for (uint32_t j = 0; j < n; j++) lut[(idx + j) * NT] = (uint16_t) ((s << 4) | l);
-        }
-    };
-    int s = 0;
-#pragma unroll 1
-    for (; s + 4 <= nsyms; s += 4) {
-        const int l0 = (int) lens(s), l1 = (int) lens(s + 1), l2 = (int) lens(s + 2), l3 = (int) lens(s + 3);
-        place(s, l0); place(s + 1, l1); place(s + 2, l2); place(s + 3, l3);
-    }
-#pragma unroll 1
-    for (; s < nsyms; s++) place(s, (int) lens(s));
-    return 0;
-}
-
-
 template <int ROOT, int NT, class LensFn>
 MS_D int ms_canon_build(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
                         uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
 {
     return ms_canon_build_h<ROOT, NT>(lens, nsyms, ref_tablebits, MsBo32<NT>{ bo }, cnt, sorted,
                                       [=](uint32_t k, uint32_t s) { if (k < headn) head[k * NT] = (uint16_t) s; }, lut, limv);
-}
-
-template <int ROOT, int NT, class LensFn>
-MS_D int ms_canon_build4(LensFn lens, int nsyms, int ref_tablebits, uint32_t *bo, uint16_t *cnt, uint16_t *sorted,
-                         uint16_t *head, uint32_t headn, uint16_t *lut, uint32_t limv[16])
-{
-    return ms_canon_build_h4<ROOT, NT>(lens, nsyms, ref_tablebits, MsBo32<NT>{ bo }, cnt, sorted,
-                                       [=](uint32_t k, uint32_t s) { if (k < headn) head[k * NT] = (uint16_t) s; }, lut, limv);
 }
 
 /* code length from limits in registers: lim[j] = limit[j + 1], non-decreasing.  len = 1 + #{ j : lim[j] <= v16 },
@@ -470,17 +383,6 @@ MS_D void emit_match(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
     if (e.nrec & 1u) MS_STORE4(e.rec + e.nrec - 1, e.pa, e.pb, a, b);
     else { e.pa = a; e.pb = b; }
     e.nrec++;
-}
-/* experimental (LzxLaneC OPT bit 3): every record leaves by itself as one 8-byte store - no pairing logic in the step, twice the
- * store instructions.  Same array contents; emit_end_single writes the sentinel. */
-MS_D void emit_match_single(MsEmit &e, uint32_t pos, uint32_t len, uint32_t off) {
-    MsRec r; r.a = pos; r.b = off | (len << 22);
-    e.rec[e.nrec] = r;
-    e.nrec++;
-}
-MS_D void emit_end_single(MsEmit &e, uint32_t frame_size) {
-    emit_flush_literals(e);
-    MsRec r; r.a = frame_size; r.b = 0; e.rec[e.nrec] = r;
 }
 /* LZX DELTA: offsets up to 2^25 (bits 22.. of the offset travel in a's upper half) and lengths up to a whole frame (cut into
  * pieces of at most 1023 bytes with the same offset, which copies the same bytes as the one long match) */

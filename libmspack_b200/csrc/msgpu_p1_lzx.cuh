@@ -45,24 +45,12 @@ struct LzxSharedC {
     uint16_t cnt[17 * NT];
 };
 
-/* The packed layout (H8LB = 5 or 4, the LENGTH tree's LUT bits).  Measured on the headline batch the main tree of a 32 KiB text
- * frame has ~250 coded symbols with codes of 6-8 bits: a 72-symbol head misses for 29 % of the symbols, i.e. in every step some
- * lane of the warp goes to L2 for its symbol and the whole warp waits.  A main symbol is < 656 (window_bits <= 21): 10 bits, kept
- * as a byte plus two bits (16 per word), so ~1.25 bytes per head entry instead of 2; the aligned-offset tree (8 symbols, codes
- * <= 7 bits) shrinks from 100 bytes to 4 words, and the builder's counters share the LENGTH limits' array (never live together).
- * Same shared memory per lane, 208-240 head entries instead of 72. */
-template <int NT, int HEADN, int LB>
-struct LzxSharedP {
-    uint32_t mbo[17 * NT];                /* main tree: limit[l-1] >> 1 | offs[l] << 16 */
-    uint32_t lbo[17 * NT];                /* LENGTH tree; hosts the pretree while code lengths are being read */
-    uint32_t atree[4 * NT];               /* aligned-offset tree: limits 1-4 | limits 5-7 | offs (4 bits each) | symbols (3 bits each) */
-    uint32_t mhi[(HEADN / 16) * NT];      /* bits 8-9 of the head symbols, 16 per word */
-    uint16_t llim[17 * NT];               /* LENGTH / pretree limits >> 1; while a tree is being built: the builder's counters */
-    uint16_t llut[(1 << LB) * NT];        /* LB-bit LUT of the LENGTH tree */
-    static constexpr int ROW = HEADN > 224 ? NT : NT + 4;      /* rows of NT + 4 bytes spread the banks (where the space allows) */
-    uint8_t mlo[HEADN * ROW];             /* low bytes of the head symbols */
-};
-/* The packed layout with 16-bit per-length bases (MsBoK) instead of one word per length: 64 bytes less for the two big trees,
+/* The packed layout.  Measured on the headline batch the main tree of a 32 KiB text frame has ~250 coded symbols with codes of 6-8
+ * bits: a 72-symbol head misses for 29 % of the symbols, i.e. in every step some lane of the warp goes to L2 for its symbol and the
+ * whole warp waits.  A main symbol is < 656 (window_bits <= 21): 10 bits, kept as a byte plus two bits (16 per word), so ~1.25 bytes
+ * per head entry instead of 2; the aligned-offset tree (8 symbols, codes <= 7 bits) shrinks from 100 bytes to 4 words, and the
+ * builder's counters share the LENGTH limits' array (never live together). */
+/* 16-bit per-length bases (MsBoK) instead of one word per length: 64 bytes less for the two big trees,
  * spent on a full 256-entry main head and a 40-entry byte head of the LENGTH tree's symbols (the LENGTH symbols the LUT
  * misses were the other L2 round trip the profile showed: ~10 % of the steps had a lane there).  H8LB = 100 + LUT bits. */
 #define LZX_LHEAD 40
@@ -78,26 +66,10 @@ struct LzxSharedQ {
     static constexpr int ROW = NT;
     uint8_t mlo[HEADN * ROW];
 };
-template <int NT, int HEADN, int H8LB> struct LzxSharedSel { typedef typename std::conditional<(H8LB >= 100), LzxSharedQ<NT, HEADN, H8LB - 100>, LzxSharedP<NT, HEADN, H8LB>>::type type; };
+template <int NT, int HEADN, int H8LB> struct LzxSharedSel { static_assert(H8LB >= 100, "H8LB = 100 + LUT bits (LzxSharedQ) or 0 (LzxSharedC)"); typedef LzxSharedQ<NT, HEADN, H8LB - 100> type; };
 template <int NT, int HEADN> struct LzxSharedSel<NT, HEADN, 0> { typedef LzxSharedC<NT, HEADN> type; };
 
-/* OPT (experimental shapes, none of them a default until measured on the B200 - tools/variant_bench.py):
- *   bit 0  the refill in front of a match's offset bits only when the bits at hand do not cover them (extra + 4 <= 21 bits): with
- *          32 lanes per warp the unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them
- *   bit 2  extra_bits[] / position_base[] from a 64-entry table in shared memory (one per CTA, lzx_slot_entry) instead of the
- *          closed forms (~20 dependent integer instructions on every match with a new offset); window_bits <= 21 only
- *   bit 3  match records stored one by one (8 bytes each) instead of in pairs
- *   bit 5  (p1_run) the careful step - the one with the end-of-input checks - runs in a loop of its own, entered only while some lane
- *          of the warp is within 24 bytes of its input's end: the hot loop then holds ONE instantiation of the step instead of two
- *          joined at its tail (48 of the ~245 warp-instructions per step are register moves at control-flow joins)
- *   bit 4  literals stored one byte at a time instead of gathered per aligned word (4 instructions instead of ~20 per literal,
- *          up to four times the literal stores) */
-MS_D uint32_t lzx_slot_entry(uint32_t slot) {          /* extra | (position_base - 2) << 5, lzxd.c:199-255 */
-    const uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
-    const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
-    return extra | ((pbase - 2u) << 5);
-}
-template <int NT, int HEADN, bool DELTA = false, int H8LB = 0, int OPT = 0>
+template <int NT, int HEADN, bool DELTA = false, int H8LB = 0>
 struct LzxLaneC {
     typedef typename LzxSharedSel<NT, HEADN, H8LB>::type Shared;
     static constexpr bool H8 = H8LB != 0;
@@ -106,7 +78,6 @@ struct LzxLaneC {
     typedef typename std::conditional<QL, MsBoK<NT>, MsBo32<NT>>::type Bo;
     MsBits b;
     uint32_t *atree, *mhi; uint8_t *mlo, *lhead;  /* packed layouts only */
-    const uint32_t *slot_tab;             /* OPT bit 2: lzx_slot_entry(0..63) */
     uint32_t is_delta, ref_len;           /* DELTA only: this unit is an LZX DELTA stream; bytes of reference data in front of it */
     Bo mbo, lbo; uint32_t *abo;
     uint16_t *mhead, *llim, *alim, *llut, *cnt;
@@ -218,10 +189,6 @@ struct LzxLaneC {
         for (int j = 0; j < 15; j++) llim[j * NT] = (uint16_t) (lv[j] >> 1);
 #pragma unroll 1
         for (uint32_t x = first; x < last;) {
-            /* OPT bit 8: the previous length of symbol x is fetched BEFORE the pretree symbol is decoded (an L2 round trip that the
-             * decode then covers); used by the plain-delta and the run-of-deltas codes below */
-            int prevl = 0;
-            if constexpr ((OPT & 256) != 0) prevl = (int) lens[x * 32];
             lzx_refill(b);
             int z = (int) sym_smem(llim, lbo, pa.sorted);
             if (b.err) return b.err;
@@ -232,11 +199,10 @@ struct LzxLaneC {
                 lzx_refill(b);
                 z = (int) sym_smem(llim, lbo, pa.sorted);
                 if (b.err) return b.err;
-                if constexpr ((OPT & 256) != 0) z = prevl - z; else
                 z = (int) lens[x * 32] - z; if (z < 0) z += 17;
                 while (y--) { lens[x * 32] = (uint8_t) z; x++; }
             }
-            else { if constexpr ((OPT & 256) != 0) z = prevl - z; else z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
+            else { z = (int) lens[x * 32] - z; if (z < 0) z += 17; lens[x * 32] = (uint8_t) z; x++; }
         }
         return 0;
     }
@@ -247,13 +213,6 @@ struct LzxLaneC {
 #pragma unroll 1
             for (int w = 0; w < HEADN / 16; w++) mhi[w * NT] = 0;
             uint8_t *lo = mlo; uint32_t *hi = mhi;
-            if constexpr ((OPT & 256) != 0) {
-            if (ms_canon_build_h4<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
-                                        [=](uint32_t k, uint32_t sym) {
-                                            if (k < (uint32_t) HEADN) { lo[k * Shared::ROW] = (uint8_t) sym; hi[(k >> 4) * NT] |= (sym >> 8) << ((k & 15u) * 2u); }
-                                        }, (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
-            }
-            else
             if (ms_canon_build_h<0, NT>([&](int s) { return (uint32_t) l[s * 32]; }, (int) nsyms_eff, 12, mbo, cnt, ma.sorted,
                                         [=](uint32_t k, uint32_t sym) {
                                             if (k < (uint32_t) HEADN) { lo[k * Shared::ROW] = (uint8_t) sym; hi[(k >> 4) * NT] |= (sym >> 8) << ((k & 15u) * 2u); }
@@ -273,11 +232,7 @@ struct LzxLaneC {
         length_empty = 0;
         uint8_t *lh = lhead;
         int rc;
-        if constexpr ((OPT & 256) != 0)
-            rc = ms_canon_build_h4<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
-                                       [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv);
-        else
-            rc = ms_canon_build_h<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
+        rc = ms_canon_build_h<LUTB, NT>([&](int s) { return (uint32_t) l[s * 32]; }, LZX_LEN_SYMS, 12, lbo, cnt, la.sorted,
                                        [=](uint32_t k, uint32_t sym) { if (QL && k < (uint32_t) LZX_LHEAD) lh[k * NT] = (uint8_t) sym; }, llut, lv);
         if (rc) {
 #pragma unroll 1
@@ -403,10 +358,6 @@ struct LzxLaneC {
         bytes_todo -= this_run; block_remaining -= (uint32_t) this_run;
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
-            if constexpr ((OPT & 16) != 0) {       /* byte-wise literal stores: nothing may go through the word gatherer */
-#pragma unroll 1
-                while (this_run > 0) { em.out[q] = (uint8_t) raw_byte(); q++; this_run--; }
-            }
             if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
                 emit_raw(em, q, b.in, bytepos, (uint32_t) this_run);
                 bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
@@ -422,7 +373,7 @@ struct LzxLaneC {
     MS_M void frame_end() {
         /* :696-697 re-align; after raw bytes the reference's bit buffer is empty and nothing happens */
         if (!bytemode && (b.bc & 15)) { lzx_refill(b); lzx_check(b, 16); if (b.err) { fail(b.err); return; } msb_drop(b, b.bc & 15); }
-        if constexpr ((OPT & 8) != 0 && !DELTA) emit_end_single(em, frame_size); else emit_end(em, frame_size);
+        emit_end(em, frame_size);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = frame_size; fi.g0 = frame_start_pos; fi.valid = 1;
         finfo[f] = fi;
         e8info[frame] = (intel_started && intel_filesize && frame < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 */
@@ -477,38 +428,19 @@ struct LzxLaneC {
     MS_M void step() {
         /* `careful` = the unit's input ends within the next 24 bytes: only then can any of this step's reads (at most
          * two 4-byte refills) trip the reference's end-of-input rule, so only then are the exact checks compiled in */
-        if constexpr ((OPT & 64) != 0) { if (MS_UNLIKELY(near_end())) step_plain<true>(); else step_plain<false>(); }
-        else
         if (MS_UNLIKELY(b.ipos + (DELTA ? 32 : 24) > b.in_len)) step_plain<true>(); else step_plain<false>();     /* DELTA: one more refill */
     }
-    /* (OPT bit 6: the fast step loads its words unchecked, so a unit whose input is not 4-byte aligned - fast_end is then a large
-     * negative number - always takes the careful step) */
-    MS_M bool near_end() const { if constexpr ((OPT & 64) != 0) return b.ipos + (DELTA ? 28 : 20) > b.fast_end; else return b.ipos + (DELTA ? 32 : 24) > b.in_len; }
-    template <bool careful> MS_M void refill() { if constexpr (!careful && (OPT & 64) != 0) lzx_refill_nocheck(b); else lzx_refill(b); }
-    MS_M void step_fast() { step_plain<false>(); }
-    MS_M void step_careful() { step_plain<true>(); }
     /* the hot step (lzxd.c:538-651): one literal, or one match with its length / offset fields */
     template <bool careful> MS_M void step_plain() {
-        /* OPT bit 7 (fast step only): no exits in the middle of the step - an error is remembered and raised at the end, where every
-         * variable already sits where the loop expects it (the early exits cost ~20 register moves per step at the join) */
-        constexpr bool LATE = !careful && (OPT & 128) != 0;
-        uint32_t bad = 0;
-        refill<careful>();
+        lzx_refill(b);
         uint32_t sym = main_sym(careful);
-        if (sym < 256) {
-            if constexpr ((OPT & 16) != 0) em.out[q] = (uint8_t) sym;          /* (q < frame_size by construction) */
-            else emit_literal(em, q, sym);
-            q++; this_run--;
-        }
+        if (sym < 256) { emit_literal(em, q, sym); q++; this_run--; }
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
             if (ml == 7) {
-                if constexpr (LATE) { if (MS_UNLIKELY(length_empty)) bad = (uint32_t) (b.err ? b.err : MS_EDECRUNCH); else ml += length_sym(careful); }
-                else {
                 if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
                 ml += length_sym(careful);
-                }
             }
             ml += 2;
             if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
@@ -518,15 +450,13 @@ struct LzxLaneC {
             }
             else {
                 /* extra_bits[] / position_base[] (lzxd.c:199-255) in closed form */
-                uint32_t extra;
-                if constexpr ((OPT & 4) != 0) { const uint32_t e = slot_tab[slot & 63u]; extra = e & 31u; off = e >> 5; }
-                else {
-                    extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
-                    const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
-                    off = pbase - 2;
-                }
-                if constexpr ((OPT & 1) != 0) { if (b.bc < (int) extra + 4) refill<careful>(); }      /* (still below 32: the buffer has room) */
-                else refill<careful>();
+                const uint32_t extra = slot < 4 ? 0 : ((slot >> 1) - 1 < 17 ? (slot >> 1) - 1 : 17);
+                const uint32_t pbase = slot < 4 ? slot : (slot < 38 ? (2u + (slot & 1)) << ((slot >> 1) - 1) : (slot - 34) << 17);
+                off = pbase - 2;
+                /* the refill in front of the offset bits only when the bits at hand do not cover them (extra + 4 <= 21 bits): with 32
+                 * lanes per warp an unconditional "below 32 bits" refill body runs in almost every step, this one in ~15 % of them
+                 * (measured: P1 9.02 -> 8.52 ms, profiles/r2_variants.txt shape 31) */
+                if (b.bc < (int) extra + 4) lzx_refill(b);
                 if (block_type == 2 && extra >= 3) {
                     if (extra > 3) { if (careful) lzx_check(b, (int) extra - 3); off += msb_peek(b, (int) extra - 3) << 3; msb_drop(b, (int) extra - 3); }
                     if constexpr (H8) off += aligned_sym(careful); else off += sym_smem(alim, MsBo32<NT>{ abo }, aa.sorted, careful);
@@ -535,7 +465,7 @@ struct LzxLaneC {
                 R2 = R1; R1 = R0; R0 = off;
             }
             if (DELTA && is_delta && ml == 257) {                    /* lzxd.c:589-611: the longest length announces more */
-                refill<careful>();
+                lzx_refill(b);
                 if (careful) lzx_check(b, 3);
                 const uint32_t p3 = msb_peek(b, 3);
                 const int pre = p3 < 4 ? 1 : (p3 < 6 ? 2 : 3), nb = p3 < 4 ? 8 : (p3 < 6 ? 10 : (p3 == 6 ? 12 : 15));
@@ -545,12 +475,9 @@ struct LzxLaneC {
                 msb_drop(b, nb);
             }
             if (careful && b.err) { fail(b.err); return; }
-            if constexpr (LATE) { if (!bad) bad = resolve_match_late(ml, off); }
-            else
             if (!resolve_match(ml, off)) return;
         }
         if (careful && b.err) { fail(b.err); return; }
-        if constexpr (LATE) { if (MS_UNLIKELY(bad)) { fail((int) bad); return; } }
         if (this_run <= 0) phase = PH_BLOCK;
     }
     /* lzxd.c:613-634 restated (window_posn = G mod window_size, lzx->offset = frame start).  Fast path: a source
@@ -570,31 +497,9 @@ struct LzxLaneC {
         }
         if (MS_UNLIKELY((int32_t) ml > this_run)) { fail(MS_EDECRUNCH); return false; }   /* :678-693 every overrun ends in an error */
         if (DELTA) emit_match_wide(em, q, ml, eff);
-        else if constexpr ((OPT & 8) != 0) emit_match_single(em, q, ml, eff);
         else emit_match(em, q, ml, eff);
         q += ml; this_run -= (int32_t) ml;
         return true;
-    }
-    /* the same for OPT bit 7: returns the error instead of raising it, and emits nothing when there is one */
-    MS_M uint32_t resolve_match_late(uint32_t ml, uint32_t off) {
-        uint32_t G = frame_start_pos + q, eff = off; bool bad = false;
-        if (MS_UNLIKELY(off - 1u >= G || G + ml > window_size)) {
-            uint32_t wpr = G & (window_size - 1);
-            bad = (wpr + ml > window_size);
-            if (off > wpr) {
-                bad = bad || (off > frame_start_pos && (!DELTA || off - wpr > ref_len)) || (off - wpr > window_size);
-                if (off > window_size) eff = off - window_size;
-            }
-            if (eff == 0) eff = window_size;
-        }
-        bad = bad || (int32_t) ml > this_run;
-        if (!bad) {
-            if (DELTA) emit_match_wide(em, q, ml, eff);
-            else if constexpr ((OPT & 8) != 0) emit_match_single(em, q, ml, eff);
-            else emit_match(em, q, ml, eff);
-        }
-        q += ml; this_run -= (int32_t) ml;
-        return bad ? (uint32_t) MS_EDECRUNCH : 0u;
     }
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int32_t *e8, int nframes) {

@@ -36,8 +36,13 @@ struct ZipSharedC {
 
 /* SPECIAL = the instantiation that also understands the two special kinds of MSZIP unit: MSGPU_FLAG_MSZIP_KWAJ
  * (mszipd_decompress_kwaj, mszipd.c:462-495) and MSGPU_FLAG_MSZIP_REPAIR (mszipd_init(repair_mode = 1), mszipd.c:420-433) */
-template <int NT, int HEADN, bool SPECIAL = false, int OPT = 0>      /* OPT (experimental): bit 0 unchecked branch-free refill in the fast step, bit 1 prefetching table build, bit 2 byte-wise literal stores */
+template <int NT, int HEADN, bool SPECIAL = false>
 struct ZipLaneC {
+    /* BYTEWISE (the plain instantiation): literal bytes go to the output one by one instead of through the word gatherer - ~30
+     * instructions less per literal step for the lanes that have one; measured on the B200 (profiles/r2_variants.txt, shape 18):
+     * P1 8.65 -> 7.89 ms on the 32 768-unit text batch.  Every literal path of the lane must then do the same, because a gathered
+     * word is stored whole; the KWAJ / repair instantiation keeps the gatherer (its overflow frames write to a plane). */
+    static constexpr bool BYTEWISE = !SPECIAL;
     /* Repair mode.  A block the reference gives up is zero-filled to 32 KiB and decoding goes on - with the bit state of its last
      * STORE_BITS (mszipd.c:149 / :223 / :419), which is stale in two ways (see oracle/port/mspack_port.c zip_repair_restart, pinned
      * against the reference): the buffered bits are those of the STORE, and the byte pointer is the STORE's only if read_input has
@@ -170,11 +175,6 @@ struct ZipLaneC {
         }
         /* :139-146: distance lengths follow the literal lengths; both are zero-extended */
         uint8_t *l = lens;
-        if constexpr ((OPT & 2) != 0) {      /* (experimental: four code lengths fetched at a time, ms_canon_build_h4) */
-            if (ms_canon_build4<0, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
-                                       (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
-        }
-        else
         if (ms_canon_build<0, NT>([&](int s) { return (uint32_t) (s < (int) lit_codes ? l[s * 32] : 0); }, 288, 9, lbo, cnt, la.sorted, lhead, HEADN,
                                   (uint16_t *) nullptr, lv)) return MS_EDECRUNCH;
 #pragma unroll
@@ -263,7 +263,7 @@ struct ZipLaneC {
             {   /* bulk copy when the block's bytes all lie inside the input and the frame (the common case) */
                 int32_t bp = lsb_bytepos(b);
                 if (len && q + len <= MS_FRAME && bp + (int32_t) len <= b.in_len) {
-                    if constexpr ((OPT & 4) != 0) { for (uint32_t k = 0; k < len; k++) lit_bytewise(q + k, b.in[bp + (int32_t) k]); }
+                    if constexpr (BYTEWISE) { for (uint32_t k = 0; k < len; k++) lit_bytewise(q + k, b.in[bp + (int32_t) k]); }
                     else
                     emit_raw(em, q, b.in, bp, len);
                     q += len; lsb_seek_byte(b, bp + (int32_t) len);
@@ -277,7 +277,7 @@ struct ZipLaneC {
                 uint32_t v = rd(8);
                 if (b.err) { fail(b.err); return; }
                 if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
-                if constexpr ((OPT & 4) != 0) lit_bytewise(q, v); else
+                if constexpr (BYTEWISE) lit_bytewise(q, v); else
                 emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), v);
                 if (++q >= 2 * MS_FRAME) { fail(MS_EDECRUNCH); return; }   /* second FLUSH_IF_NEEDED: bytes_output > 32 KiB (:323-333) */
             }
@@ -401,22 +401,16 @@ struct ZipLaneC {
      * `careful` = the unit's input ends within the next 24 bytes: only then can one of this step's reads (two 4-byte refills)
      * trip the reference's end-of-input rule, so only then are the exact checks compiled in. */
     MS_M void step() {
-        if constexpr ((OPT & 1) != 0) { if (MS_UNLIKELY(b.ipos + 20 > b.fast_end) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>(); }    /* (fast_end < 0: input not 4-byte aligned) */
-        else
         if (MS_UNLIKELY(b.ipos + 24 > b.in_len) || (SPECIAL && repairing())) step_t<true>(); else step_t<false>();
     }
-    template <bool careful> MS_M void refill() { if constexpr (!careful && (OPT & 1) != 0) lsb_refill_nocheck(b); else lsb_refill(b); }
-    /* OPT bit 2 (experimental, plain instantiation only): literal bytes go to the output one by one instead of through the word
-     * gatherer (~30 instructions per literal step for the lanes that have one); every literal path of the lane must then do the same,
-     * because a gathered word is stored whole */
-    static_assert(!(SPECIAL && (OPT & 4) != 0), "byte-wise literals are not implemented for the KWAJ / repair instantiation");
+    template <bool careful> MS_M void refill() { lsb_refill(b); }
     MS_M void lit_bytewise(uint32_t qq, uint32_t v) { if (qq < em.limit) em.out[qq] = (uint8_t) v; }
     template <bool careful> MS_M void step_t() {
         refill<careful>();
         uint32_t sym = litlen_sym<careful>();
         if (sym < 256) {
             if (SPECIAL && q >= MS_FRAME && !qbase && repairing()) { start_overflow(); if (done) return; }
-            if constexpr ((OPT & 4) != 0) lit_bytewise(q, sym); else
+            if constexpr (BYTEWISE) lit_bytewise(q, sym); else
             emit_literal_checked(em, q - (SPECIAL ? qbase : 0u), sym); q++;
         }
         else if (sym == 256) phase = last_block ? PH_END : PH_BLOCK;

@@ -26,59 +26,37 @@
 #define QM6L  373
 #define QTM_SAVE_BYTES 1280   /* per-slot save area: 401 u16 + 401 u8 + 9 u8 + 9 u16, padded */
 
-/* OPT bit 0 (experimental, MSGPU_QTM_VARIANT=1 or 3; not a default until measured): two-level scan.  The 32 lanes of a warp run
- * GET_SYMBOL in lockstep, so a scan costs the warp as many rounds as its SLOWEST lane needs: measured on the text workload, 11.2
- * four-entry rounds per symbol for the warp against 3.0 for a lane alone.  With the sum of every 8 differences kept next to them
- * (grp[]: 51 sums, +102 bytes per lane) the scan first walks at most 8 group sums, then at most 8 entries: 3.4 rounds per
- * symbol for the warp on the same data.  The sums follow every change of g[] (symbol update, rescale, re-sort) and are rebuilt
- * from g[] when a unit's state is reloaded. */
+/* Two-level scan.  The 32 lanes of a warp run GET_SYMBOL in lockstep, so a scan costs the warp as many rounds as its SLOWEST lane
+ * needs: measured on the text workload, 11.2 four-entry rounds per symbol for the warp against 3.0 for a lane alone.  With the sum of
+ * every 8 differences kept next to them (grp[]: 51 sums, +102 bytes per lane) the scan first walks at most 8 group sums, then at most
+ * 8 entries: 3.4 rounds per symbol for the warp on the same data.  The sums follow every change of g[] (symbol update, rescale,
+ * re-sort) and are rebuilt from g[] when a unit's state is reloaded.  Measured on the B200 together with the loop-free
+ * renormalisation below (profiles/r2_variants.txt, Quantum shape 3): P1 77.3 -> 56.0 ms for 16 384 units. */
 #define QTM_GRP 56            /* 1 + 4 x 8 + 3 + 5 + 6 + 4 = 51 group sums, padded for the four-wide reads */
-/* OPT bit 2 (experimental): the three 32-bit divisions of GET_SYMBOL through a float reciprocal.  Quotients here are small (a
- * frequency below 2^12, or a 16-bit interval bound), so q = trunc(float(n) * (1 / float(d))) is off by at most one - relative error
- * of the product < 1.5 * 2^-22 (approximate reciprocal included), times a quotient < 2^20, is < 0.4 - and one remainder test each
- * way makes it exact; a quotient estimate of 2^20 or more (only a damaged stream gets there) takes the plain division. */
-MS_D float ms_rcpf(uint32_t d) {
-#if defined(__CUDA_ARCH__)
-    return __fdividef(1.0f, (float) d);
-#else
-    return 1.0f / (float) d;
-#endif
-}
-MS_D uint32_t ms_div_rcp(uint32_t n, uint32_t d, float rd) {
-    const float qf = (float) n * rd;
-    if (MS_UNLIKELY(!(qf < 1048576.0f))) return n / d;
-    uint32_t q = (uint32_t) qf;
-    const int32_t r = (int32_t) (n - q * d);
-    if (r < 0) q--;
-    else if ((uint32_t) r >= d) q++;
-    return q;
-}
-template <int NT, bool ON> struct QtmGroups { uint16_t grp[QTM_GRP * NT]; };
-template <int NT> struct QtmGroups<NT, false> { };
-template <int NT, int OPT = 0>
-struct QtmShared : QtmGroups<NT, (OPT & 1) != 0> {
+template <int NT>
+struct QtmShared {
+    uint16_t grp[QTM_GRP * NT];
     uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
     uint16_t tot[9 * NT];             /* T = cum[0] per model */
     uint8_t  sym[QTM_ENT * NT];
     uint8_t  shl[9 * NT];
 };
 
-template <int NT, int OPT = 0>
+template <int NT>
 struct QtmLane {
-    static constexpr bool GRP = (OPT & 1) != 0;
     MsBits b;
     uint16_t *cum, *tot; uint8_t *sym, *shl;
     uint32_t H, L, C;                 /* 16-bit values */
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
 
-    MS_M void bind(QtmShared<NT, OPT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; if constexpr (GRP) grp = sh->grp + tid; else grp = nullptr; }
+    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; grp = sh->grp + tid; }
 
     MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
         shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
 #pragma unroll 1
         for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
-        if constexpr (GRP) regroup(base, midx, len);
+        regroup(base, midx, len);
     }
 
     /* READ_BYTES bookkeeping: two more bytes fetched; fails past in_len + 2 (readbits.h:192-214) */
@@ -90,25 +68,15 @@ struct QtmLane {
             /* :130-136 on cumulative values: cum[i] >>= 1; if (cum[i] <= cum[i+1]) cum[i] = cum[i+1] + 1 */
             shl[midx * NT] = (uint8_t) s;
             uint32_t old = 0, nn = 0;
-            if constexpr (GRP) {                 /* the same loop, with the group sums rebuilt on the way down */
-                const int gb = grp_base(midx);
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int i = entries - 1; i >= 0; i--) {
-                    old += cum[(base + i) * NT];
-                    uint32_t c = old >> 1;
-                    if (c <= nn) c = nn + 1;
-                    cum[(base + i) * NT] = (uint16_t) (c - nn); acc += c - nn; nn = c;
-                    if ((i & 7) == 0) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
-                }
-            }
-            else
+            const int gb = grp_base(midx);       /* (the group sums are rebuilt on the way down) */
+            uint32_t acc = 0;
 #pragma unroll 1
             for (int i = entries - 1; i >= 0; i--) {
                 old += cum[(base + i) * NT];                               /* the reference's cum[i] before the rescale */
                 uint32_t c = old >> 1;
                 if (c <= nn) c = nn + 1;
-                cum[(base + i) * NT] = (uint16_t) (c - nn); nn = c;
+                cum[(base + i) * NT] = (uint16_t) (c - nn); acc += c - nn; nn = c;
+                if ((i & 7) == 0) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
             }
             tot[midx * NT] = (uint16_t) nn;
         }
@@ -138,7 +106,7 @@ struct QtmLane {
 #pragma unroll 1
             for (int i = 0; i < entries; i++) T += cum[(base + i) * NT];   /* :162-164 back to cumulative: T = cum[0] */
             tot[midx * NT] = (uint16_t) T;
-            if constexpr (GRP) regroup(base, midx, entries);
+            regroup(base, midx, entries);
         }
     }
 
@@ -147,15 +115,14 @@ struct QtmLane {
         uint32_t range = ((H - L) & 0xFFFFu) + 1u;
         uint32_t c0 = tot[midx * NT];
         uint32_t symf;
-        if constexpr ((OPT & 4) != 0) symf = ms_div_rcp((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1), range, ms_rcpf(range)) & 0xFFFFu;
-        else symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
+        symf = ((uint32_t) ((int32_t) (C - L + 1) * (int32_t) c0 - 1) / range) & 0xFFFFu;
         /* first j with cum[j+1] <= symf, or the last entry (cum[j+1] = cum[j] - g[j]).  Four entries per round: the four
          * shared-memory loads are independent, so a round costs one load latency instead of four (the kernel is latency
          * bound: 5 warps per SM).  Entries past the model's end may be read (they lie inside the shared arrays) but are
          * never selected. */
         uint32_t prev = c0, cur, gj; int j = 0;
         uint32_t sg = 0; int gsel = 0;
-        if constexpr (GRP) {
+        {
             /* level 1: the first group whose END (cum[8 (k+1)]) is <= symf, or the last group; prev becomes cum at its start */
             const int gb = grp_base(midx), ng = (entries + 7) >> 3;
             int gi = 0;
@@ -184,22 +151,15 @@ struct QtmLane {
         uint32_t s = sym[(base + j) * NT];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
         uint32_t Hn, Ln;
-        if constexpr ((OPT & 4) != 0) {
-            const float rc = ms_rcpf(c0);
-            Hn = (L + ms_div_rcp(prev * range, c0, rc) - 1) & 0xFFFFu;
-            Ln = (L + ms_div_rcp(cur * range, c0, rc)) & 0xFFFFu;
-        }
-        else {
         Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
         Ln = (L + (cur * range) / c0) & 0xFFFFu;
-        }
         H = Hn; L = Ln;
         cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
-        if constexpr (GRP) grp[gsel * NT] = (uint16_t) (sg + 8);
+        grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
         if (c0 > 3800) update_model(base, midx, entries);
-        if constexpr ((OPT & 2) != 0) {
-            /* OPT bit 1 (experimental): the renormalisation without a loop.  The reference's loop (:109-122) first shifts out the
+        {
+            /* The renormalisation without a loop.  The reference's loop (:109-122) first shifts out the
              * leading bits L and H share, then - the top bits now being 0 / 1 - the run of "underflow" positions right below
              * (L bit 1, H bit 0), and stops; the order cannot repeat because an underflow shift leaves the top bits at 0 / 1.  So:
              * one shift by the count of equal leading bits, one by the length of the underflow run (m shifts of C ^= 0x4000 flip,
@@ -224,24 +184,6 @@ struct QtmLane {
                 C = (((C << m) ^ 0x8000u) | msb_peek(b, m)) & 0xFFFFu; msb_drop(b, m);
             }
             return s;
-        }
-        else {
-        /* :109-122 renormalise: all leading equal bits of L and H leave at once; the underflow case goes bit by bit */
-#pragma unroll 1
-        for (;;) {
-            uint32_t x = (L ^ H) & 0xFFFFu; int n;
-            if (x & 0x8000u) {
-                if ((L & 0x4000u) && !(H & 0x4000u)) { C ^= 0x4000u; L &= 0x3FFFu; H |= 0x4000u; n = 1; }
-                else break;
-            }
-            else n = x ? MS_CLZ(x << 16) : 16;
-            L = (L << n) & 0xFFFFu; H = ((H << n) | ((1u << n) - 1u)) & 0xFFFFu;
-            while (bl < n) fetch2();                           /* ENSURE_BITS(1) per shifted bit */
-            bl -= n;
-            if (b.bc < n) qtm_refill(b);
-            C = ((C << n) | msb_peek(b, n)) & 0xFFFFu; msb_drop(b, n);
-        }
-        return s;
         }
     }
 
@@ -389,10 +331,8 @@ struct QtmLane {
                 for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; sym[i * NT] = save[QTM_ENT * 2 + i]; }
 #pragma unroll 1
                 for (int i = 0; i < 9; i++) { shl[i * NT] = save[QTM_ENT * 3 + i]; tot[i * NT] = reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i]; }
-                if constexpr (GRP) {
-                    regroup(QM0, 0, 64); regroup(QM1, 1, 64); regroup(QM2, 2, 64); regroup(QM3, 3, 64);
-                    regroup(QM4, 4, ent4); regroup(QM5, 5, ent5); regroup(QM6, 6, ent6); regroup(QM6L, 7, 27); regroup(QM7, 8, 7);
-                }
+                regroup(QM0, 0, 64); regroup(QM1, 1, 64); regroup(QM2, 2, 64); regroup(QM3, 3, 64);
+                regroup(QM4, 4, ent4); regroup(QM5, 5, ent5); regroup(QM6, 6, ent6); regroup(QM6L, 7, 27); regroup(QM7, 8, 7);
             }
         }
         phase = done ? PH_IDLE : PH_FRAME;

@@ -130,58 +130,6 @@ MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa
     }
 }
 
-/* ---- experimental pass A (PA = 1; not a default until measured on the B200): byte-parallel instead of record-parallel --------
- * The record-parallel pass above gives every lane one record and lets it write the descriptors that record covers: the trip
- * count is the longest match among the warp's 32 records (profile: 12.7 of 32 threads active in that loop).  Here every lane
- * builds the descriptors of ITS OWN 16 positions, always 16 trips:
- *   1. the record in effect at the lane's first position: binary search of the window (positions do not decrease);
- *   2. lanes zero their 16 slots, then the records that START inside the chunk drop their b word (off | len << 22, never 0)
- *      into the slot of their start position;
- *   3. each lane walks its 16 slots: a marker switches to that record; while a record lasts the descriptor is
- *      (record start - off) + fold, fold counting up and wrapping at `off` (only overlapping matches ever wrap - the same
- *      folding as p2_desc); otherwise "literal in place".
- * Returns the window index of the record in effect at the lane's first position (-1: none); lane 0's is the next r_lo. */
-MS_D int p2_pass_a2_search(uint32_t q0, const uint32_t *wa) {
-    int lo = 0;                                 /* number of window records with pos <= q0 (they form a prefix) */
-#pragma unroll
-    for (int step = 256; step; step >>= 1)
-        if (lo + step <= P2_WIN && rec_pos(wa[lo + step - 1]) <= q0) lo += step;
-    return lo - 1;
-}
-MS_D void p2_pass_a2_zero(uint32_t q0, uint32_t c, uint32_t *src) {
-    uint32_t *row = src + P2_SIDX(q0 - c);
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) row[k] = 0;
-}
-MS_D void p2_pass_a2_scatter(int lane, int r0, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src) {
-#pragma unroll 1
-    for (int r = (r0 > 0 ? r0 : 0) + lane; r < P2_WIN; r += 32) {
-        const uint32_t pos = rec_pos(wa[r]);
-        if (pos >= cend) break;
-        if (pos >= c) src[P2_SIDX(pos - c)] = wb[r];
-    }
-}
-MS_D void p2_pass_a2_walk(uint32_t q0, uint32_t c, int j, const uint32_t *wa, const uint32_t *wb, uint32_t *src) {
-    const uint32_t SB = 1u << 22;               /* P2_SBIAS of the plain instantiation (PA = 1 exists for it only) */
-    uint32_t *row = src + P2_SIDX(q0 - c);
-    uint32_t cur_src = 0, cur_off = 1, rem = 0, fold = 0;
-    if (j >= 0) {
-        const uint32_t pos = rec_pos(wa[j]), b = wb[j], off = rec_off(b), len = rec_len(b);
-        if (pos + len > q0) {
-            const uint32_t kk = q0 - pos;
-            rem = pos + len - q0; cur_off = off; cur_src = pos - off + SB;
-            fold = (off >= len || kk < off) ? kk : kk % off;
-        }
-    }
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) {
-        const uint32_t p = q0 + k, m = row[k];
-        if (m) { cur_off = m & 0x3FFFFFu; rem = m >> 22; cur_src = p - cur_off + SB; fold = 0; }
-        row[k] = rem ? cur_src + fold : (P2_LIT | (p + SB));
-        if (rem) { rem--; fold++; if (fold == cur_off) fold = 0; }
-    }
-}
-
 /* Pass B: fetch this lane's 16 bytes [q0, q0+16) (little-endian in 4 words; positions >= size give 0).  A source inside
  * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
  * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
@@ -227,7 +175,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-template <bool WIDE, bool RING = false, bool PLANE = false, int PA = 0>
+template <bool WIDE, bool RING = false, bool PLANE = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
                                                  const uint8_t *plane = nullptr)
@@ -247,17 +195,6 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         }
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
-        if (PA == 1) {
-            const int j = p2_pass_a2_search(q0, wa);
-            p2_pass_a2_zero(q0, c, src);
-            const int j0 = __shfl_sync(0xFFFFFFFFu, j, 0);        /* also orders the zeroing (it is a warp sync) */
-            r_lo = j0 > 0 ? j0 : 0;
-            p2_pass_a2_scatter(lane, j0, c, cend, wa, wb, src);
-            __syncwarp();
-            p2_pass_a2_walk(q0, c, j, wa, wb, src);
-            __syncwarp();
-        }
-        else {
         if (lane == 0) longq[0] = 0;
         p2_pass_a_literals<WIDE>(q0, c, src);
         __syncwarp();
@@ -266,7 +203,6 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         __syncwarp();
         p2_pass_a_long<WIDE>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        }
         p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (PLANE) __syncwarp();     /* an MSZIP overflow frame reads the bytes it is about to replace (ZipLaneC::qbase): every load before any store */

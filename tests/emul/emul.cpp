@@ -18,7 +18,6 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
-static bool g_pa2;      /* the experimental byte-parallel pass A for plain frames (frames_per_round bit 0x1000) */
 template <bool WIDE, bool RING = false, bool PLANE = false>
 static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr,
                           const uint8_t *plane = nullptr) {
@@ -34,19 +33,6 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         longq[0] = 0;
         for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;
-        if (g_pa2 && !WIDE && !RING) {
-            int j[32];
-            for (int lane = 0; lane < 32; lane++) { j[lane] = p2_pass_a2_search(c + 16u * lane, wa.data()); p2_pass_a2_zero(c + 16u * lane, c, src); }
-            r_lo = j[0] > 0 ? j[0] : 0;
-            for (int lane = 0; lane < 32; lane++) p2_pass_a2_scatter(lane, j[0], c, cend, wa.data(), wb.data(), src);
-            for (int lane = 0; lane < 32; lane++) p2_pass_a2_walk(c + 16u * lane, c, j[lane], wa.data(), wb.data(), src);
-            for (int lane = 0; lane < 32; lane++) p2_pass_b<WIDE, RING, PLANE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist, plane);
-            for (int lane = 0; lane < 32; lane++) {
-                uint32_t q0 = c + 16u * lane;
-                for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
-            }
-            continue;
-        }
         for (int lane = 0; lane < 32; lane++) p2_pass_a_literals<WIDE>(c + 16u * lane, c, src);
         int nlo = P2_WIN;
         for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
@@ -86,34 +72,11 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
     }
 }
 
-template <class Lane, bool TWO = false>
-static void emul_run3(Lane &t) {      /* p1_run<Lane, TWO, SPLIT = true> */
-    for (;;) {
-        t.service();
-        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
-        if (!m0) break;
-        if (MS_BALLOT(t.phase == PH_DECODE && t.near_end()))
-            do { if (t.phase == PH_DECODE) t.step_careful(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0 && MS_BALLOT(t.phase == PH_DECODE && t.near_end()));
-        else
-            do { if (t.phase == PH_DECODE) t.step_fast(); if (TWO) { if (t.phase == PH_DECODE && !t.near_end()) t.step_fast(); } } while (MS_BALLOT(t.phase == PH_DECODE && !t.near_end()) == m0);
-    }
-}
-template <class Lane>
-static void emul_run2(Lane &t) {      /* p1_run<Lane, TWO = true> */
-    for (;;) {
-        t.service();
-        const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
-        if (!m0) break;
-        do { if (t.phase == PH_DECODE) t.step(); if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
-    }
-}
-
 static uint32_t g_last_produced;
 extern "C" uint32_t emul_last_produced() { return g_last_produced; }
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
     if (u->codec == MSGPU_CODEC_MSZIP && (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) && F < 2) F = 2;      /* as run_wave does */
-    g_pa2 = (frames_per_round & 0x1000) != 0;
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
     std::vector<MsFrameInfo> finfo(F);
@@ -143,12 +106,10 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
 
     if (u->codec == MSGPU_CODEC_MSZIP) {
         typedef ZipSharedC<1, 32> SH; typedef ZipLaneC<1, 32> TH; typedef ZipLaneC<1, 32, true> THK;     /* THK: units with KWAJ framing */
-        typedef ZipLaneC<1, 32, false, 7> TH1;      /* the experimental unchecked refill (frames_per_round bit 0x4000) */
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *aux = (uint8_t *) aligned_alloc(64, (ZIP_AUX_BYTES + 63) & ~(size_t) 63); memset(aux, 0, ZIP_AUX_BYTES);   /* 32-byte aligned like the device's */
         const bool kwaj = (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) != 0;
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
             if (kwaj) { THK t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
-            else if (frames_per_round & 0x4000) { TH1 t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
             else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F); emul_run(t); t.end(st); }
             resolve();
         }
@@ -156,19 +117,11 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     }
     else if (u->codec == MSGPU_CODEC_LZX) {
         typedef LzxSharedC<1, 32> SH; typedef LzxLaneC<1, 32, false> TH; typedef LzxLaneC<1, 32, true> THD;
-        typedef LzxSharedP<1, 32, 4> SHP; typedef LzxLaneC<1, 32, false, 4> THP;        /* the packed shared-memory layouts */
-        typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ; typedef LzxLaneC<1, 32, false, 104, 29> THQ1;     /* + OPT bits 0, 2, 3 and 4 */
-        typedef LzxLaneC<1, 32, false, 104, 448> THQ6; typedef LzxLaneC<1, 32, false, 104, 511> THQ7;     /* OPT bits 6, 7 and 8 (unchecked refill in the fast step, one exit at its end, prefetched code lengths): alone, and with everything but "two steps" (frames_per_round bit 0x4000) */
-        static uint32_t slot_tab[64]; for (uint32_t k = 0; k < 64; k++) slot_tab[k] = lzx_slot_entry(k);
-        const bool packed = (frames_per_round & 0x200) != 0, packedq = (frames_per_round & 0x400) != 0;
-        SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHP) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
+        typedef LzxSharedQ<1, 32, 4> SHQ; typedef LzxLaneC<1, 32, false, 104> THQ;        /* the packed shared-memory layout of the plain kernel (frames_per_round bit 0x400) */
+        const bool packedq = (frames_per_round & 0x400) != 0;
+        SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(SHQ)); uint8_t *aux = (uint8_t *) calloc(1, LZX_AUX_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if (packedq && !wide && (frames_per_round & 0x4000) && (frames_per_round & 0x2000)) { THQ7 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3<THQ7, true>(t); t.end(st); }
-            else if (packedq && !wide && (frames_per_round & 0x4000)) { THQ6 t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
-            else if (packedq && !wide && (frames_per_round & 0x2000)) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run3(t); t.end(st); }
-            else if (packedq && !wide && (frames_per_round & 0x800)) { THQ1 t; t.slot_tab = slot_tab; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run2(t); t.end(st); }
-            else if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
-            else if (packed && !wide) { THP t; t.bind((SHP *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
+            if (packedq && !wide) { THQ t; t.bind((SHQ *) sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else if (wide) { THD t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             else { TH t; t.bind(sh, 0, aux, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), e8info.data(), F); emul_run(t); t.end(st); }
             resolve();
@@ -181,26 +134,8 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
     }
     else if (u->codec == MSGPU_CODEC_QUANTUM) {
         typedef QtmShared<1> SH; typedef QtmLane<1> TH;
-        SH *sh = (SH *) calloc(1, sizeof(SH) + sizeof(QtmShared<1, 1>)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
+        SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            if ((frames_per_round & 0x4000) && (frames_per_round & 0x2000)) {       /* + the loop-free renormalisation */
-                QtmLane<1, 7> t; t.bind((QtmShared<1, 7> *) sh, 0);
-                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
-                emul_run(t); t.end(st); resolve();
-                continue;
-            }
-            if (frames_per_round & 0x2000) {
-                QtmLane<1, 6> t; t.bind((QtmShared<1, 6> *) sh, 0);
-                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
-                emul_run(t); t.end(st); resolve();
-                continue;
-            }
-            if (frames_per_round & 0x4000) {       /* the experimental two-level model scan */
-                QtmLane<1, 1> t; t.bind((QtmShared<1, 1> *) sh, 0);
-                t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
-                emul_run(t); t.end(st); resolve();
-                continue;
-            }
             TH t; t.bind(sh, 0);
             t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
             emul_run(t); t.end(st); resolve();

@@ -10,10 +10,6 @@ import pytest
 from util import kwaj_mszip_stream
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# These two rows were written after round 1's GPU budget was spent: their device logic is pinned on the CPU (host emulation of the
-# same kernel code against the unmodified reference), but the kernels themselves have not run on a B200 yet.  Until they have, a
-# failure here must not hide the state of the verified tier in front of it: non-strict xfail (XPASS = they work).
-FIRST_GPU_RUN_PENDING = pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: first B200 run pending")
 KWAJX_REF = os.path.join(ROOT, "oracle", "_ref", "kwajx_ref")
 KWAJX_GPU = os.path.join(ROOT, "oracle", "_ref", "kwajx_gpu")
 
@@ -59,7 +55,6 @@ def test_kwaj_files_decode_with_the_reference(tmp_path):
 
 
 @pytest.mark.gpu
-@FIRST_GPU_RUN_PENDING
 @pytest.mark.skipif(not os.path.exists(KWAJX_GPU), reason="oracle/_ref/kwajx_gpu not built")
 def test_kwaj_files_decode_through_the_gpu_dropin(tmp_path):
     got = _check(KWAJX_GPU, tmp_path)
@@ -72,7 +67,6 @@ def test_kwaj_files_decode_through_the_gpu_dropin(tmp_path):
 
 
 @pytest.mark.gpu
-@FIRST_GPU_RUN_PENDING
 @pytest.mark.parametrize("seed", range(4))
 def test_mszip_repair_mode_on_the_gpu(decoder, oracle_ref, seed):
     """mszipd_init(repair_mode = 1) through the batch ABI (MSGPU_FLAG_MSZIP_REPAIR + the input buffer size): damaged MSZIP folders

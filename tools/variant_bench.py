@@ -1,7 +1,6 @@
-"""A/B of kernel shapes on one generated batch (development aid): one context per shape, stage timing P1 / P2, round trip verified.
-usage: variant_bench.py [units] [variant ids...]
-VB_CODEC=1 / 2 / 3 picks MSZIP (MSGPU_ZIP_VARIANT) / Quantum (MSGPU_QTM_VARIANT) / LZX (MSGPU_LZX_VARIANT, default);
-VB_P2=0,1 also loops over MSGPU_P2_VARIANT; VB_LIBS=a.so,b.so compares builds; VB_DATA picks the corpus.
+"""A/B of kernel builds / knobs on one generated batch (development aid): one context per job, stage timing P1 / P2, round trip verified.
+usage: variant_bench.py [units] [job ...]      a job is a comma-separated list of ENV=value settings ("-" = none), e.g. MSGPU_EXP=1
+VB_CODEC=1 / 2 / 3 picks MSZIP / Quantum / LZX (default); VB_LIBS=a.so,b.so compares builds; VB_DATA picks the corpus; VB_KW='dict(...)' extra generator arguments.
 Every shape runs in a process of its own (VB_ISOLATE=0 turns that off): a shape that faults or hangs costs its own line and a
 timeout, not the rest of the run - the batch is generated once and handed over through a file in /dev/shm."""
 import json, os, subprocess, sys, time
@@ -14,8 +13,9 @@ def run_one(units, comp, raw, out_bytes, codec, data, lib, v, p2v):
     from libmspack_b200 import codec as _codec
     from libmspack_b200.codec import BatchDecoder
     n = len(units)
-    os.environ["MSGPU_LZX_VARIANT" if codec == 3 else ("MSGPU_QTM_VARIANT" if codec == 2 else "MSGPU_ZIP_VARIANT")] = str(v)
-    os.environ["MSGPU_P2_VARIANT"] = str(p2v)
+    for kv in (v.split(",") if v != "-" else []):
+        k, _, val = kv.partition("=")
+        os.environ[k] = val
     if lib:
         _codec._lib = None; _codec.LIB_PATH = os.path.abspath(lib)       # another build of the library (dlopen keeps both)
     d_in = torch.from_numpy(comp).cuda(); d_out = torch.zeros(out_bytes, dtype=torch.uint8, device="cuda"); d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
@@ -38,18 +38,18 @@ def run_one(units, comp, raw, out_bytes, codec, data, lib, v, p2v):
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
-        path, codec, data, lib, v, p2v = sys.argv[2], int(sys.argv[3]), sys.argv[4], (sys.argv[5] if sys.argv[5] != "-" else None), int(sys.argv[6]), int(sys.argv[7])
+        path, codec, data, lib, v, p2v = sys.argv[2], int(sys.argv[3]), sys.argv[4], (sys.argv[5] if sys.argv[5] != "-" else None), sys.argv[6], int(sys.argv[7])
         z = np.load(path)
         run_one(z["units"], z["comp"], z["raw"], int(z["out_bytes"]), codec, data, lib, v, p2v)
         return
     from libmspack_b200 import gen
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-    variants = [int(v) for v in sys.argv[2:]] or [30]
+    variants = sys.argv[2:] or ["-"]
     data = os.environ.get("VB_DATA", "text")
     codec = int(os.environ.get("VB_CODEC", "3"))
-    b = gen.make_batch(codec, n, keep_raw=True, data=data)
+    b = gen.make_batch(codec, n, keep_raw=True, data=data, **eval(os.environ.get("VB_KW", "dict()")))
     libs = os.environ.get("VB_LIBS", "").split(",") if os.environ.get("VB_LIBS") else [None]
-    p2s = [int(x) for x in os.environ.get("VB_P2", "0").split(",")]          # MSGPU_P2_VARIANT values (1 = the byte-parallel pass A)
+    p2s = [0]
     jobs = [(l, v, q) for l in libs for q in p2s for v in variants]
     if os.environ.get("VB_ISOLATE", "1") == "0":
         for lib, v, p2v in jobs:
