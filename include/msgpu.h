@@ -50,7 +50,15 @@ extern "C" {
                                        * <= the window size).  The caller stores them in the OUTPUT buffer directly in front
                                        * of the unit, at [out_off - n, out_off): the reference preloads them at the end of its
                                        * window, i.e. logically just before the first output byte */
-#define MSGPU_UNIT_REF_BYTES(u) ((u)->flags >> MSGPU_FLAG_REF_SHIFT)
+#define MSGPU_UNIT_REF_BYTES(u) (((u)->flags & MSGPU_FLAG_LZX_STREAM_BASE) ? 0u : ((u)->flags >> MSGPU_FLAG_REF_SHIFT))
+/* An LZX unit that is a LATER reset interval of a longer stream (a CHM content section cut at its reset table, msgpu_chm.h): the
+ * reference, which decodes the section as one stream, keeps counting frames and bytes across resets - lzx->frame for the "no E8
+ * translation from frame 32768 on" rule and lzx->offset for the E8 call offsets (lzxd.c:706-712) - while everything else starts
+ * afresh at a reset (lzxd.c:423-438).  flags >> MSGPU_FLAG_REF_SHIFT = the index of the unit's first frame within its stream (not
+ * combinable with MSGPU_FLAG_LZX_DELTA / reference data).  intel_started, the third thing that survives a reset, needs no
+ * carrying: an interval can only contain a 0xE8 byte after one of ITS blocks coded that literal or was stored, which sets it. */
+#define MSGPU_FLAG_LZX_STREAM_BASE 0x20u
+#define MSGPU_UNIT_FRAME_BASE(u) (((u)->flags & MSGPU_FLAG_LZX_STREAM_BASE) ? ((u)->flags >> MSGPU_FLAG_REF_SHIFT) : 0u)
 /* MSZIP block chains (intra-folder parallelism).  The CK blocks of one MSZIP folder are independent
  * bitstreams - only their match SOURCES reach into the previous block's 32 KiB (mszipd.c:267-268) - so a caller that knows
  * where every block starts (a cabinet's CFDATA table does) can hand them over as consecutive units: CHAIN_FIRST for the first
@@ -101,8 +109,13 @@ const char *msgpu_last_error(const msgpu_ctx *ctx);
  *   d_out     device pointer, base for units[i].out_off (16-byte aligned)
  *   d_status  device pointer to n int32 (MSGPU_ERR_* per unit), may be NULL
  *   stream    a cudaStream_t passed as void* (NULL = the context's own stream)
- * Asynchronous with respect to the host when `stream` is given; returns 0 when the
- * work was enqueued, nonzero MSGPU_ERR_* on argument / launch failure. */
+ * Returns 0 when the work was enqueued, nonzero MSGPU_ERR_* on argument / launch failure.
+ * Asynchrony: a batch of LZX / Quantum units that fits one wave (the scratch budget: ~100 000 units on a B200) is queued on
+ * `stream` without waiting for the device - the unit table travels through pinned staging memory.  The call does wait
+ * (a) for the previous wave's table upload before it reuses the staging memory (batches larger than one wave, back-to-back
+ * calls: a wait for a COPY, not for kernels), and (b) per launch round in waves that hold MSZIP units, whose CK blocks may
+ * be shorter than 32 KiB, so that the number of rounds a folder needs is only known from a counter read back from the device.
+ * Results are complete when `stream` is. */
 int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
                               const void *d_in, size_t in_bytes,
                               void *d_out, size_t out_bytes,

@@ -18,8 +18,12 @@
  *
  * The reference seeks to one interval per extracted file and decodes forward from there; here all intervals are
  * independent units (fresh LZX state at every reset, lzxd.c:257-270 - what chmd.c itself relies on for random access).
- * Each unit's in_len reaches 4 bytes into the next interval where there is one: the reference's frame loop looks ahead
- * that far at a reset point (lzxd.c:419-453), and a unit cut exactly at its last byte would report MSPACK_ERR_READ.
+ * Each unit's in_len reaches 8 bytes into the next interval where there is one: the reference's frame loop looks ahead
+ * that far at a reset point (lzxd.c:419-453: the next interval's intel header, 1 or 33 bits fetched in 16-bit words), and a
+ * unit cut exactly at its last byte would report MSPACK_ERR_READ.  What does NOT start afresh at a reset - the stream's frame
+ * count and byte offset, which E8 call translation uses (lzxd.c:706-712) - travels in the unit: interval k > 0 carries
+ * MSGPU_FLAG_LZX_STREAM_BASE with its first frame's index, so a section whose intervals have E8 translation on decodes to the
+ * bytes the reference produces for the section as one stream.
  * Host-only; no GPU needed.
  */
 #ifndef MSGPU_CHM_H

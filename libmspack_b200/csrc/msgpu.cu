@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <utility>
 
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, u
         uint32_t start = f * MS_FRAME, size = u.out_len - start < MS_FRAME ? u.out_len - start : MS_FRAME;
         if (start + size > produced) break;
         int32_t fs = e8info[e8base[ti] + f];
-        if (fs) e8_translate_frame(lane, unit_out + start, size, (int32_t) start, fs);
+        if (fs) e8_translate_frame(lane, unit_out + start, size, (int32_t) (start + MSGPU_UNIT_FRAME_BASE(&u) * MS_FRAME), fs);      /* curpos = the STREAM offset (lzx->offset) */
     }
 }
 
@@ -277,6 +278,9 @@ struct msgpu_ctx {
     std::vector<cudaEvent_t> stage_pool;
     DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
+    /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
+     * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
         return units.cap + ustate.cap + recs.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
                save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap + chains.cap;
@@ -307,7 +311,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
         if (cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
     }
-    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess) { delete c; return nullptr; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
@@ -333,6 +337,8 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
                        &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status, &c->chains };
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
     for (cudaEvent_t e : c->stage_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->io_evs) cudaEventDestroy(e);
@@ -462,27 +468,42 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 
     uint32_t *d_order = reinterpret_cast<uint32_t *>(ctx->order.p);
     uint32_t *d_ord_z = d_order, *d_ord_q = d_order + nz, *d_ord_l = d_order + nz + nq;
-    CK(cudaMemcpyAsync(ctx->units.p, h_units + lo, (size_t) n * sizeof(msgpu_unit), cudaMemcpyHostToDevice, s), "copy units");
-    if (nz) CK(cudaMemcpyAsync(d_ord_z, ord[1].data(), nz * 4, cudaMemcpyHostToDevice, s), "copy order");
-    if (nchains) CK(cudaMemcpyAsync(ctx->chains.p, chains.data(), chains.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s), "copy chains");
-    if (nq) CK(cudaMemcpyAsync(d_ord_q, ord[2].data(), nq * 4, cudaMemcpyHostToDevice, s), "copy order");
-    if (nl) {
-        CK(cudaMemcpyAsync(d_ord_l, ord[3].data(), nl * 4, cudaMemcpyHostToDevice, s), "copy order");
-        CK(cudaMemcpyAsync(ctx->e8base.p, e8base.data(), nl * 4, cudaMemcpyHostToDevice, s), "copy e8 base");
-        CK(cudaMemsetAsync(ctx->e8info.p, 0, (size_t) (e8total + 1) * sizeof(int32_t), s), "clear e8 info");
+    {
+        /* the wave's tables go through the pinned staging area (one event guards its reuse by the next wave / call) */
+        const size_t b_units = (size_t) n * sizeof(msgpu_unit), b_ord = (size_t) (nz + nq + nl) * 4, b_e8 = (size_t) nl * 4, b_ch = chains.size() * 4;
+        const size_t need = b_units + b_ord + b_e8 + b_ch + 64;
+        if (ctx->stage_busy) { CK(cudaEventSynchronize(ctx->ev_stage), "staging sync"); ctx->stage_busy = false; }
+        if (need > ctx->h_stage_cap) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+            CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_stage), need + need / 4), "alloc staging");
+            ctx->h_stage_cap = need + need / 4;
+        }
+        uint8_t *hs = ctx->h_stage;
+        memcpy(hs, h_units + lo, b_units);
+        uint32_t *ho = reinterpret_cast<uint32_t *>(hs + b_units);
+        if (nz) memcpy(ho, ord[1].data(), (size_t) nz * 4);
+        if (nq) memcpy(ho + nz, ord[2].data(), (size_t) nq * 4);
+        if (nl) { memcpy(ho + nz + nq, ord[3].data(), (size_t) nl * 4); memcpy(ho + nz + nq + nl, e8base.data(), b_e8); }
+        if (b_ch) memcpy(ho + nz + nq + nl + nl, chains.data(), b_ch);
+        CK(cudaMemcpyAsync(ctx->units.p, hs, b_units, cudaMemcpyHostToDevice, s), "copy units");
+        if (b_ord) CK(cudaMemcpyAsync(d_order, ho, b_ord, cudaMemcpyHostToDevice, s), "copy order");
+        if (nl) CK(cudaMemcpyAsync(ctx->e8base.p, ho + nz + nq + nl, b_e8, cudaMemcpyHostToDevice, s), "copy e8 base");
+        if (b_ch) CK(cudaMemcpyAsync(ctx->chains.p, ho + nz + nq + nl + nl, b_ch, cudaMemcpyHostToDevice, s), "copy chains");
+        CK(cudaEventRecord(ctx->ev_stage, s), "event"); ctx->stage_busy = true;
     }
+    if (nl) CK(cudaMemsetAsync(ctx->e8info.p, 0, (size_t) (e8total + 1) * sizeof(int32_t), s), "clear e8 info");
     CK(cudaMemsetAsync(ctx->ustate.p, 0, (size_t) n * sizeof(MsUnitState), s), "clear state");
     CK(cudaMemsetAsync(ctx->misc.p, 0, MISC_WORDS * 4, s), "clear counters");
     if (any_delta && h_out) {
-        /* host buffers: the reference data of the LZX DELTA units lives in the caller's output buffer, in front of each unit */
+        /* host buffers: the reference data of the LZX DELTA units lives in the caller's output buffer, in front of each unit
+         * (the caller's buffer outlives the call, which synchronises before it returns) */
         for (uint32_t i = 0; i < n; i++) {
             const msgpu_unit &u = h_units[lo + i]; const uint32_t rl = MSGPU_UNIT_REF_BYTES(&u);
             if (u.codec == MSGPU_CODEC_LZX && rl)
                 CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + u.out_off - rl, h_out + u.out_off - rl, rl, cudaMemcpyHostToDevice, s), "copy reference data");
         }
     }
-    /* the pageable host vectors above must outlive the async copies */
-    CK(cudaStreamSynchronize(s), "sync uploads");
 
     WaveArgs a;
     a.units = reinterpret_cast<const msgpu_unit *>(ctx->units.p); a.in_base = reinterpret_cast<const uint8_t *>(d_in);
@@ -512,6 +533,23 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (e > b1) b1 = e;
         }
     };
+    /* Output ranges of a sub-wave's units, sorted and merged where they touch: the host-buffer call may only write the bytes units
+     * own ([out_off, out_off + out_len)), never the gaps between them (the 16-byte alignment of out_off leaves gaps after ragged
+     * units).  A sub-wave whose units leave more than MAXR separate ranges is handled the other way round: the caller's bytes of
+     * the whole span are copied IN first (`prime`), so that the one copy out returns them unchanged. */
+    const size_t MAXR = 512;
+    auto out_ranges = [&](const std::vector<uint32_t> &v, uint32_t f0, uint32_t f1, std::vector<std::pair<uint64_t, uint64_t>> &r) {
+        r.clear();
+        for (uint32_t k = f0; k < f1; k++) { const msgpu_unit &u = h_units[lo + v[k]]; if (u.out_len) r.push_back(std::make_pair((uint64_t) u.out_off, (uint64_t) u.out_off + u.out_len)); }
+        if (!std::is_sorted(r.begin(), r.end())) std::sort(r.begin(), r.end());
+        size_t w = 0;
+        for (size_t k = 0; k < r.size(); k++) {
+            if (w && r[k].first <= r[w - 1].second) { if (r[k].second > r[w - 1].second) r[w - 1].second = r[k].second; }
+            else r[w++] = r[k];
+        }
+        r.resize(w);
+    };
+    std::vector<std::pair<uint64_t, uint64_t>> rng;
     auto copy_in = [&](uint32_t sub, cudaStream_t st) {
         if (!h_in) return;
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
@@ -521,16 +559,21 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             io_range(*lists[c], f0, f1, false, b0, b1);
             b0 &= ~3ull;                                   /* keep 4-byte loads of the first unit inside the copied range */
             if (b1 > b0) cudaMemcpyAsync(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(d_in)) + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, st);
+            if (h_out) {
+                out_ranges(*lists[c], f0, f1, rng);
+                if (rng.size() > MAXR) cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + rng.front().first, h_out + rng.front().first, rng.back().second - rng.front().first, cudaMemcpyHostToDevice, st);      /* prime */
+            }
         }
     };
     auto copy_out = [&](uint32_t sub, cudaStream_t st) {
         if (!h_out) return;
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (int c = 0; c < 3; c++) {
-            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt; uint64_t b0, b1;
+            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt;
             if (f0 >= cnt) continue;
-            io_range(*lists[c], f0, f1, true, b0, b1);
-            if (b1 > b0) cudaMemcpyAsync(h_out + b0, reinterpret_cast<uint8_t *>(d_out) + b0, b1 - b0, cudaMemcpyDeviceToHost, st);
+            out_ranges(*lists[c], f0, f1, rng);
+            if (rng.size() > MAXR) { rng.front().second = rng.back().second; rng.resize(1); }      /* (primed by copy_in) */
+            for (const auto &r : rng) cudaMemcpyAsync(h_out + r.first, reinterpret_cast<uint8_t *>(d_out) + r.first, r.second - r.first, cudaMemcpyDeviceToHost, st);
         }
     };
     /* the sub-wave's output is complete on stream st: send it home */
@@ -653,9 +696,11 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
     for (size_t i = 0; i < n; i++) {
         const msgpu_unit &u = units[i];
         if (u.codec < 1 || u.codec > 3) return fail(ctx, MSGPU_ERR_ARGS, "unit with unknown codec");
-        if (u.in_off + u.in_len > in_bytes || u.out_off + u.out_len > out_bytes) return fail(ctx, MSGPU_ERR_ARGS, "unit outside the input/output buffer");
+        if (u.in_off > in_bytes || u.in_len > in_bytes - u.in_off || u.out_off > out_bytes || u.out_len > out_bytes - u.out_off)      /* (no sums: they could wrap) */
+            return fail(ctx, MSGPU_ERR_ARGS, "unit outside the input/output buffer");
         if (u.in_len >= 0x7FFFFFF0u) return fail(ctx, MSGPU_ERR_ARGS, "unit input too large");
         if (u.out_off & 15u) return fail(ctx, MSGPU_ERR_ARGS, "out_off must be a multiple of 16");
+        if ((u.flags & MSGPU_FLAG_LZX_STREAM_BASE) && (u.codec != MSGPU_CODEC_LZX || (u.flags & MSGPU_FLAG_LZX_DELTA))) return fail(ctx, MSGPU_ERR_ARGS, "MSGPU_FLAG_LZX_STREAM_BASE is for plain LZX units");
         if (u.codec == MSGPU_CODEC_LZX && MSGPU_UNIT_REF_BYTES(&u) > u.out_off) return fail(ctx, MSGPU_ERR_ARGS, "LZX DELTA reference data must lie in front of the unit inside the output buffer");
         if (u.flags & (MSGPU_FLAG_CHAIN_FIRST | MSGPU_FLAG_CHAIN_NEXT)) {           /* MSZIP block chains, include/msgpu.h */
             if (u.codec != MSGPU_CODEC_MSZIP || (u.flags & MSGPU_FLAG_CHAIN_FIRST && u.flags & MSGPU_FLAG_CHAIN_NEXT)) return fail(ctx, MSGPU_ERR_ARGS, "bad chain flags");

@@ -220,6 +220,7 @@ extern "C" int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan,
     CKC(cudaMalloc(&B.status, (nf + nb + 1) * sizeof(int32_t)));         /* one per unit: a folder, or a block of a chain */
     CKC(cudaMemcpyAsync(B.image, image, image_bytes, cudaMemcpyHostToDevice, B.st));
     CKC(cudaMemsetAsync(B.packed, 0, plan->packed_bytes + 16, B.st));
+    CKC(cudaMemsetAsync(B.out, 0, plan->out_bytes + 16, B.st));      /* folders that fail hand back zeros, never stale device memory */
     std::vector<uint8_t> ok(nb, 1);
     if (nb) {
         CKC(cudaMemcpyAsync(B.blocks, plan->blocks.data(), nb * sizeof(msgpu_cab_block), cudaMemcpyHostToDevice, B.st));

@@ -54,9 +54,14 @@ extern "C" int msgpu_chm_units(const void *control_data, size_t control_bytes, c
         msgpu_unit u; memset(&u, 0, sizeof(u));
         u.codec = MSGPU_CODEC_LZX; u.window_bits = (uint8_t) window_bits; u.reset_interval = (uint16_t) frames_per_unit;
         u.in_off = off; u.out_off = k * reset_interval; u.out_len = (uint32_t) reset_interval;
+        /* interval k starts at frame k * frames_per_unit of the section's stream (E8 offsets and the frame-32768 rule count on) */
+        if (k * frames_per_unit >= (1ull << 26)) return MSGPU_ERR_DATAFORMAT;
+        if (k) u.flags = MSGPU_FLAG_LZX_STREAM_BASE | ((uint32_t) (k * frames_per_unit) << MSGPU_FLAG_REF_SHIFT);
         units[k] = u;
         if (k) {
-            uint64_t len = off - prev_off, slack = content_bytes - off < 4 ? content_bytes - off : 4;
+            /* the zero-sized extra frame pass of lzxd.c:419 reads the NEXT interval's intel header (1 bit, or 1 + 32 bits when E8
+             * translation is on: up to 8 bytes in 16-bit words) before the request is found complete: the unit may look that far */
+            uint64_t len = off - prev_off, slack = content_bytes - off < 8 ? content_bytes - off : 8;
             if (len + slack >= 0x7FFFFFF0ull) return MSGPU_ERR_DATAFORMAT;
             units[k - 1].in_len = (uint32_t) (len + slack);
         }

@@ -376,7 +376,7 @@ struct LzxLaneC {
         emit_end(em, frame_size);
         MsFrameInfo fi; fi.nrec = em.nrec; fi.size = frame_size; fi.g0 = frame_start_pos; fi.valid = 1;
         finfo[f] = fi;
-        e8info[frame] = (intel_started && intel_filesize && frame < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 */
+        e8info[frame] = (intel_started && intel_filesize && frame + MSGPU_UNIT_FRAME_BASE(u) < 32768 && frame_size > 10) ? intel_filesize : 0;   /* :706-709 (the stream's frame count) */
         produced += frame_size; frame++; f++;
         if (produced >= u->out_len) {
             done = 1; phase = PH_IDLE;

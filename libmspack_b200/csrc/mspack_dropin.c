@@ -4,12 +4,17 @@
  *
  * Stream model.  The reference codecs are pull/push state machines: X_decompress(state, n) must deliver
  * exactly n more bytes to system->write, reading input through system->read as it goes.
- * A GPU wants the whole unit, so the first X_decompress call slurps the input until read() reports EOF
- * (for a CAB folder that is also when cabd_sys_read announces the final length through
- * lzxd_set_output_length, cabd.c:1335-1340), decodes on the device, and the calls then replay the
- * decoded bytes.  Errors stay lazy like the reference's: if the whole unit does not decode, only the
- * frames needed for the current request are decoded, so a request that ends before a corrupt frame still
- * succeeds and the error (sticky, lzxd.c:396) surfaces with the first request that reaches it.
+ * A GPU wants the whole unit, so the first X_decompress call slurps the input until read() reports EOF or an
+ * error (for a CAB folder that is also when cabd_sys_read announces the final length through
+ * lzxd_set_output_length, cabd.c:1335-1340), decodes AS MUCH OF THE UNIT AS DECODES in one device call, and
+ * every later call replays decoded bytes - one decode per folder however many member files cabd extracts from
+ * it.  Errors stay as lazy as the reference's: the device reports how many whole frames decoded in front of
+ * the first failing one; a request that ends inside them succeeds, the first request that reaches the failing
+ * frame gets its MSPACK_ERR_* (sticky, lzxd.c:396).  A read() error ends the input where the reference's
+ * would have ended (see ds_slurp).  Known leniency: where the reference tops up its bit buffer at the end of
+ * the last good frame (lzxd.c:696-697) and THAT read fails, it fails the frame; here the frame decodes.
+ * One device context per process, calls serialised by a mutex: the drop-in is the compatibility path (a
+ * batch of n = 1), callers that want throughput hand whole batches to include/msgpu.h.
  *
  * There is no CPU decoder here: without a CUDA device X_init returns NULL (-> MSPACK_ERR_NOMEMORY in cabd.c:1255).
  */
@@ -44,9 +49,21 @@ struct dstream {                     /* common state; the three public stream ty
     off_t offset;                    /* bytes delivered to write() so far */
     int error;                       /* sticky */
     unsigned char *in; size_t in_len, in_cap; int in_done;
-    unsigned char *out; size_t out_len;  /* decoded prefix [0, out_len) */
-    int whole_failed;                /* the whole-unit decode failed: fall back to request-sized prefixes */
+    int read_failed;                 /* system->read reported an error: the input ends where the reference's would have (see ds_slurp) */
+    unsigned char *out; size_t out_cap;  /* decoded prefix [0, out_len) at out + out_base */
+    size_t out_len;
+    int tail_status;                 /* nonzero: the stream fails right behind out_len with this MSPACK_ERR_* (everything decodable is decoded) */
 };
+
+/* All buffers come from the caller's mspack_system, as the reference's do (lzxd.c:308-314, mspack.h:399-420); there is no realloc
+ * in that interface, so growing means alloc + copy + free. */
+static unsigned char *ds_grow(struct dstream *s, unsigned char *old, size_t old_bytes, size_t new_bytes) {
+    unsigned char *p = (unsigned char *) s->sys->alloc(s->sys, new_bytes);
+    if (!p) return NULL;
+    if (old && old_bytes) memcpy(p, old, old_bytes < new_bytes ? old_bytes : new_bytes);
+    if (old) s->sys->free(old);
+    return p;
+}
 
 static struct dstream *ds_new(struct mspack_system *sys, struct mspack_file *in, struct mspack_file *out, int codec) {
     struct dstream *s;
@@ -63,23 +80,29 @@ static struct dstream *ds_new(struct mspack_system *sys, struct mspack_file *in,
 
 static void ds_free(struct dstream *s) {
     if (!s) return;
-    free(s->in); free(s->out); free(s->ref);
+    if (s->in) s->sys->free(s->in);
+    if (s->out) s->sys->free(s->out);
+    if (s->ref) s->sys->free(s->ref);
     s->sys->free(s);
 }
 
-/* read the unit's whole input through system->read (mspack.h:329-338: a short read or 0 means EOF) */
+/* Read the unit's whole input through system->read (mspack.h:329-338: a short read or 0 means EOF).  A read ERROR does not fail
+ * the stream here: cabd_sys_read returns -1 for a CFDATA block with a bad checksum or a missing next cabinet (cabd.c:1322-1324),
+ * and the reference, which pulls input as it decodes, still extracts every file that lies in front of that block.  So the bytes
+ * read so far are kept, the input simply ends there, and the decoder reports MSPACK_ERR_READ when - and only when - a request
+ * reaches the missing bytes (msgpu_cab.cu cuts a folder's input in front of its first bad block the same way). */
 static int ds_slurp(struct dstream *s) {
     if (s->in_done) return MSPACK_ERR_OK;
     for (;;) {
         int got;
         if (s->in_len + 65536 > s->in_cap) {
             size_t ncap = s->in_cap ? s->in_cap * 2 : (1u << 18);
-            unsigned char *p = (unsigned char *) realloc(s->in, ncap);
+            unsigned char *p = ds_grow(s, s->in, s->in_len, ncap);
             if (!p) return MSPACK_ERR_NOMEMORY;
             s->in = p; s->in_cap = ncap;
         }
         got = s->sys->read(s->input, s->in + s->in_len, 65536);
-        if (got < 0) return MSPACK_ERR_READ;
+        if (got < 0) { s->read_failed = 1; break; }
         if (got == 0) break;
         s->in_len += (size_t) got;
     }
@@ -87,25 +110,35 @@ static int ds_slurp(struct dstream *s) {
     return MSPACK_ERR_OK;
 }
 
-/* decode the unit's first `want` output bytes on the device */
-static int ds_decode(struct dstream *s, size_t want) {
-    msgpu_unit u; int32_t st = -1; int rc; unsigned char *buf;
+/* Decode as much of the unit as `cap` output bytes allow, ONCE: afterwards out_len = the bytes that decoded (whole frames in front
+ * of the first failing one, or all of cap) and tail_status = what the stream fails with behind them (0 = nothing failed yet).
+ * Requests are then served from that prefix - a folder with many member files costs one decode, not one per file - and the error
+ * surfaces, like the reference's, with the first request that reaches the failing frame. */
+static int ds_decode(struct dstream *s, size_t cap) {
+    msgpu_unit u; int32_t st = -1; uint32_t produced = 0; int rc;
     const size_t rpad = (s->ref_len + 15) & ~(size_t) 15;      /* the batch ABI wants the reference data right in front of the output */
-    buf = (unsigned char *) realloc(s->out, rpad + want + 64);
-    if (!buf) return MSPACK_ERR_NOMEMORY;
-    s->out = buf; s->out_base = rpad;
+    if (rpad + cap + 64 > s->out_cap) {
+        unsigned char *buf;
+        if (s->out) { s->sys->free(s->out); s->out = NULL; s->out_cap = 0; }      /* (its contents are decoded again below) */
+        buf = (unsigned char *) s->sys->alloc(s->sys, rpad + cap + 64);
+        if (!buf) return MSPACK_ERR_NOMEMORY;
+        s->out = buf; s->out_cap = rpad + cap + 64;
+    }
+    s->out_base = rpad; s->out_len = 0; s->tail_status = 0;
     if (s->ref_len) memcpy(s->out + rpad - s->ref_len, s->ref, s->ref_len);
     memset(&u, 0, sizeof(u));
     u.codec = (uint8_t) s->codec; u.window_bits = (uint8_t) s->window_bits; u.reset_interval = (uint16_t) s->reset_interval;
     u.flags = s->repair_mode ? (MSGPU_FLAG_MSZIP_REPAIR | ((uint32_t) s->bufsize << MSGPU_FLAG_REF_SHIFT)) : 0;
     if (s->is_delta) u.flags |= MSGPU_FLAG_LZX_DELTA | ((uint32_t) s->ref_len << MSGPU_FLAG_REF_SHIFT);
-    u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = rpad; u.out_len = (uint32_t) want;
+    u.in_off = 0; u.in_len = (uint32_t) s->in_len; u.out_off = rpad; u.out_len = (uint32_t) cap;
     pthread_mutex_lock(&g_mu);
-    rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len + 0, s->out, rpad + want, &st);
+    rc = msgpu_decode_batch_host(ctx_get(), &u, 1, s->in, s->in_len + 0, s->out, rpad + cap, &st);
+    if (!rc) rc = msgpu_last_produced(ctx_get(), &produced, 1);
     pthread_mutex_unlock(&g_mu);
     if (rc) return MSPACK_ERR_NOMEMORY;
-    if (st == MSGPU_ERR_OK) { s->out_len = want; return MSPACK_ERR_OK; }
-    return st;
+    if (st == MSGPU_ERR_OK) { s->out_len = cap; return MSPACK_ERR_OK; }
+    s->out_len = produced < cap ? produced : cap; s->tail_status = st;
+    return MSPACK_ERR_OK;
 }
 
 static int ds_decompress(struct dstream *s, off_t out_bytes) {
@@ -116,22 +149,23 @@ static int ds_decompress(struct dstream *s, off_t out_bytes) {
     if ((e = ds_slurp(s))) return s->error = e;
     if (s->in_len >= 0x7FFFFFF0u || (uint64_t) s->offset + (uint64_t) out_bytes > 0xFFFFFFFFu) return s->error = MSPACK_ERR_DECRUNCH;
     end = (size_t) (s->offset + out_bytes);
-    if (end > s->out_len) {
-        /* first try the whole unit (its length is known for LZX once the input has been read) ... */
-        if (!s->whole_failed) {
-            size_t whole = (s->codec == MSGPU_CODEC_LZX && s->length > 0 && (size_t) s->length >= end) ? (size_t) s->length : end;
-            e = ds_decode(s, whole);
-            if (e && whole > end) { s->whole_failed = 1; e = -1; }
+    while (end > s->out_len) {
+        size_t cap;
+        if (s->tail_status) return s->error = s->tail_status;      /* everything that decodes is decoded: the request reaches the failing frame */
+        /* how far to decode: the whole unit where its length is known (LZX, once cabd has announced it: cabd.c:1335-1340); otherwise
+         * a generous multiple of the input (a CAB folder's MSZIP / Quantum data), four times the last try if that was not enough.
+         * Decoding "too far" is harmless: the stream ends with an error behind its last frame, which is what tail_status records. */
+        if (s->codec == MSGPU_CODEC_LZX && s->length > 0 && (size_t) s->length >= end) cap = (size_t) s->length;
+        else {
+            cap = s->in_len * 8 + 4 * FRAME;
+            if (cap < 4 * s->out_len) cap = 4 * s->out_len;
+            if (cap < end) cap = end;
+            cap = (cap + FRAME - 1) / FRAME * FRAME;
+            if (s->codec == MSGPU_CODEC_LZX && s->length > 0 && cap > (size_t) s->length) cap = (size_t) s->length;
         }
-        else e = -1;
-        /* ... and if that fails, just the frames this request needs (errors stay as lazy as the reference's) */
-        if (e == -1) {
-            size_t want = (end + FRAME - 1) / FRAME * FRAME;
-            if (s->codec == MSGPU_CODEC_LZX && s->length > 0 && want > (size_t) s->length) want = (size_t) s->length;
-            if (s->codec != MSGPU_CODEC_LZX) want = end;
-            e = ds_decode(s, want);
-        }
-        if (e) return s->error = e;
+        if (cap > 0xFFFF0000u) cap = 0xFFFF0000u;
+        if (cap < end) return s->error = MSPACK_ERR_DECRUNCH;
+        if ((e = ds_decode(s, cap))) return s->error = e;
     }
     /* replay: exactly out_bytes more bytes to write() (mspack.h:346-355 write must return the count) */
     while (out_bytes > 0) {
@@ -169,14 +203,15 @@ int lzxd_set_reference_data(struct lzxd_stream *lzx, struct mspack_system *syste
     if (s->offset) return MSPACK_ERR_ARGS;                       /* too late once decoding has started */
     if (length > (1u << s->window_bits)) return MSPACK_ERR_ARGS; /* longer than the window */
     if (length > 0 && (!system || !input)) return MSPACK_ERR_ARGS;
-    free(s->ref); s->ref = NULL; s->ref_len = length;
+    if (s->ref) s->sys->free(s->ref);
+    s->ref = NULL; s->ref_len = length;
     if (length > 0) {
         int bytes;
-        if (!(s->ref = (unsigned char *) malloc(length))) { s->ref_len = 0; return MSPACK_ERR_NOMEMORY; }
+        if (!(s->ref = (unsigned char *) s->sys->alloc(s->sys, length))) { s->ref_len = 0; return MSPACK_ERR_NOMEMORY; }
         bytes = system->read(input, s->ref, (int) length);
         if (bytes < (int) length) return MSPACK_ERR_READ;
     }
-    s->out_len = 0;                                              /* anything decoded before used other reference data */
+    s->out_len = 0; s->tail_status = 0;                          /* anything decoded before used other reference data */
     return MSPACK_ERR_OK;
 }
 int lzxd_decompress(struct lzxd_stream *lzx, off_t out_bytes) { return ds_decompress((struct dstream *) lzx, out_bytes); }
@@ -226,9 +261,13 @@ int mszipd_decompress_kwaj(struct mszipd_stream *zip) {
     for (;;) {
         msgpu_unit u; int32_t st = -1; uint32_t produced = 0; int rc; unsigned char *buf; size_t off;
         if (cap > 0xFFFF0000u) cap = 0xFFFF0000u;
-        buf = (unsigned char *) realloc(s->out, cap + 64);
-        if (!buf) return s->error = MSPACK_ERR_NOMEMORY;
-        s->out = buf; s->out_base = 0;
+        if (cap + 64 > s->out_cap) {
+            if (s->out) { s->sys->free(s->out); s->out = NULL; s->out_cap = 0; }
+            buf = (unsigned char *) s->sys->alloc(s->sys, cap + 64);
+            if (!buf) return s->error = MSPACK_ERR_NOMEMORY;
+            s->out = buf; s->out_cap = cap + 64;
+        }
+        s->out_base = 0;
         memset(&u, 0, sizeof(u));
         u.codec = MSGPU_CODEC_MSZIP; u.flags = MSGPU_FLAG_MSZIP_KWAJ;
         u.in_len = (uint32_t) s->in_len; u.out_len = (uint32_t) cap;

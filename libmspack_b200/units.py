@@ -17,6 +17,7 @@ FLAG_LZX_DELTA = 0x2          # include/msgpu.h MSGPU_FLAG_LZX_DELTA
 FLAG_CHAIN_FIRST, FLAG_CHAIN_NEXT = 0x4, 0x8   # MSZIP block chains
 FLAG_MSZIP_KWAJ = 0x10        # MSZIP inside a KWAJ file: out_len is a capacity, the stream ends at a zero block length
 ERR_CHAIN, ERR_CAPACITY = 100, 101
+FLAG_LZX_STREAM_BASE = 0x20  # include/msgpu.h MSGPU_FLAG_LZX_STREAM_BASE: flags >> 6 = index of the unit's first frame in its stream
 FLAG_REF_SHIFT = 6            # flags >> 6 = LZX DELTA reference bytes stored in front of the unit's output
 
 # MSPACK_ERR_* (libmspack/mspack/mspack.h:485-507)

@@ -128,7 +128,7 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         }
         for (uint32_t f = 0; f < nframes_total; f++) if (e8info[f]) {
             uint32_t start = f * MS_FRAME, size = u->out_len - start < MS_FRAME ? u->out_len - start : MS_FRAME;
-            if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) start, e8info[f]);
+            if (start + size <= st.produced) emul_e8_frame(unit_out + start, size, (int32_t) (start + MSGPU_UNIT_FRAME_BASE(u) * MS_FRAME), e8info[f]);
         }
         free(sh); free(aux);
     }

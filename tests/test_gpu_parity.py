@@ -136,3 +136,24 @@ def test_full_size_lzx_properties(decoder):
     out, st = decoder.decode_host(b.units, b.comp, b.out_bytes)
     assert (st == 0).all()
     assert np.array_equal(out, b.raw)
+
+
+@pytest.mark.parametrize("n,unit_bytes", [(40, 5003), (3000, 1001)], ids=["few-ranges", "primed-span"])
+def test_host_call_writes_only_unit_bytes(decoder, oracle_ref, n, unit_bytes):
+    """msgpu_decode_batch_host returns exactly the bytes units own: the gaps between ragged units (out_off is 16-byte aligned) and
+    the bytes of failed units' neighbours keep what the caller had there - per merged range for a few ranges, through the primed
+    span for many (msgpu.cu run_wave out_ranges)."""
+    parts = [gen.make_batch(CODEC_MSZIP, n, unit_bytes=unit_bytes), gen.make_batch(CODEC_LZX, n, unit_bytes=unit_bytes + 2, first_unit=5000),
+             gen.make_batch(CODEC_QUANTUM, n // 4 + 1, unit_bytes=unit_bytes + 5, first_unit=9000)]
+    m = gen.concat_batches(parts)
+    perm = np.random.default_rng(3).permutation(m.n)
+    m.units = m.units[perm].copy()
+    init = np.full(m.out_bytes, 0xA5, dtype=np.uint8)
+    out_g, st_g = decoder.decode_host(m.units, m.comp, m.out_bytes, out_init=init)
+    out_o, st_o, _ = oracle_ref.decode_batch(m.units, m.comp, m.out_bytes, threads=8)
+    assert_same(m.units, out_o, st_o, out_g, st_g, "ragged mixed batch")
+    owned = np.zeros(m.out_bytes, dtype=bool)
+    for u in m.units:
+        owned[int(u["out_off"]):int(u["out_off"]) + int(u["out_len"])] = True
+    assert (~owned).any()
+    assert (out_g[~owned] == 0xA5).all(), "bytes outside every unit were overwritten"

@@ -68,9 +68,18 @@ def test_mszip_block_chains(decoder, oracle_ref):
     m = gen.concat_batches([chain, extra])
     out, st = decoder.decode_host(m.units, m.comp, m.out_bytes)
     assert (st == 0).all()
-    for k, r in enumerate(raws):                    # per folder: the bytes between two folders (alignment gaps) belong to nobody
+    for k, r in enumerate(raws):
         assert np.array_equal(plain.unit_output(out, k), plain.unit_output(o1, k)), k
         assert plain.unit_output(out, k).tobytes() == r
+    # the whole buffer: the bytes between two folders (alignment gaps) belong to nobody and keep the caller's contents
+    init = np.full(m.out_bytes, 0x5A, dtype=np.uint8)
+    out2, st2 = decoder.decode_host(m.units, m.comp, m.out_bytes, out_init=init)
+    ref = init.copy()
+    for k in range(plain.n):
+        lo = int(plain.units["out_off"][k]); ref[lo:lo + int(plain.units["out_len"][k])] = plain.unit_output(o1, k)
+    for k in range(extra.n):
+        lo = chain.out_bytes + int(extra.units["out_off"][k]); ref[lo:lo + int(extra.units["out_len"][k])] = extra.unit_output(out[chain.out_bytes:], k)
+    assert (st2 == 0).all() and np.array_equal(out2, ref)
     oe, se, _ = oracle_ref.decode_batch(extra.units, extra.comp, extra.out_bytes, threads=8)
     for k in range(extra.n):
         assert np.array_equal(extra.unit_output(out[chain.out_bytes:], k), extra.unit_output(oe, k)), k
