@@ -134,6 +134,16 @@ int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
                             const void *h_in, size_t in_bytes,
                             void *h_out, size_t out_bytes, int32_t *status);
 
+/* Several GPUs, one call.  Units are independent, so devices share a batch by unit index with no exchange step (the reference's
+ * unit of independence: a CAB folder, cabd.c:1142-1177; a CHM reset interval, chmd.c:1146-1186):
+ *   msgpu_shard_range            shard `shard` of `nshards` owns units [*lo, *hi) = [floor(shard n / nshards), floor((shard + 1) n /
+ *                                nshards)), moved forward where that would cut an MSZIP block chain (the same split bench.py's ranks use)
+ *   msgpu_decode_batch_host_multi one thread + one context (ctxs[d], created on ndev different devices) per shard; each device copies
+ *                                in / out only its shard's bytes.  status[] and the return value as for msgpu_decode_batch_host. */
+int msgpu_shard_range(const msgpu_unit *units, size_t n, int shard, int nshards, size_t *lo, size_t *hi);
+int msgpu_decode_batch_host_multi(msgpu_ctx *const *ctxs, int ndev, const msgpu_unit *units, size_t n,
+                                  const void *h_in, size_t in_bytes, void *h_out, size_t out_bytes, int32_t *status);
+
 /* Bytes every unit of the most recent batch produced (complete frames only if the unit failed): produced[0..n).  Valid for a
  * batch that ran as one wave (n units; up to several thousand units always do, larger ones as far as the scratch budget
  * reaches); synchronises with the batch.  Returns 0, or MSGPU_ERR_ARGS if the last batch was not a single wave of n units. */

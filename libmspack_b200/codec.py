@@ -21,6 +21,7 @@ ABI_SYMBOLS = [
     "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
     "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
     "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version", "msgpu_last_produced",
+    "msgpu_shard_range", "msgpu_decode_batch_host_multi",
 ]
 
 _lib = None
@@ -50,6 +51,10 @@ def load_library() -> ctypes.CDLL:
     lib.msgpu_decode_batch_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p]
     lib.msgpu_last_produced.restype = ctypes.c_int
     lib.msgpu_last_produced.argtypes = [vp, vp, sz]
+    lib.msgpu_shard_range.restype = ctypes.c_int
+    lib.msgpu_shard_range.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+    lib.msgpu_decode_batch_host_multi.restype = ctypes.c_int
+    lib.msgpu_decode_batch_host_multi.argtypes = [vp, ctypes.c_int, vp, sz, vp, sz, vp, sz, i32p]
     lib.msgpu_launch_count.restype = ctypes.c_uint64
     lib.msgpu_launch_count.argtypes = [vp]
     lib.msgpu_scratch_bytes.restype = ctypes.c_size_t

@@ -16,6 +16,7 @@
 #include <vector>
 #include <algorithm>
 #include <utility>
+#include <thread>
 
 #include "msgpu_core.cuh"
 #include "msgpu_p1_mszip.cuh"
@@ -762,5 +763,61 @@ extern "C" int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, 
     if (r) return r;
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "copy status");
     CK(cudaStreamSynchronize(s), "sync");
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ several GPUs, one call */
+/* Units are independent, so several devices share a batch by unit index: shard r of R owns units
+ * [floor(r n / R), floor((r + 1) n / R)), moved forward where that would cut an MSZIP block chain in two. */
+extern "C" int msgpu_shard_range(const msgpu_unit *units, size_t n, int shard, int nshards, size_t *lo, size_t *hi)
+{
+    if (!lo || !hi || nshards <= 0 || shard < 0 || shard >= nshards || (n && !units)) return MSGPU_ERR_ARGS;
+    auto cut = [&](int r) { size_t c = (size_t) (((unsigned __int128) n * (unsigned) r) / (unsigned) nshards); while (c < n && c > 0 && (units[c].flags & MSGPU_FLAG_CHAIN_NEXT)) c++; return c; };
+    *lo = cut(shard); *hi = shard + 1 == nshards ? n : cut(shard + 1);
+    if (*hi < *lo) *hi = *lo;
+    return 0;
+}
+
+/* One batch with host buffers over ndev devices: one thread and one context per device, every device copies in only its
+ * shard's compressed bytes and copies out only its shard's output (the shard's units are re-based onto the byte range they
+ * cover, so a device never allocates more than its share).  No data-path collective: nothing a shard produces is another
+ * shard's input.  status[] as in msgpu_decode_batch_host; returns the first shard's failure, 0 if all shards ran. */
+extern "C" int msgpu_decode_batch_host_multi(msgpu_ctx *const *ctxs, int ndev, const msgpu_unit *units, size_t n,
+                                             const void *h_in, size_t in_bytes, void *h_out, size_t out_bytes, int32_t *status)
+{
+    if (!ctxs || ndev <= 0 || ndev > 64) return MSGPU_ERR_ARGS;
+    for (int d = 0; d < ndev; d++) if (!ctxs[d]) return MSGPU_ERR_ARGS;
+    if (n == 0) return 0;
+    if (!units || !h_in || !h_out) return fail(ctxs[0], MSGPU_ERR_ARGS, "null argument");
+    for (size_t i = 0; i < n; i++) {
+        const msgpu_unit &u = units[i];
+        if (u.in_off > in_bytes || u.in_len > in_bytes - u.in_off || u.out_off > out_bytes || u.out_len > out_bytes - u.out_off)
+            return fail(ctxs[0], MSGPU_ERR_ARGS, "unit outside the input/output buffer");
+        if (u.codec == MSGPU_CODEC_LZX && MSGPU_UNIT_REF_BYTES(&u) > u.out_off) return fail(ctxs[0], MSGPU_ERR_ARGS, "LZX DELTA reference data must lie in front of the unit inside the output buffer");
+    }
+    std::vector<int> rc((size_t) ndev, 0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++) {
+        th.emplace_back([&, d]() {
+            size_t lo = 0, hi = 0;
+            if (msgpu_shard_range(units, n, d, ndev, &lo, &hi) || hi == lo) return;
+            uint64_t i0 = ~0ull, i1 = 0, o0 = ~0ull, o1 = 0;
+            for (size_t i = lo; i < hi; i++) {
+                const msgpu_unit &u = units[i];
+                const uint64_t ob = u.out_off - (u.codec == MSGPU_CODEC_LZX ? MSGPU_UNIT_REF_BYTES(&u) : 0u);
+                if (u.in_off < i0) i0 = u.in_off;
+                if (u.in_off + u.in_len > i1) i1 = u.in_off + u.in_len;
+                if (ob < o0) o0 = ob;
+                if (u.out_off + u.out_len > o1) o1 = u.out_off + u.out_len;
+            }
+            i0 &= ~15ull; o0 &= ~15ull;                     /* keeps every unit's alignment (in: 4-byte loads, out: out_off % 16) */
+            std::vector<msgpu_unit> ru(units + lo, units + hi);
+            for (msgpu_unit &u : ru) { u.in_off -= i0; u.out_off -= o0; }
+            rc[(size_t) d] = msgpu_decode_batch_host(ctxs[d], ru.data(), ru.size(), reinterpret_cast<const uint8_t *>(h_in) + i0, (size_t) (i1 - i0),
+                                                     reinterpret_cast<uint8_t *>(h_out) + o0, (size_t) (o1 - o0), status ? status + lo : nullptr);
+        });
+    }
+    for (std::thread &t : th) t.join();
+    for (int d = 0; d < ndev; d++) if (rc[(size_t) d]) return rc[(size_t) d];
     return 0;
 }

@@ -210,11 +210,13 @@ def make_batch(codec: int, n: int, unit_bytes: int = FRAME, window_bits: int = 2
     padded = (l64 + 3) & ~3
     offs = np.concatenate([[0], np.cumsum(padded)[:-1]]) if n else np.zeros(0, dtype=np.int64)
     comp = np.zeros(int(padded.sum()) + 16, dtype=np.uint8)
-    # compact the slots (vectorised gather)
-    if n:
-        idx_unit = np.repeat(np.arange(n, dtype=np.int64), l64)
-        within = np.arange(int(l64.sum()), dtype=np.int64) - np.repeat(np.cumsum(l64) - l64, l64)
-        comp[np.repeat(offs, l64) + within] = comp_slots[idx_unit * slot + within]
+    # compact the slots (vectorised gather, a few thousand units at a time: the index arrays are 24 bytes per compressed byte)
+    for c0 in range(0, n, 4096):
+        c1 = min(n, c0 + 4096)
+        lc = l64[c0:c1]
+        idx_unit = np.repeat(np.arange(c0, c1, dtype=np.int64), lc)
+        within = np.arange(int(lc.sum()), dtype=np.int64) - np.repeat(np.cumsum(lc) - lc, lc)
+        comp[np.repeat(offs[c0:c1], lc) + within] = comp_slots[idx_unit * slot + within]
     units["codec"], units["window_bits"] = codec, window_bits
     units["reset_interval"] = reset_interval if codec == CODEC_LZX else 0
     units["in_off"], units["in_len"], units["out_len"] = offs, lens + np.uint32(slack), unit_bytes

@@ -47,6 +47,14 @@ class Oracle:
         self._batch.restype = ctypes.c_double
         self._batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_int]
+        self._decode_only = getattr(self.lib, pre + "_last_decode_only", None)      # (reference harness only)
+        if self._decode_only is not None:
+            self._decode_only.restype = ctypes.c_double
+            self._decode_only.argtypes = []
+
+    def last_decode_only_seconds(self):
+        """Seconds the slowest thread of the last decode_batch spent inside X_decompress (no X_init / X_free); None for the port."""
+        return float(self._decode_only()) if self._decode_only is not None else None
 
     def decode_batch(self, units: np.ndarray, in_bytes: np.ndarray, out_size: int | None = None,
                      threads: int = 1, out_init: np.ndarray | None = None):

@@ -64,6 +64,12 @@ static struct mspack_system mem_system = {
     NULL, NULL, &mem_read, &mem_write, NULL, NULL, &mem_msg, &mem_alloc, &mem_free, &mem_copy, NULL
 };
 
+/* time spent inside X_decompress alone (without X_init / X_free: lzxd_init allocates and the first touch of a 2 MiB window is
+ * a large part of a one-frame unit's cost on the CPU), per thread; bench.py reports it beside the init-inclusive figure */
+static __thread double t_decode_only;
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec; }
+#define TIMED(call) do { double t0_ = now_s(); call; t_decode_only += now_s() - t0_; } while (0)
+
 /* Decode one unit with the reference decoder.  Returns the reference's MSPACK_ERR_* code;
  * *produced receives the number of bytes the decoder wrote. */
 int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigned char *out_base,
@@ -83,8 +89,8 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
                                               (struct mspack_file *) &f, bufsize,
                                               (u->flags & MSGPU_FLAG_MSZIP_REPAIR) ? 1 : 0);
         if (!z) { err = MSPACK_ERR_NOMEMORY; break; }
-        if (u->flags & MSGPU_FLAG_MSZIP_KWAJ) err = mszipd_decompress_kwaj(z);       /* out_len is only the capacity (mem_write drops the rest) */
-        else err = mszipd_decompress(z, (off_t) u->out_len);
+        if (u->flags & MSGPU_FLAG_MSZIP_KWAJ) TIMED(err = mszipd_decompress_kwaj(z));       /* out_len is only the capacity (mem_write drops the rest) */
+        else TIMED(err = mszipd_decompress(z, (off_t) u->out_len));
         mszipd_free(z);
         break;
     }
@@ -92,7 +98,7 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
         struct qtmd_stream *q = qtmd_init(&mem_system, (struct mspack_file *) &f,
                                           (struct mspack_file *) &f, u->window_bits, 4096);
         if (!q) { err = MSPACK_ERR_NOMEMORY; break; }
-        err = qtmd_decompress(q, (off_t) u->out_len);
+        TIMED(err = qtmd_decompress(q, (off_t) u->out_len));
         qtmd_free(q);
         break;
     }
@@ -111,7 +117,7 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
             err = lzxd_set_reference_data(l, &mem_system, (struct mspack_file *) &rf, ref_len);
             if (err) { lzxd_free(l); break; }
         }
-        err = lzxd_decompress(l, (off_t) u->out_len);
+        TIMED(err = lzxd_decompress(l, (off_t) u->out_len));
         lzxd_free(l);
         break;
     }
@@ -124,15 +130,21 @@ int oracle_ref_decode(const msgpu_unit *u, const unsigned char *in_base, unsigne
 struct batch_job {
     const msgpu_unit *units; size_t lo, hi;
     const unsigned char *in_base; unsigned char *out_base; int32_t *status;
+    double decode_only;
 };
+static double g_last_decode_only;
+/* seconds the slowest thread of the most recent oracle_ref_decode_batch call spent inside X_decompress */
+double oracle_ref_last_decode_only(void) { return g_last_decode_only; }
 
 static void *batch_worker(void *arg) {
     struct batch_job *j = (struct batch_job *) arg;
     size_t i;
+    t_decode_only = 0.0;
     for (i = j->lo; i < j->hi; i++) {
         int e = oracle_ref_decode(&j->units[i], j->in_base, j->out_base, NULL);
         if (j->status) j->status[i] = e;
     }
+    j->decode_only = t_decode_only;
     return NULL;
 }
 
@@ -159,6 +171,8 @@ double oracle_ref_decode_batch(const msgpu_unit *units, size_t n, const unsigned
     }
     if (threads > 1) for (t = 0; t < threads; t++) pthread_join(tid[t], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    g_last_decode_only = 0.0;
+    for (t = 0; t < threads; t++) if (jobs[t].decode_only > g_last_decode_only) g_last_decode_only = jobs[t].decode_only;
     free(tid); free(jobs);
     return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }

@@ -157,3 +157,31 @@ def test_host_call_writes_only_unit_bytes(decoder, oracle_ref, n, unit_bytes):
         owned[int(u["out_off"]):int(u["out_off"]) + int(u["out_len"])] = True
     assert (~owned).any()
     assert (out_g[~owned] == 0xA5).all(), "bytes outside every unit were overwritten"
+
+
+def test_multi_device_host_call(oracle_ref):
+    """msgpu_decode_batch_host_multi: one batch, host buffers, every visible device (two contexts on the one device of a 1-GPU box
+    - the sharding, re-basing and threading are the same): mixed codecs, ragged units, LZX DELTA reference data, an MSZIP chain
+    across the shard boundary; output and status equal the oracle's, bytes outside the units untouched."""
+    import torch
+    from libmspack_b200.sharding import MultiDecoder
+    from util import chain_batch
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0]
+    chain, plain, raws = chain_batch([32768 * 9 + 5])
+    parts = [gen.make_batch(CODEC_LZX, 300, unit_bytes=40001), chain, gen.make_batch(CODEC_QUANTUM, 100, unit_bytes=9000, first_unit=700),
+             gen.make_batch(CODEC_LZX, 40, window_bits=17, unit_bytes=50000, delta=1, ref_bytes=20000, first_unit=900), gen.make_batch(CODEC_MSZIP, 301, unit_bytes=5003)]
+    m = gen.concat_batches(parts)
+    md = MultiDecoder(devices)
+    try:
+        init = m.out_init.copy() if m.out_init is not None else np.zeros(m.out_bytes, np.uint8)
+        out_g, st_g = md.decode_host(m.units, m.comp, m.out_bytes, out_init=init)
+        assert md.launches > 0
+    finally:
+        md.close()
+    pm = gen.concat_batches([parts[0], plain, parts[2], parts[3], parts[4]])       # the chain as ONE plain unit: what the reference decodes
+    out_o, st_o, _ = oracle_ref.decode_batch(pm.units, pm.comp, pm.out_bytes, threads=8, out_init=pm.out_init)
+    assert (st_g == 0).all() and (st_o == 0).all()
+    for u in pm.units:
+        lo, n = int(u["out_off"]), int(u["out_len"])
+        assert np.array_equal(out_g[lo:lo + n], out_o[lo:lo + n])

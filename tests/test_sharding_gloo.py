@@ -52,3 +52,25 @@ def test_two_rank_sharding_equals_single_process():
     assert (st == 0).all()
     assert b"".join(r[3] for r in res) == ref.tobytes()
     assert all(r[4] == n for r in res)
+
+
+def test_shard_ranges_cover_the_batch_and_keep_chains_whole():
+    """msgpu_shard_range (the split msgpu_decode_batch_host_multi and bench.py's ranks use): the shards tile [0, n) in order for any
+    shard count, equal floor(r n / R) without chains, and never start on a CHAIN_NEXT unit."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from libmspack_b200 import gen
+    from libmspack_b200.sharding import shard_range
+    from libmspack_b200.units import CODEC_MSZIP
+    from util import chain_batch
+    b = gen.make_batch(CODEC_MSZIP, 101, unit_bytes=2000)
+    for world in (1, 2, 3, 8, 64):
+        rs = [shard_range(b.n, r, world, b.units) for r in range(world)]
+        assert rs == [shard_range(b.n, r, world) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == b.n and all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+    chain, _, _ = chain_batch([32768 * 5 + 100, 32768 * 3, 32768 * 7 + 1])
+    for world in (2, 3, 5):
+        rs = [shard_range(chain.n, r, world, chain.units) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == chain.n and all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        for lo, hi in rs:
+            assert lo == chain.n or not (int(chain.units["flags"][lo]) & 0x8), (world, lo)
