@@ -134,6 +134,24 @@ int msgpu_decode_batch_host(msgpu_ctx *ctx, const msgpu_unit *units, size_t n,
                             const void *h_in, size_t in_bytes,
                             void *h_out, size_t out_bytes, int32_t *status);
 
+/* Output sinks on the device: a digest of every unit's decoded bytes instead of the bytes.  The reference's own
+ * tests verify extraction this way (test/md5_fh.h:72-77 + cabd_test.c:472-478: MD5 of what cabd writes; oabd.c:98: running CRC-32,
+ * mspack/crc32.h); for a caller that only verifies, the device-to-host copy of the output - what bounds msgpu_decode_batch_host -
+ * shrinks to 16 / 4 bytes per unit.
+ *   MSGPU_DIGEST_MD5    16 bytes per unit (RFC 1321, as printed by md5sum)
+ *   MSGPU_DIGEST_CRC32  4 bytes per unit, little-endian: crc32(0xFFFFFFFF, data, len) ^ 0xFFFFFFFF in the terms of mspack/crc32.h (= zlib's)
+ * A unit whose status is nonzero gets an all-zero digest (its bytes are unspecified).
+ *   msgpu_digest_device             digests of units already decoded in device memory (d_status may be NULL = digest every unit);
+ *                                   queued on `stream` like msgpu_decode_batch_device
+ *   msgpu_decode_batch_host_digest  msgpu_decode_batch_host without the output copy: compressed bytes in, digests + status out
+ *                                   (the output lives in the context's own device buffer; not for LZX DELTA units with reference data) */
+#define MSGPU_DIGEST_MD5   1
+#define MSGPU_DIGEST_CRC32 2
+int msgpu_digest_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_out, size_t out_bytes, const int32_t *d_status,
+                        int kind, void *d_digest, void *stream);
+int msgpu_decode_batch_host_digest(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *h_in, size_t in_bytes, size_t out_bytes,
+                                   int kind, void *h_digest, int32_t *status);
+
 /* Several GPUs, one call.  Units are independent, so devices share a batch by unit index with no exchange step (the reference's
  * unit of independence: a CAB folder, cabd.c:1142-1177; a CHM reset interval, chmd.c:1146-1186):
  *   msgpu_shard_range            shard `shard` of `nshards` owns units [*lo, *hi) = [floor(shard n / nshards), floor((shard + 1) n /
@@ -161,7 +179,8 @@ float msgpu_last_kernel_ms(msgpu_ctx *ctx);
 
 /* Stage timing (measurement aid): when on, the stages of the next batches run back to back on one stream,
  * each launch bracketed by CUDA events; msgpu_stage_ms(ctx, stage) then returns the summed duration of
- * stage 0 = P1 entropy kernels, 1 = P2 resolve kernel, 2 = E8 kernel for the most recent batch. */
+ * stage 0 = P1 entropy kernels, 1 = P2 resolve kernels (LZX: including the E8 call translation, their epilogue) for the most
+ * recent batch; stage 2 (the separate E8 kernel of round 1) no longer exists and reads 0. */
 int   msgpu_set_stage_timing(msgpu_ctx *ctx, int on);
 float msgpu_stage_ms(msgpu_ctx *ctx, int stage);
 

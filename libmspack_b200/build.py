@@ -39,7 +39,8 @@ def build_msgpu(force: bool = False) -> str:
     so = os.path.join(PKG, "libmsgpu.so")
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "msgpu.h"), os.path.join(ROOT, "include", "msgpu_cab.h"), os.path.join(ROOT, "include", "msgpu_chm.h")]
     if force or _newer(so, srcs):
-        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-o", so, os.path.join(CSRC, "msgpu.cu"), os.path.join(CSRC, "msgpu_cab.cu"), os.path.join(CSRC, "msgpu_chm.cu")])
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-o", so, os.path.join(CSRC, "msgpu.cu"), os.path.join(CSRC, "msgpu_cab.cu"), os.path.join(CSRC, "msgpu_chm.cu"),
+                                                               os.path.join(CSRC, "msgpu_digest.cu")])
     return so
 
 

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
     "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
     "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version", "msgpu_last_produced",
-    "msgpu_shard_range", "msgpu_decode_batch_host_multi",
+    "msgpu_shard_range", "msgpu_decode_batch_host_multi", "msgpu_digest_device", "msgpu_decode_batch_host_digest",
 ]
 
 _lib = None
@@ -51,6 +51,10 @@ def load_library() -> ctypes.CDLL:
     lib.msgpu_decode_batch_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32p]
     lib.msgpu_last_produced.restype = ctypes.c_int
     lib.msgpu_last_produced.argtypes = [vp, vp, sz]
+    lib.msgpu_digest_device.restype = ctypes.c_int
+    lib.msgpu_digest_device.argtypes = [vp, vp, sz, vp, sz, vp, ctypes.c_int, vp, vp]
+    lib.msgpu_decode_batch_host_digest.restype = ctypes.c_int
+    lib.msgpu_decode_batch_host_digest.argtypes = [vp, vp, sz, vp, sz, sz, ctypes.c_int, vp, i32p]
     lib.msgpu_shard_range.restype = ctypes.c_int
     lib.msgpu_shard_range.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
     lib.msgpu_decode_batch_host_multi.restype = ctypes.c_int
@@ -137,6 +141,28 @@ class BatchDecoder:
                                               out.ctypes.data, out_bytes, status.ctypes.data)
         self._check(rc)
         return out[:out_bytes], status
+
+    def decode_host_digest(self, units: np.ndarray, comp: np.ndarray, out_bytes: int, kind: int = 1):
+        """Host buffers in, per-unit digests out (kind 1 = MD5: uint8[n, 16]; 2 = CRC-32: uint32[n]); the output stays on the device."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        dig = np.zeros((len(units), 16), dtype=np.uint8) if kind == 1 else np.zeros(len(units), dtype=np.uint32)
+        status = np.full(len(units), -1, dtype=np.int32)
+        self._check(self.lib.msgpu_decode_batch_host_digest(self.ctx, units.ctypes.data, len(units), comp.ctypes.data, comp.size, out_bytes, kind,
+                                                            dig.ctypes.data, status.ctypes.data))
+        return dig, status
+
+    def decode_host_digest_into(self, units: np.ndarray, comp_ptr: int, comp_bytes: int, out_bytes: int, kind: int, dig: np.ndarray, status: np.ndarray):
+        self._check(self.lib.msgpu_decode_batch_host_digest(self.ctx, units.ctypes.data, len(units), ctypes.c_void_p(comp_ptr), comp_bytes, out_bytes, kind,
+                                                            dig.ctypes.data, status.ctypes.data))
+
+    def digest_device(self, units: np.ndarray, d_out, kind: int, d_digest, d_status=None, stream=None) -> None:
+        """Digests of units already decoded into the CUDA tensor d_out; d_digest: uint8 CUDA tensor of n * 16 (MD5) / n * 4 (CRC-32) bytes."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self.lib.msgpu_digest_device(self.ctx, units.ctypes.data, len(units), ctypes.c_void_p(d_out.data_ptr()), d_out.numel(),
+                                                 ctypes.c_void_p(d_status.data_ptr()) if d_status is not None else None, kind,
+                                                 ctypes.c_void_p(d_digest.data_ptr()), sp))
 
     def last_produced(self, n: int) -> np.ndarray:
         """Bytes each unit of the most recent (single-wave) batch produced - the way to learn a KWAJ unit's size."""

@@ -4,7 +4,7 @@
  *     repeat until every unit of the wave is done:
  *         k_p1_<codec>   one thread per unit : bitstream -> literals + match records, F frames per launch
  *         k_p2_resolve   one warp per unit   : records -> output bytes (16-byte stores)
- *     k_e8               one warp per LZX unit : E8 call translation of finished frames
+ *                        (+ for LZX units the E8 call translation, once a unit's last frame is resolved)
  *     k_status           per-unit MSPACK_ERR_* out
  * There is no CPU path: without a CUDA device msgpu_create() fails.
  */
@@ -45,7 +45,11 @@ __device__ __forceinline__ void p1_run(Lane &t)
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
-        if (!m0) break;
+        if (!m0) {
+            if (!MS_BALLOT(t.phase == PH_PARK)) break;
+            if (t.phase == PH_PARK) t.phase = PH_FRAME | 0x100u;      /* nobody decodes: the parked lanes start their frames together (msgpu_core.cuh PH_PARK) */
+            continue;
+        }
         do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
     }
 }
@@ -126,10 +130,16 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
 #else
 #define P2_BOUNDS __launch_bounds__(P2_WARPS * 32)
 #endif
-template <bool WIDE>
-__global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots)
+/* e8info / e8base (LZX lists only, else NULL): the E8 call translation of lzxd.c:706-737 as the resolve stage's epilogue.  The
+ * reference translates a COPY of each frame because later matches must see the untranslated bytes; here the unit's warp runs the
+ * translation once the unit's last frame has been resolved - nothing reads those bytes as match sources any more - while they
+ * are still in L1 / L2, instead of a separate kernel over the whole batch. */
+template <bool WIDE, bool BULK = false>
+__global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots, const int32_t *e8info, const uint32_t *e8base)
 {
-    __shared__ uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];
+    __shared__ __align__(16) uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];      /* BULK: s_wa[w] .. s_wb[w] is not contiguous - it uses s_w2 */
+    __shared__ __align__(16) uint32_t s_w2[BULK ? P2_WARPS : 1][BULK ? 2 * P2_WIN : 4];
+    __shared__ __align__(8) uint64_t s_mbar[P2_WARPS];
     __shared__ uint32_t s_src[P2_WARPS][P2_SRC_WORDS];
     __shared__ uint32_t s_longq[P2_WARPS][P2_LONG_MAX + 1];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,11 +148,28 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
     uint32_t slot = slots[si];
     uint8_t *unit_out = a.out_base + a.units[slot].out_off;
     const uint32_t ref_len = (WIDE && a.units[slot].codec == MSGPU_CODEC_LZX) ? MSGPU_UNIT_REF_BYTES(&a.units[slot]) : 0u;
+    uint32_t mphase = 0;
+    if (BULK) { if (lane == 0) p2_mbar_init(&s_mbar[warp]); __syncwarp(); }
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
+        if (BULK) p2_resolve_frame<WIDE, false, false, true>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+                               s_w2[BULK ? warp : 0], s_w2[BULK ? warp : 0] + 1, s_src[warp], s_longq[warp], ref_len, nullptr, nullptr, &s_mbar[warp], &mphase);
+        else
         p2_resolve_frame<WIDE, false, false>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
+    }
+    if (e8info && a.ustate[slot].done && !a.ustate[slot].pad[0]) {          /* (pad[0]: translated - a finished unit may see further launch rounds) */
+        const msgpu_unit u = a.units[slot];
+        const uint32_t produced = a.ustate[slot].produced, nfr = (u.out_len + MS_FRAME - 1) / MS_FRAME;
+        __syncwarp();
+        for (uint32_t f = 0; f < nfr; f++) {
+            const uint32_t start = f * MS_FRAME, size = u.out_len - start < MS_FRAME ? u.out_len - start : MS_FRAME;
+            if (start + size > produced) break;
+            const int32_t fs = e8info[e8base[si] + f];
+            if (fs) e8_translate_frame(lane, unit_out + start, size, (int32_t) (start + MSGPU_UNIT_FRAME_BASE(&u) * MS_FRAME), fs);      /* curpos = the STREAM offset (lzx->offset) */
+        }
+        if (lane == 0) a.ustate[slot].pad[0] = 1u;
     }
 }
 
@@ -198,22 +225,6 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_chain(WaveArgs a, const ui
         p2_resolve_frame<true>(lane, a.recs + (size_t) slot * a.F * MS_MAXREC, fi.nrec, fi.size, a.out_base + a.units[slot].out_off, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], k ? MS_FRAME : 0u);
         __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(256) k_e8(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, const int32_t *e8info, const uint32_t *e8base)
-{
-    uint32_t ti = first + blockIdx.x * 8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
-    if (ti >= count) return;
-    uint32_t slot = order[ti];
-    const msgpu_unit u = a.units[slot];
-    uint32_t produced = a.ustate[slot].produced, nfr = (u.out_len + MS_FRAME - 1) / MS_FRAME;
-    uint8_t *unit_out = a.out_base + u.out_off;
-    for (uint32_t f = 0; f < nfr; f++) {
-        uint32_t start = f * MS_FRAME, size = u.out_len - start < MS_FRAME ? u.out_len - start : MS_FRAME;
-        if (start + size > produced) break;
-        int32_t fs = e8info[e8base[ti] + f];
-        if (fs) e8_translate_frame(lane, unit_out + start, size, (int32_t) (start + MSGPU_UNIT_FRAME_BASE(&u) * MS_FRAME), fs);      /* curpos = the STREAM offset (lzx->offset) */
     }
 }
 
@@ -277,14 +288,15 @@ struct msgpu_ctx {
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
-    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains;
+    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains, dig_units, dig_out;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
+    int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
         return units.cap + ustate.cap + recs.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
-               save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap + chains.cap;
+               save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap + chains.cap + dig_units.cap + dig_out.cap;
     }
 };
 
@@ -317,6 +329,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     cudaMemGetInfo(&free_b, &total_b);
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
+    { const char *v = getenv("MSGPU_P2_BULK"); c->p2_bulk = v ? atoi(v) : 1; }
     /* the entropy kernels use most of an SM's shared memory: opt in */
     cudaError_t ae = cudaSuccess;
 #define SETA(kernel, bytes) { cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)); if (e_ != cudaSuccess) ae = e_; }
@@ -335,7 +348,7 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
-                       &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status, &c->chains };
+                       &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status, &c->chains, &c->dig_units, &c->dig_out };
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -516,7 +529,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
-    const bool hostpipe = h_in && h_out && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above */
+    const bool hostpipe = h_in && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above (h_out may be absent: msgpu_decode_batch_host_digest) */
     const int NS = (nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : 3) : 1;
     auto kstream = [&](uint32_t sub) { return NS == 1 ? s : ctx->sub[sub % (uint32_t) NS]; };
     if (hostpipe) {
@@ -536,8 +549,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     /* Output ranges of a sub-wave's units, sorted and merged where they touch: the host-buffer call may only write the bytes units
      * own ([out_off, out_off + out_len)), never the gaps between them (the 16-byte alignment of out_off leaves gaps after ragged
-     * units).  A sub-wave whose units leave more than MAXR separate ranges is handled the other way round: the caller's bytes of
-     * the whole span are copied IN first (`prime`), so that the one copy out returns them unchanged. */
+     * units).  A wave in which some sub-wave's units leave more than MAXR separate ranges (ragged or scattered units) is handled
+     * the other way round (`bulk_out`): the caller's bytes of the wave's whole span are copied IN before the first kernel starts,
+     * and ONE copy of that span after the last kernel returns them unchanged around the decoded units. */
     const size_t MAXR = 512;
     auto out_ranges = [&](const std::vector<uint32_t> &v, uint32_t f0, uint32_t f1, std::vector<std::pair<uint64_t, uint64_t>> &r) {
         r.clear();
@@ -560,20 +574,31 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             io_range(*lists[c], f0, f1, false, b0, b1);
             b0 &= ~3ull;                                   /* keep 4-byte loads of the first unit inside the copied range */
             if (b1 > b0) cudaMemcpyAsync(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(d_in)) + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, st);
-            if (h_out) {
-                out_ranges(*lists[c], f0, f1, rng);
-                if (rng.size() > MAXR) cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + rng.front().first, h_out + rng.front().first, rng.back().second - rng.front().first, cudaMemcpyHostToDevice, st);      /* prime */
-            }
         }
     };
+    bool bulk_out = false; uint64_t wave_o0 = ~0ull, wave_o1 = 0;
+    if (h_out) {
+        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
+        for (uint32_t sub = 0; sub < nsub && !bulk_out; sub++)
+            for (int c = 0; c < 3 && !bulk_out; c++) {
+                uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt;
+                if (f0 >= cnt) continue;
+                out_ranges(*lists[c], f0, f1, rng);
+                if (rng.size() > MAXR) bulk_out = true;
+            }
+        if (bulk_out) {
+            for (uint32_t i = 0; i < n; i++) { const msgpu_unit &u = h_units[lo + i]; if (!u.out_len) continue; if (u.out_off < wave_o0) wave_o0 = u.out_off; if (u.out_off + u.out_len > wave_o1) wave_o1 = u.out_off + u.out_len; }
+            if (wave_o1 > wave_o0)      /* prime: queued behind ev_fork on the first stream anything of this wave runs on, in front of every kernel */
+                cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + wave_o0, h_out + wave_o0, wave_o1 - wave_o0, cudaMemcpyHostToDevice, hostpipe ? ctx->cp_in : s);
+        }
+    }
     auto copy_out = [&](uint32_t sub, cudaStream_t st) {
-        if (!h_out) return;
+        if (!h_out || bulk_out) return;
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (int c = 0; c < 3; c++) {
             uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt;
             if (f0 >= cnt) continue;
             out_ranges(*lists[c], f0, f1, rng);
-            if (rng.size() > MAXR) { rng.front().second = rng.back().second; rng.resize(1); }      /* (primed by copy_in) */
             for (const auto &r : rng) cudaMemcpyAsync(h_out + r.first, reinterpret_cast<uint8_t *>(d_out) + r.first, r.second - r.first, cudaMemcpyDeviceToHost, st);
         }
     };
@@ -597,8 +622,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (e) { cudaEventRecord(e, st); ctx->stage_evs[stage].push_back(e); }
     };
     auto p2_launch = [&](const WaveArgs &w, const uint32_t *list, uint32_t f0, uint32_t f1, cudaStream_t st) {
-        if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
-        else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1);
+        const int32_t *e8i = list == d_ord_l ? reinterpret_cast<const int32_t *>(ctx->e8info.p) : nullptr;      /* LZX lists: E8 translation as the epilogue */
+        const uint32_t *e8b = list == d_ord_l ? reinterpret_cast<const uint32_t *>(ctx->e8base.p) : nullptr;
+        /* the record window comes through the copy engine (cp.async.bulk, msgpu_p2.cuh BULK): measured 5.33 against 6.19 ms for the
+         * headline batch (profiles/r2_p2_bulk_ab.txt); MSGPU_P2_BULK=0 keeps the load-by-lanes variant for A/B runs */
+        if (any_delta && ctx->p2_bulk) k_p2_resolve<true, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
+        else if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
+        else if (ctx->p2_bulk) k_p2_resolve<false, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
+        else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
     };
     auto launch_round = [&](uint32_t sub, cudaStream_t st) {
         uint32_t f0 = sub * subsz, f1;
@@ -626,12 +657,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_q, f0, f1, st); ctx->launches += 2; mark(1, st); }
     };
-    auto launch_tail = [&](uint32_t sub, cudaStream_t st) {
-        uint32_t f0 = sub * subsz, f1;
-        if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
-            mark(2, st);
-            k_e8<<<(f1 - f0 + 7) / 8, 256, 0, st>>>(a, d_ord_l, f0, f1, reinterpret_cast<const int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p)); ctx->launches++; mark(2, st); }
-    };
     for (uint32_t sub = 0; sub < nsub; sub++) {
         cudaStream_t st = kstream(sub);
         if (hostpipe) { copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[2 * sub], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(st, ctx->io_evs[2 * sub], 0), "stream wait"); }
@@ -640,7 +665,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (round + 1 == rounds_planned && any_zip) CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
             launch_round(sub, st);
         }
-        if (!any_zip) { launch_tail(sub, st); finish_out(sub, st); }
+        if (!any_zip) finish_out(sub, st);
     }
     CK(cudaGetLastError(), "kernel launch");
     if (any_zip) {
@@ -659,13 +684,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
         }
-        for (uint32_t sub = 0; sub < nsub; sub++) { launch_tail(sub, kstream(sub)); finish_out(sub, kstream(sub)); }
+        for (uint32_t sub = 0; sub < nsub; sub++) finish_out(sub, kstream(sub));
     }
     if (NS > 1) for (int i = 0; i < NS; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->sub[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[i], 0), "stream wait"); }
     if (hostpipe) {
         CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB], 0), "stream wait");
         CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB + 1], ctx->cp_out), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB + 1], 0), "stream wait");
     }
+    if (bulk_out && wave_o1 > wave_o0) CK(cudaMemcpyAsync(h_out + wave_o0, reinterpret_cast<uint8_t *>(d_out) + wave_o0, wave_o1 - wave_o0, cudaMemcpyDeviceToHost, s), "copy out");
     if (d_status) { k_status<<<(n + 255) / 256, 256, 0, s>>>(a.ustate, n, d_status + lo); ctx->launches++; }
     CK(cudaEventRecord(ev1, s), "event");
     ctx->ev_used += 2;
@@ -819,5 +845,56 @@ extern "C" int msgpu_decode_batch_host_multi(msgpu_ctx *const *ctxs, int ndev, c
     }
     for (std::thread &t : th) t.join();
     for (int d = 0; d < ndev; d++) if (rc[(size_t) d]) return rc[(size_t) d];
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ output sinks (msgpu_digest.cu) */
+extern "C" cudaError_t msgpu_launch_digest(int kind, const msgpu_unit *d_units, const uint8_t *d_out, uint32_t n, const int32_t *d_status, uint8_t *d_digest, cudaStream_t s);
+
+extern "C" int msgpu_digest_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_out, size_t out_bytes, const int32_t *d_status,
+                                   int kind, void *d_digest, void *stream)
+{
+    if (!ctx) return MSGPU_ERR_ARGS;
+    ctx->err.clear();
+    if (n == 0) return 0;
+    if (!units || !d_out || !d_digest || (kind != MSGPU_DIGEST_MD5 && kind != MSGPU_DIGEST_CRC32) || n > 0x7FFFFFFFull) return fail(ctx, MSGPU_ERR_ARGS, "bad argument");
+    for (size_t i = 0; i < n; i++) {
+        const msgpu_unit &u = units[i];
+        if (u.out_off > out_bytes || u.out_len > out_bytes - u.out_off || (u.out_off & 15u)) return fail(ctx, MSGPU_ERR_ARGS, "unit outside the output buffer");
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    CK(ctx->dig_units.reserve(n * sizeof(msgpu_unit)), "alloc units");
+    CK(cudaMemcpyAsync(ctx->dig_units.p, units, n * sizeof(msgpu_unit), cudaMemcpyHostToDevice, s), "copy units");
+    CK(msgpu_launch_digest(kind, reinterpret_cast<const msgpu_unit *>(ctx->dig_units.p), reinterpret_cast<const uint8_t *>(d_out), (uint32_t) n, d_status,
+                           reinterpret_cast<uint8_t *>(d_digest), s), "digest launch");
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int msgpu_decode_batch_host_digest(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *h_in, size_t in_bytes, size_t out_bytes,
+                                              int kind, void *h_digest, int32_t *status)
+{
+    if (!ctx) return MSGPU_ERR_ARGS;
+    ctx->err.clear();
+    if (n == 0) return 0;
+    if (!units || !h_in || !h_digest || (kind != MSGPU_DIGEST_MD5 && kind != MSGPU_DIGEST_CRC32)) return fail(ctx, MSGPU_ERR_ARGS, "bad argument");
+    for (size_t i = 0; i < n; i++)
+        if (units[i].codec == MSGPU_CODEC_LZX && MSGPU_UNIT_REF_BYTES(&units[i])) return fail(ctx, MSGPU_ERR_ARGS, "LZX DELTA reference data lives in the caller's output buffer: use msgpu_decode_batch_host");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MSGPU_ERR_ARGS, "cudaSetDevice failed");
+    cudaStream_t s = ctx->stream;
+    const size_t dsz = kind == MSGPU_DIGEST_MD5 ? 16 : 4;
+    CK(ctx->io_in.reserve(in_bytes + 64), "alloc input");
+    CK(ctx->io_out.reserve(out_bytes + 64), "alloc output");
+    CK(ctx->io_status.reserve(n * sizeof(int32_t)), "alloc status");
+    CK(ctx->dig_out.reserve(n * dsz), "alloc digests");
+    int r = decode_batch_impl(ctx, units, n, ctx->io_in.p, in_bytes, ctx->io_out.p, out_bytes, reinterpret_cast<int32_t *>(ctx->io_status.p), s,
+                              reinterpret_cast<const uint8_t *>(h_in), nullptr);
+    if (r) return r;
+    r = msgpu_digest_device(ctx, units, n, ctx->io_out.p, out_bytes, reinterpret_cast<const int32_t *>(ctx->io_status.p), kind, ctx->dig_out.p, s);
+    if (r) return r;
+    CK(cudaMemcpyAsync(h_digest, ctx->dig_out.p, n * dsz, cudaMemcpyDeviceToHost, s), "copy digests");
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "copy status");
+    CK(cudaStreamSynchronize(s), "sync");
     return 0;
 }

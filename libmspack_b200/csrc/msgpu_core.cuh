@@ -60,6 +60,14 @@ static inline uint32_t ms_brev32_host(uint32_t v) {
 #define PH_FRAME  2u      /* start the next frame */
 #define PH_BLOCK  3u      /* read the next block header / continue the frame */
 #define PH_END    4u      /* finish the current frame */
+#define PH_PARK   5u      /* at a frame start, waiting for the warp's decoding lanes (p1_run): see below */
+/* Frame boundaries and the warp.  A frame start is expensive for LZX and MSZIP (code-length tables are read and the canonical
+ * tables built: ~15 % of a frame's decode time), and the lanes of a warp reach the end of their frames at different times.  If
+ * every lane did its frame start the moment it got there, the other 31 lanes would sit through 32 table builds per frame instead
+ * of one: measured on 64 KiB CHM intervals (two frames per unit), P1 took 72 ms where two frames' worth of one-frame units take
+ * 34 ms.  So a lane that reaches a frame start PARKS until no lane of its warp is decoding any more, and the parked lanes then
+ * build their tables together, converged.  A lane waits at most for the slowest lane's current run, once per frame - the warp
+ * finishes with its slowest lane anyway. */
 
 #define MS_FRAME      32768u
 #define MS_MAXREC     16400u     /* matches per frame <= 32768/2, + sentinel, padded            */

@@ -401,8 +401,9 @@ struct LzxLaneC {
 
     MS_M void service() {
 #pragma unroll 1
-        while (phase >= PH_FRAME) {
-            if (phase == PH_FRAME) frame_start();
+        while (phase >= PH_FRAME && phase != PH_PARK) {
+            if (phase == PH_FRAME) phase = PH_PARK;                   /* wait for the warp (msgpu_core.cuh PH_PARK) */
+            else if (phase == (PH_FRAME | 0x100u)) frame_start();
             else if (phase == PH_BLOCK) next_run();
             else frame_end();
         }

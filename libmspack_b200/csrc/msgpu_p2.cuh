@@ -83,14 +83,14 @@ MS_D void p2_pass_a_literals(uint32_t q0, uint32_t c, uint32_t *src) {
  * data) are queued in shared memory and filled by all 32 lanes together.  longq[0] = count, longq[1..] = window indices.
  * Returns the first window index this lane saw whose match ends beyond cend (P2_WIN if none): the minimum over the warp is
  * the next chunk's r_lo. */
-template <bool WIDE>
+template <bool WIDE, int WS = 1>      /* WS: words between two records of the window (2: records as they lie in memory, wb = wa + 1) */
 MS_D int p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb,
                            uint32_t *src, uint32_t *longq)
 {
     int next_lo = P2_WIN;
 #pragma unroll 1
     for (int r = r_lo + lane; r < P2_WIN; r += 32) {
-        uint32_t a = wa[r], pos = rec_pos(a), b = wb[r], off = rec_off_w<WIDE>(a, b), len = rec_len(b), end = pos + len;
+        uint32_t a = wa[r * WS], pos = rec_pos(a), b = wb[r * WS], off = rec_off_w<WIDE>(a, b), len = rec_len(b), end = pos + len;
         if (pos >= cend) { if (next_lo == P2_WIN) next_lo = r; break; }               /* (the sentinel has pos >= size >= cend) */
         if (end > cend && next_lo == P2_WIN) next_lo = r;
         uint32_t p = pos > c ? pos : c, p1 = end < cend ? end : cend;
@@ -116,14 +116,14 @@ MS_D int p2_pass_a_records(int lane, int r_lo, uint32_t c, uint32_t cend, const 
     return next_lo;
 }
 /* Pass A, step 3: the queued long matches, all lanes together (call after a warp sync) */
-template <bool WIDE>
+template <bool WIDE, int WS = 1>
 MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src, const uint32_t *longq)
 {
     uint32_t nl = longq[0] < P2_LONG_MAX ? longq[0] : P2_LONG_MAX;
 #pragma unroll 1
     for (uint32_t i = 0; i < nl; i++) {
         int r = (int) longq[1 + i];
-        uint32_t a = wa[r], pos = rec_pos(a), b = wb[r], off = rec_off_w<WIDE>(a, b), len = rec_len(b);
+        uint32_t a = wa[r * WS], pos = rec_pos(a), b = wb[r * WS], off = rec_off_w<WIDE>(a, b), len = rec_len(b);
         uint32_t p0 = pos > c ? pos : c, p1 = pos + len < cend ? pos + len : cend;
 #pragma unroll 1
         for (uint32_t p = p0 + (uint32_t) lane; p < p1; p += 32) src[P2_SIDX(p - c)] = p2_desc<WIDE>(p, pos, off, len);
@@ -175,15 +175,53 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 /* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-template <bool WIDE, bool RING = false, bool PLANE = false>
+/* BULK: the record window is filled by the copy engine (cp.async.bulk into shared memory, completion on an mbarrier) instead of
+ * nine 8-byte loads per lane; the chunk's literal descriptors are written while the copy is in flight.  The window then holds the
+ * records as they lie in memory (wa = window, wb = wa + 1, stride 2) and starts at an even record index (16-byte source alignment). */
+#if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
+__device__ __forceinline__ uint32_t p2_smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void p2_mbar_init(uint64_t *mbar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(p2_smem_addr(mbar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void p2_bulk_load(void *dst, const void *gsrc, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* earlier generic-proxy reads of the window are done before the async proxy overwrites it */
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(p2_smem_addr(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(p2_smem_addr(dst)), "l"(gsrc), "r"(bytes), "r"(p2_smem_addr(mbar)) : "memory");
+}
+__device__ __forceinline__ void p2_mbar_wait(uint64_t *mbar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(p2_smem_addr(mbar)), "r"(parity) : "memory");
+}
+#endif
+template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
-                                                 const uint8_t *plane = nullptr)
+                                                 const uint8_t *plane = nullptr, uint64_t *mbar = nullptr, uint32_t *mphase = nullptr)
 {
+    constexpr int WS = BULK ? 2 : 1;
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     int r_lo = 0;                                              /* first window record ending beyond the chunk start */
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
-        if (!loaded || (c + P2_CHUNK > wcover && wcover < size)) {
+        const bool reload = !loaded || (c + P2_CHUNK > wcover && wcover < size);
+        uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
+        const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
+        if (BULK) {
+            uint32_t cnt = 0;
+            if (reload) {
+                wbase += (uint32_t) r_lo; r_lo = (int) (wbase & 1u); wbase &= ~1u;      /* (16-byte aligned source) */
+                cnt = MS_MAXREC - wbase < (uint32_t) P2_WIN ? MS_MAXREC - wbase : (uint32_t) P2_WIN;
+                __syncwarp();
+                if (lane == 0) p2_bulk_load(wa, recs + wbase, cnt * 8u, mbar);
+            }
+            if (lane == 0) longq[0] = 0;
+            p2_pass_a_literals<WIDE>(q0, c, src);             /* (the copy is in flight) */
+            if (reload) {
+                p2_mbar_wait(mbar, *mphase & 1u); *mphase += 1u;
+                for (int j = lane; j < P2_WIN; j += 32) if (wbase + (uint32_t) j > nrec || (uint32_t) j >= cnt) { wa[2 * j] = size; wa[2 * j + 1] = 0; }   /* behind the sentinel: sentinels */
+                __syncwarp();
+                wcover = rec_pos(wa[2 * (P2_WIN - 1)]); loaded = true;
+            }
+        }
+        else {
+        if (reload) {
             wbase += (uint32_t) r_lo; r_lo = 0;
             __syncwarp();
             for (int j = lane; j < P2_WIN; j += 32) {
@@ -193,15 +231,14 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
             __syncwarp();
             wcover = rec_pos(wa[P2_WIN - 1]); loaded = true;
         }
-        uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
-        const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         if (lane == 0) longq[0] = 0;
         p2_pass_a_literals<WIDE>(q0, c, src);
+        }
         __syncwarp();
-        int nlo = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa, wb, src, longq);
+        int nlo = p2_pass_a_records<WIDE, WS>(lane, r_lo, c, cend, wa, wb, src, longq);
         r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);            /* also orders the descriptor stores (it is a warp sync) */
         __syncwarp();
-        p2_pass_a_long<WIDE>(lane, c, cend, wa, wb, src, longq);
+        p2_pass_a_long<WIDE, WS>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
         p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
         uint8_t *dst = unit_out + (size_t) g0 + q0;

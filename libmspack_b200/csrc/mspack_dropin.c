@@ -53,6 +53,7 @@ struct dstream {                     /* common state; the three public stream ty
     unsigned char *out; size_t out_cap;  /* decoded prefix [0, out_len) at out + out_base */
     size_t out_len;
     int tail_status;                 /* nonzero: the stream fails right behind out_len with this MSPACK_ERR_* (everything decodable is decoded) */
+    int ahead_failed;                /* the decode-ahead ended in an error: requests behind its prefix are decoded exactly (see ds_decompress) */
 };
 
 /* All buffers come from the caller's mspack_system, as the reference's do (lzxd.c:308-314, mspack.h:399-420); there is no realloc
@@ -90,18 +91,24 @@ static void ds_free(struct dstream *s) {
  * the stream here: cabd_sys_read returns -1 for a CFDATA block with a bad checksum or a missing next cabinet (cabd.c:1322-1324),
  * and the reference, which pulls input as it decodes, still extracts every file that lies in front of that block.  So the bytes
  * read so far are kept, the input simply ends there, and the decoder reports MSPACK_ERR_READ when - and only when - a request
- * reaches the missing bytes (msgpu_cab.cu cuts a folder's input in front of its first bad block the same way). */
+ * reaches the missing bytes (msgpu_cab.cu cuts a folder's input in front of its first bad block the same way).
+ * Every read() asks for input_buffer_size bytes, exactly like the reference's read_input (readbits.h:192-214): cabd_sys_read
+ * fails a WHOLE call that runs into a bad block, including the good bytes it had already copied for it, so which bytes the
+ * decoder ever gets to see depends on the size of the reads - with the reference's sequence of calls the input ends where the
+ * reference's ends. */
 static int ds_slurp(struct dstream *s) {
+    const int chunk = s->bufsize > 0 ? s->bufsize : 4096;
     if (s->in_done) return MSPACK_ERR_OK;
     for (;;) {
         int got;
-        if (s->in_len + 65536 > s->in_cap) {
+        if (s->in_len + (size_t) chunk > s->in_cap) {
             size_t ncap = s->in_cap ? s->in_cap * 2 : (1u << 18);
+            while (ncap < s->in_len + (size_t) chunk) ncap *= 2;
             unsigned char *p = ds_grow(s, s->in, s->in_len, ncap);
             if (!p) return MSPACK_ERR_NOMEMORY;
             s->in = p; s->in_cap = ncap;
         }
-        got = s->sys->read(s->input, s->in + s->in_len, 65536);
+        got = s->sys->read(s->input, s->in + s->in_len, chunk);
         if (got < 0) { s->read_failed = 1; break; }
         if (got == 0) break;
         s->in_len += (size_t) got;
@@ -151,10 +158,17 @@ static int ds_decompress(struct dstream *s, off_t out_bytes) {
     end = (size_t) (s->offset + out_bytes);
     while (end > s->out_len) {
         size_t cap;
-        if (s->tail_status) return s->error = s->tail_status;      /* everything that decodes is decoded: the request reaches the failing frame */
-        /* how far to decode: the whole unit where its length is known (LZX, once cabd has announced it: cabd.c:1335-1340); otherwise
-         * a generous multiple of the input (a CAB folder's MSZIP / Quantum data), four times the last try if that was not enough.
-         * Decoding "too far" is harmless: the stream ends with an error behind its last frame, which is what tail_status records. */
+        if (s->ahead_failed) {
+            /* The decode-ahead stopped in front of this request: at a frame that really fails, or at a stream's SHORT LAST FRAME - a
+             * Quantum / LZX frame only counts as decoded when all of it is, and asking for more bytes than a stream holds fails the
+             * frame they would be in.  Decode exactly as far as the request reaches, like the reference does; what fails now fails. */
+            if ((e = ds_decode(s, end))) return s->error = e;
+            if (s->tail_status) return s->error = s->tail_status;
+            continue;
+        }
+        /* how far to decode ahead: the whole unit where its length is known (LZX, once cabd has announced it: cabd.c:1335-1340);
+         * otherwise a generous multiple of the input (a CAB folder's MSZIP / Quantum data), four times the last try if that was not
+         * enough.  Decoding "too far" is harmless: the stream ends with an error behind its last frame, which tail_status records. */
         if (s->codec == MSGPU_CODEC_LZX && s->length > 0 && (size_t) s->length >= end) cap = (size_t) s->length;
         else {
             cap = s->in_len * 8 + 4 * FRAME;
@@ -166,6 +180,7 @@ static int ds_decompress(struct dstream *s, off_t out_bytes) {
         if (cap > 0xFFFF0000u) cap = 0xFFFF0000u;
         if (cap < end) return s->error = MSPACK_ERR_DECRUNCH;
         if ((e = ds_decode(s, cap))) return s->error = e;
+        if (s->tail_status) s->ahead_failed = 1;
     }
     /* replay: exactly out_bytes more bytes to write() (mspack.h:346-355 write must return the count) */
     while (out_bytes > 0) {
@@ -189,7 +204,7 @@ struct lzxd_stream *lzxd_init(struct mspack_system *system, struct mspack_file *
     if (reset_interval > 0xFFFF) return NULL;
     s = ds_new(system, input, output, MSGPU_CODEC_LZX);
     if (!s) return NULL;
-    s->window_bits = window_bits; s->reset_interval = reset_interval; s->length = output_length; s->is_delta = is_delta ? 1 : 0;
+    s->window_bits = window_bits; s->reset_interval = reset_interval; s->length = output_length; s->is_delta = is_delta ? 1 : 0; s->bufsize = input_buffer_size;
     return (struct lzxd_stream *) s;
 }
 void lzxd_set_output_length(struct lzxd_stream *lzx, off_t out_bytes) {     /* lzxd.c:384-386 */
@@ -211,7 +226,7 @@ int lzxd_set_reference_data(struct lzxd_stream *lzx, struct mspack_system *syste
         bytes = system->read(input, s->ref, (int) length);
         if (bytes < (int) length) return MSPACK_ERR_READ;
     }
-    s->out_len = 0; s->tail_status = 0;                          /* anything decoded before used other reference data */
+    s->out_len = 0; s->tail_status = 0; s->ahead_failed = 0;     /* anything decoded before used other reference data */
     return MSPACK_ERR_OK;
 }
 int lzxd_decompress(struct lzxd_stream *lzx, off_t out_bytes) { return ds_decompress((struct dstream *) lzx, out_bytes); }
@@ -227,7 +242,7 @@ struct qtmd_stream *qtmd_init(struct mspack_system *system, struct mspack_file *
     if (input_buffer_size < 2) return NULL;
     s = ds_new(system, input, output, MSGPU_CODEC_QUANTUM);
     if (!s) return NULL;
-    s->window_bits = window_bits;
+    s->window_bits = window_bits; s->bufsize = input_buffer_size;
     return (struct qtmd_stream *) s;
 }
 int qtmd_decompress(struct qtmd_stream *qtm, off_t out_bytes) { return ds_decompress((struct dstream *) qtm, out_bytes); }

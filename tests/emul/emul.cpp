@@ -67,7 +67,11 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
     for (;;) {
         t.service();
         const uint32_t m0 = MS_BALLOT(t.phase == PH_DECODE);
-        if (!m0) break;
+        if (!m0) {
+            if (!MS_BALLOT(t.phase == PH_PARK)) break;
+            if (t.phase == PH_PARK) t.phase = PH_FRAME | 0x100u;
+            continue;
+        }
         do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
     }
 }

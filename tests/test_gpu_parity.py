@@ -185,3 +185,36 @@ def test_multi_device_host_call(oracle_ref):
     for u in pm.units:
         lo, n = int(u["out_off"]), int(u["out_len"])
         assert np.array_equal(out_g[lo:lo + n], out_o[lo:lo + n])
+
+
+def test_device_digest_sinks(decoder, oracle_ref):
+    """MD5 / CRC-32 of every unit's output computed on the device (msgpu_decode_batch_host_digest: no output copy)
+    equal hashlib.md5 / zlib.crc32 of the bytes the reference decodes - ragged sizes around MD5's 55 / 56 / 64-byte padding cases,
+    all three codecs, and a failing unit (all-zero digest, the reference's error code)."""
+    import zlib
+    for codec, sizes in ((CODEC_MSZIP, (1, 55, 56, 63, 64, 65, 119, 120, 4097, 32768, 40000)), (CODEC_LZX, (3, 57, 128, 9999, 32768, 70001)), (CODEC_QUANTUM, (5, 64, 5000))):
+        parts = [gen.make_batch(codec, 24, unit_bytes=s, first_unit=100 * k) for k, s in enumerate(sizes)]
+        m = gen.concat_batches(parts)
+        lo, nbad = int(m.units["in_off"][5]), int(m.units["in_len"][5])
+        m.comp = m.comp.copy(); m.comp[lo + nbad // 2:lo + nbad // 2 + 8] ^= 0xFF        # one damaged unit
+        out_o, st_o, _ = oracle_ref.decode_batch(m.units, m.comp, m.out_bytes, threads=8)
+        md5, st = decoder.decode_host_digest(m.units, m.comp, m.out_bytes, 1)
+        crc, st2 = decoder.decode_host_digest(m.units, m.comp, m.out_bytes, 2)
+        assert np.array_equal(st, st_o) and np.array_equal(st2, st_o)
+        for i, u in enumerate(m.units):
+            data = out_o[int(u["out_off"]):int(u["out_off"]) + int(u["out_len"])].tobytes()
+            if st_o[i]:
+                assert not md5[i].any() and crc[i] == 0
+            else:
+                assert md5[i].tobytes() == hashlib.md5(data).digest(), (codec, i)
+                assert int(crc[i]) == zlib.crc32(data), (codec, i)
+
+
+def test_device_digest_of_the_golden_vectors(decoder):
+    """The MD5s the reference's own test asserts (libmspack/test/cabd_test.c:472-478, tests/golden/manifest.json), computed on the device."""
+    for entry in golden_manifest():
+        if entry["err"]:
+            continue
+        u, comp = golden_unit(entry)
+        md5, st = decoder.decode_host_digest(u, comp, entry["out_len"], 1)
+        assert int(st[0]) == 0 and md5[0].tobytes().hex() == entry["md5"], entry["name"]
