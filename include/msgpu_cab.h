@@ -18,8 +18,13 @@
  * One folder = one unit of include/msgpu.h; all folders of the cabinet decode as one batch.  Folders with
  * compression type 0 ("none", cabd.c noned_*) are copied block by block by the gather kernel.
  *
- * Not handled (the scan reports them per folder as MSGPU_ERR_DATAFORMAT and decodes the rest): folders continued from /
- * into another cabinet of a set (cabd.c:1421-1452, CFFILE folder indices 0xFFFD-0xFFFF).  Salvage mode is not offered.
+ * Cabinet SETS (cabd.c:760-1002 append / cabd_merge, :1421-1452): msgpu_cab_scan_set() takes the set's cabinets in order and
+ * merges a folder that is continued in the next cabinet with its continuation - CFFILE folder indices 0xFFFD-0xFFFF say which -
+ * including a CFDATA block that is split over two cabinets (its two pieces are joined in front of the codec, each piece is
+ * checksummed by itself).  A folder whose other half is not among the images is reported as MSGPU_ERR_DATAFORMAT, the rest decodes.
+ * MSGPU_CAB_SALVAGE is MSCABD_PARAM_SALVAGE as far as the data path goes: no checksum test, blocks of up to 65535 compressed
+ * bytes and any claimed uncompressed size, running out of blocks is not an error of its own (cabd.c:1289-1292, :1312, :1393-1402);
+ * the header scan's own salvage behaviour (file tables read from the header's offset, cabd.c:466-489) is not offered.
  *
  * Per-folder status == what the reference's mscab_decompressor::extract() (cabd.c:1004-1140) returns for a file that needs
  * the whole folder: MSGPU_ERR_OK, the codec's MSGPU_ERR_DECRUNCH, MSGPU_ERR_CHECKSUM for a block whose stored checksum is
@@ -55,16 +60,19 @@ typedef struct msgpu_cab_folder {
 } msgpu_cab_folder;
 
 typedef struct msgpu_cab_block {
-    uint64_t payload_off;      /* offset of the block's payload in the image                     */
+    uint64_t payload_off;      /* offset of the block's payload in the image (a set: in the images laid end to end, each
+                                * starting at a multiple of 16)                                    */
     uint64_t dst_off;          /* where it goes: packed input (codec folders) or output (stored) */
     uint32_t checksum;         /* stored value, 0 = none                                          */
     uint16_t comp_len, uncomp_len;
     uint32_t folder;
-    uint32_t flags;            /* bit 0: Quantum (append 0xFF), bit 1: stored (dst is the output buffer) */
+    uint32_t flags;            /* bit 0: Quantum (append 0xFF), bit 1: stored (dst is the output buffer), bit 2: first piece of a block
+                                * that continues in the next cabinet (uncomp_len 0) */
 } msgpu_cab_block;
 
 typedef struct msgpu_cab_file {
-    uint32_t folder;           /* index, or 0xFFFFFFFF if the file lives in a folder of another cabinet */
+    uint32_t folder;           /* index into msgpu_cab_folders() (a file continued from / in another cabinet: the merged folder;
+                                * a set lists such a file once per cabinet that names it, as the cabinets do)  */
     uint32_t offset, length;   /* uoffFolderStart / cbFile, cab.h:33-34                          */
     uint32_t name_off;         /* offset of the NUL-terminated name in the image                 */
 } msgpu_cab_file;
@@ -74,6 +82,9 @@ typedef struct msgpu_cab_plan msgpu_cab_plan;
 /* Parse the headers of a single cabinet image held in HOST memory.  No GPU needed.  Returns NULL and sets *err
  * (MSGPU_ERR_SIGNATURE, MSGPU_ERR_DATAFORMAT, MSGPU_ERR_READ for a truncated header area, MSGPU_ERR_NOMEMORY) on failure. */
 msgpu_cab_plan *msgpu_cab_scan(const void *image, size_t image_bytes, int *err);
+/* The same for a SET of cabinets given in order (see above); flags: MSGPU_CAB_SALVAGE. */
+#define MSGPU_CAB_SALVAGE 1u
+msgpu_cab_plan *msgpu_cab_scan_set(const void *const *images, const size_t *image_bytes, size_t ncabs, uint32_t flags, int *err);
 void msgpu_cab_free(msgpu_cab_plan *plan);
 
 size_t msgpu_cab_num_folders(const msgpu_cab_plan *plan);
@@ -89,6 +100,8 @@ size_t msgpu_cab_packed_bytes(const msgpu_cab_plan *plan);   /* device scratch f
  * folders[f].out_off) and folder_status[num_folders] (may be NULL).  Synchronous.  Returns 0 if the batch ran. */
 int msgpu_cab_decode_host(msgpu_ctx *ctx, const msgpu_cab_plan *plan, const void *image, size_t image_bytes,
                           void *h_out, size_t out_bytes, int32_t *folder_status);
+int msgpu_cab_decode_host_set(msgpu_ctx *ctx, const msgpu_cab_plan *plan, const void *const *images, const size_t *image_bytes, size_t ncabs,
+                              void *h_out, size_t out_bytes, int32_t *folder_status);
 
 #ifdef __cplusplus
 }

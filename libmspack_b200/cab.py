@@ -13,7 +13,8 @@ from .codec import load_library
 
 CAB_SYMBOLS = ["msgpu_cab_scan", "msgpu_cab_free", "msgpu_cab_num_folders", "msgpu_cab_num_blocks", "msgpu_cab_num_files",
                "msgpu_cab_folders", "msgpu_cab_blocks", "msgpu_cab_files", "msgpu_cab_out_bytes", "msgpu_cab_packed_bytes",
-               "msgpu_cab_decode_host"]
+               "msgpu_cab_decode_host", "msgpu_cab_scan_set", "msgpu_cab_decode_host_set"]
+SALVAGE = 1          # MSGPU_CAB_SALVAGE
 
 FOLDER_DTYPE = np.dtype([("comp_type", "<u2"), ("codec", "u1"), ("window_bits", "u1"), ("num_blocks", "<u4"), ("first_block", "<u4"),
                          ("scan_status", "<i4"), ("bad_block", "<u4"), ("_pad", "<u4"), ("out_off", "<u8"), ("out_len", "<u8"),
@@ -42,6 +43,10 @@ def _lib():
             getattr(lib, name).argtypes = [vp]
         lib.msgpu_cab_decode_host.restype = ctypes.c_int
         lib.msgpu_cab_decode_host.argtypes = [vp, vp, vp, sz, vp, sz, vp]
+        lib.msgpu_cab_scan_set.restype = vp
+        lib.msgpu_cab_scan_set.argtypes = [vp, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+        lib.msgpu_cab_decode_host_set.restype = ctypes.c_int
+        lib.msgpu_cab_decode_host_set.argtypes = [vp, vp, vp, vp, sz, vp, sz, vp]
         _declared = True
     return lib
 
@@ -60,11 +65,20 @@ def _table(ptr, n, dtype):
 
 
 class CabPlan:
-    def __init__(self, image: bytes):
+    """One cabinet (image: bytes) or a set of cabinets in order (image: list of bytes); flags: SALVAGE."""
+
+    def __init__(self, image, flags: int = 0):
         self.lib = _lib()
-        self.image = np.frombuffer(bytes(image), dtype=np.uint8)
+        images = [image] if isinstance(image, (bytes, bytearray, memoryview)) else list(image)
+        self.images = [np.frombuffer(bytes(im), dtype=np.uint8) for im in images]
+        self.image = self.images[0]
+        self._ptrs = (ctypes.c_void_p * len(self.images))(*[im.ctypes.data for im in self.images])
+        self._sizes = (ctypes.c_size_t * len(self.images))(*[im.size for im in self.images])
         err = ctypes.c_int(0)
-        self.ptr = self.lib.msgpu_cab_scan(self.image.ctypes.data, self.image.size, ctypes.byref(err))
+        if len(self.images) == 1 and not flags:
+            self.ptr = self.lib.msgpu_cab_scan(self.image.ctypes.data, self.image.size, ctypes.byref(err))
+        else:
+            self.ptr = self.lib.msgpu_cab_scan_set(self._ptrs, self._sizes, len(self.images), flags, ctypes.byref(err))
         if not self.ptr:
             raise CabError(err.value)
         assert FOLDER_DTYPE.itemsize == 56 and BLOCK_DTYPE.itemsize == 32 and FILE_DTYPE.itemsize == 16
@@ -82,8 +96,8 @@ class CabPlan:
         """-> (out uint8[out_bytes], status int32[num_folders]); folder f's bytes are out[out_off : out_off + out_len]."""
         out = np.zeros(max(self.out_bytes, 1), np.uint8)
         st = np.full(len(self.folders), -1, np.int32)
-        rc = self.lib.msgpu_cab_decode_host(decoder.ctx, self.ptr, self.image.ctypes.data, self.image.size, out.ctypes.data, out.size,
-                                            st.ctypes.data)
+        rc = self.lib.msgpu_cab_decode_host_set(decoder.ctx, self.ptr, self._ptrs, self._sizes, len(self.images), out.ctypes.data, out.size,
+                                                st.ctypes.data)
         if rc:
             raise RuntimeError(f"msgpu_cab_decode_host failed: {rc}")
         return out[:self.out_bytes], st
@@ -97,5 +111,5 @@ class CabPlan:
         self.close()
 
 
-def scan(image: bytes) -> CabPlan:
-    return CabPlan(image)
+def scan(image, flags: int = 0) -> CabPlan:
+    return CabPlan(image, flags)

@@ -85,14 +85,24 @@ def cab_checksum(data: bytes, seed: int = 0) -> int:
     return (s ^ ul) & 0xFFFFFFFF
 
 
-def build_cab(folders, with_checksums: bool = True) -> bytes:
-    """folders: list of dicts {comp_type, blocks: [(payload bytes, uncompressed size)], files: [(name, offset, length)]}."""
+def build_cab(folders, with_checksums: bool = True, prev=None, next=None, set_id: int = 0x1234, set_index: int = 0) -> bytes:
+    """folders: list of dicts {comp_type, blocks: [(payload bytes, uncompressed size)], files: [(name, offset, length[, folder index])]}.
+    A file's optional 4th element overrides its folder index (0xFFFD continued from the previous cabinet, 0xFFFE continued in the
+    next one, 0xFFFF both: cab.h:55-57); prev / next = (cabinet name, disk label) set the header flags 1 / 2 (cab.h:60-62)."""
     nfiles = sum(len(f["files"]) for f in folders)
-    hdr_len = 0x24 + 8 * len(folders)
+    names = b""
+    flags = 0
+    for bit, pn in ((1, prev), (2, next)):
+        if pn:
+            flags |= bit
+            names += pn[0].encode() + b"\0" + pn[1].encode() + b"\0"
+    hdr_len = 0x24 + len(names) + 8 * len(folders)
     files_blob = b""
     for i, f in enumerate(folders):
-        for name, off, length in f["files"]:
-            files_blob += struct.pack("<IIHHHH", length, off, i, 0x2A21, 0x6000, 0x20) + name.encode() + b"\0"
+        for ent in f["files"]:
+            name, off, length = ent[:3]
+            fidx = ent[3] if len(ent) > 3 else i
+            files_blob += struct.pack("<IIHHHH", length, off, fidx, 0x2A21, 0x6000, 0x20) + name.encode() + b"\0"
     data_off = hdr_len + len(files_blob)
     fold_blob, data_blob = b"", b""
     for f in folders:
@@ -102,5 +112,5 @@ def build_cab(folders, with_checksums: bool = True) -> bytes:
             csum = cab_checksum(tail, cab_checksum(payload)) if with_checksums else 0
             data_blob += struct.pack("<I", csum) + tail + payload
     total = data_off + len(data_blob)
-    head = struct.pack("<4sIIIIIBBHHHHH", b"MSCF", 0, total, 0, hdr_len, 0, 3, 1, len(folders), nfiles, 0, 0x1234, 0)
-    return head + fold_blob + files_blob + data_blob
+    head = struct.pack("<4sIIIIIBBHHHHH", b"MSCF", 0, total, 0, hdr_len, 0, 3, 1, len(folders), nfiles, flags, set_id, set_index)
+    return head + names + fold_blob + files_blob + data_blob

@@ -98,3 +98,50 @@ def test_cabinet_decode_matches_reference(decoder, entry):
                     assert hashlib.md5(data).hexdigest() == r["md5"], (entry["name"], fi, r["index"])
     if entry["name"].startswith("synth"):
         assert checked == len(plan.folders)
+
+
+# ---- cabinet sets and salvage mode (tests/golden/cab/manifest_sets.json: the reference's open + append + extract) ----
+SETS = json.load(open(os.path.join(CABDIR, "manifest_sets.json")))
+
+
+def _set_id(e):
+    return "+".join(c.replace(".cab", "") for c in e["cabs"]) + ("/salvage" if e["salvage"] else "")
+
+
+def _set_plan(e):
+    return cab.scan([open(os.path.join(CABDIR, c), "rb").read() for c in e["cabs"]], cab.SALVAGE if e["salvage"] else 0)
+
+
+@pytest.mark.parametrize("entry", SETS, ids=_set_id)
+def test_set_scan_merges_folders_like_the_reference(entry):
+    """msgpu_cab_scan_set: as many folders as the reference has after append() (cabd.c:878-1000), every member file inside its folder,
+    and a folder whose other half is not among the images refused (the reference fails its files with DATAFORMAT / DECRUNCH)."""
+    assert entry["open"] == "open 0"
+    plan = _set_plan(entry)
+    assert len(plan.folders) == max(f["folder"] for f in entry["files"]) + 1
+    for fi in range(len(plan.folders)):
+        recs = [r for r in entry["files"] if r["folder"] == fi]
+        if all(r["err"] == 0 for r in recs) and not entry["salvage"]:
+            assert int(plan.folders["scan_status"][fi]) == 0, (fi, plan.folders[fi])
+            assert max(r["offset"] + r["length"] for r in recs) <= int(plan.folders["out_len"][fi])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("entry", SETS, ids=_set_id)
+def test_set_decode_matches_reference(decoder, entry):
+    """Every file the reference extracts from the set (or from the damaged cabinet in salvage mode) has the same bytes in the
+    merged folder's output; a folder none of whose files the reference can extract reports an error."""
+    plan = _set_plan(entry)
+    out, st = plan.decode(decoder)
+    for fi in range(len(plan.folders)):
+        recs = [r for r in entry["files"] if r["folder"] == fi]
+        base, olen = int(plan.folders["out_off"][fi]), int(plan.folders["out_len"][fi])
+        good = [r for r in recs if r["err"] == 0]
+        if recs and not good:
+            assert int(st[fi]) != 0, (fi, int(st[fi]))
+        if recs and len(good) == len(recs):
+            assert int(st[fi]) == 0, (fi, int(st[fi]), plan.folders[fi])
+        for r in good:
+            if r["offset"] + r["length"] <= olen and r.get("written") == r["length"]:
+                data = out[base + r["offset"]: base + r["offset"] + r["length"]].tobytes()
+                assert hashlib.md5(data).hexdigest() == r["md5"], (_set_id(entry), fi, r["index"])
