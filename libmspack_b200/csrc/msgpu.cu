@@ -50,7 +50,7 @@ __device__ __forceinline__ void p1_run(Lane &t)
             if (t.phase == PH_PARK) t.phase = PH_FRAME | 0x100u;      /* nobody decodes: the parked lanes start their frames together (msgpu_core.cuh PH_PARK) */
             continue;
         }
-        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run */
+        do { if (t.phase == PH_DECODE) t.step(); t.post_step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);   /* until a lane leaves the run (post_step: warp-cooperative work, all lanes) */
     }
 }
 

@@ -33,6 +33,14 @@
 #define MS_SYNCWARP() __syncwarp()
 #define MS_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define MS_STORE4(p, a, b, c, d) (*reinterpret_cast<uint4 *>(p) = make_uint4((a), (b), (c), (d)))      /* p 16-byte aligned */
+/* warp-cooperative sections (the Quantum model updates): a PHASE is a piece of code every lane of the warp runs for its own lane
+ * index, reading only what earlier phases wrote (shared memory); the emulation runs a phase for the 32 lane indices one after
+ * the other, the device runs it once per lane and closes it with a warp barrier - the same source either way */
+#define MS_LANES(vl) for (int vl = (int) (threadIdx.x & 31u), ms_once_ = 1; ms_once_; ms_once_ = 0)
+#define MS_PHASE_END() __syncwarp()
+#define MS_SHFL(x, l) __shfl_sync(0xFFFFFFFFu, (x), (l))
+#define MS_SMEM_MIN(p, v) atomicMin((p), (v))
+#define MS_LANE_ID() ((int) (threadIdx.x & 31u))
 #else
 #define MS_STORE4(p, a, b, c, d) do { uint32_t *p_ = reinterpret_cast<uint32_t *>(p); p_[0] = (a); p_[1] = (b); p_[2] = (c); p_[3] = (d); } while (0)
 #define MS_D static inline
@@ -50,6 +58,11 @@ static inline uint32_t ms_brev32_host(uint32_t v) {
 #define MS_BALLOT(p) ((p) ? 1u : 0u)      /* emulation runs one lane at a time */
 #define MS_SYNCWARP() do { } while (0)
 #define MS_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define MS_LANES(vl) for (int vl = 0; vl < 32; vl++)
+#define MS_PHASE_END() do { } while (0)
+#define MS_SHFL(x, l) (x)
+#define MS_SMEM_MIN(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
+#define MS_LANE_ID() 0
 #endif
 
 /* lane phases of the warp-synchronous P1 state machines: every lane of a warp loops

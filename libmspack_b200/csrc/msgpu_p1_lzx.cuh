@@ -399,6 +399,7 @@ struct LzxLaneC {
         else phase = (f < max_frames) ? PH_FRAME : PH_IDLE;
     }
 
+    MS_M void post_step() { }
     MS_M void service() {
 #pragma unroll 1
         while (phase >= PH_FRAME && phase != PH_PARK) {

@@ -366,6 +366,7 @@ struct ZipLaneC {
         return true;
     }
 
+    MS_M void post_step() { }
     /* the rare, divergent work: run until the lane is decoding symbols or has nothing left to do */
     MS_M void service() {
 #pragma unroll 1

@@ -33,8 +33,24 @@
  * re-sort) and are rebuilt from g[] when a unit's state is reloaded.  Measured on the B200 together with the loop-free
  * renormalisation below (profiles/r2_variants.txt, Quantum shape 3): P1 77.3 -> 56.0 ms for 16 384 units. */
 #define QTM_GRP 56            /* 1 + 4 x 8 + 3 + 5 + 6 + 4 = 51 group sums, padded for the four-wide reads */
+/* Model updates, warp-cooperative.  qtmd_update_model (qtmd.c:125-166) is rare for one stream - a model is rescaled every ~240
+ * of its symbols, re-sorted every 50th time - but a warp advances 32 streams in lockstep and SOME lane is due every few steps;
+ * done by that lane alone, the 24-64-entry loops (and the exchange sort's entries^2 / 2 compares) ran with one active thread
+ * while 31 waited: 20 % of the kernel's warp-instructions (profiles/r2_p1qtm_d.txt).  Now the lane only flags the model
+ * (upd_pending) and after the step all 32 lanes do the update together (QtmLane::post_step), one flagged lane at a time:
+ *   rescale   cum[i] >>= 1, then cum[i] = max(cum[i], cum[i+1] + 1) from the end  ==  c[i] = max(max_{k >= i} (h[k] + k), entries) - i
+ *             with h = the halved old values: a suffix sum (differences -> cumulative), a suffix max, a difference;
+ *   re-sort   the reference's in-place exchange sort, whose treatment of ties is part of the format: pass i moves the largest
+ *             remaining frequency to position i and shifts every strict prefix-maximum ("record") of f[i..] one record to the
+ *             right - the smallest record lands where the next one was.  A pass is a prefix-max scan plus a gather; passes whose
+ *             position already holds the maximum of what follows change nothing and are skipped (first inversion by a min-reduction).
+ * Scans are Hillis-Steele over 64-entry scratch rows in shared memory, phase by phase (msgpu_core.cuh MS_LANES): the same source
+ * runs on the device and in the host emulation.  Models of at most QTM_COOP_MIN entries (the selector) stay with their lane. */
+#define QTM_COOP_MIN 8
 template <int NT>
 struct QtmShared {
+    uint32_t ws[(NT + 31) / 32][3][64];  /* per warp: three scratch rows for the cooperative updates */
+    uint32_t wsmin[(NT + 31) / 32];
     uint16_t grp[QTM_GRP * NT];
     uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
     uint16_t tot[9 * NT];             /* T = cum[0] per model */
@@ -50,7 +66,114 @@ struct QtmLane {
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
 
-    MS_M void bind(QtmShared<NT> *sh, int tid) { cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; grp = sh->grp + tid; }
+    uint32_t *ws, *wsmin; uint32_t upd_pending; int upd_base, upd_midx, upd_ent;
+    MS_M void bind(QtmShared<NT> *sh, int tid) {
+        cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; grp = sh->grp + tid;
+        ws = &sh->ws[tid >> 5][0][0]; wsmin = &sh->wsmin[tid >> 5]; upd_pending = 0; upd_base = upd_midx = upd_ent = 0;
+    }
+
+    /* Hillis-Steele scan over a 64-entry row (two entries per lane): dst[i] = op over src[i], src[i + d], src[i + 2d] ... (SUFFIX) or
+     * src[i], src[i - d] ... (prefix); returns the row that holds the result (a or b) */
+    template <bool SUFFIX, class Op>
+    MS_M uint32_t *coop_scan(uint32_t *a, uint32_t *b, Op op) {
+#pragma unroll 1
+        for (int d = 1; d < 64; d <<= 1) {
+            MS_LANES(vl) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = vl + 32 * h, j = SUFFIX ? i + d : i - d;
+                    uint32_t v = a[i];
+                    if (j >= 0 && j < 64) v = op(v, a[j]);
+                    b[i] = v;
+                }
+            }
+            MS_PHASE_END();
+            uint32_t *t = a; a = b; b = t;
+        }
+        return a;
+    }
+
+    /* all lanes, uniform arguments: update model (base, midx, entries) of lane L's stream */
+    MS_M void coop_update(int L, int base, int midx, int entries) {
+        const int me = MS_LANE_ID();
+        uint16_t *ocum = cum - me + L, *ogrp = grp - me + L, *otot = tot - me + L; uint8_t *osym = sym - me + L, *oshl = shl - me + L;
+        uint32_t *r0 = ws, *r1 = ws + 64, *r2 = ws + 128;
+        const uint32_t s = (uint32_t) oshl[midx * NT] - 1u;
+        const int gb = grp_base(midx);
+        if (s) {
+            /* rescale (qtmd.c:130-136) */
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; r0[i] = i < entries ? (uint32_t) ocum[(base + i) * NT] : 0u; } }
+            MS_PHASE_END();
+            uint32_t *c = coop_scan<true>(r0, r1, [](uint32_t x, uint32_t y) { return x + y; });           /* the reference's cum[i] */
+            uint32_t *o = c == r0 ? r1 : r0;
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; o[i] = i < entries ? (c[i] >> 1) + (uint32_t) i : 0u; } }
+            MS_PHASE_END();
+            uint32_t *m = coop_scan<true>(o, r2, [](uint32_t x, uint32_t y) { return x > y ? x : y; });
+            uint32_t *cn = (m == o) ? r2 : o;                        /* a row that is free now */
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; const uint32_t mm = m[i] > (uint32_t) entries ? m[i] : (uint32_t) entries; cn[i] = i < entries ? mm - (uint32_t) i : 0u; } }
+            MS_PHASE_END();
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) ocum[(base + i) * NT] = (uint16_t) (cn[i] - (i + 1 < 64 ? cn[i + 1] : 0u)); } }
+            MS_PHASE_END();
+            MS_LANES(vl) {
+                if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += ocum[(base + 8 * vl + j) * NT]; ogrp[(gb + vl) * NT] = (uint16_t) acc; }
+                if (vl == 8) { otot[midx * NT] = (uint16_t) cn[0]; oshl[midx * NT] = (uint8_t) s; }
+            }
+            MS_PHASE_END();
+            return;
+        }
+        /* re-sort (qtmd.c:138-164): rows hold f << 8 | sym */
+        uint32_t *fy = r0, *sa = r1, *sb = r2;
+        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h;
+            fy[i] = i < entries ? ((((uint32_t) ocum[(base + i) * NT] + 1u) >> 1) << 8) | (uint32_t) osym[(base + i) * NT] : 0u; } }
+        MS_PHASE_END();
+#pragma unroll 1
+        for (int guard = 0; guard < 64; guard++) {
+            /* the first position whose frequency is below the maximum of what follows it: the next pass that changes anything */
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; sa[i] = fy[i] >> 8; } if (vl == 0) *wsmin = 64u; }
+            MS_PHASE_END();
+            uint32_t *m = coop_scan<true>(sa, sb, [](uint32_t x, uint32_t y) { return x > y ? x : y; });
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i + 1 < entries && (fy[i] >> 8) < m[i + 1]) MS_SMEM_MIN(wsmin, (uint32_t) i); } }
+            MS_PHASE_END();
+            const int i0 = (int) *wsmin;
+            MS_PHASE_END();
+            if (i0 >= 64) break;
+            /* pass i0: keys f << 8 | (63 - j) make the FIRST of equal frequencies the larger one, so "key above the prefix maximum"
+             * is the reference's strict f[i] < f[j] */
+            uint32_t *ka = m == sa ? sb : sa, *kb = m;
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int j = vl + 32 * h; ka[j] = (j >= i0 && j < entries) ? (fy[j] & ~0xFFu) | (uint32_t) (63 - j) : 0u; } }
+            MS_PHASE_END();
+            uint32_t *pm = coop_scan<false>(ka, kb, [](uint32_t x, uint32_t y) { return x > y ? x : y; });      /* inclusive prefix maxima of the keys */
+            uint32_t *nw = pm == ka ? kb : ka;
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int j = vl + 32 * h;
+                uint32_t v = fy[j];
+                if (j == i0) v = fy[63 - (int) (pm[entries - 1] & 0xFFu)];                                   /* the maximum of f[i0..] comes to i0 */
+                else if (j > i0 && j < entries) {
+                    const uint32_t before = pm[j - 1], key = (fy[j] & ~0xFFu) | (uint32_t) (63 - j);
+                    if (key > before) v = fy[63 - (int) (before & 0xFFu)];                                   /* a record: the previous record moves here */
+                }
+                nw[j] = v; } }
+            MS_PHASE_END();
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int j = vl + 32 * h; fy[j] = nw[j]; } }
+            MS_PHASE_END();
+        }
+        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) { ocum[(base + i) * NT] = (uint16_t) (fy[i] >> 8); osym[(base + i) * NT] = (uint8_t) fy[i]; } } }
+        MS_PHASE_END();
+        MS_LANES(vl) { if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += ocum[(base + 8 * vl + j) * NT]; ogrp[(gb + vl) * NT] = (uint16_t) acc; } }
+        MS_PHASE_END();
+        MS_LANES(vl) { if (vl == 0) { uint32_t T = 0; for (int k = 0; 8 * k < entries; k++) T += ogrp[(gb + k) * NT]; otot[midx * NT] = (uint16_t) T; oshl[midx * NT] = 50; } }
+        MS_PHASE_END();
+    }
+    /* after every step, all lanes: the model updates the step's lanes asked for */
+    MS_M void post_step() {
+        uint32_t need = MS_BALLOT(upd_pending != 0);
+#pragma unroll 1
+        while (need) {
+            const int L = __builtin_ffs((int) need) - 1;
+            need &= need - 1;
+            coop_update(L, MS_SHFL(upd_base, L), MS_SHFL(upd_midx, L), MS_SHFL(upd_ent, L));
+            if (MS_LANE_ID() == L) upd_pending = 0;
+        }
+    }
 
     MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
         shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
@@ -157,7 +280,10 @@ struct QtmLane {
         cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
         grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
-        if (c0 > 3800) update_model(base, midx, entries);
+        if (c0 > 3800) {
+            if (entries <= QTM_COOP_MIN) update_model(base, midx, entries);
+            else { upd_pending = 1; upd_base = base; upd_midx = midx; upd_ent = entries; }      /* all lanes together, after the step (post_step) */
+        }
         {
             /* The renormalisation without a loop.  The reference's loop (:109-122) first shifts out the
              * leading bits L and H share, then - the top bits now being 0 / 1 - the run of "underflow" positions right below

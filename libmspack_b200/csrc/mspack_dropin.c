@@ -162,7 +162,15 @@ static int ds_decompress(struct dstream *s, off_t out_bytes) {
             /* The decode-ahead stopped in front of this request: at a frame that really fails, or at a stream's SHORT LAST FRAME - a
              * Quantum / LZX frame only counts as decoded when all of it is, and asking for more bytes than a stream holds fails the
              * frame they would be in.  Decode exactly as far as the request reaches, like the reference does; what fails now fails. */
-            if ((e = ds_decode(s, end))) return s->error = e;
+            size_t exact = end;
+            if (s->codec == MSGPU_CODEC_LZX) {
+                /* an LZX frame is cut short by the STREAM's length only, never by the request (lzxd.c:441-447): a request that ends
+                 * inside a frame still decodes all 32 KiB of it - and fails if the frame's input is not there */
+                exact = (end + FRAME - 1) / FRAME * FRAME;
+                if (s->length > 0 && exact > (size_t) s->length) exact = (size_t) s->length;
+                if (exact < end) return s->error = MSPACK_ERR_DECRUNCH;
+            }
+            if ((e = ds_decode(s, exact))) return s->error = e;
             if (s->tail_status) return s->error = s->tail_status;
             continue;
         }

@@ -72,7 +72,7 @@ static void emul_run(Lane &t) {       /* same loop as p1_run() in msgpu.cu, for 
             if (t.phase == PH_PARK) t.phase = PH_FRAME | 0x100u;
             continue;
         }
-        do { if (t.phase == PH_DECODE) t.step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
+        do { if (t.phase == PH_DECODE) t.step(); t.post_step(); } while (MS_BALLOT(t.phase == PH_DECODE) == m0);
     }
 }
 

@@ -64,7 +64,11 @@ def run(cabs, salvage):
     try:
         paths = [os.path.join(OUT, c) for c in cabs]
         cmd = [CABX] + (["--salvage"] if salvage else []) + [paths[0], tmp] + paths[1:]
-        lines = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=300).stdout.decode("ascii", "replace").split("\n")
+        # A damaged stream can copy from window positions nothing was decoded to yet; the reference's window is malloc'd and never
+        # cleared (qtmd.c:396-409 reads it as it is), so what such a match yields is whatever the heap held.  Every allocation of a
+        # page or more straight from mmap (zero pages) makes the reference's answer the deterministic one the GPU path defines.
+        env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="4096")
+        lines = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=300, env=env).stdout.decode("ascii", "replace").split("\n")
         entry = {"cabs": list(cabs), "salvage": int(salvage), "open": lines[0].strip(), "files": []}
         for ln in lines[1:]:
             if not ln.strip():
