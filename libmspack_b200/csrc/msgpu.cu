@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
     uint32_t slot = valid ? order[ti] : 0;
     QtmLane<NT> t; t.phase = PH_IDLE;
     MsUnitState st;
+    t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);      /* every thread: idle lanes take part in the warp-cooperative model updates */
     if (valid) {
-        t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);
         st = a.ustate[slot];
         t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
                 a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
@@ -245,14 +245,15 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * wave.  Round 2 measured every shape round 1 had prepared (profiles/r2_variants.txt) and kept one per codec:
  *   MSZIP   448 lanes, 124-entry head, byte-wise literal stores            (round-1 shape 18: P1 8.65 -> 7.89 ms on 32 768 units)
  *   LZX     448 lanes, LzxSharedQ (256-entry packed head + LENGTH head), exact-need refill   (shape 31: P1 9.02 -> 8.52 ms)
- *   Quantum 160 lanes, two-level model scan + loop-free renormalisation    (shape 3: P1 77.3 -> 56.0 ms on 16 384 units)
+ *   Quantum 224 lanes (symbol bytes in global memory), two-level model scan + loop-free renormalisation (shape 3: P1 77.3 -> 56.0 ms
+ *           on 16 384 units with 160 lanes), warp-cooperative model updates
  * the other 32 shapes and the byte-parallel pass A of P2 (6.77 against 6.20 ms) measured slower or equal and were deleted. */
 #define ZIP_NT 448
 #define ZIP_HEADN 124
 #define LZX_NT 448
 #define LZX_HEADN 256
 #define LZX_H8LB 104
-#define QTM_NT 160
+#define QTM_NT 224
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
 
@@ -292,6 +293,7 @@ struct msgpu_ctx {
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
+    int dev_streams = 3;  /* MSGPU_STREAMS: internal streams the sub-waves of a device-buffer batch alternate over (1 = all on the caller's stream) */
     int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
@@ -330,6 +332,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_P2_BULK"); c->p2_bulk = v ? atoi(v) : 1; }
+    { const char *v = getenv("MSGPU_STREAMS"); if (v) { int k = atoi(v); c->dev_streams = k < 1 ? 1 : (k > (int) msgpu_ctx::NSUB ? (int) msgpu_ctx::NSUB : k); } }
     /* the entropy kernels use most of an SM's shared memory: opt in */
     cudaError_t ae = cudaSuccess;
 #define SETA(kernel, bytes) { cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)); if (e_ != cudaSuccess) ae = e_; }
@@ -446,7 +449,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
-    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 2240u;   /* mixed batches: lcm of the 448- and 160-lane CTA shapes */
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 448u;   /* mixed batches: lcm of the 448- and 224-lane CTA shapes */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     const uint32_t nchains = (uint32_t) (chains.size() / 2);
     if (nchains) subsz = 0x40000000u;          /* a chain is resolved in order after ALL its blocks left P1: one sub-wave */
@@ -530,7 +533,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
     const bool hostpipe = h_in && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above (h_out may be absent: msgpu_decode_batch_host_digest) */
-    const int NS = (nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : 3) : 1;
+    const int NS = (nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : ctx->dev_streams) : 1;
     auto kstream = [&](uint32_t sub) { return NS == 1 ? s : ctx->sub[sub % (uint32_t) NS]; };
     if (hostpipe) {
         while (ctx->io_evs.size() < 2 * (size_t) nsub) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->io_evs.push_back(e); }

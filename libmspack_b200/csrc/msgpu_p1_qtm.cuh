@@ -47,6 +47,11 @@
  * Scans are Hillis-Steele over 64-entry scratch rows in shared memory, phase by phase (msgpu_core.cuh MS_LANES): the same source
  * runs on the device and in the host emulation.  Models of at most QTM_COOP_MIN entries (the selector) stay with their lane. */
 #define QTM_COOP_MIN 8
+/* Shared memory per lane: the frequency differences (802 bytes), group sums, totals, rescale counters = 941 bytes -> 224 lanes
+ * (7 warps) per SM.  The models' SYMBOL bytes (401 per lane; one read per decoded symbol, rewritten only by a re-sort) live in
+ * global memory instead - in the unit's save area, unit-major, where a multi-frame unit keeps them between launches anyway:
+ * with them in shared memory an SM held 160 lanes (5 warps, IPC 0.56: the kernel is latency bound, profiles/r2_p1qtm_d.txt),
+ * and a 65 536-unit batch needed three waves of CTAs instead of two. */
 template <int NT>
 struct QtmShared {
     uint32_t ws[(NT + 31) / 32][3][64];  /* per warp: three scratch rows for the cooperative updates */
@@ -54,7 +59,6 @@ struct QtmShared {
     uint16_t grp[QTM_GRP * NT];
     uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
     uint16_t tot[9 * NT];             /* T = cum[0] per model */
-    uint8_t  sym[QTM_ENT * NT];
     uint8_t  shl[9 * NT];
 };
 
@@ -68,7 +72,7 @@ struct QtmLane {
 
     uint32_t *ws, *wsmin; uint32_t upd_pending; int upd_base, upd_midx, upd_ent;
     MS_M void bind(QtmShared<NT> *sh, int tid) {
-        cum = sh->cum + tid; tot = sh->tot + tid; sym = sh->sym + tid; shl = sh->shl + tid; grp = sh->grp + tid;
+        cum = sh->cum + tid; tot = sh->tot + tid; shl = sh->shl + tid; grp = sh->grp + tid;
         ws = &sh->ws[tid >> 5][0][0]; wsmin = &sh->wsmin[tid >> 5]; upd_pending = 0; upd_base = upd_midx = upd_ent = 0;
     }
 
@@ -94,9 +98,9 @@ struct QtmLane {
     }
 
     /* all lanes, uniform arguments: update model (base, midx, entries) of lane L's stream */
-    MS_M void coop_update(int L, int base, int midx, int entries) {
+    MS_M void coop_update(int L, uint8_t *lane_sym, int base, int midx, int entries) {
         const int me = MS_LANE_ID();
-        uint16_t *ocum = cum - me + L, *ogrp = grp - me + L, *otot = tot - me + L; uint8_t *osym = sym - me + L, *oshl = shl - me + L;
+        uint16_t *ocum = cum - me + L, *ogrp = grp - me + L, *otot = tot - me + L; uint8_t *osym = lane_sym, *oshl = shl - me + L;
         uint32_t *r0 = ws, *r1 = ws + 64, *r2 = ws + 128;
         const uint32_t s = (uint32_t) oshl[midx * NT] - 1u;
         const int gb = grp_base(midx);
@@ -124,7 +128,7 @@ struct QtmLane {
         /* re-sort (qtmd.c:138-164): rows hold f << 8 | sym */
         uint32_t *fy = r0, *sa = r1, *sb = r2;
         MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h;
-            fy[i] = i < entries ? ((((uint32_t) ocum[(base + i) * NT] + 1u) >> 1) << 8) | (uint32_t) osym[(base + i) * NT] : 0u; } }
+            fy[i] = i < entries ? ((((uint32_t) ocum[(base + i) * NT] + 1u) >> 1) << 8) | (uint32_t) osym[base + i] : 0u; } }
         MS_PHASE_END();
 #pragma unroll 1
         for (int guard = 0; guard < 64; guard++) {
@@ -156,7 +160,7 @@ struct QtmLane {
             MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int j = vl + 32 * h; fy[j] = nw[j]; } }
             MS_PHASE_END();
         }
-        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) { ocum[(base + i) * NT] = (uint16_t) (fy[i] >> 8); osym[(base + i) * NT] = (uint8_t) fy[i]; } } }
+        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) { ocum[(base + i) * NT] = (uint16_t) (fy[i] >> 8); osym[base + i] = (uint8_t) fy[i]; } } }
         MS_PHASE_END();
         MS_LANES(vl) { if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += ocum[(base + 8 * vl + j) * NT]; ogrp[(gb + vl) * NT] = (uint16_t) acc; } }
         MS_PHASE_END();
@@ -170,7 +174,7 @@ struct QtmLane {
         while (need) {
             const int L = __builtin_ffs((int) need) - 1;
             need &= need - 1;
-            coop_update(L, MS_SHFL(upd_base, L), MS_SHFL(upd_midx, L), MS_SHFL(upd_ent, L));
+            coop_update(L, reinterpret_cast<uint8_t *>(MS_SHFL((unsigned long long) reinterpret_cast<uintptr_t>(sym), L)), MS_SHFL(upd_base, L), MS_SHFL(upd_midx, L), MS_SHFL(upd_ent, L));
             if (MS_LANE_ID() == L) upd_pending = 0;
         }
     }
@@ -178,7 +182,7 @@ struct QtmLane {
     MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
         shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
 #pragma unroll 1
-        for (int i = 0; i <= len; i++) { sym[(base + i) * NT] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
+        for (int i = 0; i <= len; i++) { sym[base + i] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
         regroup(base, midx, len);
     }
 
@@ -214,17 +218,17 @@ struct QtmLane {
             /* the reference's in-place exchange sort; its (in)stability is part of the format (:148-150) */
 #pragma unroll 1
             for (int i = 0; i < entries - 1; i++) {
-                uint32_t ci = cum[(base + i) * NT], si = sym[(base + i) * NT];
+                uint32_t ci = cum[(base + i) * NT], si = sym[base + i];
 #pragma unroll 1
                 for (int j = i + 1; j < entries; j++) {
                     uint32_t cj = cum[(base + j) * NT];
                     if (ci < cj) {
-                        uint32_t sj = sym[(base + j) * NT];
-                        cum[(base + j) * NT] = (uint16_t) ci; sym[(base + j) * NT] = (uint8_t) si;
+                        uint32_t sj = sym[base + j];
+                        cum[(base + j) * NT] = (uint16_t) ci; sym[base + j] = (uint8_t) si;
                         ci = cj; si = sj;
                     }
                 }
-                cum[(base + i) * NT] = (uint16_t) ci; sym[(base + i) * NT] = (uint8_t) si;
+                cum[(base + i) * NT] = (uint16_t) ci; sym[base + i] = (uint8_t) si;
             }
 #pragma unroll 1
             for (int i = 0; i < entries; i++) T += cum[(base + i) * NT];   /* :162-164 back to cumulative: T = cum[0] */
@@ -271,7 +275,7 @@ struct QtmLane {
             if (j + 4 >= entries || c4 <= symf) { gj = g3; cur = c4; prev = c3; j += 3; break; }
             prev = c4;
         }
-        uint32_t s = sym[(base + j) * NT];
+        uint32_t s = sym[base + j];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
         uint32_t Hn, Ln;
         Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
@@ -430,6 +434,7 @@ struct QtmLane {
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,
                     int nframes, uint8_t *save_area) {
         u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; save = save_area; f = 0; q = 0; limit = 0; frame_start_pos = 0;
+        sym = save_area + QTM_ENT * 2;          /* the symbol bytes live in the unit's save area (see QtmShared) */
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         const int wb = unit->window_bits, wb2 = wb * 2;
@@ -454,7 +459,7 @@ struct QtmLane {
             header_read = st.header_read; frame_todo = st.frame_todo;
             if (save && !done) {
 #pragma unroll 1
-                for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; sym[i * NT] = save[QTM_ENT * 2 + i]; }
+                for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; }
 #pragma unroll 1
                 for (int i = 0; i < 9; i++) { shl[i * NT] = save[QTM_ENT * 3 + i]; tot[i * NT] = reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i]; }
                 regroup(QM0, 0, 64); regroup(QM1, 1, 64); regroup(QM2, 2, 64); regroup(QM3, 3, 64);
@@ -470,7 +475,7 @@ struct QtmLane {
         st.header_read = header_read; st.frame_todo = frame_todo;
         if (save && !done) {
 #pragma unroll 1
-            for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; save[QTM_ENT * 2 + i] = sym[i * NT]; }
+            for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; }
 #pragma unroll 1
             for (int i = 0; i < 9; i++) { save[QTM_ENT * 3 + i] = shl[i * NT]; reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i] = tot[i * NT]; }
         }
