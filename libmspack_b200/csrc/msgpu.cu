@@ -293,7 +293,7 @@ struct msgpu_ctx {
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
-    int dev_streams = 3;  /* MSGPU_STREAMS: internal streams the sub-waves of a device-buffer batch alternate over (1 = all on the caller's stream) */
+    int dev_streams = 3;  /* MSGPU_STREAMS=1: everything of a device-buffer batch in the caller's stream order (default: mixed batches run each codec on a stream of its own) */
     int p2_owner = 1;     /* MSGPU_P2_OWNER=0: the record-parallel pass A on every chunk (A/B) */
     int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
@@ -455,6 +455,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     const uint32_t nchains = (uint32_t) (chains.size() / 2);
     if (nchains) subsz = 0x40000000u;          /* a chain is resolved in order after ALL its blocks left P1: one sub-wave */
+    /* Device buffers: ONE sub-wave, i.e. one P1 launch per codec and round over all its units.  A P1 CTA owns its SM (all the
+     * shared memory), so P1 of one sub-wave never shares an SM with P2 of another; cutting a 131 072-unit batch into two
+     * sub-waves on alternating streams only let the block scheduler interleave them badly - measured on BASELINE config 4:
+     * 73.4 ms with the sub-waves on two or three streams, 52.2 ms with everything in stream order (profiles/r2_config4_streams.txt).
+     * With one launch the CTAs beyond one resident wave simply start as earlier ones finish. */
+    if (!h_in && !env) subsz = 0x40000000u;
     if (h_in && !env && !nchains) {
         /* host buffers: cut the wave into ~16 sub-waves; their H2D copies queue on one copy stream, their kernels run on
          * eight compute streams as soon as "their" input has landed, their D2H copies queue on a second copy stream as soon as
@@ -535,7 +541,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
     const bool hostpipe = h_in && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above (h_out may be absent: msgpu_decode_batch_host_digest) */
-    const int NS = (nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : ctx->dev_streams) : 1;
+    /* A batch of several codecs on device buffers: every codec's launches on a stream of its own (MSGPU_STREAMS=1: all in the
+     * caller's stream order).  The three P1 kernels have CTAs of different shapes that each take a whole SM; the partial last
+     * "wave" of one codec (Quantum: 224 lanes per SM, 7x the latency of the others) then shares the GPU with the other codecs'
+     * CTAs instead of leaving two thirds of the SMs idle. */
+    const bool percodec = !h_in && !ctx->stage_timing && nsub == 1 && ctx->dev_streams > 1 && ((nz != 0) + (nl != 0) + (nq != 0)) > 1;
+    const int NS = percodec ? 3 : ((nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : ctx->dev_streams) : 1);
     auto kstream = [&](uint32_t sub) { return NS == 1 ? s : ctx->sub[sub % (uint32_t) NS]; };
     if (hostpipe) {
         while (ctx->io_evs.size() < 2 * (size_t) nsub) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->io_evs.push_back(e); }
@@ -637,9 +648,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         else if (ctx->p2_bulk) k_p2_resolve<false, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
         else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
     };
-    auto launch_round = [&](uint32_t sub, cudaStream_t st) {
+    /* clear: zero the "units still running" counter in front of the round's kernels.  With a stream per codec every codec
+     * counts in a slot of its own (w.sub = its stream index; there is one sub-wave), cleared in its own stream order. */
+    auto launch_round = [&](uint32_t sub, cudaStream_t st_all, bool clear) {
         uint32_t f0 = sub * subsz, f1;
         WaveArgs w = a; w.sub = (int) sub;
+        cudaStream_t st = percodec ? ctx->sub[1] : st_all;
+        if (clear && !percodec) cudaMemsetAsync(a.not_done + sub, 0, 4, st_all);
+        if (percodec) { w.sub = 1; if (clear) cudaMemsetAsync(a.not_done + 1, 0, 4, st); }
         if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
             mark(0, st);
             if (any_kwaj) k_p1_mszip<ZIP_NT, ZIP_HEADN, true><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
@@ -651,12 +667,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (any_kwaj) { k_p2_ring<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches++; }
             if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
             mark(1, st); }
+        if (percodec) { st = ctx->sub[2]; w.sub = 2; if (clear) cudaMemsetAsync(a.not_done + 2, 0, 4, st); }
         if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
             mark(0, st);
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             else k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
+        if (percodec) { st = ctx->sub[0]; w.sub = 0; if (clear) cudaMemsetAsync(a.not_done + 0, 0, 4, st); }
         if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
             mark(0, st);
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
@@ -668,8 +686,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (hostpipe) { copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[2 * sub], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(st, ctx->io_evs[2 * sub], 0), "stream wait"); }
         else copy_in(sub, st);
         for (uint32_t round = 0; round < rounds_planned; round++) {
-            if (round + 1 == rounds_planned && any_zip) CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
-            launch_round(sub, st);
+            launch_round(sub, st, round + 1 == rounds_planned && any_zip);      /* the last planned round counts the units still running */
         }
         if (!any_zip) finish_out(sub, st);
     }
@@ -679,13 +696,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
          * read the per-sub-wave "units still running" counters back and finish the stragglers */
         for (int guard = 0;; guard++) {
             for (int i = 0; i < NS; i++) CK(cudaStreamSynchronize(NS == 1 ? s : ctx->sub[i]), "sync");
-            CK(cudaMemcpy(ctx->h_pinned, a.not_done, nsub * 4, cudaMemcpyDeviceToHost), "read counters");
+            CK(cudaMemcpy(ctx->h_pinned, a.not_done, (percodec ? 3 : nsub) * 4, cudaMemcpyDeviceToHost), "read counters");
             bool again = false;
-            for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
-                cudaStream_t st = kstream(sub);
+            if (percodec) { if (ctx->h_pinned[0] | ctx->h_pinned[1] | ctx->h_pinned[2]) { again = true; launch_round(0, s, true); } }
+            else for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
                 again = true;
-                CK(cudaMemsetAsync(a.not_done + sub, 0, 4, st), "clear counter");
-                launch_round(sub, st);
+                launch_round(sub, kstream(sub), true);
             }
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
