@@ -195,7 +195,13 @@ MS_D void p2_owner_desc(uint32_t q0, uint32_t prel0, const uint32_t x[16], uint3
  * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
  * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero - except for the ref_len bytes
  * directly in front of the unit, the reference data of an LZX DELTA unit (WIDE only). */
-template <bool WIDE, bool RING = false, bool PLANE = false>
+/* WORDS: a byte is taken out of the aligned 4-byte word that holds it, and a position whose source directly follows its left
+ * neighbour's inside the same word re-uses that word instead of loading again.  The resolve kernel is bound by the load/store
+ * unit (l1tex__data_pipe_lsu_wavefronts 87 % of peak, profiles/r2_p2_f.txt) and 41 % of its wavefronts are these byte loads - 8 cache
+ * lines per warp-instruction; with matches of ~5 bytes most lanes sit out most of the 16 load instructions.  The word may reach
+ * up to 3 bytes beyond the byte asked for: inside the same 16-byte-aligned unit, or the slack every output buffer has behind it
+ * (include/msgpu.h: 16 bytes). */
+template <bool WIDE, bool RING = false, bool PLANE = false, bool WORDS = false>
 MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0,
                     const uint32_t *hist = nullptr, const uint8_t *plane = nullptr, const uint32_t *dreg = nullptr)      /* dreg: this lane's descriptors, if pass A kept them (owner form) */
 {
@@ -215,6 +221,21 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
     const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
     uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
     if (WIDE) ulim = ulim > ref_len ? ulim - ref_len : 0u;
+    if (WORDS && !RING && !PLANE) {
+        const uint32_t a0 = (uint32_t) reinterpret_cast<uintptr_t>(obase);
+        uint32_t px = 0xFFFFFFF0u, pw = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) {
+            const uint32_t x = d[k];
+            const bool valid = k < n && x >= ulim;
+            const uint32_t sh = (a0 + x) & 3u;
+            if (valid && !(x == px + 1u && sh != 0u)) pw = *reinterpret_cast<const uint32_t *>(obase + x - sh);
+            const uint32_t v = valid ? (pw >> (8u * sh)) & 0xFFu : 0u;
+            px = valid ? x : 0xFFFFFFF0u;
+            w[k >> 2] |= v << (8 * (k & 3));
+        }
+        return;
+    }
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
@@ -251,7 +272,7 @@ __device__ __forceinline__ void p2_mbar_wait(uint64_t *mbar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(p2_smem_addr(mbar)), "r"(parity) : "memory");
 }
 #endif
-template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false, bool OWNER = false>
+template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false, bool OWNER = false, bool WORDS = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
                                                  const uint8_t *plane = nullptr, uint64_t *mbar = nullptr, uint32_t *mphase = nullptr)
@@ -314,7 +335,7 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
                 carry = carry > strad ? carry : strad;
                 p2_owner_desc(q0, q0 - c, x, carry, row, d);
                 __syncwarp();
-                p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane, d);
+                p2_pass_b<WIDE, RING, PLANE, WORDS>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane, d);
                 r_lo = r_next;
                 owner_done = true;
             }
@@ -326,7 +347,7 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         __syncwarp();
         p2_pass_a_long<WIDE, WS>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
+        p2_pass_b<WIDE, RING, PLANE, WORDS>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
         }
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (PLANE) __syncwarp();     /* an MSZIP overflow frame reads the bytes it is about to replace (ZipLaneC::qbase): every load before any store */
