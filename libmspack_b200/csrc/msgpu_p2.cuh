@@ -130,80 +130,9 @@ MS_D void p2_pass_a_long(int lane, uint32_t c, uint32_t cend, const uint32_t *wa
     }
 }
 
-/* Pass A, OWNER form (the plain instantiation, chunks that no overlapping match reaches into).  The record-parallel fill above
- * costs a warp as many trips as its longest match of each round and leaves 12.7 of 32 threads active in its store loop (25 % of
- * the kernel's instructions, profiles/r2_p2_f.txt).  Here a record only leaves ONE word - its b = off | len << 22 - at its start
- * position, and every lane then derives the descriptors of its own 16 positions from the marks: the record in effect at a
- * position is the last mark at or before it, a position is inside it while (position - mark position) < len.  The mark that is in
- * effect when a lane's row begins comes from the lanes below: records are disjoint and sorted, so it is the one with the largest
- * END, and (end - chunk start) << 22 | off fits one word (lengths <= 259, offsets < 2^22): an exclusive max-scan over the lanes,
- * seeded with the match that straddles the chunk start.  No loop depends on a match length, every lane is active throughout, and
- * the descriptors stay in registers for pass B. */
-MS_D void p2_owner_clear(uint32_t q0, uint32_t c, uint32_t *src) {
-    uint32_t *row = src + P2_SIDX(q0 - c);
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) row[k] = 0;
-}
-/* marks of the records that START inside [c, cend); returns what p2_pass_a_records returns; ovl |= 1 if an overlapping match
- * (off < len) reaches into the chunk - such chunks take the general path */
-template <int WS>
-MS_D int p2_owner_marks(int lane, int r_lo, uint32_t c, uint32_t cend, const uint32_t *wa, const uint32_t *wb, uint32_t *src, uint32_t &ovl) {
-    int next_lo = P2_WIN;
-#pragma unroll 1
-    for (int r = r_lo + lane; r < P2_WIN; r += 32) {
-        const uint32_t a = wa[r * WS], pos = rec_pos(a);
-        if (pos >= cend) { if (next_lo == P2_WIN) next_lo = r; break; }
-        const uint32_t b = wb[r * WS], len = rec_len(b), end = pos + len;
-        if (end > cend && next_lo == P2_WIN) next_lo = r;
-        if (end > c && rec_off(b) < len) ovl = 1u;
-        if (pos >= c) src[P2_SIDX(pos - c)] = b;
-    }
-    return next_lo;
-}
-/* the match straddling the chunk start, as a scan key (0 if there is none): record r_lo, if it starts in front of the chunk */
-template <int WS>
-MS_D uint32_t p2_owner_straddler(int r_lo, uint32_t c, const uint32_t *wa, const uint32_t *wb) {
-    if (r_lo >= P2_WIN) return 0u;
-    const uint32_t a = wa[r_lo * WS], b = wb[r_lo * WS], pos = rec_pos(a), end = pos + rec_len(b);
-    return (pos < c && end > c) ? ((end - c) << 22) | rec_off(b) : 0u;
-}
-/* this lane's marks into x[]; returns the scan key of its last mark (0 if it has none).  prel0 = q0 - c */
-MS_D uint32_t p2_owner_key(uint32_t prel0, const uint32_t *row, uint32_t x[16]) {
-    uint32_t last = 0, lk = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) { x[k] = row[k]; const bool m = x[k] != 0; last = m ? x[k] : last; lk = m ? k : lk; }
-    return last ? ((prel0 + lk + rec_len(last)) << 22) | rec_off(last) : 0u;
-}
-/* descriptors of this lane's 16 positions into d[] and into its row (other lanes' pointer jumps read them); carry = the key in
- * effect when the row begins */
-MS_D void p2_owner_desc(uint32_t q0, uint32_t prel0, const uint32_t x[16], uint32_t carry, uint32_t *row, uint32_t d[16]) {
-    constexpr bool WIDE = false;
-    uint32_t cur_end = carry >> 22, cur_off = rec_off(carry);
-#pragma unroll
-    for (uint32_t k = 0; k < 16; k++) {
-        const bool m = x[k] != 0;
-        cur_end = m ? prel0 + k + rec_len(x[k]) : cur_end;
-        cur_off = m ? rec_off(x[k]) : cur_off;
-        const uint32_t p = q0 + k;
-        d[k] = (prel0 + k < cur_end) ? p - cur_off + P2_SBIAS : P2_LIT | (p + P2_SBIAS);
-        row[k] = d[k];
-    }
-}
-
-/* Pass B: fetch this lane's 16 bytes [q0, q0+16) (little-endian in 4 words; positions >= size give 0).  A source inside
- * the current chunk is followed through the shared descriptors to ITS source (pointer jumping; positions strictly
- * decrease so it terminates; literal descriptors are negative as int32 and end the walk).  All walks first, then all
- * byte loads, so the loads overlap.  A source before the unit's first byte reads as zero - except for the ref_len bytes
- * directly in front of the unit, the reference data of an LZX DELTA unit (WIDE only). */
-/* WORDS: a byte is taken out of the aligned 4-byte word that holds it, and a position whose source directly follows its left
- * neighbour's inside the same word re-uses that word instead of loading again.  The resolve kernel is bound by the load/store
- * unit (l1tex__data_pipe_lsu_wavefronts 87 % of peak, profiles/r2_p2_f.txt) and 41 % of its wavefronts are these byte loads - 8 cache
- * lines per warp-instruction; with matches of ~5 bytes most lanes sit out most of the 16 load instructions.  The word may reach
- * up to 3 bytes beyond the byte asked for: inside the same 16-byte-aligned unit, or the slack every output buffer has behind it
- * (include/msgpu.h: 16 bytes). */
-template <bool WIDE, bool RING = false, bool PLANE = false, bool WORDS = false>
+template <bool WIDE, bool RING = false, bool PLANE = false>
 MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src, const uint8_t *unit_out, uint32_t g0, uint32_t w[4], uint32_t ref_len = 0,
-                    const uint32_t *hist = nullptr, const uint8_t *plane = nullptr, const uint32_t *dreg = nullptr)      /* dreg: this lane's descriptors, if pass A kept them (owner form) */
+                    const uint32_t *hist = nullptr, const uint8_t *plane = nullptr)
 {
     w[0] = w[1] = w[2] = w[3] = 0;
     if (q0 >= size) return;
@@ -213,7 +142,7 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
     uint32_t d[16];
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
-        uint32_t x = (k < n) ? (dreg ? dreg[k] : row[k]) : P2_LIT;
+        uint32_t x = (k < n) ? row[k] : P2_LIT;
 #pragma unroll 1
         while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];
         d[k] = PLANE ? x : (x & ~P2_LIT);         /* (PLANE keeps the literal flag: an overflow frame's literals sit in its plane) */
@@ -221,21 +150,6 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
     const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
     uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;    /* descriptors below this lie before the unit */
     if (WIDE) ulim = ulim > ref_len ? ulim - ref_len : 0u;
-    if (WORDS && !RING && !PLANE) {
-        const uint32_t a0 = (uint32_t) reinterpret_cast<uintptr_t>(obase);
-        uint32_t px = 0xFFFFFFF0u, pw = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 16; k++) {
-            const uint32_t x = d[k];
-            const bool valid = k < n && x >= ulim;
-            const uint32_t sh = (a0 + x) & 3u;
-            if (valid && !(x == px + 1u && sh != 0u)) pw = *reinterpret_cast<const uint32_t *>(obase + x - sh);
-            const uint32_t v = valid ? (pw >> (8u * sh)) & 0xFFu : 0u;
-            px = valid ? x : 0xFFFFFFF0u;
-            w[k >> 2] |= v << (8 * (k & 3));
-        }
-        return;
-    }
 #pragma unroll
     for (uint32_t k = 0; k < 16; k++) {
         uint32_t v = 0, x = d[k];
@@ -272,7 +186,7 @@ __device__ __forceinline__ void p2_mbar_wait(uint64_t *mbar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(p2_smem_addr(mbar)), "r"(parity) : "memory");
 }
 #endif
-template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false, bool OWNER = false, bool WORDS = false>
+template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
                                                  const uint8_t *plane = nullptr, uint64_t *mbar = nullptr, uint32_t *mphase = nullptr)
@@ -293,8 +207,7 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
                 if (lane == 0) p2_bulk_load(wa, recs + wbase, cnt * 8u, mbar);
             }
             if (lane == 0) longq[0] = 0;
-            if (OWNER) p2_owner_clear(q0, c, src);            /* (the copy is in flight) */
-            else p2_pass_a_literals<WIDE>(q0, c, src);
+            p2_pass_a_literals<WIDE>(q0, c, src);             /* (the copy is in flight) */
             if (reload) {
                 p2_mbar_wait(mbar, *mphase & 1u); *mphase += 1u;
                 for (int j = lane; j < P2_WIN; j += 32) if (wbase + (uint32_t) j > nrec || (uint32_t) j >= cnt) { wa[2 * j] = size; wa[2 * j + 1] = 0; }   /* behind the sentinel: sentinels */
@@ -317,38 +230,12 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         p2_pass_a_literals<WIDE>(q0, c, src);
         }
         __syncwarp();
-        bool owner_done = false;
-        if (OWNER) {
-            static_assert(!OWNER || (!WIDE && !RING && !PLANE && BULK), "the owner form of pass A is the plain instantiation's");
-            uint32_t ovl = 0;
-            const int nlo_o = p2_owner_marks<WS>(lane, r_lo, c, cend, wa, wb, src, ovl);
-            const int r_next = __reduce_min_sync(0xFFFFFFFFu, nlo_o);      /* (a warp sync: the marks are visible) */
-            if (!__any_sync(0xFFFFFFFFu, ovl != 0)) {
-                uint32_t x[16], d[16];
-                uint32_t *row = src + P2_SIDX(q0 - c);
-                const uint32_t strad = p2_owner_straddler<WS>(r_lo, c, wa, wb);
-                uint32_t v = p2_owner_key(q0 - c, row, x);
-#pragma unroll
-                for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, sft); if (lane >= sft) v = v > t ? v : t; }
-                uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, v, 1);
-                if (lane == 0) carry = 0;
-                carry = carry > strad ? carry : strad;
-                p2_owner_desc(q0, q0 - c, x, carry, row, d);
-                __syncwarp();
-                p2_pass_b<WIDE, RING, PLANE, WORDS>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane, d);
-                r_lo = r_next;
-                owner_done = true;
-            }
-            else { p2_pass_a_literals<WIDE>(q0, c, src); __syncwarp(); }      /* an overlapping match: the general path, over the marks */
-        }
-        if (!owner_done) {
         int nlo = p2_pass_a_records<WIDE, WS>(lane, r_lo, c, cend, wa, wb, src, longq);
         r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);            /* also orders the descriptor stores (it is a warp sync) */
         __syncwarp();
         p2_pass_a_long<WIDE, WS>(lane, c, cend, wa, wb, src, longq);
         __syncwarp();
-        p2_pass_b<WIDE, RING, PLANE, WORDS>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
-        }
+        p2_pass_b<WIDE, RING, PLANE>(q0, c, size, src, unit_out, g0, w, ref_len, hist, plane);
         uint8_t *dst = unit_out + (size_t) g0 + q0;
         if (PLANE) __syncwarp();     /* an MSZIP overflow frame reads the bytes it is about to replace (ZipLaneC::qbase): every load before any store */
         if (q0 + 16 <= size && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {

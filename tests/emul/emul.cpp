@@ -18,11 +18,6 @@
 #include "../../libmspack_b200/csrc/msgpu_p2.cuh"
 
 /* P2 for one frame, lanes run one after another (a lane only reads output bytes of EARLIER chunks, or literals) */
-/* the plain instantiation's owner form of pass A (msgpu_p2.cuh p2_owner_*): same per-lane functions as the kernel, the warp's max-scan
- * written out as a loop over the 32 lanes */
-static bool g_p2_owner = true, g_p2_words = false;      /* mode bit 0x1000: word loads in pass B */
-static uint64_t g_owner_chunks = 0, g_general_chunks = 0;
-extern "C" void emul_p2_chunk_counts(uint64_t *o) { o[0] = g_owner_chunks; o[1] = g_general_chunks; }        /* emul_decode_unit mode bit 0x800 turns it off (the general pass A on every chunk) */
 template <bool WIDE, bool RING = false, bool PLANE = false>
 static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0, uint32_t ref_len, const uint32_t *hist = nullptr,
                           const uint8_t *plane = nullptr) {
@@ -38,33 +33,6 @@ static void emul_p2_frame(const MsRec *recs, uint32_t nrec, uint32_t size, uint8
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
         longq[0] = 0;
         for (uint32_t k = 0; k < P2_SRC_WORDS; k++) src[k] = 0xDEADBEEFu;
-        if (!WIDE && !RING && !PLANE && g_p2_owner) {
-            uint32_t ovl = 0; int nlo_o = P2_WIN;
-            for (int lane = 0; lane < 32; lane++) p2_owner_clear(c + 16u * lane, c, src);
-            for (int lane = 0; lane < 32; lane++) { int v = p2_owner_marks<1>(lane, r_lo, c, cend, wa.data(), wb.data(), src, ovl); if (v < nlo_o) nlo_o = v; }
-            if (!ovl) {
-                uint32_t x[32][16], d[32][16], key[32];
-                const uint32_t strad = p2_owner_straddler<1>(r_lo, c, wa.data(), wb.data());
-                for (int lane = 0; lane < 32; lane++) key[lane] = p2_owner_key(16u * lane, src + P2_SIDX(16u * lane), x[lane]);
-                uint32_t run = 0;                                   /* exclusive max-scan */
-                for (int lane = 0; lane < 32; lane++) {
-                    const uint32_t carry = run > strad ? run : strad;
-                    p2_owner_desc(c + 16u * lane, 16u * lane, x[lane], carry, src + P2_SIDX(16u * lane), d[lane]);
-                    if (key[lane] > run) run = key[lane];
-                }
-                for (int lane = 0; lane < 32; lane++) {
-                    if (g_p2_words) p2_pass_b<WIDE, RING, PLANE, true>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist, plane, d[lane]);
-                    else p2_pass_b<WIDE, RING, PLANE>(c + 16u * lane, c, size, src, unit_out, g0, w[lane], ref_len, hist, plane, d[lane]);
-                }
-                for (int lane = 0; lane < 32; lane++) {
-                    uint32_t q0 = c + 16u * lane;
-                    for (uint32_t k = 0; k < 16 && q0 + k < size; k++) unit_out[(size_t) g0 + q0 + k] = (uint8_t) (w[lane][k >> 2] >> (8 * (k & 3)));
-                }
-                r_lo = nlo_o; g_owner_chunks++;
-                continue;
-            }
-        }
-        g_general_chunks++;
         for (int lane = 0; lane < 32; lane++) p2_pass_a_literals<WIDE>(c + 16u * lane, c, src);
         int nlo = P2_WIN;
         for (int lane = 0; lane < 32; lane++) { int v = p2_pass_a_records<WIDE>(lane, r_lo, c, cend, wa.data(), wb.data(), src, longq); if (v < nlo) nlo = v; }
@@ -113,7 +81,6 @@ extern "C" uint32_t emul_last_produced() { return g_last_produced; }
 extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uint8_t *out_base, int frames_per_round) {
     int F = (frames_per_round & 0xFF) > 0 ? (frames_per_round & 0xFF) : 1;
     if (u->codec == MSGPU_CODEC_MSZIP && (u->flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR)) && F < 2) F = 2;      /* as run_wave does */
-    g_p2_owner = (frames_per_round & 0x800) == 0; g_p2_words = (frames_per_round & 0x1000) != 0;
     const bool force_wide = (frames_per_round & 0x100) != 0;      /* run a plain LZX unit through the DELTA / WIDE instantiations (mixed waves) */
     std::vector<MsRec> recs((size_t) F * MS_MAXREC);
     std::vector<MsFrameInfo> finfo(F);

@@ -436,20 +436,3 @@ def test_device_logic_mszip_repair_mode(emul, oracle_ref, seed):
 
 
 
-
-P2_FORM_CASES = [(CODEC_LZX, dict(window_bits=21)), (CODEC_LZX, dict(window_bits=16, unit_bytes=100000, block_mode=4)), (CODEC_LZX, dict(data="zeros")),
-                 (CODEC_LZX, dict(data="binary", unit_bytes=50001)), (CODEC_MSZIP, dict(unit_bytes=70000)), (CODEC_MSZIP, dict(data="binary", unit_bytes=12345)),
-                 (CODEC_QUANTUM, dict(window_bits=17, unit_bytes=40000)), (CODEC_QUANTUM, dict(window_bits=10, unit_bytes=9000, data="zeros"))]
-
-
-@pytest.mark.parametrize("codec,kw", P2_FORM_CASES, ids=lambda c: str(c))
-def test_resolve_stage_forms_agree_with_the_reference(emul, oracle_ref, codec, kw):
-    """The three forms of the resolve stage's pass A / pass B (msgpu_p2.cuh): the general record-parallel fill (mode bit 0x800: on every
-    chunk), the owner form (default: one mark per record, descriptors derived per lane; chunks an overlapping match reaches into
-    fall back to the general fill) and the owner form with word loads in pass B (0x1000) - same bytes as the reference."""
-    b = gen.make_batch(codec, 10, **kw)
-    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
-    for form in (0, 0x800, 0x1000):
-        for fpr in (1, 2):
-            o2, s2 = emul(b.units, b.comp, b.out_bytes, form | 0x400 | fpr)
-            assert_same(b.units, o1, s1, o2, s2, f"form {form:#x} F={fpr} {kw}")
