@@ -249,6 +249,80 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
     }
 }
 
+/* The same frame resolve, SOFTWARE-PIPELINED over the chunks (plain BULK instantiation).  The kernel is latency bound at the 32
+ * warps per SM its registers allow - 3.3 of the 11 cycles per issued instruction are spent waiting for the scattered byte loads
+ * of the match sources (profiles/r2_p2_f.txt) - and nothing in pass A of chunk c + 1 depends on the bytes of chunk c.  So the 16
+ * byte loads of chunk c are ISSUED, pass A of chunk c + 1 runs while they are in flight, and only then are the bytes packed and
+ * stored.  One descriptor array is enough: pass A of c + 1 may overwrite it as soon as every lane has finished its pointer jumps
+ * of chunk c (a warp sync), and the byte loads need registers only.  Sources of chunk c + 1 that lie in chunk c are read after
+ * the store of chunk c and the sync behind it, as before. */
+template <bool WIDE>
+__device__ __forceinline__ void p2_resolve_frame_pipe(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
+                                                      uint32_t *wa, uint32_t *src, uint32_t *longq, uint32_t ref_len, uint64_t *mbar, uint32_t *mphase)
+{
+    constexpr int WS = 2;
+    uint32_t *wb = wa + 1;
+    uint32_t wbase = 0, wcover = 0; bool loaded = false;
+    int r_lo = 0;
+    if (size == 0) return;
+    auto pass_a = [&](uint32_t c) {
+        const bool reload = !loaded || (c + P2_CHUNK > wcover && wcover < size);
+        const uint32_t q0 = c + 16u * (uint32_t) lane, cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
+        uint32_t cnt = 0;
+        if (reload) {
+            wbase += (uint32_t) r_lo; r_lo = (int) (wbase & 1u); wbase &= ~1u;
+            cnt = MS_MAXREC - wbase < (uint32_t) P2_WIN ? MS_MAXREC - wbase : (uint32_t) P2_WIN;
+            __syncwarp();
+            if (lane == 0) p2_bulk_load(wa, recs + wbase, cnt * 8u, mbar);
+        }
+        if (lane == 0) longq[0] = 0;
+        p2_pass_a_literals<WIDE>(q0, c, src);
+        if (reload) {
+            p2_mbar_wait(mbar, *mphase & 1u); *mphase += 1u;
+            for (int j = lane; j < P2_WIN; j += 32) if (wbase + (uint32_t) j > nrec || (uint32_t) j >= cnt) { wa[2 * j] = size; wa[2 * j + 1] = 0; }
+            __syncwarp();
+            wcover = rec_pos(wa[2 * (P2_WIN - 1)]); loaded = true;
+        }
+        __syncwarp();
+        const int nlo = p2_pass_a_records<WIDE, WS>(lane, r_lo, c, cend, wa, wb, src, longq);
+        r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);
+        __syncwarp();
+        p2_pass_a_long<WIDE, WS>(lane, c, cend, wa, wb, src, longq);
+        __syncwarp();
+    };
+    pass_a(0);
+    const uint8_t *obase = unit_out + ((int64_t) g0 - P2_SBIAS);
+    uint32_t ulim = g0 < (uint32_t) P2_SBIAS ? (uint32_t) P2_SBIAS - g0 : 0u;
+    if (WIDE) ulim = ulim > ref_len ? ulim - ref_len : 0u;
+    for (uint32_t c = 0; c < size; c += P2_CHUNK) {
+        const uint32_t q0 = c + 16u * (uint32_t) lane;
+        const uint32_t n = q0 < size ? (size - q0 < 16 ? size - q0 : 16) : 0u;
+        const uint32_t inchunk = c + P2_SBIAS;
+        const uint32_t *row = src + P2_SIDX(q0 - c);
+        uint32_t v[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) {                      /* pointer jumps (p2_pass_b) */
+            uint32_t x = (k < n) ? row[k] : P2_LIT;
+#pragma unroll 1
+            while ((int32_t) x >= (int32_t) inchunk) x = src[P2_SIDX(x - inchunk)];
+            v[k] = x & ~P2_LIT;
+        }
+        __syncwarp();                                            /* nobody reads this chunk's descriptors any more */
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) v[k] = (k < n && v[k] >= ulim) ? (uint32_t) obase[v[k]] : 0u;      /* issued, not yet needed */
+        if (c + P2_CHUNK < size) pass_a(c + P2_CHUNK);
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) asm volatile("" : "+r"(v[k]) :: "memory");      /* (keeps the first use of a loaded byte behind pass A: ptxas would hoist the shifts) */
+        uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k++) w[k >> 2] |= v[k] << (8 * (k & 3));
+        uint8_t *dst = unit_out + (size_t) g0 + q0;
+        if (n == 16 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (uint32_t k = 0; k < n; k++) dst[k] = (uint8_t) (w[k >> 2] >> (8 * (k & 3)));
+        __syncwarp();                                            /* the chunk is visible to the whole warp before anyone reads it back */
+    }
+}
+
 /* LZX E8 call translation of one finished frame (lzxd.c:706-737), one warp.  `data` = first byte
  * of the frame, curpos0 = the stream offset of that byte (lzx->offset), filesize = intel_filesize. */
 __device__ __forceinline__ void e8_translate_frame(int lane, uint8_t *data, uint32_t frame_size, int32_t curpos0, int32_t filesize)
