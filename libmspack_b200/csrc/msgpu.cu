@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
  * reference translates a COPY of each frame because later matches must see the untranslated bytes; here the unit's warp runs the
  * translation once the unit's last frame has been resolved - nothing reads those bytes as match sources any more - while they
  * are still in L1 / L2, instead of a separate kernel over the whole batch. */
-template <bool WIDE, bool BULK = false, bool PIPE = false>      /* PIPE: the software-pipelined frame resolve (msgpu_p2.cuh p2_resolve_frame_pipe) */
+template <bool WIDE, bool BULK = false>      /* BULK: record window by the copy engine + software-pipelined chunks (msgpu_p2.cuh p2_resolve_frame_pipe) */
 __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32_t first, uint32_t nslots, const int32_t *e8info, const uint32_t *e8base)
 {
     __shared__ __align__(16) uint32_t s_wa[P2_WARPS][P2_WIN], s_wb[P2_WARPS][P2_WIN];      /* BULK: s_wa[w] .. s_wb[w] is not contiguous - it uses s_w2 */
@@ -153,10 +153,8 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
     for (int f = 0; f < a.F; f++) {
         MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
         if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
-        if (BULK && PIPE) p2_resolve_frame_pipe<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        if (BULK) p2_resolve_frame_pipe<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_w2[BULK ? warp : 0], s_src[warp], s_longq[warp], ref_len, &s_mbar[warp], &mphase);
-        else if (BULK) p2_resolve_frame<WIDE, false, false, true>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
-                               s_w2[BULK ? warp : 0], s_w2[BULK ? warp : 0] + 1, s_src[warp], s_longq[warp], ref_len, nullptr, nullptr, &s_mbar[warp], &mphase);
         else
         p2_resolve_frame<WIDE, false, false>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
@@ -296,7 +294,6 @@ struct msgpu_ctx {
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
     int dev_streams = 3;  /* MSGPU_STREAMS=1: everything of a device-buffer batch in the caller's stream order (default: mixed batches run each codec on a stream of its own) */
-    int p2_pipe = 0;      /* MSGPU_P2_PIPE=1: the software-pipelined resolve (A/B) */
     int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
@@ -335,7 +332,6 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_P2_BULK"); c->p2_bulk = v ? atoi(v) : 1; }
-    { const char *v = getenv("MSGPU_P2_PIPE"); c->p2_pipe = v ? atoi(v) : 0; }
     { const char *v = getenv("MSGPU_STREAMS"); if (v) { int k = atoi(v); c->dev_streams = k < 1 ? 1 : (k > (int) msgpu_ctx::NSUB ? (int) msgpu_ctx::NSUB : k); } }
     /* the entropy kernels use most of an SM's shared memory: opt in */
     cudaError_t ae = cudaSuccess;
@@ -647,7 +643,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
          * headline batch (profiles/r2_p2_bulk_ab.txt); MSGPU_P2_BULK=0 keeps the load-by-lanes variant for A/B runs */
         if (any_delta && ctx->p2_bulk) k_p2_resolve<true, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
         else if (any_delta) k_p2_resolve<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
-        else if (ctx->p2_bulk && ctx->p2_pipe) k_p2_resolve<false, true, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
         else if (ctx->p2_bulk) k_p2_resolve<false, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
         else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
     };

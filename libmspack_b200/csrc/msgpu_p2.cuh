@@ -169,10 +169,8 @@ MS_D void p2_pass_b(uint32_t q0, uint32_t c, uint32_t size, const uint32_t *src,
 }
 
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
-/* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory. */
-/* BULK: the record window is filled by the copy engine (cp.async.bulk into shared memory, completion on an mbarrier) instead of
- * nine 8-byte loads per lane; the chunk's literal descriptors are written while the copy is in flight.  The window then holds the
- * records as they lie in memory (wa = window, wb = wa + 1, stride 2) and starts at an even record index (16-byte source alignment). */
+/* Resolve one frame with one warp.  wa/wb: this warp's P2_WIN-entry windows in shared memory, loaded by the lanes (the ring / plane /
+ * chain kernels and MSGPU_P2_BULK=0; the main resolve kernel uses p2_resolve_frame_pipe below). */
 #if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
 __device__ __forceinline__ uint32_t p2_smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void p2_mbar_init(uint64_t *mbar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(p2_smem_addr(mbar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -186,36 +184,18 @@ __device__ __forceinline__ void p2_mbar_wait(uint64_t *mbar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(p2_smem_addr(mbar)), "r"(parity) : "memory");
 }
 #endif
-template <bool WIDE, bool RING = false, bool PLANE = false, bool BULK = false>
+template <bool WIDE, bool RING = false, bool PLANE = false>
 __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, uint32_t nrec, uint32_t size, uint8_t *unit_out, uint32_t g0,
                                                  uint32_t *wa, uint32_t *wb, uint32_t *src, uint32_t *longq, uint32_t ref_len, const uint32_t *hist = nullptr,
-                                                 const uint8_t *plane = nullptr, uint64_t *mbar = nullptr, uint32_t *mphase = nullptr)
+                                                 const uint8_t *plane = nullptr)
 {
-    constexpr int WS = BULK ? 2 : 1;
+    constexpr int WS = 1;
     uint32_t wbase = 0, wcover = 0; bool loaded = false;
     int r_lo = 0;                                              /* first window record ending beyond the chunk start */
     for (uint32_t c = 0; c < size; c += P2_CHUNK) {
         const bool reload = !loaded || (c + P2_CHUNK > wcover && wcover < size);
         uint32_t q0 = c + 16u * (uint32_t) lane, w[4];
         const uint32_t cend = c + P2_CHUNK < size ? c + P2_CHUNK : size;
-        if (BULK) {
-            uint32_t cnt = 0;
-            if (reload) {
-                wbase += (uint32_t) r_lo; r_lo = (int) (wbase & 1u); wbase &= ~1u;      /* (16-byte aligned source) */
-                cnt = MS_MAXREC - wbase < (uint32_t) P2_WIN ? MS_MAXREC - wbase : (uint32_t) P2_WIN;
-                __syncwarp();
-                if (lane == 0) p2_bulk_load(wa, recs + wbase, cnt * 8u, mbar);
-            }
-            if (lane == 0) longq[0] = 0;
-            p2_pass_a_literals<WIDE>(q0, c, src);             /* (the copy is in flight) */
-            if (reload) {
-                p2_mbar_wait(mbar, *mphase & 1u); *mphase += 1u;
-                for (int j = lane; j < P2_WIN; j += 32) if (wbase + (uint32_t) j > nrec || (uint32_t) j >= cnt) { wa[2 * j] = size; wa[2 * j + 1] = 0; }   /* behind the sentinel: sentinels */
-                __syncwarp();
-                wcover = rec_pos(wa[2 * (P2_WIN - 1)]); loaded = true;
-            }
-        }
-        else {
         if (reload) {
             wbase += (uint32_t) r_lo; r_lo = 0;
             __syncwarp();
@@ -228,7 +208,6 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
         }
         if (lane == 0) longq[0] = 0;
         p2_pass_a_literals<WIDE>(q0, c, src);
-        }
         __syncwarp();
         int nlo = p2_pass_a_records<WIDE, WS>(lane, r_lo, c, cend, wa, wb, src, longq);
         r_lo = __reduce_min_sync(0xFFFFFFFFu, nlo);            /* also orders the descriptor stores (it is a warp sync) */
@@ -249,9 +228,13 @@ __device__ __forceinline__ void p2_resolve_frame(int lane, const MsRec *recs, ui
     }
 }
 
-/* The same frame resolve, SOFTWARE-PIPELINED over the chunks (plain BULK instantiation).  The kernel is latency bound at the 32
- * warps per SM its registers allow - 3.3 of the 11 cycles per issued instruction are spent waiting for the scattered byte loads
- * of the match sources (profiles/r2_p2_f.txt) - and nothing in pass A of chunk c + 1 depends on the bytes of chunk c.  So the 16
+/* The main resolve kernel's frame resolve.
+ * (1) The record window is filled by the copy engine (cp.async.bulk into shared memory, completion on an mbarrier) instead of
+ * nine 8-byte loads per lane; the chunk's literal descriptors are written while the copy is in flight.  The window holds the
+ * records as they lie in memory (wa = window, wb = wa + 1, stride 2) and starts at an even record index (16-byte source alignment).
+ * (2) It is SOFTWARE-PIPELINED over the chunks.  The unpipelined loop was latency bound at the 32 warps per SM its registers
+ * allow - 3.3 of the 11 cycles per issued instruction went into waiting for the scattered byte loads of the match sources
+ * (profiles/r2_p2_f.txt; 0.4 of 9.6 now, profiles/r2_p2_pipe_k.txt) - and nothing in pass A of chunk c + 1 depends on the bytes of chunk c.  So the 16
  * byte loads of chunk c are ISSUED, pass A of chunk c + 1 runs while they are in flight, and only then are the bytes packed and
  * stored.  One descriptor array is enough: pass A of c + 1 may overwrite it as soon as every lane has finished its pointer jumps
  * of chunk c (a warp sync), and the byte loads need registers only.  Sources of chunk c + 1 that lie in chunk c are read after
