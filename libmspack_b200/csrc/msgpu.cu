@@ -245,7 +245,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
  * wave.  Round 2 measured every shape round 1 had prepared (profiles/r2_variants.txt) and kept one per codec:
  *   MSZIP   448 lanes, 124-entry head, byte-wise literal stores            (round-1 shape 18: P1 8.65 -> 7.89 ms on 32 768 units)
  *   LZX     448 lanes, LzxSharedQ (256-entry packed head + LENGTH head), exact-need refill   (shape 31: P1 9.02 -> 8.52 ms)
- *   Quantum 224 lanes (symbol bytes in global memory), two-level model scan + loop-free renormalisation (shape 3: P1 77.3 -> 56.0 ms
+ *   Quantum 448 lanes (symbol bytes and the cold part of the frequency tables in global memory), two-level model scan + loop-free renormalisation (shape 3: P1 77.3 -> 56.0 ms
  *           on 16 384 units with 160 lanes), warp-cooperative model updates
  * the other 32 shapes and the byte-parallel pass A of P2 (6.77 against 6.20 ms) measured slower or equal and were deleted. */
 #define ZIP_NT 448
@@ -253,7 +253,7 @@ __global__ void k_set_status(int32_t *status, const uint32_t *idx, const int32_t
 #define LZX_NT 448
 #define LZX_HEADN 256
 #define LZX_H8LB 104
-#define QTM_NT 224
+#define QTM_NT 448
 #define LZXD_NT 448          /* the one shape of the LZX DELTA instantiation */
 #define LZXD_HEADN 72
 
@@ -450,7 +450,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     /* sub-wave size: must be a multiple of 32 (a warp and its aux block may not straddle two sub-waves); a multiple of the
      * CTA size keeps the last CTA of every sub-wave full.  Default: about one resident P1 CTA per SM. */
     const uint32_t one = (nl && !nz && !nq) ? lzx_nt : ((nz && !nl && !nq) ? zip_nt : (uint32_t) QTM_NT);
-    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 448u;   /* mixed batches: lcm of the 448- and 224-lane CTA shapes */
+    const uint32_t gran = (nl + nz + nq == nl || nl + nz + nq == nz || nl + nz + nq == nq) ? one : 448u;   /* mixed batches: every P1 kernel has 448-lane CTAs */
     uint32_t subsz = env ? (uint32_t) atoi(env) : 148u * one;
     const uint32_t nchains = (uint32_t) (chains.size() / 2);
     if (nchains) subsz = 0x40000000u;          /* a chain is resolved in order after ALL its blocks left P1: one sub-wave */

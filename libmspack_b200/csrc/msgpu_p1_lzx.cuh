@@ -440,9 +440,8 @@ struct LzxLaneC {
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
-#ifdef LZX_DEFER_LEN
             /* a LENGTH symbol beyond the LUT and the shared-memory head comes from L2 (45 % of P1's long-scoreboard stalls,
-             * profiles/r2_p1lzx_f.txt): the code's LENGTH is known without it, so the load is issued here and its value only
+             * profiles/r2_p1lzx_f.txt; deferring it: P1 8.51 -> 8.37 ms): the code's LENGTH is known without it, so the load is issued here and its value only
              * added in front of the match's range checks - the offset fields are decoded while it is in flight */
             uint32_t lgv = 0; bool lslow = false;
             if (ml == 7) {
@@ -460,15 +459,7 @@ struct LzxLaneC {
                 }
             }
             ml += 2;
-#define LZX_LEN_LATE() do { if (lslow) ml += lgv; } while (0)
-#else
-            if (ml == 7) {
-                if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
-                ml += length_sym(careful);
-            }
-            ml += 2;
-#define LZX_LEN_LATE() do { } while (0)
-#endif
+
             if (slot < 3) {                                         /* repeated offsets, lzxd.c:590-600, as selects */
                 const uint32_t r0 = R0;
                 off = slot == 0 ? r0 : (slot == 1 ? R1 : R2);
@@ -490,7 +481,7 @@ struct LzxLaneC {
                 else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;
             }
-            LZX_LEN_LATE();
+            if (lslow) ml += lgv;
             if (DELTA && is_delta && ml == 257) {                    /* lzxd.c:589-611: the longest length announces more */
                 lzx_refill(b);
                 if (careful) lzx_check(b, 3);

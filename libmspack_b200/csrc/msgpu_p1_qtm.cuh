@@ -47,6 +47,15 @@
  * Scans are Hillis-Steele over 64-entry scratch rows in shared memory, phase by phase (msgpu_core.cuh MS_LANES): the same source
  * runs on the device and in the host emulation.  Models of at most QTM_COOP_MIN entries (the selector) stay with their lane. */
 #define QTM_COOP_MIN 8
+/* Hot / cold split of the frequency tables.  The four literal models (64 entries each) are 65 % of a lane's table bytes, and a
+ * model is kept sorted by frequency (the re-sort), so a scan mostly ends within its first entries.  Only the first QTM_HOT entries
+ * of each literal model live in shared memory; entries QTM_HOT.. (and the sentinel) live in the unit's save area in global
+ * memory - where a multi-frame unit keeps all of them between launches anyway - and come through L1 / L2 when a scan, a rescale or
+ * a re-sort reaches them.  493 bytes of shared memory per lane instead of 941: 448 lanes (14 warps) per SM, ONE resident CTA wave
+ * for 65 536 units instead of two - the kernel is latency bound (IPC 1.1 per busy SM at 7 warps, profiles/r2_p1qtm_g.txt). */
+#define QTM_HOT  8
+#define QTM_COLD (4 * (65 - QTM_HOT))       /* entries that live in global memory */
+#define QTM_HENT (QTM_ENT - QTM_COLD)       /* entries that live in shared memory */
 /* Shared memory per lane: the frequency differences (802 bytes), group sums, totals, rescale counters = 941 bytes -> 224 lanes
  * (7 warps) per SM.  The models' SYMBOL bytes (401 per lane; one read per decoded symbol, rewritten only by a re-sort) live in
  * global memory instead - in the unit's save area, unit-major, where a multi-frame unit keeps them between launches anyway:
@@ -57,7 +66,7 @@ struct QtmShared {
     uint32_t ws[(NT + 31) / 32][3][64];  /* per warp: three scratch rows for the cooperative updates */
     uint32_t wsmin[(NT + 31) / 32];
     uint16_t grp[QTM_GRP * NT];
-    uint16_t cum[QTM_ENT * NT];       /* g[i] = cum[i] - cum[i+1] (see the header comment) */
+    uint16_t cum[QTM_HENT * NT];      /* g[i] = cum[i] - cum[i+1] (see the header comment): the hot entries, compact (hidx) */
     uint16_t tot[9 * NT];             /* T = cum[0] per model */
     uint8_t  shl[9 * NT];
 };
@@ -70,6 +79,10 @@ struct QtmLane {
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
 
+    uint16_t *gcum;                   /* the cold entries: the unit's save area, indexed like the reference's arrays */
+    /* entry i of model (base, midx): compact index among the hot entries / a reference to wherever it lives */
+    MS_M static int hidx(int base, int midx, int i) { return midx < 4 ? QM0 + QTM_HOT * midx + i : (midx == 8 ? i : base - QTM_COLD + i); }
+    MS_M static uint16_t &cref(uint16_t *hot, uint16_t *cold, int base, int midx, int i) { return (midx < 4 && i >= QTM_HOT) ? cold[base + i] : hot[hidx(base, midx, i) * NT]; }
     uint32_t *ws, *wsmin; uint32_t upd_pending; int upd_base, upd_midx, upd_ent;
     MS_M void bind(QtmShared<NT> *sh, int tid) {
         cum = sh->cum + tid; tot = sh->tot + tid; shl = sh->shl + tid; grp = sh->grp + tid;
@@ -100,13 +113,13 @@ struct QtmLane {
     /* all lanes, uniform arguments: update model (base, midx, entries) of lane L's stream */
     MS_M void coop_update(int L, uint8_t *lane_sym, int base, int midx, int entries) {
         const int me = MS_LANE_ID();
-        uint16_t *ocum = cum - me + L, *ogrp = grp - me + L, *otot = tot - me + L; uint8_t *osym = lane_sym, *oshl = shl - me + L;
+        uint16_t *ocum = cum - me + L, *ogc = reinterpret_cast<uint16_t *>(lane_sym - QTM_ENT * 2), *ogrp = grp - me + L, *otot = tot - me + L; uint8_t *osym = lane_sym, *oshl = shl - me + L;
         uint32_t *r0 = ws, *r1 = ws + 64, *r2 = ws + 128;
         const uint32_t s = (uint32_t) oshl[midx * NT] - 1u;
         const int gb = grp_base(midx);
         if (s) {
             /* rescale (qtmd.c:130-136) */
-            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; r0[i] = i < entries ? (uint32_t) ocum[(base + i) * NT] : 0u; } }
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; r0[i] = i < entries ? (uint32_t) cref(ocum, ogc, base, midx, i) : 0u; } }
             MS_PHASE_END();
             uint32_t *c = coop_scan<true>(r0, r1, [](uint32_t x, uint32_t y) { return x + y; });           /* the reference's cum[i] */
             uint32_t *o = c == r0 ? r1 : r0;
@@ -116,10 +129,10 @@ struct QtmLane {
             uint32_t *cn = (m == o) ? r2 : o;                        /* a row that is free now */
             MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; const uint32_t mm = m[i] > (uint32_t) entries ? m[i] : (uint32_t) entries; cn[i] = i < entries ? mm - (uint32_t) i : 0u; } }
             MS_PHASE_END();
-            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) ocum[(base + i) * NT] = (uint16_t) (cn[i] - (i + 1 < 64 ? cn[i + 1] : 0u)); } }
+            MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) cref(ocum, ogc, base, midx, i) = (uint16_t) (cn[i] - (i + 1 < 64 ? cn[i + 1] : 0u)); } }
             MS_PHASE_END();
             MS_LANES(vl) {
-                if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += ocum[(base + 8 * vl + j) * NT]; ogrp[(gb + vl) * NT] = (uint16_t) acc; }
+                if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += cref(ocum, ogc, base, midx, 8 * vl + j); ogrp[(gb + vl) * NT] = (uint16_t) acc; }
                 if (vl == 8) { otot[midx * NT] = (uint16_t) cn[0]; oshl[midx * NT] = (uint8_t) s; }
             }
             MS_PHASE_END();
@@ -128,7 +141,7 @@ struct QtmLane {
         /* re-sort (qtmd.c:138-164): rows hold f << 8 | sym */
         uint32_t *fy = r0, *sa = r1, *sb = r2;
         MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h;
-            fy[i] = i < entries ? ((((uint32_t) ocum[(base + i) * NT] + 1u) >> 1) << 8) | (uint32_t) osym[base + i] : 0u; } }
+            fy[i] = i < entries ? ((((uint32_t) cref(ocum, ogc, base, midx, i) + 1u) >> 1) << 8) | (uint32_t) osym[base + i] : 0u; } }
         MS_PHASE_END();
 #pragma unroll 1
         for (int guard = 0; guard < 64; guard++) {
@@ -160,9 +173,9 @@ struct QtmLane {
             MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int j = vl + 32 * h; fy[j] = nw[j]; } }
             MS_PHASE_END();
         }
-        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) { ocum[(base + i) * NT] = (uint16_t) (fy[i] >> 8); osym[base + i] = (uint8_t) fy[i]; } } }
+        MS_LANES(vl) { for (int h = 0; h < 2; h++) { const int i = vl + 32 * h; if (i < entries) { cref(ocum, ogc, base, midx, i) = (uint16_t) (fy[i] >> 8); osym[base + i] = (uint8_t) fy[i]; } } }
         MS_PHASE_END();
-        MS_LANES(vl) { if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += ocum[(base + 8 * vl + j) * NT]; ogrp[(gb + vl) * NT] = (uint16_t) acc; } }
+        MS_LANES(vl) { if (vl < 8 && 8 * vl < entries) { uint32_t acc = 0; for (int j = 0; j < 8 && 8 * vl + j < entries; j++) acc += cref(ocum, ogc, base, midx, 8 * vl + j); ogrp[(gb + vl) * NT] = (uint16_t) acc; } }
         MS_PHASE_END();
         MS_LANES(vl) { if (vl == 0) { uint32_t T = 0; for (int k = 0; 8 * k < entries; k++) T += ogrp[(gb + k) * NT]; otot[midx * NT] = (uint16_t) T; oshl[midx * NT] = 50; } }
         MS_PHASE_END();
@@ -182,7 +195,7 @@ struct QtmLane {
     MS_M void init_model(int base, int midx, int start, int len) {         /* qtmd.c:169-182: cum[i] = len - i  <=>  g[i] = 1, T = len */
         shl[midx * NT] = 4; tot[midx * NT] = (uint16_t) len;
 #pragma unroll 1
-        for (int i = 0; i <= len; i++) { sym[base + i] = (uint8_t) (start + i); cum[(base + i) * NT] = (uint16_t) (i < len ? 1 : 0); }
+        for (int i = 0; i <= len; i++) { sym[base + i] = (uint8_t) (start + i); cref(cum, gcum, base, midx, i) = (uint16_t) (i < len ? 1 : 0); }
         regroup(base, midx, len);
     }
 
@@ -199,10 +212,10 @@ struct QtmLane {
             uint32_t acc = 0;
 #pragma unroll 1
             for (int i = entries - 1; i >= 0; i--) {
-                old += cum[(base + i) * NT];                               /* the reference's cum[i] before the rescale */
+                old += cref(cum, gcum, base, midx, i);                               /* the reference's cum[i] before the rescale */
                 uint32_t c = old >> 1;
                 if (c <= nn) c = nn + 1;
-                cum[(base + i) * NT] = (uint16_t) (c - nn); acc += c - nn; nn = c;
+                cref(cum, gcum, base, midx, i) = (uint16_t) (c - nn); acc += c - nn; nn = c;
                 if ((i & 7) == 0) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
             }
             tot[midx * NT] = (uint16_t) nn;
@@ -212,26 +225,26 @@ struct QtmLane {
             uint32_t T = 0;
 #pragma unroll 1
             for (int i = 0; i < entries; i++) {                            /* :141-146 frequencies, halved, never zero */
-                uint32_t c = (uint16_t) (cum[(base + i) * NT] + 1); c >>= 1;
-                cum[(base + i) * NT] = (uint16_t) c;
+                uint32_t c = (uint16_t) (cref(cum, gcum, base, midx, i) + 1); c >>= 1;
+                cref(cum, gcum, base, midx, i) = (uint16_t) c;
             }
             /* the reference's in-place exchange sort; its (in)stability is part of the format (:148-150) */
 #pragma unroll 1
             for (int i = 0; i < entries - 1; i++) {
-                uint32_t ci = cum[(base + i) * NT], si = sym[base + i];
+                uint32_t ci = cref(cum, gcum, base, midx, i), si = sym[base + i];
 #pragma unroll 1
                 for (int j = i + 1; j < entries; j++) {
-                    uint32_t cj = cum[(base + j) * NT];
+                    uint32_t cj = cref(cum, gcum, base, midx, j);
                     if (ci < cj) {
                         uint32_t sj = sym[base + j];
-                        cum[(base + j) * NT] = (uint16_t) ci; sym[base + j] = (uint8_t) si;
+                        cref(cum, gcum, base, midx, j) = (uint16_t) ci; sym[base + j] = (uint8_t) si;
                         ci = cj; si = sj;
                     }
                 }
-                cum[(base + i) * NT] = (uint16_t) ci; sym[base + i] = (uint8_t) si;
+                cref(cum, gcum, base, midx, i) = (uint16_t) ci; sym[base + i] = (uint8_t) si;
             }
 #pragma unroll 1
-            for (int i = 0; i < entries; i++) T += cum[(base + i) * NT];   /* :162-164 back to cumulative: T = cum[0] */
+            for (int i = 0; i < entries; i++) T += cref(cum, gcum, base, midx, i);   /* :162-164 back to cumulative: T = cum[0] */
             tot[midx * NT] = (uint16_t) T;
             regroup(base, midx, entries);
         }
@@ -265,14 +278,18 @@ struct QtmLane {
             }
             gsel = gb + gi; j = gi << 3;
         }
+        /* the group's eight entries are all hot or all cold (QTM_HOT is a multiple of 8): one pointer and stride for the walk */
+        const bool cold = midx < 4 && j >= QTM_HOT;
+        const int cs = cold ? 1 : NT;
+        uint16_t *cp = cold ? gcum + base + j : cum + hidx(base, midx, j) * NT;
 #pragma unroll 1
-        for (;; j += 4) {
-            const uint32_t g0 = cum[(base + j) * NT], g1 = cum[(base + j + 1) * NT], g2 = cum[(base + j + 2) * NT], g3 = cum[(base + j + 3) * NT];
+        for (;; j += 4, cp += 4 * cs) {
+            const uint32_t g0 = cp[0], g1 = cp[cs], g2 = cp[2 * cs], g3 = cp[3 * cs];
             const uint32_t c1 = prev - g0, c2 = c1 - g1, c3 = c2 - g2, c4 = c3 - g3;
             if (j + 1 >= entries || c1 <= symf) { gj = g0; cur = c1; break; }
-            if (j + 2 >= entries || c2 <= symf) { gj = g1; cur = c2; prev = c1; j += 1; break; }
-            if (j + 3 >= entries || c3 <= symf) { gj = g2; cur = c3; prev = c2; j += 2; break; }
-            if (j + 4 >= entries || c4 <= symf) { gj = g3; cur = c4; prev = c3; j += 3; break; }
+            if (j + 2 >= entries || c2 <= symf) { gj = g1; cur = c2; prev = c1; j += 1; cp += cs; break; }
+            if (j + 3 >= entries || c3 <= symf) { gj = g2; cur = c3; prev = c2; j += 2; cp += 2 * cs; break; }
+            if (j + 4 >= entries || c4 <= symf) { gj = g3; cur = c4; prev = c3; j += 3; cp += 3 * cs; break; }
             prev = c4;
         }
         uint32_t s = sym[base + j];
@@ -281,7 +298,7 @@ struct QtmLane {
         Hn = (L + (prev * range) / c0 - 1) & 0xFFFFu;
         Ln = (L + (cur * range) / c0) & 0xFFFFu;
         H = Hn; L = Ln;
-        cum[(base + j) * NT] = (uint16_t) (gj + 8);            /* == cum[0..j] += 8 */
+        *cp = (uint16_t) (gj + 8);                             /* == cum[0..j] += 8 */
         grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
         if (c0 > 3800) {
@@ -435,6 +452,7 @@ struct QtmLane {
                     int nframes, uint8_t *save_area) {
         u = unit; recs = r; uout = l; finfo = fi; max_frames = nframes; save = save_area; f = 0; q = 0; limit = 0; frame_start_pos = 0;
         sym = save_area + QTM_ENT * 2;          /* the symbol bytes live in the unit's save area (see QtmShared) */
+        gcum = reinterpret_cast<uint16_t *>(save_area);      /* and so do the cold frequency entries (QTM_HOT) */
 #pragma unroll 1
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         const int wb = unit->window_bits, wb2 = wb * 2;
@@ -459,7 +477,7 @@ struct QtmLane {
             header_read = st.header_read; frame_todo = st.frame_todo;
             if (save && !done) {
 #pragma unroll 1
-                for (int i = 0; i < QTM_ENT; i++) { cum[i * NT] = reinterpret_cast<uint16_t *>(save)[i]; }
+                for (int m = 0; m < 9; m++) { const int mb = model_base(m), hn = m < 4 ? QTM_HOT : model_len(m) + 1; for (int i = 0; i < hn; i++) cum[hidx(mb, m, i) * NT] = gcum[mb + i]; }
 #pragma unroll 1
                 for (int i = 0; i < 9; i++) { shl[i * NT] = save[QTM_ENT * 3 + i]; tot[i * NT] = reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i]; }
                 regroup(QM0, 0, 64); regroup(QM1, 1, 64); regroup(QM2, 2, 64); regroup(QM3, 3, 64);
@@ -475,7 +493,7 @@ struct QtmLane {
         st.header_read = header_read; st.frame_todo = frame_todo;
         if (save && !done) {
 #pragma unroll 1
-            for (int i = 0; i < QTM_ENT; i++) { reinterpret_cast<uint16_t *>(save)[i] = cum[i * NT]; }
+            for (int m = 0; m < 9; m++) { const int mb = model_base(m), hn = m < 4 ? QTM_HOT : model_len(m) + 1; for (int i = 0; i < hn; i++) gcum[mb + i] = cum[hidx(mb, m, i) * NT]; }
 #pragma unroll 1
             for (int i = 0; i < 9; i++) { save[QTM_ENT * 3 + i] = shl[i * NT]; reinterpret_cast<uint16_t *>(save + QTM_ENT * 3 + 11)[i] = tot[i * NT]; }
         }
@@ -483,13 +501,15 @@ struct QtmLane {
 
     uint16_t *grp;
     /* first group sum of model midx (0-3 literals, 4-6 offsets, 7 length, 8 selector) */
+    MS_M static int model_base(int midx) { return midx < 4 ? QM0 + 65 * midx : (midx == 4 ? QM4 : (midx == 5 ? QM5 : (midx == 6 ? QM6 : (midx == 7 ? QM6L : QM7)))); }
+    MS_M int model_len(int midx) const { return midx < 4 ? 64 : (midx == 4 ? ent4 : (midx == 5 ? ent5 : (midx == 6 ? ent6 : (midx == 7 ? 27 : 7)))); }
     MS_M static int grp_base(int midx) { return midx < 4 ? 1 + 8 * midx : (midx == 4 ? 33 : (midx == 5 ? 36 : (midx == 6 ? 41 : (midx == 7 ? 47 : 0)))); }
     MS_M void regroup(int base, int midx, int entries) {              /* group sums from g[] */
         const int gb = grp_base(midx);
         uint32_t acc = 0;
 #pragma unroll 1
         for (int i = 0; i < entries; i++) {
-            acc += cum[(base + i) * NT];
+            acc += cref(cum, gcum, base, midx, i);
             if ((i & 7) == 7 || i == entries - 1) { grp[(gb + (i >> 3)) * NT] = (uint16_t) acc; acc = 0; }
         }
     }
