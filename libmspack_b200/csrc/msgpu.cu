@@ -472,7 +472,24 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     }
     subsz = (subsz + gran - 1) / gran * gran;
     const uint32_t nmaxc = nz > nl ? (nz > nq ? nz : nq) : (nl > nq ? nl : nq);
-    const uint32_t nsub = (nmaxc + subsz - 1) / subsz;
+    /* sub-wave k = entries [sub_lo[k], sub_lo[k + 1]) of EACH codec's list; every boundary is a multiple of the CTA size.
+     * Host buffers: the D2H engine is the floor of that path and cannot start before the first sub-wave has gone through
+     * H2D + P1 + P2 - and P1 takes the serial decode latency of a frame however few units it has.  So the first sub-waves are
+     * small and grow by 1.75x (the output of sub-wave k - 1 must keep the D2H engine busy until sub-wave k is ready: its
+     * input arrives at ~48 GB/s compressed, its output leaves at ~54 GB/s) up to the regular size. */
+    std::vector<uint32_t> sub_lo;
+    sub_lo.push_back(0);
+    if (h_in && !env && !nchains && !ctx->stage_timing && nmaxc > 4 * subsz) {
+        uint32_t sz = gran;
+        while (sub_lo.back() < nmaxc) {
+            uint32_t step = (sz + gran - 1) / gran * gran; if (step > subsz) step = subsz;
+            sub_lo.push_back(sub_lo.back() + step);
+            sz = sz + sz * 3 / 4; if (sz > subsz) sz = subsz;
+        }
+    }
+    else for (uint32_t p0 = 0; p0 < nmaxc; p0 += subsz) sub_lo.push_back(p0 + subsz < nmaxc ? p0 + subsz : (p0 / subsz + 1) * subsz);
+    if (sub_lo.size() < 2) sub_lo.push_back(subsz);
+    const uint32_t nsub = (uint32_t) sub_lo.size() - 1;
     if (nsub > 1000) return fail(ctx, MSGPU_ERR_ARGS, "too many sub-waves");
 
     CK(ctx->units.reserve((size_t) n * sizeof(msgpu_unit)), "alloc units");
@@ -584,7 +601,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (!h_in) return;
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (int c = 0; c < 3; c++) {
-            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt; uint64_t b0, b1;
+            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt; uint64_t b0, b1;
             if (f0 >= cnt) continue;
             io_range(*lists[c], f0, f1, false, b0, b1);
             b0 &= ~3ull;                                   /* keep 4-byte loads of the first unit inside the copied range */
@@ -596,7 +613,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (uint32_t sub = 0; sub < nsub && !bulk_out; sub++)
             for (int c = 0; c < 3 && !bulk_out; c++) {
-                uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt;
+                uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt;
                 if (f0 >= cnt) continue;
                 out_ranges(*lists[c], f0, f1, rng);
                 if (rng.size() > MAXR) bulk_out = true;
@@ -611,7 +628,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (!h_out || bulk_out) return;
         const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (int c = 0; c < 3; c++) {
-            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub * subsz, f1 = f0 + subsz < cnt ? f0 + subsz : cnt;
+            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt;
             if (f0 >= cnt) continue;
             out_ranges(*lists[c], f0, f1, rng);
             for (const auto &r : rng) cudaMemcpyAsync(h_out + r.first, reinterpret_cast<uint8_t *>(d_out) + r.first, r.second - r.first, cudaMemcpyDeviceToHost, st);
@@ -628,7 +645,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     size_t sev_used = ctx->stage_evs[0].size() + ctx->stage_evs[1].size() + ctx->stage_evs[2].size();
     for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
 
-    /* sub-wave k = entries [k * subsz, (k + 1) * subsz) of EACH codec's list (subsz is a multiple of the CTA
+    /* sub-wave k = entries [sub_lo[k], sub_lo[k + 1]) of EACH codec's list (every boundary is a multiple of the CTA
      * size, so warps and their aux blocks never straddle two sub-waves); P2 walks the same list ranges */
     const uint32_t rounds_planned = (maxfr + F - 1) / F;
     auto mark = [&](int stage, cudaStream_t st) {      /* stage timing: an event on either side of a launch */
@@ -649,12 +666,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     /* clear: zero the "units still running" counter in front of the round's kernels.  With a stream per codec every codec
      * counts in a slot of its own (w.sub = its stream index; there is one sub-wave), cleared in its own stream order. */
     auto launch_round = [&](uint32_t sub, cudaStream_t st_all, bool clear) {
-        uint32_t f0 = sub * subsz, f1;
+        const uint32_t f0 = sub_lo[sub], fe = sub_lo[sub + 1]; uint32_t f1;
         WaveArgs w = a; w.sub = (int) sub;
         cudaStream_t st = percodec ? ctx->sub[1] : st_all;
         if (clear && !percodec) cudaMemsetAsync(a.not_done + sub, 0, 4, st_all);
         if (percodec) { w.sub = 1; if (clear) cudaMemsetAsync(a.not_done + 1, 0, 4, st); }
-        if (f0 < nz) { f1 = f0 + subsz < nz ? f0 + subsz : nz;
+        if (f0 < nz) { f1 = fe < nz ? fe : nz;
             mark(0, st);
             if (any_kwaj) k_p1_mszip<ZIP_NT, ZIP_HEADN, true><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             else k_p1_mszip<ZIP_NT, ZIP_HEADN><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
@@ -666,14 +683,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
             mark(1, st); }
         if (percodec) { st = ctx->sub[2]; w.sub = 2; if (clear) cudaMemsetAsync(a.not_done + 2, 0, 4, st); }
-        if (f0 < nl) { f1 = f0 + subsz < nl ? f0 + subsz : nl;
+        if (f0 < nl) { f1 = fe < nl ? fe : nl;
             mark(0, st);
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             else k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (percodec) { st = ctx->sub[0]; w.sub = 0; if (clear) cudaMemsetAsync(a.not_done + 0, 0, 4, st); }
-        if (f0 < nq) { f1 = f0 + subsz < nq ? f0 + subsz : nq;
+        if (f0 < nq) { f1 = fe < nq ? fe : nq;
             mark(0, st);
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);
