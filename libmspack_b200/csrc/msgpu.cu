@@ -2,7 +2,7 @@
  *
  * Launch structure for one wave of units:
  *     repeat until every unit of the wave is done:
- *         k_p1_<codec>   one thread per unit : bitstream -> literals + match records, F frames per launch
+ *         k_p1_<codec>   one thread per unit : bitstream -> literals + match records, up to frame_slots() frames per launch
  *         k_p2_resolve   one warp per unit   : records -> output bytes (16-byte stores)
  *                        (+ for LZX units the E8 call translation, once a unit's last frame is resolved)
  *     k_status           per-unit MSPACK_ERR_* out
@@ -30,10 +30,11 @@ struct WaveArgs {
     const uint8_t *in_base;
     uint8_t *out_base;
     MsUnitState *ustate;         /* [slots] */
-    MsRec *recs;                 /* [slots][F][MS_MAXREC] */
-    MsFrameInfo *finfo;          /* [slots][F] */
+    MsRec *recs;                 /* [frame slots][MS_MAXREC]: slot i owns frame slots [fbase[i], fbase[i + 1]) */
+    MsFrameInfo *finfo;          /* [frame slots] */
+    const uint32_t *fbase;       /* [slots + 1]: a unit decodes as many frames per launch round as it has frame slots (frame_slots()) */
     uint32_t *not_done;          /* per sub-wave counters; a kernel adds to not_done[sub] */
-    int F, sub;
+    int sub;
 };
 
 /* The warp-synchronous driver of a P1 lane state machine: all 32 lanes take part in every vote, so the
@@ -63,23 +64,24 @@ __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *ord
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
+    const uint32_t fb = valid ? a.fbase[slot] : 0;
     ZipLaneC<NT, HEADN, SPECIAL> t; t.phase = PH_IDLE;
     MsUnitState st;
     if (valid) {
         t.bind(reinterpret_cast<ZipSharedC<NT, HEADN> *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * ZIP_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
-                a.finfo + (size_t) slot * a.F, a.F);
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) fb * MS_MAXREC, a.out_base + a.units[slot].out_off,
+                a.finfo + fb, (int) (a.fbase[slot + 1] - fb));
     }
     p1_run(t);
     if (valid) {
         t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u);
         if (SPECIAL) {       /* (the special instantiation also makes overflow frames, valid == 4, and may use two frame slots for one block) */
             bool any = false;
-            for (int k = 0; k < t.f; k++) { const uint32_t v = a.finfo[(size_t) slot * a.F + k].valid; any = any || v == 2u || v == 4u; }
+            for (int k = 0; k < t.f; k++) { const uint32_t v = a.finfo[fb + k].valid; any = any || v == 2u || v == 4u; }
             if (any) a.not_done[MISC_RING + a.sub] = 1u;
         }
-        else if (t.f > 0 && a.finfo[(size_t) slot * a.F + t.f - 1].valid == 2u) a.not_done[MISC_RING + a.sub] = 1u;          /* frames for k_p2_ring (ring is sticky) */
+        else if (t.f > 0 && a.finfo[fb + t.f - 1].valid == 2u) a.not_done[MISC_RING + a.sub] = 1u;          /* frames for k_p2_ring (ring is sticky) */
     }
 }
 
@@ -97,8 +99,9 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     if (valid) {
         t.bind(reinterpret_cast<typename LzxSharedSel<NT, HEADN, H8LB>::type *>(smem_raw), (int) threadIdx.x, aux + (size_t) (ti >> 5) * LZX_AUX_BYTES, (int) (ti & 31));
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
-                a.finfo + (size_t) slot * a.F, e8info + e8base[ti], a.F);
+        const uint32_t fb = a.fbase[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) fb * MS_MAXREC, a.out_base + a.units[slot].out_off,
+                a.finfo + fb, e8info + e8base[ti], (int) (a.fbase[slot + 1] - fb));
     }
     p1_run(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
@@ -116,8 +119,9 @@ __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order
     t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);      /* every thread: idle lanes take part in the warp-cooperative model updates */
     if (valid) {
         st = a.ustate[slot];
-        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) slot * a.F * MS_MAXREC, a.out_base + a.units[slot].out_off,
-                a.finfo + (size_t) slot * a.F, a.F, save + (size_t) ti * QTM_SAVE_BYTES);
+        const uint32_t fb = a.fbase[slot];
+        t.begin(&a.units[slot], a.in_base, st, a.recs + (size_t) fb * MS_MAXREC, a.out_base + a.units[slot].out_off,
+                a.finfo + fb, (int) (a.fbase[slot + 1] - fb), save + (size_t) ti * QTM_SAVE_BYTES);
     }
     p1_run(t);
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
@@ -150,13 +154,14 @@ __global__ void P2_BOUNDS k_p2_resolve(WaveArgs a, const uint32_t *slots, uint32
     const uint32_t ref_len = (WIDE && a.units[slot].codec == MSGPU_CODEC_LZX) ? MSGPU_UNIT_REF_BYTES(&a.units[slot]) : 0u;
     uint32_t mphase = 0;
     if (BULK) { if (lane == 0) p2_mbar_init(&s_mbar[warp]); __syncwarp(); }
-    for (int f = 0; f < a.F; f++) {
-        MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
+    const uint32_t fb = a.fbase[slot], nf = a.fbase[slot + 1] - fb;
+    for (uint32_t f = 0; f < nf; f++) {
+        MsFrameInfo fi = a.finfo[fb + f];
         if (fi.valid != 1u || fi.size == 0) continue;           /* (2 = an MSZIP frame for k_p2_ring) */
-        if (BULK) p2_resolve_frame_pipe<WIDE>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        if (BULK) p2_resolve_frame_pipe<WIDE>(lane, a.recs + (size_t) (fb + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_w2[BULK ? warp : 0], s_src[warp], s_longq[warp], ref_len, &s_mbar[warp], &mphase);
         else
-        p2_resolve_frame<WIDE, false, false>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        p2_resolve_frame<WIDE, false, false>(lane, a.recs + (size_t) (fb + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], ref_len);
     }
     if (e8info && a.ustate[slot].done && !a.ustate[slot].pad[0]) {          /* (pad[0]: translated - a finished unit may see further launch rounds) */
@@ -191,16 +196,17 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_ring(WaveArgs a, const uin
     if (si >= nslots) return;
     uint32_t slot = slots[si];
     uint8_t *unit_out = a.out_base + a.units[slot].out_off;
-    for (int f = 0; f < a.F; f++) {
-        MsFrameInfo fi = a.finfo[(size_t) slot * a.F + f];
+    const uint32_t fb = a.fbase[slot], nf = a.fbase[slot + 1] - fb;
+    for (uint32_t f = 0; f < nf; f++) {
+        MsFrameInfo fi = a.finfo[fb + f];
         if (fi.valid != (OVF ? 4u : 2u) || fi.size == 0) continue;
         __syncwarp();
-        const uint32_t *sn = reinterpret_cast<const uint32_t *>(a.recs + ((size_t) slot * a.F + f) * MS_MAXREC + P2_HIST_REC);
+        const uint32_t *sn = reinterpret_cast<const uint32_t *>(a.recs + (size_t) (fb + f) * MS_MAXREC + P2_HIST_REC);
         for (int j = lane; j < (int) P2_HIST_WORDS; j += 32) s_hist[warp][j] = sn[j];
         __syncwarp();
-        p2_resolve_frame<false, true, OVF>(lane, a.recs + ((size_t) slot * a.F + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
+        p2_resolve_frame<false, true, OVF>(lane, a.recs + (size_t) (fb + f) * MS_MAXREC, fi.nrec, fi.size, unit_out, fi.g0,
                                            s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], 0u, s_hist[warp],
-                                           OVF ? reinterpret_cast<const uint8_t *>(a.recs + ((size_t) slot * a.F + f) * MS_MAXREC + P2_PLANE_REC) : nullptr);
+                                           OVF ? reinterpret_cast<const uint8_t *>(a.recs + (size_t) (fb + f) * MS_MAXREC + P2_PLANE_REC) : nullptr);
     }
 }
 
@@ -219,10 +225,11 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_p2_chain(WaveArgs a, const ui
     const uint32_t first = chains[2 * ci], count = chains[2 * ci + 1];
     for (uint32_t k = 0; k < count; k++) {
         const uint32_t slot = slots[first + k];
-        MsFrameInfo fi = a.finfo[(size_t) slot * a.F];
+        const uint32_t fb = a.fbase[slot];
+        MsFrameInfo fi = a.finfo[fb];
         if (fi.valid != 3u) break;
         if (fi.size == 0) continue;
-        p2_resolve_frame<true>(lane, a.recs + (size_t) slot * a.F * MS_MAXREC, fi.nrec, fi.size, a.out_base + a.units[slot].out_off, fi.g0,
+        p2_resolve_frame<true>(lane, a.recs + (size_t) fb * MS_MAXREC, fi.nrec, fi.size, a.out_base + a.units[slot].out_off, fi.g0,
                                s_wa[warp], s_wb[warp], s_src[warp], s_longq[warp], k ? MS_FRAME : 0u);
         __syncwarp();
     }
@@ -289,7 +296,7 @@ struct msgpu_ctx {
     int stage_timing = 0;                        /* msgpu_set_stage_timing: serialise the stages and time each with events */
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
-    DevBuf units, ustate, recs, finfo, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains, dig_units, dig_out;
+    DevBuf units, ustate, recs, finfo, fbase, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains, dig_units, dig_out;
     uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
@@ -297,7 +304,7 @@ struct msgpu_ctx {
     int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
-        return units.cap + ustate.cap + recs.cap + finfo.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
+        return units.cap + ustate.cap + recs.cap + finfo.cap + fbase.cap + misc.cap + order.cap + aux_zip.cap + aux_lzx.cap +
                save_qtm.cap + e8info.cap + e8base.cap + status_tmp.cap + io_in.cap + io_out.cap + io_status.cap + chains.cap + dig_units.cap + dig_out.cap;
     }
 };
@@ -351,7 +358,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
 extern "C" void msgpu_destroy(msgpu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->finfo, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
+    DevBuf *bufs[] = { &c->units, &c->ustate, &c->recs, &c->finfo, &c->fbase, &c->misc, &c->order, &c->aux_zip, &c->aux_lzx, &c->save_qtm,
                        &c->e8info, &c->e8base, &c->status_tmp, &c->io_in, &c->io_out, &c->io_status, &c->chains, &c->dig_units, &c->dig_out };
     for (DevBuf *b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -417,6 +424,43 @@ static cudaEvent_t stage_event(msgpu_ctx *c, size_t &used) {
 
 static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_FRAME - 1) / MS_FRAME; }
 
+/* Frame slots of a unit = the frames it decodes per launch round (one record array and one MsFrameInfo each).  A unit never gets
+ * more slots than it has frames; a KWAJ / repair-mode MSZIP unit gets at least two (a repaired block may need two). */
+static inline uint32_t frame_slots(const msgpu_unit &u, uint32_t fmax) {
+    uint32_t fr = frames_of(u);
+    if (fr < 1) fr = 1;
+    if (fr > fmax) fr = fmax;
+    if (fr < 2 && u.codec == MSGPU_CODEC_MSZIP && (u.flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR))) fr = 2;
+    return fr;
+}
+#define MS_FRAME_SLOT_BYTES ((size_t) MS_MAXREC * sizeof(MsRec))
+#define MS_UNIT_FIXED_BYTES (sizeof(MsUnitState) + 10240u)      /* + the largest per-lane aux share (LZX_AUX_BYTES / 32) */
+
+/* Frames per launch round for the long units of a batch.  Big batches of short units keep two (the record arrays of the headline
+ * and CHM batches are what the scratch budget is sized for); a batch of FEW LONG units - a cabinet's multi-megabyte LZX or
+ * Quantum folders, whose frames must be decoded in order by one lane - gets up to 64, so a folder of 65 535 frames
+ * (cabextract/test/large-files.test) takes 1 024 launch rounds instead of 32 768, each of which would reload the lane's state
+ * and rebuild its Huffman tables.  The rule: the largest power of two that keeps the batch within 131 072 frame slots (17 GB
+ * of records) and half the scratch budget; MSGPU_FMAX overrides. */
+static uint32_t pick_fmax(const msgpu_ctx *ctx, const msgpu_unit *units, size_t n, uint32_t maxfr) {
+    if (maxfr <= 2) return 2;
+    const char *env = getenv("MSGPU_FMAX");
+    if (env) { int v = atoi(env); return v < 2 ? 2u : (v > 4096 ? 4096u : (uint32_t) v); }
+    uint64_t s2 = 0;
+    for (size_t i = 0; i < n; i++) s2 += frame_slots(units[i], 2);
+    uint64_t target = ctx->scratch_budget / 2 / MS_FRAME_SLOT_BYTES;
+    if (target > 131072) target = 131072;
+    if (target < s2) target = s2;
+    uint32_t fmax = 2;
+    while (fmax < 64 && fmax < maxfr) {
+        uint64_t sn = 0;
+        for (size_t i = 0; i < n && sn <= target; i++) sn += frame_slots(units[i], fmax * 2);
+        if (sn > target) break;
+        fmax *= 2;
+    }
+    return fmax;
+}
+
 /* Decode one wave: units[lo, hi) of the host array (already validated).
  *
  * The wave is cut into sub-waves of MSGPU_SUBWAVE units (default 148 x the P1 CTA size = one resident P1 CTA per SM;
@@ -425,25 +469,27 @@ static inline uint32_t frames_of(const msgpu_unit &u) { return (u.out_len + MS_F
  * bound) of another.  Host buffers (h_in / h_out): ~16 sub-waves, copies on two dedicated streams, kernels on eight
  * (see `hostpipe` below). */
 static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t hi, const void *d_in, void *d_out,
-                    int32_t *d_status, cudaStream_t s, const uint8_t *h_in = nullptr, uint8_t *h_out = nullptr)
+                    int32_t *d_status, cudaStream_t s, uint32_t fmax, const uint8_t *h_in = nullptr, uint8_t *h_out = nullptr)
 {
     const uint32_t n = (uint32_t) (hi - lo);
-    std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base, chains;
-    uint32_t maxfr = 1, e8total = 0; bool any_zip = false, any_delta = false, any_kwaj = false;
+    std::vector<uint32_t> ord[4]; std::vector<uint32_t> e8base, chains, fbase((size_t) n + 1);
+    uint32_t e8total = 0, rounds_planned = 1, rounds_of[4] = { 1, 1, 1, 1 }; bool any_zip = false, any_delta = false, any_kwaj = false;
+    fbase[0] = 0;
     for (uint32_t i = 0; i < n; i++) {
         const msgpu_unit &u = h_units[lo + i];
         ord[u.codec].push_back(i);
+        { const uint32_t cap = frame_slots(u, fmax), fr0 = frames_of(u), r = (fr0 + cap - 1) / cap; fbase[i + 1] = fbase[i] + cap; if (r > rounds_planned) rounds_planned = r; if (r > rounds_of[u.codec]) rounds_of[u.codec] = r; }
         if (u.codec == MSGPU_CODEC_LZX && ((u.flags & MSGPU_FLAG_LZX_DELTA) || MSGPU_UNIT_REF_BYTES(&u))) any_delta = true;
         if (u.codec == MSGPU_CODEC_MSZIP && (u.flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR))) any_kwaj = true;      /* the special MSZIP instantiation */
         if (u.codec == MSGPU_CODEC_MSZIP) {          /* block chains: runs of consecutive entries of the MSZIP list */
             if (u.flags & MSGPU_FLAG_CHAIN_FIRST) { chains.push_back((uint32_t) ord[1].size() - 1); chains.push_back(1); }
             else if ((u.flags & MSGPU_FLAG_CHAIN_NEXT) && !chains.empty()) chains.back()++;
         }
-        uint32_t fr = frames_of(u); if (fr > maxfr) maxfr = fr;
+        uint32_t fr = frames_of(u);
         if (u.codec == MSGPU_CODEC_LZX) { e8base.push_back(e8total); e8total += fr ? fr : 1; }
         if (u.codec == MSGPU_CODEC_MSZIP) any_zip = true;
     }
-    const int F = (maxfr >= 2 || any_kwaj) ? 2 : 1;            /* (a repair-mode MSZIP block may need two frame slots) */
+    const size_t nfslots = fbase[n];
     const uint32_t nz = (uint32_t) ord[1].size(), nq = (uint32_t) ord[2].size(), nl = (uint32_t) ord[3].size();
     const char *env = getenv("MSGPU_SUBWAVE");
     const uint32_t lzx_nt = any_delta ? LZXD_NT : LZX_NT, zip_nt = ZIP_NT;
@@ -494,8 +540,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 
     CK(ctx->units.reserve((size_t) n * sizeof(msgpu_unit)), "alloc units");
     CK(ctx->ustate.reserve((size_t) n * sizeof(MsUnitState)), "alloc state");
-    CK(ctx->recs.reserve((size_t) n * F * MS_MAXREC * sizeof(MsRec)), "alloc records");
-    CK(ctx->finfo.reserve((size_t) n * F * sizeof(MsFrameInfo)), "alloc frame info");
+    CK(ctx->recs.reserve(nfslots * MS_FRAME_SLOT_BYTES), "alloc records");
+    CK(ctx->finfo.reserve(nfslots * sizeof(MsFrameInfo)), "alloc frame info");
+    CK(ctx->fbase.reserve(((size_t) n + 1) * sizeof(uint32_t)), "alloc frame slot table");
     CK(ctx->misc.reserve(MISC_WORDS * 4), "alloc misc");
     CK(ctx->order.reserve((size_t) (2 * n + 3) * sizeof(uint32_t)), "alloc order");
     if (nz) CK(ctx->aux_zip.reserve((size_t) ((nz + 31) / 32) * ZIP_AUX_BYTES), "alloc mszip aux");
@@ -511,8 +558,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     uint32_t *d_ord_z = d_order, *d_ord_q = d_order + nz, *d_ord_l = d_order + nz + nq;
     {
         /* the wave's tables go through the pinned staging area (one event guards its reuse by the next wave / call) */
-        const size_t b_units = (size_t) n * sizeof(msgpu_unit), b_ord = (size_t) (nz + nq + nl) * 4, b_e8 = (size_t) nl * 4, b_ch = chains.size() * 4;
-        const size_t need = b_units + b_ord + b_e8 + b_ch + 64;
+        const size_t b_units = (size_t) n * sizeof(msgpu_unit), b_ord = (size_t) (nz + nq + nl) * 4, b_e8 = (size_t) nl * 4, b_ch = chains.size() * 4, b_fb = ((size_t) n + 1) * 4;
+        const size_t need = b_units + b_ord + b_e8 + b_ch + b_fb + 64;
         if (ctx->stage_busy) { CK(cudaEventSynchronize(ctx->ev_stage), "staging sync"); ctx->stage_busy = false; }
         if (need > ctx->h_stage_cap) {
             if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -527,6 +574,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (nq) memcpy(ho + nz, ord[2].data(), (size_t) nq * 4);
         if (nl) { memcpy(ho + nz + nq, ord[3].data(), (size_t) nl * 4); memcpy(ho + nz + nq + nl, e8base.data(), b_e8); }
         if (b_ch) memcpy(ho + nz + nq + nl + nl, chains.data(), b_ch);
+        memcpy(ho + nz + nq + nl + nl + chains.size(), fbase.data(), b_fb);
+        CK(cudaMemcpyAsync(ctx->fbase.p, ho + nz + nq + nl + nl + chains.size(), b_fb, cudaMemcpyHostToDevice, s), "copy frame slot table");
         CK(cudaMemcpyAsync(ctx->units.p, hs, b_units, cudaMemcpyHostToDevice, s), "copy units");
         if (b_ord) CK(cudaMemcpyAsync(d_order, ho, b_ord, cudaMemcpyHostToDevice, s), "copy order");
         if (nl) CK(cudaMemcpyAsync(ctx->e8base.p, ho + nz + nq + nl, b_e8, cudaMemcpyHostToDevice, s), "copy e8 base");
@@ -550,7 +599,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     a.units = reinterpret_cast<const msgpu_unit *>(ctx->units.p); a.in_base = reinterpret_cast<const uint8_t *>(d_in);
     a.out_base = reinterpret_cast<uint8_t *>(d_out); a.ustate = reinterpret_cast<MsUnitState *>(ctx->ustate.p);
     a.recs = reinterpret_cast<MsRec *>(ctx->recs.p);
-    a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.F = F; a.sub = 0;
+    a.finfo = reinterpret_cast<MsFrameInfo *>(ctx->finfo.p); a.not_done = reinterpret_cast<uint32_t *>(ctx->misc.p); a.fbase = reinterpret_cast<const uint32_t *>(ctx->fbase.p); a.sub = 0;
 
     while (ctx->evs.size() < ctx->ev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e), "event create"); ctx->evs.push_back(e); }
     cudaEvent_t ev0 = ctx->evs[ctx->ev_used], ev1 = ctx->evs[ctx->ev_used + 1];
@@ -647,7 +696,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 
     /* sub-wave k = entries [sub_lo[k], sub_lo[k + 1]) of EACH codec's list (every boundary is a multiple of the CTA
      * size, so warps and their aux blocks never straddle two sub-waves); P2 walks the same list ranges */
-    const uint32_t rounds_planned = (maxfr + F - 1) / F;
     auto mark = [&](int stage, cudaStream_t st) {      /* stage timing: an event on either side of a launch */
         if (!ctx->stage_timing) return;
         cudaEvent_t e = stage_event(ctx, sev_used);
@@ -665,13 +713,16 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     /* clear: zero the "units still running" counter in front of the round's kernels.  With a stream per codec every codec
      * counts in a slot of its own (w.sub = its stream index; there is one sub-wave), cleared in its own stream order. */
-    auto launch_round = [&](uint32_t sub, cudaStream_t st_all, bool clear) {
+    /* round: a codec whose longest unit needs fewer rounds than the wave's sits the later ones out (all but the last planned
+     * round, which counts the units still running) - next to a 65 535-frame LZX folder the other folders' units are long done */
+    auto launch_round = [&](uint32_t sub, cudaStream_t st_all, bool clear, uint32_t round = 0) {
         const uint32_t f0 = sub_lo[sub], fe = sub_lo[sub + 1]; uint32_t f1;
+        const bool last = round + 1 >= rounds_planned;
         WaveArgs w = a; w.sub = (int) sub;
         cudaStream_t st = percodec ? ctx->sub[1] : st_all;
         if (clear && !percodec) cudaMemsetAsync(a.not_done + sub, 0, 4, st_all);
         if (percodec) { w.sub = 1; if (clear) cudaMemsetAsync(a.not_done + 1, 0, 4, st); }
-        if (f0 < nz) { f1 = fe < nz ? fe : nz;
+        if (f0 < nz && (last || round < rounds_of[1])) { f1 = fe < nz ? fe : nz;
             mark(0, st);
             if (any_kwaj) k_p1_mszip<ZIP_NT, ZIP_HEADN, true><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             else k_p1_mszip<ZIP_NT, ZIP_HEADN><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
@@ -683,14 +734,14 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
             mark(1, st); }
         if (percodec) { st = ctx->sub[2]; w.sub = 2; if (clear) cudaMemsetAsync(a.not_done + 2, 0, 4, st); }
-        if (f0 < nl) { f1 = fe < nl ? fe : nl;
+        if (f0 < nl && (last || round < rounds_of[3])) { f1 = fe < nl ? fe : nl;
             mark(0, st);
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             else k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
         if (percodec) { st = ctx->sub[0]; w.sub = 0; if (clear) cudaMemsetAsync(a.not_done + 0, 0, 4, st); }
-        if (f0 < nq) { f1 = fe < nq ? fe : nq;
+        if (f0 < nq && (last || round < rounds_of[2])) { f1 = fe < nq ? fe : nq;
             mark(0, st);
             k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
             mark(0, st); mark(1, st);
@@ -701,7 +752,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         if (hostpipe) { copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[2 * sub], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(st, ctx->io_evs[2 * sub], 0), "stream wait"); }
         else copy_in(sub, st);
         for (uint32_t round = 0; round < rounds_planned; round++) {
-            launch_round(sub, st, round + 1 == rounds_planned && any_zip);      /* the last planned round counts the units still running */
+            launch_round(sub, st, round + 1 == rounds_planned && any_zip, round);      /* the last planned round counts the units still running */
         }
         if (!any_zip) finish_out(sub, st);
     }
@@ -713,10 +764,10 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             for (int i = 0; i < NS; i++) CK(cudaStreamSynchronize(NS == 1 ? s : ctx->sub[i]), "sync");
             CK(cudaMemcpy(ctx->h_pinned, a.not_done, (percodec ? 3 : nsub) * 4, cudaMemcpyDeviceToHost), "read counters");
             bool again = false;
-            if (percodec) { if (ctx->h_pinned[0] | ctx->h_pinned[1] | ctx->h_pinned[2]) { again = true; launch_round(0, s, true); } }
+            if (percodec) { if (ctx->h_pinned[0] | ctx->h_pinned[1] | ctx->h_pinned[2]) { again = true; launch_round(0, s, true, rounds_planned); } }
             else for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
                 again = true;
-                launch_round(sub, kstream(sub), true);
+                launch_round(sub, kstream(sub), true, rounds_planned);
             }
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
@@ -777,18 +828,22 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
         }
     }
     /* wave size from the scratch budget */
-    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; if (units[i].codec == MSGPU_CODEC_MSZIP && (units[i].flags & (MSGPU_FLAG_MSZIP_KWAJ | MSGPU_FLAG_MSZIP_REPAIR))) maxfr = maxfr < 2 ? 2 : maxfr; }
-    const int F = maxfr >= 2 ? 2 : 1;
-    size_t per_slot = (size_t) F * (MS_MAXREC * sizeof(MsRec)) + sizeof(MsUnitState) + 10240;      /* + the largest per-lane aux share (LZX_AUX_BYTES / 32) */
-    size_t slots = ctx->scratch_budget / per_slot; if (slots < 1024) slots = 1024;
+    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
+    const uint32_t fmax = pick_fmax(ctx, units, n, maxfr);
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
     ctx->last_waves = 0; ctx->last_stream = s;
     for (size_t lo = 0; lo < n;) {
-        size_t hi = lo + slots < n ? lo + slots : n;
+        /* a wave = as many units as the scratch budget holds (record arrays per frame slot + per-unit state), at least 1 024 */
+        size_t hi = lo; uint64_t used = 0;
+        while (hi < n) {
+            const uint64_t c = (uint64_t) frame_slots(units[hi], fmax) * MS_FRAME_SLOT_BYTES + MS_UNIT_FIXED_BYTES;
+            if (hi - lo >= 1024 && used + c > ctx->scratch_budget) break;
+            used += c; hi++;
+        }
         while (hi < n && hi > lo && (units[hi].flags & MSGPU_FLAG_CHAIN_NEXT)) hi--;       /* a chain stays inside one wave */
         if (hi == lo) return fail(ctx, MSGPU_ERR_NOMEMORY, "a block chain does not fit the scratch budget");
-        int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, h_in, h_out);
+        int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, fmax, h_in, h_out);
         if (r) return r;
         ctx->last_waves++; ctx->last_wave_n = hi - lo;
         lo = hi;

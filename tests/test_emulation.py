@@ -36,7 +36,7 @@ def emul():
 
 
 @pytest.mark.parametrize("entry", golden_manifest(), ids=lambda e: e["name"])
-@pytest.mark.parametrize("frames_per_round", [1, 2])
+@pytest.mark.parametrize("frames_per_round", [1, 2, 7, 64])
 def test_device_logic_on_golden_vectors(emul, entry, frames_per_round):
     u, comp = golden_unit(entry)
     out, st = emul(u, comp, entry["out_len"], frames_per_round)
@@ -436,3 +436,30 @@ def test_device_logic_mszip_repair_mode(emul, oracle_ref, seed):
 
 
 
+
+
+@pytest.mark.parametrize("fpr", [2, 5, 64])
+def test_long_units_frames_per_round(emul, oracle_ref, fpr):
+    """SURVEY.md 8 f3 (LZX / Quantum folders): long units decoded 2 / 5 / 64 frames per launch round (msgpu.cu frame_slots) give
+    the reference's bytes and status, intact and damaged (the GPU twin is tests/test_w_long_units_gpu.py)"""
+    parts = [gen.make_batch(CODEC_LZX, 2, unit_bytes=40 * 32768 + 777, block_mode=4, split=2, intel=1, data="binary"),
+             gen.make_batch(CODEC_LZX, 2, unit_bytes=33 * 32768, reset_interval=4, window_bits=16, first_unit=10),
+             gen.make_batch(CODEC_QUANTUM, 2, unit_bytes=20 * 32768 + 5, window_bits=17, first_unit=20),
+             gen.make_batch(CODEC_MSZIP, 2, unit_bytes=30 * 32768 + 100, first_unit=30)]
+    m = gen.concat_batches(parts)
+    o1, s1, _ = oracle_ref.decode_batch(m.units, m.comp, m.out_bytes, threads=4)
+    assert (s1 == 0).all()
+    o2, s2 = emul(m.units, m.comp, m.out_bytes, fpr)
+    assert_same(m.units, o1, s1, o2, s2, f"long units F={fpr}")
+    rng = np.random.default_rng(3)
+    comp, units = m.comp.copy(), m.units.copy()
+    for i, u in enumerate(units):
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        if i % 2 == 0:
+            comp[lo + n // 2 + int(rng.integers(0, n // 4))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            units["in_len"][i] = n - n // 3
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, m.out_bytes, threads=4)
+    o2, s2 = emul(units, comp, m.out_bytes, fpr)
+    assert (s1 != 0).any()
+    assert_same(units, o1, s1, o2, s2, f"damaged long units F={fpr}")
