@@ -40,6 +40,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# msgpu_decode_batch_host keeps up to ~40 streams busy; with CUDA's default of 8 hardware launch queues unrelated streams wait for
+# each other's dependencies ("Environment").  msgpu_create() sets the same default when it is the process's
+# first CUDA call; here torch initialises CUDA first, so it is set before that.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 FRAME = 32768
 WINDOW_BITS = 21

@@ -55,8 +55,8 @@ __device__ __forceinline__ void p1_run(Lane &t)
     }
 }
 
-#define MISC_WORDS 2048u          /* counters: [sub] units still running, [MISC_RING + sub] MSZIP ring frames present */
-#define MISC_RING  1024u
+#define MISC_WORDS 8192u          /* counters: [3 sub + c] units of codec c still running, [MISC_RING + 3 sub] MSZIP ring frames present */
+#define MISC_RING  4096u
 template <int NT, int HEADN, bool SPECIAL = false>      /* SPECIAL: the instantiation for KWAJ framing and repair mode (ZipLaneC) */
 __global__ void __launch_bounds__(NT) k_p1_mszip(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *aux)
 {
@@ -297,7 +297,8 @@ struct msgpu_ctx {
     std::vector<cudaEvent_t> stage_evs[3];       /* [0] P1 (entropy), [1] P2 (resolve), [2] E8: (start, end) pairs of the last batch */
     std::vector<cudaEvent_t> stage_pool;
     DevBuf units, ustate, recs, finfo, fbase, misc, order, aux_zip, aux_lzx, save_qtm, e8info, e8base, status_tmp, io_in, io_out, io_status, chains, dig_units, dig_out;
-    uint32_t *h_pinned = nullptr;      /* [0] = not_done readback */
+    uint32_t *h_pinned = nullptr;      /* not_done readback: 3 words per sub-wave */
+    std::vector<cudaStream_t> xs; std::vector<cudaEvent_t> xs_ev;      /* host-buffer path, mixed batches: a stream per sub-wave for its Quantum chain (run_wave `qsplit`) */
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
     int dev_streams = 3;  /* MSGPU_STREAMS=1: everything of a device-buffer batch in the caller's stream order (default: mixed batches run each codec on a stream of its own) */
@@ -322,12 +323,16 @@ extern "C" const char *msgpu_version(void) { return "libmspack_b200 msgpu 0.1 (s
 
 extern "C" msgpu_ctx *msgpu_create(int device) {
     int ndev = 0;
+    /* the host-buffer pipeline keeps up to ~40 streams busy (run_wave); with the default 8 hardware launch queues unrelated
+     * streams wait for each other's dependencies.  Only has an effect if this is the process's first CUDA call; never overrides
+     * the caller's own setting. */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;   /* no CPU fallback */
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     msgpu_ctx *c = new msgpu_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 4096) != cudaSuccess) { delete c; return nullptr; }
+        cudaMallocHost(reinterpret_cast<void **>(&c->h_pinned), 16384) != cudaSuccess) { delete c; return nullptr; }
     for (int i = 0; i < msgpu_ctx::NSUB + 2; i++) {
         cudaStream_t *sp = i < msgpu_ctx::NSUB ? &c->sub[i] : (i == msgpu_ctx::NSUB ? &c->cp_in : &c->cp_out);
         if (cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking) != cudaSuccess ||
@@ -367,6 +372,8 @@ extern "C" void msgpu_destroy(msgpu_ctx *c) {
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
     for (cudaEvent_t e : c->stage_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->io_evs) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->xs_ev) cudaEventDestroy(e);
+    for (cudaStream_t st : c->xs) cudaStreamDestroy(st);
     for (int i = 0; i < msgpu_ctx::NSUB; i++) if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
     if (c->cp_in) cudaStreamDestroy(c->cp_in);
     if (c->cp_out) cudaStreamDestroy(c->cp_out);
@@ -606,15 +613,37 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     CK(cudaEventRecord(ev0, s), "event");
     CK(cudaEventRecord(ctx->ev_fork, s), "event");
     const bool hostpipe = h_in && !ctx->stage_timing && nsub > 1;          /* decoupled copy queues, see above (h_out may be absent: msgpu_decode_batch_host_digest) */
+    const bool mixed = ((nz != 0) + (nl != 0) + (nq != 0)) > 1;
     /* A batch of several codecs on device buffers: every codec's launches on a stream of its own (MSGPU_STREAMS=1: all in the
-     * caller's stream order).  The three P1 kernels have CTAs of different shapes that each take a whole SM; the partial last
-     * "wave" of one codec (Quantum: 224 lanes per SM, 7x the latency of the others) then shares the GPU with the other codecs'
-     * CTAs instead of leaving two thirds of the SMs idle. */
-    const bool percodec = !h_in && !ctx->stage_timing && nsub == 1 && ctx->dev_streams > 1 && ((nz != 0) + (nl != 0) + (nq != 0)) > 1;
+     * caller's stream order), Quantum's first.  The three P1 kernels have CTAs of different shapes that each take a whole SM;
+     * Quantum's take 9x as long as the others', so they start at once and the other codecs' CTAs share the SMs they leave free. */
+    const bool percodec = !h_in && !ctx->stage_timing && nsub == 1 && ctx->dev_streams > 1 && mixed;
     const int NS = percodec ? 3 : ((nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : ctx->dev_streams) : 1);
+    /* Host buffers, several codecs: the three codecs of a sub-wave run on three streams - a Quantum P1 launch takes ~80 ms however
+     * few units it has (the serial decode of a frame), and in one stream order it held back the sub-wave's LZX / MSZIP output and
+     * everything queued behind it (BASELINE config 5 end to end: 17 GB/s).  Every sub-wave's Quantum chain gets a stream of its own
+     * (ctx->xs), so all of them are resident together, and its output is queued for the D2H engine behind the other codecs'. */
+    const bool qsplit = hostpipe && mixed && nq != 0;
+    const bool qbreadth = qsplit && rounds_planned == 1;      /* (one-frame units: every P1 launch of the wave can be issued before any resolve launch) */
+    size_t nxs = 0;
+    if (qsplit) {
+        nxs = nsub < 32 ? nsub : 32;
+        while (ctx->xs.size() < nxs) {
+            cudaStream_t st; cudaEvent_t e;
+            CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream create"); ctx->xs.push_back(st);
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->xs_ev.push_back(e);
+        }
+    }
     auto kstream = [&](uint32_t sub) { return NS == 1 ? s : ctx->sub[sub % (uint32_t) NS]; };
+    /* the stream of codec c (0 MSZIP, 1 LZX, 2 Quantum) of sub-wave `sub` */
+    auto cstream = [&](uint32_t sub, int c) -> cudaStream_t {
+        if (NS == 1) return s;
+        if (percodec) return ctx->sub[c == 0 ? 1 : (c == 1 ? 2 : 0)];
+        if (hostpipe && mixed) return (c == 2 && qsplit) ? ctx->xs[sub % nxs] : ctx->sub[(2 * sub + (uint32_t) (c & 1)) % (uint32_t) msgpu_ctx::NSUB];
+        return kstream(sub);
+    };
     if (hostpipe) {
-        while (ctx->io_evs.size() < 2 * (size_t) nsub) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->io_evs.push_back(e); }
+        while (ctx->io_evs.size() < 4 * (size_t) nsub) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create"); ctx->io_evs.push_back(e); }
         CK(cudaStreamWaitEvent(ctx->cp_in, ctx->ev_fork, 0), "stream wait");
         CK(cudaStreamWaitEvent(ctx->cp_out, ctx->ev_fork, 0), "stream wait");
     }
@@ -646,9 +675,9 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         r.resize(w);
     };
     std::vector<std::pair<uint64_t, uint64_t>> rng;
+    const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };      /* codec index c: 0 MSZIP, 1 LZX, 2 Quantum */
     auto copy_in = [&](uint32_t sub, cudaStream_t st) {
         if (!h_in) return;
-        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (int c = 0; c < 3; c++) {
             uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt; uint64_t b0, b1;
             if (f0 >= cnt) continue;
@@ -659,7 +688,6 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     };
     bool bulk_out = false; uint64_t wave_o0 = ~0ull, wave_o1 = 0;
     if (h_out) {
-        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
         for (uint32_t sub = 0; sub < nsub && !bulk_out; sub++)
             for (int c = 0; c < 3 && !bulk_out; c++) {
                 uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt;
@@ -673,26 +701,26 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
                 cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_out) + wave_o0, h_out + wave_o0, wave_o1 - wave_o0, cudaMemcpyHostToDevice, hostpipe ? ctx->cp_in : s);
         }
     }
-    auto copy_out = [&](uint32_t sub, cudaStream_t st) {
+    auto copy_out = [&](uint32_t sub, int c, cudaStream_t st) {
         if (!h_out || bulk_out) return;
-        const std::vector<uint32_t> *lists[3] = { &ord[1], &ord[3], &ord[2] };
-        for (int c = 0; c < 3; c++) {
-            uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt;
-            if (f0 >= cnt) continue;
-            out_ranges(*lists[c], f0, f1, rng);
-            for (const auto &r : rng) cudaMemcpyAsync(h_out + r.first, reinterpret_cast<uint8_t *>(d_out) + r.first, r.second - r.first, cudaMemcpyDeviceToHost, st);
-        }
+        uint32_t cnt = (uint32_t) lists[c]->size(), f0 = sub_lo[sub], f1 = sub_lo[sub + 1] < cnt ? sub_lo[sub + 1] : cnt;
+        if (f0 >= cnt) return;
+        out_ranges(*lists[c], f0, f1, rng);
+        for (const auto &r : rng) cudaMemcpyAsync(h_out + r.first, reinterpret_cast<uint8_t *>(d_out) + r.first, r.second - r.first, cudaMemcpyDeviceToHost, st);
     };
-    /* the sub-wave's output is complete on stream st: send it home */
-    auto finish_out = [&](uint32_t sub, cudaStream_t st) -> int {
-        if (!hostpipe) { copy_out(sub, st); return 0; }
-        CK(cudaEventRecord(ctx->io_evs[2 * sub + 1], st), "event");
-        CK(cudaStreamWaitEvent(ctx->cp_out, ctx->io_evs[2 * sub + 1], 0), "stream wait");
-        copy_out(sub, ctx->cp_out);
+    /* the output of codec c of the sub-wave is complete on its stream: send it home */
+    auto finish_out = [&](uint32_t sub, int c) -> int {
+        if (sub_lo[sub] >= (uint32_t) lists[c]->size()) return 0;
+        cudaStream_t st = cstream(sub, c);
+        if (!hostpipe) { copy_out(sub, c, st); return 0; }
+        CK(cudaEventRecord(ctx->io_evs[4 * sub + 1 + (size_t) c], st), "event");
+        CK(cudaStreamWaitEvent(ctx->cp_out, ctx->io_evs[4 * sub + 1 + (size_t) c], 0), "stream wait");
+        copy_out(sub, c, ctx->cp_out);
         return 0;
     };
     size_t sev_used = ctx->stage_evs[0].size() + ctx->stage_evs[1].size() + ctx->stage_evs[2].size();
     for (int i = 0; i < NS; i++) CK(cudaStreamWaitEvent(ctx->sub[i], ctx->ev_fork, 0), "stream wait");
+    for (size_t i = 0; i < nxs; i++) CK(cudaStreamWaitEvent(ctx->xs[i], ctx->ev_fork, 0), "stream wait");
 
     /* sub-wave k = entries [sub_lo[k], sub_lo[k + 1]) of EACH codec's list (every boundary is a multiple of the CTA
      * size, so warps and their aux blocks never straddle two sub-waves); P2 walks the same list ranges */
@@ -711,18 +739,33 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
         else if (ctx->p2_bulk) k_p2_resolve<false, true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
         else k_p2_resolve<false><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, list, f0, f1, e8i, e8b);
     };
-    /* clear: zero the "units still running" counter in front of the round's kernels.  With a stream per codec every codec
-     * counts in a slot of its own (w.sub = its stream index; there is one sub-wave), cleared in its own stream order. */
-    /* round: a codec whose longest unit needs fewer rounds than the wave's sits the later ones out (all but the last planned
+    /* One launch round of a sub-wave: per codec its P1 kernel, then its resolve kernels, on the codec's stream (cstream), Quantum
+     * first.  Every (sub-wave, codec) counts its "units still running" in a slot of its own (w.sub = 3 sub + c), which `clear`
+     * zeroes in front of the round's kernels in that codec's stream order.
+     * round: a codec whose longest unit needs fewer rounds than the wave's sits the later ones out (all but the last planned
      * round, which counts the units still running) - next to a 65 535-frame LZX folder the other folders' units are long done */
-    auto launch_round = [&](uint32_t sub, cudaStream_t st_all, bool clear, uint32_t round = 0) {
+    /* qstage: 0 = Quantum's P1 and its resolve kernel, 1 = its P1 only, 2 = its resolve kernel only (and nothing of the other
+     * codecs): with `qsplit` all sub-waves' Quantum P1 launches are issued before the first Quantum resolve launch - a resolve
+     * kernel waits ~80 ms for its P1, and while it sits at the head of a hardware launch queue (there are 8, or
+     * CUDA_DEVICE_MAX_CONNECTIONS, shared by all streams) every launch queued behind it waits too, whatever its stream:
+     * issued depth-first, three Quantum chains per queue ran one after the other (BASELINE config 5 end to end: 260 ms) */
+    auto launch_round = [&](uint32_t sub, bool clear, uint32_t round, int qstage = 0) {
         const uint32_t f0 = sub_lo[sub], fe = sub_lo[sub + 1]; uint32_t f1;
         const bool last = round + 1 >= rounds_planned;
-        WaveArgs w = a; w.sub = (int) sub;
-        cudaStream_t st = percodec ? ctx->sub[1] : st_all;
-        if (clear && !percodec) cudaMemsetAsync(a.not_done + sub, 0, 4, st_all);
-        if (percodec) { w.sub = 1; if (clear) cudaMemsetAsync(a.not_done + 1, 0, 4, st); }
+        WaveArgs w = a;
+        if (f0 < nq && (last || round < rounds_of[2])) { f1 = fe < nq ? fe : nq;
+            cudaStream_t st = cstream(sub, 2); w.sub = (int) (3 * sub + 2);
+            if (qstage != 2) {
+                if (clear) cudaMemsetAsync(a.not_done + w.sub, 0, 4, st);
+                mark(0, st);
+                k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+                mark(0, st); ctx->launches++;
+            }
+            if (qstage != 1) { mark(1, st); p2_launch(w, d_ord_q, f0, f1, st); ctx->launches++; mark(1, st); } }
+        if (qstage == 2) return;
         if (f0 < nz && (last || round < rounds_of[1])) { f1 = fe < nz ? fe : nz;
+            cudaStream_t st = cstream(sub, 0); w.sub = (int) (3 * sub);
+            if (clear) cudaMemsetAsync(a.not_done + w.sub, 0, 4, st);
             mark(0, st);
             if (any_kwaj) k_p1_mszip<ZIP_NT, ZIP_HEADN, true><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
             else k_p1_mszip<ZIP_NT, ZIP_HEADN><<<(f1 - f0 + ZIP_NT - 1) / ZIP_NT, ZIP_NT, sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>), st>>>(w, d_ord_z, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_zip.p));
@@ -733,48 +776,59 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (any_kwaj) { k_p2_ring<true><<<(f1 - f0 + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, f0, f1); ctx->launches++; }
             if (nchains) { k_p2_chain<<<(nchains + P2_WARPS - 1) / P2_WARPS, P2_WARPS * 32, 0, st>>>(w, d_ord_z, reinterpret_cast<const uint32_t *>(ctx->chains.p), nchains); ctx->launches++; }
             mark(1, st); }
-        if (percodec) { st = ctx->sub[2]; w.sub = 2; if (clear) cudaMemsetAsync(a.not_done + 2, 0, 4, st); }
         if (f0 < nl && (last || round < rounds_of[3])) { f1 = fe < nl ? fe : nl;
+            cudaStream_t st = cstream(sub, 1); w.sub = (int) (3 * sub + 1);
+            if (clear) cudaMemsetAsync(a.not_done + w.sub, 0, 4, st);
             mark(0, st);
             if (any_delta) k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0><<<(f1 - f0 + LZXD_NT - 1) / LZXD_NT, LZXD_NT, sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             else k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB><<<(f1 - f0 + LZX_NT - 1) / LZX_NT, LZX_NT, sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type), st>>>(w, d_ord_l, f0, f1, reinterpret_cast<uint8_t *>(ctx->aux_lzx.p), reinterpret_cast<int32_t *>(ctx->e8info.p), reinterpret_cast<const uint32_t *>(ctx->e8base.p));
             mark(0, st); mark(1, st);
             p2_launch(w, d_ord_l, f0, f1, st); ctx->launches += 2; mark(1, st); }
-        if (percodec) { st = ctx->sub[0]; w.sub = 0; if (clear) cudaMemsetAsync(a.not_done + 0, 0, 4, st); }
-        if (f0 < nq && (last || round < rounds_of[2])) { f1 = fe < nq ? fe : nq;
-            mark(0, st);
-            k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
-            mark(0, st); mark(1, st);
-            p2_launch(w, d_ord_q, f0, f1, st); ctx->launches += 2; mark(1, st); }
     };
     for (uint32_t sub = 0; sub < nsub; sub++) {
-        cudaStream_t st = kstream(sub);
-        if (hostpipe) { copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[2 * sub], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(st, ctx->io_evs[2 * sub], 0), "stream wait"); }
-        else copy_in(sub, st);
-        for (uint32_t round = 0; round < rounds_planned; round++) {
-            launch_round(sub, st, round + 1 == rounds_planned && any_zip, round);      /* the last planned round counts the units still running */
+        if (hostpipe) {
+            copy_in(sub, ctx->cp_in); CK(cudaEventRecord(ctx->io_evs[4 * sub], ctx->cp_in), "event");
+            cudaStream_t seen[3] = { nullptr, nullptr, nullptr };
+            for (int c = 0; c < 3; c++) {
+                cudaStream_t st = cstream(sub, c);
+                if (sub_lo[sub] >= (uint32_t) lists[c]->size() || st == seen[0] || st == seen[1]) continue;
+                seen[c] = st;
+                CK(cudaStreamWaitEvent(st, ctx->io_evs[4 * sub], 0), "stream wait");
+            }
         }
-        if (!any_zip) finish_out(sub, st);
+        else copy_in(sub, kstream(sub));
+        for (uint32_t round = 0; round < rounds_planned; round++)
+            launch_round(sub, round + 1 == rounds_planned && any_zip, round, qbreadth ? 1 : 0);      /* the last planned round counts the units still running */
+        /* The output goes home as soon as the planned rounds are through - MSZIP's too: a folder whose blocks are shorter than
+         * 32 KiB needs more rounds than its size suggests (below), and only its sub-wave is then copied once more. */
+        { int r_; if ((r_ = finish_out(sub, 0)) || (r_ = finish_out(sub, 1))) return r_; }
+        if (!qsplit) { int r_ = finish_out(sub, 2); if (r_) return r_; }
     }
+    if (qsplit) for (uint32_t sub = 0; sub < nsub; sub++) {
+        if (qbreadth) launch_round(sub, false, 0, 2);
+        int r_ = finish_out(sub, 2); if (r_) return r_;
+    }      /* Quantum's output: behind everything else in the D2H queue */
     CK(cudaGetLastError(), "kernel launch");
     if (any_zip) {
         /* MSZIP blocks may be shorter than 32 KiB, so a folder can need more rounds than its size suggests:
          * read the per-sub-wave "units still running" counters back and finish the stragglers */
+        std::vector<uint8_t> redo(nsub, 0);
         for (int guard = 0;; guard++) {
             for (int i = 0; i < NS; i++) CK(cudaStreamSynchronize(NS == 1 ? s : ctx->sub[i]), "sync");
-            CK(cudaMemcpy(ctx->h_pinned, a.not_done, (percodec ? 3 : nsub) * 4, cudaMemcpyDeviceToHost), "read counters");
+            for (size_t i = 0; i < nxs; i++) CK(cudaStreamSynchronize(ctx->xs[i]), "sync");
+            CK(cudaMemcpy(ctx->h_pinned, a.not_done, (size_t) nsub * 12, cudaMemcpyDeviceToHost), "read counters");
             bool again = false;
-            if (percodec) { if (ctx->h_pinned[0] | ctx->h_pinned[1] | ctx->h_pinned[2]) { again = true; launch_round(0, s, true, rounds_planned); } }
-            else for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[sub]) {
-                again = true;
-                launch_round(sub, kstream(sub), true, rounds_planned);
+            for (uint32_t sub = 0; sub < nsub; sub++) if (ctx->h_pinned[3 * sub] | ctx->h_pinned[3 * sub + 1] | ctx->h_pinned[3 * sub + 2]) {
+                again = true; redo[sub] = 1;
+                launch_round(sub, true, rounds_planned);
             }
             if (!again) break;
             if (guard > (1 << 17)) return fail(ctx, MSGPU_ERR_DECRUNCH, "wave did not converge");
         }
-        for (uint32_t sub = 0; sub < nsub; sub++) finish_out(sub, kstream(sub));
+        for (uint32_t sub = 0; sub < nsub; sub++) if (redo[sub]) for (int c = 0; c < 3; c++) { int r_ = finish_out(sub, c); if (r_) return r_; }
     }
     if (NS > 1) for (int i = 0; i < NS; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->sub[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[i], 0), "stream wait"); }
+    for (size_t i = 0; i < nxs; i++) { CK(cudaEventRecord(ctx->xs_ev[i], ctx->xs[i]), "event"); CK(cudaStreamWaitEvent(s, ctx->xs_ev[i], 0), "stream wait"); }
     if (hostpipe) {
         CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB], ctx->cp_in), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB], 0), "stream wait");
         CK(cudaEventRecord(ctx->ev_join[msgpu_ctx::NSUB + 1], ctx->cp_out), "event"); CK(cudaStreamWaitEvent(s, ctx->ev_join[msgpu_ctx::NSUB + 1], 0), "stream wait");

@@ -127,6 +127,23 @@ def test_host_pipeline_many_subwaves(decoder, oracle_ref):
     _check_batch(decoder, oracle_ref, m, "host pipeline mixed")
 
 
+def test_host_pipeline_codec_streams(decoder, oracle_ref):
+    """Host buffers, several codecs, contiguous units (per-range copies, no primed span): every sub-wave's codecs run on streams of
+    their own with Quantum's output queued last (msgpu.cu run_wave `qsplit`), MSZIP output goes home before the straggler check and
+    the sub-waves that hold folders of short blocks (more rounds than their size suggests) are copied once more."""
+    from util import RING_CASES, ring_batch
+    rb, raws = ring_batch(RING_CASES[:-1])
+    parts = [gen.make_batch(CODEC_MSZIP, 4600), rb, gen.make_batch(CODEC_MSZIP, 900, first_unit=7000),
+             gen.make_batch(CODEC_LZX, 5000, first_unit=10000), gen.make_batch(CODEC_QUANTUM, 4700, unit_bytes=4096, first_unit=20000)]
+    m = gen.concat_batches(parts)
+    out, st = _check_batch(decoder, oracle_ref, m, "host pipeline, a stream per codec")
+    assert (st == 0).all()
+    for i, r in enumerate(raws):
+        assert m.unit_output(out, 4600 + i).tobytes() == r
+    z = gen.concat_batches([gen.make_batch(CODEC_MSZIP, 4600), rb, gen.make_batch(CODEC_MSZIP, 4600, first_unit=7000)])
+    _check_batch(decoder, oracle_ref, z, "host pipeline, MSZIP with stragglers")
+
+
 def test_full_size_lzx_properties(decoder):
     """BASELINE config 3 at a quarter of full size (16 384 LZX wb21 units, 512 MiB): round trip against the
     generator's raw data - the size-independent property decode(encode(x)) == x; bench.py checks the
