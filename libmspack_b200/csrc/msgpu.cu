@@ -619,11 +619,12 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
      * Quantum's take 9x as long as the others', so they start at once and the other codecs' CTAs share the SMs they leave free. */
     const bool percodec = !h_in && !ctx->stage_timing && nsub == 1 && ctx->dev_streams > 1 && mixed;
     const int NS = percodec ? 3 : ((nsub > 1 && !ctx->stage_timing) ? (hostpipe ? (int) msgpu_ctx::NSUB : ctx->dev_streams) : 1);
-    /* Host buffers, several codecs: the three codecs of a sub-wave run on three streams - a Quantum P1 launch takes ~80 ms however
-     * few units it has (the serial decode of a frame), and in one stream order it held back the sub-wave's LZX / MSZIP output and
-     * everything queued behind it (BASELINE config 5 end to end: 17 GB/s).  Every sub-wave's Quantum chain gets a stream of its own
-     * (ctx->xs), so all of them are resident together, and its output is queued for the D2H engine behind the other codecs'. */
-    const bool qsplit = hostpipe && mixed && nq != 0;
+    /* Host buffers: the three codecs of a sub-wave run on three streams - a Quantum P1 launch takes ~80 ms however few units it
+     * has (the serial decode of a frame), and in one stream order it held back the sub-wave's LZX / MSZIP output and everything
+     * queued behind it (BASELINE config 5 end to end: 17 GB/s).  Every sub-wave's Quantum chain gets a stream of its own
+     * (ctx->xs), so all of them are resident together (also in a Quantum-only batch: two or three sub-waves per compute stream
+     * ran one after the other), and its output is queued for the D2H engine behind the other codecs'. */
+    const bool qsplit = hostpipe && nq != 0;
     const bool qbreadth = qsplit && rounds_planned == 1;      /* (one-frame units: every P1 launch of the wave can be issued before any resolve launch) */
     size_t nxs = 0;
     if (qsplit) {
@@ -639,7 +640,7 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
     auto cstream = [&](uint32_t sub, int c) -> cudaStream_t {
         if (NS == 1) return s;
         if (percodec) return ctx->sub[c == 0 ? 1 : (c == 1 ? 2 : 0)];
-        if (hostpipe && mixed) return (c == 2 && qsplit) ? ctx->xs[sub % nxs] : ctx->sub[(2 * sub + (uint32_t) (c & 1)) % (uint32_t) msgpu_ctx::NSUB];
+        if (hostpipe && (mixed || qsplit)) return (c == 2 && qsplit) ? ctx->xs[sub % nxs] : ctx->sub[(2 * sub + (uint32_t) (c & 1)) % (uint32_t) msgpu_ctx::NSUB];
         return kstream(sub);
     };
     if (hostpipe) {
