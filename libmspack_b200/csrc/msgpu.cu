@@ -107,14 +107,14 @@ __global__ void __launch_bounds__(NT) k_p1_lzx(WaveArgs a, const uint32_t *order
     if (valid) { t.end(st); a.ustate[slot] = st; if (!st.done) atomicAdd(a.not_done + a.sub, 1u); }
 }
 
-template <int NT>
+template <int NT, bool CONV>      /* CONV: GET_SYMBOL's scans as branch-free eight-wide walks (msgpu_p1_qtm.cuh scan8) */
 __global__ void __launch_bounds__(NT) k_p1_qtm(WaveArgs a, const uint32_t *order, uint32_t first, uint32_t count, uint8_t *save)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t ti = first + blockIdx.x * NT + threadIdx.x;
     const bool valid = ti < count;
     uint32_t slot = valid ? order[ti] : 0;
-    QtmLane<NT> t; t.phase = PH_IDLE;
+    QtmLane<NT, CONV> t; t.phase = PH_IDLE;
     MsUnitState st;
     t.bind(reinterpret_cast<QtmShared<NT> *>(smem_raw), (int) threadIdx.x);      /* every thread: idle lanes take part in the warp-cooperative model updates */
     if (valid) {
@@ -302,6 +302,7 @@ struct msgpu_ctx {
     /* pinned staging for a wave's tables (unit descriptors, per-codec order lists, E8 bases, chains): the uploads are true async
      * copies, so a device-buffer batch of LZX / Quantum units never blocks the caller (MSZIP waves still read a counter back) */
     int dev_streams = 3;  /* MSGPU_STREAMS=1: everything of a device-buffer batch in the caller's stream order (default: mixed batches run each codec on a stream of its own) */
+    int qtm_conv = 1;     /* MSGPU_QTM_CONV=0: the Quantum P1 kernel with the early-exit scan loops instead of the converged eight-wide scans (A/B: P1 70.3 against 63.1 ms, profiles/r2_qtm_ab_t.txt) */
     int p2_bulk = 1;      /* MSGPU_P2_BULK=0: the load-by-lanes variant of the resolve kernel's record window (A/B, see profiles/r2_p2_bulk_ab.txt) */
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
     size_t bytes_held() const {
@@ -344,6 +345,7 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     const char *env = getenv("MSGPU_SCRATCH_MB");
     c->scratch_budget = env ? (size_t) atoll(env) << 20 : (size_t) ((double) free_b * 0.45);
     { const char *v = getenv("MSGPU_P2_BULK"); c->p2_bulk = v ? atoi(v) : 1; }
+    { const char *v = getenv("MSGPU_QTM_CONV"); c->qtm_conv = v ? atoi(v) : 1; }
     { const char *v = getenv("MSGPU_STREAMS"); if (v) { int k = atoi(v); c->dev_streams = k < 1 ? 1 : (k > (int) msgpu_ctx::NSUB ? (int) msgpu_ctx::NSUB : k); } }
     /* the entropy kernels use most of an SM's shared memory: opt in */
     cudaError_t ae = cudaSuccess;
@@ -351,7 +353,8 @@ extern "C" msgpu_ctx *msgpu_create(int device) {
     SETA((k_p1_mszip<ZIP_NT, ZIP_HEADN>), sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>))
     SETA((k_p1_lzx<LZX_NT, LZX_HEADN, false, LZX_H8LB>), sizeof(LzxSharedSel<LZX_NT, LZX_HEADN, LZX_H8LB>::type))
     SETA((k_p1_lzx<LZXD_NT, LZXD_HEADN, true, 0>), sizeof(LzxSharedC<LZXD_NT, LZXD_HEADN>))
-    SETA((k_p1_qtm<QTM_NT>), sizeof(QtmShared<QTM_NT>))
+    SETA((k_p1_qtm<QTM_NT, false>), sizeof(QtmShared<QTM_NT>))
+    SETA((k_p1_qtm<QTM_NT, true>), sizeof(QtmShared<QTM_NT>))
     /* (the KWAJ / repair-mode instantiation: a refusal here only fails the waves that hold such units, at their launch) */
     if (cudaFuncSetAttribute(k_p1_mszip<ZIP_NT, ZIP_HEADN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ZipSharedC<ZIP_NT, ZIP_HEADN>)) != cudaSuccess) (void) cudaGetLastError();
 #undef SETA
@@ -759,7 +762,8 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
             if (qstage != 2) {
                 if (clear) cudaMemsetAsync(a.not_done + w.sub, 0, 4, st);
                 mark(0, st);
-                k_p1_qtm<QTM_NT><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+                if (ctx->qtm_conv) k_p1_qtm<QTM_NT, true><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
+                else k_p1_qtm<QTM_NT, false><<<(f1 - f0 + QTM_NT - 1) / QTM_NT, QTM_NT, sizeof(QtmShared<QTM_NT>), st>>>(w, d_ord_q, f0, f1, reinterpret_cast<uint8_t *>(ctx->save_qtm.p));
                 mark(0, st); ctx->launches++;
             }
             if (qstage != 1) { mark(1, st); p2_launch(w, d_ord_q, f0, f1, st); ctx->launches++; mark(1, st); } }

@@ -71,7 +71,8 @@ struct QtmShared {
     uint8_t  shl[9 * NT];
 };
 
-template <int NT>
+/* CONV: the two scan levels of GET_SYMBOL as fixed eight-wide, branch-free walks (scan8) instead of loops with early exits */
+template <int NT, bool CONV = false>
 struct QtmLane {
     MsBits b;
     uint16_t *cum, *tot; uint8_t *sym, *shl;
@@ -201,6 +202,22 @@ struct QtmLane {
 
     /* READ_BYTES bookkeeping: two more bytes fetched; fails past in_len + 2 (readbits.h:192-214) */
     MS_M void fetch2() { if (fp + 2 > b.in_len + 2) b.err = MS_EREAD; fp += 2; bl += 16; }
+    /* `while (bl < n) fetch2(); bl -= n;` for 0 <= n <= 31 without a loop or a branch: k = 0..2 fetches; the last one is the one
+     * that can run past the input (fp only grows).  In lockstep SOME lane of the warp needs a fetch in almost every step, so the
+     * loop's body ran in almost every step with two or three active threads (profiles/r2_p1qtm_m.txt: 2.1 % of the kernel's
+     * warp-instructions at 2.2 threads each, per call site). */
+    MS_M void take_bits(int n) {
+        const int d = bl - n;
+        const int k = d < 0 ? (15 - d) >> 4 : 0;
+        if (k > 0 && fp + 2 * (k - 1) > b.in_len) b.err = MS_EREAD;
+        fp += 2 * k; bl = d + 16 * k;
+    }
+    /* n stream bits (0 <= n <= 31) off the top of the bit buffer; the caller has made sure b.bc >= n */
+    MS_M uint32_t pull_bits(int n) {
+        const uint32_t v = (uint32_t) ((b.bb >> 1) >> (63 - n));
+        b.bb <<= n; b.bc -= n;
+        return v;
+    }
 
     MS_M void update_model(int base, int midx, int entries) {             /* qtmd.c:125-166 */
         uint32_t s = shl[midx * NT] - 1u;
@@ -250,6 +267,30 @@ struct QtmLane {
         }
     }
 
+    /* Eight entries of a cumulative-frequency walk in one go, every lane the same instructions: c_0 = start, c_{k+1} = c_k - g(k);
+     * returns the first k with k + 1 >= nleft or c_{k+1} <= symf (there is one: the walk's last entry, or the group's end that level
+     * 1 chose), prev = c_k, cur = c_{k+1}.  In lockstep the loops with early exits run as many rounds as the warp's slowest lane
+     * needs, each exit a divergent block: 27 % of the kernel's warp-instructions at 18 active threads (profiles/r2_p1qtm_m.txt). */
+    template <class G>
+    MS_M static int scan8(uint32_t start, uint32_t symf, int nleft, G g, uint32_t &prev, uint32_t &cur) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = g(k);
+        uint32_t c = start, pv = start, cv = 0; int ks = 0; bool seen = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t cn = c - v[k];
+            const bool stop = (k + 1 >= nleft) || (cn <= symf);     /* once true it stays true: the c_k decrease */
+            cv = (stop && !seen) ? cn : cv;
+            pv = stop ? pv : cn;
+            ks += stop ? 0 : 1;
+            seen = seen || stop;
+            c = cn;
+        }
+        prev = pv; cur = cv;
+        return ks;
+    }
+
     /* GET_SYMBOL, qtmd.c:92-123 */
     MS_M uint32_t get_symbol(int base, int midx, int entries) {
         uint32_t range = ((H - L) & 0xFFFFu) + 1u;
@@ -262,6 +303,21 @@ struct QtmLane {
          * never selected. */
         uint32_t prev = c0, cur, gj; int j = 0;
         uint32_t sg = 0; int gsel = 0;
+        uint16_t *cp;
+        if constexpr (CONV) {
+            const int gb = grp_base(midx), ng = (entries + 7) >> 3;
+            uint32_t p1, e1;
+            const uint16_t *gp = grp + gb * NT;
+            const int gi = scan8(c0, symf, ng, [&](int k) { return (uint32_t) gp[k * NT]; }, p1, e1);
+            sg = p1 - e1; gsel = gb + gi; j = gi << 3;
+            const bool cold = midx < 4 && j >= QTM_HOT;
+            const int cs = cold ? 1 : NT;
+            cp = cold ? gcum + base + j : cum + hidx(base, midx, j) * NT;
+            const uint16_t *rp = cp;
+            const int k2 = scan8(p1, symf, entries - j, [&](int k) { return (uint32_t) rp[k * cs]; }, prev, cur);
+            gj = prev - cur; j += k2; cp += k2 * cs;
+        }
+        else {
         {
             /* level 1: the first group whose END (cum[8 (k+1)]) is <= symf, or the last group; prev becomes cum at its start */
             const int gb = grp_base(midx), ng = (entries + 7) >> 3;
@@ -281,7 +337,7 @@ struct QtmLane {
         /* the group's eight entries are all hot or all cold (QTM_HOT is a multiple of 8): one pointer and stride for the walk */
         const bool cold = midx < 4 && j >= QTM_HOT;
         const int cs = cold ? 1 : NT;
-        uint16_t *cp = cold ? gcum + base + j : cum + hidx(base, midx, j) * NT;
+        cp = cold ? gcum + base + j : cum + hidx(base, midx, j) * NT;
 #pragma unroll 1
         for (;; j += 4, cp += 4 * cs) {
             const uint32_t g0 = cp[0], g1 = cp[cs], g2 = cp[2 * cs], g3 = cp[3 * cs];
@@ -291,6 +347,7 @@ struct QtmLane {
             if (j + 3 >= entries || c3 <= symf) { gj = g2; cur = c3; prev = c2; j += 2; cp += 2 * cs; break; }
             if (j + 4 >= entries || c4 <= symf) { gj = g3; cur = c4; prev = c3; j += 3; cp += 3 * cs; break; }
             prev = c4;
+        }
         }
         uint32_t s = sym[base + j];
         range = (uint32_t) ((int32_t) H - (int32_t) L + 1);
@@ -312,35 +369,40 @@ struct QtmLane {
              * one shift by the count of equal leading bits, one by the length of the underflow run (m shifts of C ^= 0x4000 flip,
              * in the end, only the bit that lands on top).  In lockstep the loop costs a warp 4.3 iterations per symbol on the text
              * workload (its slowest lane), these two blocks cost 2. */
+            /* Both shifts as ONE read: n + m <= 31 bits leave the bit buffer together (one refill test, one fetch count - the
+             * reference's two requests of n and of m bits fetch exactly as often as one request of n + m: a fetch in front of the
+             * first implies bl < n + m, one in front of the second implies bl - n < m, and 16 more bits always cover what is left
+             * of a sum below 32), and every lane runs the same instructions whether its symbol shifts or not. */
             const uint32_t x = (L ^ H) & 0xFFFFu;
-            if (!(x & 0x8000u)) {
-                const int n = x ? MS_CLZ(x << 16) : 16;
-                L = (L << n) & 0xFFFFu; H = ((H << n) | ((1u << n) - 1u)) & 0xFFFFu;
-                while (bl < n) fetch2();
-                bl -= n;
-                if (b.bc < n) qtm_refill(b);
-                C = ((C << n) | msb_peek(b, n)) & 0xFFFFu; msb_drop(b, n);
-            }
-            const uint32_t u = L & ~H & 0x7FFFu;
+            const int n = (x & 0x8000u) ? 0 : (x ? MS_CLZ(x << 16) : 16);
+            const uint32_t L1 = (L << n) & 0xFFFFu, H1 = ((H << n) | ((1u << n) - 1u)) & 0xFFFFu;
+            const uint32_t u = L1 & ~H1 & 0x7FFFu;
             const int m = MS_CLZ(~(u << 17));                  /* ones from bit 14 downwards: 0..15 */
-            if (m) {
-                L = (L << m) & 0x7FFFu; H = ((H << m) | ((1u << m) - 1u) | 0x8000u) & 0xFFFFu;
-                while (bl < m) fetch2();
-                bl -= m;
-                if (b.bc < m) qtm_refill(b);
-                C = (((C << m) ^ 0x8000u) | msb_peek(b, m)) & 0xFFFFu; msb_drop(b, m);
-            }
+            const int t = n + m;
+            take_bits(t);
+            if (b.bc < t) qtm_refill(b);
+            const uint32_t bits = pull_bits(t);
+            L = m ? (L1 << m) & 0x7FFFu : L1;
+            H = m ? ((H1 << m) | ((1u << m) - 1u) | 0x8000u) & 0xFFFFu : H1;
+            C = (((C << t) | bits) ^ (m ? 0x8000u : 0u)) & 0xFFFFu;
             return s;
         }
     }
 
-    MS_M uint32_t read_many(int n) {                                      /* READ_MANY_BITS, readbits.h:143-153 */
-        if (n == 0) return 0;
-        int needed = n;
-        while (needed > 0) { if (bl <= 16) fetch2(); int run = bl < needed ? bl : needed; bl -= run; needed -= run; }
+    /* READ_MANY_BITS (readbits.h:143-153), 0 <= n <= 19, without a loop or a branch: the macro fetches when 16 bits or fewer are
+     * left, takes what is there, and - only when that was not enough, i.e. the buffer is empty now - fetches once more.  n == 0
+     * touches nothing.  All lanes of the warp call this in every step (most with n == 0, see step()). */
+    MS_M uint32_t read_many(int n) {
+        const bool f1 = n > 0 && bl <= 16;
+        if (f1 && fp > b.in_len) b.err = MS_EREAD;
+        fp += f1 ? 2 : 0; bl += f1 ? 16 : 0;
+        const int run = bl < n ? bl : n, needed = n - run;
+        bl -= run;
+        const bool f2 = needed > 0;
+        if (f2 && fp > b.in_len) b.err = MS_EREAD;
+        fp += f2 ? 2 : 0; bl += f2 ? 16 - needed : 0;
         qtm_refill(b);
-        uint32_t v = msb_peek(b, n); msb_drop(b, n);
-        return v;
+        return pull_bits(n);
     }
     MS_M uint32_t read_bits(int n) {                                      /* READ_BITS, 1 <= n <= 16 */
         while (bl < n) fetch2();
@@ -404,48 +466,47 @@ struct QtmLane {
 
     MS_M void next_selector() { mst = QS_SELECTOR; m_base = QM7; m_idx = 8; m_ent = 7; }
 
+    /* One model symbol, whatever it means, in ONE instruction stream.  The four meanings used to be the arms of a switch: in
+     * lockstep a warp has lanes in all four states, so every step ran all four arms, each with a quarter of the lanes - 35 % of
+     * the kernel's warp-instructions at 7 active threads (profiles/r2_p1qtm_m.txt: the switch, the emit code and the two
+     * READ_MANY_BITS it inlines).  Now the extra-bit count and base of a length or offset symbol come from selects (0 for the
+     * other two states), all lanes run one read_many(), and only the two emit calls stay conditional. */
     MS_M void step() {
-        uint32_t s = get_symbol(m_base, m_idx, m_ent);
-        if (mst == QS_SELECTOR) {
-            if (s < 4) { mst = QS_LITERAL; m_base = QM0 + 65 * (int) s; m_idx = (int) s; m_ent = 64; }
-            else if (s == 4) { mst = QS_OFFSET; m_ml = 3; m_base = QM4; m_idx = 4; m_ent = ent4; }
-            else if (s == 5) { mst = QS_OFFSET; m_ml = 4; m_base = QM5; m_idx = 5; m_ent = ent5; }
-            else if (s == 6) { mst = QS_LENGTH; m_base = QM6L; m_idx = 7; m_ent = 27; }
-            else { fail(b.err ? b.err : MS_EDECRUNCH); return; }
-            if (MS_UNLIKELY(b.err)) fail(b.err);
-            return;
-        }
-        if (mst == QS_LITERAL) { emit_literal(em, q, s); q++; frame_todo--; }
-        else if (mst == QS_LENGTH) {
-            /* length_base[] / length_extra[] (qtmd.c:76-83) in closed form */
-            uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
-            uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
-            m_ml = lb + read_many((int) le) + 5;
-            mst = QS_OFFSET; m_base = QM6; m_idx = 6; m_ent = ent6;
-            if (MS_UNLIKELY(b.err)) fail(b.err);
-            return;
-        }
-        else {
-            /* position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
-            uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
-            uint32_t pb = s < 2 ? s : (2u + (s & 1)) << pe;
-            uint32_t off = pb + read_many((int) pe) + 1, ml = m_ml;
-            if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-            uint32_t G = frame_start_pos + q, window_posn = G & (window_size - 1);
+        const uint32_t s = get_symbol(m_base, m_idx, m_ent);
+        const bool is_sel = mst == QS_SELECTOR, is_lit = mst == QS_LITERAL, is_len = mst == QS_LENGTH, is_off = mst == QS_OFFSET;
+        /* length_base[] / length_extra[] (qtmd.c:76-83) and position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
+        const uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
+        const uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
+        const uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
+        const uint32_t pb = s < 2 ? s : (2u + (s & 1)) << (pe & 31u);
+        const uint32_t xb = read_many((int) (is_len ? le : (is_off ? pe : 0u)));
+        if (MS_UNLIKELY(is_sel && s > 6)) { fail(b.err ? b.err : MS_EDECRUNCH); return; }
+        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
+        if (is_lit) { emit_literal(em, q, s); q++; frame_todo--; }
+        else if (is_off) {
+            const uint32_t off = pb + xb + 1, ml = m_ml;
+            const uint32_t G = frame_start_pos + q, window_posn = G & (window_size - 1);
             if (ml > frame_todo) { fail(MS_EDECRUNCH); return; }           /* :424-427 overshot frame alignment */
             frame_todo -= ml;
             if (window_posn + ml > window_size) {
                 /* :358-390 the reference flushes the whole window first and bails out if that is more than requested */
-                uint32_t lap_start = G - window_posn;
+                const uint32_t lap_start = G - window_posn;
                 if ((uint64_t) lap_start + window_size > u->out_len) { fail(MS_EDECRUNCH); return; }
             }
-            uint32_t emit_len = ml < limit - q ? ml : limit - q;
+            const uint32_t emit_len = ml < limit - q ? ml : limit - q;
             emit_match(em, q, emit_len, off);
             q += ml;
         }
-        next_selector();
-        if (MS_UNLIKELY(b.err)) { fail(b.err); return; }
-        if (q >= limit) phase = PH_END;
+        /* what the next model symbol means: selector -> literal model s / offset model 4, 5 (match length 3, 4) / length model;
+         * length -> offset model 6; literal, offset -> selector */
+        const bool to_sel = is_lit || is_off;
+        const bool to_off = is_len || (is_sel && (s == 4 || s == 5));
+        const bool to_lit = is_sel && s < 4;
+        m_ml = is_len ? lb + xb + 5 : (is_sel ? s - 1 : m_ml);              /* (selector 4 / 5: a match of 3 / 4 bytes) */
+        mst = to_sel ? (uint32_t) QS_SELECTOR : (to_lit ? (uint32_t) QS_LITERAL : (to_off ? (uint32_t) QS_OFFSET : (uint32_t) QS_LENGTH));
+        const int nm = to_sel ? 8 : (to_lit ? (int) s : (is_len ? 6 : (s == 4 ? 4 : (s == 5 ? 5 : 7))));
+        m_idx = nm; m_base = model_base(nm); m_ent = model_len(nm);
+        if (to_sel && q >= limit) phase = PH_END;
     }
 
     MS_M void begin(const msgpu_unit *unit, const uint8_t *in_base, const MsUnitState &st, MsRec *r, uint8_t *l, MsFrameInfo *fi,

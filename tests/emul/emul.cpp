@@ -137,12 +137,13 @@ extern "C" int emul_decode_unit(const msgpu_unit *u, const uint8_t *in_base, uin
         free(sh); free(aux);
     }
     else if (u->codec == MSGPU_CODEC_QUANTUM) {
-        typedef QtmShared<1> SH; typedef QtmLane<1> TH;
+        typedef QtmShared<1> SH; typedef QtmLane<1> TH; typedef QtmLane<1, true> THC;      /* THC: the converged scans (frames_per_round bit 0x800) */
+        const bool conv = (frames_per_round & 0x800) != 0;
         SH *sh = (SH *) calloc(1, sizeof(SH)); uint8_t *save = (uint8_t *) calloc(1, QTM_SAVE_BYTES);
         for (int guard = 0; !(st.started && st.done) && guard < 1 << 20; guard++) {
-            TH t; t.bind(sh, 0);
-            t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save);
-            emul_run(t); t.end(st); resolve();
+            if (conv) { THC t; t.bind(sh, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save); emul_run(t); t.end(st); }
+            else { TH t; t.bind(sh, 0); t.begin(u, in_base, st, recs.data(), unit_out, finfo.data(), F, save); emul_run(t); t.end(st); }
+            resolve();
         }
         free(sh); free(save);
     }

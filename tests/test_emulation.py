@@ -463,3 +463,42 @@ def test_long_units_frames_per_round(emul, oracle_ref, fpr):
     o2, s2 = emul(units, comp, m.out_bytes, fpr)
     assert (s1 != 0).any()
     assert_same(units, o1, s1, o2, s2, f"damaged long units F={fpr}")
+
+
+QTM_CONV = 0x800          # tests/emul/emul.cpp: QtmLane<1, true> (the converged eight-wide scans, msgpu_p1_qtm.cuh scan8)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(window_bits=10), dict(window_bits=12, data="binary", unit_bytes=65536), dict(window_bits=16, unit_bytes=100000),
+                                dict(data="zeros", unit_bytes=65536), dict(data="random"), dict(unit_bytes=3), dict(unit_bytes=32769)],
+                         ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
+def test_quantum_converged_scans(emul, oracle_ref, kw):
+    """GET_SYMBOL's two scan levels as branch-free eight-wide walks (QtmLane CONV): the same bytes and status as the reference on
+    intact, bit-flipped and truncated units, 1 and 2 frames per launch round."""
+    b = gen.make_batch(CODEC_QUANTUM, 12, **kw)
+    o1, s1, _ = oracle_ref.decode_batch(b.units, b.comp, b.out_bytes, threads=4)
+    assert (s1 == 0).all()
+    for fpr in (1, 2):
+        o2, s2 = emul(b.units, b.comp, b.out_bytes, fpr | QTM_CONV)
+        assert_same(b.units, o1, s1, o2, s2, f"quantum converged {kw} F={fpr}")
+    rng = np.random.default_rng(9)
+    comp, units = b.comp.copy(), b.units.copy()
+    for i, u in enumerate(units):
+        lo, n = int(u["in_off"]), int(u["in_len"])
+        if i % 2 == 0:
+            comp[lo + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            units["in_len"][i] = max(1, n - int(rng.integers(1, 40)))
+    o1, s1, _ = oracle_ref.decode_batch(units, comp, b.out_bytes, threads=4)
+    o2, s2 = emul(units, comp, b.out_bytes, 1 | QTM_CONV)
+    assert_same(units, o1, s1, o2, s2, f"damaged quantum converged {kw}")
+
+
+def test_quantum_converged_scans_goldens(emul):
+    for entry in golden_manifest():
+        if entry["codec"] != CODEC_QUANTUM:
+            continue
+        u, comp = golden_unit(entry)
+        out, st = emul(u, comp, entry["out_len"], 2 | QTM_CONV)
+        assert int(st[0]) == entry["err"], entry["name"]
+        if entry["err"] == 0:
+            assert hashlib.md5(out.tobytes()).hexdigest() == entry["md5"], entry["name"]
