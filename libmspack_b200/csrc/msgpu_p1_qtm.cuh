@@ -79,10 +79,11 @@ struct QtmLane {
     uint32_t H, L, C;                 /* 16-bit values */
     int32_t bl, fp;                   /* the reference's bits_left and fetched-byte count, for the EOF rule only */
     int ent4, ent5, ent6;
+    uint64_t entpack;                 /* entries of models 4..8, a byte each (model_len) */
 
     uint16_t *gcum;                   /* the cold entries: the unit's save area, indexed like the reference's arrays */
     /* entry i of model (base, midx): compact index among the hot entries / a reference to wherever it lives */
-    MS_M static int hidx(int base, int midx, int i) { return midx < 4 ? QM0 + QTM_HOT * midx + i : (midx == 8 ? i : base - QTM_COLD + i); }
+    MS_M static int hidx(int base, int midx, int i) { (void) base; return hot_base(midx) + i; }
     MS_M static uint16_t &cref(uint16_t *hot, uint16_t *cold, int base, int midx, int i) { return (midx < 4 && i >= QTM_HOT) ? cold[base + i] : hot[hidx(base, midx, i) * NT]; }
     uint32_t *ws, *wsmin; uint32_t upd_pending; int upd_base, upd_midx, upd_ent;
     MS_M void bind(QtmShared<NT> *sh, int tid) {
@@ -219,6 +220,24 @@ struct QtmLane {
         return v;
     }
 
+    /* qtmd.c:130-136 for the selector model (7 entries, all hot, one group), which stays with its lane (QTM_COOP_MIN): the rescale
+     * with the seven differences in registers - the lane does this alone while its warp waits, so every instruction counts 32-fold */
+    MS_M void rescale_selector() {
+        shl[8 * NT] = (uint8_t) (shl[8 * NT] - 1u);
+        uint32_t g[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) g[i] = cum[i * NT];
+        uint32_t old = 0, nn = 0;
+#pragma unroll
+        for (int i = 6; i >= 0; i--) {
+            old += g[i];
+            uint32_t c = old >> 1;
+            if (c <= nn) c = nn + 1;
+            cum[i * NT] = (uint16_t) (c - nn); nn = c;
+        }
+        tot[8 * NT] = (uint16_t) nn; grp[0] = (uint16_t) nn;
+    }
+
     MS_M void update_model(int base, int midx, int entries) {             /* qtmd.c:125-166 */
         uint32_t s = shl[midx * NT] - 1u;
         if (s) {
@@ -276,17 +295,19 @@ struct QtmLane {
         uint32_t v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = g(k);
-        uint32_t c = start, pv = start, cv = 0; int ks = 0; bool seen = false;
+        uint32_t c = start, pv = start; int ks = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t cn = c - v[k];
             const bool stop = (k + 1 >= nleft) || (cn <= symf);     /* once true it stays true: the c_k decrease */
-            cv = (stop && !seen) ? cn : cv;
-            pv = stop ? pv : cn;
+            pv = stop ? pv : cn;                                    /* ends as c at the first stop */
             ks += stop ? 0 : 1;
-            seen = seen || stop;
             c = cn;
         }
+        /* g(ks) out of the eight loaded values: a select tree on the bits of ks */
+        const uint32_t a0 = (ks & 1) ? v[1] : v[0], a1 = (ks & 1) ? v[3] : v[2], a2 = (ks & 1) ? v[5] : v[4], a3 = (ks & 1) ? v[7] : v[6];
+        const uint32_t b0 = (ks & 2) ? a1 : a0, b1 = (ks & 2) ? a3 : a2;
+        const uint32_t cv = pv - ((ks & 4) ? b1 : b0);
         prev = pv; cur = cv;
         return ks;
     }
@@ -359,7 +380,7 @@ struct QtmLane {
         grp[gsel * NT] = (uint16_t) (sg + 8);
         c0 = (c0 + 8) & 0xFFFFu; tot[midx * NT] = (uint16_t) c0;
         if (c0 > 3800) {
-            if (entries <= QTM_COOP_MIN) update_model(base, midx, entries);
+            if (entries <= QTM_COOP_MIN) { if (midx == 8 && shl[8 * NT] > 1u) rescale_selector(); else update_model(base, midx, entries); }
             else { upd_pending = 1; upd_base = base; upd_midx = midx; upd_ent = entries; }      /* all lanes together, after the step (post_step) */
         }
         {
@@ -518,6 +539,7 @@ struct QtmLane {
         for (int k = 0; k < nframes; k++) { MsFrameInfo z; z.nrec = 0; z.size = 0; z.g0 = 0; z.valid = 0; fi[k] = z; }
         const int wb = unit->window_bits, wb2 = wb * 2;
         ent4 = wb2 > 24 ? 24 : wb2; ent5 = wb2 > 36 ? 36 : wb2; ent6 = wb2;
+        entpack = (uint64_t) (uint32_t) ent4 | ((uint64_t) (uint32_t) ent5 << 8) | ((uint64_t) (uint32_t) (ent6 & 0xFF) << 16) | (27ull << 24) | (7ull << 32);
         window_size = 1u << (wb & 31);
         if (!st.started) {
             done = 0; status = 0; produced = 0; frame = 0; header_read = 0; frame_todo = MS_FRAME;
@@ -562,9 +584,26 @@ struct QtmLane {
 
     uint16_t *grp;
     /* first group sum of model midx (0-3 literals, 4-6 offsets, 7 length, 8 selector) */
-    MS_M static int model_base(int midx) { return midx < 4 ? QM0 + 65 * midx : (midx == 4 ? QM4 : (midx == 5 ? QM5 : (midx == 6 ? QM6 : (midx == 7 ? QM6L : QM7)))); }
-    MS_M int model_len(int midx) const { return midx < 4 ? 64 : (midx == 4 ? ent4 : (midx == 5 ? ent5 : (midx == 6 ? ent6 : (midx == 7 ? 27 : 7)))); }
-    MS_M static int grp_base(int midx) { return midx < 4 ? 1 + 8 * midx : (midx == 4 ? 33 : (midx == 5 ? 36 : (midx == 6 ? 41 : (midx == 7 ? 47 : 0)))); }
+    /* The per-model constants as a formula for the four literal models and a packed table for the other five (index midx - 4),
+     * picked by ONE select: as chains of conditionals the compiler turned them into branches, and with the lanes of a warp in
+     * different models every step walked those at 12 active threads - 9 % of the kernel's warp-instructions and 16 % of its
+     * stall samples (profiles/r2_p1qtm_u.txt). */
+    MS_M static int tab9(uint64_t packed, int bits, int midx) { return (int) ((packed >> (bits * ((midx - 4) & 7))) & ((1u << bits) - 1u)); }
+    MS_M static int model_base(int midx) {
+        const int lo = QM0 + 65 * midx, hi = tab9((uint64_t) QM4 | ((uint64_t) QM5 << 9) | ((uint64_t) QM6 << 18) | ((uint64_t) QM6L << 27) | ((uint64_t) QM7 << 36), 9, midx);
+        return midx < 4 ? lo : hi;
+    }
+    MS_M int model_len(int midx) const { const int hi = tab9(entpack, 8, midx); return midx < 4 ? 64 : hi; }
+    MS_M static int grp_base(int midx) {
+        const int lo = 1 + 8 * midx, hi = tab9(33ull | (36ull << 6) | (41ull << 12) | (47ull << 18), 6, midx);
+        return midx < 4 ? lo : hi;
+    }
+    /* compact index of a model's first hot entry (QtmShared::cum): the selector, the first QTM_HOT entries of each literal model, then
+     * models 4..7 whole */
+    MS_M static int hot_base(int midx) {
+        const int lo = QM0 + QTM_HOT * midx, hi = tab9((uint64_t) (QM4 - QTM_COLD) | ((uint64_t) (QM5 - QTM_COLD) << 8) | ((uint64_t) (QM6 - QTM_COLD) << 16) | ((uint64_t) (QM6L - QTM_COLD) << 24), 8, midx);
+        return midx < 4 ? lo : hi;
+    }
     MS_M void regroup(int base, int midx, int entries) {              /* group sums from g[] */
         const int gb = grp_base(midx);
         uint32_t acc = 0;
