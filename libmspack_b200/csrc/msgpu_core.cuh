@@ -328,10 +328,14 @@ MS_D int ms_canon_len(const uint32_t lim[15], uint32_t v16) {
  * lengths <= 15 are even, so the halved compare is exact) */
 template <int NT>
 MS_D int ms_canon_len_smem(const uint16_t *lim16, uint32_t v16) {
-    int len = 1; uint32_t h = v16 >> 1;
-#pragma unroll
-    for (int j = 0; j < 15; j++) len += (h >= lim16[j * NT]) ? 1 : 0;
-    return len;
+    /* two rounds of three loads (the pivots 3 / 7 / 11 pick a quarter, then its three limits) instead of fifteen loads and
+     * compares: the limits are non-decreasing, so the count of limits <= h is 4 q + the count inside quarter q.  The LZX step's
+     * LENGTH symbols beyond the LUT come through here with a quarter of the warp's lanes (profiles/r2_p1lzx_f.txt: 3 % of the
+     * kernel's warp-instructions at 7 active threads). */
+    const uint32_t h = v16 >> 1;
+    const int q = ((h >= lim16[3 * NT]) ? 1 : 0) + ((h >= lim16[7 * NT]) ? 1 : 0) + ((h >= lim16[11 * NT]) ? 1 : 0);
+    const uint16_t *p = lim16 + 4 * q * NT;
+    return 1 + 4 * q + ((h >= p[0]) ? 1 : 0) + ((h >= p[NT]) ? 1 : 0) + ((h >= p[2 * NT]) ? 1 : 0);
 }
 /* canonical index of the code v16 of length len */
 template <int NT>

@@ -161,6 +161,29 @@ struct LzxLaneC {
         return v;
     }
 
+    /* Literal bytes go to the output one by one, not through MsEmit's word gatherer: a byte store per literal instead of the
+     * gatherer's compare / merge per literal plus a flush path that a fifth of the warp's lanes walk in every step (4.6 % of the
+     * kernel's warp-instructions at 6.7 active threads, profiles/r2_p1lzx_f.txt; the same change was worth 9 % of MSZIP's P1).  The
+     * lane's current 32-byte sector stays in L2 between its stores.  Every literal path of the lane does the same - a gathered
+     * word is stored whole and would wipe out bytes stored one by one.  q < frame size by construction (lzxd.c:538-651). */
+    MS_M void lit_store(uint32_t qq, uint32_t v) { em.out[qq] = (uint8_t) v; }
+    /* n raw input bytes to frame positions q.. (uncompressed blocks): whole aligned words directly, the ragged ends bytewise */
+    MS_M void raw_store(uint32_t qq, const uint8_t *in, int32_t bp, uint32_t n) {
+        if (qq >= em.limit) return;
+        if (n > em.limit - qq) n = em.limit - qq;
+        const uint8_t *p = in + bp;
+#pragma unroll 1
+        for (; n && (qq & 3u); n--, qq++, p++) em.out[qq] = *p;
+#pragma unroll 1
+        for (; n >= 4; n -= 4, p += 4, qq += 4) {
+            if ((qq >> 2) < em.wlimit)
+                *reinterpret_cast<uint32_t *>(em.out + qq) = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+            else { em.out[qq] = p[0]; em.out[qq + 1] = p[1]; em.out[qq + 2] = p[2]; em.out[qq + 3] = p[3]; }
+        }
+#pragma unroll 1
+        for (; n; n--, qq++, p++) em.out[qq] = *p;
+    }
+
     /* the reference's bit buffer is empty and its byte pointer is at bytepos: go back to bit reading.
      * An odd byte pointer (odd-sized uncompressed block whose pad byte was not skipped because a reset
      * cleared block_type first, lzxd.c:257-270 vs :469-474) moves the 16-bit word grid by one byte. */
@@ -359,11 +382,11 @@ struct LzxLaneC {
         if (block_type == 1 || block_type == 2) { if (this_run > 0) phase = PH_DECODE; return; }
         if (block_type == 3) {
             if (this_run > 0 && bytepos + this_run <= b.in_len) {      /* the whole run lies inside the input: bulk copy */
-                emit_raw(em, q, b.in, bytepos, (uint32_t) this_run);
+                raw_store(q, b.in, bytepos, (uint32_t) this_run);
                 bytepos += this_run; q += (uint32_t) this_run; this_run = 0;
             }
 #pragma unroll 1
-            while (this_run > 0) { emit_literal(em, q, raw_byte()); q++; this_run--; }
+            while (this_run > 0) { lit_store(q, raw_byte()); q++; this_run--; }
             if (b.err) fail(b.err);
             return;
         }
@@ -436,7 +459,7 @@ struct LzxLaneC {
     template <bool careful> MS_M void step_plain() {
         lzx_refill(b);
         uint32_t sym = main_sym(careful);
-        if (sym < 256) { emit_literal(em, q, sym); q++; this_run--; }
+        if (sym < 256) { lit_store(q, sym); q++; this_run--; }
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
