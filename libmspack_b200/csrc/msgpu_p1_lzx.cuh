@@ -463,10 +463,12 @@ struct LzxLaneC {
         else {
             sym -= 256;
             uint32_t ml = sym & 7, slot = sym >> 3, off;
-            /* a LENGTH symbol beyond the LUT and the shared-memory head comes from L2 (45 % of P1's long-scoreboard stalls,
-             * profiles/r2_p1lzx_f.txt; deferring it: P1 8.51 -> 8.37 ms): the code's LENGTH is known without it, so the load is issued here and its value only
-             * added in front of the match's range checks - the offset fields are decoded while it is in flight */
-            uint32_t lgv = 0; bool lslow = false;
+            /* A LENGTH symbol beyond the LUT and the shared-memory head comes from L2.  Its value is consumed INSIDE that branch (the
+             * empty asm pins the wait for the load there): when the add sat behind the branches' join - `ml += length_sym()`, or the
+             * load issued early and `if (lslow) ml += lgv` after the offset decode - the one add every match step executes carried the
+             * load's scoreboard in its wait mask, and the same scoreboard guards the input word the bit reader prefetches one refill
+             * ahead: 60 % of the kernel's long-scoreboard stall samples sat on that add although the text batch never takes the
+             * branch (profiles/r2_p1lzx_z.txt) - every step waited for some lane's prefetch to land. */
             if (ml == 7) {
                 if (length_empty) { fail(b.err ? b.err : MS_EDECRUNCH); return; }                    /* :555-558 */
                 if (careful) lzx_check(b, 16);
@@ -478,7 +480,13 @@ struct LzxLaneC {
                     const uint32_t idx = lbo.index(v16, len);
                     msb_drop(b, len);
                     if (QL && idx < (uint32_t) LZX_LHEAD) ml += lhead[idx * NT];
-                    else { lslow = true; lgv = la.sorted[idx * MS_WARP]; }
+                    else {
+                        uint32_t lgv = la.sorted[idx * MS_WARP];
+#if defined(__CUDACC__) && !defined(MSGPU_EMULATE)
+                        asm volatile("" : "+r"(lgv));
+#endif
+                        ml += lgv;
+                    }
                 }
             }
             ml += 2;
@@ -504,7 +512,6 @@ struct LzxLaneC {
                 else if (extra) { if (careful) lzx_check(b, (int) extra); off += msb_peek(b, (int) extra); msb_drop(b, (int) extra); }
                 R2 = R1; R1 = R0; R0 = off;
             }
-            if (lslow) ml += lgv;
             if (DELTA && is_delta && ml == 257) {                    /* lzxd.c:589-611: the longest length announces more */
                 lzx_refill(b);
                 if (careful) lzx_check(b, 3);
