@@ -173,6 +173,14 @@ uint64_t msgpu_launch_count(const msgpu_ctx *ctx);
 /* Bytes of device scratch the context currently holds. */
 size_t msgpu_scratch_bytes(const msgpu_ctx *ctx);
 
+/* Host only (no device needed): how msgpu_decode_batch_* cuts a batch under a scratch budget.  *fmax = frames per launch round
+ * for long units (2 for big batches of short units, up to 64 for batches of few long units - a cabinet's multi-megabyte LZX /
+ * Quantum folders decode in order on one lane, DESIGN.md section 7 "Long units"; the MSGPU_FMAX environment variable overrides),
+ * *frame_slots = record arrays the batch needs in all, *waves = passes over the scratch memory, *rounds = launch rounds of the
+ * longest unit as planned (MSZIP folders of short CK blocks may take more).  Any out pointer may be NULL. */
+int msgpu_plan_batch(const msgpu_unit *units, size_t n, size_t scratch_budget_bytes,
+                     uint32_t *fmax, uint64_t *frame_slots, uint32_t *waves, uint32_t *rounds);
+
 /* Milliseconds spent in the decode kernels of the most recent batch, measured with CUDA
  * events on the launching stream (valid after the stream is synchronised; < 0 if none). */
 float msgpu_last_kernel_ms(msgpu_ctx *ctx);

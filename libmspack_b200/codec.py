@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "msgpu_create", "msgpu_destroy", "msgpu_last_error", "msgpu_decode_batch_device",
     "msgpu_decode_batch_device_units", "msgpu_decode_batch_host", "msgpu_launch_count",
     "msgpu_scratch_bytes", "msgpu_last_kernel_ms", "msgpu_set_stage_timing", "msgpu_stage_ms", "msgpu_version", "msgpu_last_produced",
-    "msgpu_shard_range", "msgpu_decode_batch_host_multi", "msgpu_digest_device", "msgpu_decode_batch_host_digest",
+    "msgpu_shard_range", "msgpu_decode_batch_host_multi", "msgpu_digest_device", "msgpu_decode_batch_host_digest", "msgpu_plan_batch",
 ]
 
 _lib = None
@@ -71,8 +71,23 @@ def load_library() -> ctypes.CDLL:
     lib.msgpu_stage_ms.argtypes = [vp, ctypes.c_int]
     lib.msgpu_version.restype = ctypes.c_char_p
     lib.msgpu_version.argtypes = []
+    lib.msgpu_plan_batch.restype = ctypes.c_int
+    lib.msgpu_plan_batch.argtypes = [vp, sz, sz, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32),
+                                     ctypes.POINTER(ctypes.c_uint32)]
     _lib = lib
     return lib
+
+
+def plan_batch(units: np.ndarray, scratch_budget_bytes: int) -> dict:
+    """msgpu_plan_batch (host only, no GPU needed): how a batch would be cut under a scratch budget."""
+    lib = load_library()
+    units = np.ascontiguousarray(units)
+    fmax, slots, waves, rounds = ctypes.c_uint32(0), ctypes.c_uint64(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+    rc = lib.msgpu_plan_batch(units.ctypes.data, len(units), int(scratch_budget_bytes), ctypes.byref(fmax), ctypes.byref(slots), ctypes.byref(waves),
+                              ctypes.byref(rounds))
+    if rc:
+        raise RuntimeError(f"msgpu_plan_batch failed: {rc}")
+    return dict(fmax=fmax.value, frame_slots=slots.value, waves=waves.value, rounds=rounds.value)
 
 
 class BatchDecoder:

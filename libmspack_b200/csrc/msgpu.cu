@@ -452,13 +452,13 @@ static inline uint32_t frame_slots(const msgpu_unit &u, uint32_t fmax) {
  * (cabextract/test/large-files.test) takes 1 024 launch rounds instead of 32 768, each of which would reload the lane's state
  * and rebuild its Huffman tables.  The rule: the largest power of two that keeps the batch within 131 072 frame slots (17 GB
  * of records) and half the scratch budget; MSGPU_FMAX overrides. */
-static uint32_t pick_fmax(const msgpu_ctx *ctx, const msgpu_unit *units, size_t n, uint32_t maxfr) {
+static uint32_t pick_fmax(size_t scratch_budget, const msgpu_unit *units, size_t n, uint32_t maxfr) {
     if (maxfr <= 2) return 2;
     const char *env = getenv("MSGPU_FMAX");
     if (env) { int v = atoi(env); return v < 2 ? 2u : (v > 4096 ? 4096u : (uint32_t) v); }
     uint64_t s2 = 0;
     for (size_t i = 0; i < n; i++) s2 += frame_slots(units[i], 2);
-    uint64_t target = ctx->scratch_budget / 2 / MS_FRAME_SLOT_BYTES;
+    uint64_t target = scratch_budget / 2 / MS_FRAME_SLOT_BYTES;
     if (target > 131072) target = 131072;
     if (target < s2) target = s2;
     uint32_t fmax = 2;
@@ -849,6 +849,37 @@ static int run_wave(msgpu_ctx *ctx, const msgpu_unit *h_units, size_t lo, size_t
 static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
                              void *d_out, size_t out_bytes, int32_t *d_status, void *stream, const uint8_t *h_in, uint8_t *h_out);
 
+/* a wave = as many units from `lo` on as the scratch budget holds (record arrays per frame slot + per-unit state), at least 1 024;
+ * an MSZIP block chain stays inside one wave (returns lo when the chain at lo does not fit) */
+static size_t wave_end(const msgpu_unit *units, size_t n, size_t lo, uint32_t fmax, size_t scratch_budget) {
+    size_t hi = lo; uint64_t used = 0;
+    while (hi < n) {
+        const uint64_t c = (uint64_t) frame_slots(units[hi], fmax) * MS_FRAME_SLOT_BYTES + MS_UNIT_FIXED_BYTES;
+        if (hi - lo >= 1024 && used + c > scratch_budget) break;
+        used += c; hi++;
+    }
+    while (hi < n && hi > lo && (units[hi].flags & MSGPU_FLAG_CHAIN_NEXT)) hi--;
+    return hi;
+}
+
+/* Host only, no device work: how msgpu_decode_batch_* would cut this batch under a scratch budget - frames per launch round for
+ * its long units, frame slots (record arrays) in all, waves, launch rounds of the longest unit. */
+extern "C" int msgpu_plan_batch(const msgpu_unit *units, size_t n, size_t scratch_budget_bytes, uint32_t *fmax_out, uint64_t *frame_slots_out,
+                                uint32_t *waves_out, uint32_t *rounds_out)
+{
+    if ((n && !units) || !scratch_budget_bytes) return MSGPU_ERR_ARGS;
+    uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
+    const uint32_t fmax = pick_fmax(scratch_budget_bytes, units, n, maxfr);
+    uint64_t slots = 0; uint32_t waves = 0, rounds = n ? 1 : 0;
+    for (size_t i = 0; i < n; i++) { const uint32_t cap = frame_slots(units[i], fmax), r = (frames_of(units[i]) + cap - 1) / cap; slots += cap; if (r > rounds) rounds = r; }
+    for (size_t lo = 0; lo < n; waves++) { const size_t hi = wave_end(units, n, lo, fmax, scratch_budget_bytes); if (hi == lo) return MSGPU_ERR_NOMEMORY; lo = hi; }
+    if (fmax_out) *fmax_out = fmax;
+    if (frame_slots_out) *frame_slots_out = slots;
+    if (waves_out) *waves_out = waves;
+    if (rounds_out) *rounds_out = rounds;
+    return 0;
+}
+
 extern "C" int msgpu_decode_batch_device(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, const void *d_in, size_t in_bytes,
                                          void *d_out, size_t out_bytes, int32_t *d_status, void *stream)
 {
@@ -888,19 +919,12 @@ static int decode_batch_impl(msgpu_ctx *ctx, const msgpu_unit *units, size_t n, 
     }
     /* wave size from the scratch budget */
     uint32_t maxfr = 1; for (size_t i = 0; i < n; i++) { uint32_t fr = frames_of(units[i]); if (fr > maxfr) maxfr = fr; }
-    const uint32_t fmax = pick_fmax(ctx, units, n, maxfr);
+    const uint32_t fmax = pick_fmax(ctx->scratch_budget, units, n, maxfr);
     ctx->ev_used = 0;
     for (int k = 0; k < 3; k++) ctx->stage_evs[k].clear();
     ctx->last_waves = 0; ctx->last_stream = s;
     for (size_t lo = 0; lo < n;) {
-        /* a wave = as many units as the scratch budget holds (record arrays per frame slot + per-unit state), at least 1 024 */
-        size_t hi = lo; uint64_t used = 0;
-        while (hi < n) {
-            const uint64_t c = (uint64_t) frame_slots(units[hi], fmax) * MS_FRAME_SLOT_BYTES + MS_UNIT_FIXED_BYTES;
-            if (hi - lo >= 1024 && used + c > ctx->scratch_budget) break;
-            used += c; hi++;
-        }
-        while (hi < n && hi > lo && (units[hi].flags & MSGPU_FLAG_CHAIN_NEXT)) hi--;       /* a chain stays inside one wave */
+        const size_t hi = wave_end(units, n, lo, fmax, ctx->scratch_budget);
         if (hi == lo) return fail(ctx, MSGPU_ERR_NOMEMORY, "a block chain does not fit the scratch budget");
         int r = run_wave(ctx, units, lo, hi, d_in, d_out, d_status, s, fmax, h_in, h_out);
         if (r) return r;
