@@ -497,7 +497,12 @@ struct QtmLane {
         const bool is_sel = mst == QS_SELECTOR, is_lit = mst == QS_LITERAL, is_len = mst == QS_LENGTH, is_off = mst == QS_OFFSET;
         /* length_base[] / length_extra[] (qtmd.c:76-83) and position_base[] / extra_bits[] (qtmd.c:66-75) in closed form */
         const uint32_t le = s < 6 ? 0 : (s == 26 ? 0 : (s - 2) >> 2);
-        const uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << le) - 2);
+#if defined(MSGPU_EMULATE)
+        const uint32_t lsh = le & 31u;       /* (s is a literal byte in two of the four states: le is then unused but up to 63 - undefined for a C shift, a clamped one on the device) */
+#else
+        const uint32_t lsh = le;
+#endif
+        const uint32_t lb = s < 6 ? s : (s == 26 ? 254 : ((4 + ((s - 2) & 3)) << lsh) - 2);
         const uint32_t pe = s < 2 ? 0 : (s >> 1) - 1;
         const uint32_t pb = s < 2 ? s : (2u + (s & 1)) << (pe & 31u);
         const uint32_t xb = read_many((int) (is_len ? le : (is_off ? pe : 0u)));

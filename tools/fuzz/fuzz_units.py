@@ -34,7 +34,7 @@ t0=time.time(); total=0; bad=0
 cases = [(3, dict(block_mode=4, split=3, unit_bytes=20000), (1,0x401,0x4401,0x6401)), (3, dict(block_mode=4, unit_bytes=70000, window_bits=15), (2,0x402,0x4402,0x6402)),
          (3, dict(block_mode=3, unit_bytes=9999), (1,0x401,0x4401,0x6401)), (3, dict(unit_bytes=65536, reset_interval=1, block_mode=4, slack=4), (1,0x401,0x4401,0x6401)),
          (1, dict(unit_bytes=40000), (1,2,0x4001)), (1, dict(unit_bytes=70000, data="random"), (1,0x4001)), (1, dict(unit_bytes=5000, level=1), (1,0x4001)),
-         (2, dict(unit_bytes=40000, window_bits=10), (1,2,0x4001,0x4002,0x6001)), (2, dict(unit_bytes=20000, window_bits=15, data="binary"), (1,0x4001,0x2001,0x6001)),
+         (2, dict(unit_bytes=40000, window_bits=10), (1,2,0x801,0x802,0x4001,0x4002,0x6001)), (2, dict(unit_bytes=20000, window_bits=15, data="binary"), (1,0x801,0x4001,0x2001,0x6001)),
          (3, dict(delta=1, window_bits=17, ref_bytes=5000, unit_bytes=40000, block_mode=4), (1,))]
 for rnd in range(int(sys.argv[2]) if len(sys.argv)>2 else 6):
     for codec, kw, modes in cases:
